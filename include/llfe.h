@@ -1,0 +1,207 @@
+/*
+ * llfe.h -- C ABI of libllfe.so: the B200 (sm_100a) image hot path of
+ * Kira7dn/Low_Level_Feature_Extraction.
+ *
+ * The reference has no FFI for this path: every arithmetic step is a call from
+ * a Python service method into OpenCV/NumPy.  Each entry point below replaces
+ * one such call site (cited as file:line relative to the reference tree; "pyc"
+ * = app/services/__pycache__/<module>.cpython-312.pyc, line = original source
+ * line recorded in the code object).  INTEGRATION.md shows the ctypes stubs a
+ * maintainer of the reference would add to bind them.
+ *
+ * Conventions
+ *   - plain C types only; no CUDA or torch types in the signatures.
+ *   - every function returns 0 on success or a negative LLFE_E_* code;
+ *     llfe_last_error() returns a thread-local human-readable message.
+ *   - images are uint8, HWC, BGR channel order (the OpenCV convention of the
+ *     reference), C-contiguous; a batch is `n` images of identical h x w stored
+ *     back to back.
+ *   - pointers named d_* are DEVICE pointers, pointers named h_* are HOST
+ *     pointers.  All d_* work is enqueued on the context's stream and is
+ *     asynchronous; *_host entry points copy in, run and copy out, and return
+ *     after the result is in host memory.
+ *   - the caller owns every buffer; the context owns only its workspace arena
+ *     and pinned staging buffers.
+ *   - one context per (process, device); calls on one context are serialised on
+ *     its stream (the reference handles one request at a time per worker).
+ *   - there is NO CPU fallback: if no CUDA device is usable, llfe_create fails.
+ */
+#ifndef LLFE_H
+#define LLFE_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define LLFE_OK 0
+#define LLFE_E_INVALID (-1)  /* bad argument */
+#define LLFE_E_CUDA (-2)     /* CUDA runtime error (message has the detail) */
+#define LLFE_E_NOMEM (-3)    /* allocation failed */
+#define LLFE_E_UNSUPPORTED (-4)
+#define LLFE_E_NODEVICE (-5)
+
+typedef struct llfe_ctx llfe_ctx;
+
+/* ---- library / context ------------------------------------------------ */
+int llfe_version(void);
+const char* llfe_last_error(void);
+int llfe_device_count(void);
+int llfe_create(int device, llfe_ctx** out);
+int llfe_destroy(llfe_ctx* ctx);
+/* Use an existing CUDA stream (a cudaStream_t passed as void*), e.g. torch's
+ * current stream; NULL restores the context's own stream. */
+int llfe_set_stream(llfe_ctx* ctx, void* cuda_stream);
+int llfe_sync(llfe_ctx* ctx);
+/* Number of kernels this context has launched so far (for accounting). */
+uint64_t llfe_launch_count(llfe_ctx* ctx);
+int llfe_sm_count(llfe_ctx* ctx);
+
+/* ---- memory helpers (so a C / ctypes host needs no CUDA runtime) -------- */
+int llfe_malloc(llfe_ctx* ctx, size_t bytes, void** d_out);
+int llfe_free(llfe_ctx* ctx, void* d_ptr);
+int llfe_malloc_host(llfe_ctx* ctx, size_t bytes, void** h_out); /* pinned */
+int llfe_free_host(llfe_ctx* ctx, void* h_ptr);
+int llfe_memcpy_h2d(llfe_ctx* ctx, void* d_dst, const void* h_src, size_t bytes); /* async on stream */
+int llfe_memcpy_d2h(llfe_ctx* ctx, void* h_dst, const void* d_src, size_t bytes); /* async on stream */
+int llfe_memset(llfe_ctx* ctx, void* d_dst, int value, size_t bytes);
+
+/* ---- per-op entry points (device pointers, batched) ---------------------- */
+
+/* cv2.cvtColor(img, COLOR_BGR2GRAY): shape_analyzer pyc L18, shadow_analyzer
+ * pyc L8, app/services/analyze/text_extractor.py:27, font_detector.py:28.
+ * Y = (3735 B + 19235 G + 9798 R + 16384) >> 15. */
+int llfe_bgr2gray(llfe_ctx* ctx, const uint8_t* d_bgr, int n, int h, int w, uint8_t* d_gray);
+
+/* cv2.cvtColor(img, COLOR_BGR2RGB): app/services/analyze/color_extractor.py:151. */
+int llfe_bgr2rgb(llfe_ctx* ctx, const uint8_t* d_bgr, int n, int h, int w, uint8_t* d_rgb);
+
+/* cv2.GaussianBlur(src, (5,5), 0) on u8 with c = 1 or 3 channels:
+ * shape_analyzer pyc L21, shadow_analyzer pyc L9, image_transformer pyc L103. */
+int llfe_gaussian_blur5(llfe_ctx* ctx, const uint8_t* d_src, int n, int h, int w, int c, uint8_t* d_dst);
+
+/* gray + blur fused: ShadowAnalyzer.preprocess_image, shadow_analyzer pyc L5-10. */
+int llfe_gray_blur5(llfe_ctx* ctx, const uint8_t* d_bgr, int n, int h, int w, uint8_t* d_blurred);
+
+/* cv2.Canny(gray, low, high) (aperture 3, L1 norm): shape_analyzer pyc L24. */
+int llfe_canny(llfe_ctx* ctx, const uint8_t* d_gray, int n, int h, int w, int low, int high, uint8_t* d_edges);
+
+/* cv2.dilate(src, ones(3,3), iterations=1): shape_analyzer pyc L27-28. */
+int llfe_dilate3(llfe_ctx* ctx, const uint8_t* d_src, int n, int h, int w, uint8_t* d_dst);
+
+/* ShapeAnalyzer.preprocess_image (shape_analyzer pyc L6-30), fused:
+ * gray -> blur5 -> Canny(low, high) -> dilate3.  d_mask is (n,h,w) u8 in {0,255}. */
+int llfe_shape_mask(llfe_ctx* ctx, const uint8_t* d_bgr, int n, int h, int w, int low, int high, uint8_t* d_mask);
+
+/* cv2.adaptiveThreshold(src, 255, ADAPTIVE_THRESH_GAUSSIAN_C, THRESH_BINARY_INV,
+ * 11, C): shadow_analyzer pyc L17-18, font_detector.py:31-35.  If d_sum_count is
+ * not NULL it receives, per image, {sum of src where mask==255, count of
+ * mask==255} as two uint64 (the masked mean of shadow_analyzer pyc L21-24). */
+int llfe_adaptive_threshold(llfe_ctx* ctx, const uint8_t* d_gray, int n, int h, int w, int C, uint8_t* d_mask,
+                            uint64_t* d_sum_count);
+
+/* ShadowAnalyzer.analyze_shadow_level up to the scalar (shadow_analyzer pyc
+ * L12-24), fused: gray -> blur5 -> adaptive(11, 2) -> masked sum/count.
+ * d_blurred may be NULL when the caller does not need the blurred image. */
+int llfe_shadow_mask(llfe_ctx* ctx, const uint8_t* d_bgr, int n, int h, int w, uint8_t* d_mask, uint8_t* d_blurred,
+                     uint64_t* d_sum_count);
+
+/* FontDetector.preprocess_image (font_detector.py:16-37): gray -> adaptive(11,2). */
+int llfe_font_mask(llfe_ctx* ctx, const uint8_t* d_bgr, int n, int h, int w, uint8_t* d_mask);
+
+/* cv2.threshold(gray, 0, 255, THRESH_BINARY + THRESH_OTSU): text_extractor.py:40.
+ * d_thresh receives the Otsu level per image (int32).  If invert_if_light != 0 the
+ * mask is inverted when mean(mask) > 127 (text_extractor.py:43-44). */
+int llfe_otsu(llfe_ctx* ctx, const uint8_t* d_gray, int n, int h, int w, int invert_if_light, uint8_t* d_mask,
+              int32_t* d_thresh);
+
+/* TextExtractor.preprocess_image for h >= 30 and w >= 100 (text_extractor.py:15-46):
+ * gray -> Otsu -> invert if mostly white. */
+int llfe_text_mask(llfe_ctx* ctx, const uint8_t* d_bgr, int n, int h, int w, uint8_t* d_mask, int32_t* d_thresh);
+
+/* cv2.resize(src, (dw, dh), interpolation=INTER_AREA), down-scaling, c = 1 or 3:
+ * app/services/analyze/utils.py:127, image_processor.py:112, image_transformer
+ * pyc L53, L170-173. */
+int llfe_resize_area(llfe_ctx* ctx, const uint8_t* d_src, int n, int sh, int sw, int c, uint8_t* d_dst, int dh,
+                     int dw);
+
+/* cv2.convertScaleAbs(x, alpha=a1, beta=0) followed by (alpha=a2, beta=0), the
+ * pair of calls of ImageTransformer.adjust_brightness_contrast (image_transformer
+ * pyc L139-142) fused into one pass.  Pass a2 = 1.0f with single = 1 for one call. */
+int llfe_convert_scale_abs(llfe_ctx* ctx, const uint8_t* d_src, size_t count, float a1, float a2, int single,
+                           uint8_t* d_dst);
+
+/* ---- palette (ColorExtractor) -------------------------------------------- */
+
+/* Noise + unique colours: color_extractor.py:151 (BGR2RGB), :224-225 (noise add +
+ * clip) and :177 (np.unique(axis=0)).  d_noise is the reference's int8 noise
+ * tensor (n,h,w,3) in RGB order, or NULL to generate noise of the same
+ * distribution on the device from `seed` (throughput mode; not bit-equal to
+ * NumPy's MT19937 stream).  d_keys receives, per image, the sorted unique colours
+ * as R<<16|G<<8|B (== np.unique row order) at d_keys + i*max_unique; d_count[i]
+ * receives the number of unique colours (values above max_unique mean truncated).
+ * If d_hist is not NULL it receives the pixel count of each unique colour
+ * (uint32, same layout as d_keys) -- the weights of the per-pixel k-means mode. */
+int llfe_unique_colors(llfe_ctx* ctx, const uint8_t* d_bgr, int n, int h, int w, const int8_t* d_noise,
+                       uint64_t seed, uint32_t* d_keys, uint32_t* d_hist, int32_t* d_count, int max_unique);
+
+/* cv2.kmeans(float32(unique), K, None, (EPS+MAX_ITER, max_iter, eps), attempts,
+ * KMEANS_PP_CENTERS) on each image's unique-colour list: color_extractor.py:189-197.
+ * rng_state[i] is the cv::RNG state the reference would start image i with
+ * (cv2.setRNGSeed(s) => s, 0 => 0xffffffff).  Outputs per image: centers (k x 3
+ * float32, RGB), labels (int32 per unique colour), compactness (double), and
+ * k_used = min(k, n_unique).  Images with fewer than 2 unique colours follow
+ * color_extractor.py:185-186 (centers = the colours, labels = 0). */
+int llfe_kmeans_unique(llfe_ctx* ctx, const uint32_t* d_keys, const int32_t* d_count, int n, int max_unique, int k,
+                       int attempts, int max_iter, double eps, const uint64_t* d_rng_state, float* d_centers,
+                       int32_t* d_labels, double* d_compactness, int32_t* d_k_used);
+
+/* Lloyd iterations from given initial centres (the "seeded mode" of SURVEY.md
+ * A.8) over weighted colours (d_weights NULL = all ones).  exact_sums = 0:
+ * cv2's float32 centre rule (sum * (1.f/count)); exact_sums = 1: the pinned
+ * per-pixel rule c = float(double(sum)/double(count)).  d_iters gets the
+ * iteration count per problem. */
+int llfe_kmeans_lloyd(llfe_ctx* ctx, const uint32_t* d_keys, const uint32_t* d_weights, const int32_t* d_count, int n,
+                      int max_unique, int k, int max_iter, double eps, int exact_sums, const float* d_init_centers,
+                      float* d_centers, int32_t* d_labels, int32_t* d_iters, uint64_t* d_sums_counts);
+
+/* One per-pixel k-means step for a row shard of ONE image (multi-GPU mode,
+ * SURVEY.md 8(e)): assign every pixel of d_bgr (rows x w) to the nearest of k
+ * centres (float32 RGB) and ADD the exact per-cluster sums into
+ * d_sums_counts[k][4] = {sum R, sum G, sum B, count} (uint64).  The caller
+ * zeroes the accumulator, all-reduces it across ranks (ncclSum) and calls
+ * llfe_kmeans_update. */
+int llfe_kmeans_pixels_step(llfe_ctx* ctx, const uint8_t* d_bgr, size_t n_pixels, int k, const float* d_centers,
+                            uint64_t* d_sums_counts, uint8_t* d_labels_or_null);
+
+/* Centre update + convergence test from (all-reduced) sums: c =
+ * float(double(sum)/double(count)); d_state[0] = iteration counter (in/out),
+ * d_state[1] = converged flag (out), d_state[2] = number of empty clusters (out).
+ * d_shift receives max_k |c - old|^2 (double). */
+int llfe_kmeans_update(llfe_ctx* ctx, int k, const uint64_t* d_sums_counts, float* d_centers, int max_iter,
+                       double eps, int32_t* d_state, double* d_shift);
+
+/* ---- fused service pipelines ---------------------------------------------- */
+
+/* colours + shapes + shadows from one read of the image (BASELINE config 4):
+ * shape mask (llfe_shape_mask), shadow mask + sum/count (llfe_shadow_mask) and
+ * the unique-colour list (llfe_unique_colors) of every image. Any output group
+ * may be disabled by passing NULL for its mask / keys pointer. */
+int llfe_pipeline(llfe_ctx* ctx, const uint8_t* d_bgr, int n, int h, int w, int low, int high, uint8_t* d_shape_mask,
+                  uint8_t* d_shadow_mask, uint64_t* d_shadow_sum_count, const int8_t* d_noise, uint64_t seed,
+                  uint32_t* d_keys, int32_t* d_count, int max_unique);
+
+/* ---- host-buffer convenience entry points (single image, synchronous) ------ */
+int llfe_shape_mask_host(llfe_ctx* ctx, const uint8_t* h_bgr, int h, int w, int low, int high, uint8_t* h_mask);
+int llfe_shadow_mask_host(llfe_ctx* ctx, const uint8_t* h_bgr, int h, int w, uint8_t* h_mask, uint8_t* h_blurred,
+                          uint64_t* h_sum_count);
+int llfe_text_mask_host(llfe_ctx* ctx, const uint8_t* h_bgr, int h, int w, uint8_t* h_mask, int32_t* h_thresh);
+int llfe_font_mask_host(llfe_ctx* ctx, const uint8_t* h_bgr, int h, int w, uint8_t* h_mask);
+int llfe_resize_area_host(llfe_ctx* ctx, const uint8_t* h_src, int sh, int sw, int c, uint8_t* h_dst, int dh, int dw);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* LLFE_H */

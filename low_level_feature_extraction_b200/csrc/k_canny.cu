@@ -1,0 +1,397 @@
+// Canny edge chain (cv2.Canny(img, low, high), aperture 3, L1 norm) + 3x3 dilate.
+//
+//   front      : Sobel (BORDER_REPLICATE) -> |dx|+|dy| -> non-max suppression ->
+//                two BIT PLANES per image: weak (kept, mag > low) and strong
+//                (kept, mag > high).  One bit per pixel: 1/32 of a u8 map.
+//   hysteresis : edges = fixed point of  E <- weak & dilate8(E),  E0 = strong,
+//                done on the bit planes with word-parallel fills; strips of rows
+//                converge locally in shared memory, cross-strip propagation is
+//                finished by one CTA per image (no host round trips, no grid sync).
+//   expand     : bit plane -> u8 {0,255} mask, optionally 3x3-dilated on the way.
+#include "llfe_common.cuh"
+#include "llfe_device.cuh"
+
+namespace {
+
+// ------------------------------------------------------------------ front ---
+constexpr int FTW = 64;  // tile width  (2 plane words)
+constexpr int FTH = 32;  // tile height
+
+__global__ void __launch_bounds__(256) k_canny_front(const uint8_t* __restrict__ gray, int h, int w, int low, int high,
+                                                     uint32_t* __restrict__ weak, uint32_t* __restrict__ strong) {
+    __shared__ uint8_t g[FTH + 4][FTW + 4 + 4];
+    __shared__ uint16_t mg[FTH + 2][FTW + 2 + 2];
+    __shared__ short2 dxy[FTH][FTW];
+    const int img = blockIdx.z;
+    const uint8_t* s = gray + (size_t)img * h * w;
+    const int wpr = plane_wpr(w);
+    uint32_t* pw = weak + (size_t)img * h * wpr;
+    uint32_t* ps = strong + (size_t)img * h * wpr;
+    const int x0 = blockIdx.x * FTW, y0 = blockIdx.y * FTH;
+    const int tid = threadIdx.x;
+
+    // stage the source with replicated borders: rows y0-2.., cols x0-2..
+    for (int i = tid; i < (FTH + 4) * (FTW + 4); i += 256) {
+        int ry = i / (FTW + 4), rx = i - ry * (FTW + 4);
+        int y = clampi(y0 - 2 + ry, 0, h - 1), x = clampi(x0 - 2 + rx, 0, w - 1);
+        g[ry][rx] = s[(size_t)y * w + x];
+    }
+    __syncthreads();
+    // gradient magnitude on the tile + 1 halo; zero outside the image
+    for (int i = tid; i < (FTH + 2) * (FTW + 2); i += 256) {
+        int ry = i / (FTW + 2), rx = i - ry * (FTW + 2);
+        int y = y0 - 1 + ry, x = x0 - 1 + rx;
+        int m = 0;
+        if (y >= 0 && y < h && x >= 0 && x < w) {
+            // g index of (y, x) is [ry + 1][rx + 1]
+            const int a = ry + 1, b = rx + 1;
+            int tl = g[a - 1][b - 1], tc = g[a - 1][b], tr = g[a - 1][b + 1];
+            int ml = g[a][b - 1], mr = g[a][b + 1];
+            int bl = g[a + 1][b - 1], bc = g[a + 1][b], br = g[a + 1][b + 1];
+            int dx = (tr + 2 * mr + br) - (tl + 2 * ml + bl);
+            int dy = (bl + 2 * bc + br) - (tl + 2 * tc + tr);
+            m = abs(dx) + abs(dy);
+            if (ry >= 1 && ry <= FTH && rx >= 1 && rx <= FTW) dxy[ry - 1][rx - 1] = make_short2((short)dx, (short)dy);
+        }
+        mg[ry][rx] = (uint16_t)m;
+    }
+    __syncthreads();
+    // non-max suppression; each warp covers 32 consecutive pixels of a row -> one plane word
+    const int lane = tid & 31, warp = tid >> 5;
+    for (int job = warp; job < FTH * (FTW / 32); job += 8) {
+        int ry = job / (FTW / 32), wx = job - ry * (FTW / 32);
+        int rx = wx * 32 + lane;
+        int y = y0 + ry, x = x0 + rx;
+        bool keep = false, is_strong = false;
+        if (y < h && x < w) {
+            int m = mg[ry + 1][rx + 1];
+            if (m > low) {
+                short2 d = dxy[ry][rx];
+                int dx = d.x, dy = d.y;
+                int ax = abs(dx), ay = abs(dy) << 15;
+                int tg22x = ax * 13573;
+                int tg67x = tg22x + (ax << 16);
+                if (ay < tg22x) {
+                    keep = (m > mg[ry + 1][rx]) && (m >= mg[ry + 1][rx + 2]);
+                } else if (ay > tg67x) {
+                    keep = (m > mg[ry][rx + 1]) && (m >= mg[ry + 2][rx + 1]);
+                } else {
+                    int sgn = ((dx ^ dy) < 0) ? -1 : 1;
+                    keep = (m > mg[ry][rx + 1 - sgn]) && (m > mg[ry + 2][rx + 1 + sgn]);
+                }
+                is_strong = keep && (m > high);
+            }
+        }
+        uint32_t bw = __ballot_sync(0xffffffffu, keep);
+        uint32_t bs = __ballot_sync(0xffffffffu, is_strong);
+        if (lane == 0 && y < h && (x0 + wx * 32) < w) {
+            size_t o = (size_t)y * wpr + ((x0 >> 5) + wx);
+            pw[o] = bw;
+            ps[o] = bs;
+        }
+    }
+}
+
+// ------------------------------------------------------------- hysteresis ---
+constexpr int HROWS = 32;      // rows per strip
+constexpr int HTHREADS = 256;  // threads per CTA
+
+// fill `e` along runs of `w` inside one 32-bit word (both directions), e subset of w
+__device__ __forceinline__ uint32_t fill_word(uint32_t e, uint32_t w) {
+    // Kogge-Stone occluded fill towards higher bits, then lower bits
+    uint32_t g1 = e, p = w;
+    g1 |= p & (g1 << 1);
+    p &= p << 1;
+    g1 |= p & (g1 << 2);
+    p &= p << 2;
+    g1 |= p & (g1 << 4);
+    p &= p << 4;
+    g1 |= p & (g1 << 8);
+    p &= p << 8;
+    g1 |= p & (g1 << 16);
+    uint32_t g2 = e;
+    p = w;
+    g2 |= p & (g2 >> 1);
+    p &= p >> 1;
+    g2 |= p & (g2 >> 2);
+    p &= p >> 2;
+    g2 |= p & (g2 >> 4);
+    p &= p >> 4;
+    g2 |= p & (g2 >> 8);
+    p &= p >> 8;
+    g2 |= p & (g2 >> 16);
+    return g1 | g2;
+}
+
+// Converge one strip held in shared memory.
+//   sw : weak rows   [rows][wpr]
+//   se : edge rows   [rows + 2][wpr]  (row 0 = halo above, row rows+1 = halo below)
+// Each thread owns word-columns c = tid, tid + T, ... and sweeps them down then
+// up, so a whole column propagates per iteration; words propagate sideways
+// through the neighbours' top/bottom bits.  Returns true if anything changed.
+__device__ bool converge_strip(uint32_t* sw, uint32_t* se, int rows, int wpr, int* s_flag) {
+    bool any = false;
+    for (;;) {
+        bool changed = false;
+        for (int c = threadIdx.x; c < wpr; c += blockDim.x) {
+#pragma unroll 1
+            for (int pass = 0; pass < 2; ++pass) {
+                for (int k = 0; k < rows; ++k) {
+                    int r = pass == 0 ? k : rows - 1 - k;
+                    uint32_t wv = sw[r * wpr + c];
+                    uint32_t e = se[(r + 1) * wpr + c];
+                    if ((wv & ~e) == 0) continue;
+                    const uint32_t* up = se + r * wpr;
+                    const uint32_t* mid = se + (r + 1) * wpr;
+                    const uint32_t* dn = se + (r + 2) * wpr;
+                    uint32_t v = up[c] | mid[c] | dn[c];
+                    uint32_t sp = v | (v << 1) | (v >> 1);
+                    if (c > 0) sp |= (up[c - 1] | mid[c - 1] | dn[c - 1]) >> 31;
+                    if (c + 1 < wpr) sp |= (up[c + 1] | mid[c + 1] | dn[c + 1]) << 31;
+                    uint32_t ne = e | (wv & sp);
+                    if (ne != e) {
+                        ne = fill_word(ne, wv);
+                        se[(r + 1) * wpr + c] = ne;
+                        changed = true;
+                    }
+                }
+            }
+        }
+        int r = __syncthreads_or(changed);
+        if (!r) break;
+        any = true;
+    }
+    (void)s_flag;
+    return any;
+}
+
+// Load a strip (weak rows, edge rows + halos) into shared memory.
+__device__ void load_strip(const uint32_t* __restrict__ weak, const uint32_t* edges, int h, int wpr, int r0, int rows,
+                           uint32_t* sw, uint32_t* se) {
+    for (int i = threadIdx.x; i < rows * wpr; i += blockDim.x) sw[i] = weak[(size_t)r0 * wpr + i];
+    for (int i = threadIdx.x; i < (rows + 2) * wpr; i += blockDim.x) {
+        int rr = r0 - 1 + i / wpr;
+        uint32_t v = 0;
+        if (rr >= 0 && rr < h) v = __ldcg(edges + (size_t)rr * wpr + (i % wpr));
+        se[i] = v;
+    }
+}
+
+// Phase 1: every strip of every image in parallel.  `edges` enters holding the
+// strong plane and is updated in place.  flags[img][strip] is set to 1 when a
+// neighbouring strip must be revisited by phase 2.
+__global__ void __launch_bounds__(HTHREADS) k_hyst_strips(const uint32_t* __restrict__ weak, uint32_t* edges, int h,
+                                                          int wpr, int nstrips, uint32_t* flags) {
+    extern __shared__ uint32_t sm[];
+    const int img = blockIdx.y, strip = blockIdx.x;
+    const size_t plane = (size_t)h * wpr;
+    const uint32_t* pw = weak + img * plane;
+    uint32_t* pe = edges + img * plane;
+    const int r0 = strip * HROWS, rows = min(HROWS, h - r0);
+    uint32_t* sw = sm;
+    uint32_t* se = sm + HROWS * wpr;
+    __shared__ int s_flag;
+    load_strip(pw, pe, h, wpr, r0, rows, sw, se);
+    __syncthreads();
+    bool any = converge_strip(sw, se, rows, wpr, &s_flag);
+    if (!any) return;
+    // write back and tell the neighbours whose halo we may have changed
+    bool top = false, bot = false;
+    for (int i = threadIdx.x; i < rows * wpr; i += blockDim.x) {
+        uint32_t v = se[wpr + i];
+        size_t o = (size_t)r0 * wpr + i;
+        uint32_t old = pe[o];
+        if (v != old) {
+            pe[o] = v;
+            if (i < wpr) top = true;
+            if (i >= (rows - 1) * wpr) bot = true;
+        }
+    }
+    top = __syncthreads_or(top);
+    bot = __syncthreads_or(bot);
+    if (threadIdx.x == 0) {
+        uint32_t* f = flags + (size_t)img * nstrips;
+        if (top && strip > 0) f[strip - 1] = 1;
+        if (bot && strip + 1 < nstrips) f[strip + 1] = 1;
+    }
+}
+
+// Phase 2: one CTA per image finishes the cross-strip propagation: visit flagged
+// strips (down sweep, then up sweep) until no flag is left.
+__global__ void __launch_bounds__(HTHREADS) k_hyst_finish(const uint32_t* __restrict__ weak, uint32_t* edges, int h,
+                                                          int wpr, int nstrips, uint32_t* flags) {
+    extern __shared__ uint32_t sm[];
+    const int img = blockIdx.x;
+    const size_t plane = (size_t)h * wpr;
+    const uint32_t* pw = weak + img * plane;
+    uint32_t* pe = edges + img * plane;
+    uint32_t* f = flags + (size_t)img * nstrips;
+    uint32_t* sw = sm;
+    uint32_t* se = sm + HROWS * wpr;
+    __shared__ int s_flag;
+    for (;;) {
+        bool worked = false;
+        for (int pass = 0; pass < 2; ++pass) {
+            for (int k = 0; k < nstrips; ++k) {
+                int strip = pass == 0 ? k : nstrips - 1 - k;
+                __syncthreads();
+                if (f[strip] == 0) continue;  // uniform: read after the barrier by all threads
+                __syncthreads();
+                if (threadIdx.x == 0) f[strip] = 0;
+                worked = true;
+                const int r0 = strip * HROWS, rows = min(HROWS, h - r0);
+                load_strip(pw, pe, h, wpr, r0, rows, sw, se);
+                __syncthreads();
+                bool any = converge_strip(sw, se, rows, wpr, &s_flag);
+                if (!any) continue;
+                bool top = false, bot = false;
+                for (int i = threadIdx.x; i < rows * wpr; i += blockDim.x) {
+                    uint32_t v = se[wpr + i];
+                    size_t o = (size_t)r0 * wpr + i;
+                    if (v != pe[o]) {
+                        pe[o] = v;
+                        if (i < wpr) top = true;
+                        if (i >= (rows - 1) * wpr) bot = true;
+                    }
+                }
+                top = __syncthreads_or(top);
+                bot = __syncthreads_or(bot);
+                if (threadIdx.x == 0) {
+                    if (top && strip > 0) f[strip - 1] = 1;
+                    if (bot && strip + 1 < nstrips) f[strip + 1] = 1;
+                }
+                __threadfence_block();
+            }
+        }
+        if (!worked) break;
+    }
+}
+
+// ----------------------------------------------------------------- expand ---
+// bit plane -> u8 mask (0 / 255); DILATE: 3x3 max (out-of-image neighbours ignored).
+// One thread per 16 output pixels (half a plane word).
+template <bool DILATE>
+__global__ void __launch_bounds__(256) k_plane_to_mask(const uint32_t* __restrict__ plane, int h, int w, int wpr,
+                                                       uint8_t* __restrict__ mask, int aligned) {
+    const int img = blockIdx.z;
+    const uint32_t* p = plane + (size_t)img * h * wpr;
+    uint8_t* m = mask + (size_t)img * h * w;
+    const int halves = 2 * wpr;
+    int idx = blockIdx.x * blockDim.x + threadIdx.x;
+    int y = blockIdx.y;
+    if (idx >= halves) return;
+    int c = idx >> 1, half = idx & 1;
+    uint32_t v;
+    if (DILATE) {
+        uint32_t ctr = 0, lft = 0, rgt = 0;
+#pragma unroll
+        for (int dy = -1; dy <= 1; ++dy) {
+            int yy = y + dy;
+            if (yy < 0 || yy >= h) continue;
+            const uint32_t* row = p + (size_t)yy * wpr;
+            ctr |= row[c];
+            if (c > 0) lft |= row[c - 1];
+            if (c + 1 < wpr) rgt |= row[c + 1];
+        }
+        v = ctr | (ctr << 1) | (ctr >> 1) | (lft >> 31) | (rgt << 31);
+    } else {
+        v = p[(size_t)y * wpr + c];
+    }
+    uint32_t bits = (v >> (16 * half)) & 0xffffu;
+    int x = c * 32 + half * 16;
+    if (x >= w) return;
+    // 4 bits -> 4 bytes of 0x00 / 0xff
+    uint32_t o[4];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+        uint32_t nib = (bits >> (4 * k)) & 0xfu;
+        uint32_t spread = (nib * 0x00204081u) & 0x01010101u;  // bit i -> byte i
+        o[k] = spread * 255u;
+    }
+    uint8_t* dst = m + (size_t)y * w + x;
+    if (aligned && x + 16 <= w) {
+        *reinterpret_cast<uint4*>(dst) = make_uint4(o[0], o[1], o[2], o[3]);
+    } else {
+        for (int k = 0; k < 16 && x + k < w; ++k) dst[k] = (uint8_t)(o[k >> 2] >> (8 * (k & 3)));
+    }
+}
+
+// generic 3x3 max on u8 (standalone cv2.dilate with a 3x3 ones kernel)
+__global__ void __launch_bounds__(256) k_dilate3_u8(const uint8_t* __restrict__ src, int h, int w,
+                                                    uint8_t* __restrict__ dst) {
+    const int img = blockIdx.z;
+    const uint8_t* s = src + (size_t)img * h * w;
+    uint8_t* d = dst + (size_t)img * h * w;
+    int x = blockIdx.x * blockDim.x + threadIdx.x, y = blockIdx.y;
+    if (x >= w) return;
+    int m = 0;
+    for (int dy = -1; dy <= 1; ++dy) {
+        int yy = y + dy;
+        if (yy < 0 || yy >= h) continue;
+        for (int dx = -1; dx <= 1; ++dx) {
+            int xx = x + dx;
+            if (xx < 0 || xx >= w) continue;
+            m = max(m, (int)s[(size_t)yy * w + xx]);
+        }
+    }
+    d[(size_t)y * w + x] = (uint8_t)m;
+}
+
+}  // namespace
+
+int launch_canny_front(llfe_ctx* ctx, const uint8_t* gray, int n, int h, int w, int low, int high, uint32_t* weak,
+                       uint32_t* strong) {
+    if (n == 0 || h == 0 || w == 0) return LLFE_OK;
+    dim3 grid(ceil_div(w, FTW), ceil_div(h, FTH), n);
+    k_canny_front<<<grid, 256, 0, ctx->stream>>>(gray, h, w, low, high, weak, strong);
+    LLFE_LAUNCHED(ctx);
+    return LLFE_OK;
+}
+
+size_t hysteresis_flag_words(int n, int h) { return (size_t)n * ceil_div(h, HROWS); }
+
+// `edges` holds the strong plane on entry and the final edge plane on exit.
+int launch_hysteresis(llfe_ctx* ctx, const uint32_t* weak, uint32_t* edges, int n, int h, int w, uint32_t* flags) {
+    if (n == 0 || h == 0 || w == 0) return LLFE_OK;
+    const int wpr = plane_wpr(w);
+    const int nstrips = ceil_div(h, HROWS);
+    size_t smem = (size_t)(2 * HROWS + 2) * wpr * sizeof(uint32_t);
+    if (smem > ctx->smem_optin) {
+        llfe_set_error("hysteresis: image width %d needs %zu B of shared memory per strip (limit %zu)", w, smem,
+                       ctx->smem_optin);
+        return LLFE_E_UNSUPPORTED;
+    }
+    static bool attr_set = false;
+    if (!attr_set) {
+        LLFE_CUDA(cudaFuncSetAttribute(k_hyst_strips, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ctx->smem_optin));
+        LLFE_CUDA(cudaFuncSetAttribute(k_hyst_finish, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ctx->smem_optin));
+        attr_set = true;
+    }
+    LLFE_CUDA(cudaMemsetAsync(flags, 0, hysteresis_flag_words(n, h) * sizeof(uint32_t), ctx->stream));
+    k_hyst_strips<<<dim3(nstrips, n), HTHREADS, smem, ctx->stream>>>(weak, edges, h, wpr, nstrips, flags);
+    LLFE_LAUNCHED(ctx);
+    k_hyst_finish<<<n, HTHREADS, smem, ctx->stream>>>(weak, edges, h, wpr, nstrips, flags);
+    LLFE_LAUNCHED(ctx);
+    return LLFE_OK;
+}
+
+int launch_plane_to_mask(llfe_ctx* ctx, const uint32_t* plane, int n, int h, int w, int dilate, uint8_t* mask) {
+    if (n == 0 || h == 0 || w == 0) return LLFE_OK;
+    const int wpr = plane_wpr(w);
+    int aligned = (w % 16 == 0) && ((uintptr_t)mask % 16 == 0);
+    dim3 grid(ceil_div(2 * wpr, 256), h, n);
+    if (dilate)
+        k_plane_to_mask<true><<<grid, 256, 0, ctx->stream>>>(plane, h, w, wpr, mask, aligned);
+    else
+        k_plane_to_mask<false><<<grid, 256, 0, ctx->stream>>>(plane, h, w, wpr, mask, aligned);
+    LLFE_LAUNCHED(ctx);
+    return LLFE_OK;
+}
+
+int launch_dilate3_u8(llfe_ctx* ctx, const uint8_t* src, int n, int h, int w, uint8_t* dst) {
+    if (n == 0 || h == 0 || w == 0) return LLFE_OK;
+    dim3 grid(ceil_div(w, 256), h, n);
+    k_dilate3_u8<<<grid, 256, 0, ctx->stream>>>(src, h, w, dst);
+    LLFE_LAUNCHED(ctx);
+    return LLFE_OK;
+}

@@ -1,0 +1,211 @@
+// cv2.resize(..., interpolation=INTER_AREA) for down-scaling u8 images (1 or 3
+// channels), all three OpenCV code paths:
+//   * both ratios integer and == 2 : (sum of 2x2 + 2) >> 2
+//   * both ratios integer          : sat_u8(rint(float(sum) * (1.f / area)))
+//   * otherwise                    : per-axis (index, float32 weight) tables; the
+//     horizontal pass accumulates  buf = f32(buf + f32(S * alpha))  in table order
+//     (separate multiply and add), the vertical pass  sum = beta * buf  for the
+//     first entry and  sum = f32(sum + f32(beta * buf))  afterwards.
+// The tables are built on the host in float64 exactly as OpenCV builds them and
+// cached per (source size, destination size) on the context.
+#include <math.h>
+
+#include <vector>
+
+#include "llfe_common.cuh"
+#include "llfe_device.cuh"
+
+struct AreaTab {
+    int ssize, dsize;
+    int n_entries;
+    int max_per_dst;
+    int* d_ofs;  // dsize + 1 offsets into the entry arrays
+    int* d_idx;
+    float* d_w;
+    AreaTab* next;
+};
+
+namespace {
+
+void build_tab(int ssize, int dsize, double scale, std::vector<int>& ofs, std::vector<int>& idx, std::vector<float>& wt) {
+    ofs.assign(dsize + 1, 0);
+    for (int d = 0; d < dsize; ++d) {
+        ofs[d] = (int)idx.size();
+        double fsx1 = d * scale, fsx2 = fsx1 + scale;
+        double cell = fmin(scale, ssize - fsx1);
+        int sx1 = (int)ceil(fsx1), sx2 = (int)floor(fsx2);
+        sx2 = sx2 < ssize - 1 ? sx2 : ssize - 1;
+        sx1 = sx1 < sx2 ? sx1 : sx2;
+        if (sx1 - fsx1 > 1e-3) {
+            idx.push_back(sx1 - 1);
+            wt.push_back((float)((sx1 - fsx1) / cell));
+        }
+        for (int sx = sx1; sx < sx2; ++sx) {
+            idx.push_back(sx);
+            wt.push_back((float)(1.0 / cell));
+        }
+        if (fsx2 - sx2 > 1e-3) {
+            idx.push_back(sx2);
+            wt.push_back((float)(fmin(fmin(fsx2 - sx2, 1.0), cell) / cell));
+        }
+    }
+    ofs[dsize] = (int)idx.size();
+}
+
+int get_tab(llfe_ctx* ctx, int ssize, int dsize, AreaTab** out) {
+    for (AreaTab* t = ctx->area_tabs; t; t = t->next)
+        if (t->ssize == ssize && t->dsize == dsize) {
+            *out = t;
+            return LLFE_OK;
+        }
+    std::vector<int> ofs, idx;
+    std::vector<float> wt;
+    const double scale = 1.0 / ((double)dsize / (double)ssize);
+    build_tab(ssize, dsize, scale, ofs, idx, wt);
+    AreaTab* t = new AreaTab();
+    t->ssize = ssize;
+    t->dsize = dsize;
+    t->n_entries = (int)idx.size();
+    t->max_per_dst = 0;
+    for (int d = 0; d < dsize; ++d) t->max_per_dst = ofs[d + 1] - ofs[d] > t->max_per_dst ? ofs[d + 1] - ofs[d] : t->max_per_dst;
+    t->d_ofs = nullptr;
+    t->d_idx = nullptr;
+    t->d_w = nullptr;
+    t->next = nullptr;
+    cudaError_t e;
+    if ((e = cudaMalloc(&t->d_ofs, ofs.size() * sizeof(int))) != cudaSuccess ||
+        (e = cudaMalloc(&t->d_idx, (idx.size() + 1) * sizeof(int))) != cudaSuccess ||
+        (e = cudaMalloc(&t->d_w, (wt.size() + 1) * sizeof(float))) != cudaSuccess) {
+        if (t->d_ofs) cudaFree(t->d_ofs);
+        if (t->d_idx) cudaFree(t->d_idx);
+        delete t;
+        return llfe_cuda_fail(e, "cudaMalloc(area table)", __FILE__, __LINE__);
+    }
+    // synchronous copies: the host vectors die at the end of this function
+    LLFE_CUDA(cudaMemcpy(t->d_ofs, ofs.data(), ofs.size() * sizeof(int), cudaMemcpyHostToDevice));
+    LLFE_CUDA(cudaMemcpy(t->d_idx, idx.data(), idx.size() * sizeof(int), cudaMemcpyHostToDevice));
+    LLFE_CUDA(cudaMemcpy(t->d_w, wt.data(), wt.size() * sizeof(float), cudaMemcpyHostToDevice));
+    t->next = ctx->area_tabs;
+    ctx->area_tabs = t;
+    *out = t;
+    return LLFE_OK;
+}
+
+template <int C>
+__global__ void __launch_bounds__(256) k_resize_area_tab(const uint8_t* __restrict__ src, int sh, int sw,
+                                                         uint8_t* __restrict__ dst, int dh, int dw,
+                                                         const int* __restrict__ xofs, const int* __restrict__ xidx,
+                                                         const float* __restrict__ xw, const int* __restrict__ yofs,
+                                                         const int* __restrict__ yidx, const float* __restrict__ yw) {
+    const int img = blockIdx.z;
+    const uint8_t* s = src + (size_t)img * sh * sw * C;
+    uint8_t* d = dst + (size_t)img * dh * dw * C;
+    int dx = blockIdx.x * blockDim.x + threadIdx.x, dy = blockIdx.y;
+    if (dx >= dw) return;
+    const int xb = xofs[dx], xe = xofs[dx + 1];
+    const int yb = yofs[dy], ye = yofs[dy + 1];
+    float sum[C];
+    for (int k = yb; k < ye; ++k) {
+        const uint8_t* row = s + (size_t)yidx[k] * sw * C;
+        const float beta = yw[k];
+        float buf[C];
+#pragma unroll
+        for (int ch = 0; ch < C; ++ch) buf[ch] = 0.f;
+        for (int j = xb; j < xe; ++j) {
+            const uint8_t* p = row + (size_t)xidx[j] * C;
+            const float alpha = xw[j];
+#pragma unroll
+            for (int ch = 0; ch < C; ++ch) buf[ch] = __fadd_rn(buf[ch], __fmul_rn((float)p[ch], alpha));
+        }
+#pragma unroll
+        for (int ch = 0; ch < C; ++ch) {
+            float t = __fmul_rn(beta, buf[ch]);
+            sum[ch] = (k == yb) ? t : __fadd_rn(sum[ch], t);
+        }
+    }
+#pragma unroll
+    for (int ch = 0; ch < C; ++ch) {
+        int v = __float2int_rn(sum[ch]);
+        d[((size_t)dy * dw + dx) * C + ch] = (uint8_t)min(max(v, 0), 255);
+    }
+}
+
+template <int C>
+__global__ void __launch_bounds__(256) k_resize_area_int(const uint8_t* __restrict__ src, int sh, int sw,
+                                                         uint8_t* __restrict__ dst, int dh, int dw, int isx, int isy) {
+    const int img = blockIdx.z;
+    const uint8_t* s = src + (size_t)img * sh * sw * C;
+    uint8_t* d = dst + (size_t)img * dh * dw * C;
+    int dx = blockIdx.x * blockDim.x + threadIdx.x, dy = blockIdx.y;
+    if (dx >= dw) return;
+    int sum[C];
+#pragma unroll
+    for (int ch = 0; ch < C; ++ch) sum[ch] = 0;
+    for (int yy = 0; yy < isy; ++yy) {
+        const uint8_t* row = s + ((size_t)(dy * isy + yy) * sw + (size_t)dx * isx) * C;
+        for (int xx = 0; xx < isx; ++xx)
+#pragma unroll
+            for (int ch = 0; ch < C; ++ch) sum[ch] += row[xx * C + ch];
+    }
+    const bool two = (isx == 2 && isy == 2);
+    const float inv = __fdiv_rn(1.f, (float)(isx * isy));
+#pragma unroll
+    for (int ch = 0; ch < C; ++ch) {
+        int v = two ? ((sum[ch] + 2) >> 2) : __float2int_rn(__fmul_rn((float)sum[ch], inv));
+        d[((size_t)dy * dw + dx) * C + ch] = (uint8_t)min(max(v, 0), 255);
+    }
+}
+
+}  // namespace
+
+void llfe_free_area_tabs(llfe_ctx* ctx) {
+    AreaTab* t = ctx->area_tabs;
+    while (t) {
+        AreaTab* nx = t->next;
+        cudaFree(t->d_ofs);
+        cudaFree(t->d_idx);
+        cudaFree(t->d_w);
+        delete t;
+        t = nx;
+    }
+    ctx->area_tabs = nullptr;
+}
+
+extern "C" int llfe_resize_area(llfe_ctx* ctx, const uint8_t* d_src, int n, int sh, int sw, int c, uint8_t* d_dst,
+                                int dh, int dw) {
+    LLFE_CHECK_ARG(ctx != nullptr && d_src != nullptr && d_dst != nullptr);
+    LLFE_CHECK_ARG(n >= 0 && n <= 65535 && sh > 0 && sw > 0 && dh > 0 && dw > 0 && (c == 1 || c == 3));
+    if (dh > sh || dw > sw) {
+        llfe_set_error("llfe_resize_area: only down-scaling is on the hot path (%dx%d -> %dx%d)", sw, sh, dw, dh);
+        return LLFE_E_UNSUPPORTED;
+    }
+    if (dh > 65535) return LLFE_E_UNSUPPORTED;
+    if (n == 0) return LLFE_OK;
+    if (dh == sh && dw == sw) {
+        LLFE_CUDA(cudaMemcpyAsync(d_dst, d_src, (size_t)n * sh * sw * c, cudaMemcpyDeviceToDevice, ctx->stream));
+        return LLFE_OK;
+    }
+    const double scale_x = 1.0 / ((double)dw / sw), scale_y = 1.0 / ((double)dh / sh);
+    const int isx = (int)lrint(scale_x), isy = (int)lrint(scale_y);
+    const bool fast = fabs(scale_x - isx) < 2.220446049250313e-16 && fabs(scale_y - isy) < 2.220446049250313e-16;
+    dim3 grid(ceil_div(dw, 256), dh, n);
+    if (fast) {
+        if (c == 3)
+            k_resize_area_int<3><<<grid, 256, 0, ctx->stream>>>(d_src, sh, sw, d_dst, dh, dw, isx, isy);
+        else
+            k_resize_area_int<1><<<grid, 256, 0, ctx->stream>>>(d_src, sh, sw, d_dst, dh, dw, isx, isy);
+        LLFE_LAUNCHED(ctx);
+        return LLFE_OK;
+    }
+    AreaTab *xt, *yt;
+    LLFE_TRY(get_tab(ctx, sw, dw, &xt));
+    LLFE_TRY(get_tab(ctx, sh, dh, &yt));
+    if (c == 3)
+        k_resize_area_tab<3><<<grid, 256, 0, ctx->stream>>>(d_src, sh, sw, d_dst, dh, dw, xt->d_ofs, xt->d_idx, xt->d_w,
+                                                            yt->d_ofs, yt->d_idx, yt->d_w);
+    else
+        k_resize_area_tab<1><<<grid, 256, 0, ctx->stream>>>(d_src, sh, sw, d_dst, dh, dw, xt->d_ofs, xt->d_idx, xt->d_w,
+                                                            yt->d_ofs, yt->d_idx, yt->d_w);
+    LLFE_LAUNCHED(ctx);
+    return LLFE_OK;
+}

@@ -1,0 +1,419 @@
+// extern "C" surface of libllfe.so: context, memory helpers and the per-op
+// entry points declared in include/llfe.h.  Kernels live in the k_*.cu files.
+#include <stdarg.h>
+#include <string.h>
+
+#include <new>
+
+#include "llfe_common.cuh"
+
+#define LLFE_VERSION_NUM 100
+
+static thread_local char g_err[512] = "";
+
+void llfe_set_error(const char* fmt, ...) {
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_err, sizeof(g_err), fmt, ap);
+    va_end(ap);
+}
+
+int llfe_cuda_fail(cudaError_t e, const char* what, const char* file, int line) {
+    llfe_set_error("CUDA error %d (%s) at %s:%d: %s", (int)e, cudaGetErrorString(e), file, line, what);
+    return e == cudaErrorMemoryAllocation ? LLFE_E_NOMEM : LLFE_E_CUDA;
+}
+
+int llfe_workspace(llfe_ctx* ctx, size_t bytes, void** out) {
+    if (bytes > ctx->ws_bytes) {
+        // grow: everything queued so far may still be using the old arena
+        LLFE_CUDA(cudaStreamSynchronize(ctx->stream));
+        if (ctx->ws) LLFE_CUDA(cudaFree(ctx->ws));
+        ctx->ws = nullptr;
+        ctx->ws_bytes = 0;
+        size_t want = bytes + bytes / 4 + (1 << 20);
+        LLFE_CUDA(cudaMalloc(&ctx->ws, want));
+        ctx->ws_bytes = want;
+    }
+    *out = ctx->ws;
+    return LLFE_OK;
+}
+
+static int ensure_stage(llfe_ctx* ctx, size_t pin_bytes, size_t dev_bytes) {
+    if (pin_bytes > ctx->pin_bytes) {
+        LLFE_CUDA(cudaStreamSynchronize(ctx->stream));
+        if (ctx->pin) LLFE_CUDA(cudaFreeHost(ctx->pin));
+        ctx->pin = nullptr;
+        ctx->pin_bytes = 0;
+        LLFE_CUDA(cudaMallocHost(&ctx->pin, pin_bytes));
+        ctx->pin_bytes = pin_bytes;
+    }
+    if (dev_bytes > ctx->dev_stage_bytes) {
+        LLFE_CUDA(cudaStreamSynchronize(ctx->stream));
+        if (ctx->dev_stage) LLFE_CUDA(cudaFree(ctx->dev_stage));
+        ctx->dev_stage = nullptr;
+        ctx->dev_stage_bytes = 0;
+        LLFE_CUDA(cudaMalloc(&ctx->dev_stage, dev_bytes));
+        ctx->dev_stage_bytes = dev_bytes;
+    }
+    return LLFE_OK;
+}
+
+extern "C" {
+
+int llfe_version(void) { return LLFE_VERSION_NUM; }
+const char* llfe_last_error(void) { return g_err; }
+
+int llfe_device_count(void) {
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess) {
+        cudaGetLastError();
+        return 0;
+    }
+    return n;
+}
+
+int llfe_create(int device, llfe_ctx** out) {
+    LLFE_CHECK_ARG(out != nullptr);
+    *out = nullptr;
+    int n = 0;
+    cudaError_t e = cudaGetDeviceCount(&n);
+    if (e != cudaSuccess || n == 0) {
+        cudaGetLastError();
+        llfe_set_error("llfe_create: no usable CUDA device (%s); this library has no CPU fallback",
+                       e == cudaSuccess ? "device count is 0" : cudaGetErrorString(e));
+        return LLFE_E_NODEVICE;
+    }
+    LLFE_CHECK_ARG(device >= 0 && device < n);
+    LLFE_CUDA(cudaSetDevice(device));
+    cudaDeviceProp prop;
+    LLFE_CUDA(cudaGetDeviceProperties(&prop, device));
+    if (prop.major < 10) {
+        llfe_set_error("llfe_create: device %d is sm_%d%d; libllfe.so carries sm_100a code only", device, prop.major,
+                       prop.minor);
+        return LLFE_E_UNSUPPORTED;
+    }
+    llfe_ctx* c = new (std::nothrow) llfe_ctx();
+    if (!c) return LLFE_E_NOMEM;
+    c->device = device;
+    c->sm_count = prop.multiProcessorCount;
+    c->smem_optin = prop.sharedMemPerBlockOptin;
+    cudaError_t se = cudaStreamCreateWithFlags(&c->own_stream, cudaStreamNonBlocking);
+    if (se != cudaSuccess) {
+        delete c;
+        return llfe_cuda_fail(se, "cudaStreamCreateWithFlags", __FILE__, __LINE__);
+    }
+    c->stream = c->own_stream;
+    *out = c;
+    return LLFE_OK;
+}
+
+int llfe_destroy(llfe_ctx* ctx) {
+    if (!ctx) return LLFE_OK;
+    cudaSetDevice(ctx->device);
+    cudaStreamSynchronize(ctx->stream);
+    if (ctx->ws) cudaFree(ctx->ws);
+    if (ctx->pin) cudaFreeHost(ctx->pin);
+    if (ctx->dev_stage) cudaFree(ctx->dev_stage);
+    llfe_free_area_tabs(ctx);
+    if (ctx->own_stream) cudaStreamDestroy(ctx->own_stream);
+    delete ctx;
+    return LLFE_OK;
+}
+
+int llfe_set_stream(llfe_ctx* ctx, void* cuda_stream) {
+    LLFE_CHECK_ARG(ctx != nullptr);
+    ctx->stream = cuda_stream ? (cudaStream_t)cuda_stream : ctx->own_stream;
+    return LLFE_OK;
+}
+
+int llfe_sync(llfe_ctx* ctx) {
+    LLFE_CHECK_ARG(ctx != nullptr);
+    LLFE_CUDA(cudaStreamSynchronize(ctx->stream));
+    return LLFE_OK;
+}
+
+uint64_t llfe_launch_count(llfe_ctx* ctx) { return ctx ? ctx->launches : 0; }
+int llfe_sm_count(llfe_ctx* ctx) { return ctx ? ctx->sm_count : 0; }
+
+int llfe_malloc(llfe_ctx* ctx, size_t bytes, void** d_out) {
+    LLFE_CHECK_ARG(ctx != nullptr && d_out != nullptr);
+    LLFE_CUDA(cudaSetDevice(ctx->device));
+    LLFE_CUDA(cudaMalloc(d_out, bytes ? bytes : 1));
+    return LLFE_OK;
+}
+int llfe_free(llfe_ctx* ctx, void* d_ptr) {
+    LLFE_CHECK_ARG(ctx != nullptr);
+    if (d_ptr) {
+        LLFE_CUDA(cudaStreamSynchronize(ctx->stream));
+        LLFE_CUDA(cudaFree(d_ptr));
+    }
+    return LLFE_OK;
+}
+int llfe_malloc_host(llfe_ctx* ctx, size_t bytes, void** h_out) {
+    LLFE_CHECK_ARG(ctx != nullptr && h_out != nullptr);
+    LLFE_CUDA(cudaMallocHost(h_out, bytes ? bytes : 1));
+    return LLFE_OK;
+}
+int llfe_free_host(llfe_ctx* ctx, void* h_ptr) {
+    LLFE_CHECK_ARG(ctx != nullptr);
+    if (h_ptr) LLFE_CUDA(cudaFreeHost(h_ptr));
+    return LLFE_OK;
+}
+int llfe_memcpy_h2d(llfe_ctx* ctx, void* d_dst, const void* h_src, size_t bytes) {
+    LLFE_CHECK_ARG(ctx != nullptr);
+    if (bytes) LLFE_CUDA(cudaMemcpyAsync(d_dst, h_src, bytes, cudaMemcpyHostToDevice, ctx->stream));
+    return LLFE_OK;
+}
+int llfe_memcpy_d2h(llfe_ctx* ctx, void* h_dst, const void* d_src, size_t bytes) {
+    LLFE_CHECK_ARG(ctx != nullptr);
+    if (bytes) LLFE_CUDA(cudaMemcpyAsync(h_dst, d_src, bytes, cudaMemcpyDeviceToHost, ctx->stream));
+    return LLFE_OK;
+}
+int llfe_memset(llfe_ctx* ctx, void* d_dst, int value, size_t bytes) {
+    LLFE_CHECK_ARG(ctx != nullptr);
+    if (bytes) LLFE_CUDA(cudaMemsetAsync(d_dst, value, bytes, ctx->stream));
+    return LLFE_OK;
+}
+
+#define LLFE_IMG_ARGS(ptr) LLFE_CHECK_ARG(ctx != nullptr && (ptr) != nullptr && n >= 0 && h >= 0 && w >= 0 && n <= 65535)
+
+// ---- pointwise ----------------------------------------------------------------
+int llfe_bgr2gray(llfe_ctx* ctx, const uint8_t* d_bgr, int n, int h, int w, uint8_t* d_gray) {
+    LLFE_IMG_ARGS(d_bgr);
+    LLFE_CHECK_ARG(d_gray != nullptr);
+    return launch_bgr2gray(ctx, d_bgr, (size_t)n * h * w, d_gray);
+}
+
+int llfe_bgr2rgb(llfe_ctx* ctx, const uint8_t* d_bgr, int n, int h, int w, uint8_t* d_rgb) {
+    LLFE_IMG_ARGS(d_bgr);
+    LLFE_CHECK_ARG(d_rgb != nullptr);
+    return launch_bgr2rgb(ctx, d_bgr, (size_t)n * h * w, d_rgb);
+}
+
+int llfe_convert_scale_abs(llfe_ctx* ctx, const uint8_t* d_src, size_t count, float a1, float a2, int single,
+                           uint8_t* d_dst) {
+    LLFE_CHECK_ARG(ctx != nullptr && d_src != nullptr && d_dst != nullptr);
+    return launch_lut2(ctx, d_src, count, a1, a2, single, d_dst);
+}
+
+// ---- blur -------------------------------------------------------------------
+int llfe_gaussian_blur5(llfe_ctx* ctx, const uint8_t* d_src, int n, int h, int w, int c, uint8_t* d_dst) {
+    LLFE_IMG_ARGS(d_src);
+    LLFE_CHECK_ARG(d_dst != nullptr && (c == 1 || c == 3) && d_src != d_dst);
+    return launch_blur5(ctx, d_src, n, h, w, c, d_dst);
+}
+
+int llfe_gray_blur5(llfe_ctx* ctx, const uint8_t* d_bgr, int n, int h, int w, uint8_t* d_blurred) {
+    LLFE_IMG_ARGS(d_bgr);
+    LLFE_CHECK_ARG(d_blurred != nullptr);
+    return launch_gray_blur5(ctx, d_bgr, n, h, w, d_blurred);
+}
+
+// ---- edges ------------------------------------------------------------------
+static int canny_from_gray(llfe_ctx* ctx, const uint8_t* d_gray, int n, int h, int w, int low, int high, int dilate,
+                           uint8_t* d_out, char* ws_base) {
+    const size_t plane = (size_t)n * h * plane_wpr(w);
+    WsCarver ws(ws_base);
+    uint32_t* weak = ws.take<uint32_t>(plane);
+    uint32_t* edges = ws.take<uint32_t>(plane);
+    uint32_t* flags = ws.take<uint32_t>(hysteresis_flag_words(n, h));
+    LLFE_TRY(launch_canny_front(ctx, d_gray, n, h, w, low, high, weak, edges));
+    LLFE_TRY(launch_hysteresis(ctx, weak, edges, n, h, w, flags));
+    return launch_plane_to_mask(ctx, edges, n, h, w, dilate, d_out);
+}
+
+static size_t canny_ws_bytes(int n, int h, int w) {
+    const size_t plane = (size_t)n * h * plane_wpr(w) * sizeof(uint32_t);
+    return 2 * WsCarver::need(plane) + WsCarver::need(hysteresis_flag_words(n, h) * sizeof(uint32_t));
+}
+
+int llfe_canny(llfe_ctx* ctx, const uint8_t* d_gray, int n, int h, int w, int low, int high, uint8_t* d_edges) {
+    LLFE_IMG_ARGS(d_gray);
+    LLFE_CHECK_ARG(d_edges != nullptr);
+    if ((size_t)n * h * w == 0) return LLFE_OK;
+    void* ws;
+    LLFE_TRY(llfe_workspace(ctx, canny_ws_bytes(n, h, w), &ws));
+    return canny_from_gray(ctx, d_gray, n, h, w, low, high, 0, d_edges, (char*)ws);
+}
+
+int llfe_dilate3(llfe_ctx* ctx, const uint8_t* d_src, int n, int h, int w, uint8_t* d_dst) {
+    LLFE_IMG_ARGS(d_src);
+    LLFE_CHECK_ARG(d_dst != nullptr && d_src != d_dst);
+    return launch_dilate3_u8(ctx, d_src, n, h, w, d_dst);
+}
+
+int llfe_shape_mask(llfe_ctx* ctx, const uint8_t* d_bgr, int n, int h, int w, int low, int high, uint8_t* d_mask) {
+    LLFE_IMG_ARGS(d_bgr);
+    LLFE_CHECK_ARG(d_mask != nullptr);
+    if ((size_t)n * h * w == 0) return LLFE_OK;
+    const size_t img = WsCarver::need((size_t)n * h * w);
+    void* ws;
+    LLFE_TRY(llfe_workspace(ctx, img + canny_ws_bytes(n, h, w), &ws));
+    uint8_t* blurred = (uint8_t*)ws;
+    LLFE_TRY(launch_gray_blur5(ctx, d_bgr, n, h, w, blurred));
+    return canny_from_gray(ctx, blurred, n, h, w, low, high, 1, d_mask, (char*)ws + img);
+}
+
+// ---- thresholds ---------------------------------------------------------------
+int llfe_adaptive_threshold(llfe_ctx* ctx, const uint8_t* d_gray, int n, int h, int w, int C, uint8_t* d_mask,
+                            uint64_t* d_sum_count) {
+    LLFE_IMG_ARGS(d_gray);
+    LLFE_CHECK_ARG(d_mask != nullptr);
+    return launch_adaptive(ctx, d_gray, n, h, w, C, d_mask, d_sum_count);
+}
+
+int llfe_shadow_mask(llfe_ctx* ctx, const uint8_t* d_bgr, int n, int h, int w, uint8_t* d_mask, uint8_t* d_blurred,
+                     uint64_t* d_sum_count) {
+    LLFE_IMG_ARGS(d_bgr);
+    LLFE_CHECK_ARG(d_mask != nullptr);
+    if ((size_t)n * h * w == 0) return LLFE_OK;
+    uint8_t* blurred = d_blurred;
+    if (!blurred) {
+        void* ws;
+        LLFE_TRY(llfe_workspace(ctx, (size_t)n * h * w, &ws));
+        blurred = (uint8_t*)ws;
+    }
+    LLFE_TRY(launch_gray_blur5(ctx, d_bgr, n, h, w, blurred));
+    return launch_adaptive(ctx, blurred, n, h, w, 2, d_mask, d_sum_count);
+}
+
+int llfe_font_mask(llfe_ctx* ctx, const uint8_t* d_bgr, int n, int h, int w, uint8_t* d_mask) {
+    LLFE_IMG_ARGS(d_bgr);
+    LLFE_CHECK_ARG(d_mask != nullptr);
+    if ((size_t)n * h * w == 0) return LLFE_OK;
+    void* ws;
+    LLFE_TRY(llfe_workspace(ctx, (size_t)n * h * w, &ws));
+    LLFE_TRY(launch_bgr2gray(ctx, d_bgr, (size_t)n * h * w, (uint8_t*)ws));
+    return launch_adaptive(ctx, (uint8_t*)ws, n, h, w, 2, d_mask, nullptr);
+}
+
+static int otsu_impl(llfe_ctx* ctx, const uint8_t* d_gray, int n, size_t npix, int invert_if_light, uint8_t* d_mask,
+                     int32_t* d_thresh, char* ws_base) {
+    WsCarver ws(ws_base);
+    uint32_t* hist = ws.take<uint32_t>((size_t)n * 256);
+    int32_t* thr = ws.take<int32_t>(n);
+    int32_t* inv = ws.take<int32_t>(n);
+    LLFE_TRY(launch_hist256(ctx, d_gray, n, npix, hist));
+    LLFE_TRY(launch_otsu_sweep(ctx, hist, n, npix, invert_if_light, d_thresh ? d_thresh : thr, inv));
+    return launch_binarize(ctx, d_gray, n, npix, d_thresh ? d_thresh : thr, inv, d_mask);
+}
+
+static size_t otsu_ws_bytes(int n) {
+    return WsCarver::need((size_t)n * 256 * 4) + 2 * WsCarver::need((size_t)n * 4);
+}
+
+int llfe_otsu(llfe_ctx* ctx, const uint8_t* d_gray, int n, int h, int w, int invert_if_light, uint8_t* d_mask,
+              int32_t* d_thresh) {
+    LLFE_IMG_ARGS(d_gray);
+    LLFE_CHECK_ARG(d_mask != nullptr);
+    if ((size_t)n * h * w == 0) return LLFE_OK;
+    void* ws;
+    LLFE_TRY(llfe_workspace(ctx, otsu_ws_bytes(n), &ws));
+    return otsu_impl(ctx, d_gray, n, (size_t)h * w, invert_if_light, d_mask, d_thresh, (char*)ws);
+}
+
+int llfe_text_mask(llfe_ctx* ctx, const uint8_t* d_bgr, int n, int h, int w, uint8_t* d_mask, int32_t* d_thresh) {
+    LLFE_IMG_ARGS(d_bgr);
+    LLFE_CHECK_ARG(d_mask != nullptr);
+    if ((size_t)n * h * w == 0) return LLFE_OK;
+    const size_t img = WsCarver::need((size_t)n * h * w);
+    void* ws;
+    LLFE_TRY(llfe_workspace(ctx, img + otsu_ws_bytes(n), &ws));
+    uint8_t* gray = (uint8_t*)ws;
+    LLFE_TRY(launch_bgr2gray(ctx, d_bgr, (size_t)n * h * w, gray));
+    return otsu_impl(ctx, gray, n, (size_t)h * w, 1, d_mask, d_thresh, (char*)ws + img);
+}
+
+// ---- host-buffer convenience entry points ----------------------------------------
+// Stage through pinned memory, run on the context's stream, copy back, synchronise.
+struct HostStage {
+    llfe_ctx* ctx;
+    uint8_t* d_in;
+    uint8_t* d_out;
+    uint8_t* p_in;
+    uint8_t* p_out;
+};
+
+static int stage_begin(llfe_ctx* ctx, const void* h_in, size_t in_bytes, size_t out_bytes, HostStage* st) {
+    const size_t a = WsCarver::need(in_bytes), b = WsCarver::need(out_bytes);
+    LLFE_TRY(ensure_stage(ctx, a + b, a + b));
+    st->ctx = ctx;
+    st->p_in = (uint8_t*)ctx->pin;
+    st->p_out = st->p_in + a;
+    st->d_in = (uint8_t*)ctx->dev_stage;
+    st->d_out = st->d_in + a;
+    memcpy(st->p_in, h_in, in_bytes);
+    LLFE_CUDA(cudaMemcpyAsync(st->d_in, st->p_in, in_bytes, cudaMemcpyHostToDevice, ctx->stream));
+    return LLFE_OK;
+}
+
+static int stage_end(HostStage* st, void* h_out, size_t out_bytes, size_t d_off) {
+    LLFE_CUDA(cudaMemcpyAsync(st->p_out + d_off, st->d_out + d_off, out_bytes, cudaMemcpyDeviceToHost, st->ctx->stream));
+    LLFE_CUDA(cudaStreamSynchronize(st->ctx->stream));
+    memcpy(h_out, st->p_out + d_off, out_bytes);
+    return LLFE_OK;
+}
+
+int llfe_shape_mask_host(llfe_ctx* ctx, const uint8_t* h_bgr, int h, int w, int low, int high, uint8_t* h_mask) {
+    LLFE_CHECK_ARG(ctx != nullptr && h_bgr != nullptr && h_mask != nullptr && h > 0 && w > 0);
+    const size_t p = (size_t)h * w;
+    HostStage st;
+    LLFE_TRY(stage_begin(ctx, h_bgr, 3 * p, p, &st));
+    LLFE_TRY(llfe_shape_mask(ctx, st.d_in, 1, h, w, low, high, st.d_out));
+    return stage_end(&st, h_mask, p, 0);
+}
+
+int llfe_shadow_mask_host(llfe_ctx* ctx, const uint8_t* h_bgr, int h, int w, uint8_t* h_mask, uint8_t* h_blurred,
+                          uint64_t* h_sum_count) {
+    LLFE_CHECK_ARG(ctx != nullptr && h_bgr != nullptr && h > 0 && w > 0 && (h_mask || h_sum_count));
+    const size_t p = (size_t)h * w, pa = WsCarver::need(p);
+    HostStage st;
+    LLFE_TRY(stage_begin(ctx, h_bgr, 3 * p, 2 * pa + 256, &st));
+    uint8_t* d_mask = st.d_out;
+    uint8_t* d_blur = st.d_out + pa;
+    uint64_t* d_sc = (uint64_t*)(st.d_out + 2 * pa);
+    LLFE_TRY(llfe_shadow_mask(ctx, st.d_in, 1, h, w, d_mask, d_blur, d_sc));
+    if (h_mask) LLFE_CUDA(cudaMemcpyAsync(st.p_out, d_mask, p, cudaMemcpyDeviceToHost, ctx->stream));
+    if (h_blurred) LLFE_CUDA(cudaMemcpyAsync(st.p_out + pa, d_blur, p, cudaMemcpyDeviceToHost, ctx->stream));
+    LLFE_CUDA(cudaMemcpyAsync(st.p_out + 2 * pa, d_sc, 16, cudaMemcpyDeviceToHost, ctx->stream));
+    LLFE_CUDA(cudaStreamSynchronize(ctx->stream));
+    if (h_mask) memcpy(h_mask, st.p_out, p);
+    if (h_blurred) memcpy(h_blurred, st.p_out + pa, p);
+    if (h_sum_count) memcpy(h_sum_count, st.p_out + 2 * pa, 16);
+    return LLFE_OK;
+}
+
+int llfe_text_mask_host(llfe_ctx* ctx, const uint8_t* h_bgr, int h, int w, uint8_t* h_mask, int32_t* h_thresh) {
+    LLFE_CHECK_ARG(ctx != nullptr && h_bgr != nullptr && h_mask != nullptr && h > 0 && w > 0);
+    const size_t p = (size_t)h * w, pa = WsCarver::need(p);
+    HostStage st;
+    LLFE_TRY(stage_begin(ctx, h_bgr, 3 * p, pa + 256, &st));
+    int32_t* d_thr = (int32_t*)(st.d_out + pa);
+    LLFE_TRY(llfe_text_mask(ctx, st.d_in, 1, h, w, st.d_out, d_thr));
+    LLFE_CUDA(cudaMemcpyAsync(st.p_out, st.d_out, p, cudaMemcpyDeviceToHost, ctx->stream));
+    LLFE_CUDA(cudaMemcpyAsync(st.p_out + pa, d_thr, 4, cudaMemcpyDeviceToHost, ctx->stream));
+    LLFE_CUDA(cudaStreamSynchronize(ctx->stream));
+    memcpy(h_mask, st.p_out, p);
+    if (h_thresh) memcpy(h_thresh, st.p_out + pa, 4);
+    return LLFE_OK;
+}
+
+int llfe_font_mask_host(llfe_ctx* ctx, const uint8_t* h_bgr, int h, int w, uint8_t* h_mask) {
+    LLFE_CHECK_ARG(ctx != nullptr && h_bgr != nullptr && h_mask != nullptr && h > 0 && w > 0);
+    const size_t p = (size_t)h * w;
+    HostStage st;
+    LLFE_TRY(stage_begin(ctx, h_bgr, 3 * p, p, &st));
+    LLFE_TRY(llfe_font_mask(ctx, st.d_in, 1, h, w, st.d_out));
+    return stage_end(&st, h_mask, p, 0);
+}
+
+int llfe_resize_area_host(llfe_ctx* ctx, const uint8_t* h_src, int sh, int sw, int c, uint8_t* h_dst, int dh, int dw) {
+    LLFE_CHECK_ARG(ctx != nullptr && h_src != nullptr && h_dst != nullptr && sh > 0 && sw > 0 && dh > 0 && dw > 0);
+    const size_t in = (size_t)sh * sw * c, out = (size_t)dh * dw * c;
+    HostStage st;
+    LLFE_TRY(stage_begin(ctx, h_src, in, out, &st));
+    LLFE_TRY(llfe_resize_area(ctx, st.d_in, 1, sh, sw, c, st.d_out, dh, dw));
+    return stage_end(&st, h_dst, out, 0);
+}
+
+}  // extern "C"

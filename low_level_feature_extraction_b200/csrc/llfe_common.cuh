@@ -1,0 +1,104 @@
+// Shared declarations for libllfe.so (sm_100a only).
+#pragma once
+
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+
+#include "llfe.h"
+
+struct llfe_ctx {
+    int device = 0;
+    int sm_count = 0;
+    size_t smem_optin = 0;
+    cudaStream_t own_stream = nullptr;
+    cudaStream_t stream = nullptr;
+    // workspace arena (grown on demand; ops carve it per call)
+    void* ws = nullptr;
+    size_t ws_bytes = 0;
+    // pinned staging for the *_host entry points
+    void* pin = nullptr;
+    size_t pin_bytes = 0;
+    void* dev_stage = nullptr;
+    size_t dev_stage_bytes = 0;
+    // INTER_AREA tables cached per (ssize, dsize)
+    struct AreaTab* area_tabs = nullptr;
+    uint64_t launches = 0;
+};
+
+void llfe_set_error(const char* fmt, ...);
+int llfe_cuda_fail(cudaError_t e, const char* what, const char* file, int line);
+
+#define LLFE_CUDA(call)                                                       \
+    do {                                                                      \
+        cudaError_t _e = (call);                                              \
+        if (_e != cudaSuccess) return llfe_cuda_fail(_e, #call, __FILE__, __LINE__); \
+    } while (0)
+
+#define LLFE_CHECK_ARG(cond)                                                  \
+    do {                                                                      \
+        if (!(cond)) {                                                        \
+            llfe_set_error("%s: invalid argument: %s", __func__, #cond);      \
+            return LLFE_E_INVALID;                                            \
+        }                                                                     \
+    } while (0)
+
+#define LLFE_TRY(expr)                \
+    do {                              \
+        int _r = (expr);              \
+        if (_r != LLFE_OK) return _r; \
+    } while (0)
+
+// after every kernel launch: count it and surface launch-configuration errors
+#define LLFE_LAUNCHED(ctx)                      \
+    do {                                        \
+        (ctx)->launches++;                      \
+        LLFE_CUDA(cudaPeekAtLastError());       \
+    } while (0)
+
+// workspace: returns a device pointer to at least `bytes` of scratch (256-B aligned).
+// May synchronise and reallocate when the arena has to grow.
+int llfe_workspace(llfe_ctx* ctx, size_t bytes, void** out);
+
+struct WsCarver {
+    char* base;
+    size_t off = 0;
+    explicit WsCarver(void* p) : base(static_cast<char*>(p)) {}
+    template <typename T>
+    T* take(size_t count) {
+        T* p = reinterpret_cast<T*>(base + off);
+        off += (count * sizeof(T) + 255) & ~size_t(255);
+        return p;
+    }
+    static size_t need(size_t bytes) { return (bytes + 255) & ~size_t(255); }
+};
+
+static inline int ceil_div(int a, int b) { return (a + b - 1) / b; }
+static inline size_t ceil_div_sz(size_t a, size_t b) { return (a + b - 1) / b; }
+
+// ---- internal kernels' host launchers (defined across the .cu files) --------
+// bit-plane layout used by the edge chain: one bit per pixel, bit (x & 31) of
+// word (x >> 5); rows padded to `wpr` 32-bit words; planes of a batch back to back.
+__host__ __device__ static inline int plane_wpr(int w) { return (w + 31) / 32; }
+
+int launch_bgr2gray(llfe_ctx* ctx, const uint8_t* bgr, size_t npix, uint8_t* gray);
+int launch_bgr2rgb(llfe_ctx* ctx, const uint8_t* bgr, size_t npix, uint8_t* rgb);
+int launch_lut2(llfe_ctx* ctx, const uint8_t* src, size_t count, float a1, float a2, int single, uint8_t* dst);
+int launch_blur5(llfe_ctx* ctx, const uint8_t* src, int n, int h, int w, int c, uint8_t* dst);
+int launch_gray_blur5(llfe_ctx* ctx, const uint8_t* bgr, int n, int h, int w, uint8_t* dst);
+int launch_canny_front(llfe_ctx* ctx, const uint8_t* gray, int n, int h, int w, int low, int high, uint32_t* weak,
+                       uint32_t* strong);
+int launch_edge_front_bgr(llfe_ctx* ctx, const uint8_t* bgr, int n, int h, int w, int low, int high, uint32_t* weak,
+                          uint32_t* strong);
+int launch_hysteresis(llfe_ctx* ctx, const uint32_t* weak, uint32_t* edges, int n, int h, int w, uint32_t* flags);
+int launch_plane_to_mask(llfe_ctx* ctx, const uint32_t* plane, int n, int h, int w, int dilate, uint8_t* mask);
+int launch_mask_to_plane(llfe_ctx* ctx, const uint8_t* mask, int n, int h, int w, uint32_t* plane);
+int launch_adaptive(llfe_ctx* ctx, const uint8_t* gray, int n, int h, int w, int C, uint8_t* mask, uint64_t* sum_count);
+int launch_hist256(llfe_ctx* ctx, const uint8_t* gray, int n, size_t npix_per_image, uint32_t* hist);
+int launch_otsu_sweep(llfe_ctx* ctx, const uint32_t* hist, int n, size_t npix_per_image, int invert_if_light,
+                      int32_t* thresh, int32_t* invert);
+int launch_binarize(llfe_ctx* ctx, const uint8_t* gray, int n, size_t npix_per_image, const int32_t* thresh,
+                    const int32_t* invert, uint8_t* mask);
+size_t hysteresis_flag_words(int n, int h);
+int launch_dilate3_u8(llfe_ctx* ctx, const uint8_t* src, int n, int h, int w, uint8_t* dst);
+void llfe_free_area_tabs(llfe_ctx* ctx);

@@ -219,7 +219,7 @@ def otsu_from_hist(hist: np.ndarray, n: int) -> int:
     q1 = 0.0
     max_sigma = 0.0
     max_val = 0
-    eps = np.finfo(np.float64).eps
+    eps = float(np.finfo(np.float32).eps)  # FLT_EPSILON (probed: 1 px of 16.7M is skipped, 3 px are not)
     for i in range(256):
         p_i = float(hist[i]) * scale
         mu1 *= q1

@@ -76,6 +76,15 @@ def test_otsu(seed):
     assert np.array_equal(cvops.text_mask(img), refpath.text_mask(img))
 
 
+def test_otsu_tiny_class_uses_flt_epsilon():
+    # OpenCV skips classes lighter than FLT_EPSILON: 1 px of 16.7M is ignored, 3 px are not
+    g = np.full((4096, 4096), 200, np.uint8)
+    g[0, 0] = 50
+    assert cvops.otsu_threshold(g) == int(cv2.threshold(g, 0, 255, cv2.THRESH_BINARY + cv2.THRESH_OTSU)[0]) == 0
+    g[0, 0:3] = 50
+    assert cvops.otsu_threshold(g) == int(cv2.threshold(g, 0, 255, cv2.THRESH_BINARY + cv2.THRESH_OTSU)[0]) == 50
+
+
 @pytest.mark.parametrize("case", [((216, 384, 3), (200, 112)), ((120, 240, 3), (200, 100)), ((150, 210), (200, 142)),
                                   ((128, 128, 3), (64, 64)), ((128, 256, 3), (64, 32)), ((96, 96), (12, 12)),
                                   ((90, 120, 3), (40, 30)), ((100, 300, 3), (299, 99)), ((64, 64, 3), (64, 64))])
