@@ -52,8 +52,11 @@ int llfe_device_count(void);
 int llfe_create(int device, llfe_ctx** out);
 int llfe_destroy(llfe_ctx* ctx);
 /* Use an existing CUDA stream (a cudaStream_t passed as void*), e.g. torch's
- * current stream; NULL restores the context's own stream. */
+ * current stream.  NULL is a valid stream: the CUDA legacy default stream (what
+ * torch calls its default stream).  llfe_use_own_stream goes back to the
+ * non-blocking stream the context created for itself. */
 int llfe_set_stream(llfe_ctx* ctx, void* cuda_stream);
+int llfe_use_own_stream(llfe_ctx* ctx);
 int llfe_sync(llfe_ctx* ctx);
 /* Number of kernels this context has launched so far (for accounting). */
 uint64_t llfe_launch_count(llfe_ctx* ctx);

@@ -9,7 +9,7 @@ kernels behind a C ABI (`libllfe.so`, include/llfe.h).
     from low_level_feature_extraction_b200.services import ...     # drop-in service classes
 
 There is no CPU fallback: importing the package loads libllfe.so and fails if
-it has not been built (`python -m low_level_feature_extraction_b200.build`).
+it has not been built (`python low_level_feature_extraction_b200/build.py`).
 """
 from ._native import Context, LlfeError, load_library, PROTOTYPES, LIB_PATH  # noqa: F401
 

@@ -32,6 +32,7 @@ PROTOTYPES = {
     "llfe_create": (i32, [i32, C.POINTER(vp)]),
     "llfe_destroy": (i32, [vp]),
     "llfe_set_stream": (i32, [vp, vp]),
+    "llfe_use_own_stream": (i32, [vp]),
     "llfe_sync": (i32, [vp]),
     "llfe_launch_count": (u64, [vp]),
     "llfe_sm_count": (i32, [vp]),
@@ -80,7 +81,7 @@ def load_library() -> C.CDLL:
         if _lib is None:
             if not os.path.exists(LIB_PATH):
                 raise ImportError(
-                    f"{LIB_PATH} is missing: build it with `python -m low_level_feature_extraction_b200.build` "
+                    f"{LIB_PATH} is missing: build it with `python low_level_feature_extraction_b200/build.py` "
                     "(there is no CPU fallback)")
             lib = C.CDLL(LIB_PATH)
             for name, (res, args) in PROTOTYPES.items():
@@ -134,7 +135,11 @@ class Context:
             raise LlfeError(rc, self.lib.llfe_last_error().decode())
 
     def set_stream(self, cuda_stream: int | None):
+        """cuda_stream: a cudaStream_t as int; 0 / None = the legacy default stream."""
         self.call("llfe_set_stream", cuda_stream or None)
+
+    def use_own_stream(self):
+        self.call("llfe_use_own_stream")
 
     def sync(self):
         self.call("llfe_sync")

@@ -1,6 +1,6 @@
 """Build libllfe.so (sm_100a only) in-tree with nvcc.
 
-    python -m low_level_feature_extraction_b200.build [--force]
+    python low_level_feature_extraction_b200/build.py [--force]
 
 nvcc cross-compiles without a GPU.  Objects go to csrc/build/, the shared
 library next to this file so that it travels with the repo snapshot.

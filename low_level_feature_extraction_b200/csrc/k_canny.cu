@@ -225,7 +225,7 @@ __global__ void __launch_bounds__(HTHREADS) k_hyst_finish(const uint32_t* __rest
     const size_t plane = (size_t)h * wpr;
     const uint32_t* pw = weak + img * plane;
     uint32_t* pe = edges + img * plane;
-    uint32_t* f = flags + (size_t)img * nstrips;
+    volatile uint32_t* f = flags + (size_t)img * nstrips;
     uint32_t* sw = sm;
     uint32_t* se = sm + HROWS * wpr;
     __shared__ int s_flag;

@@ -122,7 +122,13 @@ int llfe_destroy(llfe_ctx* ctx) {
 
 int llfe_set_stream(llfe_ctx* ctx, void* cuda_stream) {
     LLFE_CHECK_ARG(ctx != nullptr);
-    ctx->stream = cuda_stream ? (cudaStream_t)cuda_stream : ctx->own_stream;
+    ctx->stream = (cudaStream_t)cuda_stream;
+    return LLFE_OK;
+}
+
+int llfe_use_own_stream(llfe_ctx* ctx) {
+    LLFE_CHECK_ARG(ctx != nullptr);
+    ctx->stream = ctx->own_stream;
     return LLFE_OK;
 }
 
