@@ -61,6 +61,11 @@ int llfe_sync(llfe_ctx* ctx);
 /* Number of kernels this context has launched so far (for accounting). */
 uint64_t llfe_launch_count(llfe_ctx* ctx);
 int llfe_sm_count(llfe_ctx* ctx);
+/* Per-kernel timing with CUDA events on the context's stream.  Between begin and
+ * end every kernel launch is bracketed by an event pair; end synchronises and
+ * writes {"kernel name": {"ms": total, "launches": count}, ...} into json. */
+int llfe_profile_begin(llfe_ctx* ctx);
+int llfe_profile_end(llfe_ctx* ctx, char* json, size_t cap);
 
 /* ---- memory helpers (so a C / ctypes host needs no CUDA runtime) -------- */
 int llfe_malloc(llfe_ctx* ctx, size_t bytes, void** d_out);
@@ -179,10 +184,20 @@ int llfe_kmeans_lloyd(llfe_ctx* ctx, const uint32_t* d_keys, const uint32_t* d_w
 int llfe_kmeans_pixels_step(llfe_ctx* ctx, const uint8_t* d_bgr, size_t n_pixels, int k, const float* d_centers,
                             uint64_t* d_sums_counts, uint8_t* d_labels_or_null);
 
+/* Empty-cluster repair support for the per-pixel mode: among the pixels of this
+ * shard whose nearest centre (under d_centers) is `donor`, find the one farthest
+ * (float32 distance) from h_base3 = the donor's provisional mean; ties go to the
+ * highest pixel index.  *d_out = max(*d_out, ((dist bits << 32) | (index_base +
+ * local pixel index)) + 1); the caller zeroes it first and all-reduces with max. */
+int llfe_kmeans_pixels_farthest(llfe_ctx* ctx, const uint8_t* d_bgr, size_t n_pixels, int k, const float* d_centers,
+                                int donor, const float* h_base3, uint32_t index_base, uint64_t* d_out);
+
 /* Centre update + convergence test from (all-reduced) sums: c =
  * float(double(sum)/double(count)); d_state[0] = iteration counter (in/out),
- * d_state[1] = converged flag (out), d_state[2] = number of empty clusters (out).
- * d_shift receives max_k |c - old|^2 (double). */
+ * d_state[1] = converged flag (out), d_state[2] = number of empty clusters (out; when
+ * it is non-zero nothing else is updated: repair the sums, then call again).
+ * d_shift receives max_k |c - old|^2 (double).  The first call (iteration 0) never
+ * reports convergence, as in cv2's KMEANS_USE_INITIAL_LABELS mode. */
 int llfe_kmeans_update(llfe_ctx* ctx, int k, const uint64_t* d_sums_counts, float* d_centers, int max_iter,
                        double eps, int32_t* d_state, double* d_shift);
 

@@ -36,6 +36,8 @@ PROTOTYPES = {
     "llfe_sync": (i32, [vp]),
     "llfe_launch_count": (u64, [vp]),
     "llfe_sm_count": (i32, [vp]),
+    "llfe_profile_begin": (i32, [vp]),
+    "llfe_profile_end": (i32, [vp, C.c_char_p, sz]),
     "llfe_malloc": (i32, [vp, sz, C.POINTER(vp)]),
     "llfe_free": (i32, [vp, vp]),
     "llfe_malloc_host": (i32, [vp, sz, C.POINTER(vp)]),
@@ -61,6 +63,7 @@ PROTOTYPES = {
     "llfe_kmeans_unique": (i32, [vp, vp, vp, i32, i32, i32, i32, i32, f64, vp, vp, vp, vp, vp]),
     "llfe_kmeans_lloyd": (i32, [vp, vp, vp, vp, i32, i32, i32, i32, f64, i32, vp, vp, vp, vp, vp]),
     "llfe_kmeans_pixels_step": (i32, [vp, vp, sz, i32, vp, vp, vp]),
+    "llfe_kmeans_pixels_farthest": (i32, [vp, vp, sz, i32, vp, i32, vp, C.c_uint32, vp]),
     "llfe_kmeans_update": (i32, [vp, i32, vp, vp, i32, f64, vp, vp]),
     "llfe_pipeline": (i32, [vp, vp, i32, i32, i32, i32, i32, vp, vp, vp, vp, u64, vp, vp, i32]),
     "llfe_shape_mask_host": (i32, [vp, vp, i32, i32, i32, i32, vp]),
@@ -143,6 +146,18 @@ class Context:
 
     def sync(self):
         self.call("llfe_sync")
+
+    def profile_begin(self):
+        self.call("llfe_profile_begin")
+
+    def profile_end(self) -> dict:
+        import json
+
+        buf = C.create_string_buffer(1 << 14)
+        rc = self.lib.llfe_profile_end(self.handle, buf, len(buf))
+        if rc != LLFE_OK:
+            raise LlfeError(rc, self.lib.llfe_last_error().decode())
+        return json.loads(buf.value.decode())
 
     @property
     def launches(self) -> int:

@@ -83,6 +83,7 @@ __global__ void __launch_bounds__(256) k_blur5(const uint8_t* __restrict__ src, 
 int launch_blur5(llfe_ctx* ctx, const uint8_t* src, int n, int h, int w, int c, uint8_t* dst) {
     if (n == 0 || h == 0 || w == 0) return LLFE_OK;
     dim3 grid(ceil_div(w * c, TWB), ceil_div(h, TH), n);
+    LLFE_KERNEL(ctx, "k_blur5");
     k_blur5<false><<<grid, 256, 0, ctx->stream>>>(src, dst, h, w, c);
     LLFE_LAUNCHED(ctx);
     return LLFE_OK;
@@ -91,6 +92,7 @@ int launch_blur5(llfe_ctx* ctx, const uint8_t* src, int n, int h, int w, int c, 
 int launch_gray_blur5(llfe_ctx* ctx, const uint8_t* bgr, int n, int h, int w, uint8_t* dst) {
     if (n == 0 || h == 0 || w == 0) return LLFE_OK;
     dim3 grid(ceil_div(w, TWB), ceil_div(h, TH), n);
+    LLFE_KERNEL(ctx, "k_gray_blur5");
     k_blur5<true><<<grid, 256, 0, ctx->stream>>>(bgr, dst, h, w, 1);
     LLFE_LAUNCHED(ctx);
     return LLFE_OK;

@@ -343,6 +343,7 @@ int launch_canny_front(llfe_ctx* ctx, const uint8_t* gray, int n, int h, int w, 
                        uint32_t* strong) {
     if (n == 0 || h == 0 || w == 0) return LLFE_OK;
     dim3 grid(ceil_div(w, FTW), ceil_div(h, FTH), n);
+    LLFE_KERNEL(ctx, "k_canny_front");
     k_canny_front<<<grid, 256, 0, ctx->stream>>>(gray, h, w, low, high, weak, strong);
     LLFE_LAUNCHED(ctx);
     return LLFE_OK;
@@ -368,8 +369,10 @@ int launch_hysteresis(llfe_ctx* ctx, const uint32_t* weak, uint32_t* edges, int 
         attr_set = true;
     }
     LLFE_CUDA(cudaMemsetAsync(flags, 0, hysteresis_flag_words(n, h) * sizeof(uint32_t), ctx->stream));
+    LLFE_KERNEL(ctx, "k_hyst_strips");
     k_hyst_strips<<<dim3(nstrips, n), HTHREADS, smem, ctx->stream>>>(weak, edges, h, wpr, nstrips, flags);
     LLFE_LAUNCHED(ctx);
+    LLFE_KERNEL(ctx, "k_hyst_finish");
     k_hyst_finish<<<n, HTHREADS, smem, ctx->stream>>>(weak, edges, h, wpr, nstrips, flags);
     LLFE_LAUNCHED(ctx);
     return LLFE_OK;
@@ -380,6 +383,7 @@ int launch_plane_to_mask(llfe_ctx* ctx, const uint32_t* plane, int n, int h, int
     const int wpr = plane_wpr(w);
     int aligned = (w % 16 == 0) && ((uintptr_t)mask % 16 == 0);
     dim3 grid(ceil_div(2 * wpr, 256), h, n);
+    LLFE_KERNEL(ctx, dilate ? "k_plane_to_mask_dilate" : "k_plane_to_mask");
     if (dilate)
         k_plane_to_mask<true><<<grid, 256, 0, ctx->stream>>>(plane, h, w, wpr, mask, aligned);
     else
@@ -391,6 +395,7 @@ int launch_plane_to_mask(llfe_ctx* ctx, const uint32_t* plane, int n, int h, int
 int launch_dilate3_u8(llfe_ctx* ctx, const uint8_t* src, int n, int h, int w, uint8_t* dst) {
     if (n == 0 || h == 0 || w == 0) return LLFE_OK;
     dim3 grid(ceil_div(w, 256), h, n);
+    LLFE_KERNEL(ctx, "k_dilate3_u8");
     k_dilate3_u8<<<grid, 256, 0, ctx->stream>>>(src, h, w, dst);
     LLFE_LAUNCHED(ctx);
     return LLFE_OK;

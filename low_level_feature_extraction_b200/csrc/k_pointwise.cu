@@ -31,12 +31,14 @@ int launch_bgr2gray(llfe_ctx* ctx, const uint8_t* bgr, size_t npix, uint8_t* gra
     size_t nvec = 0;
     if (((uintptr_t)bgr % 16 == 0) && ((uintptr_t)gray % 16 == 0)) nvec = npix / 16;
     if (nvec) {
+        LLFE_KERNEL(ctx, "k_bgr2gray_vec");
         k_bgr2gray_vec<<<(unsigned)ceil_div_sz(nvec, 256), 256, 0, ctx->stream>>>((const uint4*)bgr, (uint4*)gray, nvec);
         LLFE_LAUNCHED(ctx);
     }
     size_t done = nvec * 16;
     if (done < npix) {
         size_t rest = npix - done;
+        LLFE_KERNEL(ctx, "k_bgr2gray_scalar");
         k_bgr2gray_scalar<<<(unsigned)ceil_div_sz(rest, 256), 256, 0, ctx->stream>>>(bgr, gray, done, npix);
         LLFE_LAUNCHED(ctx);
     }
@@ -71,12 +73,14 @@ int launch_bgr2rgb(llfe_ctx* ctx, const uint8_t* bgr, size_t npix, uint8_t* rgb)
     size_t nvec = 0;
     if (((uintptr_t)bgr % 4 == 0) && ((uintptr_t)rgb % 4 == 0)) nvec = npix / 4;
     if (nvec) {
+        LLFE_KERNEL(ctx, "k_bgr2rgb_vec");
         k_bgr2rgb_vec<<<(unsigned)ceil_div_sz(nvec, 256), 256, 0, ctx->stream>>>((const uint32_t*)bgr, (uint32_t*)rgb,
                                                                                 nvec);
         LLFE_LAUNCHED(ctx);
     }
     size_t done = nvec * 4;
     if (done < npix) {
+        LLFE_KERNEL(ctx, "k_bgr2rgb_scalar");
         k_bgr2rgb_scalar<<<(unsigned)ceil_div_sz(npix - done, 256), 256, 0, ctx->stream>>>(bgr, rgb, done, npix);
         LLFE_LAUNCHED(ctx);
     }
@@ -122,6 +126,7 @@ int launch_lut2(llfe_ctx* ctx, const uint8_t* src, size_t count, float a1, float
     if (count == 0) return LLFE_OK;
     size_t want = ceil_div_sz(count, 16 * 256);
     unsigned grid = (unsigned)(want < (size_t)ctx->sm_count * 16 ? (want ? want : 1) : (size_t)ctx->sm_count * 16);
+    LLFE_KERNEL(ctx, "k_lut2");
     k_lut2<<<grid, 256, 0, ctx->stream>>>(src, count, a1, a2, single, dst);
     LLFE_LAUNCHED(ctx);
     return LLFE_OK;

@@ -190,6 +190,7 @@ extern "C" int llfe_resize_area(llfe_ctx* ctx, const uint8_t* d_src, int n, int 
     const bool fast = fabs(scale_x - isx) < 2.220446049250313e-16 && fabs(scale_y - isy) < 2.220446049250313e-16;
     dim3 grid(ceil_div(dw, 256), dh, n);
     if (fast) {
+        LLFE_KERNEL(ctx, "k_resize_area_int");
         if (c == 3)
             k_resize_area_int<3><<<grid, 256, 0, ctx->stream>>>(d_src, sh, sw, d_dst, dh, dw, isx, isy);
         else
@@ -200,6 +201,7 @@ extern "C" int llfe_resize_area(llfe_ctx* ctx, const uint8_t* d_src, int n, int 
     AreaTab *xt, *yt;
     LLFE_TRY(get_tab(ctx, sw, dw, &xt));
     LLFE_TRY(get_tab(ctx, sh, dh, &yt));
+    LLFE_KERNEL(ctx, "k_resize_area_tab");
     if (c == 3)
         k_resize_area_tab<3><<<grid, 256, 0, ctx->stream>>>(d_src, sh, sw, d_dst, dh, dw, xt->d_ofs, xt->d_idx, xt->d_w,
                                                             yt->d_ofs, yt->d_idx, yt->d_w);

@@ -201,6 +201,7 @@ int launch_adaptive(llfe_ctx* ctx, const uint8_t* gray, int n, int h, int w, int
     if (n == 0 || h == 0 || w == 0) return LLFE_OK;
     if (sum_count) LLFE_CUDA(cudaMemsetAsync(sum_count, 0, (size_t)n * 2 * sizeof(uint64_t), ctx->stream));
     dim3 grid(ceil_div(w, ATW), ceil_div(h, ATH), n);
+    LLFE_KERNEL(ctx, "k_adaptive");
     k_adaptive<<<grid, 256, 0, ctx->stream>>>(gray, h, w, C, mask, (unsigned long long*)sum_count);
     LLFE_LAUNCHED(ctx);
     return LLFE_OK;
@@ -211,6 +212,7 @@ int launch_hist256(llfe_ctx* ctx, const uint8_t* gray, int n, size_t npix, uint3
     if (n == 0 || npix == 0) return LLFE_OK;
     size_t want = ceil_div_sz(npix, 16 * 256 * 4);
     unsigned gx = (unsigned)(want < 1 ? 1 : (want > 1024 ? 1024 : want));
+    LLFE_KERNEL(ctx, "k_hist256");
     k_hist256<<<dim3(gx, n), 256, 0, ctx->stream>>>(gray, npix, hist);
     LLFE_LAUNCHED(ctx);
     return LLFE_OK;
@@ -219,6 +221,7 @@ int launch_hist256(llfe_ctx* ctx, const uint8_t* gray, int n, size_t npix, uint3
 int launch_otsu_sweep(llfe_ctx* ctx, const uint32_t* hist, int n, size_t npix, int invert_if_light, int32_t* thresh,
                       int32_t* invert) {
     if (n == 0) return LLFE_OK;
+    LLFE_KERNEL(ctx, "k_otsu_sweep");
     k_otsu_sweep<<<ceil_div(n, 64), 64, 0, ctx->stream>>>(hist, n, npix, invert_if_light, thresh, invert);
     LLFE_LAUNCHED(ctx);
     return LLFE_OK;
@@ -229,6 +232,7 @@ int launch_binarize(llfe_ctx* ctx, const uint8_t* gray, int n, size_t npix, cons
     if (n == 0 || npix == 0) return LLFE_OK;
     size_t want = ceil_div_sz(npix, 16 * 256 * 2);
     unsigned gx = (unsigned)(want < 1 ? 1 : (want > 2048 ? 2048 : want));
+    LLFE_KERNEL(ctx, "k_binarize");
     k_binarize<<<dim3(gx, n), 256, 0, ctx->stream>>>(gray, npix, thresh, invert, mask);
     LLFE_LAUNCHED(ctx);
     return LLFE_OK;

@@ -38,6 +38,25 @@ int llfe_workspace(llfe_ctx* ctx, size_t bytes, void** out) {
     return LLFE_OK;
 }
 
+// ---- per-kernel CUDA-event timing ---------------------------------------------------
+void llfe_prof_mark(llfe_ctx* ctx, const char* name) {
+    if (!ctx->prof_on || ctx->prof_used >= ctx->prof_cap) return;
+    int i = ctx->prof_used;
+    if (i >= ctx->prof_events) {
+        if (cudaEventCreate(&ctx->prof[i].a) != cudaSuccess || cudaEventCreate(&ctx->prof[i].b) != cudaSuccess) return;
+        ctx->prof_events = i + 1;
+    }
+    ctx->prof[i].name = name;
+    cudaEventRecord(ctx->prof[i].a, ctx->stream);
+    ctx->prof_pending = i;
+    ctx->prof_used = i + 1;
+}
+
+void llfe_prof_stop(llfe_ctx* ctx) {
+    if (ctx->prof_pending >= 0) cudaEventRecord(ctx->prof[ctx->prof_pending].b, ctx->stream);
+    ctx->prof_pending = -1;
+}
+
 static int ensure_stage(llfe_ctx* ctx, size_t pin_bytes, size_t dev_bytes) {
     if (pin_bytes > ctx->pin_bytes) {
         LLFE_CUDA(cudaStreamSynchronize(ctx->stream));
@@ -115,6 +134,13 @@ int llfe_destroy(llfe_ctx* ctx) {
     if (ctx->pin) cudaFreeHost(ctx->pin);
     if (ctx->dev_stage) cudaFree(ctx->dev_stage);
     llfe_free_area_tabs(ctx);
+    if (ctx->prof) {
+        for (int i = 0; i < ctx->prof_events; ++i) {
+            cudaEventDestroy(ctx->prof[i].a);
+            cudaEventDestroy(ctx->prof[i].b);
+        }
+        delete[] ctx->prof;
+    }
     if (ctx->own_stream) cudaStreamDestroy(ctx->own_stream);
     delete ctx;
     return LLFE_OK;
@@ -135,6 +161,55 @@ int llfe_use_own_stream(llfe_ctx* ctx) {
 int llfe_sync(llfe_ctx* ctx) {
     LLFE_CHECK_ARG(ctx != nullptr);
     LLFE_CUDA(cudaStreamSynchronize(ctx->stream));
+    return LLFE_OK;
+}
+
+int llfe_profile_begin(llfe_ctx* ctx) {
+    LLFE_CHECK_ARG(ctx != nullptr);
+    if (!ctx->prof) {
+        ctx->prof_cap = 1 << 16;
+        ctx->prof = new (std::nothrow) ProfRec[ctx->prof_cap];
+        if (!ctx->prof) return LLFE_E_NOMEM;
+    }
+    ctx->prof_used = 0;
+    ctx->prof_pending = -1;
+    ctx->prof_on = true;
+    return LLFE_OK;
+}
+
+int llfe_profile_end(llfe_ctx* ctx, char* json, size_t cap) {
+    LLFE_CHECK_ARG(ctx != nullptr && json != nullptr && cap >= 64);
+    ctx->prof_on = false;
+    LLFE_CUDA(cudaStreamSynchronize(ctx->stream));
+    // aggregate by name (names are string literals: compare by content, few distinct)
+    struct Agg {
+        const char* name;
+        double ms;
+        long n;
+    } agg[64];
+    int na = 0;
+    for (int i = 0; i < ctx->prof_used; ++i) {
+        float ms = 0.f;
+        if (cudaEventElapsedTime(&ms, ctx->prof[i].a, ctx->prof[i].b) != cudaSuccess) {
+            cudaGetLastError();
+            continue;
+        }
+        int k = 0;
+        for (; k < na; ++k)
+            if (strcmp(agg[k].name, ctx->prof[i].name) == 0) break;
+        if (k == na) {
+            if (na == 64) continue;
+            agg[na++] = {ctx->prof[i].name, 0.0, 0};
+        }
+        agg[k].ms += ms;
+        agg[k].n += 1;
+    }
+    size_t off = 0;
+    off += snprintf(json + off, cap - off, "{");
+    for (int k = 0; k < na && off + 96 < cap; ++k)
+        off += snprintf(json + off, cap - off, "%s\"%s\": {\"ms\": %.6f, \"launches\": %ld}", k ? ", " : "", agg[k].name,
+                        agg[k].ms, agg[k].n);
+    snprintf(json + off, cap - off, "}");
     return LLFE_OK;
 }
 
@@ -328,6 +403,20 @@ int llfe_text_mask(llfe_ctx* ctx, const uint8_t* d_bgr, int n, int h, int w, uin
     uint8_t* gray = (uint8_t*)ws;
     LLFE_TRY(launch_bgr2gray(ctx, d_bgr, (size_t)n * h * w, gray));
     return otsu_impl(ctx, gray, n, (size_t)h * w, 1, d_mask, d_thresh, (char*)ws + img);
+}
+
+// ---- fused service pipeline ------------------------------------------------------
+int llfe_pipeline(llfe_ctx* ctx, const uint8_t* d_bgr, int n, int h, int w, int low, int high, uint8_t* d_shape_mask,
+                  uint8_t* d_shadow_mask, uint64_t* d_shadow_sum_count, const int8_t* d_noise, uint64_t seed,
+                  uint32_t* d_keys, int32_t* d_count, int max_unique) {
+    LLFE_IMG_ARGS(d_bgr);
+    LLFE_CHECK_ARG(h > 0 && w > 0);
+    LLFE_CHECK_ARG(d_keys == nullptr || (d_count != nullptr && max_unique > 0));
+    if (n == 0) return LLFE_OK;
+    if (d_shape_mask) LLFE_TRY(llfe_shape_mask(ctx, d_bgr, n, h, w, low, high, d_shape_mask));
+    if (d_shadow_mask) LLFE_TRY(llfe_shadow_mask(ctx, d_bgr, n, h, w, d_shadow_mask, nullptr, d_shadow_sum_count));
+    if (d_keys) LLFE_TRY(launch_unique_colors(ctx, d_bgr, n, h, w, d_noise, seed, d_keys, nullptr, d_count, max_unique));
+    return LLFE_OK;
 }
 
 // ---- host-buffer convenience entry points ----------------------------------------

@@ -24,7 +24,23 @@ struct llfe_ctx {
     // INTER_AREA tables cached per (ssize, dsize)
     struct AreaTab* area_tabs = nullptr;
     uint64_t launches = 0;
+    // optional per-kernel CUDA-event timing (llfe_profile_begin / llfe_profile_end)
+    struct ProfRec* prof = nullptr;
+    int prof_cap = 0, prof_used = 0, prof_events = 0, prof_pending = -1;
+    bool prof_on = false;
 };
+
+struct ProfRec {
+    const char* name;
+    cudaEvent_t a, b;
+};
+void llfe_prof_mark(llfe_ctx* ctx, const char* name);
+void llfe_prof_stop(llfe_ctx* ctx);
+// put right before a kernel launch; LLFE_LAUNCHED closes the interval
+#define LLFE_KERNEL(ctx, name)                        \
+    do {                                              \
+        if ((ctx)->prof_on) llfe_prof_mark(ctx, name); \
+    } while (0)
 
 void llfe_set_error(const char* fmt, ...);
 int llfe_cuda_fail(cudaError_t e, const char* what, const char* file, int line);
@@ -53,6 +69,7 @@ int llfe_cuda_fail(cudaError_t e, const char* what, const char* file, int line);
 #define LLFE_LAUNCHED(ctx)                      \
     do {                                        \
         (ctx)->launches++;                      \
+        if ((ctx)->prof_pending >= 0) llfe_prof_stop(ctx); \
         LLFE_CUDA(cudaPeekAtLastError());       \
     } while (0)
 
@@ -102,3 +119,5 @@ int launch_binarize(llfe_ctx* ctx, const uint8_t* gray, int n, size_t npix_per_i
 size_t hysteresis_flag_words(int n, int h);
 int launch_dilate3_u8(llfe_ctx* ctx, const uint8_t* src, int n, int h, int w, uint8_t* dst);
 void llfe_free_area_tabs(llfe_ctx* ctx);
+int launch_unique_colors(llfe_ctx* ctx, const uint8_t* d_bgr, int n, int h, int w, const int8_t* d_noise, uint64_t seed,
+                         uint32_t* d_keys, uint32_t* d_hist, int32_t* d_count, int max_unique);

@@ -205,3 +205,121 @@ class Engine:
         self._bind()
         self.ctx.call("llfe_resize_area", x, n, sh, sw, c, out, int(dh), int(dw))
         return out[0] if single else out
+
+    # -- palette ------------------------------------------------------------------
+    def unique_colors(self, bgr: torch.Tensor, noise: torch.Tensor | None = None, seed: int = 0,
+                      max_unique: int = 1 << 16, with_counts: bool = False):
+        """np.unique(noised RGB pixels, axis=0) per image.
+
+        noise: int8 (n,h,w,3) tensor in RGB order (the reference's
+        `np.random.normal(0, 0.5, pixels.shape).astype(np.int8)`), or None to
+        generate noise of the same distribution on the device from `seed`.
+        -> (keys uint32-as-int32 (n,max_unique) = R<<16|G<<8|B ascending,
+            count int32 (n,)[, pixel counts int32 (n,max_unique)])."""
+        x, single = _batch(bgr, 3)
+        n, h, w, _ = x.shape
+        if noise is not None:
+            if noise.dtype != torch.int8 or noise.numel() != x.numel():
+                raise ValueError("noise must be int8 with the shape of the image batch")
+            noise = noise.contiguous()
+        keys = self._empty((n, max_unique), torch.int32)
+        count = self._empty((n,), torch.int32)
+        hist = self._empty((n, max_unique), torch.int32) if with_counts else None
+        self._bind()
+        self.ctx.call("llfe_unique_colors", x, n, h, w, noise, int(seed) & 0xFFFFFFFFFFFFFFFF, keys, hist, count,
+                      int(max_unique))
+        res = (keys, count, hist) if with_counts else (keys, count)
+        return tuple(t[0] for t in res) if single else res
+
+    def kmeans_unique(self, keys: torch.Tensor, count: torch.Tensor, k: int, rng_state, attempts: int = 10,
+                      max_iter: int = 200, eps: float = 0.2):
+        """cv2.kmeans(float32(unique), k, None, (EPS+MAX_ITER, max_iter, eps), attempts, KMEANS_PP_CENTERS)
+        per image.  rng_state: int or sequence of ints (cv::RNG state; cv2.setRNGSeed(s) => s).
+        -> (centers float32 (n,k,3) RGB, labels int32 (n,max_unique), compactness float64 (n,), k_used int32 (n,))."""
+        if keys.dim() == 1:
+            keys, count = keys.unsqueeze(0), count.reshape(1)
+        n, max_unique = keys.shape
+        states = [rng_state] * n if isinstance(rng_state, int) else list(rng_state)
+        rs = torch.tensor([int(s) & 0xFFFFFFFFFFFFFFFF for s in states], dtype=torch.uint64).view(torch.int64).to(self.device)
+        centers = torch.zeros((n, k, 3), dtype=torch.float32, device=self.device)
+        labels = self._empty((n, max_unique), torch.int32)
+        comp = self._empty((n,), torch.float64)
+        kused = self._empty((n,), torch.int32)
+        self._bind()
+        self.ctx.call("llfe_kmeans_unique", keys.contiguous(), count.contiguous(), n, max_unique, int(k), int(attempts),
+                      int(max_iter), float(eps), rs, centers, labels, comp, kused)
+        return centers, labels, comp, kused
+
+    def kmeans_lloyd(self, keys: torch.Tensor, count: torch.Tensor, init_centers: torch.Tensor,
+                     weights: torch.Tensor | None = None, exact_sums: bool = False, max_iter: int = 200,
+                     eps: float = 0.2):
+        """Lloyd from given centres over (optionally weighted) colour lists.
+        -> (centers (n,k,3) f32, labels int32 (n,max_unique), iters int32 (n,), sums_counts int64 (n,k,4))."""
+        if keys.dim() == 1:
+            keys, count = keys.unsqueeze(0), count.reshape(1)
+            init_centers = init_centers.unsqueeze(0)
+            if weights is not None:
+                weights = weights.unsqueeze(0)
+        n, max_unique = keys.shape
+        k = init_centers.shape[1]
+        init = init_centers.to(device=self.device, dtype=torch.float32).contiguous()
+        centers = torch.zeros((n, k, 3), dtype=torch.float32, device=self.device)
+        labels = self._empty((n, max_unique), torch.int32)
+        iters = self._empty((n,), torch.int32)
+        sums = torch.zeros((n, k, 4), dtype=torch.int64, device=self.device)
+        self._bind()
+        self.ctx.call("llfe_kmeans_lloyd", keys.contiguous(), weights.contiguous() if weights is not None else None,
+                      count.contiguous(), n, max_unique, k, int(max_iter), float(eps), 1 if exact_sums else 0, init,
+                      centers, labels, iters, sums)
+        return centers, labels, iters, sums
+
+    # -- per-pixel k-means building blocks (row shard of one image) ---------------
+    def kmeans_pixels_step(self, bgr_rows: torch.Tensor, centers: torch.Tensor, sums: torch.Tensor,
+                           labels: torch.Tensor | None = None):
+        """sums (k,4) int64 += exact {sum R, sum G, sum B, count} per cluster over the pixels of bgr_rows."""
+        x = bgr_rows.contiguous()
+        npix = x.numel() // 3
+        k = centers.shape[0]
+        self._bind()
+        self.ctx.call("llfe_kmeans_pixels_step", x, npix, k, centers, sums, labels)
+
+    def kmeans_update(self, sums: torch.Tensor, centers: torch.Tensor, state: torch.Tensor, shift: torch.Tensor,
+                      max_iter: int = 200, eps: float = 0.2):
+        self._bind()
+        self.ctx.call("llfe_kmeans_update", centers.shape[0], sums, centers, int(max_iter), float(eps), state, shift)
+
+    def kmeans_pixels_farthest(self, bgr_rows: torch.Tensor, centers: torch.Tensor, donor: int, base3,
+                               index_base: int, out: torch.Tensor):
+        import ctypes
+
+        x = bgr_rows.contiguous()
+        arr = (ctypes.c_float * 3)(*[float(v) for v in base3])
+        self._bind()
+        self.ctx.call("llfe_kmeans_pixels_farthest", x, x.numel() // 3, centers.shape[0], centers, int(donor),
+                      ctypes.addressof(arr), int(index_base), out)
+
+    # -- fused pipeline -------------------------------------------------------------
+    def pipeline(self, bgr: torch.Tensor, shapes: bool = True, shadows: bool = True, colors: bool = True,
+                 noise: torch.Tensor | None = None, seed: int = 0, max_unique: int = 1 << 16, low: int = 50,
+                 high: int = 150, out: dict | None = None) -> dict:
+        """colours + shapes + shadows from one batch: returns a dict with
+        shape_mask, shadow_mask, shadow_sums, keys, count (device tensors)."""
+        x, _ = _batch(bgr, 3)
+        n, h, w, _ = x.shape
+        out = {} if out is None else out
+        if shapes and "shape_mask" not in out:
+            out["shape_mask"] = self._empty((n, h, w))
+        if shadows and "shadow_mask" not in out:
+            out["shadow_mask"] = self._empty((n, h, w))
+            out["shadow_sums"] = self._empty((n, 2), torch.int64)
+        if colors and "keys" not in out:
+            out["keys"] = self._empty((n, max_unique), torch.int32)
+            out["count"] = self._empty((n,), torch.int32)
+        if noise is not None:
+            noise = noise.contiguous()
+        self._bind()
+        self.ctx.call("llfe_pipeline", x, n, h, w, int(low), int(high), out.get("shape_mask") if shapes else None,
+                      out.get("shadow_mask") if shadows else None, out.get("shadow_sums") if shadows else None,
+                      noise, int(seed) & 0xFFFFFFFFFFFFFFFF, out.get("keys") if colors else None,
+                      out.get("count") if colors else None, int(max_unique))
+        return out

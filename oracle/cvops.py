@@ -465,10 +465,19 @@ def _sums_f32_sequential(data: np.ndarray, labels: np.ndarray, k: int):
     return c, cnt
 
 
-def centers_update_cv(data: np.ndarray, labels: np.ndarray, k: int):
+def center_shift(centers: np.ndarray, old: np.ndarray) -> float:
+    """max_k sum_j t^2 with t = float32(c - old) widened to double (OpenCV:
+    `double t = center[j] - old_center[j]` on float operands)."""
+    t = (centers.astype(f32) - old.astype(f32)).astype(f32).astype(np.float64)
+    return float((t * t).sum(1).max())
+
+
+def centers_update_cv(data: np.ndarray, labels: np.ndarray, k: int, old: np.ndarray | None = None):
     """One cv2.kmeans centre update INCLUDING the empty-cluster repair:
     f32 sequential sums in index order, repair, then sum * f32(1/count).
-    Returns (centers f32, labels possibly modified by the repair)."""
+    Returns (centers f32, labels possibly modified by the repair).  As in
+    OpenCV, a repair overwrites the donor cluster's row of `old` (in place)
+    with its provisional mean, which the following shift test then sees."""
     labels = labels.copy()
     c, cnt = _sums_f32_sequential(data, labels, k)
     for j in range(k):
@@ -479,6 +488,8 @@ def centers_update_cv(data: np.ndarray, labels: np.ndarray, k: int):
             if cnt[max_k] < cnt[k1]:
                 max_k = k1
         base = (c[max_k] * f32(f32(1.0) / f32(cnt[max_k]))).astype(f32)
+        if old is not None:
+            old[max_k] = base
         members = np.flatnonzero(labels == max_k)
         d = l2sqr(data[members], base)
         far = int(members[len(d) - 1 - int(np.argmax(d[::-1]))])  # last max wins ('<=')
@@ -491,7 +502,8 @@ def centers_update_cv(data: np.ndarray, labels: np.ndarray, k: int):
     return centers, labels
 
 
-def centers_update_exact(data_int: np.ndarray, labels: np.ndarray, k: int, weights: np.ndarray | None = None):
+def centers_update_exact(data_int: np.ndarray, labels: np.ndarray, k: int, weights: np.ndarray | None = None,
+                         old: np.ndarray | None = None):
     """The pinned exact-sum rule of SURVEY.md A.8: integer sums,
     c = float32(double(sum) / double(count)).  Empty-cluster repair follows
     cv2's rule (biggest cluster, farthest member, last max wins) and moves ONE
@@ -513,6 +525,8 @@ def centers_update_exact(data_int: np.ndarray, labels: np.ndarray, k: int, weigh
             if cnt[max_k] < cnt[k1]:
                 max_k = k1
         base = (sums[max_k].astype(np.float64) / float(cnt[max_k])).astype(f32)
+        if old is not None:
+            old[max_k] = base
         members = np.flatnonzero(labels == max_k)
         d = l2sqr(data_int[members].astype(f32), base)
         far = int(members[len(d) - 1 - int(np.argmax(d[::-1]))])
@@ -537,9 +551,9 @@ def lloyd_cv(data: np.ndarray, init_centers: np.ndarray, max_iter: int = 200, ep
     centers = np.zeros_like(init_centers, dtype=f32)
     it = 0
     while True:
-        old = centers
-        centers, labels = centers_update_cv(data, labels, k)
-        shift = np.inf if it == 0 else float(((centers.astype(np.float64) - old.astype(np.float64)) ** 2).sum(1).max())
+        old = centers.copy()
+        centers, labels = centers_update_cv(data, labels, k, old)
+        shift = np.inf if it == 0 else center_shift(centers, old)
         it += 1
         if it == max(max_iter, 2) or shift <= eps2:
             _, d = assign(data, centers)
@@ -562,9 +576,9 @@ def lloyd_exact(data_u8: np.ndarray, init_centers: np.ndarray, max_iter: int = 2
     centers = np.zeros((k, data_u8.shape[1]), f32)
     it = 0
     while True:
-        old = centers
-        centers, labels, sums, cnt = centers_update_exact(data_u8, labels, k, weights)
-        shift = np.inf if it == 0 else float(((centers.astype(np.float64) - old.astype(np.float64)) ** 2).sum(1).max())
+        old = centers.copy()
+        centers, labels, sums, cnt = centers_update_exact(data_u8, labels, k, weights, old)
+        shift = np.inf if it == 0 else center_shift(centers, old)
         it += 1
         if it == max(max_iter, 2) or shift <= eps2:
             return centers, labels, it, sums, cnt
@@ -581,9 +595,9 @@ def cv_kmeans(data: np.ndarray, k: int, rng: CvRNG, attempts: int = 10, max_iter
         it = 1  # iteration 0 generated the centres (shift = DBL_MAX, never last)
         labels, _ = assign(data, centers)
         while True:
-            old = centers
-            centers, labels = centers_update_cv(data, labels, k)
-            shift = float(((centers.astype(np.float64) - old.astype(np.float64)) ** 2).sum(1).max())
+            old = centers.copy()
+            centers, labels = centers_update_cv(data, labels, k, old)
+            shift = center_shift(centers, old)
             it += 1
             if it == max(max_iter, 2) or shift <= eps2:
                 _, d = assign(data, centers)
