@@ -160,11 +160,13 @@ int llfe_unique_colors(llfe_ctx* ctx, const uint8_t* d_bgr, int n, int h, int w,
  * rng_state[i] is the cv::RNG state the reference would start image i with
  * (cv2.setRNGSeed(s) => s, 0 => 0xffffffff).  Outputs per image: centers (k x 3
  * float32, RGB), labels (int32 per unique colour), compactness (double), and
- * k_used = min(k, n_unique).  Images with fewer than 2 unique colours follow
- * color_extractor.py:185-186 (centers = the colours, labels = 0). */
+ * k_used = min(k, n_unique), and cluster_sizes (k int32: unique colours per cluster,
+ * the np.bincount(labels) of color_extractor.py:232).  Optional outputs may be NULL.
+ * Images with fewer than 2 unique colours follow color_extractor.py:185-186
+ * (centers = the colours, labels = 0). */
 int llfe_kmeans_unique(llfe_ctx* ctx, const uint32_t* d_keys, const int32_t* d_count, int n, int max_unique, int k,
                        int attempts, int max_iter, double eps, const uint64_t* d_rng_state, float* d_centers,
-                       int32_t* d_labels, double* d_compactness, int32_t* d_k_used);
+                       int32_t* d_labels, double* d_compactness, int32_t* d_k_used, int32_t* d_cluster_sizes);
 
 /* Lloyd iterations from given initial centres (the "seeded mode" of SURVEY.md
  * A.8) over weighted colours (d_weights NULL = all ones).  exact_sums = 0:
@@ -218,6 +220,16 @@ int llfe_shadow_mask_host(llfe_ctx* ctx, const uint8_t* h_bgr, int h, int w, uin
 int llfe_text_mask_host(llfe_ctx* ctx, const uint8_t* h_bgr, int h, int w, uint8_t* h_mask, int32_t* h_thresh);
 int llfe_font_mask_host(llfe_ctx* ctx, const uint8_t* h_bgr, int h, int w, uint8_t* h_mask);
 int llfe_resize_area_host(llfe_ctx* ctx, const uint8_t* h_src, int sh, int sw, int c, uint8_t* h_dst, int dh, int dw);
+int llfe_gaussian_blur5_host(llfe_ctx* ctx, const uint8_t* h_src, int h, int w, int c, uint8_t* h_dst);
+int llfe_convert_scale_abs_host(llfe_ctx* ctx, const uint8_t* h_src, size_t count, float a1, float a2, int single,
+                                uint8_t* h_dst);
+/* ColorExtractor._get_dominant_colors on one host image (color_extractor.py:151,
+ * :224-225, :173-201): BGR2RGB + noise + np.unique + cv2.kmeans.  h_noise: the int8
+ * noise tensor (h,w,3, RGB order) or NULL for device noise from `seed`.  h_centers:
+ * k*3 floats; h_labels: room for min(h*w, 2^24) int32 (n_unique are written). */
+int llfe_dominant_colors_host(llfe_ctx* ctx, const uint8_t* h_bgr, int h, int w, const int8_t* h_noise, uint64_t seed,
+                              int k, int attempts, int max_iter, double eps, uint64_t rng_state, float* h_centers,
+                              int32_t* h_labels, int32_t* h_n_unique, int32_t* h_k_used, double* h_compactness);
 
 #ifdef __cplusplus
 }

@@ -1,0 +1,128 @@
+"""Batched colours + shapes + shadows over many images (BASELINE configs 2-4).
+
+`BatchAnalyzer.run_device` works on a device-resident (B, H, W, 3) uint8 BGR batch
+and leaves every result on the device.  `run_host` is the end-to-end path: pinned
+host images in, host results out, with the host<->device copies of one chunk
+overlapping the kernels of the other (two streams, two llfe contexts because a
+context's workspace belongs to one stream at a time).
+
+Batches shard across GPUs by image index with no collective (see dist.py).
+"""
+from __future__ import annotations
+
+from dataclasses import dataclass
+
+import torch
+
+from .ops import Engine
+
+
+@dataclass
+class BatchConfig:
+    colors: bool = True
+    shapes: bool = True
+    shadows: bool = True
+    k: int = 5                 # ColorExtractor default n_colors
+    attempts: int = 10         # cv2.kmeans attempts of the reference
+    max_iter: int = 200
+    eps: float = 0.2
+    max_unique: int = 1 << 16  # capacity of the per-image unique-colour list
+    low: int = 50
+    high: int = 150
+    seed: int = 0              # device noise seed / cv::RNG state base
+    chunk: int = 32            # images per launch group (keeps scratch L2-sized)
+
+
+class BatchAnalyzer:
+    def __init__(self, device: int, h: int, w: int, cfg: BatchConfig | None = None):
+        self.cfg = cfg or BatchConfig()
+        self.h, self.w = h, w
+        self.device = torch.device("cuda", device)
+        self.engines = [Engine(device), Engine(device)]
+        self.streams = [torch.cuda.Stream(self.device), torch.cuda.Stream(self.device)]
+        self._dev_in = None
+
+    # ---- device-resident ---------------------------------------------------------------
+    def alloc_outputs(self, n: int) -> dict:
+        c, d = self.cfg, self.device
+        out = {}
+        if c.shapes:
+            out["shape_mask"] = torch.empty((n, self.h, self.w), dtype=torch.uint8, device=d)
+        if c.shadows:
+            out["shadow_mask"] = torch.empty((n, self.h, self.w), dtype=torch.uint8, device=d)
+            out["shadow_sums"] = torch.empty((n, 2), dtype=torch.int64, device=d)
+        if c.colors:
+            out["keys"] = torch.empty((n, c.max_unique), dtype=torch.int32, device=d)
+            out["count"] = torch.empty((n,), dtype=torch.int32, device=d)
+            out["centers"] = torch.zeros((n, c.k, 3), dtype=torch.float32, device=d)
+            out["labels"] = torch.empty((n, c.max_unique), dtype=torch.int32, device=d)
+            out["k_used"] = torch.empty((n,), dtype=torch.int32, device=d)
+            out["cluster_sizes"] = torch.empty((n, c.k), dtype=torch.int32, device=d)
+            out["rng"] = (torch.arange(n, dtype=torch.int64, device=d) + 1000 + c.seed)
+        return out
+
+    def run_device(self, bgr: torch.Tensor, out: dict | None = None, engine: Engine | None = None,
+                   noise: torch.Tensor | None = None) -> dict:
+        """All results stay on the device.  Asynchronous on torch's current stream."""
+        c = self.cfg
+        eng = engine or self.engines[0]
+        n = bgr.shape[0]
+        out = out if out is not None else self.alloc_outputs(n)
+        for i0 in range(0, n, c.chunk):
+            sl = slice(i0, min(n, i0 + c.chunk))
+            view = {k: v[sl] for k, v in out.items()}
+            eng.pipeline(bgr[sl], shapes=c.shapes, shadows=c.shadows, colors=c.colors,
+                         noise=None if noise is None else noise[sl], seed=c.seed + i0, max_unique=c.max_unique,
+                         low=c.low, high=c.high, out=view)
+            if c.colors:
+                eng._bind()
+                eng.ctx.call("llfe_kmeans_unique", view["keys"], view["count"], sl.stop - sl.start, c.max_unique, c.k,
+                             c.attempts, c.max_iter, float(c.eps), view["rng"], view["centers"], view["labels"], None,
+                             view["k_used"], view["cluster_sizes"])
+        return out
+
+    # ---- end to end: pinned host in, host out -------------------------------------------------
+    def alloc_host_outputs(self, n: int) -> dict:
+        c = self.cfg
+        out = {}
+        if c.shapes:
+            out["shape_mask"] = torch.empty((n, self.h, self.w), dtype=torch.uint8).pin_memory()
+        if c.shadows:
+            out["shadow_mask"] = torch.empty((n, self.h, self.w), dtype=torch.uint8).pin_memory()
+            out["shadow_sums"] = torch.empty((n, 2), dtype=torch.int64).pin_memory()
+        if c.colors:
+            out["centers"] = torch.empty((n, c.k, 3), dtype=torch.float32).pin_memory()
+            out["count"] = torch.empty((n,), dtype=torch.int32).pin_memory()
+            out["k_used"] = torch.empty((n,), dtype=torch.int32).pin_memory()
+            out["cluster_sizes"] = torch.empty((n, c.k), dtype=torch.int32).pin_memory()
+        return out
+
+    def run_host(self, images: torch.Tensor, host_out: dict | None = None) -> dict:
+        """images: pinned CPU uint8 (B, H, W, 3).  Returns host tensors; synchronous."""
+        c = self.cfg
+        n = images.shape[0]
+        host_out = host_out if host_out is not None else self.alloc_host_outputs(n)
+        if self._dev_in is None:
+            self._dev_in = [torch.empty((c.chunk, self.h, self.w, 3), dtype=torch.uint8, device=self.device) for _ in range(2)]
+            self._dev_out = [self.alloc_outputs(c.chunk) for _ in range(2)]
+            self._events = [torch.cuda.Event() for _ in range(2)]
+        bytes_in = bytes_out = 0
+        for j, i0 in enumerate(range(0, n, c.chunk)):
+            b = j & 1
+            m = min(c.chunk, n - i0)
+            st = self.streams[b]
+            with torch.cuda.stream(st):
+                din = self._dev_in[b][:m]
+                din.copy_(images[i0:i0 + m], non_blocking=True)
+                bytes_in += din.numel()
+                dout = {k: v[:m] for k, v in self._dev_out[b].items()}
+                self.run_device(din, dout, engine=self.engines[b])
+                for key in ("shape_mask", "shadow_mask", "shadow_sums", "centers", "count", "k_used", "cluster_sizes"):
+                    if key in host_out:
+                        host_out[key][i0:i0 + m].copy_(dout[key], non_blocking=True)
+                        bytes_out += dout[key].numel() * dout[key].element_size()
+        for st in self.streams:
+            st.synchronize()
+        host_out["_h2d_bytes"] = bytes_in
+        host_out["_d2h_bytes"] = bytes_out
+        return host_out

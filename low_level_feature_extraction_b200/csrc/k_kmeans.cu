@@ -336,7 +336,7 @@ __global__ void __launch_bounds__(KT) k_kmeans(KmParams P) {
 // keep the attempt with the smallest compactness (strict '<': the first wins ties)
 __global__ void __launch_bounds__(256) k_kmeans_pick(KmParams P, float* out_centers, int32_t* out_labels,
                                                      double* out_compact, int32_t* out_kused, int32_t* out_iters,
-                                                     unsigned long long* out_sums) {
+                                                     unsigned long long* out_sums, int32_t* out_sizes) {
     const int img = blockIdx.x, tid = threadIdx.x;
     const int U = min(P.count[img], P.max_unique);
     const int K = min(P.k, U);
@@ -349,6 +349,8 @@ __global__ void __launch_bounds__(256) k_kmeans_pick(KmParams P, float* out_cent
             if (out_iters) out_iters[img] = 0;
             if (U > 0) unpack(keys[0], out_centers[(size_t)img * P.k * 3], out_centers[(size_t)img * P.k * 3 + 1],
                               out_centers[(size_t)img * P.k * 3 + 2]);
+            if (out_sizes)
+                for (int i = 0; i < P.k; ++i) out_sizes[(size_t)img * P.k + i] = (i == 0) ? U : 0;
         }
         if (out_labels)
             for (int i = tid; i < U; i += 256) out_labels[(size_t)img * P.max_unique + i] = 0;
@@ -369,6 +371,9 @@ __global__ void __launch_bounds__(256) k_kmeans_pick(KmParams P, float* out_cent
         for (int i = tid; i < U; i += 256) out_labels[(size_t)img * P.max_unique + i] = P.labels[slot * P.max_unique + i];
     if (out_sums && P.sums)
         for (int i = tid; i < K * 4; i += 256) out_sums[(size_t)img * P.k * 4 + i] = P.sums[slot * KMAX * 4 + i];
+    if (out_sizes)
+        for (int i = tid; i < P.k; i += 256)
+            out_sizes[(size_t)img * P.k + i] = i < K ? (int32_t)P.sums[slot * KMAX * 4 + 4 * i + 3] : 0;
     if (tid == 0) {
         if (out_kused) out_kused[img] = K;
         if (out_compact) out_compact[img] = bc;
@@ -377,7 +382,7 @@ __global__ void __launch_bounds__(256) k_kmeans_pick(KmParams P, float* out_cent
 }
 
 int run_kmeans(llfe_ctx* ctx, KmParams P, int n, float* d_centers, int32_t* d_labels, double* d_compact, int32_t* d_kused,
-               int32_t* d_iters, uint64_t* d_sums) {
+               int32_t* d_iters, uint64_t* d_sums, int32_t* d_sizes) {
     const size_t slots = (size_t)n * P.attempts;
     const size_t need = WsCarver::need(slots * P.max_unique * 4) + WsCarver::need(slots * P.max_unique) +
                         WsCarver::need(slots * KMAX * 3 * 4) + 3 * WsCarver::need(slots * 8) +
@@ -397,7 +402,7 @@ int run_kmeans(llfe_ctx* ctx, KmParams P, int n, float* d_centers, int32_t* d_la
     LLFE_LAUNCHED(ctx);
     LLFE_KERNEL(ctx, "k_kmeans_pick");
     k_kmeans_pick<<<n, 256, 0, ctx->stream>>>(P, d_centers, d_labels, d_compact, d_kused, d_iters,
-                                              (unsigned long long*)d_sums);
+                                              (unsigned long long*)d_sums, d_sizes);
     LLFE_LAUNCHED(ctx);
     return LLFE_OK;
 }
@@ -406,7 +411,8 @@ int run_kmeans(llfe_ctx* ctx, KmParams P, int n, float* d_centers, int32_t* d_la
 
 extern "C" int llfe_kmeans_unique(llfe_ctx* ctx, const uint32_t* d_keys, const int32_t* d_count, int n, int max_unique,
                                   int k, int attempts, int max_iter, double eps, const uint64_t* d_rng_state,
-                                  float* d_centers, int32_t* d_labels, double* d_compactness, int32_t* d_k_used) {
+                                  float* d_centers, int32_t* d_labels, double* d_compactness, int32_t* d_k_used,
+                                  int32_t* d_cluster_sizes) {
     LLFE_CHECK_ARG(ctx != nullptr && d_keys != nullptr && d_count != nullptr && d_rng_state != nullptr &&
                    d_centers != nullptr);
     LLFE_CHECK_ARG(n >= 0 && n <= 65535 && max_unique > 0 && k >= 1 && k <= KMAX && attempts >= 1 && attempts <= 64 &&
@@ -436,7 +442,7 @@ extern "C" int llfe_kmeans_unique(llfe_ctx* ctx, const uint32_t* d_keys, const i
         Q.rng_state = d_rng_state + i0;
         LLFE_TRY(run_kmeans(ctx, Q, m, d_centers + (size_t)i0 * k * 3, d_labels ? d_labels + (size_t)i0 * max_unique : nullptr,
                             d_compactness ? d_compactness + i0 : nullptr, d_k_used ? d_k_used + i0 : nullptr, nullptr,
-                            nullptr));
+                            nullptr, d_cluster_sizes ? d_cluster_sizes + (size_t)i0 * k : nullptr));
     }
     return LLFE_OK;
 }
@@ -473,7 +479,7 @@ extern "C" int llfe_kmeans_lloyd(llfe_ctx* ctx, const uint32_t* d_keys, const ui
         Q.init = d_init_centers + (size_t)i0 * k * 3;
         LLFE_TRY(run_kmeans(ctx, Q, m, d_centers + (size_t)i0 * k * 3, d_labels ? d_labels + (size_t)i0 * max_unique : nullptr,
                             nullptr, nullptr, d_iters ? d_iters + i0 : nullptr,
-                            d_sums_counts ? d_sums_counts + (size_t)i0 * k * 4 : nullptr));
+                            d_sums_counts ? d_sums_counts + (size_t)i0 * k * 4 : nullptr, nullptr));
     }
     return LLFE_OK;
 }

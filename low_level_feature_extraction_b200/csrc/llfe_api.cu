@@ -502,6 +502,75 @@ int llfe_font_mask_host(llfe_ctx* ctx, const uint8_t* h_bgr, int h, int w, uint8
     return stage_end(&st, h_mask, p, 0);
 }
 
+int llfe_dominant_colors_host(llfe_ctx* ctx, const uint8_t* h_bgr, int h, int w, const int8_t* h_noise, uint64_t seed,
+                              int k, int attempts, int max_iter, double eps, uint64_t rng_state, float* h_centers,
+                              int32_t* h_labels, int32_t* h_n_unique, int32_t* h_k_used, double* h_compactness) {
+    LLFE_CHECK_ARG(ctx != nullptr && h_bgr != nullptr && h_centers != nullptr && h_labels != nullptr &&
+                   h_n_unique != nullptr && h_k_used != nullptr && h > 0 && w > 0 && k >= 1);
+    const size_t p = (size_t)h * w;
+    const int max_unique = (int)(p < ((size_t)1 << 24) ? p : ((size_t)1 << 24));
+    const size_t in_bytes = WsCarver::need(3 * p) + (h_noise ? WsCarver::need(3 * p) : 0);
+    const size_t keys_b = WsCarver::need((size_t)max_unique * 4), lab_b = keys_b;
+    const size_t small_b = 4096;
+    // device staging: [image | noise | keys | labels | small]   pinned: [image | noise | labels | small]
+    LLFE_TRY(ensure_stage(ctx, in_bytes + lab_b + small_b, in_bytes + keys_b + lab_b + small_b));
+    uint8_t* pin = (uint8_t*)ctx->pin;
+    uint8_t* dv = (uint8_t*)ctx->dev_stage;
+    memcpy(pin, h_bgr, 3 * p);
+    if (h_noise) memcpy(pin + WsCarver::need(3 * p), h_noise, 3 * p);
+    LLFE_CUDA(cudaMemcpyAsync(dv, pin, in_bytes, cudaMemcpyHostToDevice, ctx->stream));
+    const uint8_t* d_img = dv;
+    const int8_t* d_noise = h_noise ? (const int8_t*)(dv + WsCarver::need(3 * p)) : nullptr;
+    uint32_t* d_keys = (uint32_t*)(dv + in_bytes);
+    int32_t* d_labels = (int32_t*)(dv + in_bytes + keys_b);
+    uint8_t* d_small = dv + in_bytes + keys_b + lab_b;
+    int32_t* d_count = (int32_t*)d_small;             // [0..3]
+    int32_t* d_kused = (int32_t*)(d_small + 8);
+    uint64_t* d_rng = (uint64_t*)(d_small + 16);
+    double* d_comp = (double*)(d_small + 24);
+    float* d_centers = (float*)(d_small + 64);         // k*3 floats (k <= 32)
+    uint8_t* p_small = pin + in_bytes + lab_b;
+    memcpy(p_small + 16, &rng_state, 8);
+    LLFE_CUDA(cudaMemcpyAsync(d_rng, p_small + 16, 8, cudaMemcpyHostToDevice, ctx->stream));
+    LLFE_TRY(llfe_unique_colors(ctx, d_img, 1, h, w, d_noise, seed, d_keys, nullptr, d_count, max_unique));
+    LLFE_TRY(llfe_kmeans_unique(ctx, d_keys, d_count, 1, max_unique, k, attempts, max_iter, eps, d_rng, d_centers, d_labels,
+                                d_comp, d_kused, nullptr));
+    LLFE_CUDA(cudaMemcpyAsync(p_small, d_small, 64 + (size_t)k * 12, cudaMemcpyDeviceToHost, ctx->stream));
+    LLFE_CUDA(cudaStreamSynchronize(ctx->stream));
+    int32_t n_unique = *(int32_t*)p_small;
+    *h_n_unique = n_unique;
+    *h_k_used = *(int32_t*)(p_small + 8);
+    if (h_compactness) *h_compactness = *(double*)(p_small + 24);
+    memcpy(h_centers, p_small + 64, (size_t)k * 12);
+    const size_t nl = (size_t)(n_unique < max_unique ? n_unique : max_unique);
+    if (nl) {
+        uint8_t* p_lab = pin + in_bytes;
+        LLFE_CUDA(cudaMemcpyAsync(p_lab, d_labels, nl * 4, cudaMemcpyDeviceToHost, ctx->stream));
+        LLFE_CUDA(cudaStreamSynchronize(ctx->stream));
+        memcpy(h_labels, p_lab, nl * 4);
+    }
+    return LLFE_OK;
+}
+
+int llfe_convert_scale_abs_host(llfe_ctx* ctx, const uint8_t* h_src, size_t count, float a1, float a2, int single,
+                                uint8_t* h_dst) {
+    LLFE_CHECK_ARG(ctx != nullptr && h_src != nullptr && h_dst != nullptr);
+    if (count == 0) return LLFE_OK;
+    HostStage st;
+    LLFE_TRY(stage_begin(ctx, h_src, count, count, &st));
+    LLFE_TRY(llfe_convert_scale_abs(ctx, st.d_in, count, a1, a2, single, st.d_out));
+    return stage_end(&st, h_dst, count, 0);
+}
+
+int llfe_gaussian_blur5_host(llfe_ctx* ctx, const uint8_t* h_src, int h, int w, int c, uint8_t* h_dst) {
+    LLFE_CHECK_ARG(ctx != nullptr && h_src != nullptr && h_dst != nullptr && h > 0 && w > 0 && (c == 1 || c == 3));
+    const size_t b = (size_t)h * w * c;
+    HostStage st;
+    LLFE_TRY(stage_begin(ctx, h_src, b, b, &st));
+    LLFE_TRY(llfe_gaussian_blur5(ctx, st.d_in, 1, h, w, c, st.d_out));
+    return stage_end(&st, h_dst, b, 0);
+}
+
 int llfe_resize_area_host(llfe_ctx* ctx, const uint8_t* h_src, int sh, int sw, int c, uint8_t* h_dst, int dh, int dw) {
     LLFE_CHECK_ARG(ctx != nullptr && h_src != nullptr && h_dst != nullptr && sh > 0 && sw > 0 && dh > 0 && dw > 0);
     const size_t in = (size_t)sh * sw * c, out = (size_t)dh * dw * c;

@@ -235,7 +235,8 @@ class Engine:
                       max_iter: int = 200, eps: float = 0.2):
         """cv2.kmeans(float32(unique), k, None, (EPS+MAX_ITER, max_iter, eps), attempts, KMEANS_PP_CENTERS)
         per image.  rng_state: int or sequence of ints (cv::RNG state; cv2.setRNGSeed(s) => s).
-        -> (centers float32 (n,k,3) RGB, labels int32 (n,max_unique), compactness float64 (n,), k_used int32 (n,))."""
+        -> (centers float32 (n,k,3) RGB, labels int32 (n,max_unique), compactness float64 (n,), k_used int32 (n,)).
+        self.last_cluster_sizes holds np.bincount(labels) per image (int32 (n,k))."""
         if keys.dim() == 1:
             keys, count = keys.unsqueeze(0), count.reshape(1)
         n, max_unique = keys.shape
@@ -245,9 +246,11 @@ class Engine:
         labels = self._empty((n, max_unique), torch.int32)
         comp = self._empty((n,), torch.float64)
         kused = self._empty((n,), torch.int32)
+        sizes = self._empty((n, k), torch.int32)
         self._bind()
         self.ctx.call("llfe_kmeans_unique", keys.contiguous(), count.contiguous(), n, max_unique, int(k), int(attempts),
-                      int(max_iter), float(eps), rs, centers, labels, comp, kused)
+                      int(max_iter), float(eps), rs, centers, labels, comp, kused, sizes)
+        self.last_cluster_sizes = sizes
         return centers, labels, comp, kused
 
     def kmeans_lloyd(self, keys: torch.Tensor, count: torch.Tensor, init_centers: torch.Tensor,

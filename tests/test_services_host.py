@@ -1,0 +1,67 @@
+"""Host-side logic of the drop-in services (CPU only; no compute calls)."""
+import numpy as np
+import pytest
+from PIL import Image
+
+from oracle import cvops, load_reference
+from low_level_feature_extraction_b200.services import ColorExtractor, ColorFeatures
+from low_level_feature_extraction_b200.services.color_extractor import _CV_RNG_COEFF  # noqa: F401
+
+
+def test_helpers():
+    assert ColorExtractor.rgb_to_hex((255, 0, 16)) == "#ff0010"
+    assert ColorExtractor.hex_to_rgb("#ff0010") == (255, 0, 16)
+    assert ColorExtractor.is_light_color((255, 255, 255)) and not ColorExtractor.is_light_color((10, 10, 10))
+    assert abs(ColorExtractor.get_contrast_ratio("#ffffff", "#000000") - 21.0) < 1e-9
+    cf = ColorFeatures(primary="#112233", background="#FFFFFF", accent=["#000000"] * 3, metadata={"success": True})
+    assert cf.primary == "#112233"
+    with pytest.raises(Exception):
+        ColorFeatures(primary="nothex", background="#FFFFFF", accent=[])
+
+
+def test_rng_state_advance_matches_cv_rng():
+    ColorExtractor.set_rng_seed(12345)
+    r = cvops.CvRNG(12345)
+    ColorExtractor._advance_rng(37)
+    for _ in range(37):
+        r.next()
+    assert ColorExtractor._rng_state == r.state
+    ColorExtractor.set_rng_seed(0)
+    assert ColorExtractor._rng_state == 0xFFFFFFFF
+
+
+INPUTS = {
+    "bgr": lambda r: r.integers(0, 256, (12, 9, 3), dtype=np.uint8),
+    "gray2d": lambda r: r.integers(0, 256, (12, 9), dtype=np.uint8),
+    "gray1ch": lambda r: r.integers(0, 256, (12, 9, 1), dtype=np.uint8),
+    "bgra": lambda r: r.integers(0, 256, (12, 9, 4), dtype=np.uint8),
+    "chw_quirk": lambda r: r.integers(0, 256, (3, 20, 7), dtype=np.uint8),
+    "float": lambda r: r.random((12, 9, 3)).astype(np.float32),
+    "flat_square": lambda r: r.integers(0, 256, (6 * 6 * 3,), dtype=np.uint8),
+    "flat_bad": lambda r: r.integers(0, 256, (50,), dtype=np.uint8),
+    "empty": lambda r: np.zeros((0, 3), np.uint8),
+    "five_ch": lambda r: r.integers(0, 256, (12, 9, 5), dtype=np.uint8),
+    "pil_rgb": lambda r: Image.fromarray(r.integers(0, 256, (12, 9, 3), dtype=np.uint8), "RGB"),
+    "pil_rgba": lambda r: Image.fromarray(r.integers(0, 256, (12, 9, 4), dtype=np.uint8), "RGBA"),
+    "pil_l": lambda r: Image.fromarray(r.integers(0, 256, (12, 9), dtype=np.uint8), "L"),
+    "none": lambda r: None,
+}
+
+
+@pytest.mark.skipif(not load_reference.available(), reason="/root/reference is only present in the build container")
+@pytest.mark.parametrize("kind", sorted(INPUTS))
+def test_process_image_matches_live_reference(kind):
+    ref = load_reference.load()["ColorExtractor"]
+    x = INPUTS[kind](np.random.default_rng(1))
+    a = ColorExtractor._process_image(x if not isinstance(x, np.ndarray) else x.copy())
+    b = ref._process_image(x if not isinstance(x, np.ndarray) else x.copy())
+    assert a.dtype == b.dtype and a.shape == b.shape and np.array_equal(a, b), kind
+
+
+def test_process_image_without_reference():
+    r = np.random.default_rng(2)
+    bgr = INPUTS["bgr"](r)
+    assert np.array_equal(ColorExtractor._process_image(bgr), bgr[..., ::-1])
+    assert ColorExtractor._process_image(None).shape == (100, 100, 3)
+    g = INPUTS["gray2d"](r)
+    assert np.array_equal(ColorExtractor._process_image(g), np.stack([g, g, g], -1))
