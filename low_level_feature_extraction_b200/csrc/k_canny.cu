@@ -133,11 +133,16 @@ __device__ bool converge_strip(uint32_t* sw, uint32_t* se, int rows, int wpr, in
     bool any = false;
     for (;;) {
         bool changed = false;
-        for (int c = threadIdx.x; c < wpr; c += blockDim.x) {
+        // (word column, row group) jobs: each job sweeps its rows down then up
+        const int G = max(1, min((int)blockDim.x / wpr, (rows + 3) / 4));
+        const int rg = (rows + G - 1) / G;
+        for (int job = threadIdx.x; job < wpr * G; job += blockDim.x) {
+            const int c = job % wpr, g = job / wpr;
+            const int r_lo = g * rg, r_hi = min(rows, r_lo + rg);
 #pragma unroll 1
             for (int pass = 0; pass < 2; ++pass) {
-                for (int k = 0; k < rows; ++k) {
-                    int r = pass == 0 ? k : rows - 1 - k;
+                for (int k = r_lo; k < r_hi; ++k) {
+                    int r = pass == 0 ? k : r_hi - 1 - (k - r_lo);
                     uint32_t wv = sw[r * wpr + c];
                     uint32_t e = se[(r + 1) * wpr + c];
                     if ((wv & ~e) == 0) continue;
@@ -181,9 +186,11 @@ __device__ void load_strip(const uint32_t* __restrict__ weak, const uint32_t* ed
 // strong plane and is updated in place.  flags[img][strip] is set to 1 when a
 // neighbouring strip must be revisited by phase 2.
 __global__ void __launch_bounds__(HTHREADS) k_hyst_strips(const uint32_t* __restrict__ weak, uint32_t* edges, int h,
-                                                          int wpr, int nstrips, uint32_t* flags) {
+                                                          int wpr, int nstrips, const uint32_t* flags_in,
+                                                          uint32_t* flags) {
     extern __shared__ uint32_t sm[];
     const int img = blockIdx.y, strip = blockIdx.x;
+    if (flags_in && flags_in[(size_t)img * nstrips + strip] == 0) return;  // later rounds: flagged strips only
     const size_t plane = (size_t)h * wpr;
     const uint32_t* pw = weak + img * plane;
     uint32_t* pe = edges + img * plane;
@@ -349,7 +356,7 @@ int launch_canny_front(llfe_ctx* ctx, const uint8_t* gray, int n, int h, int w, 
     return LLFE_OK;
 }
 
-size_t hysteresis_flag_words(int n, int h) { return (size_t)n * ceil_div(h, HROWS); }
+size_t hysteresis_flag_words(int n, int h) { return 2 * (size_t)n * ceil_div(h, HROWS); }
 
 // `edges` holds the strong plane on entry and the final edge plane on exit.
 int launch_hysteresis(llfe_ctx* ctx, const uint32_t* weak, uint32_t* edges, int n, int h, int w, uint32_t* flags) {
@@ -368,12 +375,26 @@ int launch_hysteresis(llfe_ctx* ctx, const uint32_t* weak, uint32_t* edges, int 
         LLFE_CUDA(cudaFuncSetAttribute(k_hyst_finish, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ctx->smem_optin));
         attr_set = true;
     }
-    LLFE_CUDA(cudaMemsetAsync(flags, 0, hysteresis_flag_words(n, h) * sizeof(uint32_t), ctx->stream));
+    // round 0 visits every strip; rounds 1..2 only strips whose halo changed; one CTA per image
+    // then finishes whatever cross-strip propagation is left (usually nothing).
+    const size_t fw = (size_t)n * nstrips;
+    uint32_t* fa = flags;
+    uint32_t* fb = flags + fw;
+    LLFE_CUDA(cudaMemsetAsync(flags, 0, 2 * fw * sizeof(uint32_t), ctx->stream));
     LLFE_KERNEL(ctx, "k_hyst_strips");
-    k_hyst_strips<<<dim3(nstrips, n), HTHREADS, smem, ctx->stream>>>(weak, edges, h, wpr, nstrips, flags);
+    k_hyst_strips<<<dim3(nstrips, n), HTHREADS, smem, ctx->stream>>>(weak, edges, h, wpr, nstrips, nullptr, fa);
     LLFE_LAUNCHED(ctx);
+    for (int round = 1; round <= 2; ++round) {
+        LLFE_KERNEL(ctx, "k_hyst_strips_again");
+        k_hyst_strips<<<dim3(nstrips, n), HTHREADS, smem, ctx->stream>>>(weak, edges, h, wpr, nstrips, fa, fb);
+        LLFE_LAUNCHED(ctx);
+        LLFE_CUDA(cudaMemsetAsync(fa, 0, fw * sizeof(uint32_t), ctx->stream));
+        uint32_t* t = fa;
+        fa = fb;
+        fb = t;
+    }
     LLFE_KERNEL(ctx, "k_hyst_finish");
-    k_hyst_finish<<<n, HTHREADS, smem, ctx->stream>>>(weak, edges, h, wpr, nstrips, flags);
+    k_hyst_finish<<<n, HTHREADS, smem, ctx->stream>>>(weak, edges, h, wpr, nstrips, fa);
     LLFE_LAUNCHED(ctx);
     return LLFE_OK;
 }

@@ -14,43 +14,17 @@
 // c = float(double(sum)/double(count))) that backs the per-pixel k-means mode.
 #include "llfe_common.cuh"
 #include "llfe_device.cuh"
+#include "k_kmeans_shared.cuh"
 
 namespace {
 
-constexpr int KMAX = 32;
 constexpr int KT = 512;  // threads per CTA
 constexpr int KW = KT / 32;
-
-struct KmParams {
-    const uint32_t* keys;      // [n][max_unique]  R<<16|G<<8|B
-    const uint32_t* weights;   // [n][max_unique] or null
-    const int32_t* count;      // [n]
-    int max_unique, k, attempts, max_iter;
-    double eps2;
-    int exact_sums;            // 1: c = float(double(sum)/double(cnt))
-    const uint64_t* rng_state; // [n] (PP mode) or null
-    const float* init;         // [n][k][3] (seeded mode) or null
-    // scratch, per (image, attempt)
-    uint32_t* dist;            // [n][attempts][max_unique]
-    uint8_t* labels;           // [n][attempts][max_unique]
-    float* centers;            // [n][attempts][KMAX][3]
-    double* compact;           // [n][attempts]
-    int32_t* iters;            // [n][attempts]
-    int32_t* inexact;          // [n][attempts]
-    unsigned long long* sums;  // [n][attempts][KMAX][4]  final sums/counts (seeded mode output)
-};
 
 __device__ __forceinline__ void unpack(uint32_t key, float& r, float& g, float& b) {
     r = (float)(key >> 16);
     g = (float)((key >> 8) & 255u);
     b = (float)(key & 255u);
-}
-
-__device__ __forceinline__ uint32_t idist(uint32_t a, uint32_t b) {
-    int dr = (int)(a >> 16) - (int)(b >> 16);
-    int dg = (int)((a >> 8) & 255u) - (int)((b >> 8) & 255u);
-    int db = (int)(a & 255u) - (int)(b & 255u);
-    return (uint32_t)(dr * dr + dg * dg + db * db);
 }
 
 // OpenCV normL2Sqr for 3 floats: ((0 + t0*t0) + t1*t1) + t2*t2, every op rounded
@@ -85,11 +59,6 @@ __device__ __forceinline__ double block_sum_f64(double v, double* sh) {
     return t;
 }
 
-__device__ __forceinline__ uint32_t rng_next(unsigned long long& s) {
-    s = (unsigned long long)(uint32_t)s * 4164903690ull + (s >> 32);
-    return (uint32_t)s;
-}
-
 __global__ void __launch_bounds__(KT) k_kmeans(KmParams P) {
     const int att = blockIdx.x, img = blockIdx.y, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int U = min(P.count[img], P.max_unique);
@@ -105,7 +74,7 @@ __global__ void __launch_bounds__(KT) k_kmeans(KmParams P) {
     }
     const uint32_t* keys = P.keys + (size_t)img * P.max_unique;
     const uint32_t* wts = P.weights ? P.weights + (size_t)img * P.max_unique : nullptr;
-    uint32_t* dist = P.dist + slot * P.max_unique;
+    uint32_t* dist = P.dist + slot * 2 * (size_t)P.max_unique;
     uint8_t* labels = P.labels + slot * P.max_unique;
 
     __shared__ float s_c[KMAX][3];      // current centres
@@ -384,22 +353,26 @@ __global__ void __launch_bounds__(256) k_kmeans_pick(KmParams P, float* out_cent
 int run_kmeans(llfe_ctx* ctx, KmParams P, int n, float* d_centers, int32_t* d_labels, double* d_compact, int32_t* d_kused,
                int32_t* d_iters, uint64_t* d_sums, int32_t* d_sizes) {
     const size_t slots = (size_t)n * P.attempts;
-    const size_t need = WsCarver::need(slots * P.max_unique * 4) + WsCarver::need(slots * P.max_unique) +
+    const size_t need = WsCarver::need(slots * P.max_unique * 8) + WsCarver::need(slots * P.max_unique) +
                         WsCarver::need(slots * KMAX * 3 * 4) + 3 * WsCarver::need(slots * 8) +
                         WsCarver::need(slots * KMAX * 4 * 8);
     void* ws;
     LLFE_TRY(llfe_workspace(ctx, need, &ws));
     WsCarver c(ws);
-    P.dist = c.take<uint32_t>(slots * P.max_unique);
+    P.dist = c.take<uint32_t>(slots * 2 * P.max_unique);
     P.labels = c.take<uint8_t>(slots * P.max_unique);
     P.centers = c.take<float>(slots * KMAX * 3);
     P.compact = c.take<double>(slots);
     P.iters = (int32_t*)c.take<double>(slots);
     P.inexact = (int32_t*)c.take<double>(slots);
     P.sums = (unsigned long long*)c.take<unsigned long long>(slots * KMAX * 4);
-    LLFE_KERNEL(ctx, "k_kmeans");
-    k_kmeans<<<dim3(P.attempts, n), KT, 0, ctx->stream>>>(P);
-    LLFE_LAUNCHED(ctx);
+    if (P.weights == nullptr && !P.exact_sums) {
+        LLFE_TRY(launch_kmeans_fast(ctx, P, n));
+    } else {
+        LLFE_KERNEL(ctx, "k_kmeans");
+        k_kmeans<<<dim3(P.attempts, n), KT, 0, ctx->stream>>>(P);
+        LLFE_LAUNCHED(ctx);
+    }
     LLFE_KERNEL(ctx, "k_kmeans_pick");
     k_kmeans_pick<<<n, 256, 0, ctx->stream>>>(P, d_centers, d_labels, d_compact, d_kused, d_iters,
                                               (unsigned long long*)d_sums, d_sizes);
@@ -431,7 +404,7 @@ extern "C" int llfe_kmeans_unique(llfe_ctx* ctx, const uint32_t* d_keys, const i
     P.rng_state = d_rng_state;
     P.init = nullptr;
     // bound the scratch: process the batch in chunks of images
-    const size_t per_img = (size_t)attempts * max_unique * 5 + 4096;
+    const size_t per_img = (size_t)attempts * max_unique * 9 + 4096;
     int chunk = (int)((size_t)(256u << 20) / per_img);
     if (chunk < 1) chunk = 1;
     for (int i0 = 0; i0 < n; i0 += chunk) {
@@ -467,7 +440,7 @@ extern "C" int llfe_kmeans_lloyd(llfe_ctx* ctx, const uint32_t* d_keys, const ui
     P.exact_sums = exact_sums ? 1 : 0;
     P.rng_state = nullptr;
     P.init = d_init_centers;
-    const size_t per_img = (size_t)max_unique * 5 + 4096;
+    const size_t per_img = (size_t)max_unique * 9 + 4096;
     int chunk = (int)((size_t)(256u << 20) / per_img);
     if (chunk < 1) chunk = 1;
     for (int i0 = 0; i0 < n; i0 += chunk) {

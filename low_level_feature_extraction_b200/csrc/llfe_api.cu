@@ -413,8 +413,16 @@ int llfe_pipeline(llfe_ctx* ctx, const uint8_t* d_bgr, int n, int h, int w, int 
     LLFE_CHECK_ARG(h > 0 && w > 0);
     LLFE_CHECK_ARG(d_keys == nullptr || (d_count != nullptr && max_unique > 0));
     if (n == 0) return LLFE_OK;
-    if (d_shape_mask) LLFE_TRY(llfe_shape_mask(ctx, d_bgr, n, h, w, low, high, d_shape_mask));
-    if (d_shadow_mask) LLFE_TRY(llfe_shadow_mask(ctx, d_bgr, n, h, w, d_shadow_mask, nullptr, d_shadow_sum_count));
+    if (d_shape_mask || d_shadow_mask) {
+        // gray + blur once, shared by the edge chain and the adaptive threshold
+        const size_t img = WsCarver::need((size_t)n * h * w);
+        void* ws;
+        LLFE_TRY(llfe_workspace(ctx, img + canny_ws_bytes(n, h, w), &ws));
+        uint8_t* blurred = (uint8_t*)ws;
+        LLFE_TRY(launch_gray_blur5(ctx, d_bgr, n, h, w, blurred));
+        if (d_shape_mask) LLFE_TRY(canny_from_gray(ctx, blurred, n, h, w, low, high, 1, d_shape_mask, (char*)ws + img));
+        if (d_shadow_mask) LLFE_TRY(launch_adaptive(ctx, blurred, n, h, w, 2, d_shadow_mask, d_shadow_sum_count));
+    }
     if (d_keys) LLFE_TRY(launch_unique_colors(ctx, d_bgr, n, h, w, d_noise, seed, d_keys, nullptr, d_count, max_unique));
     return LLFE_OK;
 }
