@@ -123,68 +123,95 @@ __device__ __forceinline__ uint32_t fill_word(uint32_t e, uint32_t w) {
     return g1 | g2;
 }
 
-// Converge one strip held in shared memory.
-//   sw : weak rows   [rows][wpr]
-//   se : edge rows   [rows + 2][wpr]  (row 0 = halo above, row rows+1 = halo below)
-// Each thread owns word-columns c = tid, tid + T, ... and sweeps them down then
-// up, so a whole column propagates per iteration; words propagate sideways
-// through the neighbours' top/bottom bits.  Returns true if anything changed.
-__device__ bool converge_strip(uint32_t* sw, uint32_t* se, int rows, int wpr, int* s_flag) {
+// shared-memory pitch (words) of a strip row: odd, so that row-parallel sweeps hit distinct banks
+__host__ __device__ static inline int strip_pitch(int wpr) { return wpr | 1; }
+
+// Grow word (r, c) of the strip from its 8-neighbourhood; returns true if it changed.
+//   sw : weak rows [rows][sp]      se : edge rows [rows + 2][sp] (row 0 / rows+1 = halos)
+__device__ __forceinline__ bool grow_word(const uint32_t* sw, uint32_t* se, int r, int c, int wpr, int sp) {
+    const uint32_t wv = sw[r * sp + c];
+    const uint32_t e = se[(r + 1) * sp + c];
+    if ((wv & ~e) == 0) return false;
+    const uint32_t* up = se + r * sp;
+    const uint32_t* mid = up + sp;
+    const uint32_t* dn = mid + sp;
+    uint32_t v = up[c] | mid[c] | dn[c];
+    uint32_t spread = v | (v << 1) | (v >> 1);
+    if (c > 0) spread |= (up[c - 1] | mid[c - 1] | dn[c - 1]) >> 31;
+    if (c + 1 < wpr) spread |= (up[c + 1] | mid[c + 1] | dn[c + 1]) << 31;
+    uint32_t ne = e | (wv & spread);
+    if (ne == e) return false;
+    se[(r + 1) * sp + c] = fill_word(ne, wv);
+    return true;
+}
+
+// Converge one strip held in shared memory.  Only CANDIDATE words (weak bits that are not
+// edges yet) can ever change, and on real images they are a small fraction of the strip, so
+// they are compacted into a work list once and every iteration touches just that list (one
+// thread per candidate word, 32 pixels filled per step by fill_word).  Updates are monotone
+// (bits are only set), so unsynchronised neighbour reads are benign; the loop ends after an
+// iteration in which nothing changed.  Returns true if anything changed.
+__device__ bool converge_strip(const uint32_t* sw, uint32_t* se, int rows, int wpr, int sp, uint16_t* list,
+                               int* s_n) {
+    if (threadIdx.x == 0) *s_n = 0;
+    __syncthreads();
+    for (int i = threadIdx.x; i < rows * wpr; i += blockDim.x) {
+        int r = i / wpr, c = i - r * wpr;
+        if (sw[r * sp + c] & ~se[(r + 1) * sp + c]) list[atomicAdd(s_n, 1)] = (uint16_t)((r << 9) | c);
+    }
+    __syncthreads();
+    const int n = *s_n;
     bool any = false;
+    if (n == 0) return false;
     for (;;) {
         bool changed = false;
-        // (word column, row group) jobs: each job sweeps its rows down then up
-        const int G = max(1, min((int)blockDim.x / wpr, (rows + 3) / 4));
-        const int rg = (rows + G - 1) / G;
-        for (int job = threadIdx.x; job < wpr * G; job += blockDim.x) {
-            const int c = job % wpr, g = job / wpr;
-            const int r_lo = g * rg, r_hi = min(rows, r_lo + rg);
-#pragma unroll 1
-            for (int pass = 0; pass < 2; ++pass) {
-                for (int k = r_lo; k < r_hi; ++k) {
-                    int r = pass == 0 ? k : r_hi - 1 - (k - r_lo);
-                    uint32_t wv = sw[r * wpr + c];
-                    uint32_t e = se[(r + 1) * wpr + c];
-                    if ((wv & ~e) == 0) continue;
-                    const uint32_t* up = se + r * wpr;
-                    const uint32_t* mid = se + (r + 1) * wpr;
-                    const uint32_t* dn = se + (r + 2) * wpr;
-                    uint32_t v = up[c] | mid[c] | dn[c];
-                    uint32_t sp = v | (v << 1) | (v >> 1);
-                    if (c > 0) sp |= (up[c - 1] | mid[c - 1] | dn[c - 1]) >> 31;
-                    if (c + 1 < wpr) sp |= (up[c + 1] | mid[c + 1] | dn[c + 1]) << 31;
-                    uint32_t ne = e | (wv & sp);
-                    if (ne != e) {
-                        ne = fill_word(ne, wv);
-                        se[(r + 1) * wpr + c] = ne;
-                        changed = true;
-                    }
-                }
-            }
+        for (int j = threadIdx.x; j < n; j += blockDim.x) {
+            int rc = list[j];
+            changed |= grow_word(sw, se, rc >> 9, rc & 511, wpr, sp);
         }
-        int r = __syncthreads_or(changed);
-        if (!r) break;
+        if (!__syncthreads_or(changed)) break;
         any = true;
     }
-    (void)s_flag;
     return any;
 }
 
 // Load a strip (weak rows, edge rows + halos) into shared memory.
-__device__ void load_strip(const uint32_t* __restrict__ weak, const uint32_t* edges, int h, int wpr, int r0, int rows,
-                           uint32_t* sw, uint32_t* se) {
-    for (int i = threadIdx.x; i < rows * wpr; i += blockDim.x) sw[i] = weak[(size_t)r0 * wpr + i];
+__device__ void load_strip(const uint32_t* __restrict__ weak, const uint32_t* edges, int h, int wpr, int sp, int r0,
+                           int rows, uint32_t* sw, uint32_t* se) {
+    for (int i = threadIdx.x; i < rows * wpr; i += blockDim.x) {
+        int r = i / wpr, c = i - r * wpr;
+        sw[r * sp + c] = weak[(size_t)(r0 + r) * wpr + c];
+    }
     for (int i = threadIdx.x; i < (rows + 2) * wpr; i += blockDim.x) {
-        int rr = r0 - 1 + i / wpr;
+        int r = i / wpr, c = i - r * wpr;
+        int rr = r0 - 1 + r;
         uint32_t v = 0;
-        if (rr >= 0 && rr < h) v = __ldcg(edges + (size_t)rr * wpr + (i % wpr));
-        se[i] = v;
+        if (rr >= 0 && rr < h) v = __ldcg(edges + (size_t)rr * wpr + c);
+        se[r * sp + c] = v;
     }
 }
 
-// Phase 1: every strip of every image in parallel.  `edges` enters holding the
-// strong plane and is updated in place.  flags[img][strip] is set to 1 when a
-// neighbouring strip must be revisited by phase 2.
+// Write a converged strip back; reports whether its first / last row changed (-> the
+// neighbouring strips' halos are stale and they must be revisited).
+__device__ void store_strip(uint32_t* pe, const uint32_t* se, int wpr, int sp, int r0, int rows, bool& top, bool& bot) {
+    bool t = false, b = false;
+    for (int i = threadIdx.x; i < rows * wpr; i += blockDim.x) {
+        int r = i / wpr, c = i - r * wpr;
+        uint32_t v = se[(r + 1) * sp + c];
+        size_t o = (size_t)(r0 + r) * wpr + c;
+        if (v != pe[o]) {
+            pe[o] = v;
+            t |= r == 0;
+            b |= r == rows - 1;
+        }
+    }
+    top = __syncthreads_or(t);
+    bot = __syncthreads_or(b);
+}
+
+// Phase 1: strips in parallel.  `edges` enters holding the strong plane and is updated in
+// place.  With flags_in only the flagged strips run.  flags[img][strip] = 1 tells that a
+// neighbouring strip must be revisited.
 __global__ void __launch_bounds__(HTHREADS) k_hyst_strips(const uint32_t* __restrict__ weak, uint32_t* edges, int h,
                                                           int wpr, int nstrips, const uint32_t* flags_in,
                                                           uint32_t* flags) {
@@ -194,28 +221,17 @@ __global__ void __launch_bounds__(HTHREADS) k_hyst_strips(const uint32_t* __rest
     const size_t plane = (size_t)h * wpr;
     const uint32_t* pw = weak + img * plane;
     uint32_t* pe = edges + img * plane;
+    const int sp = strip_pitch(wpr);
     const int r0 = strip * HROWS, rows = min(HROWS, h - r0);
     uint32_t* sw = sm;
-    uint32_t* se = sm + HROWS * wpr;
-    __shared__ int s_flag;
-    load_strip(pw, pe, h, wpr, r0, rows, sw, se);
+    uint32_t* se = sm + HROWS * sp;
+    uint16_t* list = reinterpret_cast<uint16_t*>(se + (HROWS + 2) * sp);
+    __shared__ int s_n;
+    load_strip(pw, pe, h, wpr, sp, r0, rows, sw, se);
     __syncthreads();
-    bool any = converge_strip(sw, se, rows, wpr, &s_flag);
-    if (!any) return;
-    // write back and tell the neighbours whose halo we may have changed
-    bool top = false, bot = false;
-    for (int i = threadIdx.x; i < rows * wpr; i += blockDim.x) {
-        uint32_t v = se[wpr + i];
-        size_t o = (size_t)r0 * wpr + i;
-        uint32_t old = pe[o];
-        if (v != old) {
-            pe[o] = v;
-            if (i < wpr) top = true;
-            if (i >= (rows - 1) * wpr) bot = true;
-        }
-    }
-    top = __syncthreads_or(top);
-    bot = __syncthreads_or(bot);
+    if (!converge_strip(sw, se, rows, wpr, sp, list, &s_n)) return;
+    bool top, bot;
+    store_strip(pe, se, wpr, sp, r0, rows, top, bot);
     if (threadIdx.x == 0) {
         uint32_t* f = flags + (size_t)img * nstrips;
         if (top && strip > 0) f[strip - 1] = 1;
@@ -223,8 +239,8 @@ __global__ void __launch_bounds__(HTHREADS) k_hyst_strips(const uint32_t* __rest
     }
 }
 
-// Phase 2: one CTA per image finishes the cross-strip propagation: visit flagged
-// strips (down sweep, then up sweep) until no flag is left.
+// Phase 2: one CTA per image finishes the cross-strip propagation: visit flagged strips
+// (down sweep, then up sweep) until no flag is left.  Usually there is nothing to do.
 __global__ void __launch_bounds__(HTHREADS) k_hyst_finish(const uint32_t* __restrict__ weak, uint32_t* edges, int h,
                                                           int wpr, int nstrips, uint32_t* flags) {
     extern __shared__ uint32_t sm[];
@@ -233,44 +249,35 @@ __global__ void __launch_bounds__(HTHREADS) k_hyst_finish(const uint32_t* __rest
     const uint32_t* pw = weak + img * plane;
     uint32_t* pe = edges + img * plane;
     volatile uint32_t* f = flags + (size_t)img * nstrips;
+    const int sp = strip_pitch(wpr);
     uint32_t* sw = sm;
-    uint32_t* se = sm + HROWS * wpr;
-    __shared__ int s_flag;
+    uint32_t* se = sm + HROWS * sp;
+    uint16_t* list = reinterpret_cast<uint16_t*>(se + (HROWS + 2) * sp);
+    __shared__ int s_n;
     for (;;) {
-        bool worked = false;
+        bool mine = false;
+        for (int i = threadIdx.x; i < nstrips; i += blockDim.x) mine |= f[i] != 0;
+        if (!__syncthreads_or(mine)) break;
         for (int pass = 0; pass < 2; ++pass) {
             for (int k = 0; k < nstrips; ++k) {
                 int strip = pass == 0 ? k : nstrips - 1 - k;
                 __syncthreads();
-                if (f[strip] == 0) continue;  // uniform: read after the barrier by all threads
+                if (f[strip] == 0) continue;  // uniform: every thread reads it after the barrier
                 __syncthreads();
                 if (threadIdx.x == 0) f[strip] = 0;
-                worked = true;
                 const int r0 = strip * HROWS, rows = min(HROWS, h - r0);
-                load_strip(pw, pe, h, wpr, r0, rows, sw, se);
+                load_strip(pw, pe, h, wpr, sp, r0, rows, sw, se);
                 __syncthreads();
-                bool any = converge_strip(sw, se, rows, wpr, &s_flag);
-                if (!any) continue;
-                bool top = false, bot = false;
-                for (int i = threadIdx.x; i < rows * wpr; i += blockDim.x) {
-                    uint32_t v = se[wpr + i];
-                    size_t o = (size_t)r0 * wpr + i;
-                    if (v != pe[o]) {
-                        pe[o] = v;
-                        if (i < wpr) top = true;
-                        if (i >= (rows - 1) * wpr) bot = true;
-                    }
-                }
-                top = __syncthreads_or(top);
-                bot = __syncthreads_or(bot);
+                if (!converge_strip(sw, se, rows, wpr, sp, list, &s_n)) continue;
+                bool top, bot;
+                store_strip(pe, se, wpr, sp, r0, rows, top, bot);
                 if (threadIdx.x == 0) {
                     if (top && strip > 0) f[strip - 1] = 1;
                     if (bot && strip + 1 < nstrips) f[strip + 1] = 1;
                 }
-                __threadfence_block();
             }
         }
-        if (!worked) break;
+        __syncthreads();
     }
 }
 
@@ -363,16 +370,16 @@ int launch_hysteresis(llfe_ctx* ctx, const uint32_t* weak, uint32_t* edges, int 
     if (n == 0 || h == 0 || w == 0) return LLFE_OK;
     const int wpr = plane_wpr(w);
     const int nstrips = ceil_div(h, HROWS);
-    size_t smem = (size_t)(2 * HROWS + 2) * wpr * sizeof(uint32_t);
-    if (smem > ctx->smem_optin) {
+    size_t smem = (size_t)(2 * HROWS + 2) * strip_pitch(wpr) * sizeof(uint32_t) + (size_t)HROWS * wpr * sizeof(uint16_t);
+    if (smem > ctx->smem_optin - 1024) {
         llfe_set_error("hysteresis: image width %d needs %zu B of shared memory per strip (limit %zu)", w, smem,
                        ctx->smem_optin);
         return LLFE_E_UNSUPPORTED;
     }
     static bool attr_set = false;
     if (!attr_set) {
-        LLFE_CUDA(cudaFuncSetAttribute(k_hyst_strips, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ctx->smem_optin));
-        LLFE_CUDA(cudaFuncSetAttribute(k_hyst_finish, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ctx->smem_optin));
+        LLFE_CUDA(cudaFuncSetAttribute(k_hyst_strips, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(ctx->smem_optin - 1024)));
+        LLFE_CUDA(cudaFuncSetAttribute(k_hyst_finish, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(ctx->smem_optin - 1024)));
         attr_set = true;
     }
     // round 0 visits every strip; rounds 1..2 only strips whose halo changed; one CTA per image
