@@ -1,6 +1,7 @@
 // extern "C" surface of libllfe.so: context, memory helpers and the per-op
 // entry points declared in include/llfe.h.  Kernels live in the k_*.cu files.
 #include <stdarg.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include <new>
@@ -327,6 +328,8 @@ int llfe_shape_mask(llfe_ctx* ctx, const uint8_t* d_bgr, int n, int h, int w, in
     LLFE_IMG_ARGS(d_bgr);
     LLFE_CHECK_ARG(d_mask != nullptr);
     if ((size_t)n * h * w == 0) return LLFE_OK;
+    if (fused_supported(h, w) && !getenv("LLFE_UNFUSED"))
+        return llfe_pipeline(ctx, d_bgr, n, h, w, low, high, d_mask, nullptr, nullptr, nullptr, 0, nullptr, nullptr, 0);
     const size_t img = WsCarver::need((size_t)n * h * w);
     void* ws;
     LLFE_TRY(llfe_workspace(ctx, img + canny_ws_bytes(n, h, w), &ws));
@@ -348,6 +351,8 @@ int llfe_shadow_mask(llfe_ctx* ctx, const uint8_t* d_bgr, int n, int h, int w, u
     LLFE_IMG_ARGS(d_bgr);
     LLFE_CHECK_ARG(d_mask != nullptr);
     if ((size_t)n * h * w == 0) return LLFE_OK;
+    if (!d_blurred && fused_supported(h, w) && !getenv("LLFE_UNFUSED"))
+        return llfe_pipeline(ctx, d_bgr, n, h, w, 50, 150, nullptr, d_mask, d_sum_count, nullptr, 0, nullptr, nullptr, 0);
     uint8_t* blurred = d_blurred;
     if (!blurred) {
         void* ws;
@@ -413,6 +418,39 @@ int llfe_pipeline(llfe_ctx* ctx, const uint8_t* d_bgr, int n, int h, int w, int 
     LLFE_CHECK_ARG(h > 0 && w > 0);
     LLFE_CHECK_ARG(d_keys == nullptr || (d_count != nullptr && max_unique > 0));
     if (n == 0) return LLFE_OK;
+    if (fused_supported(h, w) && !getenv("LLFE_UNFUSED")) {
+        // one read of the image per chunk: planes + shadow mask + colour bitmap, then the small post-passes
+        const int chunk = n < 32 ? n : 32;
+        const size_t plane_words = (size_t)chunk * h * plane_wpr(w);
+        const size_t bmw = bitmap_words_per_image(), bmb = bitmap_blocks_per_image();
+        size_t need = 2 * WsCarver::need(plane_words * 4) + WsCarver::need(hysteresis_flag_words(chunk, h) * 4);
+        if (d_keys) need += WsCarver::need(bmw * 4 * chunk) + WsCarver::need(bmb * 4 * chunk);
+        void* ws;
+        LLFE_TRY(llfe_workspace(ctx, need, &ws));
+        WsCarver carve(ws);
+        uint32_t* weak = carve.take<uint32_t>(plane_words);
+        uint32_t* edges = carve.take<uint32_t>(plane_words);
+        uint32_t* flags = carve.take<uint32_t>(hysteresis_flag_words(chunk, h));
+        uint32_t* bitmap = d_keys ? carve.take<uint32_t>(bmw * chunk) : nullptr;
+        uint32_t* bsum = d_keys ? carve.take<uint32_t>(bmb * chunk) : nullptr;
+        const size_t p = (size_t)h * w;
+        for (int i0 = 0; i0 < n; i0 += chunk) {
+            const int m = (n - i0) < chunk ? (n - i0) : chunk;
+            if (d_keys) LLFE_CUDA(cudaMemsetAsync(bitmap, 0, bmw * 4 * m, ctx->stream));
+            LLFE_TRY(launch_fused(ctx, d_bgr + i0 * p * 3, m, h, w, low, high, d_shape_mask ? weak : nullptr,
+                                  d_shape_mask ? edges : nullptr, d_shadow_mask ? d_shadow_mask + i0 * p : nullptr,
+                                  d_shadow_sum_count ? d_shadow_sum_count + 2 * i0 : nullptr,
+                                  d_noise ? d_noise + i0 * p * 3 : nullptr, seed, i0, bitmap));
+            if (d_shape_mask) {
+                LLFE_TRY(launch_hysteresis(ctx, weak, edges, m, h, w, flags));
+                LLFE_TRY(launch_plane_to_mask(ctx, edges, m, h, w, 1, d_shape_mask + i0 * p));
+            }
+            if (d_keys)
+                LLFE_TRY(launch_bitmap_compact(ctx, bitmap, bsum, m, d_keys + (size_t)i0 * max_unique, nullptr,
+                                               d_count + i0, max_unique));
+        }
+        return LLFE_OK;
+    }
     if (d_shape_mask || d_shadow_mask) {
         // gray + blur once, shared by the edge chain and the adaptive threshold
         const size_t img = WsCarver::need((size_t)n * h * w);

@@ -121,3 +121,12 @@ int launch_dilate3_u8(llfe_ctx* ctx, const uint8_t* src, int n, int h, int w, ui
 void llfe_free_area_tabs(llfe_ctx* ctx);
 int launch_unique_colors(llfe_ctx* ctx, const uint8_t* d_bgr, int n, int h, int w, const int8_t* d_noise, uint64_t seed,
                          uint32_t* d_keys, uint32_t* d_hist, int32_t* d_count, int max_unique);
+
+size_t bitmap_words_per_image();
+size_t bitmap_blocks_per_image();
+int launch_bitmap_compact(llfe_ctx* ctx, const uint32_t* bitmap, uint32_t* bsum, int m, uint32_t* d_keys, uint32_t* rank,
+                          int32_t* d_count, int max_unique);
+bool fused_supported(int h, int w);
+int launch_fused(llfe_ctx* ctx, const uint8_t* bgr, int n, int h, int w, int low, int high, uint32_t* weak,
+                 uint32_t* strong, uint8_t* mask, uint64_t* sum_count, const int8_t* noise, uint64_t seed, int img0,
+                 uint32_t* bitmap);

@@ -78,3 +78,44 @@ __device__ __forceinline__ unsigned long long warp_sum_u64(unsigned long long v)
     for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
     return v;
 }
+
+// ---- palette noise (shared by k_palette.cu and k_fused.cu) -----------------------------
+__device__ __forceinline__ uint32_t fmix32(uint32_t x) {
+    x ^= x >> 16;
+    x *= 0x85ebca6bu;
+    x ^= x >> 13;
+    x *= 0xc2b2ae35u;
+    x ^= x >> 16;
+    return x;
+}
+
+// Device-generated noise with the distribution of  int8(trunc(N(0, 0.5)))  :
+// P(+-1) = 0.0227501 each, P(+-2) = 3.167e-5 each (|n| >= 3: 1e-9, dropped), quantised
+// to 2^-21.  Counter-based: a function of (seed, pixel index) only, so every pass
+// over the image regenerates the same noise.  NOT NumPy's MT19937 stream.
+__device__ __forceinline__ int noise21(uint32_t u21) {
+    // thresholds on a 21-bit uniform: [0,T1) -> +1, [T1,2T1) -> -1, [2T1,2T1+T2) -> +2, [..,2T1+2T2) -> -2
+    constexpr uint32_t T1 = 47710;  // round(0.02275013 * 2^21)
+    constexpr uint32_t T2 = 66;     // round(3.1671e-5 * 2^21)
+    if (u21 >= 2 * T1 + 2 * T2) return 0;
+    if (u21 < T1) return 1;
+    if (u21 < 2 * T1) return -1;
+    if (u21 < 2 * T1 + T2) return 2;
+    return -2;
+}
+
+__device__ __forceinline__ void device_noise(uint64_t seed, uint64_t pix, int& nr, int& ng, int& nb) {
+    uint32_t lo = (uint32_t)pix, hi = (uint32_t)(pix >> 32);
+    uint32_t a = fmix32(lo * 0x9E3779B1u ^ (uint32_t)seed ^ (hi * 0x7F4A7C15u));
+    uint32_t b = fmix32(a ^ (uint32_t)(seed >> 32) ^ 0x68E31DA4u);
+    uint64_t r = ((uint64_t)a << 32) | b;
+    nr = noise21((uint32_t)(r & 0x1fffff));
+    ng = noise21((uint32_t)((r >> 21) & 0x1fffff));
+    nb = noise21((uint32_t)((r >> 42) & 0x1fffff));
+}
+
+__device__ __forceinline__ uint32_t noisy_key(uint32_t b, uint32_t g, uint32_t r, int nr, int ng, int nb) {
+    int R = min(max((int)r + nr, 0), 255), G = min(max((int)g + ng, 0), 255), B = min(max((int)b + nb, 0), 255);
+    return ((uint32_t)R << 16) | ((uint32_t)G << 8) | (uint32_t)B;
+}
+
