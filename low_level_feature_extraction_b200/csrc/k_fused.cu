@@ -69,50 +69,103 @@ struct FusedArgs {
 };
 
 // ---------------------------------------------------------------------------------------
-// gray row: 8 pixels of one lane (24 bytes, three 64-bit loads) -> Q4; optional colour pass
+// One lane's 8 pixels of a row as loaded: 24 bytes of BGR (+ 24 bytes of injected noise).
+struct Raw {
+    uint32_t w[6];
+    uint32_t nz[6];
+};
+
 template <bool COLORS>
-__device__ __forceinline__ Q4 load_gray(const FusedArgs& A, int img, int y, int x, bool in_x, bool own_row) {
-    Q4 g = {0u, 0u, 0u, 0u};
-    if (in_x) {
-        const uint2* p = reinterpret_cast<const uint2*>(A.bgr + ((size_t)img * A.h * A.w + (size_t)y * A.w + x) * 3);
-        const uint2 a = p[0], b = p[1], c = p[2];
-        uint32_t t0, t1, t2, t3, t4, t5, t6, t7;
-        gray4_sums(a.x, a.y, b.x, t0, t1, t2, t3);
-        gray4_sums(b.y, c.x, c.y, t4, t5, t6, t7);
-        g.p0 = __byte_perm(t0, t1, 0x7632);
-        g.p1 = __byte_perm(t2, t3, 0x7632);
-        g.p2 = __byte_perm(t4, t5, 0x7632);
-        g.p3 = __byte_perm(t6, t7, 0x7632);
-        if (COLORS && own_row) {
-            const uint32_t wds[6] = {a.x, a.y, b.x, b.y, c.x, c.y};
-            uint32_t* bm = A.bitmap + (size_t)img * (1u << 19);
-            const size_t pix0 = (size_t)y * A.w + x;
-            uint32_t nw[6];
-            if (A.noise) {
-                const uint2* q = reinterpret_cast<const uint2*>(A.noise + ((size_t)img * A.h * A.w + pix0) * 3);
-                const uint2 na = q[0], nb = q[1], nc = q[2];
-                nw[0] = na.x; nw[1] = na.y; nw[2] = nb.x; nw[3] = nb.y; nw[4] = nc.x; nw[5] = nc.y;
-            }
+__device__ __forceinline__ void issue_row(const FusedArgs& A, int img, int y, int x, bool in_x, bool own, Raw& r) {
 #pragma unroll
-            for (int j = 0; j < 8; ++j) {
-                // byte k of the 24-byte group
-                auto byte_at = [&](const uint32_t* arr, int k) -> uint32_t { return (arr[k >> 2] >> (8 * (k & 3))) & 255u; };
-                const uint32_t bb = byte_at(wds, 3 * j), gg = byte_at(wds, 3 * j + 1), rr = byte_at(wds, 3 * j + 2);
-                int nr, ng, nbv;
-                if (A.noise) {
-                    nr = (int)(int8_t)byte_at(nw, 3 * j);       // noise is in RGB order
-                    ng = (int)(int8_t)byte_at(nw, 3 * j + 1);
-                    nbv = (int)(int8_t)byte_at(nw, 3 * j + 2);
-                } else {
-                    device_noise(A.seed, (uint64_t)(A.img0 + img) * ((size_t)A.h * A.w) + pix0 + j, nr, ng, nbv);
-                }
-                const uint32_t key = noisy_key(bb, gg, rr, nr, ng, nbv);
-                const uint32_t wi = key >> 5, bit = 1u << (key & 31);
-                if (!(bm[wi] & bit)) atomicOr(&bm[wi], bit);
-            }
+    for (int k = 0; k < 6; ++k) r.w[k] = 0u;
+    if (in_x) {
+        const size_t pix0 = (size_t)img * A.h * A.w + (size_t)y * A.w + x;
+        const uint2* p = reinterpret_cast<const uint2*>(A.bgr + pix0 * 3);
+        const uint2 a = p[0], b = p[1], c = p[2];
+        r.w[0] = a.x; r.w[1] = a.y; r.w[2] = b.x; r.w[3] = b.y; r.w[4] = c.x; r.w[5] = c.y;
+        if (COLORS && own && A.noise) {
+            const uint2* q = reinterpret_cast<const uint2*>(A.noise + pix0 * 3);
+            const uint2 na = q[0], nb = q[1], nc = q[2];
+            r.nz[0] = na.x; r.nz[1] = na.y; r.nz[2] = nb.x; r.nz[3] = nb.y; r.nz[4] = nc.x; r.nz[5] = nc.y;
         }
     }
+}
+
+__device__ __forceinline__ Q4 gray_of(const Raw& r) {
+    uint32_t t0, t1, t2, t3, t4, t5, t6, t7;
+    gray4_sums(r.w[0], r.w[1], r.w[2], t0, t1, t2, t3);
+    gray4_sums(r.w[3], r.w[4], r.w[5], t4, t5, t6, t7);
+    Q4 g;
+    g.p0 = __byte_perm(t0, t1, 0x7632);
+    g.p1 = __byte_perm(t2, t3, 0x7632);
+    g.p2 = __byte_perm(t4, t5, 0x7632);
+    g.p3 = __byte_perm(t6, t7, 0x7632);
     return g;
+}
+
+// the 8 pixels of 6 packed words as 24-bit values (byte 0 first): B | G<<8 | R<<16 for image words
+__device__ __forceinline__ void unpack24(const uint32_t* w, uint32_t* o) {
+    o[0] = w[0] & 0xffffffu;
+    o[1] = __byte_perm(w[0], w[1], 0x0543) & 0xffffffu;
+    o[2] = __byte_perm(w[1], w[2], 0x0432) & 0xffffffu;
+    o[3] = w[2] >> 8;
+    o[4] = w[3] & 0xffffffu;
+    o[5] = __byte_perm(w[3], w[4], 0x0543) & 0xffffffu;
+    o[6] = __byte_perm(w[4], w[5], 0x0432) & 0xffffffu;
+    o[7] = w[5] >> 8;
+}
+
+// Colour bitmap update, split in two so that the 8 bitmap loads of a row are in flight while
+// the row's stencil work runs: issue (keys + loads) now, commit (test + rare atomicOr) a row later.
+struct ColorPending {
+    uint32_t key[8];
+    uint32_t val[8];
+};
+
+__device__ __forceinline__ uint32_t noisy_key(uint32_t b, uint32_t g, uint32_t r, int nr, int ng, int nb) {
+    int R = min(max((int)r + nr, 0), 255), G = min(max((int)g + ng, 0), 255), B = min(max((int)b + nb, 0), 255);
+    return ((uint32_t)R << 16) | ((uint32_t)G << 8) | (uint32_t)B;
+}
+
+__device__ __forceinline__ void color_issue(const FusedArgs& A, int img, int y, int x, const Raw& r, ColorPending& cp,
+                                            uint8_t* my24) {
+    // BGR bytes in memory order are already the key layout: B | G<<8 | R<<16
+    if (A.noise) {
+        unpack24(r.w, cp.key);
+        uint32_t n24[8];
+        unpack24(r.nz, n24);  // noise is stored in RGB order: byte 0 -> R
+#pragma unroll
+        for (int j = 0; j < 8; ++j)
+            if (n24[j]) {
+                const uint32_t k = cp.key[j];
+                cp.key[j] = noisy_key(k & 255u, (k >> 8) & 255u, k >> 16, (int)(int8_t)(n24[j] & 255u),
+                                      (int)(int8_t)((n24[j] >> 8) & 255u), (int)(int8_t)(n24[j] >> 16));
+            }
+    } else {
+        // device noise: sparse geometric-skip draws applied to this lane's 24 bytes in shared memory
+        uint2* slot = reinterpret_cast<uint2*>(my24);
+        slot[0] = make_uint2(r.w[0], r.w[1]);
+        slot[1] = make_uint2(r.w[2], r.w[3]);
+        slot[2] = make_uint2(r.w[4], r.w[5]);
+        const uint64_t pix0 = (uint64_t)(A.img0 + img) * ((size_t)A.h * A.w) + (size_t)y * A.w + x;
+        noise_apply_group(A.seed, pix0 >> 3, my24);
+        const uint2 a = slot[0], b = slot[1], c = slot[2];
+        const uint32_t w[6] = {a.x, a.y, b.x, b.y, c.x, c.y};
+        unpack24(w, cp.key);
+    }
+    const uint32_t* bm = A.bitmap + (size_t)img * (1u << 19);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) cp.val[j] = bm[cp.key[j] >> 5];
+}
+
+__device__ __forceinline__ void color_commit(const FusedArgs& A, int img, const ColorPending& cp) {
+    uint32_t* bm = A.bitmap + (size_t)img * (1u << 19);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+        const uint32_t bit = 1u << (cp.key[j] & 31u);
+        if (!(cp.val[j] & bit)) atomicOr(&bm[cp.key[j] >> 5], bit);  // a stale word only costs a redundant atomic
+    }
 }
 
 // horizontal [1,4,6,4,1] on a gray row (16-bit lanes, max 4080)
@@ -224,7 +277,10 @@ __device__ __forceinline__ float u2f(uint32_t v) { return __uint_as_float(0x4b00
 
 template <bool EDGES, bool SHADOW, bool COLORS>
 __global__ void __launch_bounds__(WARPS * 32) k_fused(FusedArgs A) {
-    extern __shared__ float4 ring_all[];  // SHADOW: [warp][RING][3][32] float4 (2 x floats, 1 x blurred bytes)
+    // dynamic shared memory: [128 lanes][24 B] colour scratch, then SHADOW: [warp][RING][3][32] float4
+    extern __shared__ float4 dyn_smem[];
+    uint8_t* my24 = reinterpret_cast<uint8_t*>(dyn_smem) + threadIdx.x * 24;
+    float4* ring_all = dyn_smem + (WARPS * 32 * 24) / 16;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int img = blockIdx.z;
     const int W = A.w, H = A.h;
@@ -251,13 +307,30 @@ __global__ void __launch_bounds__(WARPS * 32) k_fused(FusedArgs A) {
     gprev.ax = gprev.ay = gprev.sg = gcur.ax = gcur.ay = gcur.sg = Q4{0u, 0u, 0u, 0u};
     Q4 blurred = {0u, 0u, 0u, 0u};
     uint32_t lsum = 0, lcnt = 0;
+    int ring_slot = RING - 1;
     int rb_prev = 0;
     bool primed = false;
 
-    auto gray_row = [&](int vy) -> Q4 {
-        // virtual gray row vy: BORDER_REFLECT_101 in y; in x the halo lanes are patched below
-        const int yy = reflect101(vy, H);
-        Q4 g = load_gray<COLORS>(A, img, yy, x, in_x, COLORS && out_lane && vy >= y0 && vy < y1);
+    // Row feed with one row of prefetch: the words of gray row `next_vy` are already in flight
+    // while the previous row is being processed.
+    const int vy_last = clampi(vb_hi, 0, H - 1) + 2;
+    int next_vy = clampi(vb_lo, 0, H - 1) - 2;
+    Raw raw_next;
+    ColorPending pend;
+    bool have_pend = false;
+    auto own_row = [&](int vy) { return COLORS && out_lane && vy >= y0 && vy < y1; };
+    issue_row<COLORS>(A, img, reflect101(next_vy, H), x, in_x, own_row(next_vy), raw_next);
+    auto gray_row = [&]() -> Q4 {
+        const Raw cur = raw_next;
+        const int vy = next_vy++;
+        if (next_vy <= vy_last) issue_row<COLORS>(A, img, reflect101(next_vy, H), x, in_x, own_row(next_vy), raw_next);
+        if (COLORS) {
+            if (have_pend) color_commit(A, img, pend);
+            have_pend = own_row(vy);
+            if (have_pend) color_issue(A, img, vy, x, cur, pend, my24);
+        }
+        // virtual gray row vy: BORDER_REFLECT_101 in y (done by the loader); in x the halo lanes are patched here
+        Q4 g = gray_of(cur);
         if (left_edge) {   // lane 0 holds pixels -8..-1: (-2,-1) := (2,1)
             const uint32_t n0 = __shfl_down_sync(FULL, g.p0, 1), n1 = __shfl_down_sync(FULL, g.p1, 1);
             if (x == -8) g.p3 = lo16(n1) | (n0 & 0xffff0000u);
@@ -275,13 +348,13 @@ __global__ void __launch_bounds__(WARPS * 32) k_fused(FusedArgs A) {
             if (!primed) {
                 primed = true;
 #pragma unroll
-                for (int k = 0; k < 5; ++k) hb[k] = hblur(gray_row(rb - 2 + k));
+                for (int k = 0; k < 5; ++k) hb[k] = hblur(gray_row());
             } else {
                 hb[0] = hb[1];
                 hb[1] = hb[2];
                 hb[2] = hb[3];
                 hb[3] = hb[4];
-                hb[4] = hblur(gray_row(rb + 2));
+                hb[4] = hblur(gray_row());
             }
             rb_prev = rb;
             blurred = vblur(hb);
@@ -370,8 +443,9 @@ __global__ void __launch_bounds__(WARPS * 32) k_fused(FusedArgs A) {
                 acc = __fmaf_rn(f[j + 10], GK0, acc);
                 r[j] = acc;
             }
-            int slot = vb % RING;
-            if (slot < 0) slot += RING;
+            // ring slot of row vb: a running counter (no modulo in the loop)
+            ring_slot = ring_slot + 1 == RING ? 0 : ring_slot + 1;
+            const int slot = ring_slot;
             float4* rs = ring + (size_t)slot * 3 * 32 + lane;
             rs[0] = make_float4(r[0], r[1], r[2], r[3]);
             rs[32] = make_float4(r[4], r[5], r[6], r[7]);
@@ -380,8 +454,9 @@ __global__ void __launch_bounds__(WARPS * 32) k_fused(FusedArgs A) {
             const int va = vb - 5;
             if (vb >= vb_lo + 10 && va >= y0 && va < y1 && out_lane) {
                 float v[8];
+                // row va + d sits (5 - d) slots behind the newest row (slot of vb = va + 5)
                 auto row_at = [&](int d, float* o) {
-                    int s = (va + d) % RING;
+                    int s = slot - (5 - d);
                     if (s < 0) s += RING;
                     const float4* p = ring + (size_t)s * 3 * 32 + lane;
                     const float4 a = p[0], b = p[32];
@@ -400,7 +475,7 @@ __global__ void __launch_bounds__(WARPS * 32) k_fused(FusedArgs A) {
 #pragma unroll
                     for (int j = 0; j < 8; ++j) v[j] = __fmaf_rn(__fadd_rn(dn[j], up[j]), kk[i - 1], v[j]);
                 }
-                int sc = va % RING;
+                int sc = slot - 5;
                 if (sc < 0) sc += RING;
                 const float4 cb = ring[(size_t)sc * 3 * 32 + 64 + lane];
                 const uint32_t cp[4] = {__float_as_uint(cb.x), __float_as_uint(cb.y), __float_as_uint(cb.z), __float_as_uint(cb.w)};
@@ -422,6 +497,7 @@ __global__ void __launch_bounds__(WARPS * 32) k_fused(FusedArgs A) {
             }
         }
     }
+    if (COLORS && have_pend) color_commit(A, img, pend);
     if (SHADOW) {
         lsum = warp_sum_u32(lsum);
         lcnt = warp_sum_u32(lcnt);
@@ -479,7 +555,7 @@ int launch_fused(llfe_ctx* ctx, const uint8_t* bgr, int n, int h, int w, int low
     while (bands > 1 && h / bands < 48) bands >>= 1;
     A.rows_per_band = ceil_div(h, bands);
     dim3 grid(ceil_div(w, BAND_W), ceil_div(h, A.rows_per_band), n);
-    const size_t smem = S ? (size_t)WARPS * RING * 3 * 32 * sizeof(float4) : 0;
+    const size_t smem = (size_t)WARPS * 32 * 24 + (S ? (size_t)WARPS * RING * 3 * 32 * sizeof(float4) : 0);
     if (S && sum_count) LLFE_CUDA(cudaMemsetAsync(sum_count, 0, (size_t)n * 2 * sizeof(uint64_t), ctx->stream));
     if (E && (w % 32)) {  // the kernel writes whole bytes of in-image pixels only: clear the padding bits
         const size_t pb = (size_t)n * h * plane_wpr(w) * sizeof(uint32_t);

@@ -15,7 +15,13 @@ constexpr int BM_WORDS = 1 << 19;    // 2^24 bits
 constexpr int BM_BLOCK = 1024;       // words per scan block
 constexpr int BM_NBLK = BM_WORDS / BM_BLOCK;  // 512
 
+__device__ __forceinline__ uint32_t noisy_key(uint32_t b, uint32_t g, uint32_t r, int nr, int ng, int nb) {
+    int R = min(max((int)r + nr, 0), 255), G = min(max((int)g + ng, 0), 255), B = min(max((int)b + nb, 0), 255);
+    return ((uint32_t)R << 16) | ((uint32_t)G << 8) | (uint32_t)B;
+}
+
 // MODE 0: set bitmap bits.  MODE 1: histogram pixels into hist[rank(key)].
+// One thread per group of 8 consecutive pixels (the unit of the device noise generator).
 template <int MODE>
 __global__ void __launch_bounds__(256) k_color_pass(const uint8_t* __restrict__ bgr, size_t npix,
                                                     const int8_t* __restrict__ noise, uint64_t seed, int img0,
@@ -27,24 +33,34 @@ __global__ void __launch_bounds__(256) k_color_pass(const uint8_t* __restrict__ 
     uint32_t* bm = bitmap + (size_t)img * BM_WORDS;
     const uint32_t* rk = MODE == 1 ? rank + (size_t)img * BM_WORDS : nullptr;
     uint32_t* hs = MODE == 1 ? hist + (size_t)img * max_unique : nullptr;
+    const size_t ngroups = (npix + 7) / 8;
     const size_t stride = (size_t)gridDim.x * 256;
-    for (size_t p = blockIdx.x * (size_t)256 + threadIdx.x; p < npix; p += stride) {
-        uint32_t b = s[3 * p], g = s[3 * p + 1], r = s[3 * p + 2];
-        int nr, ng, nb;
+    for (size_t g = blockIdx.x * (size_t)256 + threadIdx.x; g < ngroups; g += stride) {
+        const size_t p0 = g * 8;
+        const int np = (int)(npix - p0 < 8 ? npix - p0 : 8);
+        uint8_t px[24];
+        for (int k = 0; k < 3 * np; ++k) px[k] = s[3 * p0 + k];
         if (nz) {
-            nr = nz[3 * p];
-            ng = nz[3 * p + 1];
-            nb = nz[3 * p + 2];
+            // injected noise is in RGB order, the image bytes in BGR order
+            for (int j = 0; j < np; ++j) {
+                const uint32_t key = noisy_key(px[3 * j], px[3 * j + 1], px[3 * j + 2], nz[3 * (p0 + j)],
+                                               nz[3 * (p0 + j) + 1], nz[3 * (p0 + j) + 2]);
+                px[3 * j] = (uint8_t)key;
+                px[3 * j + 1] = (uint8_t)(key >> 8);
+                px[3 * j + 2] = (uint8_t)(key >> 16);
+            }
         } else {
-            device_noise(seed, (uint64_t)(img0 + img) * npix + p, nr, ng, nb);
+            noise_apply_group(seed, ((uint64_t)(img0 + img) * npix + p0) >> 3, px, 3 * np);
         }
-        uint32_t key = noisy_key(b, g, r, nr, ng, nb);
-        uint32_t wi = key >> 5, bit = 1u << (key & 31);
-        if (MODE == 0) {
-            if (!(bm[wi] & bit)) atomicOr(&bm[wi], bit);  // stale reads only cost a redundant atomic
-        } else {
-            uint32_t idx = rk[wi] + __popc(bm[wi] & (bit - 1));
-            if (idx < (uint32_t)max_unique) atomicAdd(&hs[idx], 1u);
+        for (int j = 0; j < np; ++j) {
+            const uint32_t key = (uint32_t)px[3 * j] | ((uint32_t)px[3 * j + 1] << 8) | ((uint32_t)px[3 * j + 2] << 16);
+            const uint32_t wi = key >> 5, bit = 1u << (key & 31);
+            if (MODE == 0) {
+                if (!(bm[wi] & bit)) atomicOr(&bm[wi], bit);  // stale reads only cost a redundant atomic
+            } else {
+                uint32_t idx = rk[wi] + __popc(bm[wi] & (bit - 1));
+                if (idx < (uint32_t)max_unique) atomicAdd(&hs[idx], 1u);
+            }
         }
     }
 }
@@ -142,7 +158,7 @@ int launch_unique_colors(llfe_ctx* ctx, const uint8_t* d_bgr, int n, int h, int 
     uint32_t* rank = with_rank ? carve.take<uint32_t>((size_t)BM_WORDS * chunk) : nullptr;
     uint32_t* bsum = carve.take<uint32_t>((size_t)BM_NBLK * chunk);
     if (d_hist) LLFE_CUDA(cudaMemsetAsync(d_hist, 0, (size_t)n * max_unique * sizeof(uint32_t), ctx->stream));
-    size_t want = ceil_div_sz(npix, 256 * 8);
+    size_t want = ceil_div_sz(npix, 256 * 8 * 2);
     unsigned gx = (unsigned)(want < 1 ? 1 : (want > 4096 ? 4096 : want));
     for (int i0 = 0; i0 < n; i0 += chunk) {
         const int m = (n - i0) < chunk ? (n - i0) : chunk;

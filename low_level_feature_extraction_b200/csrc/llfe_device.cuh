@@ -89,33 +89,45 @@ __device__ __forceinline__ uint32_t fmix32(uint32_t x) {
     return x;
 }
 
-// Device-generated noise with the distribution of  int8(trunc(N(0, 0.5)))  :
-// P(+-1) = 0.0227501 each, P(+-2) = 3.167e-5 each (|n| >= 3: 1e-9, dropped), quantised
-// to 2^-21.  Counter-based: a function of (seed, pixel index) only, so every pass
-// over the image regenerates the same noise.  NOT NumPy's MT19937 stream.
-__device__ __forceinline__ int noise21(uint32_t u21) {
-    // thresholds on a 21-bit uniform: [0,T1) -> +1, [T1,2T1) -> -1, [2T1,2T1+T2) -> +2, [..,2T1+2T2) -> -2
-    constexpr uint32_t T1 = 47710;  // round(0.02275013 * 2^21)
-    constexpr uint32_t T2 = 66;     // round(3.1671e-5 * 2^21)
-    if (u21 >= 2 * T1 + 2 * T2) return 0;
-    if (u21 < T1) return 1;
-    if (u21 < 2 * T1) return -1;
-    if (u21 < 2 * T1 + T2) return 2;
-    return -2;
+// Device-generated noise with the distribution of  int8(trunc(N(0, 0.5)))  per channel sample:
+// P(non-zero) = p = 0.0455629 (+-1: 0.0227501 each, +-2: 3.167e-5 each; |n| >= 3 has 1e-9 and is
+// dropped), independent across samples.  NOT NumPy's MT19937 stream.
+//
+// Non-zero samples are rare, so they are drawn SPARSELY: the 24 channel samples of a group of
+// 8 consecutive pixels (linear pixel index >> 3) are visited by geometric skips -- the number
+// of zero samples before the next non-zero one is G = floor(log(u) / log(1 - p)) for uniform u,
+// which reproduces independent Bernoulli(p) samples exactly (memorylessness) at ~1.1 draws per
+// group instead of 24.  Every draw is a counter-based hash of (seed, group index, draw index),
+// so the noise is a pure function of the seed and the pixel position: any kernel, any launch
+// shape and any pass over the image regenerates the same values.
+#define LLFE_NOISE_INV_LOG2_Q (-14.863987f) /* 1 / log2(1 - 0.0455629) */
+
+__device__ __forceinline__ uint32_t noise_group_base(uint64_t seed, uint64_t group) {
+    return (uint32_t)group + (uint32_t)seed * 0x9E3779B1u + ((uint32_t)(group >> 32) ^ (uint32_t)(seed >> 32)) * 0x7F4A7C15u;
 }
 
-__device__ __forceinline__ void device_noise(uint64_t seed, uint64_t pix, int& nr, int& ng, int& nb) {
-    uint32_t lo = (uint32_t)pix, hi = (uint32_t)(pix >> 32);
-    uint32_t a = fmix32(lo * 0x9E3779B1u ^ (uint32_t)seed ^ (hi * 0x7F4A7C15u));
-    uint32_t b = fmix32(a ^ (uint32_t)(seed >> 32) ^ 0x68E31DA4u);
-    uint64_t r = ((uint64_t)a << 32) | b;
-    nr = noise21((uint32_t)(r & 0x1fffff));
-    ng = noise21((uint32_t)((r >> 21) & 0x1fffff));
-    nb = noise21((uint32_t)((r >> 42) & 0x1fffff));
+// draw #i of a group: returns the skip (zeros before the next non-zero sample) and its value
+__device__ __forceinline__ int noise_draw(uint32_t base, int i, int& value) {
+    const uint32_t h = fmix32(base + (uint32_t)(i + 1) * 0x85EBCA77u);
+    const float u = __fmul_rn(__fadd_rn((float)(h >> 9), 0.5f), 1.0f / 8388608.0f);  // (0, 1), 23 bits
+    const int skip = (int)__fmul_rn(__log2f(u), LLFE_NOISE_INV_LOG2_Q);               // floor: the product is >= 0
+    const uint32_t m = (h * 0x9E3779B1u) >> 16;                                   // 16 fresh-ish bits for the magnitude
+    const int mag = 1 + (m < 91u);                                                // P(|n| = 2 | n != 0) = 1.39e-3
+    value = (h & 0x100u) ? mag : -mag;                                            // bit 8: unused by u, sign
+    return skip;
 }
 
-__device__ __forceinline__ uint32_t noisy_key(uint32_t b, uint32_t g, uint32_t r, int nr, int ng, int nb) {
-    int R = min(max((int)r + nr, 0), 255), G = min(max((int)g + ng, 0), 255), B = min(max((int)b + nb, 0), 255);
-    return ((uint32_t)R << 16) | ((uint32_t)G << 8) | (uint32_t)B;
+// Apply the group's noise to its 24 bytes held in memory `bytes` (any address space), byte k =
+// channel sample k of the group in MEMORY order (pixel-major, channel-minor as stored).
+template <typename BytePtr>
+__device__ __forceinline__ void noise_apply_group(uint64_t seed, uint64_t group, BytePtr bytes, int n_valid = 24) {
+    const uint32_t base = noise_group_base(seed, group);
+    int pos = -1;
+    for (int i = 0; i < 24; ++i) {
+        int v;
+        pos += 1 + noise_draw(base, i, v);
+        if (pos >= n_valid) break;
+        const int nv = (int)bytes[pos] + v;
+        bytes[pos] = (uint8_t)min(max(nv, 0), 255);
+    }
 }
-
