@@ -93,8 +93,9 @@ __global__ void __launch_bounds__(256) k_canny_front(const uint8_t* __restrict__
 }
 
 // ------------------------------------------------------------- hysteresis ---
-constexpr int HROWS = 32;      // rows per strip
-constexpr int HTHREADS = 256;  // threads per CTA
+constexpr int HTHREADS = 256;        // threads per CTA
+constexpr int HROWS_MAX = 256;       // rows per strip (halved until the strip fits in shared memory)
+constexpr int HROWS_MIN = 8;
 
 // fill `e` along runs of `w` inside one 32-bit word (both directions), e subset of w
 __device__ __forceinline__ uint32_t fill_word(uint32_t e, uint32_t w) {
@@ -123,51 +124,79 @@ __device__ __forceinline__ uint32_t fill_word(uint32_t e, uint32_t w) {
     return g1 | g2;
 }
 
-// shared-memory pitch (words) of a strip row: odd, so that row-parallel sweeps hit distinct banks
+// shared-memory pitch (words) of a strip row: odd, to spread rows over the banks
 __host__ __device__ static inline int strip_pitch(int wpr) { return wpr | 1; }
 
-// Grow word (r, c) of the strip from its 8-neighbourhood; returns true if it changed.
-//   sw : weak rows [rows][sp]      se : edge rows [rows + 2][sp] (row 0 / rows+1 = halos)
-__device__ __forceinline__ bool grow_word(const uint32_t* sw, uint32_t* se, int r, int c, int wpr, int sp) {
-    const uint32_t wv = sw[r * sp + c];
-    const uint32_t e = se[(r + 1) * sp + c];
+// A strip in shared memory:
+//   se   : edge rows [rows + 2][sp]  (row 0 / rows+1 = halo rows of the neighbouring strips)
+//   lpos : candidate words (weak bits that are not edges yet) as (row << 10 | word column)
+//   lw   : their weak words
+// Only candidate words can ever change, and on real images they are a small fraction of the
+// strip, so every iteration touches just that list (one thread per candidate word, 32 pixels
+// filled per step by fill_word).  Updates are monotone (bits are only set), so unsynchronised
+// neighbour reads are benign; the loop ends after an iteration in which nothing changed.
+struct Strip {
+    uint32_t* se;
+    uint32_t* lpos;
+    uint32_t* lw;
+};
+
+__device__ __forceinline__ Strip carve_strip(uint32_t* sm, int hrows, int wpr, int sp) {
+    Strip s;
+    s.se = sm;
+    s.lpos = sm + (hrows + 2) * sp;
+    s.lw = s.lpos + hrows * wpr;
+    return s;
+}
+
+__device__ __forceinline__ bool grow_word(uint32_t wv, uint32_t* se, int r, int c, int wpr, int sp) {
+    uint32_t* mid = se + (r + 1) * sp;
+    const uint32_t e = mid[c];
     if ((wv & ~e) == 0) return false;
-    const uint32_t* up = se + r * sp;
-    const uint32_t* mid = up + sp;
+    const uint32_t* up = mid - sp;
     const uint32_t* dn = mid + sp;
-    uint32_t v = up[c] | mid[c] | dn[c];
+    uint32_t v = up[c] | e | dn[c];
     uint32_t spread = v | (v << 1) | (v >> 1);
     if (c > 0) spread |= (up[c - 1] | mid[c - 1] | dn[c - 1]) >> 31;
     if (c + 1 < wpr) spread |= (up[c + 1] | mid[c + 1] | dn[c + 1]) << 31;
-    uint32_t ne = e | (wv & spread);
+    const uint32_t ne = e | (wv & spread);
     if (ne == e) return false;
-    se[(r + 1) * sp + c] = fill_word(ne, wv);
+    mid[c] = fill_word(ne, wv);
     return true;
 }
 
-// Converge one strip held in shared memory.  Only CANDIDATE words (weak bits that are not
-// edges yet) can ever change, and on real images they are a small fraction of the strip, so
-// they are compacted into a work list once and every iteration touches just that list (one
-// thread per candidate word, 32 pixels filled per step by fill_word).  Updates are monotone
-// (bits are only set), so unsynchronised neighbour reads are benign; the loop ends after an
-// iteration in which nothing changed.  Returns true if anything changed.
-__device__ bool converge_strip(const uint32_t* sw, uint32_t* se, int rows, int wpr, int sp, uint16_t* list,
-                               int* s_n) {
+// Load the edge rows (+ halos) of a strip and build its candidate list.  Returns the list length.
+__device__ int load_strip(const uint32_t* __restrict__ weak, const uint32_t* edges, int h, int wpr, int sp, int r0,
+                          int rows, const Strip& st, int* s_n) {
     if (threadIdx.x == 0) *s_n = 0;
+    for (int i = threadIdx.x; i < (rows + 2) * wpr; i += blockDim.x) {
+        int r = i / wpr, c = i - r * wpr;
+        int rr = r0 - 1 + r;
+        uint32_t v = 0;
+        if (rr >= 0 && rr < h) v = __ldcg(edges + (size_t)rr * wpr + c);
+        st.se[r * sp + c] = v;
+    }
     __syncthreads();
     for (int i = threadIdx.x; i < rows * wpr; i += blockDim.x) {
         int r = i / wpr, c = i - r * wpr;
-        if (sw[r * sp + c] & ~se[(r + 1) * sp + c]) list[atomicAdd(s_n, 1)] = (uint16_t)((r << 9) | c);
+        const uint32_t wv = weak[(size_t)(r0 + r) * wpr + c];
+        if (wv & ~st.se[(r + 1) * sp + c]) {
+            const int k = atomicAdd(s_n, 1);
+            st.lpos[k] = ((uint32_t)r << 10) | (uint32_t)c;
+            st.lw[k] = wv;
+        }
     }
     __syncthreads();
-    const int n = *s_n;
+    return *s_n;
+}
+
+__device__ bool converge_strip(const Strip& st, int n, int wpr, int sp) {
     bool any = false;
-    if (n == 0) return false;
     for (;;) {
         bool changed = false;
         for (int j = threadIdx.x; j < n; j += blockDim.x) {
-            int rc = list[j];
-            changed |= grow_word(sw, se, rc >> 9, rc & 511, wpr, sp);
+            const uint32_t pos = st.lpos[j];
+            changed |= grow_word(st.lw[j], st.se, (int)(pos >> 10), (int)(pos & 1023u), wpr, sp);
         }
         if (!__syncthreads_or(changed)) break;
         any = true;
@@ -175,30 +204,15 @@ __device__ bool converge_strip(const uint32_t* sw, uint32_t* se, int rows, int w
     return any;
 }
 
-// Load a strip (weak rows, edge rows + halos) into shared memory.
-__device__ void load_strip(const uint32_t* __restrict__ weak, const uint32_t* edges, int h, int wpr, int sp, int r0,
-                           int rows, uint32_t* sw, uint32_t* se) {
-    for (int i = threadIdx.x; i < rows * wpr; i += blockDim.x) {
-        int r = i / wpr, c = i - r * wpr;
-        sw[r * sp + c] = weak[(size_t)(r0 + r) * wpr + c];
-    }
-    for (int i = threadIdx.x; i < (rows + 2) * wpr; i += blockDim.x) {
-        int r = i / wpr, c = i - r * wpr;
-        int rr = r0 - 1 + r;
-        uint32_t v = 0;
-        if (rr >= 0 && rr < h) v = __ldcg(edges + (size_t)rr * wpr + c);
-        se[r * sp + c] = v;
-    }
-}
-
-// Write a converged strip back; reports whether its first / last row changed (-> the
-// neighbouring strips' halos are stale and they must be revisited).
-__device__ void store_strip(uint32_t* pe, const uint32_t* se, int wpr, int sp, int r0, int rows, bool& top, bool& bot) {
+// Write the changed candidate words back; reports whether the strip's first / last row changed
+// (-> the neighbouring strips' halos are stale and they must be revisited).
+__device__ void store_strip(uint32_t* pe, const Strip& st, int n, int wpr, int sp, int r0, int rows, bool& top, bool& bot) {
     bool t = false, b = false;
-    for (int i = threadIdx.x; i < rows * wpr; i += blockDim.x) {
-        int r = i / wpr, c = i - r * wpr;
-        uint32_t v = se[(r + 1) * sp + c];
-        size_t o = (size_t)(r0 + r) * wpr + c;
+    for (int j = threadIdx.x; j < n; j += blockDim.x) {
+        const uint32_t pos = st.lpos[j];
+        const int r = (int)(pos >> 10), c = (int)(pos & 1023u);
+        const uint32_t v = st.se[(r + 1) * sp + c];
+        const size_t o = (size_t)(r0 + r) * wpr + c;
         if (v != pe[o]) {
             pe[o] = v;
             t |= r == 0;
@@ -213,25 +227,22 @@ __device__ void store_strip(uint32_t* pe, const uint32_t* se, int wpr, int sp, i
 // place.  With flags_in only the flagged strips run.  flags[img][strip] = 1 tells that a
 // neighbouring strip must be revisited.
 __global__ void __launch_bounds__(HTHREADS) k_hyst_strips(const uint32_t* __restrict__ weak, uint32_t* edges, int h,
-                                                          int wpr, int nstrips, const uint32_t* flags_in,
+                                                          int wpr, int hrows, int nstrips, const uint32_t* flags_in,
                                                           uint32_t* flags) {
     extern __shared__ uint32_t sm[];
+    __shared__ int s_n;
     const int img = blockIdx.y, strip = blockIdx.x;
     if (flags_in && flags_in[(size_t)img * nstrips + strip] == 0) return;  // later rounds: flagged strips only
     const size_t plane = (size_t)h * wpr;
     const uint32_t* pw = weak + img * plane;
     uint32_t* pe = edges + img * plane;
     const int sp = strip_pitch(wpr);
-    const int r0 = strip * HROWS, rows = min(HROWS, h - r0);
-    uint32_t* sw = sm;
-    uint32_t* se = sm + HROWS * sp;
-    uint16_t* list = reinterpret_cast<uint16_t*>(se + (HROWS + 2) * sp);
-    __shared__ int s_n;
-    load_strip(pw, pe, h, wpr, sp, r0, rows, sw, se);
-    __syncthreads();
-    if (!converge_strip(sw, se, rows, wpr, sp, list, &s_n)) return;
+    const int r0 = strip * hrows, rows = min(hrows, h - r0);
+    const Strip st = carve_strip(sm, hrows, wpr, sp);
+    const int n = load_strip(pw, pe, h, wpr, sp, r0, rows, st, &s_n);
+    if (n == 0 || !converge_strip(st, n, wpr, sp)) return;
     bool top, bot;
-    store_strip(pe, se, wpr, sp, r0, rows, top, bot);
+    store_strip(pe, st, n, wpr, sp, r0, rows, top, bot);
     if (threadIdx.x == 0) {
         uint32_t* f = flags + (size_t)img * nstrips;
         if (top && strip > 0) f[strip - 1] = 1;
@@ -242,18 +253,16 @@ __global__ void __launch_bounds__(HTHREADS) k_hyst_strips(const uint32_t* __rest
 // Phase 2: one CTA per image finishes the cross-strip propagation: visit flagged strips
 // (down sweep, then up sweep) until no flag is left.  Usually there is nothing to do.
 __global__ void __launch_bounds__(HTHREADS) k_hyst_finish(const uint32_t* __restrict__ weak, uint32_t* edges, int h,
-                                                          int wpr, int nstrips, uint32_t* flags) {
+                                                          int wpr, int hrows, int nstrips, uint32_t* flags) {
     extern __shared__ uint32_t sm[];
+    __shared__ int s_n;
     const int img = blockIdx.x;
     const size_t plane = (size_t)h * wpr;
     const uint32_t* pw = weak + img * plane;
     uint32_t* pe = edges + img * plane;
     volatile uint32_t* f = flags + (size_t)img * nstrips;
     const int sp = strip_pitch(wpr);
-    uint32_t* sw = sm;
-    uint32_t* se = sm + HROWS * sp;
-    uint16_t* list = reinterpret_cast<uint16_t*>(se + (HROWS + 2) * sp);
-    __shared__ int s_n;
+    const Strip st = carve_strip(sm, hrows, wpr, sp);
     for (;;) {
         bool mine = false;
         for (int i = threadIdx.x; i < nstrips; i += blockDim.x) mine |= f[i] != 0;
@@ -265,12 +274,11 @@ __global__ void __launch_bounds__(HTHREADS) k_hyst_finish(const uint32_t* __rest
                 if (f[strip] == 0) continue;  // uniform: every thread reads it after the barrier
                 __syncthreads();
                 if (threadIdx.x == 0) f[strip] = 0;
-                const int r0 = strip * HROWS, rows = min(HROWS, h - r0);
-                load_strip(pw, pe, h, wpr, sp, r0, rows, sw, se);
-                __syncthreads();
-                if (!converge_strip(sw, se, rows, wpr, sp, list, &s_n)) continue;
+                const int r0 = strip * hrows, rows = min(hrows, h - r0);
+                const int n = load_strip(pw, pe, h, wpr, sp, r0, rows, st, &s_n);
+                if (n == 0 || !converge_strip(st, n, wpr, sp)) continue;
                 bool top, bot;
-                store_strip(pe, se, wpr, sp, r0, rows, top, bot);
+                store_strip(pe, st, n, wpr, sp, r0, rows, top, bot);
                 if (threadIdx.x == 0) {
                     if (top && strip > 0) f[strip - 1] = 1;
                     if (bot && strip + 1 < nstrips) f[strip + 1] = 1;
@@ -363,23 +371,33 @@ int launch_canny_front(llfe_ctx* ctx, const uint8_t* gray, int n, int h, int w, 
     return LLFE_OK;
 }
 
-size_t hysteresis_flag_words(int n, int h) { return 2 * (size_t)n * ceil_div(h, HROWS); }
+size_t hysteresis_flag_words(int n, int h) { return 2 * (size_t)n * ceil_div(h, HROWS_MIN); }
+
+static size_t strip_smem(int hrows, int wpr) {
+    return ((size_t)(hrows + 2) * strip_pitch(wpr) + 2 * (size_t)hrows * wpr) * sizeof(uint32_t);
+}
 
 // `edges` holds the strong plane on entry and the final edge plane on exit.
 int launch_hysteresis(llfe_ctx* ctx, const uint32_t* weak, uint32_t* edges, int n, int h, int w, uint32_t* flags) {
     if (n == 0 || h == 0 || w == 0) return LLFE_OK;
     const int wpr = plane_wpr(w);
-    const int nstrips = ceil_div(h, HROWS);
-    size_t smem = (size_t)(2 * HROWS + 2) * strip_pitch(wpr) * sizeof(uint32_t) + (size_t)HROWS * wpr * sizeof(uint16_t);
-    if (smem > ctx->smem_optin - 1024) {
-        llfe_set_error("hysteresis: image width %d needs %zu B of shared memory per strip (limit %zu)", w, smem,
-                       ctx->smem_optin);
+    if (wpr > 1023) {
+        llfe_set_error("hysteresis: image width %d is beyond the 32736-pixel limit of the strip kernel", w);
         return LLFE_E_UNSUPPORTED;
     }
+    const size_t budget = ctx->smem_optin - 1024;
+    int hrows = HROWS_MAX;
+    while (hrows > HROWS_MIN && (strip_smem(hrows, wpr) > budget / 2 || hrows >= 2 * h)) hrows >>= 1;
+    const size_t smem = strip_smem(hrows, wpr);
+    if (smem > budget) {
+        llfe_set_error("hysteresis: image width %d needs %zu B of shared memory per strip (limit %zu)", w, smem, budget);
+        return LLFE_E_UNSUPPORTED;
+    }
+    const int nstrips = ceil_div(h, hrows);
     static bool attr_set = false;
     if (!attr_set) {
-        LLFE_CUDA(cudaFuncSetAttribute(k_hyst_strips, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(ctx->smem_optin - 1024)));
-        LLFE_CUDA(cudaFuncSetAttribute(k_hyst_finish, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(ctx->smem_optin - 1024)));
+        LLFE_CUDA(cudaFuncSetAttribute(k_hyst_strips, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)budget));
+        LLFE_CUDA(cudaFuncSetAttribute(k_hyst_finish, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)budget));
         attr_set = true;
     }
     // round 0 visits every strip; rounds 1..2 only strips whose halo changed; one CTA per image
@@ -389,20 +407,23 @@ int launch_hysteresis(llfe_ctx* ctx, const uint32_t* weak, uint32_t* edges, int 
     uint32_t* fb = flags + fw;
     LLFE_CUDA(cudaMemsetAsync(flags, 0, 2 * fw * sizeof(uint32_t), ctx->stream));
     LLFE_KERNEL(ctx, "k_hyst_strips");
-    k_hyst_strips<<<dim3(nstrips, n), HTHREADS, smem, ctx->stream>>>(weak, edges, h, wpr, nstrips, nullptr, fa);
+    k_hyst_strips<<<dim3(nstrips, n), HTHREADS, smem, ctx->stream>>>(weak, edges, h, wpr, hrows, nstrips, nullptr, fa);
     LLFE_LAUNCHED(ctx);
-    for (int round = 1; round <= 2; ++round) {
+    const int extra_rounds = nstrips > 1 ? 2 : 0;
+    for (int round = 1; round <= extra_rounds; ++round) {
         LLFE_KERNEL(ctx, "k_hyst_strips_again");
-        k_hyst_strips<<<dim3(nstrips, n), HTHREADS, smem, ctx->stream>>>(weak, edges, h, wpr, nstrips, fa, fb);
+        k_hyst_strips<<<dim3(nstrips, n), HTHREADS, smem, ctx->stream>>>(weak, edges, h, wpr, hrows, nstrips, fa, fb);
         LLFE_LAUNCHED(ctx);
         LLFE_CUDA(cudaMemsetAsync(fa, 0, fw * sizeof(uint32_t), ctx->stream));
         uint32_t* t = fa;
         fa = fb;
         fb = t;
     }
-    LLFE_KERNEL(ctx, "k_hyst_finish");
-    k_hyst_finish<<<n, HTHREADS, smem, ctx->stream>>>(weak, edges, h, wpr, nstrips, fa);
-    LLFE_LAUNCHED(ctx);
+    if (nstrips > 1) {
+        LLFE_KERNEL(ctx, "k_hyst_finish");
+        k_hyst_finish<<<n, HTHREADS, smem, ctx->stream>>>(weak, edges, h, wpr, hrows, nstrips, fa);
+        LLFE_LAUNCHED(ctx);
+    }
     return LLFE_OK;
 }
 
