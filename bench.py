@@ -26,21 +26,36 @@ if ROOT not in sys.path:
 
 METRIC = "images/sec @1080p (colors+edges)"
 
-# Compulsory HBM bytes per image per kernel (P = H*W): what the kernel must read + write once.
+# Algorithmic (compulsory) HBM bytes per image per kernel launch: what the kernel must read once +
+# write once (P = H*W pixels, U = unique colours of the image, A = k-means attempts).  DESIGN.md
+# "Kernels" derives each figure.
+BM = 1 << 21                                   # the 2^24-bit colour bitmap of one image
 KERNEL_BYTES = {
-    "k_gray_blur5": lambda P: 3 * P + P,
-    "k_canny_front": lambda P: P + P // 4,
-    "k_hyst_strips": lambda P: P // 8 + P // 8 + P // 8,
-    "k_hyst_finish": lambda P: P // 8,
-    "k_plane_to_mask_dilate": lambda P: P // 8 + P,
-    "k_plane_to_mask": lambda P: P // 8 + P,
-    "k_adaptive": lambda P: P + P,
-    "k_color_bitmap": lambda P: 3 * P,
-    "k_bm_blocksum": lambda P: 1 << 21,
-    "k_bm_emit": lambda P: 1 << 21,
-    "k_kmeans": lambda P: 0,
-    "k_edge_fused": lambda P: 3 * P + P // 4,
-    "k_pipeline_front": lambda P: 3 * P + P // 4 + P,
+    # fused front: read BGR (3P); write shadow mask (P) + weak/strong bit planes (2 * P/8); the
+    # bitmap is L2-resident scratch (zeroed + scanned by other kernels) and is not counted here
+    "k_fused": lambda P, U, A: 3 * P + P + P // 4,
+    "k_gray_blur5": lambda P, U, A: 3 * P + P,
+    "k_canny_front": lambda P, U, A: P + P // 4,
+    "k_adaptive": lambda P, U, A: P + P,
+    "k_color_bitmap": lambda P, U, A: 3 * P,
+    # hysteresis: read weak + strong planes, write the edge plane (in place)
+    "k_hyst": lambda P, U, A: 3 * (P // 8),
+    "k_hyst_mask": lambda P, U, A: 2 * (P // 8) + P,
+    "k_hyst_strips": lambda P, U, A: 3 * (P // 8),
+    "k_hyst_strips_again": lambda P, U, A: 0,   # revisits flagged strips only: no compulsory traffic
+    "k_hyst_finish": lambda P, U, A: 0,
+    "k_plane_to_mask_dilate": lambda P, U, A: P // 8 + P,
+    "k_plane_to_mask": lambda P, U, A: P // 8 + P,
+    "k_bm_blocksum": lambda P, U, A: BM,
+    "k_bm_blockscan": lambda P, U, A: 4096,
+    "k_bm_emit": lambda P, U, A: BM + 4 * U,
+    # k-means: every (attempt, image) CTA reads the key list once and writes its labels once;
+    # all iterations run out of shared memory, so this kernel is SM-bound, not HBM-bound
+    "k_kmeans_fast": lambda P, U, A: A * (4 * U + U),
+    "k_kmeans_pp": lambda P, U, A: A * 4 * U,
+    "k_kmeans_lloyd": lambda P, U, A: A * (4 * U + U),
+    "k_kmeans": lambda P, U, A: A * (4 * U + U),
+    "k_kmeans_pick": lambda P, U, A: A * U + 4 * U,
 }
 
 # Algorithmic bytes per image of a whole step: read the BGR input once,
@@ -170,6 +185,16 @@ class ClockSampler:
                 "reasons": sorted(reasons), "samples": len(sm)}
 
 
+# dram__bytes_read.sum + dram__bytes_write.sum per launch from the committed `ncu --set full` capture
+# (profiles/ncu_r1_summary.md), bytes; kernels not captured yet report null.
+NCU_TRAFFIC = {}
+try:
+    with open(os.path.join(ROOT, "profiles", "ncu_traffic.json")) as _f:
+        NCU_TRAFFIC = {k: v["bytes_per_launch"] for k, v in json.load(_f).items()}
+except Exception:
+    pass
+
+
 def measured_peak():
     p = os.path.join(ROOT, "MEASURED_PEAKS.json")
     try:
@@ -275,6 +300,11 @@ def run_ours(args):
 
     if rank == 0:
         peak, peak_src = measured_peak()
+        u_avg = float(out["count"].float().mean().item()) if "count" in out else 0.0
+
+        def kernel_bytes(name):
+            return KERNEL_BYTES.get(name, lambda P, U, A: 0)(P, u_avg, cfg.attempts)
+
         # dominant kernel: largest total device time inside the timed region
         dom = max(kernels.items(), key=lambda kv: kv[1]["ms"]) if kernels else (None, None)
         roofline = None
@@ -283,11 +313,12 @@ def run_ours(args):
             name, rec = dom
             per_launch_ms = rec["ms"] / rec["launches"]
             imgs_per_launch = B * args.steps / rec["launches"]
-            algo = KERNEL_BYTES.get(name, lambda P: 0)(P) * imgs_per_launch
+            algo = kernel_bytes(name) * imgs_per_launch
             ach = algo / (per_launch_ms / 1e3) / 1e9
             roofline = {"bound": "hbm", "kernel": name, "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak,
-                        "traffic": None, "peak_source": peak_src, "algorithmic_bytes_per_launch": algo,
-                        "avg_launch_ms": per_launch_ms, "share_of_step": rec["ms"] / total_kernel_ms}
+                        "traffic": NCU_TRAFFIC.get(name), "peak_source": peak_src, "algorithmic_bytes_per_launch": algo,
+                        "avg_launch_ms": per_launch_ms, "share_of_step": rec["ms"] / total_kernel_ms,
+                        "images_per_launch": imgs_per_launch}
         step_bytes = WORKLOAD_BYTES[args.workload](P) * B
         step_ach = step_bytes / (ms / args.steps / 1e3) / 1e9
         line = {"metric": METRIC, "value": value, "unit": "images/sec", "n_gpus": world, "steps": args.steps,
@@ -297,8 +328,10 @@ def run_ours(args):
                 "roofline_step": {"bound": "hbm", "algorithmic_bytes_per_image": WORKLOAD_BYTES[args.workload](P),
                                   "achieved": step_ach, "peak": peak, "unit": "GB/s", "frac": step_ach / peak,
                                   "note": "whole step (all kernels) against the workload's algorithmic bytes, per GPU"},
-                "kernels": {k: {"ms_per_step": v["ms"] / args.steps, "launches_per_step": v["launches"] / args.steps}
+                "kernels": {k: {"ms_per_step": v["ms"] / args.steps, "launches_per_step": v["launches"] / args.steps,
+                                "achieved_gbs": kernel_bytes(k) * B * args.steps / (v["ms"] / 1e3) / 1e9 if v["ms"] > 0 else 0.0}
                             for k, v in sorted(kernels.items(), key=lambda kv: -kv[1]["ms"])},
+                "unique_colours_per_image": u_avg,
                 "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": launches, "clocks": clocks}
         print(json.dumps(line), flush=True)
     if world > 1:

@@ -190,9 +190,12 @@ int llfe_kmeans_pixels_step(llfe_ctx* ctx, const uint8_t* d_bgr, size_t n_pixels
  * shard whose nearest centre (under d_centers) is `donor`, find the one farthest
  * (float32 distance) from h_base3 = the donor's provisional mean; ties go to the
  * highest pixel index.  *d_out = max(*d_out, ((dist bits << 32) | (index_base +
- * local pixel index)) + 1); the caller zeroes it first and all-reduces with max. */
+ * local pixel index)) + 1); the caller zeroes it first and all-reduces with max.
+ * h_skip[n_skip] (n_skip <= 32) lists global pixel indices to ignore: the pixels
+ * earlier repairs of the same update already moved out of the donor. */
 int llfe_kmeans_pixels_farthest(llfe_ctx* ctx, const uint8_t* d_bgr, size_t n_pixels, int k, const float* d_centers,
-                                int donor, const float* h_base3, uint32_t index_base, uint64_t* d_out);
+                                int donor, const float* h_base3, uint32_t index_base, const uint32_t* h_skip, int n_skip,
+                                uint64_t* d_out);
 
 /* Centre update + convergence test from (all-reduced) sums: c =
  * float(double(sum)/double(count)); d_state[0] = iteration counter (in/out),

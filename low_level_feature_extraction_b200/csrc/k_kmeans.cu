@@ -524,11 +524,16 @@ __global__ void __launch_bounds__(PT) k_pixels_step(const uint8_t* __restrict__ 
     }
 }
 
+struct SkipList {
+    int n;
+    uint32_t idx[KMAX];
+};
+
 // farthest member (f32 distance to `base`) of cluster `donor` under the assignment to
 // `centers`; result = max over pixels of (dist bits << 32 | (pixel index + index_base)) + 1
 __global__ void __launch_bounds__(PT) k_pixels_farthest(const uint8_t* __restrict__ bgr, size_t npix, int K,
                                                         const float* __restrict__ centers, int donor, float b0,
-                                                        float b1, float b2, uint32_t index_base,
+                                                        float b1, float b2, uint32_t index_base, SkipList skip,
                                                         unsigned long long* out) {
     __shared__ float s_c[KMAX][3];
     const int tid = threadIdx.x;
@@ -546,6 +551,9 @@ __global__ void __launch_bounds__(PT) k_pixels_farthest(const uint8_t* __restric
             if (d < bd) bd = d, bl = k;
         }
         if (bl != donor) continue;
+        bool skipped = false;  // pixels an earlier repair of this update already moved out of the donor
+        for (int j = 0; j < skip.n; ++j) skipped |= skip.idx[j] == (uint32_t)(p + index_base);
+        if (skipped) continue;
         float d = fdist(fr, fg, fb, base);
         unsigned long long cand = (((unsigned long long)__float_as_uint(d) << 32) | (uint32_t)(p + index_base)) + 1ull;
         best = cand > best ? cand : best;
@@ -604,8 +612,12 @@ extern "C" int llfe_kmeans_pixels_step(llfe_ctx* ctx, const uint8_t* d_bgr, size
 
 extern "C" int llfe_kmeans_pixels_farthest(llfe_ctx* ctx, const uint8_t* d_bgr, size_t n_pixels, int k,
                                            const float* d_centers, int donor, const float* h_base3,
-                                           uint32_t index_base, uint64_t* d_out) {
+                                           uint32_t index_base, const uint32_t* h_skip, int n_skip, uint64_t* d_out) {
     LLFE_CHECK_ARG(ctx != nullptr && d_bgr != nullptr && d_centers != nullptr && h_base3 != nullptr && d_out != nullptr);
+    LLFE_CHECK_ARG(n_skip >= 0 && n_skip <= KMAX && (n_skip == 0 || h_skip != nullptr));
+    SkipList skip;
+    skip.n = n_skip;
+    for (int j = 0; j < n_skip; ++j) skip.idx[j] = h_skip[j];
     LLFE_CHECK_ARG(k >= 1 && k <= KMAX && donor >= 0 && donor < k && n_pixels + index_base <= 0xffffffffull);
     if (n_pixels == 0) return LLFE_OK;
     size_t want = ceil_div_sz(n_pixels, PT * 8);
@@ -613,7 +625,7 @@ extern "C" int llfe_kmeans_pixels_farthest(llfe_ctx* ctx, const uint8_t* d_bgr, 
     unsigned grid = (unsigned)(want < 1 ? 1 : (want > cap ? cap : want));
     LLFE_KERNEL(ctx, "k_pixels_farthest");
     k_pixels_farthest<<<grid, PT, 0, ctx->stream>>>(d_bgr, n_pixels, k, d_centers, donor, h_base3[0], h_base3[1],
-                                                    h_base3[2], index_base, (unsigned long long*)d_out);
+                                                    h_base3[2], index_base, skip, (unsigned long long*)d_out);
     LLFE_LAUNCHED(ctx);
     return LLFE_OK;
 }

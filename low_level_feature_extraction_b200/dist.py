@@ -1,0 +1,162 @@
+"""Multi-GPU plumbing: one process per GPU, torch.distributed for the (few) exchanges.
+
+Two ways the path shards:
+
+* batches of images (BASELINE configs 2-4): images are independent, rank r takes
+  `shard_range(n, r, world)`; there is NO data-path collective, only an optional
+  gather of the tiny per-image results (`gather_results`);
+* one oversized image (config 5): pixel rows are split across ranks
+  (`row_shard`), every Lloyd iteration each rank accumulates exact uint64
+  {sum R, sum G, sum B, count} per cluster over its rows on the device
+  (`llfe_kmeans_pixels_step`), the K x 4 accumulator is all-reduced
+  (ncclSum over NVLink: 512 B at K = 16), and every rank then runs the identical
+  centre update + convergence test (`llfe_kmeans_update`) -- integer sums make the
+  result independent of the number of ranks, bit for bit.
+
+`PixelKMeans` is written against a small backend interface (`step`, `farthest`,
+`update`) so that the host logic -- iteration bookkeeping, the all-reduce, cv2's
+empty-cluster repair across shards -- is exercised on CPU with gloo in tests/ while
+the product backend is always `ops.Engine` (CUDA, no fallback).
+"""
+from __future__ import annotations
+
+from dataclasses import dataclass
+
+import torch
+import torch.distributed as dist
+
+
+def world() -> tuple[int, int]:
+    """(rank, world_size); (0, 1) when torch.distributed is not initialised."""
+    if dist.is_available() and dist.is_initialized():
+        return dist.get_rank(), dist.get_world_size()
+    return 0, 1
+
+
+def shard_range(n: int, rank: int, world_size: int) -> tuple[int, int]:
+    """Contiguous, balanced split of n items: the first n % world ranks get one extra."""
+    if world_size <= 0 or not (0 <= rank < world_size):
+        raise ValueError(f"bad rank/world: {rank}/{world_size}")
+    base, extra = divmod(n, world_size)
+    i0 = rank * base + min(rank, extra)
+    return i0, i0 + base + (1 if rank < extra else 0)
+
+
+def row_shard(h: int, rank: int, world_size: int) -> tuple[int, int]:
+    """Row range [r0, r1) of an h-row image owned by `rank`."""
+    return shard_range(h, rank, world_size)
+
+
+def gather_results(local: torch.Tensor, n_total: int, group=None) -> torch.Tensor:
+    """Concatenate per-image results (palettes, shadow sums, ...) of a batch sharded with
+    `shard_range` on every rank.  Not on the hot path: a few bytes per image."""
+    rank, ws = world()
+    if ws == 1:
+        return local
+    sizes = [shard_range(n_total, r, ws) for r in range(ws)]
+    cap = max(b - a for a, b in sizes)
+    pad = torch.zeros((cap,) + tuple(local.shape[1:]), dtype=local.dtype, device=local.device)
+    pad[: local.shape[0]] = local
+    out = [torch.empty_like(pad) for _ in range(ws)]
+    dist.all_gather(out, pad, group=group)
+    return torch.cat([o[: b - a] for o, (a, b) in zip(out, sizes)], dim=0)
+
+
+@dataclass
+class PixelKMeansResult:
+    centers: torch.Tensor      # (k, 3) float32, RGB
+    iters: int
+    sums_counts: torch.Tensor  # (k, 4) int64: sum R, sum G, sum B, count (global)
+    shift: float
+    labels: torch.Tensor | None = None  # (rows*w,) uint8 for this rank's rows, if requested
+
+
+class PixelKMeans:
+    """Per-pixel Lloyd k-means of ONE image whose rows are sharded across ranks.
+
+    The arithmetic is the pinned exact-sum rule of SURVEY.md A.8: float32 assignment
+    (separate mul/add, strict <), integer sums, c = float32(double(sum)/double(count)),
+    shift test max_k |c - old|^2 <= eps^2 from iteration 1 on, cv2's empty-cluster repair.
+    """
+
+    def __init__(self, backend, group=None):
+        self.be = backend
+        self.group = group
+
+    # -- collectives (identity in a single process) ----------------------------------------
+    def _allreduce(self, t: torch.Tensor, op) -> None:
+        if dist.is_available() and dist.is_initialized() and dist.get_world_size(self.group) > 1:
+            dist.all_reduce(t, op=op, group=self.group)
+
+    def fit(self, bgr_rows: torch.Tensor, init_centers: torch.Tensor, index_base: int = 0, max_iter: int = 200,
+            eps: float = 0.2, want_labels: bool = False) -> PixelKMeansResult:
+        """bgr_rows: this rank's (rows, w, 3) uint8 BGR rows (may be empty); init_centers: (k, 3)
+        float32 RGB, identical on every rank; index_base: global pixel index of the first local pixel."""
+        be = self.be
+        dev = bgr_rows.device
+        k = int(init_centers.shape[0])
+        centers = init_centers.to(device=dev, dtype=torch.float32).contiguous().clone()
+        sums = torch.zeros((k, 4), dtype=torch.int64, device=dev)
+        state = torch.zeros((3,), dtype=torch.int32, device=dev)
+        shift = torch.zeros((1,), dtype=torch.float64, device=dev)
+        far = torch.zeros((1,), dtype=torch.int64, device=dev)
+        npix = bgr_rows.numel() // 3
+        labels = torch.empty((npix,), dtype=torch.uint8, device=dev) if want_labels else None
+        flat = bgr_rows.reshape(-1, 3)
+        while True:
+            sums.zero_()
+            be.kmeans_pixels_step(bgr_rows, centers, sums, labels)
+            self._allreduce(sums, dist.ReduceOp.SUM)
+            be.kmeans_update(sums, centers, state, shift, max_iter=max_iter, eps=eps)
+            st = state.tolist()
+            if st[2]:
+                self._repair(flat, centers, sums, far, index_base, npix, labels)
+                be.kmeans_update(sums, centers, state, shift, max_iter=max_iter, eps=eps)
+                st = state.tolist()
+                if st[2]:
+                    raise RuntimeError("k-means: an empty cluster survived the repair (fewer distinct pixels than k?)")
+            if st[1]:
+                return PixelKMeansResult(centers, st[0], sums, float(shift.item()), labels)
+
+    def _repair(self, flat, centers, sums, far, index_base, npix, labels) -> None:
+        """cv2's empty-cluster repair on the all-reduced sums: for each empty cluster (in order) the
+        biggest cluster (first max) gives up its member farthest from its provisional mean (last max
+        wins => highest global pixel index).  `centers` still holds the centres the labels came from."""
+        k = centers.shape[0]
+        moved: list[int] = []
+        host = sums.cpu()
+        assigned_from = centers.clone()  # `centers` gets the donors' provisional means below
+        for j in range(k):
+            if int(host[j, 3]) != 0:
+                continue
+            cnt = host[:, 3]
+            donor = 0
+            for k1 in range(1, k):
+                if int(cnt[donor]) < int(cnt[k1]):
+                    donor = k1
+            base = (host[donor, :3].to(torch.float64) / float(cnt[donor])).to(torch.float32)
+            far.zero_()
+            self.be.kmeans_pixels_farthest(flat, assigned_from, donor, [float(v) for v in base], index_base, far,
+                                           skip=moved)
+            self._allreduce(far, dist.ReduceOp.MAX)
+            code = int(far.item())
+            if code == 0:
+                raise RuntimeError("k-means repair: the donor cluster has no member")
+            gidx = (code - 1) & 0xFFFFFFFF
+            # the owner contributes the pixel's colour (RGB); everyone else zeros
+            px = torch.zeros((3,), dtype=torch.int64, device=flat.device)
+            li = gidx - index_base
+            if 0 <= li < npix:
+                px = flat[li].flip(0).to(torch.int64)
+                if labels is not None:
+                    labels[li] = j
+            self._allreduce(px, dist.ReduceOp.SUM)
+            pxh = px.cpu()
+            host[donor, :3] -= pxh
+            host[donor, 3] -= 1
+            host[j, :3] += pxh
+            host[j, 3] += 1
+            moved.append(gidx)
+            # OpenCV stores the donor's provisional mean in old_centers[donor]: the shift is measured from it
+            centers[donor] = base.to(centers.device)
+        sums.copy_(host)

@@ -292,14 +292,17 @@ class Engine:
         self.ctx.call("llfe_kmeans_update", centers.shape[0], sums, centers, int(max_iter), float(eps), state, shift)
 
     def kmeans_pixels_farthest(self, bgr_rows: torch.Tensor, centers: torch.Tensor, donor: int, base3,
-                               index_base: int, out: torch.Tensor):
+                               index_base: int, out: torch.Tensor, skip=()):
+        """out[0] = max(out[0], code of the donor member farthest from base3); skip: global pixel
+        indices to ignore (already moved by earlier repairs of the same update)."""
         import ctypes
 
         x = bgr_rows.contiguous()
         arr = (ctypes.c_float * 3)(*[float(v) for v in base3])
+        sk = (ctypes.c_uint32 * max(1, len(skip)))(*[int(v) for v in skip])
         self._bind()
         self.ctx.call("llfe_kmeans_pixels_farthest", x, x.numel() // 3, centers.shape[0], centers, int(donor),
-                      ctypes.addressof(arr), int(index_base), out)
+                      ctypes.addressof(arr), int(index_base), ctypes.addressof(sk), len(skip), out)
 
     # -- fused pipeline -------------------------------------------------------------
     def pipeline(self, bgr: torch.Tensor, shapes: bool = True, shadows: bool = True, colors: bool = True,
