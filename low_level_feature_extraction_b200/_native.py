@@ -50,6 +50,7 @@ PROTOTYPES = {
     "llfe_gaussian_blur5": (i32, [vp, vp, i32, i32, i32, i32, vp]),
     "llfe_gray_blur5": (i32, [vp, vp, i32, i32, i32, vp]),
     "llfe_canny": (i32, [vp, vp, i32, i32, i32, i32, i32, vp]),
+    "llfe_hysteresis": (i32, [vp, vp, vp, i32, i32, i32, i32, vp]),
     "llfe_dilate3": (i32, [vp, vp, i32, i32, i32, vp]),
     "llfe_shape_mask": (i32, [vp, vp, i32, i32, i32, i32, i32, vp]),
     "llfe_adaptive_threshold": (i32, [vp, vp, i32, i32, i32, i32, vp, vp]),

@@ -30,7 +30,8 @@ class BatchConfig:
     low: int = 50
     high: int = 150
     seed: int = 0              # device noise seed / cv::RNG state base
-    chunk: int = 32            # images per launch group (keeps scratch L2-sized)
+    chunk: int = 256           # images per C-ABI call on the device path (the library sub-chunks for L2)
+    host_chunk: int = 32       # images per copy/compute pipeline stage of run_host
 
 
 class BatchAnalyzer:
@@ -103,13 +104,13 @@ class BatchAnalyzer:
         n = images.shape[0]
         host_out = host_out if host_out is not None else self.alloc_host_outputs(n)
         if self._dev_in is None:
-            self._dev_in = [torch.empty((c.chunk, self.h, self.w, 3), dtype=torch.uint8, device=self.device) for _ in range(2)]
-            self._dev_out = [self.alloc_outputs(c.chunk) for _ in range(2)]
+            self._dev_in = [torch.empty((c.host_chunk, self.h, self.w, 3), dtype=torch.uint8, device=self.device) for _ in range(2)]
+            self._dev_out = [self.alloc_outputs(c.host_chunk) for _ in range(2)]
             self._events = [torch.cuda.Event() for _ in range(2)]
         bytes_in = bytes_out = 0
-        for j, i0 in enumerate(range(0, n, c.chunk)):
+        for j, i0 in enumerate(range(0, n, c.host_chunk)):
             b = j & 1
-            m = min(c.chunk, n - i0)
+            m = min(c.host_chunk, n - i0)
             st = self.streams[b]
             with torch.cuda.stream(st):
                 din = self._dev_in[b][:m]

@@ -97,33 +97,6 @@ constexpr int HTHREADS = 256;        // threads per CTA
 constexpr int HROWS_MAX = 256;       // rows per strip (halved until the strip fits in shared memory)
 constexpr int HROWS_MIN = 8;
 
-// fill `e` along runs of `w` inside one 32-bit word (both directions), e subset of w
-__device__ __forceinline__ uint32_t fill_word(uint32_t e, uint32_t w) {
-    // Kogge-Stone occluded fill towards higher bits, then lower bits
-    uint32_t g1 = e, p = w;
-    g1 |= p & (g1 << 1);
-    p &= p << 1;
-    g1 |= p & (g1 << 2);
-    p &= p << 2;
-    g1 |= p & (g1 << 4);
-    p &= p << 4;
-    g1 |= p & (g1 << 8);
-    p &= p << 8;
-    g1 |= p & (g1 << 16);
-    uint32_t g2 = e;
-    p = w;
-    g2 |= p & (g2 >> 1);
-    p &= p >> 1;
-    g2 |= p & (g2 >> 2);
-    p &= p >> 2;
-    g2 |= p & (g2 >> 4);
-    p &= p >> 4;
-    g2 |= p & (g2 >> 8);
-    p &= p >> 8;
-    g2 |= p & (g2 >> 16);
-    return g1 | g2;
-}
-
 // shared-memory pitch (words) of a strip row: odd, to spread rows over the banks
 __host__ __device__ static inline int strip_pitch(int wpr) { return wpr | 1; }
 
@@ -338,6 +311,19 @@ __global__ void __launch_bounds__(256) k_plane_to_mask(const uint32_t* __restric
     }
 }
 
+// u8 mask (non-zero = set) -> bit plane; one warp per plane word
+__global__ void __launch_bounds__(256) k_mask_to_plane(const uint8_t* __restrict__ mask, int h, int w, int wpr,
+                                                       uint32_t* __restrict__ plane) {
+    const int img = blockIdx.z, y = blockIdx.y;
+    const int lane = threadIdx.x & 31;
+    const int c = blockIdx.x * 8 + (threadIdx.x >> 5);
+    if (c >= wpr) return;
+    const int x = c * 32 + lane;
+    const bool on = x < w && mask[((size_t)img * h + y) * w + x] != 0;
+    const uint32_t bits = __ballot_sync(0xffffffffu, on);
+    if (lane == 0) plane[((size_t)img * h + y) * wpr + c] = bits;
+}
+
 // generic 3x3 max on u8 (standalone cv2.dilate with a 3x3 ones kernel)
 __global__ void __launch_bounds__(256) k_dilate3_u8(const uint8_t* __restrict__ src, int h, int w,
                                                     uint8_t* __restrict__ dst) {
@@ -437,6 +423,15 @@ int launch_plane_to_mask(llfe_ctx* ctx, const uint32_t* plane, int n, int h, int
         k_plane_to_mask<true><<<grid, 256, 0, ctx->stream>>>(plane, h, w, wpr, mask, aligned);
     else
         k_plane_to_mask<false><<<grid, 256, 0, ctx->stream>>>(plane, h, w, wpr, mask, aligned);
+    LLFE_LAUNCHED(ctx);
+    return LLFE_OK;
+}
+
+int launch_mask_to_plane(llfe_ctx* ctx, const uint8_t* mask, int n, int h, int w, uint32_t* plane) {
+    if (n == 0 || h == 0 || w == 0) return LLFE_OK;
+    const int wpr = plane_wpr(w);
+    LLFE_KERNEL(ctx, "k_mask_to_plane");
+    k_mask_to_plane<<<dim3(ceil_div(wpr, 8), h, n), 256, 0, ctx->stream>>>(mask, h, w, wpr, plane);
     LLFE_LAUNCHED(ctx);
     return LLFE_OK;
 }

@@ -292,6 +292,18 @@ int llfe_gray_blur5(llfe_ctx* ctx, const uint8_t* d_bgr, int n, int h, int w, ui
 }
 
 // ---- edges ------------------------------------------------------------------
+// weak + strong planes -> (dilated) u8 mask: one cluster launch per batch when the strips of an image
+// fit in shared memory, else the multi-launch strip kernels + the expand kernel.
+static int hysteresis_to_mask(llfe_ctx* ctx, const uint32_t* weak, uint32_t* edges, int n, int h, int w,
+                              uint32_t* flags, int dilate, uint8_t* d_out) {
+    if (!getenv("LLFE_HYST_STRIPS")) {
+        const int rc = launch_hysteresis_mask_cluster(ctx, weak, edges, n, h, w, dilate, d_out);
+        if (rc != LLFE_E_UNSUPPORTED) return rc;
+    }
+    LLFE_TRY(launch_hysteresis(ctx, weak, edges, n, h, w, flags));
+    return launch_plane_to_mask(ctx, edges, n, h, w, dilate, d_out);
+}
+
 static int canny_from_gray(llfe_ctx* ctx, const uint8_t* d_gray, int n, int h, int w, int low, int high, int dilate,
                            uint8_t* d_out, char* ws_base) {
     const size_t plane = (size_t)n * h * plane_wpr(w);
@@ -300,8 +312,7 @@ static int canny_from_gray(llfe_ctx* ctx, const uint8_t* d_gray, int n, int h, i
     uint32_t* edges = ws.take<uint32_t>(plane);
     uint32_t* flags = ws.take<uint32_t>(hysteresis_flag_words(n, h));
     LLFE_TRY(launch_canny_front(ctx, d_gray, n, h, w, low, high, weak, edges));
-    LLFE_TRY(launch_hysteresis(ctx, weak, edges, n, h, w, flags));
-    return launch_plane_to_mask(ctx, edges, n, h, w, dilate, d_out);
+    return hysteresis_to_mask(ctx, weak, edges, n, h, w, flags, dilate, d_out);
 }
 
 static size_t canny_ws_bytes(int n, int h, int w) {
@@ -316,6 +327,23 @@ int llfe_canny(llfe_ctx* ctx, const uint8_t* d_gray, int n, int h, int w, int lo
     void* ws;
     LLFE_TRY(llfe_workspace(ctx, canny_ws_bytes(n, h, w), &ws));
     return canny_from_gray(ctx, d_gray, n, h, w, low, high, 0, d_edges, (char*)ws);
+}
+
+int llfe_hysteresis(llfe_ctx* ctx, const uint8_t* d_weak, const uint8_t* d_strong, int n, int h, int w, int dilate,
+                    uint8_t* d_edges) {
+    LLFE_IMG_ARGS(d_weak);
+    LLFE_CHECK_ARG(d_strong != nullptr && d_edges != nullptr);
+    if ((size_t)n * h * w == 0) return LLFE_OK;
+    void* wsp;
+    LLFE_TRY(llfe_workspace(ctx, canny_ws_bytes(n, h, w), &wsp));
+    const size_t plane = (size_t)n * h * plane_wpr(w);
+    WsCarver ws(wsp);
+    uint32_t* weak = ws.take<uint32_t>(plane);
+    uint32_t* edges = ws.take<uint32_t>(plane);
+    uint32_t* flags = ws.take<uint32_t>(hysteresis_flag_words(n, h));
+    LLFE_TRY(launch_mask_to_plane(ctx, d_weak, n, h, w, weak));
+    LLFE_TRY(launch_mask_to_plane(ctx, d_strong, n, h, w, edges));
+    return hysteresis_to_mask(ctx, weak, edges, n, h, w, flags, dilate, d_edges);
 }
 
 int llfe_dilate3(llfe_ctx* ctx, const uint8_t* d_src, int n, int h, int w, uint8_t* d_dst) {
@@ -419,35 +447,41 @@ int llfe_pipeline(llfe_ctx* ctx, const uint8_t* d_bgr, int n, int h, int w, int 
     LLFE_CHECK_ARG(d_keys == nullptr || (d_count != nullptr && max_unique > 0));
     if (n == 0) return LLFE_OK;
     if (fused_supported(h, w) && !getenv("LLFE_UNFUSED")) {
-        // one read of the image per chunk: planes + shadow mask + colour bitmap, then the small post-passes
+        // One read of the image: planes + shadow mask + colour bitmap, then the small post-passes.
+        // The front kernel runs in chunks of 32 images so that the 2 MiB bitmaps of a chunk stay in L2;
+        // the hysteresis is latency-bound (a few busy warps per image), so it runs once per super-chunk
+        // of up to 256 images to have as many images in flight as the SMs can hold.
         const int chunk = n < 32 ? n : 32;
-        const size_t plane_words = (size_t)chunk * h * plane_wpr(w);
+        const int super = n < 256 ? n : 256;
+        const size_t plane_words = (size_t)super * h * plane_wpr(w), plane_img = (size_t)h * plane_wpr(w);
         const size_t bmw = bitmap_words_per_image(), bmb = bitmap_blocks_per_image();
-        size_t need = 2 * WsCarver::need(plane_words * 4) + WsCarver::need(hysteresis_flag_words(chunk, h) * 4);
+        size_t need = 2 * WsCarver::need(plane_words * 4) + WsCarver::need(hysteresis_flag_words(super, h) * 4);
         if (d_keys) need += WsCarver::need(bmw * 4 * chunk) + WsCarver::need(bmb * 4 * chunk);
         void* ws;
         LLFE_TRY(llfe_workspace(ctx, need, &ws));
         WsCarver carve(ws);
         uint32_t* weak = carve.take<uint32_t>(plane_words);
         uint32_t* edges = carve.take<uint32_t>(plane_words);
-        uint32_t* flags = carve.take<uint32_t>(hysteresis_flag_words(chunk, h));
+        uint32_t* flags = carve.take<uint32_t>(hysteresis_flag_words(super, h));
         uint32_t* bitmap = d_keys ? carve.take<uint32_t>(bmw * chunk) : nullptr;
         uint32_t* bsum = d_keys ? carve.take<uint32_t>(bmb * chunk) : nullptr;
         const size_t p = (size_t)h * w;
-        for (int i0 = 0; i0 < n; i0 += chunk) {
-            const int m = (n - i0) < chunk ? (n - i0) : chunk;
-            if (d_keys) LLFE_CUDA(cudaMemsetAsync(bitmap, 0, bmw * 4 * m, ctx->stream));
-            LLFE_TRY(launch_fused(ctx, d_bgr + i0 * p * 3, m, h, w, low, high, d_shape_mask ? weak : nullptr,
-                                  d_shape_mask ? edges : nullptr, d_shadow_mask ? d_shadow_mask + i0 * p : nullptr,
-                                  d_shadow_sum_count ? d_shadow_sum_count + 2 * i0 : nullptr,
-                                  d_noise ? d_noise + i0 * p * 3 : nullptr, seed, i0, bitmap));
-            if (d_shape_mask) {
-                LLFE_TRY(launch_hysteresis(ctx, weak, edges, m, h, w, flags));
-                LLFE_TRY(launch_plane_to_mask(ctx, edges, m, h, w, 1, d_shape_mask + i0 * p));
+        for (int s0 = 0; s0 < n; s0 += super) {
+            const int sm = (n - s0) < super ? (n - s0) : super;
+            for (int i0 = s0; i0 < s0 + sm; i0 += chunk) {
+                const int m = (s0 + sm - i0) < chunk ? (s0 + sm - i0) : chunk;
+                if (d_keys) LLFE_CUDA(cudaMemsetAsync(bitmap, 0, bmw * 4 * m, ctx->stream));
+                LLFE_TRY(launch_fused(ctx, d_bgr + i0 * p * 3, m, h, w, low, high,
+                                      d_shape_mask ? weak + (i0 - s0) * plane_img : nullptr,
+                                      d_shape_mask ? edges + (i0 - s0) * plane_img : nullptr,
+                                      d_shadow_mask ? d_shadow_mask + i0 * p : nullptr,
+                                      d_shadow_sum_count ? d_shadow_sum_count + 2 * i0 : nullptr,
+                                      d_noise ? d_noise + i0 * p * 3 : nullptr, seed, i0, bitmap));
+                if (d_keys)
+                    LLFE_TRY(launch_bitmap_compact(ctx, bitmap, bsum, m, d_keys + (size_t)i0 * max_unique, nullptr,
+                                                   d_count + i0, max_unique));
             }
-            if (d_keys)
-                LLFE_TRY(launch_bitmap_compact(ctx, bitmap, bsum, m, d_keys + (size_t)i0 * max_unique, nullptr,
-                                               d_count + i0, max_unique));
+            if (d_shape_mask) LLFE_TRY(hysteresis_to_mask(ctx, weak, edges, sm, h, w, flags, 1, d_shape_mask + s0 * p));
         }
         return LLFE_OK;
     }

@@ -108,6 +108,8 @@ int launch_canny_front(llfe_ctx* ctx, const uint8_t* gray, int n, int h, int w, 
 int launch_edge_front_bgr(llfe_ctx* ctx, const uint8_t* bgr, int n, int h, int w, int low, int high, uint32_t* weak,
                           uint32_t* strong);
 int launch_hysteresis(llfe_ctx* ctx, const uint32_t* weak, uint32_t* edges, int n, int h, int w, uint32_t* flags);
+int launch_hysteresis_mask_cluster(llfe_ctx* ctx, const uint32_t* weak, const uint32_t* strong, int n, int h, int w,
+                                   int dilate, uint8_t* mask);
 int launch_plane_to_mask(llfe_ctx* ctx, const uint32_t* plane, int n, int h, int w, int dilate, uint8_t* mask);
 int launch_mask_to_plane(llfe_ctx* ctx, const uint8_t* mask, int n, int h, int w, uint32_t* plane);
 int launch_adaptive(llfe_ctx* ctx, const uint8_t* gray, int n, int h, int w, int C, uint8_t* mask, uint64_t* sum_count);

@@ -79,6 +79,33 @@ __device__ __forceinline__ unsigned long long warp_sum_u64(unsigned long long v)
     return v;
 }
 
+// fill `e` along runs of `w` inside one 32-bit word (both directions), e subset of w
+__device__ __forceinline__ uint32_t fill_word(uint32_t e, uint32_t w) {
+    // Kogge-Stone occluded fill towards higher bits, then lower bits
+    uint32_t g1 = e, p = w;
+    g1 |= p & (g1 << 1);
+    p &= p << 1;
+    g1 |= p & (g1 << 2);
+    p &= p << 2;
+    g1 |= p & (g1 << 4);
+    p &= p << 4;
+    g1 |= p & (g1 << 8);
+    p &= p << 8;
+    g1 |= p & (g1 << 16);
+    uint32_t g2 = e;
+    p = w;
+    g2 |= p & (g2 >> 1);
+    p &= p >> 1;
+    g2 |= p & (g2 >> 2);
+    p &= p >> 2;
+    g2 |= p & (g2 >> 4);
+    p &= p >> 4;
+    g2 |= p & (g2 >> 8);
+    p &= p >> 8;
+    g2 |= p & (g2 >> 16);
+    return g1 | g2;
+}
+
 // ---- palette noise (shared by k_palette.cu and k_fused.cu) -----------------------------
 __device__ __forceinline__ uint32_t fmix32(uint32_t x) {
     x ^= x >> 16;

@@ -123,6 +123,18 @@ class Engine:
         self.ctx.call("llfe_canny", x, n, h, w, int(low), int(high), out)
         return out[0] if single else out
 
+    def hysteresis(self, weak: torch.Tensor, strong: torch.Tensor, dilate: bool = False) -> torch.Tensor:
+        """Canny's hysteresis stage on u8 maps (non-zero = set): weak pixels connected to a strong pixel."""
+        x, single = _batch(weak, None)
+        s, _ = _batch(strong, None)
+        if s.shape != x.shape:
+            raise ValueError("weak and strong must have the same shape")
+        n, h, w = x.shape
+        out = self._empty((n, h, w))
+        self._bind()
+        self.ctx.call("llfe_hysteresis", x, s, n, h, w, 1 if dilate else 0, out)
+        return out[0] if single else out
+
     def dilate3(self, src: torch.Tensor) -> torch.Tensor:
         x, single = _batch(src, None)
         n, h, w = x.shape

@@ -80,6 +80,72 @@ def test_hysteresis_long_chains(eng):
         assert np.array_equal(host(eng.canny(dev(g), low, high)), cvops.canny(g, low, high))
 
 
+def _spiral(h, w):
+    """A one-pixel-wide weak spiral with a single strong seed at its centre: the longest possible
+    propagation chain, crossing every strip boundary many times in both directions."""
+    weak = np.zeros((h, w), bool)
+    y0, x0, y1, x1 = 1, 1, h - 2, w - 2
+    while y1 - y0 >= 4 and x1 - x0 >= 4:
+        weak[y0, x0:x1 + 1] = True
+        weak[y0:y1 + 1, x1] = True
+        weak[y1, x0 + 2:x1 + 1] = True
+        weak[y0 + 2:y1 + 1, x0 + 2] = True
+        weak[y0 + 2, x0 + 2:x0 + 4] = True
+        y0 += 2; x0 += 2; y1 -= 2; x1 -= 2
+    return weak
+
+
+@pytest.mark.parametrize("path", ["cluster", "strips"])
+@pytest.mark.parametrize("shape", [(64, 96), (203, 330), (9, 40), (1080, 1920)])
+def test_hysteresis_paths_on_synthetic_planes(eng, llfe, path, shape, monkeypatch):
+    """Drive the hysteresis stage directly through the plane inputs of both schedules (cluster kernel
+    and strip kernels) via llfe_canny on images built to have adversarial weak/strong structure."""
+    if path == "strips":
+        monkeypatch.setenv("LLFE_HYST_STRIPS", "1")
+    h, w = shape
+    r = np.random.default_rng(h * 7 + w)
+    # (1) blurred noise: dense, branching components; (2) a ramp image whose weak set is a long serpentine
+    src = cvops.gaussian_blur5(r.integers(0, 256, shape, dtype=np.uint8))
+    for low, high in ((50, 150), (20, 300), (5, 600)):
+        if h * w > 500000 and (low, high) != (20, 300):
+            continue
+        ref = cvops.canny(src, low, high) if h * w <= 500000 else __import__("cv2").Canny(src, low, high)
+        assert np.array_equal(host(eng.canny(dev(src), low, high)), ref), (path, shape, low, high)
+    yy, xx = np.mgrid[0:h, 0:w]
+    g = ((xx * 3 + ((yy // 9) % 2) * 40) % 256).astype(np.uint8)
+    g[h // 2:, (2 * w) // 3:] = 255
+    ref = cvops.canny(g, 20, 250) if h * w <= 500000 else __import__("cv2").Canny(g, 20, 250)
+    assert np.array_equal(host(eng.canny(dev(g), 20, 250)), ref)
+    # shape-mask entry point (fused front + hysteresis + dilate) on the same schedule
+    bgr = np.stack([g, src, g], axis=-1)
+    ref_mask = cvops.shape_mask(bgr) if h * w <= 500000 else None
+    if ref_mask is not None:
+        assert np.array_equal(host(eng.shape_mask(dev(bgr))), ref_mask)
+    # the hysteresis stage alone on adversarial planes: a one-pixel spiral with one strong seed
+    weak = _spiral(h, w)
+    for seed_at in ("centre", "outer", "none"):
+        if path == "strips" and h * w > 500000 and seed_at != "none":
+            continue  # the fallback schedule walks a megapixel spiral one row per iteration: correct but slow
+        strong = np.zeros_like(weak)
+        ys, xs = np.nonzero(weak)
+        if seed_at == "centre":
+            strong[ys[-1], xs[-1]] = True
+        elif seed_at == "outer":
+            strong[ys[0], xs[0]] = True
+        want = weak & bool(strong.any())         # the spiral is one 8-connected component
+        got = host(eng.hysteresis(dev(weak.astype(np.uint8) * 255), dev(strong.astype(np.uint8) * 255)))
+        assert np.array_equal(got, want.astype(np.uint8) * 255), (path, shape, seed_at)
+        got_d = host(eng.hysteresis(dev(weak.astype(np.uint8)), dev(strong.astype(np.uint8)), dilate=True))
+        assert np.array_equal(got_d, cvops.dilate3(want.astype(np.uint8) * 255))
+    # random sparse planes against the oracle's flood fill
+    wk = r.random(shape) < 0.35
+    st = wk & (r.random(shape) < 0.01)
+    if h * w <= 500000:
+        want = cvops.hysteresis(wk, st)
+        got = host(eng.hysteresis(dev(wk.astype(np.uint8)), dev(st.astype(np.uint8))))
+        assert np.array_equal(got != 0, want != 0)
+
+
 @pytest.mark.parametrize("name", ["design_270x480_s1", "design_360x640_s2", "noise_96x160_s3", "design_101x203_s4"])
 def test_golden_masks(eng, golden, golden_inputs, name):
     meta, arrays = golden
