@@ -353,20 +353,32 @@ __global__ void __launch_bounds__(256) k_kmeans_pick(KmParams P, float* out_cent
 int run_kmeans(llfe_ctx* ctx, KmParams P, int n, float* d_centers, int32_t* d_labels, double* d_compact, int32_t* d_kused,
                int32_t* d_iters, uint64_t* d_sums, int32_t* d_sizes) {
     const size_t slots = (size_t)n * P.attempts;
-    const size_t need = WsCarver::need(slots * P.max_unique * 8) + WsCarver::need(slots * P.max_unique) +
+    const bool fast = P.weights == nullptr && !P.exact_sums;
+    // the fast path keeps the lists in shared memory; its global scratch (lists that do not fit) is
+    // sized for a bounded number of images per launch
+    int dist_images = n;
+    if (fast) {
+        const size_t per_img = (size_t)P.attempts * P.max_unique * 8;
+        dist_images = (int)((size_t)(256u << 20) / per_img);
+        if (dist_images < 1) dist_images = 1;
+        if (dist_images > n) dist_images = n;
+    }
+    const size_t dslots = (size_t)dist_images * P.attempts;
+    const size_t need = WsCarver::need(dslots * P.max_unique * 8) + WsCarver::need(slots * P.max_unique) +
                         WsCarver::need(slots * KMAX * 3 * 4) + 3 * WsCarver::need(slots * 8) +
                         WsCarver::need(slots * KMAX * 4 * 8);
     void* ws;
     LLFE_TRY(llfe_workspace(ctx, need, &ws));
     WsCarver c(ws);
-    P.dist = c.take<uint32_t>(slots * 2 * P.max_unique);
+    P.dist = c.take<uint32_t>(dslots * 2 * P.max_unique);
+    P.dist_images = dist_images;
     P.labels = c.take<uint8_t>(slots * P.max_unique);
     P.centers = c.take<float>(slots * KMAX * 3);
     P.compact = c.take<double>(slots);
     P.iters = (int32_t*)c.take<double>(slots);
     P.inexact = (int32_t*)c.take<double>(slots);
     P.sums = (unsigned long long*)c.take<unsigned long long>(slots * KMAX * 4);
-    if (P.weights == nullptr && !P.exact_sums) {
+    if (fast) {
         LLFE_TRY(launch_kmeans_fast(ctx, P, n));
     } else {
         LLFE_KERNEL(ctx, "k_kmeans");
@@ -403,9 +415,9 @@ extern "C" int llfe_kmeans_unique(llfe_ctx* ctx, const uint32_t* d_keys, const i
     P.exact_sums = 0;
     P.rng_state = d_rng_state;
     P.init = nullptr;
-    // bound the scratch: process the batch in chunks of images
-    const size_t per_img = (size_t)attempts * max_unique * 9 + 4096;
-    int chunk = (int)((size_t)(256u << 20) / per_img);
+    // bound the scratch (labels of every attempt): process the batch in chunks of images
+    const size_t per_img = (size_t)attempts * ((size_t)max_unique + 2048) + 4096;
+    int chunk = (int)((size_t)(512u << 20) / per_img);
     if (chunk < 1) chunk = 1;
     for (int i0 = 0; i0 < n; i0 += chunk) {
         const int m = (n - i0) < chunk ? (n - i0) : chunk;

@@ -2,14 +2,22 @@
 // color_extractor.py:189-196): same arithmetic and results as k_kmeans (k_kmeans.cu), laid
 // out for the SM:
 //   * one CTA per (attempt, image); the colour list lives in SHARED MEMORY for the whole
-//     solve (key | label<<24 per point, plus one aux word per point: the kmeans++ distance),
-//     so no iteration touches HBM or L2;
+//     solve (key | label<<24 per point, plus one aux word per point), so no iteration touches
+//     HBM or L2; lists too long for shared memory run the same code on a global scratch copy
+//     (second instantiation, IN_SMEM = false);
 //   * warp-blocked point ownership (warp w owns a contiguous block, lanes stride it): bank-
 //     conflict-free and contiguous for the kmeans++ prefix search;
-//   * centroid partial sums in packed per-thread REGISTER accumulators
-//     (count|R and G|B as 16-bit fields), combined once per iteration with REDUX
-//     warp reductions -- no atomics in the inner loop;
-//   * lists too long for shared memory fall back to a global scratch copy (same code).
+//   * kmeans++ (cv::generateCentersPP): integer squared distances in two instructions
+//     (per-byte |a-b| + IDP.4A); the three trial centres of a step are drawn first (the draws
+//     do not depend on the trials) and evaluated in ONE pass over the points; the sequential
+//     "p -= d; if (p <= 0) break" walk is an exact prefix search (warp totals -> row totals ->
+//     one warp scan);
+//   * Lloyd: the first assignment is cv2's exact float32 search for every point with packed
+//     16-bit register accumulators + REDUX; later assignments use Hamerly bounds (see below) so
+//     that only points that can change their label pay for the search, with exact integer sums
+//     updated incrementally.
+#include <stdlib.h>
+
 #include "llfe_common.cuh"
 #include "llfe_device.cuh"
 #include "k_kmeans_shared.cuh"
@@ -18,8 +26,9 @@ namespace {
 
 constexpr int FT = 512;
 constexpr int FW = FT / 32;
-
-__device__ __forceinline__ float4 ld_center(const float4* c, int k) { return c[k]; }
+constexpr int QROWS = 8;    // rows (of 32 points) per bounds-test / drain block
+constexpr int RMAX = 64;    // rows per warp the row-total table holds (IN_SMEM lists are shorter)
+constexpr unsigned FULL = 0xffffffffu;
 
 __device__ __forceinline__ float fdist4(float r, float g, float b, float4 c) {
     float t0 = __fsub_rn(r, c.x), t1 = __fsub_rn(g, c.y), t2 = __fsub_rn(b, c.z);
@@ -29,18 +38,33 @@ __device__ __forceinline__ float fdist4(float r, float g, float b, float4 c) {
     return d;
 }
 
-__device__ __forceinline__ void unpackf(uint32_t key, float& r, float& g, float& b) {
-    r = (float)((key >> 16) & 255u);
-    g = (float)((key >> 8) & 255u);
-    b = (float)(key & 255u);
+// fixed-point (1/64) bounds: q_up rounds up, q_dn down, each with one extra unit of slack
+__device__ __forceinline__ uint32_t q_up(float d) { return min(65535u, (uint32_t)(d * 64.f) + 2u); }
+__device__ __forceinline__ uint32_t q_dn(float d) {
+    const float v = fminf(d * 64.f, 65535.f);
+    return v >= 2.f ? (uint32_t)v - 1u : 0u;
 }
 
-template <int KC>
-__global__ void __launch_bounds__(FT, 1) k_kmeans_fast(KmParams P, int smem_points) {
+// bytes 2/1/0 of the key as exact floats without the conversion pipe: 2^23 + byte, minus 2^23
+__device__ __forceinline__ void unpackf(uint32_t key, float& r, float& g, float& b) {
+    r = __uint_as_float(__byte_perm(key, 0x4B000000u, 0x7652)) - 8388608.0f;
+    g = __uint_as_float(__byte_perm(key, 0x4B000000u, 0x7651)) - 8388608.0f;
+    b = __uint_as_float(__byte_perm(key, 0x4B000000u, 0x7650)) - 8388608.0f;
+}
+
+// squared RGB distance of two keys whose top bytes are equal: per-byte |a-b|, then sum of squares
+__device__ __forceinline__ uint32_t idist2(uint32_t a, uint32_t b) {
+    const uint32_t d = __vabsdiffu4(a, b);
+    return __dp4a(d, d, 0u);
+}
+
+template <int KC, bool IN_SMEM>
+__global__ void __launch_bounds__(FT, 1) k_kmeans_fast(KmParams P, int smem_points, int img_base) {
     extern __shared__ uint32_t dyn[];
-    const int att = blockIdx.x, img = blockIdx.y, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int att = blockIdx.x, img = blockIdx.y + img_base, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int U = min(P.count[img], P.max_unique);
     const int K = min(P.k, U);
+    if ((U <= smem_points) != IN_SMEM) return;  // the other instantiation owns this image
     const size_t slot = (size_t)img * P.attempts + att;
     if (K <= 1) {
         if (tid == 0) {
@@ -52,36 +76,39 @@ __global__ void __launch_bounds__(FT, 1) k_kmeans_fast(KmParams P, int smem_poin
     }
     const uint32_t* keys = P.keys + (size_t)img * P.max_unique;
     // point storage: shared memory when the list fits, else this slot's global scratch
-    uint32_t* pts;
-    uint32_t* aux;
-    if (U <= smem_points) {
-        pts = dyn;
-        aux = dyn + smem_points;
-    } else {
-        pts = P.dist + slot * 2 * (size_t)P.max_unique;
-        aux = pts + P.max_unique;
-    }
+    // (the global scratch is sized for one launch of `dist_images` images: index it by blockIdx.y)
+    uint32_t* const pts = IN_SMEM ? dyn : P.dist + ((size_t)blockIdx.y * P.attempts + att) * 2 * (size_t)P.max_unique;
+    uint32_t* const aux = IN_SMEM ? dyn + smem_points : pts + P.max_unique;
     // warp-blocked ownership: rows of 32 consecutive points, `rows` rows per warp
     const int rows = (U + 32 * FW - 1) / (32 * FW);
     const int wbase = warp * rows * 32;
 
     __shared__ float4 s_c[KMAX];
     __shared__ float4 s_old[KMAX];
-    __shared__ unsigned long long s_tot[KMAX][4];
-    __shared__ unsigned long long s_red[FW];
+    __shared__ float4 s_asg[KMAX];          // the centres the current labels were assigned with
+    __shared__ int s_sum[KMAX][4];          // exact per-cluster {sum R, sum G, sum B, count}
+    __shared__ uint32_t s_dq[KMAX], s_hq[KMAX], s_m[4];
+    __shared__ uint16_t s_queue[FW][QROWS * 32];  // per-warp queue of points whose bounds failed
+    __shared__ uint32_t s_rowsum[IN_SMEM ? FW : 1][IN_SMEM ? RMAX : 1];
     __shared__ unsigned long long s_wtot[FW];
+    __shared__ unsigned long long s_red3[FW][3];
     __shared__ double s_redd[FW];
-    __shared__ int s_ci;
-    __shared__ double s_p;
+    __shared__ int s_ci[3];
+    __shared__ double s_p[3];
     __shared__ int s_flag;
+    __shared__ unsigned int s_cnt[4];
     __shared__ unsigned long long s_far;
 
+    const long long t_start = clock64();
+    long long t_first = 0;
     if (tid == 0) s_flag = 0;
+    if (tid < 4) s_cnt[tid] = 0;
     for (int r = 0; r < rows; ++r) {
         int i = wbase + r * 32 + lane;
         if (i < U) pts[i] = keys[i] & 0xffffffu;
     }
     __syncthreads();
+    const long long t_loaded = clock64();
 
     int it;
     if (P.init) {
@@ -105,85 +132,142 @@ __global__ void __launch_bounds__(FT, 1) k_kmeans_fast(KmParams P, int smem_poin
             if (rs == 0) rs = 0xffffffffull;
             const int per_attempt = 1 + 6 * (K - 1);
             for (int i = 0; i < att * per_attempt; ++i) rng_next(rs);
-            s_ci = (int)(rng_next(rs) % (uint32_t)U);
+            s_ci[0] = (int)(rng_next(rs) % (uint32_t)U);
         }
         __syncthreads();
-        uint32_t ckey = pts[s_ci];
-        if (tid == 0) {
-            float r, g, b;
-            unpackf(ckey, r, g, b);
-            s_c[0] = make_float4(r, g, b, 0.f);
-        }
-        unsigned long long part = 0;
-        for (int r = 0; r < rows; ++r) {
-            int i = wbase + r * 32 + lane;
-            if (i < U) {
-                uint32_t d = idist(pts[i], ckey);
-                aux[i] = d;
-                part += d;
+        // dist[i] = min(dist[i], |x_i - x_c|^2) (aux), with per-row and per-warp totals for the prefix search
+        auto update_pass = [&](uint32_t ckey, bool first_centre) {
+            unsigned long long wt = 0;
+            for (int r = 0; r < rows; ++r) {
+                const int i = wbase + r * 32 + lane;
+                uint32_t d = 0u;
+                if (i < U) {
+                    d = idist2(pts[i], ckey);
+                    if (!first_centre) d = min(d, aux[i]);
+                    aux[i] = d;
+                }
+                const uint32_t rs32 = __reduce_add_sync(FULL, d);
+                if (IN_SMEM && lane == 0) s_rowsum[IN_SMEM ? warp : 0][IN_SMEM ? r : 0] = rs32;
+                wt += rs32;
             }
+            if (lane == 0) s_wtot[warp] = wt;
+        };
+        {
+            const uint32_t ckey = pts[s_ci[0]];
+            if (tid == 0) {
+                float r, g, b;
+                unpackf(ckey, r, g, b);
+                s_c[0] = make_float4(r, g, b, 0.f);
+            }
+            update_pass(ckey, true);
         }
-        part = warp_sum_u64(part);
-        __syncthreads();  // everyone has read s_ci
-        if (lane == 0) s_wtot[warp] = part;
         __syncthreads();
         unsigned long long sum0 = 0;
         for (int w = 0; w < FW; ++w) sum0 += s_wtot[w];
         for (int k = 1; k < K; ++k) {
-            unsigned long long best_s = ~0ull;
-            int best_c = -1;
-            unsigned long long before = 0;
-            for (int w = 0; w < warp; ++w) before += s_wtot[w];
-            const unsigned long long mytot = s_wtot[warp];
-            for (int trial = 0; trial < 3; ++trial) {
-                if (tid == 0) {
-                    uint32_t t = rng_next(rs);
-                    unsigned long long v = ((unsigned long long)t << 32) | rng_next(rs);
-                    s_p = __dmul_rn(__dmul_rn((double)v, 5.4210108624275221700372640043497e-20), (double)sum0);
-                    s_ci = U - 1;
+            // the three trial positions of this step (the draws do not depend on the trials' outcome)
+            if (tid == 0) {
+#pragma unroll
+                for (int t = 0; t < 3; ++t) {
+                    const uint32_t hi = rng_next(rs);
+                    const unsigned long long v = ((unsigned long long)hi << 32) | rng_next(rs);
+                    s_p[t] = __dmul_rn(__dmul_rn((double)v, 5.4210108624275221700372640043497e-20), (double)sum0);
+                    s_ci[t] = U - 1;
                 }
-                __syncthreads();
-                const double p = s_p;
-                // first i with inclusive prefix >= p  (== the sequential "p -= d; if (p <= 0) break")
-                if ((double)(before + mytot) >= p && ((double)before < p || warp == 0)) {
+            }
+            __syncthreads();
+            // first i with inclusive prefix >= p  (== the sequential "p -= d; if (p <= 0) break")
+            {
+                unsigned long long before = 0;
+                for (int w = 0; w < warp; ++w) before += s_wtot[w];
+                const unsigned long long mytot = s_wtot[warp];
+#pragma unroll
+                for (int t = 0; t < 3; ++t) {
+                    const double p = s_p[t];
+                    if (!((double)(before + mytot) >= p && ((double)before < p || warp == 0))) continue;  // warp-uniform
                     unsigned long long run = before;
-                    for (int r = 0; r < rows; ++r) {
-                        int i = wbase + r * 32 + lane;
-                        uint32_t v = i < U ? aux[i] : 0u;
+                    int r = 0;
+                    if (IN_SMEM) {
+                        // row of the hit from the row totals (one scan per 32 rows), then one scan inside the row
+                        for (int rb = 0; rb < rows; rb += 32) {
+                            const uint32_t v = (rb + lane < rows) ? s_rowsum[IN_SMEM ? warp : 0][IN_SMEM ? rb + lane : 0] : 0u;
+                            unsigned long long inc = v;
+#pragma unroll
+                            for (int o = 1; o < 32; o <<= 1) {
+                                const unsigned long long nn = __shfl_up_sync(FULL, inc, o);
+                                if (lane >= o) inc += nn;
+                            }
+                            const uint32_t hit = __ballot_sync(FULL, (double)(run + inc) >= p && rb + lane < rows);
+                            if (hit) {
+                                const int l = __ffs(hit) - 1;
+                                r = rb + l;
+                                run += __shfl_sync(FULL, inc, l) - __shfl_sync(FULL, (unsigned long long)v, l);
+                                break;
+                            }
+                            run += __shfl_sync(FULL, inc, 31);
+                            r = rb + 32;
+                        }
+                    }
+                    for (; r < rows; ++r) {
+                        const int i = wbase + r * 32 + lane;
+                        const uint32_t v = i < U ? aux[i] : 0u;
                         uint32_t inc = v;
 #pragma unroll
                         for (int o = 1; o < 32; o <<= 1) {
-                            uint32_t nn = __shfl_up_sync(0xffffffffu, inc, o);
+                            const uint32_t nn = __shfl_up_sync(FULL, inc, o);
                             if (lane >= o) inc += nn;
                         }
-                        uint32_t rowsum = __shfl_sync(0xffffffffu, inc, 31);
+                        const uint32_t rowsum = __shfl_sync(FULL, inc, 31);
                         if ((double)(run + rowsum) >= p) {
-                            uint32_t hit = __ballot_sync(0xffffffffu, (double)(run + inc) >= p);
-                            int idx = wbase + r * 32 + (__ffs(hit) - 1);
-                            if (lane == 0 && idx < U - 1) atomicMin(&s_ci, idx);
+                            const uint32_t hit = __ballot_sync(FULL, (double)(run + inc) >= p);
+                            const int idx = wbase + r * 32 + (__ffs(hit) - 1);
+                            if (lane == 0 && idx < U - 1) atomicMin(&s_ci[t], idx);
                             break;
                         }
                         run += rowsum;
                     }
                 }
-                __syncthreads();
-                const int ci = s_ci;
-                const uint32_t tk = pts[ci];
-                unsigned long long ps = 0;
-                for (int r = 0; r < rows; ++r) {
-                    int i = wbase + r * 32 + lane;
-                    if (i < U) ps += min(idist(pts[i], tk), aux[i]);
+            }
+            __syncthreads();
+            // one pass evaluates the three trials: s_t = sum_i min(|x_i - x_ci(t)|^2, dist[i])
+            const int c0 = s_ci[0], c1 = s_ci[1], c2 = s_ci[2];
+            const uint32_t t0 = pts[c0], t1 = pts[c1], t2 = pts[c2];
+            unsigned long long a0 = 0, a1 = 0, a2 = 0;
+            for (int rb = 0; rb < rows; rb += 64) {   // 64 rows * 195075 < 2^32: 32-bit partial sums
+                const int re = min(rows, rb + 64);
+                uint32_t p0 = 0, p1 = 0, p2 = 0;
+                for (int r = rb; r < re; ++r) {
+                    const int i = wbase + r * 32 + lane;
+                    if (i < U) {
+                        const uint32_t x = pts[i], d = aux[i];
+                        p0 += min(idist2(x, t0), d);
+                        p1 += min(idist2(x, t1), d);
+                        p2 += min(idist2(x, t2), d);
+                    }
                 }
-                ps = warp_sum_u64(ps);
-                if (lane == 0) s_red[warp] = ps;
-                __syncthreads();
+                a0 += p0;
+                a1 += p1;
+                a2 += p2;
+            }
+            a0 = warp_sum_u64(a0);
+            a1 = warp_sum_u64(a1);
+            a2 = warp_sum_u64(a2);
+            if (lane == 0) {
+                s_red3[warp][0] = a0;
+                s_red3[warp][1] = a1;
+                s_red3[warp][2] = a2;
+            }
+            __syncthreads();
+            unsigned long long best_s = ~0ull;
+            int best_c = -1;
+#pragma unroll
+            for (int t = 0; t < 3; ++t) {
                 unsigned long long s = 0;
-                for (int w = 0; w < FW; ++w) s += s_red[w];
-                if (s < best_s) {
+                for (int w = 0; w < FW; ++w) s += s_red3[w][t];
+                if (s < best_s) {   // strictly smaller: the first trial wins ties
                     best_s = s;
-                    best_c = ci;
+                    best_c = t == 0 ? c0 : t == 1 ? c1 : c2;
                 }
-                __syncthreads();
             }
             const uint32_t bk = pts[best_c];
             if (tid == 0) {
@@ -191,17 +275,7 @@ __global__ void __launch_bounds__(FT, 1) k_kmeans_fast(KmParams P, int smem_poin
                 unpackf(bk, r, g, b);
                 s_c[k] = make_float4(r, g, b, 0.f);
             }
-            unsigned long long wt = 0;
-            for (int r = 0; r < rows; ++r) {
-                int i = wbase + r * 32 + lane;
-                if (i < U) {
-                    uint32_t d = min(idist(pts[i], bk), aux[i]);
-                    aux[i] = d;
-                    wt += d;
-                }
-            }
-            wt = warp_sum_u64(wt);
-            if (lane == 0) s_wtot[warp] = wt;
+            if (k + 1 < K) update_pass(bk, false);   // dist / totals for the next step (not needed after the last)
             sum0 = best_s;
             __syncthreads();
         }
@@ -209,75 +283,172 @@ __global__ void __launch_bounds__(FT, 1) k_kmeans_fast(KmParams P, int smem_poin
     }
 
     // ------------------------------ Lloyd ------------------------------------------
-    for (;;) {
-        if (tid < KMAX * 4) (&s_tot[0][0])[tid] = 0ull;
-        __syncthreads();
-        uint32_t acc_lo[KC], acc_hi[KC];  // lo = G<<16 | B ; hi = count<<16 | R   (16-bit fields)
+    // Assignment with Hamerly bounds.  Every point carries (in its aux word, free after the seeding)
+    // an upper bound `ub` on its distance to its own centre and a lower bound `lb` on its distance to
+    // every other centre, as 16-bit fixed point (1/64 colour units, ub rounded up, lb down, one extra
+    // unit of slack each).  When the centres move by delta_k, ub += delta_own and lb -= max delta_other
+    // stay valid; while ub < max(lb, half the distance from the own centre to its nearest neighbour)
+    // the point provably keeps its label -- and by a margin (>= 1/64) far above the float32 rounding of
+    // cv2's squared distances (< 3e-4 at 442), so cv2's argmin gives the same label.  Every other point
+    // takes cv2's exact float32 search (separate mul/add, strict '<').  Sums are kept as exact integers
+    // and updated incrementally when a label changes (== cv2's sequential float32 sums below 2^24).
+    const long long t_seeded = clock64();
+    // Ownership is ROW-INTERLEAVED here (row r of warp w = points (r * FW + w) * 32 ...): the list is
+    // sorted by colour, so the points near a cluster boundary are neighbours in it; interleaving
+    // spreads them over all warps (the seeding above needs contiguous blocks for its prefix search).
+    for (bool first = true;; first = false) {
+        if (!first && t_first == 0) t_first = clock64();
+        if (tid < KMAX) s_asg[tid] = s_c[tid];
+        if (first) {
+            if (tid < KMAX * 4) (&s_sum[0][0])[tid] = 0;
+            __syncthreads();
+            uint32_t acc_lo[KC], acc_hi[KC];  // lo = G<<16 | B ; hi = count<<16 | R   (16-bit fields)
 #pragma unroll
-        for (int k = 0; k < KC; ++k) acc_lo[k] = acc_hi[k] = 0u;
-        for (int r0 = 0; r0 < rows; r0 += 256) {
-            const int r1 = min(rows, r0 + 256);
-            for (int r = r0; r < r1; ++r) {
-                int i = wbase + r * 32 + lane;
-                if (i >= U) continue;
-                uint32_t key = pts[i] & 0xffffffu;
-                float fr, fg, fb;
-                unpackf(key, fr, fg, fb);
-                float bd = fdist4(fr, fg, fb, s_c[0]);
-                int bl = 0;
+            for (int k = 0; k < KC; ++k) acc_lo[k] = acc_hi[k] = 0u;
+            for (int r0 = 0; r0 < rows; r0 += 256) {
+                const int r1 = min(rows, r0 + 256);
+                for (int r = r0; r < r1; ++r) {
+                    int i = (r * FW + warp) * 32 + lane;
+                    if (i >= U) continue;
+                    uint32_t key = pts[i] & 0xffffffu;
+                    float fr, fg, fb;
+                    unpackf(key, fr, fg, fb);
+                    float bd = fdist4(fr, fg, fb, s_c[0]), sd = 3e38f;
+                    int bl = 0;
 #pragma unroll
-                for (int k = 1; k < KC; ++k) {
-                    if (k < K) {
-                        float d = fdist4(fr, fg, fb, s_c[k]);
-                        if (d < bd) {
-                            bd = d;
-                            bl = k;
+                    for (int k = 1; k < KC; ++k) {
+                        if (k < K) {
+                            float d = fdist4(fr, fg, fb, s_c[k]);
+                            if (d < bd) {
+                                sd = bd;
+                                bd = d;
+                                bl = k;
+                            } else {
+                                sd = fminf(sd, d);
+                            }
                         }
                     }
-                }
-                pts[i] = key | ((uint32_t)bl << 24);
-                const uint32_t plo = key & 0xffffu, pr = (key >> 16) | 0x10000u;
-                const uint32_t lo = ((plo & 0xff00u) << 8) | (plo & 0xffu);
+                    pts[i] = key | ((uint32_t)bl << 24);
+                    aux[i] = (q_up(__fsqrt_rn(bd)) << 16) | q_dn(__fsqrt_rn(sd));
+                    const uint32_t plo = key & 0xffffu, pr = (key >> 16) | 0x10000u;
+                    const uint32_t lo = ((plo & 0xff00u) << 8) | (plo & 0xffu);
 #pragma unroll
-                for (int k = 0; k < KC; ++k) {
-                    const bool m = (bl == k);
-                    acc_lo[k] += m ? lo : 0u;
-                    acc_hi[k] += m ? pr : 0u;
-                }
-            }
-            // flush the 16-bit fields before they can overflow (256 rows * 255 < 65536)
-#pragma unroll
-            for (int k = 0; k < KC; ++k) {
-                if (k < K) {
-                    uint32_t sb = __reduce_add_sync(0xffffffffu, acc_lo[k] & 0xffffu);
-                    uint32_t sg = __reduce_add_sync(0xffffffffu, acc_lo[k] >> 16);
-                    uint32_t sr = __reduce_add_sync(0xffffffffu, acc_hi[k] & 0xffffu);
-                    uint32_t sn = __reduce_add_sync(0xffffffffu, acc_hi[k] >> 16);
-                    if (lane == 0 && sn) {
-                        atomicAdd(&s_tot[k][0], (unsigned long long)sr);
-                        atomicAdd(&s_tot[k][1], (unsigned long long)sg);
-                        atomicAdd(&s_tot[k][2], (unsigned long long)sb);
-                        atomicAdd(&s_tot[k][3], (unsigned long long)sn);
+                    for (int k = 0; k < KC; ++k) {
+                        const bool m = (bl == k);
+                        acc_lo[k] += m ? lo : 0u;
+                        acc_hi[k] += m ? pr : 0u;
                     }
                 }
-                acc_lo[k] = acc_hi[k] = 0u;
+                // flush the 16-bit fields before they can overflow (256 rows * 255 < 65536)
+#pragma unroll
+                for (int k = 0; k < KC; ++k) {
+                    if (k < K) {
+                        uint32_t sb = __reduce_add_sync(FULL, acc_lo[k] & 0xffffu);
+                        uint32_t sg = __reduce_add_sync(FULL, acc_lo[k] >> 16);
+                        uint32_t sr = __reduce_add_sync(FULL, acc_hi[k] & 0xffffu);
+                        uint32_t sn = __reduce_add_sync(FULL, acc_hi[k] >> 16);
+                        if (lane == 0 && sn) {
+                            atomicAdd(&s_sum[k][0], (int)sr);
+                            atomicAdd(&s_sum[k][1], (int)sg);
+                            atomicAdd(&s_sum[k][2], (int)sb);
+                            atomicAdd(&s_sum[k][3], (int)sn);
+                        }
+                    }
+                    acc_lo[k] = acc_hi[k] = 0u;
+                }
+            }
+        } else {
+            __syncthreads();  // s_dq / s_hq / s_m of the last update are visible
+            const uint32_t m1 = s_m[0], m2 = s_m[1], kmax = s_m[2];
+            uint16_t* q = s_queue[warp];
+            // Two phases per block of QROWS rows so that the expensive path runs on full warps: (A) every
+            // lane tests the bounds of its points and the failing ones are compacted into the warp's
+            // queue; (B) the queue is drained 32 points at a time.
+            for (int rb0 = 0; rb0 < rows; rb0 += QROWS) {
+                const int rb1 = min(rows, rb0 + QROWS);
+                int qn = 0;
+                for (int r = rb0; r < rb1; ++r) {
+                    const int i = (r * FW + warp) * 32 + lane;
+                    bool need = false;
+                    if (i < U) {
+                        const uint32_t w = pts[i], x = aux[i];
+                        const uint32_t a = w >> 24;
+                        const uint32_t ub = min(65535u, (x >> 16) + s_dq[a]);
+                        const uint32_t dl = (a == kmax) ? m2 : m1;
+                        uint32_t lb = x & 0xffffu;
+                        lb = lb > dl ? lb - dl : 0u;
+                        aux[i] = (ub << 16) | lb;
+                        need = ub >= max(lb, s_hq[a]);
+                    }
+                    const uint32_t bal = __ballot_sync(FULL, need);
+                    if (need) q[qn + __popc(bal & ((1u << lane) - 1u))] = (uint16_t)((r - rb0) * 32 + lane);
+                    qn += __popc(bal);
+                }
+                if (P.dbg && lane == 0) atomicAdd(&s_cnt[0], (unsigned)qn);
+                __syncwarp();
+                for (int j = lane; j < qn; j += 32) {
+                    const int qe = (int)q[j];
+                    const int i = ((rb0 + (qe >> 5)) * FW + warp) * 32 + (qe & 31);
+                    const uint32_t w = pts[i], x = aux[i];
+                    const uint32_t a = w >> 24, lb = x & 0xffffu;
+                    const uint32_t bound = max(lb, s_hq[a]);
+                    const uint32_t key = w & 0xffffffu;
+                    float fr, fg, fb;
+                    unpackf(key, fr, fg, fb);
+                    const uint32_t ub = q_up(__fsqrt_rn(fdist4(fr, fg, fb, s_c[a])));  // tighten
+                    if (ub < bound) {
+                        aux[i] = (ub << 16) | lb;
+                        continue;
+                    }
+                    if (P.dbg) atomicAdd(&s_cnt[1], 1u);
+                    float bd = fdist4(fr, fg, fb, s_c[0]), sd = 3e38f;
+                    int bl = 0;
+#pragma unroll
+                    for (int k = 1; k < KC; ++k) {
+                        if (k < K) {
+                            float d = fdist4(fr, fg, fb, s_c[k]);
+                            if (d < bd) {
+                                sd = bd;
+                                bd = d;
+                                bl = k;
+                            } else {
+                                sd = fminf(sd, d);
+                            }
+                        }
+                    }
+                    aux[i] = (q_up(__fsqrt_rn(bd)) << 16) | q_dn(__fsqrt_rn(sd));
+                    if (P.dbg && (uint32_t)bl != a) atomicAdd(&s_cnt[2], 1u);
+                    if ((uint32_t)bl != a) {
+                        pts[i] = key | ((uint32_t)bl << 24);
+                        const int cr = (int)(key >> 16), cg = (int)((key >> 8) & 255u), cb = (int)(key & 255u);
+                        atomicAdd(&s_sum[a][0], -cr);
+                        atomicAdd(&s_sum[a][1], -cg);
+                        atomicAdd(&s_sum[a][2], -cb);
+                        atomicAdd(&s_sum[a][3], -1);
+                        atomicAdd(&s_sum[bl][0], cr);
+                        atomicAdd(&s_sum[bl][1], cg);
+                        atomicAdd(&s_sum[bl][2], cb);
+                        atomicAdd(&s_sum[bl][3], 1);
+                    }
+                }
+                __syncwarp();
             }
         }
         __syncthreads();
         // empty-cluster repair (cv2: the biggest cluster gives up its farthest member, last max wins)
         for (int k = 0; k < K; ++k) {
-            if (s_tot[k][3] != 0) continue;  // uniform (shared memory)
+            if (s_sum[k][3] != 0) continue;  // uniform (shared memory)
             int mk = 0;
             for (int k1 = 1; k1 < K; ++k1)
-                if (s_tot[mk][3] < s_tot[k1][3]) mk = k1;
-            const float sc = __fdiv_rn(1.f, (float)s_tot[mk][3]);
-            const float4 base = make_float4(__fmul_rn((float)s_tot[mk][0], sc), __fmul_rn((float)s_tot[mk][1], sc),
-                                            __fmul_rn((float)s_tot[mk][2], sc), 0.f);
+                if (s_sum[mk][3] < s_sum[k1][3]) mk = k1;
+            const float sc = __fdiv_rn(1.f, (float)s_sum[mk][3]);
+            const float4 base = make_float4(__fmul_rn((float)s_sum[mk][0], sc), __fmul_rn((float)s_sum[mk][1], sc),
+                                            __fmul_rn((float)s_sum[mk][2], sc), 0.f);
             if (tid == 0) s_far = 0ull;
             __syncthreads();
             unsigned long long best = 0ull;
             for (int r = 0; r < rows; ++r) {
-                int i = wbase + r * 32 + lane;
+                int i = (r * FW + warp) * 32 + lane;
                 if (i >= U) continue;
                 uint32_t w = pts[i];
                 if ((int)(w >> 24) != mk) continue;
@@ -293,26 +464,26 @@ __global__ void __launch_bounds__(FT, 1) k_kmeans_fast(KmParams P, int smem_poin
                 int far = (int)(uint32_t)((s_far - 1ull) & 0xffffffffull);
                 uint32_t fk = pts[far] & 0xffffffu;
                 pts[far] = fk | ((uint32_t)k << 24);
+                aux[far] = 0xffff0000u;  // bounds unknown: ub = inf, lb = 0
                 s_c[mk] = base;  // OpenCV stores the donor's provisional mean in old_centers[max_k]
-                s_tot[mk][0] -= fk >> 16;
-                s_tot[mk][1] -= (fk >> 8) & 255u;
-                s_tot[mk][2] -= fk & 255u;
-                s_tot[mk][3] -= 1;
-                s_tot[k][0] += fk >> 16;
-                s_tot[k][1] += (fk >> 8) & 255u;
-                s_tot[k][2] += fk & 255u;
-                s_tot[k][3] += 1;
+                s_sum[mk][0] -= (int)(fk >> 16);
+                s_sum[mk][1] -= (int)((fk >> 8) & 255u);
+                s_sum[mk][2] -= (int)(fk & 255u);
+                s_sum[mk][3] -= 1;
+                s_sum[k][0] += (int)(fk >> 16);
+                s_sum[k][1] += (int)((fk >> 8) & 255u);
+                s_sum[k][2] += (int)(fk & 255u);
+                s_sum[k][3] += 1;
             }
             __syncthreads();
         }
         // new centres
         if (tid < K) {
             s_old[tid] = s_c[tid];
-            const float sc = __fdiv_rn(1.f, (float)s_tot[tid][3]);
-            if (s_tot[tid][0] >= (1ull << 24) || s_tot[tid][1] >= (1ull << 24) || s_tot[tid][2] >= (1ull << 24))
-                atomicOr(&s_flag, 1);
-            s_c[tid] = make_float4(__fmul_rn((float)s_tot[tid][0], sc), __fmul_rn((float)s_tot[tid][1], sc),
-                                   __fmul_rn((float)s_tot[tid][2], sc), 0.f);
+            const float sc = __fdiv_rn(1.f, (float)s_sum[tid][3]);
+            if (s_sum[tid][0] >= (1 << 24) || s_sum[tid][1] >= (1 << 24) || s_sum[tid][2] >= (1 << 24)) atomicOr(&s_flag, 1);
+            s_c[tid] = make_float4(__fmul_rn((float)s_sum[tid][0], sc), __fmul_rn((float)s_sum[tid][1], sc),
+                                   __fmul_rn((float)s_sum[tid][2], sc), 0.f);
         }
         __syncthreads();
         double shift = 0.0;
@@ -329,13 +500,45 @@ __global__ void __launch_bounds__(FT, 1) k_kmeans_fast(KmParams P, int smem_poin
         const int last_it = P.max_iter > 2 ? P.max_iter : 2;
         const bool last = (it == last_it) || (!first_seeded && shift <= P.eps2);
         if (last) break;
+        // bounds bookkeeping for the next assignment: how far every centre moved since the assignment
+        // just done (s_asg), and half the distance of every centre to its nearest neighbour
+        if (tid < K) {
+            const float4 c = s_c[tid], o = s_asg[tid];
+            const float dx = c.x - o.x, dy = c.y - o.y, dz = c.z - o.z;
+            s_dq[tid] = q_up(sqrtf(dx * dx + dy * dy + dz * dz));
+            float nn = 3e38f;
+            for (int j = 0; j < K; ++j) {
+                if (j == tid) continue;
+                const float4 e = s_c[j];
+                const float ex = c.x - e.x, ey = c.y - e.y, ez = c.z - e.z;
+                nn = fminf(nn, ex * ex + ey * ey + ez * ez);
+            }
+            s_hq[tid] = q_dn(0.5f * sqrtf(nn));
+        }
         __syncthreads();
+        if (tid == 0) {
+            uint32_t m1 = 0, m2 = 0, km = 0;
+            for (int k = 0; k < K; ++k) {
+                const uint32_t d = s_dq[k];
+                if (d > m1) {
+                    m2 = m1;
+                    m1 = d;
+                    km = k;
+                } else if (d > m2) {
+                    m2 = d;
+                }
+            }
+            s_m[0] = m1;
+            s_m[1] = m2;
+            s_m[2] = km;
+        }
     }
+    const long long t_conv = clock64();
     // compactness with the final centres and the labels of the last assignment; labels out
     uint8_t* labels = P.labels + slot * P.max_unique;
     double part = 0.0;
     for (int r = 0; r < rows; ++r) {
-        int i = wbase + r * 32 + lane;
+        int i = (r * FW + warp) * 32 + lane;
         if (i >= U) continue;
         uint32_t w = pts[i];
         float fr, fg, fb;
@@ -344,7 +547,7 @@ __global__ void __launch_bounds__(FT, 1) k_kmeans_fast(KmParams P, int smem_poin
         labels[i] = (uint8_t)(w >> 24);
     }
 #pragma unroll
-    for (int o = 16; o > 0; o >>= 1) part += __shfl_xor_sync(0xffffffffu, part, o);
+    for (int o = 16; o > 0; o >>= 1) part += __shfl_xor_sync(FULL, part, o);
     if (lane == 0) s_redd[warp] = part;
     __syncthreads();
     if (tid == 0) {
@@ -353,6 +556,20 @@ __global__ void __launch_bounds__(FT, 1) k_kmeans_fast(KmParams P, int smem_poin
         P.compact[slot] = comp;
         P.iters[slot] = it;
         P.inexact[slot] = s_flag;
+        if (P.dbg) {
+            unsigned long long* d = P.dbg + slot * 8;
+            const long long t_end = clock64();
+            if (t_first == 0) t_first = t_conv;
+            d[0] = t_loaded - t_start;
+            d[1] = t_seeded - t_loaded;
+            d[2] = t_first - t_seeded;
+            d[3] = t_conv - t_first;
+            d[4] = t_end - t_conv;
+            d[5] = it;
+            d[6] = U;
+            d[7] = t_end - t_start;
+            d[0] = ((unsigned long long)s_cnt[0] << 40) | ((unsigned long long)s_cnt[1] << 20) | s_cnt[2];
+        }
     }
     if (tid < K) {
         const float4 c = s_c[tid];
@@ -360,35 +577,50 @@ __global__ void __launch_bounds__(FT, 1) k_kmeans_fast(KmParams P, int smem_poin
         o[0] = c.x;
         o[1] = c.y;
         o[2] = c.z;
-        for (int j = 0; j < 4; ++j) P.sums[slot * KMAX * 4 + tid * 4 + j] = s_tot[tid][j];
+        for (int j = 0; j < 4; ++j) P.sums[slot * KMAX * 4 + tid * 4 + j] = (unsigned long long)s_sum[tid][j];
     }
+}
+
+template <int KC>
+int launch_kc(llfe_ctx* ctx, const KmParams& P, int n, int smem_points, size_t dyn, size_t avail) {
+    static bool attr_set = false;
+    if (!attr_set) {
+        LLFE_CUDA(cudaFuncSetAttribute(k_kmeans_fast<KC, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)avail));
+        attr_set = true;
+    }
+    // one launch for the whole batch: the block scheduler back-fills SMs as CTAs finish, so attempts
+    // that need many iterations do not hold up a wave
+    LLFE_KERNEL(ctx, "k_kmeans_fast");
+    k_kmeans_fast<KC, true><<<dim3(P.attempts, n), FT, dyn, ctx->stream>>>(P, smem_points, 0);
+    LLFE_LAUNCHED(ctx);
+    // images whose colour list does not fit in shared memory (every CTA of the others exits at once);
+    // the global scratch holds P.dist_images images per launch
+    if (P.max_unique > smem_points) {
+        for (int i0 = 0; i0 < n; i0 += P.dist_images) {
+            const int m = (n - i0) < P.dist_images ? (n - i0) : P.dist_images;
+            LLFE_KERNEL(ctx, "k_kmeans_fast_global");
+            k_kmeans_fast<KC, false><<<dim3(P.attempts, m), FT, 0, ctx->stream>>>(P, smem_points, i0);
+            LLFE_LAUNCHED(ctx);
+        }
+    }
+    return LLFE_OK;
 }
 
 }  // namespace
 
 // smem_points: how many points (8 bytes each) the dynamic shared memory of one CTA can hold
-int launch_kmeans_fast(llfe_ctx* ctx, const KmParams& P, int n) {
-    static bool attr_set = false;
-    const size_t static_smem = 4096;  // centres, totals, reduction scratch (upper bound)
+int launch_kmeans_fast(llfe_ctx* ctx, const KmParams& P0, int n) {
+    KmParams P = P0;
+    if (const char* dbg = getenv("LLFE_KMEANS_DEBUG")) P.dbg = (unsigned long long*)(uintptr_t)strtoull(dbg, nullptr, 10);
+    const size_t static_smem = 20 * 1024;  // centres, totals, queues, row totals, reduction scratch (upper bound)
     size_t avail = ctx->smem_optin > static_smem ? ctx->smem_optin - static_smem : 0;
     int smem_points = (int)(avail / 8);
     if (smem_points > P.max_unique) smem_points = P.max_unique;
+    if (smem_points > RMAX * 32 * FW) smem_points = RMAX * 32 * FW;
     smem_points &= ~31;
     const size_t dyn = (size_t)smem_points * 8;
-    if (!attr_set) {
-        LLFE_CUDA(cudaFuncSetAttribute(k_kmeans_fast<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)avail));
-        LLFE_CUDA(cudaFuncSetAttribute(k_kmeans_fast<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)avail));
-        LLFE_CUDA(cudaFuncSetAttribute(k_kmeans_fast<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)avail));
-        attr_set = true;
-    }
-    dim3 grid(P.attempts, n);
-    LLFE_KERNEL(ctx, "k_kmeans_fast");
-    if (P.k <= 8)
-        k_kmeans_fast<8><<<grid, FT, dyn, ctx->stream>>>(P, smem_points);
-    else if (P.k <= 16)
-        k_kmeans_fast<16><<<grid, FT, dyn, ctx->stream>>>(P, smem_points);
-    else
-        k_kmeans_fast<32><<<grid, FT, dyn, ctx->stream>>>(P, smem_points);
-    LLFE_LAUNCHED(ctx);
-    return LLFE_OK;
+    if (P.k <= 5) return launch_kc<5>(ctx, P, n, smem_points, dyn, avail);
+    if (P.k <= 8) return launch_kc<8>(ctx, P, n, smem_points, dyn, avail);
+    if (P.k <= 16) return launch_kc<16>(ctx, P, n, smem_points, dyn, avail);
+    return launch_kc<32>(ctx, P, n, smem_points, dyn, avail);
 }

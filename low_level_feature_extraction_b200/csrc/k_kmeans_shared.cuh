@@ -16,13 +16,15 @@ struct KmParams {
     const uint64_t* rng_state; // [n] (PP mode) or null
     const float* init;         // [n][k][3] (seeded mode) or null
     // scratch, per (image, attempt)
-    uint32_t* dist;            // [n][attempts][2 * max_unique]
+    uint32_t* dist;            // [dist_images][attempts][2 * max_unique]
+    int dist_images;           // images the dist scratch holds (fast path: one launch of the global variant)
     uint8_t* labels;           // [n][attempts][max_unique]
     float* centers;            // [n][attempts][KMAX][3]
     double* compact;           // [n][attempts]
     int32_t* iters;            // [n][attempts]
     int32_t* inexact;          // [n][attempts]
     unsigned long long* sums;  // [n][attempts][KMAX][4]  final sums/counts
+    unsigned long long* dbg;   // optional [n][attempts][8] phase clocks (LLFE_KMEANS_DEBUG), else null
 };
 
 __device__ __forceinline__ uint32_t idist(uint32_t a, uint32_t b) {
