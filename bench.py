@@ -296,7 +296,7 @@ def run_ours(args):
                "h2d_bytes_per_step": int(res["_h2d_bytes"]) * world, "d2h_bytes_per_step": int(res["_d2h_bytes"]) * world,
                "steps": args.e2e_steps,
                "api": "BatchAnalyzer.run_host: pinned host images in, host masks/palettes out, chunked copies "
-                      "overlapped with kernels on two streams"}
+                      f"overlapped with kernels ({an.cfg.host_streams} streams, {an.cfg.host_chunk} images per stage)"}
 
     if rank == 0:
         peak, peak_src = measured_peak()

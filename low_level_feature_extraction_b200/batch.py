@@ -3,8 +3,9 @@
 `BatchAnalyzer.run_device` works on a device-resident (B, H, W, 3) uint8 BGR batch
 and leaves every result on the device.  `run_host` is the end-to-end path: pinned
 host images in, host results out, with the host<->device copies of one chunk
-overlapping the kernels of the other (two streams, two llfe contexts because a
-context's workspace belongs to one stream at a time).
+overlapping the kernels of the others (`host_streams` streams, one llfe context each
+because a context's workspace belongs to one stream at a time).  PCIe is the bound:
+1.59 GB in + 1.06 GB out per 256 images at ~56 GB/s per direction.
 
 Batches shard across GPUs by image index with no collective (see dist.py).
 """
@@ -31,7 +32,8 @@ class BatchConfig:
     high: int = 150
     seed: int = 0              # device noise seed / cv::RNG state base
     chunk: int = 256           # images per C-ABI call on the device path (the library sub-chunks for L2)
-    host_chunk: int = 32       # images per copy/compute pipeline stage of run_host
+    host_chunk: int = 16       # images per copy/compute pipeline stage of run_host
+    host_streams: int = 3      # pipeline depth of run_host (streams / llfe contexts / staging buffers)
 
 
 class BatchAnalyzer:
@@ -39,8 +41,9 @@ class BatchAnalyzer:
         self.cfg = cfg or BatchConfig()
         self.h, self.w = h, w
         self.device = torch.device("cuda", device)
-        self.engines = [Engine(device), Engine(device)]
-        self.streams = [torch.cuda.Stream(self.device), torch.cuda.Stream(self.device)]
+        ns = max(1, self.cfg.host_streams)
+        self.engines = [Engine(device) for _ in range(ns)]
+        self.streams = [torch.cuda.Stream(self.device) for _ in range(ns)]
         self._dev_in = None
 
     # ---- device-resident ---------------------------------------------------------------
@@ -104,12 +107,12 @@ class BatchAnalyzer:
         n = images.shape[0]
         host_out = host_out if host_out is not None else self.alloc_host_outputs(n)
         if self._dev_in is None:
-            self._dev_in = [torch.empty((c.host_chunk, self.h, self.w, 3), dtype=torch.uint8, device=self.device) for _ in range(2)]
-            self._dev_out = [self.alloc_outputs(c.host_chunk) for _ in range(2)]
-            self._events = [torch.cuda.Event() for _ in range(2)]
+            ns = len(self.streams)
+            self._dev_in = [torch.empty((c.host_chunk, self.h, self.w, 3), dtype=torch.uint8, device=self.device) for _ in range(ns)]
+            self._dev_out = [self.alloc_outputs(c.host_chunk) for _ in range(ns)]
         bytes_in = bytes_out = 0
         for j, i0 in enumerate(range(0, n, c.host_chunk)):
-            b = j & 1
+            b = j % len(self.streams)
             m = min(c.host_chunk, n - i0)
             st = self.streams[b]
             with torch.cuda.stream(st):

@@ -78,6 +78,49 @@ def test_fused_full_size_vs_cv2(eng):
         assert np.array_equal(out["shadow_mask"][0].cpu().numpy(), refpath.shadow_mask(img)[1])
 
 
+def test_4k_and_tall_images_vs_cv2(eng):
+    """BASELINE config 3 size (3840x2160: 120 plane words per row -> 4 words per lane, 16-CTA clusters),
+    a tall narrow image (many rows per strip), and a batch of two so that image offsets are exercised."""
+    imgs = [design_image(2160, 3840, 7), noise_image(2160, 3840, 8)]
+    batch = np.stack(imgs)
+    out = eng.pipeline(dev(batch), colors=False)
+    for i, img in enumerate(imgs):
+        assert np.array_equal(out["shape_mask"][i].cpu().numpy(), refpath.shape_mask(img)), i
+        ref_blur, ref_mask = refpath.shadow_mask(img)
+        assert np.array_equal(out["shadow_mask"][i].cpu().numpy(), ref_mask), i
+        s, n = out["shadow_sums"][i].cpu().tolist()
+        assert n == int((ref_mask == 255).sum()) and s == int(ref_blur[ref_mask == 255].astype(np.int64).sum())
+    tall = design_image(1900, 264, 9)
+    out = eng.pipeline(dev(tall[None]), colors=False)
+    assert np.array_equal(out["shape_mask"][0].cpu().numpy(), refpath.shape_mask(tall))
+    # taller than the cluster kernel's per-warp row window: takes the strip kernels
+    taller = noise_image(4000, 72, 10)
+    out = eng.pipeline(dev(taller[None]), colors=False)
+    assert np.array_equal(out["shape_mask"][0].cpu().numpy(), refpath.shape_mask(taller))
+    assert np.array_equal(out["shadow_mask"][0].cpu().numpy(), refpath.shadow_mask(taller)[1])
+
+
+def test_4k_palette_k16(eng):
+    """Config 3's palette: k = 16 on a 4K image, injected noise, against cv2.kmeans on the same unique colours."""
+    import cv2
+
+    img = design_image(2160, 3840, 11)
+    noise = cvops.make_noise((2160 * 3840, 3), 77).reshape(2160, 3840, 3)
+    keys, count = eng.unique_colors(dev(img), dev(noise), max_unique=1 << 17)
+    px = cvops.apply_noise(cvops.bgr2rgb(img).reshape(-1, 3), noise.reshape(-1, 3))
+    u = cvops.unique_colors(px)
+    c = int(count)
+    k = keys[:c].cpu().numpy().astype(np.uint32)
+    assert c == len(u) and np.array_equal(np.stack([(k >> 16) & 255, (k >> 8) & 255, k & 255], 1).astype(np.uint8), u)
+    centers, labels, comp, kused = eng.kmeans_unique(keys, count, 16, 4242)
+    cv2.setRNGSeed(4242)
+    comp_cv, lab_cv, cen_cv = cv2.kmeans(np.float32(u), 16, None, (cv2.TERM_CRITERIA_EPS + cv2.TERM_CRITERIA_MAX_ITER, 200, 0.2),
+                                          10, cv2.KMEANS_PP_CENTERS)
+    assert np.array_equal(centers[0].cpu().numpy(), cen_cv)
+    assert np.array_equal(labels[0, :c].cpu().numpy(), lab_cv.reshape(-1))
+    assert abs(float(comp[0]) - comp_cv) <= 1e-9 * max(1.0, comp_cv)
+
+
 def test_unfused_path_still_matches(eng):
     """LLFE_UNFUSED=1 forces the per-stage kernels (the path odd widths take)."""
     img = design_image(96, 160, 1)
