@@ -469,186 +469,3 @@ extern "C" int llfe_kmeans_lloyd(llfe_ctx* ctx, const uint32_t* d_keys, const ui
     return LLFE_OK;
 }
 
-// ======================================================================================
-// Per-pixel k-means building blocks for a row shard of ONE image (multi-GPU mode):
-// every rank runs `step` on its rows, the K x 4 uint64 accumulator is all-reduced
-// (ncclSum), then every rank runs the identical `update`.
-// ======================================================================================
-namespace {
-
-constexpr int PT = 256;
-
-// nearest centre for every pixel + exact per-cluster sums.  The reduction is
-// contention-free: per cluster, a warp ballot + REDUX over the member lanes.
-__global__ void __launch_bounds__(PT) k_pixels_step(const uint8_t* __restrict__ bgr, size_t npix, int K,
-                                                    const float* __restrict__ centers, unsigned long long* sums,
-                                                    uint8_t* __restrict__ labels_out) {
-    __shared__ float s_c[KMAX][3];
-    __shared__ uint32_t s_acc[PT / 32][KMAX][4];
-    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    for (int i = tid; i < K * 3; i += PT) (&s_c[0][0])[i] = centers[i];
-    for (int i = tid; i < (PT / 32) * KMAX * 4; i += PT) (&s_acc[0][0][0])[i] = 0u;
-    __syncthreads();
-    const size_t stride = (size_t)gridDim.x * PT;
-    const size_t base0 = blockIdx.x * (size_t)PT;
-    // all lanes iterate together so the warp collectives stay converged
-    for (size_t base = base0; base < npix; base += stride) {
-        size_t p = base + tid;
-        bool ok = p < npix;
-        uint32_t b = 0, g = 0, r = 0;
-        if (ok) {
-            b = bgr[3 * p];
-            g = bgr[3 * p + 1];
-            r = bgr[3 * p + 2];
-        }
-        float fr = (float)r, fg = (float)g, fb = (float)b;
-        float bd = fdist(fr, fg, fb, s_c[0]);
-        int bl = 0;
-        for (int k = 1; k < K; ++k) {
-            float d = fdist(fr, fg, fb, s_c[k]);
-            if (d < bd) {
-                bd = d;
-                bl = k;
-            }
-        }
-        if (!ok) bl = -1;
-        if (labels_out && ok) labels_out[p] = (uint8_t)bl;
-        for (int k = 0; k < K; ++k) {
-            uint32_t m = __ballot_sync(0xffffffffu, bl == k);
-            if (m == 0) continue;
-            bool in = bl == k;
-            uint32_t sr = __reduce_add_sync(0xffffffffu, in ? r : 0u);
-            uint32_t sg = __reduce_add_sync(0xffffffffu, in ? g : 0u);
-            uint32_t sb = __reduce_add_sync(0xffffffffu, in ? b : 0u);
-            if (lane == 0) {
-                s_acc[warp][k][0] += sr;
-                s_acc[warp][k][1] += sg;
-                s_acc[warp][k][2] += sb;
-                s_acc[warp][k][3] += __popc(m);
-            }
-        }
-    }
-    __syncthreads();
-    for (int i = tid; i < K * 4; i += PT) {
-        unsigned long long t = 0;
-        for (int w = 0; w < PT / 32; ++w) t += s_acc[w][i >> 2][i & 3];
-        if (t) atomicAdd(&sums[i], t);
-    }
-}
-
-struct SkipList {
-    int n;
-    uint32_t idx[KMAX];
-};
-
-// farthest member (f32 distance to `base`) of cluster `donor` under the assignment to
-// `centers`; result = max over pixels of (dist bits << 32 | (pixel index + index_base)) + 1
-__global__ void __launch_bounds__(PT) k_pixels_farthest(const uint8_t* __restrict__ bgr, size_t npix, int K,
-                                                        const float* __restrict__ centers, int donor, float b0,
-                                                        float b1, float b2, uint32_t index_base, SkipList skip,
-                                                        unsigned long long* out) {
-    __shared__ float s_c[KMAX][3];
-    const int tid = threadIdx.x;
-    for (int i = tid; i < K * 3; i += PT) (&s_c[0][0])[i] = centers[i];
-    __syncthreads();
-    const float base[3] = {b0, b1, b2};
-    unsigned long long best = 0ull;
-    const size_t stride = (size_t)gridDim.x * PT;
-    for (size_t p = blockIdx.x * (size_t)PT + tid; p < npix; p += stride) {
-        float fb = (float)bgr[3 * p], fg = (float)bgr[3 * p + 1], fr = (float)bgr[3 * p + 2];
-        float bd = fdist(fr, fg, fb, s_c[0]);
-        int bl = 0;
-        for (int k = 1; k < K; ++k) {
-            float d = fdist(fr, fg, fb, s_c[k]);
-            if (d < bd) bd = d, bl = k;
-        }
-        if (bl != donor) continue;
-        bool skipped = false;  // pixels an earlier repair of this update already moved out of the donor
-        for (int j = 0; j < skip.n; ++j) skipped |= skip.idx[j] == (uint32_t)(p + index_base);
-        if (skipped) continue;
-        float d = fdist(fr, fg, fb, base);
-        unsigned long long cand = (((unsigned long long)__float_as_uint(d) << 32) | (uint32_t)(p + index_base)) + 1ull;
-        best = cand > best ? cand : best;
-    }
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) {
-        unsigned long long n = __shfl_xor_sync(0xffffffffu, best, o);
-        best = n > best ? n : best;
-    }
-    if ((tid & 31) == 0 && best) atomicMax(out, best);
-}
-
-// centres from (all-reduced) sums; shift; iteration bookkeeping (state: iter, done, n_empty)
-__global__ void k_pixels_update(int K, const unsigned long long* __restrict__ sums, float* centers, int max_iter,
-                                double eps2, int32_t* state, double* shift_out) {
-    if (threadIdx.x != 0 || blockIdx.x != 0) return;
-    int n_empty = 0;
-    for (int k = 0; k < K; ++k) n_empty += sums[4 * k + 3] == 0;
-    state[2] = n_empty;
-    if (n_empty) return;  // the host runs the repair and calls update again
-    double shift = 0.0;
-    for (int k = 0; k < K; ++k) {
-        double s = 0.0;
-        for (int j = 0; j < 3; ++j) {
-            float c = (float)((double)sums[4 * k + j] / (double)sums[4 * k + 3]);
-            double t = (double)__fsub_rn(c, centers[3 * k + j]);
-            s = __dadd_rn(s, __dmul_rn(t, t));
-            centers[3 * k + j] = c;
-        }
-        shift = fmax(shift, s);
-    }
-    const int it0 = state[0];
-    const int it = it0 + 1;
-    state[0] = it;
-    const int last_it = max_iter > 2 ? max_iter : 2;
-    state[1] = (it == last_it) || (it0 > 0 && shift <= eps2);
-    if (shift_out) *shift_out = shift;
-}
-
-}  // namespace
-
-extern "C" int llfe_kmeans_pixels_step(llfe_ctx* ctx, const uint8_t* d_bgr, size_t n_pixels, int k,
-                                       const float* d_centers, uint64_t* d_sums_counts, uint8_t* d_labels_or_null) {
-    LLFE_CHECK_ARG(ctx != nullptr && d_bgr != nullptr && d_centers != nullptr && d_sums_counts != nullptr);
-    LLFE_CHECK_ARG(k >= 1 && k <= KMAX);
-    if (n_pixels == 0) return LLFE_OK;
-    size_t want = ceil_div_sz(n_pixels, PT * 8);
-    size_t cap = (size_t)ctx->sm_count * 8;
-    unsigned grid = (unsigned)(want < 1 ? 1 : (want > cap ? cap : want));
-    LLFE_KERNEL(ctx, "k_pixels_step");
-    k_pixels_step<<<grid, PT, 0, ctx->stream>>>(d_bgr, n_pixels, k, d_centers, (unsigned long long*)d_sums_counts,
-                                                d_labels_or_null);
-    LLFE_LAUNCHED(ctx);
-    return LLFE_OK;
-}
-
-extern "C" int llfe_kmeans_pixels_farthest(llfe_ctx* ctx, const uint8_t* d_bgr, size_t n_pixels, int k,
-                                           const float* d_centers, int donor, const float* h_base3,
-                                           uint32_t index_base, const uint32_t* h_skip, int n_skip, uint64_t* d_out) {
-    LLFE_CHECK_ARG(ctx != nullptr && d_bgr != nullptr && d_centers != nullptr && h_base3 != nullptr && d_out != nullptr);
-    LLFE_CHECK_ARG(n_skip >= 0 && n_skip <= KMAX && (n_skip == 0 || h_skip != nullptr));
-    SkipList skip;
-    skip.n = n_skip;
-    for (int j = 0; j < n_skip; ++j) skip.idx[j] = h_skip[j];
-    LLFE_CHECK_ARG(k >= 1 && k <= KMAX && donor >= 0 && donor < k && n_pixels + index_base <= 0xffffffffull);
-    if (n_pixels == 0) return LLFE_OK;
-    size_t want = ceil_div_sz(n_pixels, PT * 8);
-    size_t cap = (size_t)ctx->sm_count * 8;
-    unsigned grid = (unsigned)(want < 1 ? 1 : (want > cap ? cap : want));
-    LLFE_KERNEL(ctx, "k_pixels_farthest");
-    k_pixels_farthest<<<grid, PT, 0, ctx->stream>>>(d_bgr, n_pixels, k, d_centers, donor, h_base3[0], h_base3[1],
-                                                    h_base3[2], index_base, skip, (unsigned long long*)d_out);
-    LLFE_LAUNCHED(ctx);
-    return LLFE_OK;
-}
-
-extern "C" int llfe_kmeans_update(llfe_ctx* ctx, int k, const uint64_t* d_sums_counts, float* d_centers, int max_iter,
-                                  double eps, int32_t* d_state, double* d_shift) {
-    LLFE_CHECK_ARG(ctx != nullptr && d_sums_counts != nullptr && d_centers != nullptr && d_state != nullptr);
-    LLFE_CHECK_ARG(k >= 1 && k <= KMAX && max_iter >= 1);
-    LLFE_KERNEL(ctx, "k_pixels_update");
-    k_pixels_update<<<1, 32, 0, ctx->stream>>>(k, (const unsigned long long*)d_sums_counts, d_centers, max_iter, eps * eps,
-                                               d_state, d_shift);
-    LLFE_LAUNCHED(ctx);
-    return LLFE_OK;
-}
