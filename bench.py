@@ -190,7 +190,7 @@ class ClockSampler:
 NCU_TRAFFIC = {}
 try:
     with open(os.path.join(ROOT, "profiles", "ncu_traffic.json")) as _f:
-        NCU_TRAFFIC = {k: v["bytes_per_launch"] for k, v in json.load(_f).items()}
+        NCU_TRAFFIC = json.load(_f)
 except Exception:
     pass
 
@@ -302,6 +302,14 @@ def run_ours(args):
         peak, peak_src = measured_peak()
         u_avg = float(out["count"].float().mean().item()) if "count" in out else 0.0
 
+        def ncu_traffic(name, imgs_per_launch):
+            """dram bytes per launch from the committed ncu capture, scaled to this run's images per launch."""
+            rec = NCU_TRAFFIC.get(name)
+            if not rec:
+                return None
+            scale = imgs_per_launch / rec["images_per_launch"] if rec.get("images_per_launch") else 1.0
+            return rec["bytes_per_launch"] * scale
+
         def kernel_bytes(name):
             return KERNEL_BYTES.get(name, lambda P, U, A: 0)(P, u_avg, cfg.attempts)
 
@@ -316,7 +324,7 @@ def run_ours(args):
             algo = kernel_bytes(name) * imgs_per_launch
             ach = algo / (per_launch_ms / 1e3) / 1e9
             roofline = {"bound": "hbm", "kernel": name, "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak,
-                        "traffic": NCU_TRAFFIC.get(name), "peak_source": peak_src, "algorithmic_bytes_per_launch": algo,
+                        "traffic": ncu_traffic(name, imgs_per_launch), "peak_source": peak_src, "algorithmic_bytes_per_launch": algo,
                         "avg_launch_ms": per_launch_ms, "share_of_step": rec["ms"] / total_kernel_ms,
                         "images_per_launch": imgs_per_launch}
         step_bytes = WORKLOAD_BYTES[args.workload](P) * B

@@ -35,7 +35,12 @@ UNIT_MS = {"ns": 1e-6, "us": 1e-3, "ms": 1.0, "s": 1e3, "usecond": 1e-3, "msecon
 
 def short(name: str) -> str:
     m = re.search(r"(k_[A-Za-z0-9_]+)", name)
-    return m.group(1) if m else name[:40]
+    if not m:
+        return name[:40]
+    n = m.group(1)
+    if n == "k_kmeans_fast" and re.search(r"k_kmeans_fast<\d+, (0|false|\(bool\)0)>", name):
+        n += "_global"   # second instantiation: lists that do not fit in shared memory
+    return n
 
 
 def raw_page(rep):
@@ -138,6 +143,8 @@ def main():
     ap.add_argument("--out")
     ap.add_argument("--traffic", help="JSON file to update with dram bytes per launch per kernel")
     ap.add_argument("--title", default=None)
+    ap.add_argument("--images", type=int, default=None, help="images per launch in the captured run (stored with the traffic)")
+    ap.add_argument("--fresh", action="store_true", help="rewrite the traffic file instead of merging into it")
     a = ap.parse_args()
     raws = raw_page(a.rep)
     pages = source_pages(a.rep)
@@ -180,12 +187,12 @@ def main():
         print(text)
     if a.traffic:
         old = {}
-        if os.path.exists(a.traffic):
+        if os.path.exists(a.traffic) and not a.fresh:
             with open(a.traffic) as f:
                 old = json.load(f)
         for k, v in traffic.items():
             old[k] = {"bytes_per_launch": v["bytes_per_launch"], "ncu_ms_per_launch": v["ms"], "launches_averaged": v["n"],
-                      "report": os.path.basename(a.rep)}
+                      "report": os.path.basename(a.rep), "images_per_launch": a.images}
         with open(a.traffic, "w") as f:
             json.dump(old, f, indent=1, sort_keys=True)
 
