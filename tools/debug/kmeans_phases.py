@@ -1,4 +1,5 @@
-import os, sys; sys.path.insert(0,'.')
+import os, sys, time
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__)))))
 import numpy as np, torch
 import low_level_feature_extraction_b200 as pkg
 from low_level_feature_extraction_b200.synth import design_image
