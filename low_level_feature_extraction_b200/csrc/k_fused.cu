@@ -25,7 +25,7 @@ constexpr unsigned FULL = 0xffffffffu;
 constexpr int WARPS = 4;
 constexpr int OUT_PER_WARP = 240;            // 30 output lanes x 8 px
 constexpr int BAND_W = WARPS * OUT_PER_WARP;  // 960
-constexpr int RING = 11;
+constexpr int RING = 10;   // rows vb-10 .. vb-1 of the 11-row window; the newest row is still in registers
 
 // float32(cv2.getGaussianKernel(11, 0)), see k_threshold.cu
 #define GK0 0x1.20c256p-7f
@@ -276,8 +276,9 @@ __device__ __forceinline__ void nms_px(const Q4& m0, uint32_t e0, const Q4& m1, 
 __device__ __forceinline__ float u2f(uint32_t v) { return __uint_as_float(0x4b000000u | v) - 8388608.0f; }
 
 template <bool EDGES, bool SHADOW, bool COLORS>
-__global__ void __launch_bounds__(WARPS * 32) k_fused(FusedArgs A) {
-    // dynamic shared memory: [128 lanes][24 B] colour scratch, then SHADOW: [warp][RING][3][32] float4
+__global__ void __launch_bounds__(WARPS * 32, 4) k_fused(FusedArgs A) {
+    // dynamic shared memory: [128 lanes][24 B] colour scratch, then SHADOW per warp: [RING][2][32] float4 (row-pass
+    // results) + [RING][32] uint2 (the blurred pixels as bytes) = 1280 B per row: 4 CTAs per SM
     extern __shared__ float4 dyn_smem[];
     uint8_t* my24 = reinterpret_cast<uint8_t*>(dyn_smem) + threadIdx.x * 24;
     float4* ring_all = dyn_smem + (WARPS * 32 * 24) / 16;
@@ -293,7 +294,8 @@ __global__ void __launch_bounds__(WARPS * 32) k_fused(FusedArgs A) {
     const bool left_edge = xs < 0;              // warp-uniform: lane 0 is outside the image
     const bool right_edge = xs + 256 > W;       // warp-uniform: some lanes are outside the image
     const int wpr = (W + 31) >> 5;
-    float4* ring = SHADOW ? ring_all + (size_t)warp * RING * 3 * 32 : nullptr;
+    float4* ring = SHADOW ? ring_all + (size_t)warp * (RING * 2 * 32 + RING * 16) : nullptr;
+    uint2* ring_px = SHADOW ? reinterpret_cast<uint2*>(ring + RING * 2 * 32) : nullptr;
 
     const int vb_lo = y0 - (SHADOW ? 5 : 2);
     const int vb_hi = y1 - 1 + (SHADOW ? 5 : 2);
@@ -443,22 +445,18 @@ __global__ void __launch_bounds__(WARPS * 32) k_fused(FusedArgs A) {
                 acc = __fmaf_rn(f[j + 10], GK0, acc);
                 r[j] = acc;
             }
-            // ring slot of row vb: a running counter (no modulo in the loop)
+            // ring slot of row vb: a running counter (no modulo in the loop).  The slot still holds row vb - 10
+            // (the oldest row of this step's window); it is overwritten after the column pass.
             ring_slot = ring_slot + 1 == RING ? 0 : ring_slot + 1;
             const int slot = ring_slot;
-            float4* rs = ring + (size_t)slot * 3 * 32 + lane;
-            rs[0] = make_float4(r[0], r[1], r[2], r[3]);
-            rs[32] = make_float4(r[4], r[5], r[6], r[7]);
-            rs[64] = make_float4(__uint_as_float(blurred.p0), __uint_as_float(blurred.p1), __uint_as_float(blurred.p2),
-                                 __uint_as_float(blurred.p3));
             const int va = vb - 5;
             if (vb >= vb_lo + 10 && va >= y0 && va < y1 && out_lane) {
                 float v[8];
-                // row va + d sits (5 - d) slots behind the newest row (slot of vb = va + 5)
+                // row va + d (d = -5 .. 4) sits at slot + 5 + d (mod RING); row va + 5 = vb is r[] itself
                 auto row_at = [&](int d, float* o) {
-                    int s = slot - (5 - d);
-                    if (s < 0) s += RING;
-                    const float4* p = ring + (size_t)s * 3 * 32 + lane;
+                    int s = slot + 5 + d;
+                    if (s >= RING) s -= RING;
+                    const float4* p = ring + (size_t)s * 2 * 32 + lane;
                     const float4 a = p[0], b = p[32];
                     o[0] = a.x; o[1] = a.y; o[2] = a.z; o[3] = a.w; o[4] = b.x; o[5] = b.y; o[6] = b.z; o[7] = b.w;
                 };
@@ -470,21 +468,25 @@ __global__ void __launch_bounds__(WARPS * 32) k_fused(FusedArgs A) {
 #pragma unroll
                 for (int i = 1; i <= 5; ++i) {
                     float up[8], dn[8];
-                    row_at(i, dn);
+                    if (i < 5) {
+                        row_at(i, dn);
+                    } else {
+#pragma unroll
+                        for (int j = 0; j < 8; ++j) dn[j] = r[j];
+                    }
                     row_at(-i, up);
 #pragma unroll
                     for (int j = 0; j < 8; ++j) v[j] = __fmaf_rn(__fadd_rn(dn[j], up[j]), kk[i - 1], v[j]);
                 }
-                int sc = slot - 5;
-                if (sc < 0) sc += RING;
-                const float4 cb = ring[(size_t)sc * 3 * 32 + 64 + lane];
-                const uint32_t cp[4] = {__float_as_uint(cb.x), __float_as_uint(cb.y), __float_as_uint(cb.z), __float_as_uint(cb.w)};
+                int sc = slot + 5;
+                if (sc >= RING) sc -= RING;
+                const uint2 cb = ring_px[(size_t)sc * 32 + lane];   // 8 blurred pixels of row va, one byte each
                 uint32_t out_lo = 0, out_hi = 0;
 #pragma unroll
                 for (int j = 0; j < 8; ++j) {
                     // rint (half to even) via the 1.5*2^23 trick; v is in [0, 255.x]
                     const int mean = min(max((int)(__float_as_uint(__fadd_rn(v[j], 12582912.0f)) & 0x7fffffu) - 0x400000, 0), 255);
-                    const int pxv = (int)((j & 1) ? hi16(cp[j >> 1]) : lo16(cp[j >> 1]));
+                    const int pxv = (int)(((j < 4 ? cb.x : cb.y) >> (8 * (j & 3))) & 0xffu);
                     const bool on = (pxv - mean) <= -2;
                     if (on) {
                         lsum += pxv;
@@ -495,6 +497,12 @@ __global__ void __launch_bounds__(WARPS * 32) k_fused(FusedArgs A) {
                 }
                 *reinterpret_cast<uint2*>(A.mask + ((size_t)img * H + va) * W + x) = make_uint2(out_lo, out_hi);
             }
+            // now row vb replaces row vb - 10
+            float4* rs = ring + (size_t)slot * 2 * 32 + lane;
+            rs[0] = make_float4(r[0], r[1], r[2], r[3]);
+            rs[32] = make_float4(r[4], r[5], r[6], r[7]);
+            ring_px[(size_t)slot * 32 + lane] = make_uint2(__byte_perm(blurred.p0, blurred.p1, 0x6420),
+                                                           __byte_perm(blurred.p2, blurred.p3, 0x6420));
         }
     }
     if (COLORS && have_pend) color_commit(A, img, pend);
@@ -555,7 +563,7 @@ int launch_fused(llfe_ctx* ctx, const uint8_t* bgr, int n, int h, int w, int low
     while (bands > 1 && h / bands < 48) bands >>= 1;
     A.rows_per_band = ceil_div(h, bands);
     dim3 grid(ceil_div(w, BAND_W), ceil_div(h, A.rows_per_band), n);
-    const size_t smem = (size_t)WARPS * 32 * 24 + (S ? (size_t)WARPS * RING * 3 * 32 * sizeof(float4) : 0);
+    const size_t smem = (size_t)WARPS * 32 * 24 + (S ? (size_t)WARPS * (RING * 2 * 32 + RING * 16) * sizeof(float4) : 0);
     if (S && sum_count) LLFE_CUDA(cudaMemsetAsync(sum_count, 0, (size_t)n * 2 * sizeof(uint64_t), ctx->stream));
     if (E && (w % 32)) {  // the kernel writes whole bytes of in-image pixels only: clear the padding bits
         const size_t pb = (size_t)n * h * plane_wpr(w) * sizeof(uint32_t);
