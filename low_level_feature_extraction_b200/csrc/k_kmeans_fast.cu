@@ -1,10 +1,12 @@
 // Fast path of cv2.kmeans over UNWEIGHTED colour lists (the reference's palette call,
 // color_extractor.py:189-196): same arithmetic and results as k_kmeans (k_kmeans.cu), laid
 // out for the SM:
-//   * one CTA per (attempt, image); the colour list lives in SHARED MEMORY for the whole
-//     solve (key | label<<24 per point, plus one aux word per point), so no iteration touches
-//     HBM or L2; lists too long for shared memory run the same code on a global scratch copy
-//     (second instantiation, IN_SMEM = false);
+//   * one CTA per (attempt, image), TWO CTAs (32 warps) per SM: the kernel is held to 64 registers
+//     and keeps ONE 32-bit state word per colour in shared memory for the whole solve (the kmeans++
+//     distance during the seeding; label | upper bound | lower bound during Lloyd).  The colour keys
+//     themselves are re-read from the (L2-resident, read-only) sorted key list when a pass needs
+//     them, so no iteration touches HBM.  Lists too long for shared memory run the same code on
+//     a global scratch copy (second instantiation, IN_SMEM = false);
 //   * warp-blocked point ownership (warp w owns a contiguous block, lanes stride it): bank-
 //     conflict-free and contiguous for the kmeans++ prefix search;
 //   * kmeans++ (cv::generateCentersPP): integer squared distances in two instructions
@@ -38,12 +40,28 @@ __device__ __forceinline__ float fdist4(float r, float g, float b, float4 c) {
     return d;
 }
 
-// fixed-point (1/64) bounds: q_up rounds up, q_dn down, each with one extra unit of slack
-__device__ __forceinline__ uint32_t q_up(float d) { return min(65535u, (uint32_t)(d * 64.f) + 2u); }
-__device__ __forceinline__ uint32_t q_dn(float d) {
-    const float v = fminf(d * 64.f, 65535.f);
-    return v >= 2.f ? (uint32_t)v - 1u : 0u;
-}
+// State word of a point during Lloyd: label | ub | lb.  K <= 16: 4 + 14 + 14 bits, bounds in 1/32 colour
+// units (the largest RGB distance, 441.7, is 14134 units); K <= 32: 5 + 13 + 14 bits in 1/16 units.
+// q_up rounds up, q_dn down, each with one extra unit of slack.
+template <int KC>
+struct Fmt {
+    static constexpr int LB = KC <= 16 ? 4 : 5;            // label bits
+    static constexpr int UB = KC <= 16 ? 14 : 13;          // upper-bound bits
+    static constexpr uint32_t UMAX = (1u << UB) - 1u;      // "unknown": never passes a bound test
+    static constexpr uint32_t LMAX = (1u << 14) - 1u;
+    static constexpr float SCALE = KC <= 16 ? 32.f : 16.f;
+    __device__ static __forceinline__ uint32_t q_up(float d) { return min(UMAX, (uint32_t)(d * SCALE) + 2u); }
+    __device__ static __forceinline__ uint32_t q_dn(float d) {
+        const float v = fminf(d * SCALE, (float)LMAX);
+        return v >= 2.f ? (uint32_t)v - 1u : 0u;
+    }
+    __device__ static __forceinline__ uint32_t pack(uint32_t a, uint32_t ub, uint32_t lb) {
+        return (a << (32 - LB)) | (ub << 14) | lb;
+    }
+    __device__ static __forceinline__ uint32_t label(uint32_t x) { return x >> (32 - LB); }
+    __device__ static __forceinline__ uint32_t ub(uint32_t x) { return (x >> 14) & UMAX; }
+    __device__ static __forceinline__ uint32_t lb(uint32_t x) { return x & LMAX; }
+};
 
 // bytes 2/1/0 of the key as exact floats without the conversion pipe: 2^23 + byte, minus 2^23
 __device__ __forceinline__ void unpackf(uint32_t key, float& r, float& g, float& b) {
@@ -59,7 +77,8 @@ __device__ __forceinline__ uint32_t idist2(uint32_t a, uint32_t b) {
 }
 
 template <int KC, bool IN_SMEM>
-__global__ void __launch_bounds__(FT, 1) k_kmeans_fast(KmParams P, int smem_points, int img_base) {
+__global__ void __launch_bounds__(FT, 2) k_kmeans_fast(KmParams P, int smem_points, int img_base) {
+    typedef Fmt<KC> F;
     extern __shared__ uint32_t dyn[];
     const int att = blockIdx.x, img = blockIdx.y + img_base, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int U = min(P.count[img], P.max_unique);
@@ -74,11 +93,11 @@ __global__ void __launch_bounds__(FT, 1) k_kmeans_fast(KmParams P, int smem_poin
         }
         return;
     }
-    const uint32_t* keys = P.keys + (size_t)img * P.max_unique;
-    // point storage: shared memory when the list fits, else this slot's global scratch
+    const uint32_t* __restrict__ keys = P.keys + (size_t)img * P.max_unique;
+    // per-point state word: shared memory when the list fits, else this slot's global scratch
     // (the global scratch is sized for one launch of `dist_images` images: index it by blockIdx.y)
-    uint32_t* const pts = IN_SMEM ? dyn : P.dist + ((size_t)blockIdx.y * P.attempts + att) * 2 * (size_t)P.max_unique;
-    uint32_t* const aux = IN_SMEM ? dyn + smem_points : pts + P.max_unique;
+    uint32_t* const aux = IN_SMEM ? dyn : P.dist + ((size_t)blockIdx.y * P.attempts + att) * 2 * (size_t)P.max_unique;
+    auto key_at = [&](int i) -> uint32_t { return __ldg(keys + i) & 0xffffffu; };
     // warp-blocked ownership: rows of 32 consecutive points, `rows` rows per warp
     const int rows = (U + 32 * FW - 1) / (32 * FW);
     const int wbase = warp * rows * 32;
@@ -88,7 +107,7 @@ __global__ void __launch_bounds__(FT, 1) k_kmeans_fast(KmParams P, int smem_poin
     __shared__ float4 s_asg[KMAX];          // the centres the current labels were assigned with
     __shared__ int s_sum[KMAX][4];          // exact per-cluster {sum R, sum G, sum B, count}
     __shared__ uint32_t s_dq[KMAX], s_hq[KMAX], s_m[4];
-    __shared__ uint16_t s_queue[FW][QROWS * 32];  // per-warp queue of points whose bounds failed
+    __shared__ uint8_t s_queue[FW][QROWS * 32];   // per-warp queue of points whose bounds failed
     __shared__ uint32_t s_rowsum[IN_SMEM ? FW : 1][IN_SMEM ? RMAX : 1];
     __shared__ unsigned long long s_wtot[FW];
     __shared__ unsigned long long s_red3[FW][3];
@@ -103,10 +122,6 @@ __global__ void __launch_bounds__(FT, 1) k_kmeans_fast(KmParams P, int smem_poin
     long long t_first = 0;
     if (tid == 0) s_flag = 0;
     if (tid < 4) s_cnt[tid] = 0;
-    for (int r = 0; r < rows; ++r) {
-        int i = wbase + r * 32 + lane;
-        if (i < U) pts[i] = keys[i] & 0xffffffu;
-    }
     __syncthreads();
     const long long t_loaded = clock64();
 
@@ -138,22 +153,30 @@ __global__ void __launch_bounds__(FT, 1) k_kmeans_fast(KmParams P, int smem_poin
         // dist[i] = min(dist[i], |x_i - x_c|^2) (aux), with per-row and per-warp totals for the prefix search
         auto update_pass = [&](uint32_t ckey, bool first_centre) {
             unsigned long long wt = 0;
-            for (int r = 0; r < rows; ++r) {
-                const int i = wbase + r * 32 + lane;
-                uint32_t d = 0u;
-                if (i < U) {
-                    d = idist2(pts[i], ckey);
-                    if (!first_centre) d = min(d, aux[i]);
-                    aux[i] = d;
+            for (int r0 = 0; r0 < rows; r0 += 4) {   // four rows per step: the key loads (L2) are all in flight first
+                uint32_t kv[4], dv[4];
+#pragma unroll
+                for (int u = 0; u < 4; ++u) {
+                    const int i = wbase + (r0 + u) * 32 + lane;
+                    const bool ok = r0 + u < rows && i < U;
+                    kv[u] = ok ? key_at(i) : ckey;               // distance 0 for the padding
+                    dv[u] = (ok && !first_centre) ? aux[i] : (ok ? 0xffffffffu : 0u);
                 }
-                const uint32_t rs32 = __reduce_add_sync(FULL, d);
-                if (IN_SMEM && lane == 0) s_rowsum[IN_SMEM ? warp : 0][IN_SMEM ? r : 0] = rs32;
-                wt += rs32;
+#pragma unroll
+                for (int u = 0; u < 4; ++u) {
+                    if (r0 + u >= rows) break;   // warp-uniform
+                    const int i = wbase + (r0 + u) * 32 + lane;
+                    const uint32_t d = min(idist2(kv[u], ckey), dv[u]);
+                    if (i < U) aux[i] = d;
+                    const uint32_t rs32 = __reduce_add_sync(FULL, d);
+                    if (IN_SMEM && lane == 0) s_rowsum[IN_SMEM ? warp : 0][IN_SMEM ? r0 + u : 0] = rs32;
+                    wt += rs32;
+                }
             }
             if (lane == 0) s_wtot[warp] = wt;
         };
         {
-            const uint32_t ckey = pts[s_ci[0]];
+            const uint32_t ckey = key_at(s_ci[0]);
             if (tid == 0) {
                 float r, g, b;
                 unpackf(ckey, r, g, b);
@@ -231,18 +254,25 @@ __global__ void __launch_bounds__(FT, 1) k_kmeans_fast(KmParams P, int smem_poin
             __syncthreads();
             // one pass evaluates the three trials: s_t = sum_i min(|x_i - x_ci(t)|^2, dist[i])
             const int c0 = s_ci[0], c1 = s_ci[1], c2 = s_ci[2];
-            const uint32_t t0 = pts[c0], t1 = pts[c1], t2 = pts[c2];
+            const uint32_t t0 = key_at(c0), t1 = key_at(c1), t2 = key_at(c2);
             unsigned long long a0 = 0, a1 = 0, a2 = 0;
             for (int rb = 0; rb < rows; rb += 64) {   // 64 rows * 195075 < 2^32: 32-bit partial sums
                 const int re = min(rows, rb + 64);
                 uint32_t p0 = 0, p1 = 0, p2 = 0;
-                for (int r = rb; r < re; ++r) {
-                    const int i = wbase + r * 32 + lane;
-                    if (i < U) {
-                        const uint32_t x = pts[i], d = aux[i];
-                        p0 += min(idist2(x, t0), d);
-                        p1 += min(idist2(x, t1), d);
-                        p2 += min(idist2(x, t2), d);
+                for (int r0 = rb; r0 < re; r0 += 4) {   // four rows per step: loads first
+                    uint32_t kv[4], dv[4];
+#pragma unroll
+                    for (int u = 0; u < 4; ++u) {
+                        const int i = wbase + (r0 + u) * 32 + lane;
+                        const bool ok = r0 + u < re && i < U;
+                        kv[u] = ok ? key_at(i) : 0u;
+                        dv[u] = ok ? aux[i] : 0u;   // min(., 0) = 0 for the padding
+                    }
+#pragma unroll
+                    for (int u = 0; u < 4; ++u) {
+                        p0 += min(idist2(kv[u], t0), dv[u]);
+                        p1 += min(idist2(kv[u], t1), dv[u]);
+                        p2 += min(idist2(kv[u], t2), dv[u]);
                     }
                 }
                 a0 += p0;
@@ -269,7 +299,7 @@ __global__ void __launch_bounds__(FT, 1) k_kmeans_fast(KmParams P, int smem_poin
                     best_c = t == 0 ? c0 : t == 1 ? c1 : c2;
                 }
             }
-            const uint32_t bk = pts[best_c];
+            const uint32_t bk = key_at(best_c);
             if (tid == 0) {
                 float r, g, b;
                 unpackf(bk, r, g, b);
@@ -310,7 +340,7 @@ __global__ void __launch_bounds__(FT, 1) k_kmeans_fast(KmParams P, int smem_poin
                 for (int r = r0; r < r1; ++r) {
                     int i = (r * FW + warp) * 32 + lane;
                     if (i >= U) continue;
-                    uint32_t key = pts[i] & 0xffffffu;
+                    uint32_t key = key_at(i);
                     float fr, fg, fb;
                     unpackf(key, fr, fg, fb);
                     float bd = fdist4(fr, fg, fb, s_c[0]), sd = 3e38f;
@@ -328,8 +358,7 @@ __global__ void __launch_bounds__(FT, 1) k_kmeans_fast(KmParams P, int smem_poin
                             }
                         }
                     }
-                    pts[i] = key | ((uint32_t)bl << 24);
-                    aux[i] = (q_up(__fsqrt_rn(bd)) << 16) | q_dn(__fsqrt_rn(sd));
+                    aux[i] = F::pack((uint32_t)bl, F::q_up(__fsqrt_rn(bd)), F::q_dn(__fsqrt_rn(sd)));
                     const uint32_t plo = key & 0xffffu, pr = (key >> 16) | 0x10000u;
                     const uint32_t lo = ((plo & 0xff00u) << 8) | (plo & 0xffu);
 #pragma unroll
@@ -360,7 +389,7 @@ __global__ void __launch_bounds__(FT, 1) k_kmeans_fast(KmParams P, int smem_poin
         } else {
             __syncthreads();  // s_dq / s_hq / s_m of the last update are visible
             const uint32_t m1 = s_m[0], m2 = s_m[1], kmax = s_m[2];
-            uint16_t* q = s_queue[warp];
+            uint8_t* q = s_queue[warp];
             // Two phases per block of QROWS rows so that the expensive path runs on full warps: (A) every
             // lane tests the bounds of its points and the failing ones are compacted into the warp's
             // queue; (B) the queue is drained 32 points at a time.
@@ -371,17 +400,17 @@ __global__ void __launch_bounds__(FT, 1) k_kmeans_fast(KmParams P, int smem_poin
                     const int i = (r * FW + warp) * 32 + lane;
                     bool need = false;
                     if (i < U) {
-                        const uint32_t w = pts[i], x = aux[i];
-                        const uint32_t a = w >> 24;
-                        const uint32_t ub = min(65535u, (x >> 16) + s_dq[a]);
+                        const uint32_t x = aux[i];
+                        const uint32_t a = F::label(x);
+                        const uint32_t ub = min(F::UMAX, F::ub(x) + s_dq[a]);
                         const uint32_t dl = (a == kmax) ? m2 : m1;
-                        uint32_t lb = x & 0xffffu;
+                        uint32_t lb = F::lb(x);
                         lb = lb > dl ? lb - dl : 0u;
-                        aux[i] = (ub << 16) | lb;
+                        aux[i] = F::pack(a, ub, lb);
                         need = ub >= max(lb, s_hq[a]);
                     }
                     const uint32_t bal = __ballot_sync(FULL, need);
-                    if (need) q[qn + __popc(bal & ((1u << lane) - 1u))] = (uint16_t)((r - rb0) * 32 + lane);
+                    if (need) q[qn + __popc(bal & ((1u << lane) - 1u))] = (uint8_t)((r - rb0) * 32 + lane);
                     qn += __popc(bal);
                 }
                 if (P.dbg && lane == 0) atomicAdd(&s_cnt[0], (unsigned)qn);
@@ -389,15 +418,15 @@ __global__ void __launch_bounds__(FT, 1) k_kmeans_fast(KmParams P, int smem_poin
                 for (int j = lane; j < qn; j += 32) {
                     const int qe = (int)q[j];
                     const int i = ((rb0 + (qe >> 5)) * FW + warp) * 32 + (qe & 31);
-                    const uint32_t w = pts[i], x = aux[i];
-                    const uint32_t a = w >> 24, lb = x & 0xffffu;
+                    const uint32_t x = aux[i];
+                    const uint32_t a = F::label(x), lb = F::lb(x);
                     const uint32_t bound = max(lb, s_hq[a]);
-                    const uint32_t key = w & 0xffffffu;
+                    const uint32_t key = key_at(i);
                     float fr, fg, fb;
                     unpackf(key, fr, fg, fb);
-                    const uint32_t ub = q_up(__fsqrt_rn(fdist4(fr, fg, fb, s_c[a])));  // tighten
+                    const uint32_t ub = F::q_up(__fsqrt_rn(fdist4(fr, fg, fb, s_c[a])));  // tighten
                     if (ub < bound) {
-                        aux[i] = (ub << 16) | lb;
+                        aux[i] = F::pack(a, ub, lb);
                         continue;
                     }
                     if (P.dbg) atomicAdd(&s_cnt[1], 1u);
@@ -416,10 +445,9 @@ __global__ void __launch_bounds__(FT, 1) k_kmeans_fast(KmParams P, int smem_poin
                             }
                         }
                     }
-                    aux[i] = (q_up(__fsqrt_rn(bd)) << 16) | q_dn(__fsqrt_rn(sd));
+                    aux[i] = F::pack((uint32_t)bl, F::q_up(__fsqrt_rn(bd)), F::q_dn(__fsqrt_rn(sd)));
                     if (P.dbg && (uint32_t)bl != a) atomicAdd(&s_cnt[2], 1u);
                     if ((uint32_t)bl != a) {
-                        pts[i] = key | ((uint32_t)bl << 24);
                         const int cr = (int)(key >> 16), cg = (int)((key >> 8) & 255u), cb = (int)(key & 255u);
                         atomicAdd(&s_sum[a][0], -cr);
                         atomicAdd(&s_sum[a][1], -cg);
@@ -450,10 +478,9 @@ __global__ void __launch_bounds__(FT, 1) k_kmeans_fast(KmParams P, int smem_poin
             for (int r = 0; r < rows; ++r) {
                 int i = (r * FW + warp) * 32 + lane;
                 if (i >= U) continue;
-                uint32_t w = pts[i];
-                if ((int)(w >> 24) != mk) continue;
+                if ((int)F::label(aux[i]) != mk) continue;
                 float fr, fg, fb;
-                unpackf(w, fr, fg, fb);
+                unpackf(key_at(i), fr, fg, fb);
                 float d = fdist4(fr, fg, fb, base);
                 unsigned long long cand = (((unsigned long long)__float_as_uint(d) << 32) | (uint32_t)i) + 1ull;
                 best = cand > best ? cand : best;
@@ -462,9 +489,8 @@ __global__ void __launch_bounds__(FT, 1) k_kmeans_fast(KmParams P, int smem_poin
             __syncthreads();
             if (tid == 0) {
                 int far = (int)(uint32_t)((s_far - 1ull) & 0xffffffffull);
-                uint32_t fk = pts[far] & 0xffffffu;
-                pts[far] = fk | ((uint32_t)k << 24);
-                aux[far] = 0xffff0000u;  // bounds unknown: ub = inf, lb = 0
+                uint32_t fk = key_at(far);
+                aux[far] = F::pack((uint32_t)k, F::UMAX, 0u);  // bounds unknown: ub = inf, lb = 0
                 s_c[mk] = base;  // OpenCV stores the donor's provisional mean in old_centers[max_k]
                 s_sum[mk][0] -= (int)(fk >> 16);
                 s_sum[mk][1] -= (int)((fk >> 8) & 255u);
@@ -505,7 +531,7 @@ __global__ void __launch_bounds__(FT, 1) k_kmeans_fast(KmParams P, int smem_poin
         if (tid < K) {
             const float4 c = s_c[tid], o = s_asg[tid];
             const float dx = c.x - o.x, dy = c.y - o.y, dz = c.z - o.z;
-            s_dq[tid] = q_up(sqrtf(dx * dx + dy * dy + dz * dz));
+            s_dq[tid] = F::q_up(sqrtf(dx * dx + dy * dy + dz * dz));
             float nn = 3e38f;
             for (int j = 0; j < K; ++j) {
                 if (j == tid) continue;
@@ -513,7 +539,7 @@ __global__ void __launch_bounds__(FT, 1) k_kmeans_fast(KmParams P, int smem_poin
                 const float ex = c.x - e.x, ey = c.y - e.y, ez = c.z - e.z;
                 nn = fminf(nn, ex * ex + ey * ey + ez * ez);
             }
-            s_hq[tid] = q_dn(0.5f * sqrtf(nn));
+            s_hq[tid] = F::q_dn(0.5f * sqrtf(nn));
         }
         __syncthreads();
         if (tid == 0) {
@@ -540,11 +566,11 @@ __global__ void __launch_bounds__(FT, 1) k_kmeans_fast(KmParams P, int smem_poin
     for (int r = 0; r < rows; ++r) {
         int i = (r * FW + warp) * 32 + lane;
         if (i >= U) continue;
-        uint32_t w = pts[i];
+        const uint32_t a = F::label(aux[i]);
         float fr, fg, fb;
-        unpackf(w, fr, fg, fb);
-        part += (double)fdist4(fr, fg, fb, s_c[w >> 24]);
-        labels[i] = (uint8_t)(w >> 24);
+        unpackf(key_at(i), fr, fg, fb);
+        part += (double)fdist4(fr, fg, fb, s_c[a]);
+        labels[i] = (uint8_t)a;
     }
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) part += __shfl_xor_sync(FULL, part, o);
@@ -608,17 +634,18 @@ int launch_kc(llfe_ctx* ctx, const KmParams& P, int n, int smem_points, size_t d
 
 }  // namespace
 
-// smem_points: how many points (8 bytes each) the dynamic shared memory of one CTA can hold
+// smem_points: how many points (4 bytes each) the dynamic shared memory of one CTA can hold with two CTAs per SM
 int launch_kmeans_fast(llfe_ctx* ctx, const KmParams& P0, int n) {
     KmParams P = P0;
     if (const char* dbg = getenv("LLFE_KMEANS_DEBUG")) P.dbg = (unsigned long long*)(uintptr_t)strtoull(dbg, nullptr, 10);
-    const size_t static_smem = 20 * 1024;  // centres, totals, queues, row totals, reduction scratch (upper bound)
-    size_t avail = ctx->smem_optin > static_smem ? ctx->smem_optin - static_smem : 0;
-    int smem_points = (int)(avail / 8);
+    const size_t static_smem = 13 * 1024;  // centres, totals, queues, row totals, reduction scratch (upper bound)
+    const size_t per_cta = (ctx->smem_optin + 1024) / 2 - 1024;   // two CTAs per SM, 1 KB reserved per CTA
+    size_t avail = per_cta > static_smem ? per_cta - static_smem : 0;
+    int smem_points = (int)(avail / 4);
     if (smem_points > P.max_unique) smem_points = P.max_unique;
     if (smem_points > RMAX * 32 * FW) smem_points = RMAX * 32 * FW;
     smem_points &= ~31;
-    const size_t dyn = (size_t)smem_points * 8;
+    const size_t dyn = (size_t)smem_points * 4;
     if (P.k <= 5) return launch_kc<5>(ctx, P, n, smem_points, dyn, avail);
     if (P.k <= 8) return launch_kc<8>(ctx, P, n, smem_points, dyn, avail);
     if (P.k <= 16) return launch_kc<16>(ctx, P, n, smem_points, dyn, avail);
