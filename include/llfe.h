@@ -98,7 +98,8 @@ int llfe_canny(llfe_ctx* ctx, const uint8_t* d_gray, int n, int h, int w, int lo
 
 /* The hysteresis stage of cv2.Canny on its own (shape_analyzer pyc L24, SURVEY.md A.3
  * step 5): d_weak / d_strong are u8 maps (non-zero = pixel kept by the non-maximum
- * suppression / kept and above the high threshold; strong must be a subset of weak).
+ * suppression / kept and above the high threshold; strong pixels outside the weak set
+ * are ignored).
  * d_edges = 255 for every weak pixel whose 8-connected component of weak pixels contains
  * a strong pixel, else 0; dilate != 0 folds the 3x3 dilate of pyc L27-28 in. */
 int llfe_hysteresis(llfe_ctx* ctx, const uint8_t* d_weak, const uint8_t* d_strong, int n, int h, int w, int dilate,

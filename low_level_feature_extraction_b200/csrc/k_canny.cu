@@ -312,14 +312,16 @@ __global__ void __launch_bounds__(256) k_plane_to_mask(const uint32_t* __restric
 }
 
 // u8 mask (non-zero = set) -> bit plane; one warp per plane word
-__global__ void __launch_bounds__(256) k_mask_to_plane(const uint8_t* __restrict__ mask, int h, int w, int wpr,
+__global__ void __launch_bounds__(256) k_mask_to_plane(const uint8_t* __restrict__ mask,
+                                                       const uint8_t* __restrict__ and_mask, int h, int w, int wpr,
                                                        uint32_t* __restrict__ plane) {
     const int img = blockIdx.z, y = blockIdx.y;
     const int lane = threadIdx.x & 31;
     const int c = blockIdx.x * 8 + (threadIdx.x >> 5);
     if (c >= wpr) return;
     const int x = c * 32 + lane;
-    const bool on = x < w && mask[((size_t)img * h + y) * w + x] != 0;
+    const size_t o = ((size_t)img * h + y) * w + x;
+    const bool on = x < w && mask[o] != 0 && (and_mask == nullptr || and_mask[o] != 0);
     const uint32_t bits = __ballot_sync(0xffffffffu, on);
     if (lane == 0) plane[((size_t)img * h + y) * wpr + c] = bits;
 }
@@ -427,11 +429,12 @@ int launch_plane_to_mask(llfe_ctx* ctx, const uint32_t* plane, int n, int h, int
     return LLFE_OK;
 }
 
-int launch_mask_to_plane(llfe_ctx* ctx, const uint8_t* mask, int n, int h, int w, uint32_t* plane) {
+// and_mask (optional): a pixel is set only where both maps are non-zero
+int launch_mask_to_plane(llfe_ctx* ctx, const uint8_t* mask, const uint8_t* and_mask, int n, int h, int w, uint32_t* plane) {
     if (n == 0 || h == 0 || w == 0) return LLFE_OK;
     const int wpr = plane_wpr(w);
     LLFE_KERNEL(ctx, "k_mask_to_plane");
-    k_mask_to_plane<<<dim3(ceil_div(wpr, 8), h, n), 256, 0, ctx->stream>>>(mask, h, w, wpr, plane);
+    k_mask_to_plane<<<dim3(ceil_div(wpr, 8), h, n), 256, 0, ctx->stream>>>(mask, and_mask, h, w, wpr, plane);
     LLFE_LAUNCHED(ctx);
     return LLFE_OK;
 }

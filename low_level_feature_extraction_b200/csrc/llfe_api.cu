@@ -341,8 +341,8 @@ int llfe_hysteresis(llfe_ctx* ctx, const uint8_t* d_weak, const uint8_t* d_stron
     uint32_t* weak = ws.take<uint32_t>(plane);
     uint32_t* edges = ws.take<uint32_t>(plane);
     uint32_t* flags = ws.take<uint32_t>(hysteresis_flag_words(n, h));
-    LLFE_TRY(launch_mask_to_plane(ctx, d_weak, n, h, w, weak));
-    LLFE_TRY(launch_mask_to_plane(ctx, d_strong, n, h, w, edges));
+    LLFE_TRY(launch_mask_to_plane(ctx, d_weak, nullptr, n, h, w, weak));
+    LLFE_TRY(launch_mask_to_plane(ctx, d_strong, d_weak, n, h, w, edges));   // seeds outside the weak set cannot grow
     return hysteresis_to_mask(ctx, weak, edges, n, h, w, flags, dilate, d_edges);
 }
 

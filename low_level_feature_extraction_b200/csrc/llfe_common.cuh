@@ -111,7 +111,8 @@ int launch_hysteresis(llfe_ctx* ctx, const uint32_t* weak, uint32_t* edges, int 
 int launch_hysteresis_mask_cluster(llfe_ctx* ctx, const uint32_t* weak, const uint32_t* strong, int n, int h, int w,
                                    int dilate, uint8_t* mask);
 int launch_plane_to_mask(llfe_ctx* ctx, const uint32_t* plane, int n, int h, int w, int dilate, uint8_t* mask);
-int launch_mask_to_plane(llfe_ctx* ctx, const uint8_t* mask, int n, int h, int w, uint32_t* plane);
+int launch_mask_to_plane(llfe_ctx* ctx, const uint8_t* mask, const uint8_t* and_mask, int n, int h, int w,
+                         uint32_t* plane);
 int launch_adaptive(llfe_ctx* ctx, const uint8_t* gray, int n, int h, int w, int C, uint8_t* mask, uint64_t* sum_count);
 int launch_hist256(llfe_ctx* ctx, const uint8_t* gray, int n, size_t npix_per_image, uint32_t* hist);
 int launch_otsu_sweep(llfe_ctx* ctx, const uint32_t* hist, int n, size_t npix_per_image, int invert_if_light,

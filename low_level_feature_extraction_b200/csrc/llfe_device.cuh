@@ -79,31 +79,14 @@ __device__ __forceinline__ unsigned long long warp_sum_u64(unsigned long long v)
     return v;
 }
 
-// fill `e` along runs of `w` inside one 32-bit word (both directions), e subset of w
+// fill `e` along runs of `w` inside one 32-bit word (both directions), e subset of w.
+// Upward: adding the seeds to the word lets the carry ripple through each run from its lowest
+// seed to the top of the run (and die in the gap above it); the bits the addition flipped, plus
+// the seeds themselves, are the filled pixels.  Downward is the same on the bit-reversed words.
+// 9 instructions instead of the 30 of a Kogge-Stone fill, and a much shorter dependency chain.
+__device__ __forceinline__ uint32_t fill_up(uint32_t e, uint32_t w) { return (((w + e) ^ w) & w) | e; }
 __device__ __forceinline__ uint32_t fill_word(uint32_t e, uint32_t w) {
-    // Kogge-Stone occluded fill towards higher bits, then lower bits
-    uint32_t g1 = e, p = w;
-    g1 |= p & (g1 << 1);
-    p &= p << 1;
-    g1 |= p & (g1 << 2);
-    p &= p << 2;
-    g1 |= p & (g1 << 4);
-    p &= p << 4;
-    g1 |= p & (g1 << 8);
-    p &= p << 8;
-    g1 |= p & (g1 << 16);
-    uint32_t g2 = e;
-    p = w;
-    g2 |= p & (g2 >> 1);
-    p &= p >> 1;
-    g2 |= p & (g2 >> 2);
-    p &= p >> 2;
-    g2 |= p & (g2 >> 4);
-    p &= p >> 4;
-    g2 |= p & (g2 >> 8);
-    p &= p >> 8;
-    g2 |= p & (g2 >> 16);
-    return g1 | g2;
+    return fill_up(e, w) | __brev(fill_up(__brev(e), __brev(w)));
 }
 
 // ---- palette noise (shared by k_palette.cu and k_fused.cu) -----------------------------
