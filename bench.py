@@ -52,6 +52,8 @@ KERNEL_BYTES = {
     # k-means: every (attempt, image) CTA reads the key list once and writes its labels once;
     # all iterations run out of shared memory, so this kernel is SM-bound, not HBM-bound
     "k_kmeans_fast": lambda P, U, A: A * (4 * U + U),
+    "k_kmeans_fast_long": lambda P, U, A: 0,       # same images counted under k_kmeans_fast
+    "k_kmeans_fast_global": lambda P, U, A: 0,
     "k_kmeans_pp": lambda P, U, A: A * 4 * U,
     "k_kmeans_lloyd": lambda P, U, A: A * (4 * U + U),
     "k_kmeans": lambda P, U, A: A * (4 * U + U),
@@ -65,6 +67,7 @@ WORKLOAD_BYTES = {
     "shapes": lambda P: 3 * P + P,         # dilated edge mask                 (config 2: 4P)
     "shadows": lambda P: 3 * P + P,
     "colors": lambda P: 3 * P,
+    "palette_shadows": lambda P: 3 * P + P,   # BASELINE config 3: palette + shadow threshold mask
 }
 
 
@@ -78,6 +81,7 @@ def parse_args():
     ap.add_argument("--batch", type=int, default=256, help="images per GPU per step")
     ap.add_argument("--height", type=int, default=1080)
     ap.add_argument("--width", type=int, default=1920)
+    ap.add_argument("--k", type=int, default=5, help="palette size (n_colors); BASELINE config 3 uses 16")
     ap.add_argument("--distinct", type=int, default=8, help="distinct synthetic images generated on the host")
     ap.add_argument("--e2e-steps", type=int, default=2)
     ap.add_argument("--no-cpu-baseline", action="store_true")
@@ -93,7 +97,9 @@ def config_of(args, world):
                                    " (gray/blur/Canny/dilate) + shadow mask (gray/blur/adaptive threshold)",
                        "shapes": " through preprocess + Canny edge/shape masks (BASELINE config 2)",
                        "shadows": " through the shadow threshold mask",
-                       "colors": " through the colour palette (k=5)"}[args.workload],
+                       "colors": f" through the colour palette (k={args.k})",
+                       "palette_shadows": f" through the colour palette (k={args.k}) + shadow threshold mask (BASELINE config 3)"}[args.workload]
+                    .replace("k-means k=5", f"k-means k={args.k}"),
         "images_per_gpu": args.batch, "height": args.height, "width": args.width,
         "global_images_per_step": args.batch * world,
         "parallelism": f"dp{world} (images sharded by rank, no collective)",
@@ -106,7 +112,7 @@ def config_of(args, world):
 def cpu_baseline(args, seconds):
     from oracle.refbench import CpuReference
 
-    ref = CpuReference(args.workload, args.height, args.width)
+    ref = CpuReference(args.workload, args.height, args.width, k=args.k)
     n = ref.images_per_step(seconds)
     dt = ref.step(n)
     ref.close()
@@ -122,7 +128,7 @@ def run_reference(args):
         return
     from oracle.refbench import CpuReference
 
-    ref = CpuReference(args.workload, args.height, args.width)
+    ref = CpuReference(args.workload, args.height, args.width, k=args.k)
     n = ref.images_per_step(max(2.0, 60.0 / max(1, args.steps + args.warmup)))
     for _ in range(args.warmup):
         ref.step(n)
@@ -234,8 +240,9 @@ def run_ours(args):
         batch[i] = torch.roll(base_d[i % args.distinct], shifts=7 * (i // args.distinct), dims=0)
     del base_d
 
-    cfg = BatchConfig(colors=args.workload in ("pipeline", "colors"), shapes=args.workload in ("pipeline", "shapes"),
-                      shadows=args.workload in ("pipeline", "shadows"))
+    cfg = BatchConfig(colors=args.workload in ("pipeline", "colors", "palette_shadows"),
+                      shapes=args.workload in ("pipeline", "shapes"),
+                      shadows=args.workload in ("pipeline", "shadows", "palette_shadows"), k=args.k)
     an = BatchAnalyzer(local, H, W, cfg)
     eng = an.engines[0]
     out = an.alloc_outputs(B)

@@ -29,7 +29,7 @@ namespace {
 constexpr int FT = 512;
 constexpr int FW = FT / 32;
 constexpr int QROWS = 8;    // rows (of 32 points) per bounds-test / drain block
-constexpr int RMAX = 64;    // rows per warp the row-total table holds (IN_SMEM lists are shorter)
+constexpr int RMAX = 112;   // rows per warp the row-total table holds (IN_SMEM lists are shorter)
 constexpr unsigned FULL = 0xffffffffu;
 
 __device__ __forceinline__ float fdist4(float r, float g, float b, float4 c) {
@@ -77,13 +77,14 @@ __device__ __forceinline__ uint32_t idist2(uint32_t a, uint32_t b) {
 }
 
 template <int KC, bool IN_SMEM>
-__global__ void __launch_bounds__(FT, 2) k_kmeans_fast(KmParams P, int smem_points, int img_base) {
+__global__ void __launch_bounds__(FT, 2) k_kmeans_fast(KmParams P, int u_lo, int smem_points, int img_base) {
     typedef Fmt<KC> F;
     extern __shared__ uint32_t dyn[];
     const int att = blockIdx.x, img = blockIdx.y + img_base, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int U = min(P.count[img], P.max_unique);
     const int K = min(P.k, U);
-    if ((U <= smem_points) != IN_SMEM) return;  // the other instantiation owns this image
+    // this launch owns the images with u_lo < U <= smem_points (IN_SMEM) / U > smem_points (global scratch)
+    if (IN_SMEM ? (U <= u_lo || U > smem_points) : (U <= smem_points)) return;
     const size_t slot = (size_t)img * P.attempts + att;
     if (K <= 1) {
         if (tid == 0) {
@@ -608,24 +609,29 @@ __global__ void __launch_bounds__(FT, 2) k_kmeans_fast(KmParams P, int smem_poin
 }
 
 template <int KC>
-int launch_kc(llfe_ctx* ctx, const KmParams& P, int n, int smem_points, size_t dyn, size_t avail) {
+int launch_kc(llfe_ctx* ctx, const KmParams& P, int n, int pts2, int pts1) {
     static bool attr_set = false;
     if (!attr_set) {
-        LLFE_CUDA(cudaFuncSetAttribute(k_kmeans_fast<KC, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)avail));
+        LLFE_CUDA(cudaFuncSetAttribute(k_kmeans_fast<KC, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, pts1 * 4));
         attr_set = true;
     }
-    // one launch for the whole batch: the block scheduler back-fills SMs as CTAs finish, so attempts
-    // that need many iterations do not hold up a wave
+    // One launch for the whole batch: the block scheduler back-fills SMs as CTAs finish, so attempts
+    // that need many iterations do not hold up a wave.  Lists of up to pts2 colours run two CTAs per SM.
     LLFE_KERNEL(ctx, "k_kmeans_fast");
-    k_kmeans_fast<KC, true><<<dim3(P.attempts, n), FT, dyn, ctx->stream>>>(P, smem_points, 0);
+    k_kmeans_fast<KC, true><<<dim3(P.attempts, n), FT, (size_t)pts2 * 4, ctx->stream>>>(P, 0, pts2, 0);
     LLFE_LAUNCHED(ctx);
-    // images whose colour list does not fit in shared memory (every CTA of the others exits at once);
-    // the global scratch holds P.dist_images images per launch
-    if (P.max_unique > smem_points) {
+    // longer lists: one CTA per SM with all of its shared memory (every CTA of the other images exits at once)
+    if (P.max_unique > pts2 && pts1 > pts2) {
+        LLFE_KERNEL(ctx, "k_kmeans_fast_long");
+        k_kmeans_fast<KC, true><<<dim3(P.attempts, n), FT, (size_t)pts1 * 4, ctx->stream>>>(P, pts2, pts1, 0);
+        LLFE_LAUNCHED(ctx);
+    }
+    // lists that do not fit in shared memory at all: global scratch, P.dist_images images per launch
+    if (P.max_unique > pts1) {
         for (int i0 = 0; i0 < n; i0 += P.dist_images) {
             const int m = (n - i0) < P.dist_images ? (n - i0) : P.dist_images;
             LLFE_KERNEL(ctx, "k_kmeans_fast_global");
-            k_kmeans_fast<KC, false><<<dim3(P.attempts, m), FT, 0, ctx->stream>>>(P, smem_points, i0);
+            k_kmeans_fast<KC, false><<<dim3(P.attempts, m), FT, 0, ctx->stream>>>(P, 0, pts1, i0);
             LLFE_LAUNCHED(ctx);
         }
     }
@@ -634,20 +640,22 @@ int launch_kc(llfe_ctx* ctx, const KmParams& P, int n, int smem_points, size_t d
 
 }  // namespace
 
-// smem_points: how many points (4 bytes each) the dynamic shared memory of one CTA can hold with two CTAs per SM
+// pts2 / pts1: how many colours (4 bytes each) fit in the dynamic shared memory of one CTA with two / one CTA per SM
 int launch_kmeans_fast(llfe_ctx* ctx, const KmParams& P0, int n) {
     KmParams P = P0;
     if (const char* dbg = getenv("LLFE_KMEANS_DEBUG")) P.dbg = (unsigned long long*)(uintptr_t)strtoull(dbg, nullptr, 10);
-    const size_t static_smem = 13 * 1024;  // centres, totals, queues, row totals, reduction scratch (upper bound)
-    const size_t per_cta = (ctx->smem_optin + 1024) / 2 - 1024;   // two CTAs per SM, 1 KB reserved per CTA
-    size_t avail = per_cta > static_smem ? per_cta - static_smem : 0;
-    int smem_points = (int)(avail / 4);
-    if (smem_points > P.max_unique) smem_points = P.max_unique;
-    if (smem_points > RMAX * 32 * FW) smem_points = RMAX * 32 * FW;
-    smem_points &= ~31;
-    const size_t dyn = (size_t)smem_points * 4;
-    if (P.k <= 5) return launch_kc<5>(ctx, P, n, smem_points, dyn, avail);
-    if (P.k <= 8) return launch_kc<8>(ctx, P, n, smem_points, dyn, avail);
-    if (P.k <= 16) return launch_kc<16>(ctx, P, n, smem_points, dyn, avail);
-    return launch_kc<32>(ctx, P, n, smem_points, dyn, avail);
+    const size_t static_smem = 16 * 1024;  // centres, totals, queues, row totals, reduction scratch (upper bound)
+    const size_t per_cta2 = (ctx->smem_optin + 1024) / 2 - 1024;   // two CTAs per SM, 1 KB reserved per CTA
+    auto points = [&](size_t per_cta) {
+        size_t avail = per_cta > static_smem ? per_cta - static_smem : 0;
+        long long p = (long long)(avail / 4);
+        if (p > P.max_unique) p = P.max_unique;
+        if (p > RMAX * 32 * FW) p = RMAX * 32 * FW;
+        return (int)(p & ~31ll);
+    };
+    const int pts2 = points(per_cta2), pts1 = points(ctx->smem_optin);
+    if (P.k <= 5) return launch_kc<5>(ctx, P, n, pts2, pts1);
+    if (P.k <= 8) return launch_kc<8>(ctx, P, n, pts2, pts1);
+    if (P.k <= 16) return launch_kc<16>(ctx, P, n, pts2, pts1);
+    return launch_kc<32>(ctx, P, n, pts2, pts1);
 }

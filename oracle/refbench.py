@@ -18,13 +18,14 @@ import numpy as np
 _STATE = {}
 
 
-def _init(workload: str, h: int, w: int, use_reference: bool):
+def _init(workload: str, h: int, w: int, use_reference: bool, k: int = 5):
     import cv2
 
     cv2.setNumThreads(1)
     from low_level_feature_extraction_b200.synth import design_image
 
     _STATE["workload"] = workload
+    _STATE["k"] = k
     _STATE["imgs"] = [design_image(h, w, s) for s in range(2)]
     _STATE["ref"] = None
     if use_reference:
@@ -44,22 +45,22 @@ def _one(i: int) -> int:
     cv2.setRNGSeed(1000 + i)
     if wl in ("pipeline", "shapes"):
         (ref["ShapeAnalyzer"].preprocess_image if ref else refpath.shape_mask)(img)
-    if wl in ("pipeline", "shadows"):
+    if wl in ("pipeline", "shadows", "palette_shadows"):
         (ref["ShadowAnalyzer"].analyze_shadow_level if ref else refpath.shadow_level)(img)
-    if wl in ("pipeline", "colors"):
-        (ref["ColorExtractor"].extract_colors if ref else refpath.extract_colors)(img, 5)
+    if wl in ("pipeline", "colors", "palette_shadows"):
+        (ref["ColorExtractor"].extract_colors if ref else refpath.extract_colors)(img, _STATE.get("k", 5))
     return i
 
 
 class CpuReference:
-    def __init__(self, workload: str, h: int, w: int, procs: int | None = None):
+    def __init__(self, workload: str, h: int, w: int, procs: int | None = None, k: int = 5):
         from oracle import load_reference
 
         self.workload, self.h, self.w = workload, h, w
         self.procs = procs or os.cpu_count() or 1
         self.kind = "reference" if load_reference.available() else "port"
         ctx = mp.get_context("fork")
-        self.pool = ctx.Pool(self.procs, initializer=_init, initargs=(workload, h, w, self.kind == "reference"))
+        self.pool = ctx.Pool(self.procs, initializer=_init, initargs=(workload, h, w, self.kind == "reference", k))
         self.pool.map(_one, range(self.procs))  # warm: imports, synthetic inputs, OpenCV's lazy init
 
     def images_per_step(self, target_seconds: float = 8.0) -> int:
