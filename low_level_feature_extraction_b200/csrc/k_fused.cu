@@ -558,10 +558,27 @@ int launch_fused(llfe_ctx* ctx, const uint8_t* bgr, int n, int h, int w, int low
         if (!s_dummy) LLFE_CUDA(cudaMalloc(&s_dummy, 65536 * 2 * sizeof(unsigned long long)));
         A.sum_count = s_dummy;
     }
-    // row bands: enough CTAs to fill the machine, tall enough to amortise the warm-up rows
-    int bands = 8;
-    while (bands > 1 && h / bands < 48) bands >>= 1;
-    A.rows_per_band = ceil_div(h, bands);
+    // Row bands: the grid should fill whole waves of the machine (4 CTAs per SM) and the bands should be tall
+    // enough to amortise their ~10 warm-up rows.  Pick the band count with the best product of the two.
+    {
+        const int xb = ceil_div(w, BAND_W);
+        const double slots = 4.0 * (ctx->sm_count > 0 ? ctx->sm_count : 148);
+        const double halo = S ? 10.0 : 4.0;
+        int best = 1;
+        double best_score = -1.0;
+        for (int bands = 1; bands <= 32 && (bands == 1 || h / bands >= 32); ++bands) {
+            const int rpb = ceil_div(h, bands);
+            const double ctas = (double)xb * ceil_div(h, rpb) * n;
+            const double waves = ctas / slots;
+            const double fill = waves / (double)(long long)(waves + 0.999999);
+            const double score = fill * rpb / (rpb + halo);
+            if (score > best_score + 1e-9) {
+                best_score = score;
+                best = bands;
+            }
+        }
+        A.rows_per_band = ceil_div(h, best);
+    }
     dim3 grid(ceil_div(w, BAND_W), ceil_div(h, A.rows_per_band), n);
     const size_t smem = (size_t)WARPS * 32 * 24 + (S ? (size_t)WARPS * (RING * 2 * 32 + RING * 16) * sizeof(float4) : 0);
     if (S && sum_count) LLFE_CUDA(cudaMemsetAsync(sum_count, 0, (size_t)n * 2 * sizeof(uint64_t), ctx->stream));
