@@ -152,6 +152,7 @@ __global__ void __launch_bounds__(HC_THREADS) k_hyst_mask(HcArgs A) {
     const int g0 = r0 - (D + 1);
     uint32_t* E = sm;                      // [L][SP]
     uint32_t* W = sm + L * SP;             // [L][SP]  (context rows 0 and L-1 stay zero: never grown)
+    uint32_t* chg = sm + 2 * L * SP;       // [L + 2] epoch of the last change of each row (index i + 1; 0 = never)
     const size_t plane = (size_t)h * wpr;
     const uint32_t* gw = A.weak + img * plane;
     const uint32_t* gs = A.strong + img * plane;
@@ -165,6 +166,7 @@ __global__ void __launch_bounds__(HC_THREADS) k_hyst_mask(HcArgs A) {
     unsigned n_iter = 0, n_round = 0;
     // ---- load: zero everything, then stream the in-image rows with cp.async (all loads in flight) ----
     for (int q = tid; q < 2 * L * SP / 4; q += HC_THREADS) reinterpret_cast<uint4*>(sm)[q] = make_uint4(0u, 0u, 0u, 0u);
+    for (int q = tid; q < L + 2; q += HC_THREADS) chg[q] = 0u;
     __syncthreads();
     {
         const uint32_t sE = (uint32_t)__cvta_generic_to_shared(E), sW = (uint32_t)__cvta_generic_to_shared(W);
@@ -201,6 +203,8 @@ __global__ void __launch_bounds__(HC_THREADS) k_hyst_mask(HcArgs A) {
         for (int j = 0; j < WPL; ++j) cand |= w.v[j] & ~e.v[j];
         if (__any_sync(FULLM, cand != 0u)) live |= 1ull << (i - ra);
     }
+    unsigned long long dirty = live;
+    uint32_t ep = 0u;
     if (live && lane == 0) s_live = 1;  // benign race: everyone writes 1
     __syncthreads();
     const bool has_live = s_live != 0;
@@ -208,23 +212,43 @@ __global__ void __launch_bounds__(HC_THREADS) k_hyst_mask(HcArgs A) {
 
     for (int round = 0;; ++round) {
         const long long ta = clock64();
-        // ---- local convergence: walk down the live rows, step back when a row gained pixels ------------
+        // ---- local convergence: walk down the rows that can still grow, step back when a row gained pixels.
+        // A row needs another look only if it, or a row next to it, changed since it was last processed:
+        // `dirty` tracks that per warp (own steps directly, other warps' steps and merges through the
+        // per-row change epochs), so converged parts of the strip are not walked again.
         if (has_live) {
             for (;;) {
                 ++n_iter;
+                ++ep;
+                if (ep > 1) {   // rows next to something that changed in the previous iteration / merge
+#pragma unroll
+                    for (int half = 0; half < 2; ++half) {
+                        const int i = ra + 32 * half + lane;
+                        bool f = false;
+                        if (i < rb) f = chg[i] == ep - 1 || chg[i + 1] == ep - 1 || chg[i + 2] == ep - 1;  // rows i-1, i, i+1
+                        const unsigned long long b = __ballot_sync(FULLM, f);
+                        dirty |= b << (32 * half);
+                    }
+                }
                 bool changed = false;
                 int i = ra;
                 while (i < rb) {
-                    const unsigned long long m = live >> (i - ra);
+                    const unsigned long long m = (live & dirty) >> (i - ra);
                     if (m == 0ull) break;
-                    i += __ffsll((long long)m) - 1;            // next live row
+                    i += __ffsll((long long)m) - 1;            // next row that is live and dirty
                     const int res = hc_row_step<WPL>(E, W, i, lane);
+                    dirty &= ~(1ull << (i - ra));
                     if (res == 0) live &= ~(1ull << (i - ra));
                     if (res == 2) {
                         changed = true;
-                        if (i > ra && ((live >> (i - 1 - ra)) & 1ull)) {
-                            --i;                               // the row above may grow now
-                            continue;
+                        if (lane == 0) chg[i + 1] = ep;
+                        if (i + 1 < rb) dirty |= 1ull << (i + 1 - ra);
+                        if (i > ra) {
+                            dirty |= 1ull << (i - 1 - ra);
+                            if ((live >> (i - 1 - ra)) & 1ull) {
+                                --i;                           // the row above may grow now
+                                continue;
+                            }
                         }
                     }
                     ++i;
@@ -237,12 +261,14 @@ __global__ void __launch_bounds__(HC_THREADS) k_hyst_mask(HcArgs A) {
         // ---- OR-merge the 2 (D + 1) rows shared with each neighbour through distributed shared memory --
         bool mchanged = false;
         constexpr int NS = 2 * (D + 1);
+        ++ep;   // the merge is an epoch of its own: rows it changes are looked at by the next walk
         if (rank > 0) {  // my rows 0 .. NS-1  <->  rows rps .. L-1 of the strip above
             const uint32_t* nb = cluster.map_shared_rank(E, rank - 1) + rps * SP;
             for (int q = tid; q < NS * SP; q += HC_THREADS) {
                 const uint32_t v = nb[q], mine = E[q];
                 if (v & ~mine) {
                     E[q] = mine | v;
+                    chg[q / SP + 1] = ep;
                     mchanged = true;
                 }
             }
@@ -255,6 +281,7 @@ __global__ void __launch_bounds__(HC_THREADS) k_hyst_mask(HcArgs A) {
                 const uint32_t v = nb[q], mine = me[q];
                 if (v & ~mine) {
                     me[q] = mine | v;
+                    chg[rps + q / SP + 1] = ep;
                     mchanged = true;
                 }
             }
@@ -327,7 +354,7 @@ size_t hc_smem(int rps, int sp) {
     const int L = rps + 2 * (HC_D + 1);
     const int rpw = (L - 2 + HC_NW - 1) / HC_NW;
     if (rpw + 2 * HC_D > 64) return (size_t)1 << 40;   // the per-warp live mask is 64 bits
-    return (size_t)2 * L * sp * sizeof(uint32_t);
+    return ((size_t)2 * L * sp + L + 2 + 2) * sizeof(uint32_t);
 }
 
 template <int CL, int WPL, bool DILATE>
