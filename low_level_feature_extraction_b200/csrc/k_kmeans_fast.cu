@@ -107,7 +107,8 @@ __global__ void __launch_bounds__(FT, 2) k_kmeans_fast(KmParams P, int u_lo, int
     __shared__ float4 s_old[KMAX];
     __shared__ float4 s_asg[KMAX];          // the centres the current labels were assigned with
     __shared__ int s_sum[KMAX][4];          // exact per-cluster {sum R, sum G, sum B, count}
-    __shared__ uint32_t s_dq[KMAX], s_hq[KMAX], s_m[4];
+    __shared__ uint32_t s_dq[KMAX];
+    __shared__ uint4 s_tab[KMAX];           // per label: {own centre's drift, largest drift of another centre, half gap, -}
     __shared__ uint8_t s_queue[FW][QROWS * 32];   // per-warp queue of points whose bounds failed
     __shared__ uint32_t s_rowsum[IN_SMEM ? FW : 1][IN_SMEM ? RMAX : 1];
     __shared__ unsigned long long s_wtot[FW];
@@ -388,9 +389,11 @@ __global__ void __launch_bounds__(FT, 2) k_kmeans_fast(KmParams P, int u_lo, int
                 }
             }
         } else {
-            __syncthreads();  // s_dq / s_hq / s_m of the last update are visible
-            const uint32_t m1 = s_m[0], m2 = s_m[1], kmax = s_m[2];
+            __syncthreads();  // s_tab of the last update is visible
             uint8_t* q = s_queue[warp];
+            // rows of this warp that are completely inside the list need no bounds check
+            const int full_rows_all = U >> 5;
+            const int r_full = full_rows_all > warp ? (full_rows_all - warp + FW - 1) / FW : 0;
             // Two phases per block of QROWS rows so that the expensive path runs on full warps: (A) every
             // lane tests the bounds of its points and the failing ones are compacted into the warp's
             // queue; (B) the queue is drained 32 points at a time.
@@ -400,15 +403,14 @@ __global__ void __launch_bounds__(FT, 2) k_kmeans_fast(KmParams P, int u_lo, int
                 for (int r = rb0; r < rb1; ++r) {
                     const int i = (r * FW + warp) * 32 + lane;
                     bool need = false;
-                    if (i < U) {
+                    if (r < r_full || i < U) {   // first test is warp-uniform and almost always true
                         const uint32_t x = aux[i];
                         const uint32_t a = F::label(x);
-                        const uint32_t ub = min(F::UMAX, F::ub(x) + s_dq[a]);
-                        const uint32_t dl = (a == kmax) ? m2 : m1;
-                        uint32_t lb = F::lb(x);
-                        lb = lb > dl ? lb - dl : 0u;
+                        const uint4 t = s_tab[a];
+                        const uint32_t ub = min(F::UMAX, F::ub(x) + t.x);
+                        const uint32_t lb = max(F::lb(x), t.y) - t.y;
                         aux[i] = F::pack(a, ub, lb);
-                        need = ub >= max(lb, s_hq[a]);
+                        need = ub >= max(lb, t.z);
                     }
                     const uint32_t bal = __ballot_sync(FULL, need);
                     if (need) q[qn + __popc(bal & ((1u << lane) - 1u))] = (uint8_t)((r - rb0) * 32 + lane);
@@ -421,7 +423,7 @@ __global__ void __launch_bounds__(FT, 2) k_kmeans_fast(KmParams P, int u_lo, int
                     const int i = ((rb0 + (qe >> 5)) * FW + warp) * 32 + (qe & 31);
                     const uint32_t x = aux[i];
                     const uint32_t a = F::label(x), lb = F::lb(x);
-                    const uint32_t bound = max(lb, s_hq[a]);
+                    const uint32_t bound = max(lb, s_tab[a].z);
                     const uint32_t key = key_at(i);
                     float fr, fg, fb;
                     unpackf(key, fr, fg, fb);
@@ -529,6 +531,7 @@ __global__ void __launch_bounds__(FT, 2) k_kmeans_fast(KmParams P, int u_lo, int
         if (last) break;
         // bounds bookkeeping for the next assignment: how far every centre moved since the assignment
         // just done (s_asg), and half the distance of every centre to its nearest neighbour
+        uint32_t hq_mine = 0u;
         if (tid < K) {
             const float4 c = s_c[tid], o = s_asg[tid];
             const float dx = c.x - o.x, dy = c.y - o.y, dz = c.z - o.z;
@@ -540,10 +543,11 @@ __global__ void __launch_bounds__(FT, 2) k_kmeans_fast(KmParams P, int u_lo, int
                 const float ex = c.x - e.x, ey = c.y - e.y, ez = c.z - e.z;
                 nn = fminf(nn, ex * ex + ey * ey + ez * ez);
             }
-            s_hq[tid] = F::q_dn(0.5f * sqrtf(nn));
+            hq_mine = F::q_dn(0.5f * sqrtf(nn));
         }
         __syncthreads();
-        if (tid == 0) {
+        if (tid < K) {
+            // largest and second largest drift (every one of the K threads scans the K values itself)
             uint32_t m1 = 0, m2 = 0, km = 0;
             for (int k = 0; k < K; ++k) {
                 const uint32_t d = s_dq[k];
@@ -555,9 +559,7 @@ __global__ void __launch_bounds__(FT, 2) k_kmeans_fast(KmParams P, int u_lo, int
                     m2 = d;
                 }
             }
-            s_m[0] = m1;
-            s_m[1] = m2;
-            s_m[2] = km;
+            s_tab[tid] = make_uint4(s_dq[tid], (uint32_t)tid == km ? m2 : m1, hq_mine, 0u);
         }
     }
     const long long t_conv = clock64();
