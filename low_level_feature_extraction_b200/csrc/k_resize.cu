@@ -211,3 +211,83 @@ extern "C" int llfe_resize_area(llfe_ctx* ctx, const uint8_t* d_src, int n, int 
     LLFE_LAUNCHED(ctx);
     return LLFE_OK;
 }
+
+// ---------------------------------------------------------------------------------------------------
+// cv2.resize(..., interpolation=INTER_LINEAR) on u8 (the `performance` preprocessing mode,
+// app/services/analyze/utils.py:136-143).  OpenCV's fixed-point path, restated (oracle/cvops.py
+// resize_linear, verified against cv2 bit for bit):
+//   per axis  f = float((d + 0.5) * scale - 0.5) (double arithmetic), s = floor(f), f -= s;
+//             x only: s < 0 -> (0, f = 0);  s >= ssize - 1 -> (ssize - 1, f = 0);
+//             y: the fraction is kept and the two row indices are clipped into the image;
+//             weights = short(rint((1 - f) * 2048)), short(rint(f * 2048))
+//   H(row)    = S[row][x0] * a0 + S[row][x1] * a1                      (int32)
+//   dst       = sat_u8((((b0 * (H(y0) >> 4)) >> 16) + ((b1 * (H(y1) >> 4)) >> 16) + 2) >> 2)
+// and when both ratios are exactly 2 OpenCV takes the INTER_AREA 2x2 path instead.
+namespace {
+
+struct LinCoef {
+    int s0, s1;
+    int w0, w1;
+};
+
+template <bool CLAMP_WEIGHTS>
+__device__ __forceinline__ LinCoef lin_coef(int d, double scale, int ssize) {
+    float f = (float)(((double)d + 0.5) * scale - 0.5);
+    int s = (int)floorf(f);
+    f = __fsub_rn(f, (float)s);
+    if (CLAMP_WEIGHTS) {
+        if (s < 0) {
+            f = 0.f;
+            s = 0;
+        }
+        if (s >= ssize - 1) {
+            f = 0.f;
+            s = ssize - 1;
+        }
+    }
+    LinCoef c;
+    c.s0 = min(max(s, 0), ssize - 1);
+    c.s1 = min(max(s + 1, 0), ssize - 1);
+    c.w0 = __float2int_rn(__fmul_rn(__fsub_rn(1.f, f), 2048.f));
+    c.w1 = __float2int_rn(__fmul_rn(f, 2048.f));
+    return c;
+}
+
+template <int C>
+__global__ void __launch_bounds__(256) k_resize_linear(const uint8_t* __restrict__ src, int sh, int sw,
+                                                       uint8_t* __restrict__ dst, int dh, int dw, double scale_x,
+                                                       double scale_y) {
+    const int img = blockIdx.z, y = blockIdx.y, x = blockIdx.x * blockDim.x + threadIdx.x;
+    if (x >= dw) return;
+    const LinCoef cx = lin_coef<true>(x, scale_x, sw), cy = lin_coef<false>(y, scale_y, sh);
+    const uint8_t* s = src + (size_t)img * sh * sw * C;
+    const uint8_t* r0 = s + (size_t)cy.s0 * sw * C;
+    const uint8_t* r1 = s + (size_t)cy.s1 * sw * C;
+    uint8_t* o = dst + (((size_t)img * dh + y) * dw + x) * C;
+#pragma unroll
+    for (int ch = 0; ch < C; ++ch) {
+        const int h0 = (int)r0[cx.s0 * C + ch] * cx.w0 + (int)r0[cx.s1 * C + ch] * cx.w1;
+        const int h1 = (int)r1[cx.s0 * C + ch] * cx.w0 + (int)r1[cx.s1 * C + ch] * cx.w1;
+        const int v = (((cy.w0 * (h0 >> 4)) >> 16) + ((cy.w1 * (h1 >> 4)) >> 16) + 2) >> 2;
+        o[ch] = (uint8_t)min(max(v, 0), 255);
+    }
+}
+
+}  // namespace
+
+extern "C" int llfe_resize_linear(llfe_ctx* ctx, const uint8_t* d_src, int n, int sh, int sw, int c, uint8_t* d_dst,
+                                  int dh, int dw) {
+    LLFE_CHECK_ARG(ctx != nullptr && d_src != nullptr && d_dst != nullptr);
+    LLFE_CHECK_ARG(n >= 0 && n <= 65535 && sh > 0 && sw > 0 && dh > 0 && dw > 0 && dh <= 65535 && (c == 1 || c == 3));
+    if (n == 0) return LLFE_OK;
+    if (sw == 2 * dw && sh == 2 * dh) return llfe_resize_area(ctx, d_src, n, sh, sw, c, d_dst, dh, dw);  // OpenCV does the same
+    const double scale_x = 1.0 / ((double)dw / sw), scale_y = 1.0 / ((double)dh / sh);
+    dim3 grid(ceil_div(dw, 256), dh, n);
+    LLFE_KERNEL(ctx, "k_resize_linear");
+    if (c == 3)
+        k_resize_linear<3><<<grid, 256, 0, ctx->stream>>>(d_src, sh, sw, d_dst, dh, dw, scale_x, scale_y);
+    else
+        k_resize_linear<1><<<grid, 256, 0, ctx->stream>>>(d_src, sh, sw, d_dst, dh, dw, scale_x, scale_y);
+    LLFE_LAUNCHED(ctx);
+    return LLFE_OK;
+}

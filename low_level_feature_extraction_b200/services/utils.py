@@ -2,7 +2,7 @@
 `validate_and_preprocess_image` (:90-152).  Decode stays host libpng/libjpeg via
 cv2.imdecode (sequential entropy decoding); the `auto`
 INTER_AREA down-scale -- the mode the endpoint hard-codes (endpoints/analyze.py:90) --
-runs on the GPU.  Download and response assembly (:31-87, :155-214) are network /
+and the `performance` INTER_LINEAR down-scale run on the GPU.  Download and response assembly (:31-87, :155-214) are network /
 HTTP glue outside the path."""
 from __future__ import annotations
 
@@ -12,7 +12,7 @@ from enum import Enum
 import cv2
 import numpy as np
 
-from .image_processor import resize_area
+from .image_processor import resize_area, resize_linear
 
 logger = logging.getLogger(__name__)
 
@@ -60,12 +60,11 @@ async def validate_and_preprocess_image(image_bytes: bytes, request_id: str, pre
                 scale = max_dim / max(h, w)
                 image = cv2.resize(image, (int(w * scale), int(h * scale)), interpolation=cv2.INTER_LANCZOS4)
         elif preprocessing == "performance":
-            # LINEAR to <= 1000 px: not on the hot path; the reference's own call
             max_dim = 1000
             h, w = image.shape[:2]
             if max(h, w) > max_dim:
                 scale = max_dim / max(h, w)
-                image = cv2.resize(image, (int(w * scale), int(h * scale)), interpolation=cv2.INTER_LINEAR)
+                image = resize_linear(image, int(w * scale), int(h * scale))          # utils.py:141-143
         return image
     except Exception as e:
         logger.error(f"Error in validate_and_preprocess_image: {str(e)}", exc_info=True)

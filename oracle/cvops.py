@@ -310,6 +310,58 @@ def resize_area(src: np.ndarray, dw: int, dh: int) -> np.ndarray:
     return np.rint(out).clip(0, 255).astype(np.uint8)
 
 
+def linear_tab(ssize: int, dsize: int, clamp_weights: bool):
+    """Per-axis source indices and 11-bit fixed-point weights of cv2's INTER_LINEAR u8 path.
+    OpenCV clamps the fraction to 0 at the borders for the x axis only; for y it keeps the
+    fraction and clips the two row indices instead (they may then be the same row)."""
+    scale = float(ssize) / dsize
+    idx = np.zeros(dsize, np.int64)
+    wts = np.zeros((dsize, 2), np.int32)
+    for d in range(dsize):
+        fx = f32((d + 0.5) * scale - 0.5)
+        sx = int(np.floor(fx))
+        fx = f32(fx - f32(sx))
+        if clamp_weights:
+            if sx < 0:
+                fx, sx = f32(0), 0
+            if sx >= ssize - 1:
+                fx, sx = f32(0), ssize - 1
+        idx[d] = sx
+        wts[d, 0] = int(np.rint(f32(f32(1.0) - fx) * f32(2048)))
+        wts[d, 1] = int(np.rint(fx * f32(2048)))
+    return idx, wts
+
+
+def resize_linear(src: np.ndarray, dw: int, dh: int) -> np.ndarray:
+    """cv2.resize(src, (dw, dh), interpolation=cv2.INTER_LINEAR) on u8 -- the `performance`
+    preprocessing mode, app/services/analyze/utils.py:136-143.  Fixed point: horizontal
+    H = S[x0]*a0 + S[x1]*a1 (weights scaled by 2048), vertical
+    (((b0*(H0>>4))>>16) + ((b1*(H1>>4))>>16) + 2) >> 2; exact 2x2 ratios take INTER_AREA."""
+    sh, sw = src.shape[:2]
+    if sw == 2 * dw and sh == 2 * dh:
+        return resize_area(src, dw, dh)
+    xi, xa = linear_tab(sw, dw, True)
+    yi, ya = linear_tab(sh, dh, False)
+    S = src.astype(np.int32)
+    if S.ndim == 2:
+        S = S[:, :, None]
+    x1 = np.minimum(xi + 1, sw - 1)
+    H = S[:, xi, :] * xa[:, 0][None, :, None] + S[:, x1, :] * xa[:, 1][None, :, None]
+    y0, y1 = np.clip(yi, 0, sh - 1), np.clip(yi + 1, 0, sh - 1)
+    b0, b1 = ya[:, 0][:, None, None], ya[:, 1][:, None, None]
+    out = (((b0 * (H[y0] >> 4)) >> 16) + ((b1 * (H[y1] >> 4)) >> 16) + 2) >> 2
+    out = np.clip(out, 0, 255).astype(np.uint8)
+    return out if src.ndim == 3 else out[:, :, 0]
+
+
+def performance_resize_shape(h: int, w: int, max_dim: int = 1000):
+    """utils.py:136-143: LINEAR to max-dim 1000 -> (new_w, new_h) or None."""
+    if max(h, w) <= max_dim:
+        return None
+    scale = max_dim / max(h, w)
+    return int(w * scale), int(h * scale)
+
+
 def auto_resize_shape(h: int, w: int, max_dim: int = 2000):
     """`auto` preprocessing output size, utils.py:120-126 (Python float math)."""
     if max(h, w) <= max_dim:

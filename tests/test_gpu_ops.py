@@ -212,6 +212,23 @@ def test_resize_area(eng, case):
     assert np.array_equal(host(eng.resize_area(dev(src), dh, dw)), cvops.resize_area(src, dw, dh))
 
 
+@pytest.mark.parametrize("case", [((1080, 1920, 3), (1000, 562)), ((2160, 3840, 3), (1000, 562)), ((300, 500, 3), (250, 150)),
+                                  ((1200, 1000), (833, 1000)), ((77, 131, 3), (60, 30)), ((64, 64, 3), (32, 32)),
+                                  ((40, 60, 3), (90, 70)), ((33, 47), (47, 33)), ((50, 50, 3), (50, 50))])
+def test_resize_linear(eng, case):
+    import cv2
+
+    shp, (dw, dh) = case
+    src = np.random.default_rng(dw + dh).integers(0, 256, shp, dtype=np.uint8)
+    got = host(eng.resize_linear(dev(src), dh, dw))
+    assert np.array_equal(got, cv2.resize(src, (dw, dh), interpolation=cv2.INTER_LINEAR))
+    if src.size <= 500000:
+        assert np.array_equal(got, cvops.resize_linear(src, dw, dh))
+    batch = np.stack([src, src[::-1].copy()])
+    gb = host(eng.resize_linear(dev(batch), dh, dw))
+    assert np.array_equal(gb[0], got) and np.array_equal(gb[1], cv2.resize(batch[1], (dw, dh), interpolation=cv2.INTER_LINEAR))
+
+
 def test_golden_resize_and_transform(eng, golden):
     import hashlib
     meta, arrays = golden

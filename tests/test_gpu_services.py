@@ -93,6 +93,8 @@ def test_preprocessing_and_transforms(golden):
     out = asyncio.run(validate_and_preprocess_image(png.tobytes(), "t", "auto"))
     r = [x for x in meta["resize"] if x["name"] == "auto_600x2400_s5"][0]
     assert list(out.shape) == r["out_shape"] and sha(out) == r["out_sha256"]
+    perf = asyncio.run(validate_and_preprocess_image(png.tobytes(), "t", "performance"))     # utils.py:136-143
+    assert np.array_equal(perf, cv2.resize(big, (1000, 250), interpolation=cv2.INTER_LINEAR))
     same = asyncio.run(validate_and_preprocess_image(png.tobytes(), "t", "none"))
     assert np.array_equal(same, big)
     with pytest.raises(Exception) as e:

@@ -94,6 +94,26 @@ def test_resize_area(case):
     assert np.array_equal(cvops.resize_area(src, dw, dh), cv2.resize(src, (dw, dh), interpolation=cv2.INTER_AREA))
 
 
+LINEAR_CASES = [((1080, 1920, 3), (1000, 562)), ((300, 500, 3), (250, 150)), ((1200, 1000), (833, 1000)),
+                ((77, 131, 3), (60, 30)), ((101, 203, 3), (100, 50)), ((64, 64, 3), (32, 32)), ((40, 60, 3), (90, 70)),
+                ((33, 47), (47, 33)), ((50, 50, 3), (50, 50))]
+
+
+@pytest.mark.parametrize("case", LINEAR_CASES)
+def test_resize_linear(case):
+    """cv2's fixed-point INTER_LINEAR (the `performance` preprocessing mode, utils.py:136-143), incl. the
+    exact-2x case that OpenCV reroutes to INTER_AREA, up-scaling and the identity."""
+    shp, (dw, dh) = case
+    src = np.random.default_rng(dw + dh).integers(0, 256, shp, dtype=np.uint8)
+    assert np.array_equal(cvops.resize_linear(src, dw, dh), cv2.resize(src, (dw, dh), interpolation=cv2.INTER_LINEAR))
+
+
+def test_performance_resize_shape_matches_reference_rule():
+    assert cvops.performance_resize_shape(1080, 1920) == (1000, 562)
+    assert cvops.performance_resize_shape(2160, 3840) == (1000, 562)
+    assert cvops.performance_resize_shape(800, 1000) is None
+
+
 @pytest.mark.parametrize("alpha", [1.2, 0.9, 1.5, 0.5, 1.3, 1.0, 2.5])
 def test_convert_scale_abs(alpha):
     x = np.arange(256, dtype=np.uint8).reshape(1, -1)
