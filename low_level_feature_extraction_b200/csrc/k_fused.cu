@@ -321,11 +321,11 @@ __global__ void __launch_bounds__(WARPS * 32, 4) k_fused(FusedArgs A) {
     ColorPending pend;
     bool have_pend = false;
     auto own_row = [&](int vy) { return COLORS && out_lane && vy >= y0 && vy < y1; };
-    issue_row<COLORS>(A, img, reflect101(next_vy, H), x, in_x, own_row(next_vy), raw_next);
+    issue_row<COLORS>(A, img, reflect101_near(next_vy, H), x, in_x, own_row(next_vy), raw_next);
     auto gray_row = [&]() -> Q4 {
         const Raw cur = raw_next;
         const int vy = next_vy++;
-        if (next_vy <= vy_last) issue_row<COLORS>(A, img, reflect101(next_vy, H), x, in_x, own_row(next_vy), raw_next);
+        if (next_vy <= vy_last) issue_row<COLORS>(A, img, reflect101_near(next_vy, H), x, in_x, own_row(next_vy), raw_next);
         if (COLORS) {
             if (have_pend) color_commit(A, img, pend);
             have_pend = own_row(vy);

@@ -67,6 +67,14 @@ __device__ __forceinline__ int reflect101(int i, int n) {
     return i >= n ? period - i : i;
 }
 __device__ __forceinline__ int clampi(int i, int lo, int hi) { return min(max(i, lo), hi); }
+// BORDER_REFLECT_101 for offsets that overshoot by less than the period (one mirror suffices); falls
+// back to the general form for tiny n.  No integer division on the common path.
+__device__ __forceinline__ int reflect101_near(int i, int n) {
+    if (n < 16) return reflect101(i, n);
+    if (i < 0) i = -i;
+    if (i >= n) i = 2 * n - 2 - i;
+    return i;
+}
 
 __device__ __forceinline__ uint32_t warp_sum_u32(uint32_t v) {
 #pragma unroll
