@@ -166,19 +166,19 @@ def main():
             ms = float(d["gpu__time_duration.sum"][0]) * UNIT_MS.get(d["gpu__time_duration.sum"][1], 1)
             md.append(f"| dram traffic per launch | {(rd + wr) / 1e6:.3f} | MB |")
             md.append(f"| dram GB/s in this (serialised) launch | {(rd + wr) / 1e9 / (ms / 1e3):.1f} | GB/s |")
-            t = traffic.setdefault(name, {"bytes_per_launch": 0.0, "n": 0, "ms": 0.0})
-            t["bytes_per_launch"] += rd + wr
-            t["ms"] += ms
-            t["n"] += 1
+            traffic.setdefault(name, []).append((rd + wr, ms))
         except (KeyError, ValueError):
             pass
         md.append("")
         if i < len(pages):
             md += summarise_source(pages[i], a.top)
             md.append("")
-    for t in traffic.values():
-        t["bytes_per_launch"] /= t["n"]
-        t["ms"] /= t["n"]
+    # average per kernel, ignoring launches that exit at once (tiers that own no image in the capture)
+    for name, recs in list(traffic.items()):
+        longest = max(ms for _, ms in recs)
+        keep = [(b, ms) for b, ms in recs if ms >= 0.05 * longest]
+        traffic[name] = {"bytes_per_launch": sum(b for b, _ in keep) / len(keep), "ms": sum(ms for _, ms in keep) / len(keep),
+                         "n": len(keep)}
     text = "\n".join(md) + "\n"
     if a.out:
         with open(a.out, "w") as f:
