@@ -71,27 +71,13 @@ __device__ __forceinline__ Words<WPL> lds_words(const uint32_t* p) {
     return r;
 }
 
-// One propagation step of local row i (1 <= i <= L-2), executed by a whole warp.  Returns
-// (warp-uniform) 0: the row has no weak-but-not-edge pixel left, 1: nothing gained, 2: gained pixels.
+// 3x3 neighbourhood on bit level: v = OR of the rows above, at and below; returns w & spread(v) & ~e per word
 template <int WPL>
-__device__ __forceinline__ int hc_row_step(uint32_t* E, const uint32_t* W, int i, int lane) {
-    constexpr int SP = 32 * WPL;
-    uint32_t* erow = E + i * SP + lane * WPL;
-    const Words<WPL> e = lds_words<WPL>(erow);
-    const Words<WPL> w = lds_words<WPL>(W + i * SP + lane * WPL);
-    const Words<WPL> up = lds_words<WPL>(erow - SP);
-    const Words<WPL> dn = lds_words<WPL>(erow + SP);
-    uint32_t cand = 0u;
-    uint32_t v[WPL];
-#pragma unroll
-    for (int j = 0; j < WPL; ++j) {
-        cand |= w.v[j] & ~e.v[j];
-        v[j] = up.v[j] | e.v[j] | dn.v[j];
-    }
+__device__ __forceinline__ uint32_t hc_grow(const uint32_t* v, const Words<WPL>& w, const Words<WPL>& e, Words<WPL>& ne,
+                                            int lane) {
     uint32_t vl = __shfl_up_sync(FULLM, v[WPL - 1], 1), vr = __shfl_down_sync(FULLM, v[0], 1);
     if (lane == 0) vl = 0u;
     if (lane == 31) vr = 0u;
-    Words<WPL> ne;
     uint32_t grow = 0u;
 #pragma unroll
     for (int j = 0; j < WPL; ++j) {
@@ -101,9 +87,12 @@ __device__ __forceinline__ int hc_row_step(uint32_t* E, const uint32_t* W, int i
         grow |= g;
         ne.v[j] = e.v[j] | g;
     }
-    const uint32_t bc = __ballot_sync(FULLM, cand != 0u), bg = __ballot_sync(FULLM, grow != 0u);
-    if (bg == 0u) return bc ? 1 : 0;
-    // horizontal closure of the row: fill inside the words, carry across word / lane boundaries
+    return grow;
+}
+
+// horizontal closure of a row: fill inside the words, carry across word / lane boundaries until nothing moves
+template <int WPL>
+__device__ __forceinline__ void hc_close(Words<WPL>& ne, const Words<WPL>& w, int lane) {
     for (;;) {
 #pragma unroll
         for (int j = 0; j < WPL; ++j) ne.v[j] = fill_word(ne.v[j], w.v[j]);
@@ -120,11 +109,69 @@ __device__ __forceinline__ int hc_row_step(uint32_t* E, const uint32_t* W, int i
         }
         if (!__any_sync(FULLM, add_any != 0u)) break;
     }
+}
+
+// One propagation step of local row i (1 <= i <= L-2), executed by a whole warp.  Returns
+// (warp-uniform) 0: the row has no weak-but-not-edge pixel left, 1: nothing gained, 2: gained pixels;
+// + 4 when the row ABOVE gained pixels too.  A chain that wiggles between two adjacent rows (the usual
+// shape of a weak, nearly horizontal edge) is followed in registers: after row i grew, row i-1 is grown
+// from it, then row i from row i-1, ... until neither moves, and both rows are written back once.
+template <int WPL>
+__device__ __forceinline__ int hc_row_step(uint32_t* E, const uint32_t* W, int i, int lane) {
+    constexpr int SP = 32 * WPL;
+    uint32_t* erow = E + i * SP + lane * WPL;
+    const Words<WPL> e = lds_words<WPL>(erow);
+    const Words<WPL> w = lds_words<WPL>(W + i * SP + lane * WPL);
+    const Words<WPL> up = lds_words<WPL>(erow - SP);
+    const Words<WPL> dn = lds_words<WPL>(erow + SP);
+    uint32_t cand = 0u;
+    uint32_t v[WPL];
+#pragma unroll
+    for (int j = 0; j < WPL; ++j) {
+        cand |= w.v[j] & ~e.v[j];
+        v[j] = up.v[j] | e.v[j] | dn.v[j];
+    }
+    Words<WPL> ne;
+    const uint32_t grow = hc_grow<WPL>(v, w, e, ne, lane);
+    const uint32_t bc = __ballot_sync(FULLM, cand != 0u), bg = __ballot_sync(FULLM, grow != 0u);
+    if (bg == 0u) return bc ? 1 : 0;
+    hc_close<WPL>(ne, w, lane);
+    int above_changed = 0;
+    if (i >= 2) {
+        // ping-pong with the row above, in registers
+        const Words<WPL> w1 = lds_words<WPL>(W + (i - 1) * SP + lane * WPL);
+        const Words<WPL> upup = lds_words<WPL>(erow - 2 * SP);
+        Words<WPL> e1 = up;   // row i-1 as loaded
+        for (;;) {
+            uint32_t v1[WPL];
+#pragma unroll
+            for (int j = 0; j < WPL; ++j) v1[j] = upup.v[j] | e1.v[j] | ne.v[j];
+            Words<WPL> n1;
+            const uint32_t g1 = hc_grow<WPL>(v1, w1, e1, n1, lane);
+            if (!__any_sync(FULLM, g1 != 0u)) break;
+            hc_close<WPL>(n1, w1, lane);
+            e1 = n1;
+            above_changed = 4;
+            uint32_t v0[WPL];
+#pragma unroll
+            for (int j = 0; j < WPL; ++j) v0[j] = e1.v[j] | ne.v[j] | dn.v[j];
+            Words<WPL> n0;
+            const uint32_t g0 = hc_grow<WPL>(v0, w, ne, n0, lane);
+            if (!__any_sync(FULLM, g0 != 0u)) break;
+            hc_close<WPL>(n0, w, lane);
+            ne = n0;
+        }
+        if (above_changed) {
+#pragma unroll
+            for (int j = 0; j < WPL; ++j)
+                if (e1.v[j] != up.v[j]) atomicOr(erow - SP + j, e1.v[j]);
+        }
+    }
     // rows in the overlap of two ranges can be written by two warps: OR, never overwrite
 #pragma unroll
     for (int j = 0; j < WPL; ++j)
         if (ne.v[j] != e.v[j]) atomicOr(erow + j, ne.v[j]);
-    return 2;
+    return 2 | above_changed;
 }
 
 __device__ __forceinline__ void cp_async16(uint32_t smem_addr, const void* g) {
@@ -236,17 +283,22 @@ __global__ void __launch_bounds__(HC_THREADS) k_hyst_mask(HcArgs A) {
                     const unsigned long long m = (live & dirty) >> (i - ra);
                     if (m == 0ull) break;
                     i += __ffsll((long long)m) - 1;            // next row that is live and dirty
-                    const int res = hc_row_step<WPL>(E, W, i, lane);
+                    const int res4 = hc_row_step<WPL>(E, W, i, lane);
+                    const int res = res4 & 3;
                     dirty &= ~(1ull << (i - ra));
                     if (res == 0) live &= ~(1ull << (i - ra));
                     if (res == 2) {
                         changed = true;
-                        if (lane == 0) chg[i + 1] = ep;
+                        if (lane == 0) {
+                            chg[i + 1] = ep;
+                            if (res4 & 4) chg[i] = ep;       // the row above grew with it
+                        }
                         if (i + 1 < rb) dirty |= 1ull << (i + 1 - ra);
-                        if (i > ra) {
-                            dirty |= 1ull << (i - 1 - ra);
-                            if ((live >> (i - 1 - ra)) & 1ull) {
-                                --i;                           // the row above may grow now
+                        // the row above is already consistent with this one; look further up only if it grew
+                        if ((res4 & 4) && i - 2 >= ra) {
+                            dirty |= 1ull << (i - 2 - ra);
+                            if ((live >> (i - 2 - ra)) & 1ull) {
+                                i -= 2;
                                 continue;
                             }
                         }
