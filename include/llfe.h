@@ -150,6 +150,11 @@ int llfe_resize_area(llfe_ctx* ctx, const uint8_t* d_src, int n, int sh, int sw,
 int llfe_resize_linear(llfe_ctx* ctx, const uint8_t* d_src, int n, int sh, int sw, int c, uint8_t* d_dst, int dh,
                        int dw);
 
+/* cv2.resize(src, (dw, dh), interpolation=INTER_LANCZOS4) on u8, c = 1 or 3 (8-tap, OpenCV's 11-bit
+ * fixed-point path): the `high_quality` preprocessing mode, app/services/analyze/utils.py:128-135. */
+int llfe_resize_lanczos4(llfe_ctx* ctx, const uint8_t* d_src, int n, int sh, int sw, int c, uint8_t* d_dst, int dh,
+                         int dw);
+
 /* cv2.convertScaleAbs(x, alpha=a1, beta=0) followed by (alpha=a2, beta=0), the
  * pair of calls of ImageTransformer.adjust_brightness_contrast (image_transformer
  * pyc L139-142) fused into one pass.  Pass a2 = 1.0f with single = 1 for one call. */
@@ -239,6 +244,7 @@ int llfe_text_mask_host(llfe_ctx* ctx, const uint8_t* h_bgr, int h, int w, uint8
 int llfe_font_mask_host(llfe_ctx* ctx, const uint8_t* h_bgr, int h, int w, uint8_t* h_mask);
 int llfe_resize_area_host(llfe_ctx* ctx, const uint8_t* h_src, int sh, int sw, int c, uint8_t* h_dst, int dh, int dw);
 int llfe_resize_linear_host(llfe_ctx* ctx, const uint8_t* h_src, int sh, int sw, int c, uint8_t* h_dst, int dh, int dw);
+int llfe_resize_lanczos4_host(llfe_ctx* ctx, const uint8_t* h_src, int sh, int sw, int c, uint8_t* h_dst, int dh, int dw);
 int llfe_gaussian_blur5_host(llfe_ctx* ctx, const uint8_t* h_src, int h, int w, int c, uint8_t* h_dst);
 int llfe_convert_scale_abs_host(llfe_ctx* ctx, const uint8_t* h_src, size_t count, float a1, float a2, int single,
                                 uint8_t* h_dst);

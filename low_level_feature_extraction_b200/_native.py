@@ -60,6 +60,7 @@ PROTOTYPES = {
     "llfe_text_mask": (i32, [vp, vp, i32, i32, i32, vp, vp]),
     "llfe_resize_area": (i32, [vp, vp, i32, i32, i32, i32, vp, i32, i32]),
     "llfe_resize_linear": (i32, [vp, vp, i32, i32, i32, i32, vp, i32, i32]),
+    "llfe_resize_lanczos4": (i32, [vp, vp, i32, i32, i32, i32, vp, i32, i32]),
     "llfe_convert_scale_abs": (i32, [vp, vp, sz, f32, f32, i32, vp]),
     "llfe_unique_colors": (i32, [vp, vp, i32, i32, i32, vp, u64, vp, vp, vp, i32]),
     "llfe_kmeans_unique": (i32, [vp, vp, vp, i32, i32, i32, i32, i32, f64, vp, vp, vp, vp, vp, vp]),
@@ -74,6 +75,7 @@ PROTOTYPES = {
     "llfe_font_mask_host": (i32, [vp, vp, i32, i32, vp]),
     "llfe_resize_area_host": (i32, [vp, vp, i32, i32, i32, vp, i32, i32]),
     "llfe_resize_linear_host": (i32, [vp, vp, i32, i32, i32, vp, i32, i32]),
+    "llfe_resize_lanczos4_host": (i32, [vp, vp, i32, i32, i32, vp, i32, i32]),
     "llfe_gaussian_blur5_host": (i32, [vp, vp, i32, i32, i32, vp]),
     "llfe_convert_scale_abs_host": (i32, [vp, vp, sz, f32, f32, i32, vp]),
     "llfe_dominant_colors_host": (i32, [vp, vp, i32, i32, vp, u64, i32, i32, i32, f64, u64, vp, vp, vp, vp, vp]),

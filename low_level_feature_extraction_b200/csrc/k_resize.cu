@@ -16,6 +16,7 @@
 #include "llfe_device.cuh"
 
 struct AreaTab {
+    int kind;  // 0: INTER_AREA (offsets / indices / float weights); 1: LANCZOS4 (d_idx = first tap - 3, d_ofs = 8 weights)
     int ssize, dsize;
     int n_entries;
     int max_per_dst;
@@ -54,7 +55,7 @@ void build_tab(int ssize, int dsize, double scale, std::vector<int>& ofs, std::v
 
 int get_tab(llfe_ctx* ctx, int ssize, int dsize, AreaTab** out) {
     for (AreaTab* t = ctx->area_tabs; t; t = t->next)
-        if (t->ssize == ssize && t->dsize == dsize) {
+        if (t->kind == 0 && t->ssize == ssize && t->dsize == dsize) {
             *out = t;
             return LLFE_OK;
         }
@@ -63,6 +64,7 @@ int get_tab(llfe_ctx* ctx, int ssize, int dsize, AreaTab** out) {
     const double scale = 1.0 / ((double)dsize / (double)ssize);
     build_tab(ssize, dsize, scale, ofs, idx, wt);
     AreaTab* t = new AreaTab();
+    t->kind = 0;
     t->ssize = ssize;
     t->dsize = dsize;
     t->n_entries = (int)idx.size();
@@ -164,7 +166,7 @@ void llfe_free_area_tabs(llfe_ctx* ctx) {
         AreaTab* nx = t->next;
         cudaFree(t->d_ofs);
         cudaFree(t->d_idx);
-        cudaFree(t->d_w);
+        if (t->d_w) cudaFree(t->d_w);
         delete t;
         t = nx;
     }
@@ -288,6 +290,144 @@ extern "C" int llfe_resize_linear(llfe_ctx* ctx, const uint8_t* d_src, int n, in
         k_resize_linear<3><<<grid, 256, 0, ctx->stream>>>(d_src, sh, sw, d_dst, dh, dw, scale_x, scale_y);
     else
         k_resize_linear<1><<<grid, 256, 0, ctx->stream>>>(d_src, sh, sw, d_dst, dh, dw, scale_x, scale_y);
+    LLFE_LAUNCHED(ctx);
+    return LLFE_OK;
+}
+
+// ---------------------------------------------------------------------------------------------------
+// cv2.resize(..., interpolation=INTER_LANCZOS4) on u8 (the `high_quality` preprocessing mode,
+// app/services/analyze/utils.py:128-135).  OpenCV's fixed-point path, restated (oracle/cvops.py
+// resize_lanczos4, verified against cv2 bit for bit):
+//   per axis  f = float((d + 0.5) * scale - 0.5), s = floor(f), f -= s; 8 float coefficients from
+//             interpolateLanczos4(f) (sin / cos of the first tap in double, rotated by 45 degrees per tap,
+//             divided by y^2, normalised in float), each scaled by 2048 and rounded to short;
+//             taps s - 3 .. s + 4, indices clipped into the image (no weight clamping on either axis);
+//   H(row)  = sum_k S[row][x_k] * a_k            (int)
+//   dst     = sat_u8((sum_k H(y_k) * b_k + 2^21) >> 22)
+// The tables are built on the host with the same libm calls as OpenCV's and cached on the context.
+namespace {
+
+void lanczos4_coeffs(float x, float* coeffs) {
+    static const double s45 = 0.70710678118654752440084436210485;
+    static const double cs[][2] = {{1, 0}, {-s45, -s45}, {0, 1}, {s45, -s45}, {-1, 0}, {s45, s45}, {0, -1}, {-s45, s45}};
+    const double kPi = 3.1415926535897932384626433832795;
+    float sum = 0;
+    const double y0 = -(x + 3) * kPi * 0.25, s0 = sin(y0), c0 = cos(y0);
+    for (int i = 0; i < 8; i++) {
+        const float y0_ = (x + 3 - i);
+        if (fabs(y0_) >= 1e-6f) {
+            const double y = -y0_ * kPi * 0.25;
+            coeffs[i] = (float)((cs[i][0] * s0 + cs[i][1] * c0) / (y * y));
+        } else {
+            coeffs[i] = 1e30f;  // x ~ 0 or ~ 1: this tap takes everything after the normalisation
+        }
+        sum += coeffs[i];
+    }
+    sum = 1.f / sum;
+    for (int i = 0; i < 8; i++) coeffs[i] *= sum;
+}
+
+int get_lanczos_tab(llfe_ctx* ctx, int ssize, int dsize, AreaTab** out) {
+    for (AreaTab* t = ctx->area_tabs; t; t = t->next)
+        if (t->kind == 1 && t->ssize == ssize && t->dsize == dsize) {
+            *out = t;
+            return LLFE_OK;
+        }
+    const double scale = 1.0 / ((double)dsize / (double)ssize);
+    std::vector<int> first(dsize), wts((size_t)dsize * 8);
+    for (int d = 0; d < dsize; ++d) {
+        float f = (float)((d + 0.5) * scale - 0.5);
+        const int sx = (int)floorf(f);
+        f -= sx;
+        float c[8];
+        lanczos4_coeffs(f, c);
+        first[d] = sx - 3;
+        for (int k = 0; k < 8; ++k) {
+            long v = lrintf(c[k] * 2048.f);   // saturate_cast<short>(float): round half to even, then clamp
+            wts[(size_t)d * 8 + k] = (int)(v < -32768 ? -32768 : v > 32767 ? 32767 : v);
+        }
+    }
+    AreaTab* t = new AreaTab();
+    t->kind = 1;
+    t->ssize = ssize;
+    t->dsize = dsize;
+    t->n_entries = dsize * 8;
+    t->max_per_dst = 8;
+    t->d_ofs = nullptr;
+    t->d_idx = nullptr;
+    t->d_w = nullptr;
+    t->next = nullptr;
+    cudaError_t e;
+    if ((e = cudaMalloc(&t->d_ofs, wts.size() * sizeof(int))) != cudaSuccess ||
+        (e = cudaMalloc(&t->d_idx, first.size() * sizeof(int))) != cudaSuccess) {
+        if (t->d_ofs) cudaFree(t->d_ofs);
+        delete t;
+        return llfe_cuda_fail(e, "cudaMalloc(lanczos table)", __FILE__, __LINE__);
+    }
+    LLFE_CUDA(cudaMemcpy(t->d_ofs, wts.data(), wts.size() * sizeof(int), cudaMemcpyHostToDevice));
+    LLFE_CUDA(cudaMemcpy(t->d_idx, first.data(), first.size() * sizeof(int), cudaMemcpyHostToDevice));
+    t->next = ctx->area_tabs;
+    ctx->area_tabs = t;
+    *out = t;
+    return LLFE_OK;
+}
+
+template <int C>
+__global__ void __launch_bounds__(256) k_resize_lanczos4(const uint8_t* __restrict__ src, int sh, int sw,
+                                                         uint8_t* __restrict__ dst, int dh, int dw,
+                                                         const int* __restrict__ x_first, const int* __restrict__ x_w,
+                                                         const int* __restrict__ y_first, const int* __restrict__ y_w) {
+    const int img = blockIdx.z, y = blockIdx.y, x = blockIdx.x * blockDim.x + threadIdx.x;
+    if (x >= dw) return;
+    const uint8_t* s = src + (size_t)img * sh * sw * C;
+    int xs[8], xa[8];
+    const int x0 = x_first[x], y0 = y_first[y];
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+        xs[k] = min(max(x0 + k, 0), sw - 1) * C;
+        xa[k] = x_w[x * 8 + k];
+    }
+    long long acc[C];
+#pragma unroll
+    for (int ch = 0; ch < C; ++ch) acc[ch] = 0;
+#pragma unroll
+    for (int ky = 0; ky < 8; ++ky) {
+        const uint8_t* row = s + (size_t)min(max(y0 + ky, 0), sh - 1) * sw * C;
+        const int b = y_w[y * 8 + ky];
+#pragma unroll
+        for (int ch = 0; ch < C; ++ch) {
+            int hsum = 0;
+#pragma unroll
+            for (int k = 0; k < 8; ++k) hsum += (int)row[xs[k] + ch] * xa[k];
+            acc[ch] += (long long)hsum * b;
+        }
+    }
+    uint8_t* o = dst + (((size_t)img * dh + y) * dw + x) * C;
+#pragma unroll
+    for (int ch = 0; ch < C; ++ch) {
+        const long long v = (acc[ch] + (1ll << 21)) >> 22;
+        o[ch] = (uint8_t)(v < 0 ? 0 : v > 255 ? 255 : v);
+    }
+}
+
+}  // namespace
+
+extern "C" int llfe_resize_lanczos4(llfe_ctx* ctx, const uint8_t* d_src, int n, int sh, int sw, int c, uint8_t* d_dst,
+                                    int dh, int dw) {
+    LLFE_CHECK_ARG(ctx != nullptr && d_src != nullptr && d_dst != nullptr);
+    LLFE_CHECK_ARG(n >= 0 && n <= 65535 && sh > 0 && sw > 0 && dh > 0 && dw > 0 && dh <= 65535 && (c == 1 || c == 3));
+    if (n == 0) return LLFE_OK;
+    AreaTab *xt, *yt;
+    LLFE_TRY(get_lanczos_tab(ctx, sw, dw, &xt));
+    LLFE_TRY(get_lanczos_tab(ctx, sh, dh, &yt));
+    dim3 grid(ceil_div(dw, 256), dh, n);
+    LLFE_KERNEL(ctx, "k_resize_lanczos4");
+    if (c == 3)
+        k_resize_lanczos4<3><<<grid, 256, 0, ctx->stream>>>(d_src, sh, sw, d_dst, dh, dw, xt->d_idx, xt->d_ofs, yt->d_idx,
+                                                            yt->d_ofs);
+    else
+        k_resize_lanczos4<1><<<grid, 256, 0, ctx->stream>>>(d_src, sh, sw, d_dst, dh, dw, xt->d_idx, xt->d_ofs, yt->d_idx,
+                                                            yt->d_ofs);
     LLFE_LAUNCHED(ctx);
     return LLFE_OK;
 }

@@ -669,4 +669,13 @@ int llfe_resize_linear_host(llfe_ctx* ctx, const uint8_t* h_src, int sh, int sw,
     return stage_end(&st, h_dst, out, 0);
 }
 
+int llfe_resize_lanczos4_host(llfe_ctx* ctx, const uint8_t* h_src, int sh, int sw, int c, uint8_t* h_dst, int dh, int dw) {
+    LLFE_CHECK_ARG(ctx != nullptr && h_src != nullptr && h_dst != nullptr && sh > 0 && sw > 0 && dh > 0 && dw > 0);
+    const size_t in = (size_t)sh * sw * c, out = (size_t)dh * dw * c;
+    HostStage st;
+    LLFE_TRY(stage_begin(ctx, h_src, in, out, &st));
+    LLFE_TRY(llfe_resize_lanczos4(ctx, st.d_in, 1, sh, sw, c, st.d_out, dh, dw));
+    return stage_end(&st, h_dst, out, 0);
+}
+
 }  // extern "C"

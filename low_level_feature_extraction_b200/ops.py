@@ -233,6 +233,21 @@ class Engine:
         self.ctx.call("llfe_resize_linear", x, n, sh, sw, c, out, int(dh), int(dw))
         return out[0] if single else out
 
+    def resize_lanczos4(self, src: torch.Tensor, dh: int, dw: int) -> torch.Tensor:
+        """cv2.resize(src, (dw, dh), interpolation=cv2.INTER_LANCZOS4) on uint8 (1 or 3 channels)."""
+        if src.dim() >= 3 and src.shape[-1] == 3:
+            x, single = _batch(src, 3)
+            n, sh, sw, c = x.shape
+            out = self._empty((n, dh, dw, 3))
+        else:
+            x, single = _batch(src, None)
+            n, sh, sw = x.shape
+            c = 1
+            out = self._empty((n, dh, dw))
+        self._bind()
+        self.ctx.call("llfe_resize_lanczos4", x, n, sh, sw, c, out, int(dh), int(dw))
+        return out[0] if single else out
+
     # -- palette ------------------------------------------------------------------
     def unique_colors(self, bgr: torch.Tensor, noise: torch.Tensor | None = None, seed: int = 0,
                       max_unique: int = 1 << 16, with_counts: bool = False):

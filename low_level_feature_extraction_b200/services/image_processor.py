@@ -49,6 +49,21 @@ def resize_linear(image: np.ndarray, new_width: int, new_height: int) -> np.ndar
     return dst
 
 
+def resize_lanczos4(image: np.ndarray, new_width: int, new_height: int) -> np.ndarray:
+    """cv2.resize(image, (new_width, new_height), interpolation=cv2.INTER_LANCZOS4) for u8 images."""
+    if image.dtype != np.uint8 or image.ndim not in (2, 3) or (image.ndim == 3 and image.shape[2] not in (1, 3)):
+        raise TypeError("Unsupported image type")
+    if new_width <= 0 or new_height <= 0:
+        raise ValueError("Invalid target size")
+    src = np.ascontiguousarray(image)
+    sh, sw = src.shape[:2]
+    c = 1 if src.ndim == 2 else src.shape[2]
+    dst = np.empty((new_height, new_width) + src.shape[2:], np.uint8)
+    with _runtime.lock():
+        _runtime.context().call("llfe_resize_lanczos4_host", src, sh, sw, c, dst, new_height, new_width)
+    return dst
+
+
 class ImageProcessor:
     logger = logging.getLogger(__name__)
 

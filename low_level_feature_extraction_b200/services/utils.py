@@ -2,7 +2,7 @@
 `validate_and_preprocess_image` (:90-152).  Decode stays host libpng/libjpeg via
 cv2.imdecode (sequential entropy decoding); the `auto`
 INTER_AREA down-scale -- the mode the endpoint hard-codes (endpoints/analyze.py:90) --
-and the `performance` INTER_LINEAR down-scale run on the GPU.  Download and response assembly (:31-87, :155-214) are network /
+and the `performance` (INTER_LINEAR) and `high_quality` (INTER_LANCZOS4) down-scales run on the GPU.  Download and response assembly (:31-87, :155-214) are network /
 HTTP glue outside the path."""
 from __future__ import annotations
 
@@ -12,7 +12,7 @@ from enum import Enum
 import cv2
 import numpy as np
 
-from .image_processor import resize_area, resize_linear
+from .image_processor import resize_area, resize_lanczos4, resize_linear
 
 logger = logging.getLogger(__name__)
 
@@ -53,12 +53,11 @@ async def validate_and_preprocess_image(image_bytes: bytes, request_id: str, pre
                 scale = max_dim / max(h, w)
                 image = resize_area(image, int(w * scale), int(h * scale))            # utils.py:125-127
         elif preprocessing == "high_quality":
-            # LANCZOS4 to <= 4000 px: not on the hot path; the reference's own call
             max_dim = 4000
             h, w = image.shape[:2]
             if max(h, w) > max_dim:
                 scale = max_dim / max(h, w)
-                image = cv2.resize(image, (int(w * scale), int(h * scale)), interpolation=cv2.INTER_LANCZOS4)
+                image = resize_lanczos4(image, int(w * scale), int(h * scale))        # utils.py:133-135
         elif preprocessing == "performance":
             max_dim = 1000
             h, w = image.shape[:2]

@@ -354,6 +354,62 @@ def resize_linear(src: np.ndarray, dw: int, dh: int) -> np.ndarray:
     return out if src.ndim == 3 else out[:, :, 0]
 
 
+def lanczos4_coeffs(x) -> np.ndarray:
+    """cv::interpolateLanczos4: 8 float32 coefficients for the fraction x (float32)."""
+    import math
+
+    s45 = 0.70710678118654752440084436210485
+    cs = ((1, 0), (-s45, -s45), (0, 1), (s45, -s45), (-1, 0), (s45, s45), (0, -1), (-s45, s45))
+    x = f32(x)
+    coeffs = np.zeros(8, f32)
+    total = f32(0)
+    y0 = -float(f32(x + f32(3))) * math.pi * 0.25
+    s0, c0 = math.sin(y0), math.cos(y0)
+    for i in range(8):
+        y0_ = f32(f32(x + f32(3)) - f32(i))
+        if abs(float(y0_)) >= 1e-6:
+            y = -float(y0_) * math.pi * 0.25
+            coeffs[i] = f32((cs[i][0] * s0 + cs[i][1] * c0) / (y * y))
+        else:
+            coeffs[i] = f32(1e30)
+        total = f32(total + coeffs[i])
+    total = f32(f32(1.0) / total)
+    return (coeffs * total).astype(f32)
+
+
+def lanczos4_tab(ssize: int, dsize: int):
+    scale = float(ssize) / dsize
+    first = np.zeros(dsize, np.int64)
+    wts = np.zeros((dsize, 8), np.int64)
+    for d in range(dsize):
+        fx = f32((d + 0.5) * scale - 0.5)
+        sx = int(np.floor(fx))
+        fx = f32(fx - f32(sx))
+        first[d] = sx - 3
+        wts[d] = np.clip(np.rint(lanczos4_coeffs(fx) * f32(2048)), -32768, 32767).astype(np.int64)
+    return first, wts
+
+
+def resize_lanczos4(src: np.ndarray, dw: int, dh: int) -> np.ndarray:
+    """cv2.resize(src, (dw, dh), interpolation=cv2.INTER_LANCZOS4) on u8 -- the `high_quality`
+    preprocessing mode, app/services/analyze/utils.py:128-135.  8 taps per axis with weights
+    scaled by 2048 (short), indices clipped into the image, dst = sat_u8((sum + 2^21) >> 22)."""
+    sh, sw = src.shape[:2]
+    xf, xa = lanczos4_tab(sw, dw)
+    yf, ya = lanczos4_tab(sh, dh)
+    S = src.astype(np.int64)
+    if S.ndim == 2:
+        S = S[:, :, None]
+    H = np.zeros((sh, dw, S.shape[2]), np.int64)
+    for k in range(8):
+        H += S[:, np.clip(xf + k, 0, sw - 1), :] * xa[:, k][None, :, None]
+    out = np.zeros((dh, dw, S.shape[2]), np.int64)
+    for k in range(8):
+        out += H[np.clip(yf + k, 0, sh - 1)] * ya[:, k][:, None, None]
+    out = np.clip((out + (1 << 21)) >> 22, 0, 255).astype(np.uint8)
+    return out if src.ndim == 3 else out[:, :, 0]
+
+
 def performance_resize_shape(h: int, w: int, max_dim: int = 1000):
     """utils.py:136-143: LINEAR to max-dim 1000 -> (new_w, new_h) or None."""
     if max(h, w) <= max_dim:

@@ -229,6 +229,20 @@ def test_resize_linear(eng, case):
     assert np.array_equal(gb[0], got) and np.array_equal(gb[1], cv2.resize(batch[1], (dw, dh), interpolation=cv2.INTER_LINEAR))
 
 
+@pytest.mark.parametrize("case", [((2250, 4500, 3), (4000, 2000)), ((300, 500, 3), (250, 150)), ((1200, 1000), (833, 1000)),
+                                  ((77, 131, 3), (60, 30)), ((64, 64, 3), (32, 32)), ((40, 60, 3), (90, 70)),
+                                  ((33, 47), (47, 33)), ((50, 50, 3), (50, 50)), ((9, 7, 3), (5, 4))])
+def test_resize_lanczos4(eng, case):
+    import cv2
+
+    shp, (dw, dh) = case
+    src = np.random.default_rng(dw * 3 + dh).integers(0, 256, shp, dtype=np.uint8)
+    got = host(eng.resize_lanczos4(dev(src), dh, dw))
+    assert np.array_equal(got, cv2.resize(src, (dw, dh), interpolation=cv2.INTER_LANCZOS4))
+    if src.size <= 500000:
+        assert np.array_equal(got, cvops.resize_lanczos4(src, dw, dh))
+
+
 def test_golden_resize_and_transform(eng, golden):
     import hashlib
     meta, arrays = golden

@@ -95,6 +95,10 @@ def test_preprocessing_and_transforms(golden):
     assert list(out.shape) == r["out_shape"] and sha(out) == r["out_sha256"]
     perf = asyncio.run(validate_and_preprocess_image(png.tobytes(), "t", "performance"))     # utils.py:136-143
     assert np.array_equal(perf, cv2.resize(big, (1000, 250), interpolation=cv2.INTER_LINEAR))
+    huge = design_image(1100, 4400, 9)
+    ok2, png2 = cv2.imencode(".png", huge)
+    hq = asyncio.run(validate_and_preprocess_image(png2.tobytes(), "t", "high_quality"))       # utils.py:128-135
+    assert np.array_equal(hq, cv2.resize(huge, (4000, 1000), interpolation=cv2.INTER_LANCZOS4))
     same = asyncio.run(validate_and_preprocess_image(png.tobytes(), "t", "none"))
     assert np.array_equal(same, big)
     with pytest.raises(Exception) as e:

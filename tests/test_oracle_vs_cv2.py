@@ -108,6 +108,16 @@ def test_resize_linear(case):
     assert np.array_equal(cvops.resize_linear(src, dw, dh), cv2.resize(src, (dw, dh), interpolation=cv2.INTER_LINEAR))
 
 
+@pytest.mark.parametrize("case", [((300, 500, 3), (250, 150)), ((1200, 1000), (833, 1000)), ((77, 131, 3), (60, 30)),
+                                  ((64, 64, 3), (32, 32)), ((40, 60, 3), (90, 70)), ((33, 47), (47, 33)), ((50, 50, 3), (50, 50)),
+                                  ((9, 7, 3), (5, 4))])
+def test_resize_lanczos4(case):
+    """cv2's fixed-point INTER_LANCZOS4 (the `high_quality` preprocessing mode, utils.py:128-135)."""
+    shp, (dw, dh) = case
+    src = np.random.default_rng(dw * 3 + dh).integers(0, 256, shp, dtype=np.uint8)
+    assert np.array_equal(cvops.resize_lanczos4(src, dw, dh), cv2.resize(src, (dw, dh), interpolation=cv2.INTER_LANCZOS4))
+
+
 def test_performance_resize_shape_matches_reference_rule():
     assert cvops.performance_resize_shape(1080, 1920) == (1000, 562)
     assert cvops.performance_resize_shape(2160, 3840) == (1000, 562)
