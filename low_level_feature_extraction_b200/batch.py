@@ -101,6 +101,40 @@ class BatchAnalyzer:
             out["cluster_sizes"] = torch.empty((n, c.k), dtype=torch.int32).pin_memory()
         return out
 
+    def _stages(self, n: int):
+        """(first image, count) of every pipeline stage: short stages at both ends so that the un-overlapped
+        first upload and last download are small, full `host_chunk` stages in between."""
+        c = self.cfg.host_chunk
+        ramp = []
+        s = max(1, c // 4)
+        while s < c:
+            ramp.append(s)
+            s *= 2
+        sizes, left = [], n
+        for s in ramp:                      # ramp up
+            if left - s < sum(ramp):        # keep room for the ramp down
+                break
+            sizes.append(s)
+            left -= s
+        tail = [s for s in reversed(ramp)]
+        while left > sum(tail):
+            m = min(c, left - sum(tail))
+            sizes.append(m)
+            left -= m
+        for s in tail:
+            m = min(s, left)
+            if m > 0:
+                sizes.append(m)
+                left -= m
+        if left > 0:
+            sizes.append(left)
+        out, i0 = [], 0
+        for m in sizes:
+            out.append((i0, m))
+            i0 += m
+        assert i0 == n
+        return out
+
     def run_host(self, images: torch.Tensor, host_out: dict | None = None) -> dict:
         """images: pinned CPU uint8 (B, H, W, 3).  Returns host tensors; synchronous."""
         c = self.cfg
@@ -111,9 +145,8 @@ class BatchAnalyzer:
             self._dev_in = [torch.empty((c.host_chunk, self.h, self.w, 3), dtype=torch.uint8, device=self.device) for _ in range(ns)]
             self._dev_out = [self.alloc_outputs(c.host_chunk) for _ in range(ns)]
         bytes_in = bytes_out = 0
-        for j, i0 in enumerate(range(0, n, c.host_chunk)):
+        for j, (i0, m) in enumerate(self._stages(n)):
             b = j % len(self.streams)
-            m = min(c.host_chunk, n - i0)
             st = self.streams[b]
             with torch.cuda.stream(st):
                 din = self._dev_in[b][:m]

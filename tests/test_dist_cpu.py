@@ -104,3 +104,21 @@ def test_single_process_is_identity_collective():
     c_ref, _, it_ref, _, _ = cvops.lloyd_exact(px, init)
     res = ldist.PixelKMeans(OracleBackend()).fit(torch.from_numpy(img), torch.from_numpy(init))
     assert res.iters == it_ref and np.array_equal(res.centers.numpy(), c_ref)
+
+
+def test_host_pipeline_stage_schedule():
+    """BatchAnalyzer.run_host: stages cover the batch exactly once, never exceed host_chunk, ramp up and down."""
+    from low_level_feature_extraction_b200.batch import BatchAnalyzer, BatchConfig
+
+    class Host:   # _stages only needs cfg
+        pass
+
+    for chunk in (1, 4, 16, 32):
+        h = Host()
+        h.cfg = BatchConfig(host_chunk=chunk)
+        for n in (1, 2, 3, 15, 16, 17, 40, 100, 256, 1000):
+            st = BatchAnalyzer._stages(h, n)
+            assert [i0 for i0, _ in st] == [sum(m for _, m in st[:j]) for j in range(len(st))]
+            assert sum(m for _, m in st) == n and all(0 < m <= chunk for _, m in st)
+            if n >= 8 * chunk and chunk >= 4:
+                assert st[0][1] < chunk and st[-1][1] < chunk and max(m for _, m in st) == chunk

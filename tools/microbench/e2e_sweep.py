@@ -6,7 +6,7 @@ from low_level_feature_extraction_b200.synth import design_image
 B,H,W=256,1080,1920
 base=np.stack([design_image(H,W,s) for s in range(4)])
 host_in=torch.from_numpy(base).repeat(B//4,1,1,1).contiguous().pin_memory()
-for hc,ns in ((16,3),(8,4),(8,6),(16,4),(4,8),(12,4)):
+for hc,ns in ((16,3),(16,4),(32,3),(12,4)):
     an=BatchAnalyzer(0,H,W,BatchConfig(host_chunk=hc,host_streams=ns))
     out=an.alloc_host_outputs(B)
     an.run_host(host_in,out); torch.cuda.synchronize()
