@@ -2,6 +2,7 @@
 outputs of the unmodified reference captured in tests/golden/."""
 import asyncio
 import hashlib
+import os
 
 import cv2
 import numpy as np
@@ -123,3 +124,22 @@ def test_preprocessing_and_transforms(golden):
     assert np.array_equal(ImageTransformer.apply_filter(src4.copy(), "gaussian_blur"), arrays["transform/gaussian_blur"])
     with pytest.raises(ValueError):
         ImageTransformer.apply_filter(src4, "nope")
+
+
+def _resize_modes_golden():
+    import json
+
+    with open(os.path.join(os.path.dirname(__file__), "golden", "golden_resize_modes.json")) as f:
+        return json.load(f)
+
+
+@pytest.mark.parametrize("name", sorted(_resize_modes_golden()["cases"]))
+def test_preprocessing_modes_match_reference_golden(name):
+    """validate_and_preprocess_image in the `performance` and `high_quality` modes on the GPU vs the outputs of
+    the reference itself (tests/golden/golden_resize_modes.json)."""
+    c = _resize_modes_golden()["cases"][name]
+    img = design_image(c["h"], c["w"], c["seed"])
+    assert sha(img) == c["input_sha256"]
+    ok, png = cv2.imencode(".png", img)
+    out = asyncio.run(validate_and_preprocess_image(png.tobytes(), "t", c["mode"]))
+    assert list(out.shape) == c["out_shape"] and sha(out) == c["out_sha256"]

@@ -80,3 +80,34 @@ def test_transform(golden):
     assert np.array_equal(cvops.adjust_brightness_contrast(src, 1.2, 0.9), arrays["transform/bc_1.2_0.9"])
     assert np.array_equal(cvops.adjust_brightness_contrast(src, 1.3, 1.5), arrays["transform/bc_1.3_1.5"])
     assert np.array_equal(cvops.gaussian_blur5(src), arrays["transform/gaussian_blur"])
+
+
+def _resize_modes_golden():
+    import json
+    import os
+
+    with open(os.path.join(os.path.dirname(__file__), "golden", "golden_resize_modes.json")) as f:
+        return json.load(f)
+
+
+@pytest.mark.parametrize("name", sorted(_resize_modes_golden()["cases"]))
+def test_resize_modes_oracle_matches_reference(name):
+    """oracle restatements of the `performance` / `high_quality` modes vs outputs of the reference itself
+    (oracle/make_golden_resize_modes.py)."""
+    from low_level_feature_extraction_b200.synth import design_image
+
+    c = _resize_modes_golden()["cases"][name]
+    img = design_image(c["h"], c["w"], c["seed"])
+    assert sha(img) == c["input_sha256"]
+    h, w = img.shape[:2]
+    if c["mode"] == "performance":
+        shp = cvops.performance_resize_shape(h, w)
+        out = img if shp is None else cvops.resize_linear(img, shp[0], shp[1])
+    else:
+        max_dim = 4000
+        if max(h, w) > max_dim:
+            s = max_dim / max(h, w)
+            out = cvops.resize_lanczos4(img, int(w * s), int(h * s))
+        else:
+            out = img
+    assert list(out.shape) == c["out_shape"] and sha(out) == c["out_sha256"]
