@@ -202,9 +202,14 @@ int llfe_kmeans_lloyd(llfe_ctx* ctx, const uint32_t* d_keys, const uint32_t* d_w
  * centres (float32 RGB) and ADD the exact per-cluster sums into
  * d_sums_counts[k][4] = {sum R, sum G, sum B, count} (uint64).  The caller
  * zeroes the accumulator, all-reduces it across ranks (ncclSum) and calls
- * llfe_kmeans_update. */
+ * llfe_kmeans_update.  d_state_or_null is the state array of llfe_kmeans_update: when it
+ * says "converged" (state[1]) or "frozen" (state[3]) the call is a no-op, so a host can
+ * enqueue several iterations back to back and look at the state once per batch. */
 int llfe_kmeans_pixels_step(llfe_ctx* ctx, const uint8_t* d_bgr, size_t n_pixels, int k, const float* d_centers,
-                            uint64_t* d_sums_counts, uint8_t* d_labels_or_null);
+                            uint64_t* d_sums_counts, uint8_t* d_labels_or_null, const int32_t* d_state_or_null);
+
+/* Zero the k x 4 accumulator for the next iteration unless the state says converged / frozen. */
+int llfe_kmeans_pixels_zero(llfe_ctx* ctx, int k, uint64_t* d_sums_counts, const int32_t* d_state_or_null);
 
 /* Empty-cluster repair support for the per-pixel mode: among the pixels of this
  * shard whose nearest centre (under d_centers) is `donor`, find the one farthest
@@ -218,9 +223,10 @@ int llfe_kmeans_pixels_farthest(llfe_ctx* ctx, const uint8_t* d_bgr, size_t n_pi
                                 uint64_t* d_out);
 
 /* Centre update + convergence test from (all-reduced) sums: c =
- * float(double(sum)/double(count)); d_state[0] = iteration counter (in/out),
- * d_state[1] = converged flag (out), d_state[2] = number of empty clusters (out; when
- * it is non-zero nothing else is updated: repair the sums, then call again).
+ * float(double(sum)/double(count)); d_state (4 x int32): [0] = iteration counter (in/out),
+ * [1] = converged flag (out), [2] = number of empty clusters (out), [3] = frozen (out: set
+ * together with [2] != 0; nothing else is updated -- the host repairs the sums, clears
+ * [2] and [3], and calls again).  A converged or frozen state makes the call a no-op.
  * d_shift receives max_k |c - old|^2 (double).  The first call (iteration 0) never
  * reports convergence, as in cv2's KMEANS_USE_INITIAL_LABELS mode. */
 int llfe_kmeans_update(llfe_ctx* ctx, int k, const uint64_t* d_sums_counts, float* d_centers, int max_iter,

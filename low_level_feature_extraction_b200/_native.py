@@ -65,7 +65,8 @@ PROTOTYPES = {
     "llfe_unique_colors": (i32, [vp, vp, i32, i32, i32, vp, u64, vp, vp, vp, i32]),
     "llfe_kmeans_unique": (i32, [vp, vp, vp, i32, i32, i32, i32, i32, f64, vp, vp, vp, vp, vp, vp]),
     "llfe_kmeans_lloyd": (i32, [vp, vp, vp, vp, i32, i32, i32, i32, f64, i32, vp, vp, vp, vp, vp]),
-    "llfe_kmeans_pixels_step": (i32, [vp, vp, sz, i32, vp, vp, vp]),
+    "llfe_kmeans_pixels_step": (i32, [vp, vp, sz, i32, vp, vp, vp, vp]),
+    "llfe_kmeans_pixels_zero": (i32, [vp, i32, vp, vp]),
     "llfe_kmeans_pixels_farthest": (i32, [vp, vp, sz, i32, vp, i32, vp, C.c_uint32, vp, i32, vp]),
     "llfe_kmeans_update": (i32, [vp, i32, vp, vp, i32, f64, vp, vp]),
     "llfe_pipeline": (i32, [vp, vp, i32, i32, i32, i32, i32, vp, vp, vp, vp, u64, vp, vp, i32]),

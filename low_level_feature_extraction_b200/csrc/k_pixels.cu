@@ -87,7 +87,9 @@ __device__ __forceinline__ int nearest_scalar(float fr, float fg, float fb, cons
 // nearest centre for every pixel + exact per-cluster sums
 __global__ void __launch_bounds__(PT, 2) k_pixels_step(const uint8_t* __restrict__ bgr, size_t npix, int K,
                                                     const float* __restrict__ centers, unsigned long long* sums,
-                                                    uint8_t* __restrict__ labels_out, int head) {
+                                                    uint8_t* __restrict__ labels_out, int head,
+                                                    const int32_t* __restrict__ state) {
+    if (state && (state[1] | state[3])) return;   // converged, or waiting for the host (empty-cluster repair)
     __shared__ float s_c[KMAX][3];
     __shared__ u64 s_nc[KMAX][3];   // (-c, -c) pairs for the packed path
     __shared__ Acc s_acc;
@@ -255,10 +257,14 @@ __global__ void __launch_bounds__(PT) k_pixels_farthest(const uint8_t* __restric
 __global__ void k_pixels_update(int K, const unsigned long long* __restrict__ sums, float* centers, int max_iter,
                                 double eps2, int32_t* state, double* shift_out) {
     if (threadIdx.x != 0 || blockIdx.x != 0) return;
+    if (state[1] | state[3]) return;  // converged / frozen: later iterations of an unsynchronised batch are no-ops
     int n_empty = 0;
     for (int k = 0; k < K; ++k) n_empty += sums[4 * k + 3] == 0;
     state[2] = n_empty;
-    if (n_empty) return;  // the host runs the repair and calls update again
+    if (n_empty) {
+        state[3] = 1;  // freeze: the host repairs the sums, clears state[2..3] and calls update again
+        return;
+    }
     double shift = 0.0;
     for (int k = 0; k < K; ++k) {
         double s = 0.0;
@@ -278,10 +284,25 @@ __global__ void k_pixels_update(int K, const unsigned long long* __restrict__ su
     if (shift_out) *shift_out = shift;
 }
 
+// zero the per-rank accumulator for the next iteration -- unless the loop is converged or frozen
+__global__ void k_pixels_zero(int K, unsigned long long* sums, const int32_t* __restrict__ state) {
+    if (state && (state[1] | state[3])) return;
+    if (threadIdx.x < K * 4) sums[threadIdx.x] = 0ull;
+}
+
 }  // namespace
 
+extern "C" int llfe_kmeans_pixels_zero(llfe_ctx* ctx, int k, uint64_t* d_sums_counts, const int32_t* d_state_or_null) {
+    LLFE_CHECK_ARG(ctx != nullptr && d_sums_counts != nullptr && k >= 1 && k <= KMAX);
+    LLFE_KERNEL(ctx, "k_pixels_zero");
+    k_pixels_zero<<<1, 128, 0, ctx->stream>>>(k, (unsigned long long*)d_sums_counts, d_state_or_null);
+    LLFE_LAUNCHED(ctx);
+    return LLFE_OK;
+}
+
 extern "C" int llfe_kmeans_pixels_step(llfe_ctx* ctx, const uint8_t* d_bgr, size_t n_pixels, int k,
-                                       const float* d_centers, uint64_t* d_sums_counts, uint8_t* d_labels_or_null) {
+                                       const float* d_centers, uint64_t* d_sums_counts, uint8_t* d_labels_or_null,
+                                       const int32_t* d_state_or_null) {
     LLFE_CHECK_ARG(ctx != nullptr && d_bgr != nullptr && d_centers != nullptr && d_sums_counts != nullptr);
     LLFE_CHECK_ARG(k >= 1 && k <= KMAX);
     if (n_pixels == 0) return LLFE_OK;
@@ -293,7 +314,7 @@ extern "C" int llfe_kmeans_pixels_step(llfe_ctx* ctx, const uint8_t* d_bgr, size
     unsigned grid = (unsigned)(want < 1 ? 1 : (want > cap ? cap : want));
     LLFE_KERNEL(ctx, "k_pixels_step");
     k_pixels_step<<<grid, PT, 0, ctx->stream>>>(d_bgr, n_pixels, k, d_centers, (unsigned long long*)d_sums_counts,
-                                                d_labels_or_null, head);
+                                                d_labels_or_null, head, d_state_or_null);
     LLFE_LAUNCHED(ctx);
     return LLFE_OK;
 }

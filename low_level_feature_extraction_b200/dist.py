@@ -79,9 +79,10 @@ class PixelKMeans:
     shift test max_k |c - old|^2 <= eps^2 from iteration 1 on, cv2's empty-cluster repair.
     """
 
-    def __init__(self, backend, group=None):
+    def __init__(self, backend, group=None, iterations_per_sync: int = 4):
         self.be = backend
         self.group = group
+        self.iterations_per_sync = iterations_per_sync   # iterations enqueued per host look at the device state
 
     # -- collectives (identity in a single process) ----------------------------------------
     def _allreduce(self, t: torch.Tensor, op) -> None:
@@ -96,24 +97,32 @@ class PixelKMeans:
         dev = bgr_rows.device
         k = int(init_centers.shape[0])
         centers = init_centers.to(device=dev, dtype=torch.float32).contiguous().clone()
-        sums = torch.zeros((k, 4), dtype=torch.int64, device=dev)
-        state = torch.zeros((3,), dtype=torch.int32, device=dev)
+        local = torch.zeros((k, 4), dtype=torch.int64, device=dev)    # this rank's partial sums
+        sums = torch.zeros((k, 4), dtype=torch.int64, device=dev)     # all-reduced sums
+        state = torch.zeros((4,), dtype=torch.int32, device=dev)      # iteration, converged, n_empty, frozen
         shift = torch.zeros((1,), dtype=torch.float64, device=dev)
         far = torch.zeros((1,), dtype=torch.int64, device=dev)
         npix = bgr_rows.numel() // 3
         labels = torch.empty((npix,), dtype=torch.uint8, device=dev) if want_labels else None
         flat = bgr_rows.reshape(-1, 3)
+        batch = max(1, int(self.iterations_per_sync))
         while True:
-            sums.zero_()
-            be.kmeans_pixels_step(bgr_rows, centers, sums, labels)
-            self._allreduce(sums, dist.ReduceOp.SUM)
-            be.kmeans_update(sums, centers, state, shift, max_iter=max_iter, eps=eps)
-            st = state.tolist()
-            if st[2]:
+            # `batch` iterations are enqueued back to back; once the device state says converged (or frozen for
+            # a repair) the remaining ones are no-ops on every rank alike: the partial sums are not re-zeroed,
+            # so the out-of-place all-reduce just reproduces the same totals.
+            for _ in range(batch):
+                be.kmeans_pixels_zero(local, state)
+                be.kmeans_pixels_step(bgr_rows, centers, local, labels, state)
+                sums.copy_(local)
+                self._allreduce(sums, dist.ReduceOp.SUM)
+                be.kmeans_update(sums, centers, state, shift, max_iter=max_iter, eps=eps)
+            st = state.tolist()          # the one host synchronisation per batch
+            if st[3]:
                 self._repair(flat, centers, sums, far, index_base, npix, labels)
+                state[2:4] = 0
                 be.kmeans_update(sums, centers, state, shift, max_iter=max_iter, eps=eps)
                 st = state.tolist()
-                if st[2]:
+                if st[3]:
                     raise RuntimeError("k-means: an empty cluster survived the repair (fewer distinct pixels than k?)")
             if st[1]:
                 return PixelKMeansResult(centers, st[0], sums, float(shift.item()), labels)

@@ -320,13 +320,19 @@ class Engine:
 
     # -- per-pixel k-means building blocks (row shard of one image) ---------------
     def kmeans_pixels_step(self, bgr_rows: torch.Tensor, centers: torch.Tensor, sums: torch.Tensor,
-                           labels: torch.Tensor | None = None):
-        """sums (k,4) int64 += exact {sum R, sum G, sum B, count} per cluster over the pixels of bgr_rows."""
+                           labels: torch.Tensor | None = None, state: torch.Tensor | None = None):
+        """sums (k,4) int64 += exact {sum R, sum G, sum B, count} per cluster over the pixels of bgr_rows
+        (a no-op when `state` says converged or frozen)."""
         x = bgr_rows.contiguous()
         npix = x.numel() // 3
         k = centers.shape[0]
         self._bind()
-        self.ctx.call("llfe_kmeans_pixels_step", x, npix, k, centers, sums, labels)
+        self.ctx.call("llfe_kmeans_pixels_step", x, npix, k, centers, sums, labels, state)
+
+    def kmeans_pixels_zero(self, sums: torch.Tensor, state: torch.Tensor | None = None):
+        """Zero the (k,4) accumulator unless `state` says converged or frozen."""
+        self._bind()
+        self.ctx.call("llfe_kmeans_pixels_zero", sums.shape[0], sums, state)
 
     def kmeans_update(self, sums: torch.Tensor, centers: torch.Tensor, state: torch.Tensor, shift: torch.Tensor,
                       max_iter: int = 200, eps: float = 0.2):

@@ -17,7 +17,14 @@ f32 = np.float32
 
 
 class OracleBackend:
-    def kmeans_pixels_step(self, bgr_rows, centers, sums, labels=None):
+    def kmeans_pixels_zero(self, sums, state=None):
+        if state is not None and (int(state[1]) or int(state[3])):
+            return
+        sums.zero_()
+
+    def kmeans_pixels_step(self, bgr_rows, centers, sums, labels=None, state=None):
+        if state is not None and (int(state[1]) or int(state[3])):
+            return
         px = bgr_rows.reshape(-1, 3).numpy()[:, ::-1]  # RGB
         if len(px) == 0:
             return
@@ -44,10 +51,13 @@ class OracleBackend:
         out[0] = max(int(out[0]), int(code.max()))
 
     def kmeans_update(self, sums, centers, state, shift, max_iter=200, eps=0.2):
+        if int(state[1]) or int(state[3]):
+            return
         s = sums.numpy()
         n_empty = int((s[:, 3] == 0).sum())
         state[2] = n_empty
         if n_empty:
+            state[3] = 1
             return
         new = (s[:, :3].astype(np.float64) / s[:, 3:4].astype(np.float64)).astype(f32)
         sh = cvops.center_shift(new, centers.numpy())

@@ -92,6 +92,7 @@ def main():
     step_ms = ev[0].elapsed_time(ev[1]) / 5
     ar_ms = ev[1].elapsed_time(ev[2]) / 20
 
+    km.fit(rows, init, index_base=r0 * a.width, max_iter=a.max_iter)   # warm-up (lazy kernel loading, allocations)
     torch.cuda.synchronize()
     if world > 1:
         dist.barrier()
