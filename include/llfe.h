@@ -217,10 +217,18 @@ int llfe_kmeans_pixels_zero(llfe_ctx* ctx, int k, uint64_t* d_sums_counts, const
  * highest pixel index.  *d_out = max(*d_out, ((dist bits << 32) | (index_base +
  * local pixel index)) + 1); the caller zeroes it first and all-reduces with max.
  * h_skip[n_skip] (n_skip <= 32) lists global pixel indices to ignore: the pixels
- * earlier repairs of the same update already moved out of the donor. */
+ * earlier repairs of the same update already moved out of the donor.  With
+ * want_dist_bits != 0 only pixels at exactly that float32 distance from h_base3 are
+ * considered: when llfe_kmeans_hist_farthest has already found the answer's distance, the
+ * pass costs little more than reading the rows (0 = consider every pixel). */
 int llfe_kmeans_pixels_farthest(llfe_ctx* ctx, const uint8_t* d_bgr, size_t n_pixels, int k, const float* d_centers,
                                 int donor, const float* h_base3, uint32_t index_base, const uint32_t* h_skip, int n_skip,
-                                uint64_t* d_out);
+                                uint32_t want_dist_bits, uint64_t* d_out);
+
+/* The same search over (key, count) entries, distance only: *d_out_bits = max(*d_out_bits, bits of the
+ * largest float32 distance to h_base3 among the colours assigned to `donor`) (all-reduce with max). */
+int llfe_kmeans_hist_farthest(llfe_ctx* ctx, const uint32_t* d_keys, size_t n, int k, const float* d_centers, int donor,
+                              const float* h_base3, uint32_t* d_out_bits);
 
 /* Centre update + convergence test from (all-reduced) sums: c =
  * float(double(sum)/double(count)); d_state (4 x int32): [0] = iteration counter (in/out),
@@ -228,9 +236,46 @@ int llfe_kmeans_pixels_farthest(llfe_ctx* ctx, const uint8_t* d_bgr, size_t n_pi
  * together with [2] != 0; nothing else is updated -- the host repairs the sums, clears
  * [2] and [3], and calls again).  A converged or frozen state makes the call a no-op.
  * d_shift receives max_k |c - old|^2 (double).  The first call (iteration 0) never
- * reports convergence, as in cv2's KMEANS_USE_INITIAL_LABELS mode. */
-int llfe_kmeans_update(llfe_ctx* ctx, int k, const uint64_t* d_sums_counts, float* d_centers, int max_iter,
-                       double eps, int32_t* d_state, double* d_shift);
+ * reports convergence, as in cv2's KMEANS_USE_INITIAL_LABELS mode.
+ * d_consumed_or_null (k x 4), when given, receives the sums this update used; with
+ * zero_sums != 0 (needs d_consumed) d_sums_counts is cleared afterwards, so a per-rank
+ * accumulator can be all-reduced in place every iteration and is empty again for the next
+ * assignment -- the per-iteration loop is then step, all-reduce, update, nothing else. */
+int llfe_kmeans_update(llfe_ctx* ctx, int k, uint64_t* d_sums_counts, float* d_centers, int max_iter, double eps,
+                       int32_t* d_state, double* d_shift, uint64_t* d_consumed_or_null, int zero_sums);
+
+/* ---- colour-histogram form of the per-pixel k-means (BASELINE config 5) ------
+ * A u8 image has at most 2^24 distinct colours and the centre update needs only exact
+ * integer sums, so the rows are streamed ONCE into a count table and the Lloyd iterations
+ * run over the distinct colours weighted by their pixel counts: the same labels, sums and
+ * centres as llfe_kmeans_pixels_step (color_extractor.py:189-196 applied per pixel), without
+ * re-reading the image every iteration. */
+
+/* d_hist[key] += number of pixels of colour key = (R << 16) + (G << 8) + B, 2^24 uint32
+ * bins (the caller zeroes the table once and all-reduces it across ranks with ncclSum). */
+int llfe_pixels_histogram(llfe_ctx* ctx, const uint8_t* d_bgr, size_t n_pixels, uint32_t* d_hist);
+
+/* Ordered compaction of the non-empty bins into (key, count) entries, key ascending =
+ * np.unique's (R, G, B) order.  The table is cut into blocks of 2048 keys; only blocks b with
+ * b % parts == part are emitted (rank r of a world of G passes part = r, parts = G).
+ * *d_n = number of entries of that part; at most `cap` entries are written (cap = 0 with NULL
+ * arrays just counts). */
+int llfe_histogram_compact(llfe_ctx* ctx, const uint32_t* d_hist, int part, int parts, uint32_t* d_keys_or_null,
+                           uint32_t* d_counts_or_null, size_t cap, int32_t* d_n);
+
+/* llfe_kmeans_pixels_step over (key, count) entries: nearest centre per distinct colour
+ * (cv2's float32 distance, first minimum), d_sums_counts += count * {R, G, B, 1}; optional
+ * one label byte per entry; same d_state_or_null convention. */
+int llfe_kmeans_hist_step(llfe_ctx* ctx, const uint32_t* d_keys, const uint32_t* d_counts, size_t n, int k,
+                          const float* d_centers, uint64_t* d_sums_counts, uint8_t* d_labels_or_null,
+                          const int32_t* d_state_or_null);
+
+/* d_lut[key] = label for every entry (d_lut: 2^24 bytes, zeroed by the caller; ranks
+ * all-reduce it with ncclSum since every colour belongs to exactly one part). */
+int llfe_hist_labels_to_lut(llfe_ctx* ctx, const uint32_t* d_keys, const uint8_t* d_labels, size_t n, uint8_t* d_lut);
+
+/* d_labels[p] = d_lut[colour of pixel p]: the per-pixel labels of the last assignment. */
+int llfe_pixels_lookup(llfe_ctx* ctx, const uint8_t* d_bgr, size_t n_pixels, const uint8_t* d_lut, uint8_t* d_labels);
 
 /* ---- fused service pipelines ---------------------------------------------- */
 

@@ -1,0 +1,502 @@
+// Colour-histogram form of the per-pixel k-means of ONE oversized image (BASELINE config 5).
+//
+// A u8 image has at most 2^24 distinct colours, and Lloyd's update only needs exact INTEGER sums
+// (SURVEY.md 8(e)): sum over pixels of x = sum over distinct colours of count * x.  So the rank's
+// rows are streamed ONCE into a 2^24-bin count table keyed (R << 16) + (G << 8) + B -- the key
+// order is np.unique's lexicographic (R, G, B) order -- the table is all-reduced once, compacted
+// into (key, count) entries, and every Lloyd iteration then touches the distinct colours only:
+// the same labels, the same exact sums, the same centres as the per-pixel pass of k_pixels.cu,
+// without re-reading the image.  Per-pixel labels, when asked for, are one lookup pass through a
+// 16 MiB colour -> label table.
+//
+// Work split across ranks: the table is cut into blocks of HB keys and block b belongs to part
+// b % parts, so each rank iterates over an interleaved share of the colour space and the K x 4
+// accumulator is all-reduced per iteration exactly as in the per-pixel form.
+#include "llfe_common.cuh"
+#include "llfe_device.cuh"
+#include "k_kmeans_shared.cuh"
+
+namespace {
+
+constexpr int HT = 256;
+constexpr unsigned FULL = 0xffffffffu;
+constexpr int HB = 2048;                  // keys per compaction block
+constexpr int NBLK = (1 << 24) / HB;      // 8192 blocks
+constexpr int EPT = HB / HT;              // table entries per thread in the compaction kernels
+
+typedef unsigned long long u64;
+
+// 16 pixels = 48 bytes in 12 words -> 16 keys; a BGR pixel's three bytes ARE the little-endian key
+__device__ __forceinline__ void keys16(const uint32_t (&w)[13], uint32_t (&key)[16]) {
+#pragma unroll
+    for (int j = 0; j < 16; ++j) {
+        const int bi = 3 * j;
+        key[j] = __funnelshift_r(w[bi >> 2], w[(bi >> 2) + 1], 8 * (bi & 3)) & 0xffffffu;
+    }
+}
+
+__device__ __forceinline__ void load48(const uint4* p, uint32_t (&w)[13]) {
+    const uint4 a = ld_stream(p), b = ld_stream(p + 1), c = ld_stream(p + 2);
+    w[0] = a.x; w[1] = a.y; w[2] = a.z; w[3] = a.w;
+    w[4] = b.x; w[5] = b.y; w[6] = b.z; w[7] = b.w;
+    w[8] = c.x; w[9] = c.y; w[10] = c.z; w[11] = c.w;
+    w[12] = 0u;
+}
+
+// count table: hist[key] += 1 for every pixel (runs of equal keys inside a thread's 16 pixels are merged)
+__global__ void __launch_bounds__(HT) k_hist_count(const uint8_t* __restrict__ bgr, size_t npix, int head,
+                                                   uint32_t* __restrict__ hist) {
+    const size_t nbulk = npix > (size_t)head ? (npix - head) / 16 : 0;
+    const uint4* base = reinterpret_cast<const uint4*>(bgr + (size_t)head * 3);
+    const size_t gstride = (size_t)gridDim.x * HT;
+    for (size_t g = blockIdx.x * (size_t)HT + threadIdx.x; g < nbulk; g += gstride) {
+        uint32_t w[13], key[16];
+        load48(base + 3 * g, w);
+        keys16(w, key);
+        uint32_t cur = key[0], run = 1;
+#pragma unroll
+        for (int j = 1; j < 16; ++j) {
+            if (key[j] == cur) {
+                ++run;
+            } else {
+                atomicAdd(hist + cur, run);
+                cur = key[j];
+                run = 1;
+            }
+        }
+        atomicAdd(hist + cur, run);
+    }
+    if (blockIdx.x == 0) {   // pixels before the first aligned group and after the last one
+        const size_t hd = npix < (size_t)head ? npix : (size_t)head;
+        const size_t tail0 = (size_t)head + nbulk * 16;
+        const size_t nrest = hd + (npix > tail0 ? npix - tail0 : 0);
+        for (size_t q = threadIdx.x; q < nrest; q += HT) {
+            const size_t p = q < hd ? q : tail0 + (q - hd);
+            atomicAdd(hist + (((uint32_t)bgr[3 * p + 2] << 16) | ((uint32_t)bgr[3 * p + 1] << 8) | bgr[3 * p]), 1u);
+        }
+    }
+}
+
+// ---- ordered compaction of the non-empty bins of the blocks that belong to `part` --------------
+__global__ void __launch_bounds__(HT) k_hist_blockcount(const uint32_t* __restrict__ hist, int part, int parts,
+                                                        uint32_t* __restrict__ bcount) {
+    const int b = blockIdx.x;
+    int c = 0;
+    if (b % parts == part) {
+        const uint4* p = reinterpret_cast<const uint4*>(hist + (size_t)b * HB) + threadIdx.x * (EPT / 4);
+#pragma unroll
+        for (int i = 0; i < EPT / 4; ++i) {
+            const uint4 v = p[i];
+            c += (v.x != 0u) + (v.y != 0u) + (v.z != 0u) + (v.w != 0u);
+        }
+    }
+    __shared__ int s[HT / 32];
+    const int ws = __reduce_add_sync(FULL, c);
+    if ((threadIdx.x & 31) == 0) s[threadIdx.x >> 5] = ws;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        int t = 0;
+        for (int i = 0; i < HT / 32; ++i) t += s[i];
+        bcount[b] = (uint32_t)t;
+    }
+}
+
+// exclusive scan of the NBLK block counts (one CTA), total -> *n_out
+__global__ void __launch_bounds__(1024) k_hist_blockscan(const uint32_t* __restrict__ bcount,
+                                                         uint32_t* __restrict__ boffs, int32_t* n_out) {
+    constexpr int PER = NBLK / 1024;
+    __shared__ uint32_t s_w[32];
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    uint32_t v[PER], t = 0;
+#pragma unroll
+    for (int i = 0; i < PER; ++i) {
+        v[i] = bcount[tid * PER + i];
+        t += v[i];
+    }
+    uint32_t inc = t;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        const uint32_t n = __shfl_up_sync(FULL, inc, o);
+        if (lane >= o) inc += n;
+    }
+    if (lane == 31) s_w[warp] = inc;
+    __syncthreads();
+    if (warp == 0) {
+        uint32_t x = s_w[lane], y = x;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const uint32_t n = __shfl_up_sync(FULL, y, o);
+            if (lane >= o) y += n;
+        }
+        s_w[lane] = y - x;   // exclusive warp offsets
+        if (lane == 31) *n_out = (int32_t)y;
+    }
+    __syncthreads();
+    uint32_t run = s_w[warp] + inc - t;
+#pragma unroll
+    for (int i = 0; i < PER; ++i) {
+        boffs[tid * PER + i] = run;
+        run += v[i];
+    }
+}
+
+__global__ void __launch_bounds__(HT) k_hist_emit(const uint32_t* __restrict__ hist, int part, int parts,
+                                                  const uint32_t* __restrict__ boffs, uint32_t* __restrict__ keys,
+                                                  uint32_t* __restrict__ counts, size_t cap) {
+    const int b = blockIdx.x;
+    if (b % parts != part) return;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    uint32_t v[EPT];
+    const uint4* p = reinterpret_cast<const uint4*>(hist + (size_t)b * HB) + tid * (EPT / 4);
+    int c = 0;
+#pragma unroll
+    for (int i = 0; i < EPT / 4; ++i) {
+        const uint4 q = p[i];
+        v[4 * i] = q.x; v[4 * i + 1] = q.y; v[4 * i + 2] = q.z; v[4 * i + 3] = q.w;
+        c += (q.x != 0u) + (q.y != 0u) + (q.z != 0u) + (q.w != 0u);
+    }
+    __shared__ int s_w[HT / 32];
+    int inc = c;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        const int n = __shfl_up_sync(FULL, inc, o);
+        if (lane >= o) inc += n;
+    }
+    if (lane == 31) s_w[warp] = inc;
+    __syncthreads();
+    int woff = 0;
+    for (int i = 0; i < warp; ++i) woff += s_w[i];
+    size_t pos = (size_t)boffs[b] + woff + inc - c;
+    const uint32_t key0 = (uint32_t)b * HB + tid * EPT;
+#pragma unroll
+    for (int i = 0; i < EPT; ++i) {
+        if (v[i] != 0u) {
+            if (pos < cap) {
+                keys[pos] = key0 + i;
+                counts[pos] = v[i];
+            }
+            ++pos;
+        }
+    }
+}
+
+__device__ __forceinline__ float fdist3(float r, float g, float b, const float* c) {
+    const float t0 = __fsub_rn(r, c[0]), t1 = __fsub_rn(g, c[1]), t2 = __fsub_rn(b, c[2]);
+    float d = __fmul_rn(t0, t0);
+    d = __fadd_rn(d, __fmul_rn(t1, t1));
+    d = __fadd_rn(d, __fmul_rn(t2, t2));
+    return d;
+}
+
+// one Lloyd assignment over (key, count) entries: cv2's float32 distance and first-minimum rule per
+// distinct colour, exact u64 sums weighted by the pixel counts
+__global__ void __launch_bounds__(HT) k_hist_step(const uint32_t* __restrict__ keys,
+                                                  const uint32_t* __restrict__ counts, size_t n, int K,
+                                                  const float* __restrict__ centers, u64* sums,
+                                                  uint8_t* __restrict__ labels_out,
+                                                  const int32_t* __restrict__ state) {
+    if (state && (state[1] | state[3])) return;
+    __shared__ float s_c[KMAX][3];
+    __shared__ u64 s_acc[HT / 32][KMAX][4];
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    for (int i = tid; i < K * 3; i += HT) (&s_c[0][0])[i] = centers[i];
+    for (int i = tid; i < (HT / 32) * KMAX * 4; i += HT) (&s_acc[0][0][0])[i] = 0ull;
+    __syncthreads();
+    const size_t stride = (size_t)gridDim.x * HT;
+    for (size_t i0 = blockIdx.x * (size_t)HT; i0 < n; i0 += stride) {   // block-uniform trip count
+        const size_t i = i0 + tid;
+        int bl = -1;
+        uint32_t r = 0, g = 0, b = 0, cnt = 0;
+        if (i < n) {
+            const uint32_t key = keys[i];
+            cnt = counts[i];
+            r = key >> 16;
+            g = (key >> 8) & 0xffu;
+            b = key & 0xffu;
+            const float fr = (float)r, fg = (float)g, fb = (float)b;
+            float bd = fdist3(fr, fg, fb, s_c[0]);
+            bl = 0;
+            for (int k = 1; k < K; ++k) {
+                const float d = fdist3(fr, fg, fb, s_c[k]);
+                if (d < bd) {   // strict: the lowest index wins ties
+                    bd = d;
+                    bl = k;
+                }
+            }
+            if (labels_out) labels_out[i] = (uint8_t)bl;
+        }
+        // counts reach 2^28: reduce the low and high 16 bits of count * channel separately (REDUX is 32-bit)
+        const uint32_t cl = cnt & 0xffffu, ch = cnt >> 16;
+        uint32_t todo = __ballot_sync(FULL, bl >= 0);
+        while (todo) {
+            const int k = __shfl_sync(FULL, bl, __ffs(todo) - 1);
+            const bool in = bl == k;
+            const uint32_t m = __ballot_sync(FULL, in);
+            const uint32_t l0 = in ? cl : 0u, h0 = in ? ch : 0u;
+            const u64 sr = (u64)__reduce_add_sync(FULL, l0 * r) + ((u64)__reduce_add_sync(FULL, h0 * r) << 16);
+            const u64 sg = (u64)__reduce_add_sync(FULL, l0 * g) + ((u64)__reduce_add_sync(FULL, h0 * g) << 16);
+            const u64 sb = (u64)__reduce_add_sync(FULL, l0 * b) + ((u64)__reduce_add_sync(FULL, h0 * b) << 16);
+            const u64 sn = (u64)__reduce_add_sync(FULL, l0) + ((u64)__reduce_add_sync(FULL, h0) << 16);
+            if (lane == 0) {
+                s_acc[warp][k][0] += sr;
+                s_acc[warp][k][1] += sg;
+                s_acc[warp][k][2] += sb;
+                s_acc[warp][k][3] += sn;
+            }
+            todo &= ~m;
+        }
+    }
+    __syncthreads();
+    for (int i = tid; i < K * 4; i += HT) {
+        u64 t = 0;
+        for (int w = 0; w < HT / 32; ++w) t += s_acc[w][i >> 2][i & 3];
+        if (t) atomicAdd(&sums[i], t);
+    }
+}
+
+// largest float32 distance to `base` among the colours assigned to `donor` (bits of a non-negative float
+// order like the float): the threshold that lets the pixel pass below skip almost every pixel
+__global__ void __launch_bounds__(HT) k_hist_farthest(const uint32_t* __restrict__ keys, size_t n, int K,
+                                                      const float* __restrict__ centers, int donor, float b0, float b1,
+                                                      float b2, uint32_t* out) {
+    __shared__ float s_c[KMAX][3];
+    for (int i = threadIdx.x; i < K * 3; i += HT) (&s_c[0][0])[i] = centers[i];
+    __syncthreads();
+    const float base[3] = {b0, b1, b2};
+    uint32_t best = 0u;
+    const size_t stride = (size_t)gridDim.x * HT;
+    for (size_t i = blockIdx.x * (size_t)HT + threadIdx.x; i < n; i += stride) {
+        const uint32_t key = keys[i];
+        const float fr = (float)(key >> 16), fg = (float)((key >> 8) & 0xffu), fb = (float)(key & 0xffu);
+        float bd = fdist3(fr, fg, fb, s_c[0]);
+        int bl = 0;
+        for (int k = 1; k < K; ++k) {
+            const float d = fdist3(fr, fg, fb, s_c[k]);
+            if (d < bd) {
+                bd = d;
+                bl = k;
+            }
+        }
+        if (bl != donor) continue;
+        best = max(best, __float_as_uint(fdist3(fr, fg, fb, base)));
+    }
+    best = __reduce_max_sync(FULL, best);
+    if ((threadIdx.x & 31) == 0 && best) atomicMax(out, best);
+}
+
+struct SkipList {
+    int n;
+    uint32_t idx[KMAX];
+};
+
+// farthest member (f32 distance to `base`) of cluster `donor` under the assignment to `centers`; result = max
+// over pixels of (dist bits << 32 | (pixel index + index_base)) + 1.  With want_bits != 0 only pixels at exactly
+// that float32 distance from `base` are looked at (the answer's distance is known from the distinct colours).
+__device__ __forceinline__ void farthest_px(uint32_t r, uint32_t g, uint32_t b, size_t gidx, const float (*s_c)[3], int K,
+                                            int donor, const float* base, uint32_t want_bits, const SkipList& skip,
+                                            u64& best) {
+    const float fr = (float)r, fg = (float)g, fb = (float)b;
+    const uint32_t db = __float_as_uint(fdist3(fr, fg, fb, base));
+    if (want_bits && db != want_bits) return;
+    float bd = fdist3(fr, fg, fb, s_c[0]);
+    int bl = 0;
+    for (int k = 1; k < K; ++k) {
+        const float d = fdist3(fr, fg, fb, s_c[k]);
+        if (d < bd) {
+            bd = d;
+            bl = k;
+        }
+    }
+    if (bl != donor) return;
+    for (int j = 0; j < skip.n; ++j)   // pixels an earlier repair of this update already moved out of the donor
+        if (skip.idx[j] == (uint32_t)gidx) return;
+    const u64 cand = (((u64)db << 32) | (uint32_t)gidx) + 1ull;
+    best = cand > best ? cand : best;
+}
+
+__global__ void __launch_bounds__(HT) k_pixels_farthest(const uint8_t* __restrict__ bgr, size_t npix, int head, int K,
+                                                        const float* __restrict__ centers, int donor, float b0,
+                                                        float b1, float b2, uint32_t index_base, SkipList skip,
+                                                        uint32_t want_bits, u64* out) {
+    __shared__ float s_c[KMAX][3];
+    for (int i = threadIdx.x; i < K * 3; i += HT) (&s_c[0][0])[i] = centers[i];
+    __syncthreads();
+    const float base[3] = {b0, b1, b2};
+    u64 best = 0ull;
+    const size_t nbulk = npix > (size_t)head ? (npix - head) / 16 : 0;
+    const uint4* src = reinterpret_cast<const uint4*>(bgr + (size_t)head * 3);
+    const size_t gstride = (size_t)gridDim.x * HT;
+    for (size_t g = blockIdx.x * (size_t)HT + threadIdx.x; g < nbulk; g += gstride) {
+        uint32_t w[13], key[16];
+        load48(src + 3 * g, w);
+        keys16(w, key);
+#pragma unroll
+        for (int j = 0; j < 16; ++j)
+            farthest_px(key[j] >> 16, (key[j] >> 8) & 0xffu, key[j] & 0xffu, (size_t)head + 16 * g + j + index_base, s_c,
+                        K, donor, base, want_bits, skip, best);
+    }
+    if (blockIdx.x == 0) {
+        const size_t hd = npix < (size_t)head ? npix : (size_t)head;
+        const size_t tail0 = (size_t)head + nbulk * 16;
+        const size_t nrest = hd + (npix > tail0 ? npix - tail0 : 0);
+        for (size_t q = threadIdx.x; q < nrest; q += HT) {
+            const size_t p = q < hd ? q : tail0 + (q - hd);
+            farthest_px(bgr[3 * p + 2], bgr[3 * p + 1], bgr[3 * p], p + index_base, s_c, K, donor, base, want_bits, skip,
+                        best);
+        }
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        const u64 nb = __shfl_xor_sync(FULL, best, o);
+        best = nb > best ? nb : best;
+    }
+    if ((threadIdx.x & 31) == 0 && best) atomicMax(out, best);
+}
+
+__global__ void __launch_bounds__(HT) k_hist_lut(const uint32_t* __restrict__ keys, const uint8_t* __restrict__ labels,
+                                                 size_t n, uint8_t* __restrict__ lut) {
+    const size_t stride = (size_t)gridDim.x * HT;
+    for (size_t i = blockIdx.x * (size_t)HT + threadIdx.x; i < n; i += stride) lut[keys[i]] = labels[i];
+}
+
+// per-pixel labels through the colour -> label table
+__global__ void __launch_bounds__(HT) k_pixels_lookup(const uint8_t* __restrict__ bgr, size_t npix, int head,
+                                                      const uint8_t* __restrict__ lut, uint8_t* __restrict__ labels) {
+    const size_t nbulk = npix > (size_t)head ? (npix - head) / 16 : 0;
+    const uint4* base = reinterpret_cast<const uint4*>(bgr + (size_t)head * 3);
+    const size_t gstride = (size_t)gridDim.x * HT;
+    for (size_t g = blockIdx.x * (size_t)HT + threadIdx.x; g < nbulk; g += gstride) {
+        uint32_t w[13], key[16], o[4] = {0u, 0u, 0u, 0u};
+        load48(base + 3 * g, w);
+        keys16(w, key);
+#pragma unroll
+        for (int j = 0; j < 16; ++j) o[j >> 2] |= (uint32_t)__ldg(lut + key[j]) << (8 * (j & 3));
+        uint8_t* dst = labels + head + 16 * g;
+        if (((uintptr_t)dst & 15) == 0) {
+            *reinterpret_cast<uint4*>(dst) = make_uint4(o[0], o[1], o[2], o[3]);
+        } else {
+#pragma unroll
+            for (int j = 0; j < 16; ++j) dst[j] = (uint8_t)(o[j >> 2] >> (8 * (j & 3)));
+        }
+    }
+    if (blockIdx.x == 0) {
+        const size_t hd = npix < (size_t)head ? npix : (size_t)head;
+        const size_t tail0 = (size_t)head + nbulk * 16;
+        const size_t nrest = hd + (npix > tail0 ? npix - tail0 : 0);
+        for (size_t q = threadIdx.x; q < nrest; q += HT) {
+            const size_t p = q < hd ? q : tail0 + (q - hd);
+            labels[p] = lut[((uint32_t)bgr[3 * p + 2] << 16) | ((uint32_t)bgr[3 * p + 1] << 8) | bgr[3 * p]];
+        }
+    }
+}
+
+// pixels before the first 16-byte boundary that is also a pixel boundary: 3 h = -addr (mod 16)
+inline int head_pixels(const void* p) { return (int)(((16 - ((uintptr_t)p & 15)) & 15) * 11 % 16); }
+
+inline unsigned stream_grid(const llfe_ctx* ctx, size_t items_per_thread_groups) {
+    const size_t want = ceil_div_sz(items_per_thread_groups, HT);
+    const size_t cap = (size_t)ctx->sm_count * 16;
+    return (unsigned)(want < 1 ? 1 : (want > cap ? cap : want));
+}
+
+}  // namespace
+
+extern "C" int llfe_pixels_histogram(llfe_ctx* ctx, const uint8_t* d_bgr, size_t n_pixels, uint32_t* d_hist) {
+    LLFE_CHECK_ARG(ctx != nullptr && d_hist != nullptr && (d_bgr != nullptr || n_pixels == 0));
+    if (n_pixels == 0) return LLFE_OK;
+    LLFE_KERNEL(ctx, "k_hist_count");
+    k_hist_count<<<stream_grid(ctx, n_pixels / 16 + 1), HT, 0, ctx->stream>>>(d_bgr, n_pixels, head_pixels(d_bgr), d_hist);
+    LLFE_LAUNCHED(ctx);
+    return LLFE_OK;
+}
+
+extern "C" int llfe_histogram_compact(llfe_ctx* ctx, const uint32_t* d_hist, int part, int parts, uint32_t* d_keys_or_null,
+                                      uint32_t* d_counts_or_null, size_t cap, int32_t* d_n) {
+    LLFE_CHECK_ARG(ctx != nullptr && d_hist != nullptr && d_n != nullptr && parts >= 1 && part >= 0 && part < parts);
+    LLFE_CHECK_ARG(cap == 0 || (d_keys_or_null != nullptr && d_counts_or_null != nullptr));
+    void* ws = nullptr;
+    LLFE_TRY(llfe_workspace(ctx, 2 * WsCarver::need(NBLK * sizeof(uint32_t)), &ws));
+    WsCarver carve(ws);
+    uint32_t* bcount = carve.take<uint32_t>(NBLK);
+    uint32_t* boffs = carve.take<uint32_t>(NBLK);
+    LLFE_KERNEL(ctx, "k_hist_blockcount");
+    k_hist_blockcount<<<NBLK, HT, 0, ctx->stream>>>(d_hist, part, parts, bcount);
+    LLFE_LAUNCHED(ctx);
+    LLFE_KERNEL(ctx, "k_hist_blockscan");
+    k_hist_blockscan<<<1, 1024, 0, ctx->stream>>>(bcount, boffs, d_n);
+    LLFE_LAUNCHED(ctx);
+    if (cap > 0) {
+        LLFE_KERNEL(ctx, "k_hist_emit");
+        k_hist_emit<<<NBLK, HT, 0, ctx->stream>>>(d_hist, part, parts, boffs, d_keys_or_null, d_counts_or_null, cap);
+        LLFE_LAUNCHED(ctx);
+    }
+    return LLFE_OK;
+}
+
+extern "C" int llfe_kmeans_hist_step(llfe_ctx* ctx, const uint32_t* d_keys, const uint32_t* d_counts, size_t n, int k,
+                                     const float* d_centers, uint64_t* d_sums_counts, uint8_t* d_labels_or_null,
+                                     const int32_t* d_state_or_null) {
+    LLFE_CHECK_ARG(ctx != nullptr && d_centers != nullptr && d_sums_counts != nullptr && k >= 1 && k <= KMAX);
+    LLFE_CHECK_ARG(n == 0 || (d_keys != nullptr && d_counts != nullptr));
+    if (n == 0) return LLFE_OK;
+    const size_t want = ceil_div_sz(n, HT);
+    const size_t cap = (size_t)ctx->sm_count * 8;
+    LLFE_KERNEL(ctx, "k_hist_step");
+    k_hist_step<<<(unsigned)(want > cap ? cap : want), HT, 0, ctx->stream>>>(
+        d_keys, d_counts, n, k, d_centers, (u64*)d_sums_counts, d_labels_or_null, d_state_or_null);
+    LLFE_LAUNCHED(ctx);
+    return LLFE_OK;
+}
+
+extern "C" int llfe_hist_labels_to_lut(llfe_ctx* ctx, const uint32_t* d_keys, const uint8_t* d_labels, size_t n,
+                                       uint8_t* d_lut) {
+    LLFE_CHECK_ARG(ctx != nullptr && d_lut != nullptr && (n == 0 || (d_keys != nullptr && d_labels != nullptr)));
+    if (n == 0) return LLFE_OK;
+    LLFE_KERNEL(ctx, "k_hist_lut");
+    k_hist_lut<<<stream_grid(ctx, n), HT, 0, ctx->stream>>>(d_keys, d_labels, n, d_lut);
+    LLFE_LAUNCHED(ctx);
+    return LLFE_OK;
+}
+
+extern "C" int llfe_pixels_lookup(llfe_ctx* ctx, const uint8_t* d_bgr, size_t n_pixels, const uint8_t* d_lut,
+                                  uint8_t* d_labels) {
+    LLFE_CHECK_ARG(ctx != nullptr && d_lut != nullptr && (n_pixels == 0 || (d_bgr != nullptr && d_labels != nullptr)));
+    if (n_pixels == 0) return LLFE_OK;
+    LLFE_KERNEL(ctx, "k_pixels_lookup");
+    k_pixels_lookup<<<stream_grid(ctx, n_pixels / 16 + 1), HT, 0, ctx->stream>>>(d_bgr, n_pixels, head_pixels(d_bgr), d_lut,
+                                                                                 d_labels);
+    LLFE_LAUNCHED(ctx);
+    return LLFE_OK;
+}
+
+extern "C" int llfe_kmeans_hist_farthest(llfe_ctx* ctx, const uint32_t* d_keys, size_t n, int k, const float* d_centers,
+                                         int donor, const float* h_base3, uint32_t* d_out_bits) {
+    LLFE_CHECK_ARG(ctx != nullptr && d_centers != nullptr && h_base3 != nullptr && d_out_bits != nullptr);
+    LLFE_CHECK_ARG(k >= 1 && k <= KMAX && donor >= 0 && donor < k && (n == 0 || d_keys != nullptr));
+    if (n == 0) return LLFE_OK;
+    LLFE_KERNEL(ctx, "k_hist_farthest");
+    k_hist_farthest<<<stream_grid(ctx, n), HT, 0, ctx->stream>>>(d_keys, n, k, d_centers, donor, h_base3[0], h_base3[1],
+                                                                 h_base3[2], d_out_bits);
+    LLFE_LAUNCHED(ctx);
+    return LLFE_OK;
+}
+
+extern "C" int llfe_kmeans_pixels_farthest(llfe_ctx* ctx, const uint8_t* d_bgr, size_t n_pixels, int k,
+                                           const float* d_centers, int donor, const float* h_base3,
+                                           uint32_t index_base, const uint32_t* h_skip, int n_skip, uint32_t want_dist_bits,
+                                           uint64_t* d_out) {
+    LLFE_CHECK_ARG(ctx != nullptr && d_centers != nullptr && h_base3 != nullptr && d_out != nullptr);
+    LLFE_CHECK_ARG(n_pixels == 0 || d_bgr != nullptr);
+    LLFE_CHECK_ARG(n_skip >= 0 && n_skip <= KMAX && (n_skip == 0 || h_skip != nullptr));
+    SkipList skip;
+    skip.n = n_skip;
+    for (int j = 0; j < n_skip; ++j) skip.idx[j] = h_skip[j];
+    LLFE_CHECK_ARG(k >= 1 && k <= KMAX && donor >= 0 && donor < k && n_pixels + index_base <= 0xffffffffull);
+    if (n_pixels == 0) return LLFE_OK;
+    LLFE_KERNEL(ctx, "k_pixels_farthest");
+    k_pixels_farthest<<<stream_grid(ctx, n_pixels / 16 + 1), HT, 0, ctx->stream>>>(
+        d_bgr, n_pixels, head_pixels(d_bgr), k, d_centers, donor, h_base3[0], h_base3[1], h_base3[2], index_base, skip,
+        want_dist_bits, (u64*)d_out);
+    LLFE_LAUNCHED(ctx);
+    return LLFE_OK;
+}

@@ -217,71 +217,58 @@ __global__ void __launch_bounds__(PT, 2) k_pixels_step(const uint8_t* __restrict
     }
 }
 
-struct SkipList {
-    int n;
-    uint32_t idx[KMAX];
-};
-
-// farthest member (f32 distance to `base`) of cluster `donor` under the assignment to
-// `centers`; result = max over pixels of (dist bits << 32 | (pixel index + index_base)) + 1
-__global__ void __launch_bounds__(PT) k_pixels_farthest(const uint8_t* __restrict__ bgr, size_t npix, int K,
-                                                        const float* __restrict__ centers, int donor, float b0,
-                                                        float b1, float b2, uint32_t index_base, SkipList skip,
-                                                        unsigned long long* out) {
-    __shared__ float s_c[KMAX][3];
-    const int tid = threadIdx.x;
-    for (int i = tid; i < K * 3; i += PT) (&s_c[0][0])[i] = centers[i];
-    __syncthreads();
-    const float base[3] = {b0, b1, b2};
-    unsigned long long best = 0ull;
-    const size_t stride = (size_t)gridDim.x * PT;
-    for (size_t p = blockIdx.x * (size_t)PT + tid; p < npix; p += stride) {
-        float fb = (float)bgr[3 * p], fg = (float)bgr[3 * p + 1], fr = (float)bgr[3 * p + 2];
-        if (nearest_scalar(fr, fg, fb, s_c, K) != donor) continue;
-        bool skipped = false;  // pixels an earlier repair of this update already moved out of the donor
-        for (int j = 0; j < skip.n; ++j) skipped |= skip.idx[j] == (uint32_t)(p + index_base);
-        if (skipped) continue;
-        float d = fdist3(fr, fg, fb, base);
-        unsigned long long cand = (((unsigned long long)__float_as_uint(d) << 32) | (uint32_t)(p + index_base)) + 1ull;
-        best = cand > best ? cand : best;
-    }
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) {
-        unsigned long long n = __shfl_xor_sync(FULL, best, o);
-        best = n > best ? n : best;
-    }
-    if ((tid & 31) == 0 && best) atomicMax(out, best);
-}
-
 // centres from (all-reduced) sums; shift; iteration bookkeeping (state: iter, done, n_empty)
-__global__ void k_pixels_update(int K, const unsigned long long* __restrict__ sums, float* centers, int max_iter,
-                                double eps2, int32_t* state, double* shift_out) {
-    if (threadIdx.x != 0 || blockIdx.x != 0) return;
-    if (state[1] | state[3]) return;  // converged / frozen: later iterations of an unsynchronised batch are no-ops
-    int n_empty = 0;
-    for (int k = 0; k < K; ++k) n_empty += sums[4 * k + 3] == 0;
-    state[2] = n_empty;
+//
+// `copy_dst` (optional) receives the sums this update consumed and `zero_src` clears `sums` afterwards: with both,
+// the per-rank accumulator can be all-reduced IN PLACE every iteration -- it is zero again before the next
+// assignment adds to it, stays zero through the no-op iterations of a batch, and the totals survive in copy_dst.
+__global__ void __launch_bounds__(32) k_pixels_update(int K, unsigned long long* sums, float* centers, int max_iter,
+                                                      double eps2, int32_t* state, double* shift_out,
+                                                      unsigned long long* copy_dst, int zero_src) {
+    const int lane = threadIdx.x;   // one warp, lane = cluster (K <= 32)
+    const int blocked = state[1] | state[3];
+    const int it0 = state[0];
+    __syncwarp();
+    if (blocked) return;  // converged / frozen: later iterations of an unsynchronised batch are no-ops
+    unsigned long long s[4] = {0ull, 0ull, 0ull, 1ull};
+    if (lane < K) {
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            s[j] = sums[4 * lane + j];
+            if (copy_dst) {
+                copy_dst[4 * lane + j] = s[j];
+                if (zero_src) sums[4 * lane + j] = 0ull;
+            }
+        }
+    }
+    const int n_empty = __popc(__ballot_sync(FULL, s[3] == 0ull));
     if (n_empty) {
-        state[3] = 1;  // freeze: the host repairs the sums, clears state[2..3] and calls update again
+        if (lane == 0) {
+            state[2] = n_empty;
+            state[3] = 1;  // freeze: the host repairs the sums, clears state[2..3] and calls update again
+        }
         return;
     }
-    double shift = 0.0;
-    for (int k = 0; k < K; ++k) {
-        double s = 0.0;
+    double sh = 0.0;
+    if (lane < K) {
+#pragma unroll
         for (int j = 0; j < 3; ++j) {
-            float c = (float)((double)sums[4 * k + j] / (double)sums[4 * k + 3]);
-            double t = (double)__fsub_rn(c, centers[3 * k + j]);
-            s = __dadd_rn(s, __dmul_rn(t, t));
-            centers[3 * k + j] = c;
+            const float c = (float)((double)s[j] / (double)s[3]);
+            const double t = (double)__fsub_rn(c, centers[3 * lane + j]);
+            sh = __dadd_rn(sh, __dmul_rn(t, t));
+            centers[3 * lane + j] = c;
         }
-        shift = fmax(shift, s);
     }
-    const int it0 = state[0];
-    const int it = it0 + 1;
-    state[0] = it;
-    const int last_it = max_iter > 2 ? max_iter : 2;
-    state[1] = (it == last_it) || (it0 > 0 && shift <= eps2);
-    if (shift_out) *shift_out = shift;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) sh = fmax(sh, __shfl_xor_sync(FULL, sh, o));
+    if (lane == 0) {
+        const int it = it0 + 1;
+        const int last_it = max_iter > 2 ? max_iter : 2;
+        state[0] = it;
+        state[2] = 0;
+        state[1] = (it == last_it) || (it0 > 0 && sh <= eps2);
+        if (shift_out) *shift_out = sh;
+    }
 }
 
 // zero the per-rank accumulator for the next iteration -- unless the loop is converged or frozen
@@ -319,33 +306,15 @@ extern "C" int llfe_kmeans_pixels_step(llfe_ctx* ctx, const uint8_t* d_bgr, size
     return LLFE_OK;
 }
 
-extern "C" int llfe_kmeans_pixels_farthest(llfe_ctx* ctx, const uint8_t* d_bgr, size_t n_pixels, int k,
-                                           const float* d_centers, int donor, const float* h_base3,
-                                           uint32_t index_base, const uint32_t* h_skip, int n_skip, uint64_t* d_out) {
-    LLFE_CHECK_ARG(ctx != nullptr && d_bgr != nullptr && d_centers != nullptr && h_base3 != nullptr && d_out != nullptr);
-    LLFE_CHECK_ARG(n_skip >= 0 && n_skip <= KMAX && (n_skip == 0 || h_skip != nullptr));
-    SkipList skip;
-    skip.n = n_skip;
-    for (int j = 0; j < n_skip; ++j) skip.idx[j] = h_skip[j];
-    LLFE_CHECK_ARG(k >= 1 && k <= KMAX && donor >= 0 && donor < k && n_pixels + index_base <= 0xffffffffull);
-    if (n_pixels == 0) return LLFE_OK;
-    size_t want = ceil_div_sz(n_pixels, PT * 8);
-    size_t cap = (size_t)ctx->sm_count * 8;
-    unsigned grid = (unsigned)(want < 1 ? 1 : (want > cap ? cap : want));
-    LLFE_KERNEL(ctx, "k_pixels_farthest");
-    k_pixels_farthest<<<grid, PT, 0, ctx->stream>>>(d_bgr, n_pixels, k, d_centers, donor, h_base3[0], h_base3[1],
-                                                    h_base3[2], index_base, skip, (unsigned long long*)d_out);
-    LLFE_LAUNCHED(ctx);
-    return LLFE_OK;
-}
-
-extern "C" int llfe_kmeans_update(llfe_ctx* ctx, int k, const uint64_t* d_sums_counts, float* d_centers, int max_iter,
-                                  double eps, int32_t* d_state, double* d_shift) {
+extern "C" int llfe_kmeans_update(llfe_ctx* ctx, int k, uint64_t* d_sums_counts, float* d_centers, int max_iter,
+                                  double eps, int32_t* d_state, double* d_shift, uint64_t* d_consumed_or_null,
+                                  int zero_sums) {
     LLFE_CHECK_ARG(ctx != nullptr && d_sums_counts != nullptr && d_centers != nullptr && d_state != nullptr);
-    LLFE_CHECK_ARG(k >= 1 && k <= KMAX && max_iter >= 1);
+    LLFE_CHECK_ARG(k >= 1 && k <= KMAX && max_iter >= 1 && (!zero_sums || d_consumed_or_null != nullptr));
+    LLFE_CHECK_ARG(d_consumed_or_null != d_sums_counts);
     LLFE_KERNEL(ctx, "k_pixels_update");
-    k_pixels_update<<<1, 32, 0, ctx->stream>>>(k, (const unsigned long long*)d_sums_counts, d_centers, max_iter, eps * eps,
-                                               d_state, d_shift);
+    k_pixels_update<<<1, 32, 0, ctx->stream>>>(k, (unsigned long long*)d_sums_counts, d_centers, max_iter, eps * eps,
+                                               d_state, d_shift, (unsigned long long*)d_consumed_or_null, zero_sums);
     LLFE_LAUNCHED(ctx);
     return LLFE_OK;
 }

@@ -79,10 +79,19 @@ class PixelKMeans:
     shift test max_k |c - old|^2 <= eps^2 from iteration 1 on, cv2's empty-cluster repair.
     """
 
-    def __init__(self, backend, group=None, iterations_per_sync: int = 4):
+    def __init__(self, backend, group=None, iterations_per_sync: int = 8, histogram: bool = True):
         self.be = backend
         self.group = group
         self.iterations_per_sync = iterations_per_sync   # iterations enqueued per host look at the device state
+        # histogram=True: stream the rows once into a 2^24-bin colour count table, all-reduce it, and iterate
+        # over this rank's share of the DISTINCT colours weighted by their counts (identical labels, sums and
+        # centres; the image is not re-read every iteration).  False: every iteration re-reads the rank's rows.
+        self.histogram = histogram
+
+    def _rank_world(self) -> tuple[int, int]:
+        if dist.is_available() and dist.is_initialized():
+            return dist.get_rank(self.group), dist.get_world_size(self.group)
+        return 0, 1
 
     # -- collectives (identity in a single process) ----------------------------------------
     def _allreduce(self, t: torch.Tensor, op) -> None:
@@ -105,34 +114,61 @@ class PixelKMeans:
         npix = bgr_rows.numel() // 3
         labels = torch.empty((npix,), dtype=torch.uint8, device=dev) if want_labels else None
         flat = bgr_rows.reshape(-1, 3)
+        if self.histogram:
+            rank, ws = self._rank_world()
+            hist = torch.zeros((1 << 24,), dtype=torch.int32, device=dev)
+            be.pixels_histogram(bgr_rows, hist)
+            self._allreduce(hist, dist.ReduceOp.SUM)            # once: 64 MiB
+            keys, counts = be.histogram_compact(hist, rank, ws)  # this rank's interleaved share of the colours
+            del hist
+            entry_labels = torch.empty((keys.numel(),), dtype=torch.uint8, device=dev) if want_labels else None
+
+            def step():
+                be.kmeans_hist_step(keys, counts, centers, local, entry_labels, state)
+        else:
+            def step():
+                be.kmeans_pixels_step(bgr_rows, centers, local, labels, state)
+
+        overrides: list[tuple[int, int]] = []   # (local pixel, label) set by the repair after the last assignment
+        overrides_iter = -1
         batch = max(1, int(self.iterations_per_sync))
         while True:
-            # `batch` iterations are enqueued back to back; once the device state says converged (or frozen for
-            # a repair) the remaining ones are no-ops on every rank alike: the partial sums are not re-zeroed,
-            # so the out-of-place all-reduce just reproduces the same totals.
+            # `batch` iterations are enqueued back to back: assignment into the per-rank accumulator, in-place
+            # all-reduce, update (which keeps the totals in `sums` and clears the accumulator).  Once the device
+            # state says converged (or frozen for a repair) the remaining ones are no-ops on every rank alike.
             for _ in range(batch):
-                be.kmeans_pixels_zero(local, state)
-                be.kmeans_pixels_step(bgr_rows, centers, local, labels, state)
-                sums.copy_(local)
-                self._allreduce(sums, dist.ReduceOp.SUM)
-                be.kmeans_update(sums, centers, state, shift, max_iter=max_iter, eps=eps)
+                step()
+                self._allreduce(local, dist.ReduceOp.SUM)
+                be.kmeans_update(local, centers, state, shift, max_iter=max_iter, eps=eps, consumed=sums,
+                                 zero_sums=True)
             st = state.tolist()          # the one host synchronisation per batch
             if st[3]:
-                self._repair(flat, centers, sums, far, index_base, npix, labels)
+                overrides = self._repair(flat, centers, sums, far, index_base, npix, None if self.histogram else labels,
+                                         keys if self.histogram else None)
                 state[2:4] = 0
                 be.kmeans_update(sums, centers, state, shift, max_iter=max_iter, eps=eps)
                 st = state.tolist()
+                overrides_iter = st[0]
                 if st[3]:
                     raise RuntimeError("k-means: an empty cluster survived the repair (fewer distinct pixels than k?)")
             if st[1]:
+                if self.histogram and want_labels:
+                    lut = torch.zeros((1 << 24,), dtype=torch.uint8, device=dev)
+                    be.hist_labels_to_lut(keys, entry_labels, lut)
+                    self._allreduce(lut, dist.ReduceOp.SUM)   # every colour belongs to exactly one rank's share
+                    be.pixels_lookup(bgr_rows, lut, labels)
+                    if overrides_iter == st[0]:               # the repair came after the last assignment
+                        for li, j in overrides:
+                            labels[li] = j
                 return PixelKMeansResult(centers, st[0], sums, float(shift.item()), labels)
 
-    def _repair(self, flat, centers, sums, far, index_base, npix, labels) -> None:
+    def _repair(self, flat, centers, sums, far, index_base, npix, labels, keys=None) -> list[tuple[int, int]]:
         """cv2's empty-cluster repair on the all-reduced sums: for each empty cluster (in order) the
         biggest cluster (first max) gives up its member farthest from its provisional mean (last max
         wins => highest global pixel index).  `centers` still holds the centres the labels came from."""
         k = centers.shape[0]
         moved: list[int] = []
+        overrides: list[tuple[int, int]] = []
         host = sums.cpu()
         assigned_from = centers.clone()  # `centers` gets the donors' provisional means below
         for j in range(k):
@@ -144,11 +180,24 @@ class PixelKMeans:
                 if int(cnt[donor]) < int(cnt[k1]):
                     donor = k1
             base = (host[donor, :3].to(torch.float64) / float(cnt[donor])).to(torch.float32)
-            far.zero_()
-            self.be.kmeans_pixels_farthest(flat, assigned_from, donor, [float(v) for v in base], index_base, far,
-                                           skip=moved)
-            self._allreduce(far, dist.ReduceOp.MAX)
-            code = int(far.item())
+            base3 = [float(v) for v in base]
+            dmin = 0
+            if keys is not None:
+                # the farthest COLOUR of the donor comes from the distinct-colour list; the pass over the rows then
+                # only has to find the last pixel at exactly that distance from `base`
+                bits = torch.zeros((1,), dtype=torch.int32, device=flat.device)
+                self.be.kmeans_hist_farthest(keys, assigned_from, donor, base3, bits)
+                self._allreduce(bits, dist.ReduceOp.MAX)
+                dmin = int(bits.item())
+            code = 0
+            for threshold in ((dmin, 0) if dmin else (0,)):   # 0: every pixel of that colour was already moved
+                far.zero_()
+                self.be.kmeans_pixels_farthest(flat, assigned_from, donor, base3, index_base, far, skip=moved,
+                                               want_dist_bits=threshold)
+                self._allreduce(far, dist.ReduceOp.MAX)
+                code = int(far.item())
+                if code:
+                    break
             if code == 0:
                 raise RuntimeError("k-means repair: the donor cluster has no member")
             gidx = (code - 1) & 0xFFFFFFFF
@@ -157,6 +206,7 @@ class PixelKMeans:
             li = gidx - index_base
             if 0 <= li < npix:
                 px = flat[li].flip(0).to(torch.int64)
+                overrides.append((li, j))
                 if labels is not None:
                     labels[li] = j
             self._allreduce(px, dist.ReduceOp.SUM)
@@ -169,3 +219,4 @@ class PixelKMeans:
             # OpenCV stores the donor's provisional mean in old_centers[donor]: the shift is measured from it
             centers[donor] = base.to(centers.device)
         sums.copy_(host)
+        return overrides

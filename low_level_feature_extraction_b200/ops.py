@@ -335,14 +335,58 @@ class Engine:
         self.ctx.call("llfe_kmeans_pixels_zero", sums.shape[0], sums, state)
 
     def kmeans_update(self, sums: torch.Tensor, centers: torch.Tensor, state: torch.Tensor, shift: torch.Tensor,
-                      max_iter: int = 200, eps: float = 0.2):
+                      max_iter: int = 200, eps: float = 0.2, consumed: torch.Tensor | None = None,
+                      zero_sums: bool = False):
+        """Centres from the (all-reduced) sums + convergence bookkeeping in `state`.  `consumed` receives the
+        sums that were used; zero_sums clears `sums` afterwards (in-place all-reduce loop, see llfe.h)."""
         self._bind()
-        self.ctx.call("llfe_kmeans_update", centers.shape[0], sums, centers, int(max_iter), float(eps), state, shift)
+        self.ctx.call("llfe_kmeans_update", centers.shape[0], sums, centers, int(max_iter), float(eps), state, shift,
+                      consumed, int(bool(zero_sums)))
+
+    # ---- colour-histogram form of the per-pixel k-means (config 5) ----------------------------------
+    HIST_BINS = 1 << 24
+
+    def pixels_histogram(self, bgr_rows: torch.Tensor, hist: torch.Tensor):
+        """hist (2^24,) int32 += pixel count per colour key (R << 16) + (G << 8) + B."""
+        x = bgr_rows.contiguous()
+        assert hist.numel() == self.HIST_BINS and hist.dtype == torch.int32 and hist.is_contiguous()
+        self._bind()
+        self.ctx.call("llfe_pixels_histogram", x, x.numel() // 3, hist)
+
+    def histogram_compact(self, hist: torch.Tensor, part: int = 0, parts: int = 1):
+        """(keys, counts): the non-empty bins of this part's interleaved blocks, key ascending (int32 tensors)."""
+        self._bind()
+        n = torch.zeros((1,), dtype=torch.int32, device=hist.device)
+        self.ctx.call("llfe_histogram_compact", hist, int(part), int(parts), None, None, 0, n)
+        u = int(n.item())
+        keys = torch.empty((u,), dtype=torch.int32, device=hist.device)
+        counts = torch.empty((u,), dtype=torch.int32, device=hist.device)
+        if u:
+            self.ctx.call("llfe_histogram_compact", hist, int(part), int(parts), keys, counts, u, n)
+        return keys, counts
+
+    def kmeans_hist_step(self, keys: torch.Tensor, counts: torch.Tensor, centers: torch.Tensor, sums: torch.Tensor,
+                         labels: torch.Tensor | None = None, state: torch.Tensor | None = None):
+        """sums (k,4) int64 += count * {R, G, B, 1} per cluster over the (key, count) entries."""
+        self._bind()
+        self.ctx.call("llfe_kmeans_hist_step", keys, counts, keys.numel(), centers.shape[0], centers, sums, labels,
+                      state)
+
+    def hist_labels_to_lut(self, keys: torch.Tensor, labels: torch.Tensor, lut: torch.Tensor):
+        assert lut.numel() == self.HIST_BINS and lut.dtype == torch.uint8
+        self._bind()
+        self.ctx.call("llfe_hist_labels_to_lut", keys, labels, keys.numel(), lut)
+
+    def pixels_lookup(self, bgr_rows: torch.Tensor, lut: torch.Tensor, labels: torch.Tensor):
+        x = bgr_rows.contiguous()
+        self._bind()
+        self.ctx.call("llfe_pixels_lookup", x, x.numel() // 3, lut, labels)
 
     def kmeans_pixels_farthest(self, bgr_rows: torch.Tensor, centers: torch.Tensor, donor: int, base3,
-                               index_base: int, out: torch.Tensor, skip=()):
+                               index_base: int, out: torch.Tensor, skip=(), want_dist_bits: int = 0):
         """out[0] = max(out[0], code of the donor member farthest from base3); skip: global pixel
-        indices to ignore (already moved by earlier repairs of the same update)."""
+        indices to ignore (already moved by earlier repairs of the same update); want_dist_bits != 0: float32
+        bits of the answer's distance when already known -- only pixels at exactly that distance are considered."""
         import ctypes
 
         x = bgr_rows.contiguous()
@@ -350,7 +394,17 @@ class Engine:
         sk = (ctypes.c_uint32 * max(1, len(skip)))(*[int(v) for v in skip])
         self._bind()
         self.ctx.call("llfe_kmeans_pixels_farthest", x, x.numel() // 3, centers.shape[0], centers, int(donor),
-                      ctypes.addressof(arr), int(index_base), ctypes.addressof(sk), len(skip), out)
+                      ctypes.addressof(arr), int(index_base), ctypes.addressof(sk), len(skip), int(want_dist_bits), out)
+
+    def kmeans_hist_farthest(self, keys: torch.Tensor, centers: torch.Tensor, donor: int, base3, out_bits: torch.Tensor):
+        """out_bits[0] (int32) = max(out_bits[0], float32 bits of the largest distance to base3 among the colours
+        of `keys` assigned to `donor`)."""
+        import ctypes
+
+        arr = (ctypes.c_float * 3)(*[float(v) for v in base3])
+        self._bind()
+        self.ctx.call("llfe_kmeans_hist_farthest", keys, keys.numel(), centers.shape[0], centers, int(donor),
+                      ctypes.addressof(arr), out_bits)
 
     # -- fused pipeline -------------------------------------------------------------
     def pipeline(self, bgr: torch.Tensor, shapes: bool = True, shadows: bool = True, colors: bool = True,

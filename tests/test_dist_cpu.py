@@ -54,7 +54,7 @@ def _case(kind):
     return img, init
 
 
-def _worker(rank, world, port, kind, q):
+def _worker(rank, world, port, kind, histogram, q):
     os.environ["MASTER_ADDR"] = "127.0.0.1"
     os.environ["MASTER_PORT"] = str(port)
     dist.init_process_group("gloo", rank=rank, world_size=world)
@@ -65,7 +65,7 @@ def _worker(rank, world, port, kind, q):
         h, w, _ = img.shape
         r0, r1 = ldist.row_shard(h, rank, world)
         rows = torch.from_numpy(np.ascontiguousarray(img[r0:r1]))
-        km = ldist.PixelKMeans(OracleBackend())
+        km = ldist.PixelKMeans(OracleBackend(), histogram=histogram)
         res = km.fit(rows, torch.from_numpy(init), index_base=r0 * w, want_labels=True)
         lab = ldist.gather_results(res.labels.reshape(r1 - r0, w), h)
         q.put((rank, res.centers.numpy().copy(), res.iters, res.sums_counts.numpy().copy(), lab.numpy().copy()))
@@ -73,16 +73,17 @@ def _worker(rank, world, port, kind, q):
         dist.destroy_process_group()
 
 
+@pytest.mark.parametrize("histogram", [True, False])
 @pytest.mark.parametrize("kind", ["design", "empty_cluster"])
 @pytest.mark.parametrize("world", [2, 3])
-def test_row_sharded_kmeans_equals_single_process_oracle(kind, world):
+def test_row_sharded_kmeans_equals_single_process_oracle(kind, world, histogram):
     img, init = _case(kind)
     px = img.reshape(-1, 3)[:, ::-1]
     c_ref, l_ref, it_ref, s_ref, n_ref = cvops.lloyd_exact(px, init)
     ctx = mp.get_context("spawn")
     q = ctx.Queue()
     port = _free_port()
-    procs = [ctx.Process(target=_worker, args=(r, world, port, kind, q)) for r in range(world)]
+    procs = [ctx.Process(target=_worker, args=(r, world, port, kind, histogram, q)) for r in range(world)]
     for p in procs:
         p.start()
     got = [q.get(timeout=120) for _ in range(world)]
@@ -101,9 +102,12 @@ def test_single_process_is_identity_collective():
 
     img, init = _case("design")
     px = img.reshape(-1, 3)[:, ::-1]
-    c_ref, _, it_ref, _, _ = cvops.lloyd_exact(px, init)
-    res = ldist.PixelKMeans(OracleBackend()).fit(torch.from_numpy(img), torch.from_numpy(init))
-    assert res.iters == it_ref and np.array_equal(res.centers.numpy(), c_ref)
+    c_ref, l_ref, it_ref, _, _ = cvops.lloyd_exact(px, init)
+    for histogram in (True, False):
+        res = ldist.PixelKMeans(OracleBackend(), histogram=histogram).fit(torch.from_numpy(img), torch.from_numpy(init),
+                                                                          want_labels=True)
+        assert res.iters == it_ref and np.array_equal(res.centers.numpy(), c_ref)
+        assert np.array_equal(res.labels.numpy(), l_ref.astype(np.uint8))
 
 
 def test_host_pipeline_stage_schedule():

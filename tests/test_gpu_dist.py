@@ -30,8 +30,9 @@ def _init_from_pixels(px, k, seed):
     return np.float32(px[np.random.default_rng(seed).choice(len(px), k, replace=False)])
 
 
+@pytest.mark.parametrize("histogram", [True, False])
 @pytest.mark.parametrize("case", [("design", 96, 128, 16, 42), ("design", 45, 77, 5, 1), ("noise", 64, 96, 8, 3)])
-def test_pixel_kmeans_matches_exact_oracle(eng, case):
+def test_pixel_kmeans_matches_exact_oracle(eng, case, histogram):
     from low_level_feature_extraction_b200.dist import PixelKMeans
 
     kind, h, w, k, seed = case
@@ -39,7 +40,8 @@ def test_pixel_kmeans_matches_exact_oracle(eng, case):
     px = img.reshape(-1, 3)[:, ::-1]
     init = _init_from_pixels(px, k, seed)
     c_ref, l_ref, it_ref, s_ref, n_ref = cvops.lloyd_exact(px, init)
-    res = PixelKMeans(eng).fit(torch.from_numpy(img).cuda(), torch.from_numpy(init), want_labels=True)
+    res = PixelKMeans(eng, histogram=histogram).fit(torch.from_numpy(img).cuda(), torch.from_numpy(init),
+                                                    want_labels=True)
     assert res.iters == it_ref
     assert np.array_equal(res.centers.cpu().numpy(), c_ref)            # bit-exact centres
     assert np.array_equal(res.labels.cpu().numpy(), l_ref.astype(np.uint8))  # bit-exact pixel labels
@@ -51,7 +53,8 @@ def test_pixel_kmeans_matches_exact_oracle(eng, case):
         assert np.abs(res.centers.cpu().numpy() - c_cv).max() / 255.0 <= 1e-3
 
 
-def test_pixel_kmeans_empty_cluster_repair(eng):
+@pytest.mark.parametrize("histogram", [True, False])
+def test_pixel_kmeans_empty_cluster_repair(eng, histogram):
     from low_level_feature_extraction_b200.dist import PixelKMeans
 
     img = design_image(40, 56, 9)
@@ -60,7 +63,8 @@ def test_pixel_kmeans_empty_cluster_repair(eng):
     init[3] = init[1]
     init[4] = init[1]          # two empty clusters on the first update, same donor twice
     c_ref, l_ref, it_ref, s_ref, n_ref = cvops.lloyd_exact(px, init)
-    res = PixelKMeans(eng).fit(torch.from_numpy(img).cuda(), torch.from_numpy(init), want_labels=True)
+    res = PixelKMeans(eng, histogram=histogram).fit(torch.from_numpy(img).cuda(), torch.from_numpy(init),
+                                                    want_labels=True)
     assert res.iters == it_ref
     assert np.array_equal(res.centers.cpu().numpy(), c_ref)
     assert np.array_equal(res.labels.cpu().numpy(), l_ref.astype(np.uint8))
@@ -93,3 +97,65 @@ def test_full_size_step_properties(eng):
     tot = rows.reshape(-1, 3).to(torch.int64).sum(0).flip(0)           # RGB totals
     assert torch.equal(sums[:, :3].sum(0), tot)
     assert torch.equal(torch.bincount(lab.to(torch.int64), minlength=16), sums[:, 3])
+
+
+@pytest.mark.parametrize("shape", [(45, 77), (101, 203), (64, 96), (1, 5), (300, 517)])
+def test_colour_histogram_equals_numpy_unique(eng, shape):
+    """Count table + ordered compaction == np.unique(pixels, axis=0, return_counts=True), for every split into parts."""
+    h, w = shape
+    img = design_image(h, w, 11) if h * w > 16 else noise_image(h, w, 11)
+    d = torch.from_numpy(img).cuda()
+    hist = torch.zeros((1 << 24,), dtype=torch.int32, device="cuda")
+    eng.pixels_histogram(d[: h // 2].contiguous(), hist)          # two row shards accumulate into one table
+    eng.pixels_histogram(d[h // 2:].contiguous(), hist)
+    uq, cnt = np.unique(img.reshape(-1, 3)[:, ::-1], axis=0, return_counts=True)   # RGB rows, lexicographic
+    key_ref = (uq[:, 0].astype(np.int64) << 16) | (uq[:, 1].astype(np.int64) << 8) | uq[:, 2]
+    keys, counts = eng.histogram_compact(hist)
+    assert np.array_equal(keys.cpu().numpy(), key_ref) and np.array_equal(counts.cpu().numpy(), cnt)
+    for parts in (2, 3, 8):
+        got_k, got_c = [], []
+        for part in range(parts):
+            kk, cc = eng.histogram_compact(hist, part, parts)
+            assert np.all((kk.cpu().numpy() // 2048) % parts == part)
+            got_k.append(kk.cpu().numpy())
+            got_c.append(cc.cpu().numpy())
+        order = np.argsort(np.concatenate(got_k), kind="stable")
+        assert np.array_equal(np.concatenate(got_k)[order], key_ref)
+        assert np.array_equal(np.concatenate(got_c)[order], cnt)
+
+
+def test_histogram_step_equals_pixel_step(eng):
+    """The weighted step over distinct colours adds exactly what the per-pixel step adds; labels agree pixel by pixel."""
+    g = torch.Generator(device="cuda").manual_seed(5)
+    rows = (torch.randint(0, 40, (1024, 2048, 3), dtype=torch.uint8, device="cuda", generator=g) * 6
+            + torch.randint(0, 3, (1024, 2048, 3), dtype=torch.uint8, device="cuda", generator=g))
+    rows[:300, :, :] = torch.tensor([250, 3, 77], dtype=torch.uint8, device="cuda")   # one colour with a huge count
+    init = torch.rand((16, 3), device="cuda", generator=g) * 255
+    a = torch.zeros((16, 4), dtype=torch.int64, device="cuda")
+    lab_a = torch.empty((1024 * 2048,), dtype=torch.uint8, device="cuda")
+    eng.kmeans_pixels_step(rows, init, a, lab_a)
+    hist = torch.zeros((1 << 24,), dtype=torch.int32, device="cuda")
+    eng.pixels_histogram(rows, hist)
+    assert int(hist.sum()) == 1024 * 2048
+    keys, counts = eng.histogram_compact(hist)
+    b = torch.zeros((16, 4), dtype=torch.int64, device="cuda")
+    lab_e = torch.empty((keys.numel(),), dtype=torch.uint8, device="cuda")
+    eng.kmeans_hist_step(keys, counts, init, b, lab_e)
+    assert torch.equal(a, b)
+    lut = torch.zeros((1 << 24,), dtype=torch.uint8, device="cuda")
+    eng.hist_labels_to_lut(keys, lab_e, lut)
+    lab_b = torch.empty_like(lab_a)
+    eng.pixels_lookup(rows, lut, lab_b)
+    assert torch.equal(lab_a, lab_b)
+    # unaligned base pointer (head pixels) and a ragged tail
+    flat = rows.reshape(-1)[3 * 5: 3 * 5 + 3 * 100003].clone()
+    sub = torch.empty((flat.numel() + 3,), dtype=torch.uint8, device="cuda")[3:]
+    sub.copy_(flat)
+    h2 = torch.zeros((1 << 24,), dtype=torch.int32, device="cuda")
+    eng.pixels_histogram(sub.view(1, -1, 3), h2)
+    ref = torch.bincount((sub.view(-1, 3)[:, 2].to(torch.int64) << 16) | (sub.view(-1, 3)[:, 1].to(torch.int64) << 8)
+                         | sub.view(-1, 3)[:, 0].to(torch.int64), minlength=1 << 24)
+    assert torch.equal(h2.to(torch.int64), ref)
+    l2 = torch.empty((100003,), dtype=torch.uint8, device="cuda")
+    eng.pixels_lookup(sub.view(1, -1, 3), lut, l2)
+    assert torch.equal(l2, lab_a[5: 5 + 100003])
