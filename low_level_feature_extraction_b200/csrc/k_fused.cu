@@ -25,6 +25,10 @@ constexpr unsigned FULL = 0xffffffffu;
 constexpr int WARPS = 4;
 constexpr int OUT_PER_WARP = 240;            // 30 output lanes x 8 px
 constexpr int BAND_W = WARPS * OUT_PER_WARP;  // 960
+// resident CTAs per SM the kernel is compiled for: with the float ring (SHADOW) shared memory allows 4; the
+// edges-only variant fits 96 registers at 5 CTAs (measured 8 % faster than 4 CTAs x 122 registers; 6 CTAs x 80
+// registers spills and is 13 % slower)
+constexpr int CTAS_FULL = 4, CTAS_EDGES = 5;
 constexpr int RING = 10;   // rows vb-10 .. vb-1 of the 11-row window; the newest row is still in registers
 
 // float32(cv2.getGaussianKernel(11, 0)), see k_threshold.cu
@@ -276,7 +280,7 @@ __device__ __forceinline__ void nms_px(const Q4& m0, uint32_t e0, const Q4& m1, 
 __device__ __forceinline__ float u2f(uint32_t v) { return __uint_as_float(0x4b000000u | v) - 8388608.0f; }
 
 template <bool EDGES, bool SHADOW, bool COLORS>
-__global__ void __launch_bounds__(WARPS * 32, 4) k_fused(FusedArgs A) {
+__global__ void __launch_bounds__(WARPS * 32, (SHADOW || COLORS) ? CTAS_FULL : CTAS_EDGES) k_fused(FusedArgs A) {
     // dynamic shared memory: [128 lanes][24 B] colour scratch, then SHADOW per warp: [RING][2][32] float4 (row-pass
     // results) + [RING][32] uint2 (the blurred pixels as bytes) = 1280 B per row: 4 CTAs per SM
     extern __shared__ float4 dyn_smem[];
@@ -558,11 +562,11 @@ int launch_fused(llfe_ctx* ctx, const uint8_t* bgr, int n, int h, int w, int low
         if (!s_dummy) LLFE_CUDA(cudaMalloc(&s_dummy, 65536 * 2 * sizeof(unsigned long long)));
         A.sum_count = s_dummy;
     }
-    // Row bands: the grid should fill whole waves of the machine (4 CTAs per SM) and the bands should be tall
+    // Row bands: the grid should fill whole waves of the machine (CTAS_* CTAs per SM) and the bands should be tall
     // enough to amortise their ~10 warm-up rows.  Pick the band count with the best product of the two.
     {
         const int xb = ceil_div(w, BAND_W);
-        const double slots = 4.0 * (ctx->sm_count > 0 ? ctx->sm_count : 148);
+        const double slots = (double)((S || C) ? CTAS_FULL : CTAS_EDGES) * (ctx->sm_count > 0 ? ctx->sm_count : 148);
         const double halo = S ? 10.0 : 4.0;
         int best = 1;
         double best_score = -1.0;
