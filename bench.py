@@ -167,6 +167,12 @@ class ClockSampler:
         for ln in self.proc.stdout:
             self.rows.append((time.perf_counter(), ln.strip()))
 
+    def wait_first(self, timeout=5.0):
+        """nvidia-smi needs a moment before its first line: do not start the timed region without a live sampler."""
+        t_end = time.perf_counter() + timeout
+        while self.proc and not self.rows and time.perf_counter() < t_end and self.proc.poll() is None:
+            time.sleep(0.02)
+
     def stop(self, t0, t1):
         if not self.proc:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
@@ -253,11 +259,12 @@ def run_ours(args):
             dist.barrier()
         torch.cuda.synchronize()
 
+    sampler = ClockSampler(local) if rank == 0 else None   # started early: samples during the warm-up are the fallback
     for _ in range(args.warmup):
         an.run_device(batch, out)
     barrier()
-    sampler = ClockSampler(local) if rank == 0 else None
-    time.sleep(0.25 if rank == 0 else 0)
+    if sampler:
+        sampler.wait_first()
     barrier()
     launches0 = eng.launches
     eng.ctx.profile_begin()

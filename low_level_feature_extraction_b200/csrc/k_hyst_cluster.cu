@@ -30,7 +30,7 @@ namespace cg = cooperative_groups;
 
 namespace {
 
-constexpr int HC_THREADS = 128;
+constexpr int HC_THREADS = 256;
 constexpr int HC_NW = HC_THREADS / 32;
 constexpr int HC_D = 2;                 // rows shared with each neighbour (strip and warp range)
 constexpr unsigned FULLM = 0xffffffffu;
