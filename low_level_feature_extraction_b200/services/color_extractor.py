@@ -187,6 +187,29 @@ class ColorExtractor:
         zero = np.zeros(px.shape, np.int8)
         return ColorExtractor._dominant_from_rgb(px.reshape(1, -1, 3), zero, n_colors)
 
+    @staticmethod
+    def _palette_from_clusters(centers: np.ndarray, counts: np.ndarray | None) -> ColorFeatures:
+        """color_extractor.py:231-284 on host: order the (K,3) u8 RGB centres by the number of distinct colours
+        in their cluster (the literal NumPy argsort), drop pure white / black, pick primary, three
+        accents and the contrasting background."""
+        if len(centers) > 1:
+            sorted_indices = np.argsort(-counts)
+            centers = centers[sorted_indices]
+            counts = counts[sorted_indices]
+
+        hex_colors = [ColorExtractor.rgb_to_hex(tuple(int(v) for v in color)) for color in centers]
+        hex_colors = [c for c in hex_colors if c.lower() not in ["#ffffff", "#000000"]]
+        meta = {"success": True, "timestamp": 0.0, "processing_time": 0.0}
+        if not hex_colors:
+            bg_color = "#000000" if ColorExtractor.is_light_color((255, 255, 255)) else "#FFFFFF"
+            return ColorFeatures(primary=bg_color, background=bg_color, accent=[bg_color] * 3, metadata=meta)
+        primary = hex_colors[0]
+        accent_colors = [c for c in hex_colors if c != primary][:3]
+        while len(accent_colors) < 3:
+            accent_colors.append(accent_colors[-1] if accent_colors else primary)
+        bg_color = "#FFFFFF" if not ColorExtractor.is_light_color(ColorExtractor.hex_to_rgb(primary)) else "#000000"
+        return ColorFeatures(primary=primary, background=bg_color, accent=accent_colors[:3], metadata=meta)
+
     # ---- the service call -------------------------------------------------------------------
     @staticmethod
     def extract_colors(image: Union[np.ndarray, Image.Image], n_colors: int = 5) -> ColorFeatures:
@@ -214,24 +237,8 @@ class ColorExtractor:
             else:
                 centers, labels = np.zeros((0, 3), np.uint8), np.array([], dtype=np.int64)
 
-            if len(centers) > 1:
-                counts = np.bincount(labels, minlength=len(centers))
-                sorted_indices = np.argsort(-counts)
-                centers = centers[sorted_indices]
-                counts = counts[sorted_indices]
-
-            hex_colors = [ColorExtractor.rgb_to_hex(tuple(int(v) for v in color)) for color in centers]
-            hex_colors = [c for c in hex_colors if c.lower() not in ["#ffffff", "#000000"]]
-            meta = {"success": True, "timestamp": 0.0, "processing_time": 0.0}
-            if not hex_colors:
-                bg_color = "#000000" if ColorExtractor.is_light_color((255, 255, 255)) else "#FFFFFF"
-                return ColorFeatures(primary=bg_color, background=bg_color, accent=[bg_color] * 3, metadata=meta)
-            primary = hex_colors[0]
-            accent_colors = [c for c in hex_colors if c != primary][:3]
-            while len(accent_colors) < 3:
-                accent_colors.append(accent_colors[-1] if accent_colors else primary)
-            bg_color = "#FFFFFF" if not ColorExtractor.is_light_color(ColorExtractor.hex_to_rgb(primary)) else "#000000"
-            return ColorFeatures(primary=primary, background=bg_color, accent=accent_colors[:3], metadata=meta)
+            counts = np.bincount(labels, minlength=len(centers)) if len(centers) > 1 else None
+            return ColorExtractor._palette_from_clusters(centers, counts)
         except Exception as e:
             print(f"Error in extract_colors: {str(e)}\n{traceback.format_exc()}")
             return ColorFeatures(primary="#000000", background="#FFFFFF", accent=["#666666", "#999999", "#CCCCCC"],

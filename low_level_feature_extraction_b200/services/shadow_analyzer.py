@@ -38,6 +38,11 @@ class ShadowAnalyzer:
     def analyze_shadow_level(image: np.ndarray) -> str:
         """'Low' | 'Moderate' | 'High'   (src L12-31)."""
         _, total, count = ShadowAnalyzer.shadow_mask(image)
+        return ShadowAnalyzer.level_from_sums(total, count)
+
+    @staticmethod
+    def level_from_sums(total: int, count: int) -> str:
+        """src L19-31 from the exact sum / count of the blurred pixels under the threshold mask."""
         if count == 0:
             return "Low"
         avg_darkness = 255 - total / count   # np.mean of the masked pixels: exact integer sum / count in float64

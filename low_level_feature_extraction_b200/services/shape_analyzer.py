@@ -80,7 +80,11 @@ class ShapeAnalyzer:
     @staticmethod
     def analyze_shapes(image: np.ndarray) -> Dict[str, Any]:
         """src L125-189: {'shapes': [...], 'total_shapes', 'metadata': {'image_width','image_height'}}."""
-        preprocessed = ShapeAnalyzer.preprocess_image(image)
+        return ShapeAnalyzer.shapes_from_mask(ShapeAnalyzer.preprocess_image(image), image.shape[1], image.shape[0])
+
+    @staticmethod
+    def shapes_from_mask(preprocessed: np.ndarray, image_width: int, image_height: int) -> Dict[str, Any]:
+        """The host tail of analyze_shapes (src L134-189) on an already computed edge mask."""
         contours, _ = cv2.findContours(preprocessed, cv2.RETR_EXTERNAL, cv2.CHAIN_APPROX_SIMPLE)
         shape_results = []
         for contour in contours:
@@ -92,4 +96,4 @@ class ShapeAnalyzer:
             shape_results.append({"type": shape_type, "x": x, "y": y, "width": w, "height": h,
                                   "border_radius": border_radius, "area": cv2.contourArea(contour)})
         return {"shapes": shape_results, "total_shapes": len(shape_results),
-                "metadata": {"image_width": image.shape[1], "image_height": image.shape[0]}}
+                "metadata": {"image_width": image_width, "image_height": image_height}}

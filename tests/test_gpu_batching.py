@@ -1,0 +1,49 @@
+"""RequestBatcher on the GPU: concurrent single-image requests share launches and every request gets exactly
+what the one-at-a-time drop-in services return for its image."""
+import os
+import sys
+import threading
+
+import numpy as np
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+
+from low_level_feature_extraction_b200.synth import design_image  # noqa: E402
+
+pytestmark = pytest.mark.gpu
+
+
+def test_batched_requests_equal_single_requests():
+    from low_level_feature_extraction_b200.services import ShadowAnalyzer, ShapeAnalyzer
+    from low_level_feature_extraction_b200.services.batching import RequestBatcher
+
+    imgs = [design_image(270, 480, s) for s in range(7)] + [design_image(360, 640, 20 + s) for s in range(5)]
+    res = [None] * len(imgs)
+    with RequestBatcher(device=0, max_batch=8, max_wait_ms=50.0) as rb:
+        start = threading.Barrier(4)
+
+        def client(c):
+            start.wait()
+            for i in range(c, len(imgs), 4):
+                res[i] = rb.analyze(imgs[i])
+
+        th = [threading.Thread(target=client, args=(c,)) for c in range(4)]
+        for t in th:
+            t.start()
+        for t in th:
+            t.join()
+        assert rb.images == len(imgs) and rb.batches < len(imgs)           # launches were shared
+        again = rb.analyze(imgs[0])
+    for img, r in zip(imgs, res):
+        assert np.array_equal(r["shape_mask"], ShapeAnalyzer.preprocess_image(img))
+        mask, total, count = ShadowAnalyzer.shadow_mask(img)
+        assert np.array_equal(r["shadow_mask"], mask)
+        assert r["shadow_level"] == ShadowAnalyzer.analyze_shadow_level(img)
+        assert r["shapes"] == ShapeAnalyzer.analyze_shapes(img)
+        c = r["colors"]
+        assert c.metadata["success"] and len(c.accent) == 3
+        for hx in [c.primary, c.background] + list(c.accent):
+            assert len(hx) == 7 and hx[0] == "#" and int(hx[1:], 16) >= 0
+    assert np.array_equal(again["shape_mask"], res[0]["shape_mask"])
