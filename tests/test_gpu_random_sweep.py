@@ -83,3 +83,49 @@ def test_colours_and_fused_pipeline_on_random_shapes(eng, shape):
         _, m_ref, s_ref, n_ref, _ = cvops.shadow_parts(img)
         assert np.array_equal(out["shadow_mask"][0].cpu().numpy(), m_ref)
         assert [int(v) for v in out["shadow_sums"][0].cpu()] == [s_ref, n_ref]
+
+
+def _colour_list(kind, u, r):
+    """u distinct RGB colours (sorted like np.unique): uniform, a few tight blobs, or a gray-ish ramp."""
+    if kind == "uniform":
+        px = r.integers(0, 256, (u * 2 + 8, 3))
+    elif kind == "blobs":
+        c = r.integers(20, 236, (int(r.integers(2, 9)), 3))
+        px = c[r.integers(0, len(c), u * 3 + 8)] + r.integers(-18, 19, (u * 3 + 8, 3))
+    else:
+        t = r.integers(0, 256, (u * 3 + 8, 1))
+        px = t + r.integers(-6, 7, (u * 3 + 8, 3))
+    uq = np.unique(np.clip(px, 0, 255).astype(np.uint8), axis=0)
+    if len(uq) > u:
+        uq = uq[np.sort(r.choice(len(uq), u, replace=False))]
+    return uq
+
+
+@pytest.mark.parametrize("k", [1, 2, 3, 5, 8, 16])
+def test_kmeans_batch_of_mixed_sizes_matches_cv2(eng, k):
+    """One launch over lists of very different lengths (every tier of the k-means kernel, from a single colour to
+    a list that needs the global-memory variant) against cv2.kmeans itself: labels and float32 centres bit for bit."""
+    import cv2
+
+    r = np.random.default_rng(1000 + k)
+    sizes = [1, 2, 5, 17, 300, 2500, 9000, 16000, 24000, 40000, 60000]
+    kinds = ["uniform", "blobs", "ramp"]
+    lists = [_colour_list(kinds[(i + k) % 3], u, r) for i, u in enumerate(sizes)]
+    mu = 1 << 16
+    keys = np.zeros((len(lists), mu), np.int32)
+    cnt = np.zeros(len(lists), np.int32)
+    for i, uq in enumerate(lists):
+        keys[i, :len(uq)] = (uq[:, 0].astype(np.int64) << 16 | uq[:, 1].astype(np.int64) << 8 | uq[:, 2]).astype(np.int32)
+        cnt[i] = len(uq)
+    seeds = [int(s) for s in r.integers(0, 1 << 31, len(lists))]
+    centers, labels, comp, kused = eng.kmeans_unique(torch.from_numpy(keys).cuda(), torch.from_numpy(cnt).cuda(), k, seeds)
+    for i, uq in enumerate(lists):
+        ka = min(k, len(uq))
+        assert int(kused[i]) == ka
+        if ka <= 1:       # color_extractor.py:183-186: no cv2.kmeans call at all
+            continue
+        cv2.setRNGSeed(seeds[i])
+        c_ref, l_ref, ce_ref = cv2.kmeans(np.float32(uq), ka, None, refpath.KMEANS_CRITERIA, 10, cv2.KMEANS_PP_CENTERS)
+        assert np.array_equal(labels[i, :len(uq)].cpu().numpy(), l_ref.ravel()), (k, len(uq))
+        assert np.array_equal(centers[i, :ka].cpu().numpy(), ce_ref), (k, len(uq))
+        assert abs(float(comp[i]) - c_ref) <= 1e-9 * max(1.0, c_ref)
