@@ -188,62 +188,105 @@ __device__ __forceinline__ float fdist3(float r, float g, float b, const float* 
     return d;
 }
 
+// two IEEE float32 operations per instruction (sm_100 FADD2 / FMUL2); each half is rounded on its own
+__device__ __forceinline__ u64 pack2(float lo, float hi) {
+    return ((u64)__float_as_uint(hi) << 32) | (u64)__float_as_uint(lo);
+}
+__device__ __forceinline__ u64 add2(u64 a, u64 b) {
+    u64 r;
+    asm("add.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
+    return r;
+}
+__device__ __forceinline__ u64 mul2(u64 a, u64 b) {
+    u64 r;
+    asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
+    return r;
+}
+
+constexpr int EPS_T = 4;   // entries per thread per trip of k_hist_step (two f32x2 pairs)
+
 // one Lloyd assignment over (key, count) entries: cv2's float32 distance and first-minimum rule per
-// distinct colour, exact u64 sums weighted by the pixel counts
+// distinct colour (on PAIRS of colours with packed f32x2 arithmetic, x + (-c) == x - c exactly), exact u64
+// sums weighted by the pixel counts
 __global__ void __launch_bounds__(HT) k_hist_step(const uint32_t* __restrict__ keys,
                                                   const uint32_t* __restrict__ counts, size_t n, int K,
                                                   const float* __restrict__ centers, u64* sums,
                                                   uint8_t* __restrict__ labels_out,
                                                   const int32_t* __restrict__ state) {
     if (state && (state[1] | state[3])) return;
-    __shared__ float s_c[KMAX][3];
+    __shared__ u64 s_nc[KMAX][3];   // (-c, -c)
     __shared__ u64 s_acc[HT / 32][KMAX][4];
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    for (int i = tid; i < K * 3; i += HT) (&s_c[0][0])[i] = centers[i];
+    for (int i = tid; i < K * 3; i += HT) {
+        const float c = centers[i];
+        (&s_nc[0][0])[i] = pack2(-c, -c);
+    }
     for (int i = tid; i < (HT / 32) * KMAX * 4; i += HT) (&s_acc[0][0][0])[i] = 0ull;
     __syncthreads();
-    const size_t stride = (size_t)gridDim.x * HT;
-    for (size_t i0 = blockIdx.x * (size_t)HT; i0 < n; i0 += stride) {   // block-uniform trip count
-        const size_t i = i0 + tid;
-        int bl = -1;
-        uint32_t r = 0, g = 0, b = 0, cnt = 0;
-        if (i < n) {
-            const uint32_t key = keys[i];
-            cnt = counts[i];
-            r = key >> 16;
-            g = (key >> 8) & 0xffu;
-            b = key & 0xffu;
-            const float fr = (float)r, fg = (float)g, fb = (float)b;
-            float bd = fdist3(fr, fg, fb, s_c[0]);
-            bl = 0;
-            for (int k = 1; k < K; ++k) {
-                const float d = fdist3(fr, fg, fb, s_c[k]);
-                if (d < bd) {   // strict: the lowest index wins ties
-                    bd = d;
-                    bl = k;
+    const size_t stride = (size_t)gridDim.x * HT * EPS_T;
+    for (size_t i0 = blockIdx.x * (size_t)(HT * EPS_T); i0 < n; i0 += stride) {   // block-uniform trip count
+        uint32_t key[EPS_T], cnt[EPS_T];
+        bool ok[EPS_T];
+#pragma unroll
+        for (int j = 0; j < EPS_T; ++j) {
+            const size_t i = i0 + (size_t)j * HT + tid;
+            ok[j] = i < n;
+            key[j] = ok[j] ? keys[i] : 0u;
+            cnt[j] = ok[j] ? counts[i] : 0u;
+        }
+        u64 r2[EPS_T / 2], g2[EPS_T / 2], b2[EPS_T / 2];
+#pragma unroll
+        for (int p = 0; p < EPS_T / 2; ++p) {
+            r2[p] = pack2((float)(key[2 * p] >> 16), (float)(key[2 * p + 1] >> 16));
+            g2[p] = pack2((float)((key[2 * p] >> 8) & 0xffu), (float)((key[2 * p + 1] >> 8) & 0xffu));
+            b2[p] = pack2((float)(key[2 * p] & 0xffu), (float)(key[2 * p + 1] & 0xffu));
+        }
+        float bd[EPS_T];
+        int bl[EPS_T];
+        for (int k = 0; k < K; ++k) {
+            const u64 n0 = s_nc[k][0], n1 = s_nc[k][1], n2 = s_nc[k][2];
+#pragma unroll
+            for (int p = 0; p < EPS_T / 2; ++p) {
+                const u64 t0 = add2(r2[p], n0), t1 = add2(g2[p], n1), t2 = add2(b2[p], n2);
+                u64 d = mul2(t0, t0);
+                d = add2(d, mul2(t1, t1));
+                d = add2(d, mul2(t2, t2));
+                const float d0 = __uint_as_float((uint32_t)d), d1 = __uint_as_float((uint32_t)(d >> 32));
+                if (k == 0 || d0 < bd[2 * p]) {   // strict: the lowest index wins ties
+                    bd[2 * p] = d0;
+                    bl[2 * p] = k;
+                }
+                if (k == 0 || d1 < bd[2 * p + 1]) {
+                    bd[2 * p + 1] = d1;
+                    bl[2 * p + 1] = k;
                 }
             }
-            if (labels_out) labels_out[i] = (uint8_t)bl;
         }
-        // counts reach 2^28: reduce the low and high 16 bits of count * channel separately (REDUX is 32-bit)
-        const uint32_t cl = cnt & 0xffffu, ch = cnt >> 16;
-        uint32_t todo = __ballot_sync(FULL, bl >= 0);
-        while (todo) {
-            const int k = __shfl_sync(FULL, bl, __ffs(todo) - 1);
-            const bool in = bl == k;
-            const uint32_t m = __ballot_sync(FULL, in);
-            const uint32_t l0 = in ? cl : 0u, h0 = in ? ch : 0u;
-            const u64 sr = (u64)__reduce_add_sync(FULL, l0 * r) + ((u64)__reduce_add_sync(FULL, h0 * r) << 16);
-            const u64 sg = (u64)__reduce_add_sync(FULL, l0 * g) + ((u64)__reduce_add_sync(FULL, h0 * g) << 16);
-            const u64 sb = (u64)__reduce_add_sync(FULL, l0 * b) + ((u64)__reduce_add_sync(FULL, h0 * b) << 16);
-            const u64 sn = (u64)__reduce_add_sync(FULL, l0) + ((u64)__reduce_add_sync(FULL, h0) << 16);
-            if (lane == 0) {
-                s_acc[warp][k][0] += sr;
-                s_acc[warp][k][1] += sg;
-                s_acc[warp][k][2] += sb;
-                s_acc[warp][k][3] += sn;
+#pragma unroll
+        for (int j = 0; j < EPS_T; ++j) {
+            if (labels_out && ok[j]) labels_out[i0 + (size_t)j * HT + tid] = (uint8_t)bl[j];
+            const int lab = ok[j] ? bl[j] : -1;
+            const uint32_t r = key[j] >> 16, g = (key[j] >> 8) & 0xffu, b = key[j] & 0xffu;
+            // counts reach 2^28: reduce the low and high 16 bits of count * channel separately (REDUX is 32-bit)
+            const uint32_t cl = cnt[j] & 0xffffu, ch = cnt[j] >> 16;
+            uint32_t todo = __ballot_sync(FULL, lab >= 0);
+            while (todo) {
+                const int k = __shfl_sync(FULL, lab, __ffs(todo) - 1);
+                const bool in = lab == k;
+                const uint32_t m = __ballot_sync(FULL, in);
+                const uint32_t l0 = in ? cl : 0u, h0 = in ? ch : 0u;
+                const u64 sr = (u64)__reduce_add_sync(FULL, l0 * r) + ((u64)__reduce_add_sync(FULL, h0 * r) << 16);
+                const u64 sg = (u64)__reduce_add_sync(FULL, l0 * g) + ((u64)__reduce_add_sync(FULL, h0 * g) << 16);
+                const u64 sb = (u64)__reduce_add_sync(FULL, l0 * b) + ((u64)__reduce_add_sync(FULL, h0 * b) << 16);
+                const u64 sn = (u64)__reduce_add_sync(FULL, l0) + ((u64)__reduce_add_sync(FULL, h0) << 16);
+                if (lane == 0) {
+                    s_acc[warp][k][0] += sr;
+                    s_acc[warp][k][1] += sg;
+                    s_acc[warp][k][2] += sb;
+                    s_acc[warp][k][3] += sn;
+                }
+                todo &= ~m;
             }
-            todo &= ~m;
         }
     }
     __syncthreads();
@@ -439,7 +482,7 @@ extern "C" int llfe_kmeans_hist_step(llfe_ctx* ctx, const uint32_t* d_keys, cons
     LLFE_CHECK_ARG(ctx != nullptr && d_centers != nullptr && d_sums_counts != nullptr && k >= 1 && k <= KMAX);
     LLFE_CHECK_ARG(n == 0 || (d_keys != nullptr && d_counts != nullptr));
     if (n == 0) return LLFE_OK;
-    const size_t want = ceil_div_sz(n, HT);
+    const size_t want = ceil_div_sz(n, HT * EPS_T);
     const size_t cap = (size_t)ctx->sm_count * 8;
     LLFE_KERNEL(ctx, "k_hist_step");
     k_hist_step<<<(unsigned)(want > cap ? cap : want), HT, 0, ctx->stream>>>(
