@@ -366,7 +366,7 @@ int run_kmeans(llfe_ctx* ctx, KmParams P, int n, float* d_centers, int32_t* d_la
     const size_t dslots = (size_t)dist_images * P.attempts;
     const size_t need = WsCarver::need(dslots * P.max_unique * 8) + WsCarver::need(slots * P.max_unique) +
                         WsCarver::need(slots * KMAX * 3 * 4) + 3 * WsCarver::need(slots * 8) +
-                        WsCarver::need(slots * KMAX * 4 * 8);
+                        WsCarver::need(slots * KMAX * 4 * 8) + WsCarver::need((size_t)n * 4);
     void* ws;
     LLFE_TRY(llfe_workspace(ctx, need, &ws));
     WsCarver c(ws);
@@ -378,7 +378,9 @@ int run_kmeans(llfe_ctx* ctx, KmParams P, int n, float* d_centers, int32_t* d_la
     P.iters = (int32_t*)c.take<double>(slots);
     P.inexact = (int32_t*)c.take<double>(slots);
     P.sums = (unsigned long long*)c.take<unsigned long long>(slots * KMAX * 4);
+    P.order = nullptr;
     if (fast) {
+        P.order = c.take<int32_t>((size_t)n);   // filled by launch_kmeans_fast
         LLFE_TRY(launch_kmeans_fast(ctx, P, n));
     } else {
         LLFE_KERNEL(ctx, "k_kmeans");

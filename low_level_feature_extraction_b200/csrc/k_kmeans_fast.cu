@@ -80,7 +80,8 @@ template <int KC, bool IN_SMEM>
 __global__ void __launch_bounds__(FT, 2) k_kmeans_fast(KmParams P, int u_lo, int smem_points, int img_base) {
     typedef Fmt<KC> F;
     extern __shared__ uint32_t dyn[];
-    const int att = blockIdx.x, img = blockIdx.y + img_base, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int att = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int img = (IN_SMEM && P.order) ? P.order[blockIdx.y] : blockIdx.y + img_base;
     const int U = min(P.count[img], P.max_unique);
     const int K = min(P.k, U);
     // this launch owns the images with u_lo < U <= smem_points (IN_SMEM) / U > smem_points (global scratch)
@@ -610,6 +611,20 @@ __global__ void __launch_bounds__(FT, 2) k_kmeans_fast(KmParams P, int u_lo, int
     }
 }
 
+// order[r] = the image with the r-th longest colour list (ties by index): the block scheduler hands out CTAs in
+// grid order, so the long lists start first and the short ones fill the tail of the launch
+__global__ void __launch_bounds__(256) k_kmeans_order(const int32_t* __restrict__ count, int n, int32_t* __restrict__ order) {
+    const int i = blockIdx.x * 256 + threadIdx.x;
+    if (i >= n) return;
+    const int ci = count[i];
+    int rank = 0;
+    for (int j = 0; j < n; ++j) {
+        const int cj = count[j];
+        rank += (cj > ci) || (cj == ci && j < i);
+    }
+    order[rank] = i;
+}
+
 template <int KC>
 int launch_kc(llfe_ctx* ctx, const KmParams& P, int n, int pts2, int pts1) {
     static bool attr_set = false;
@@ -619,6 +634,11 @@ int launch_kc(llfe_ctx* ctx, const KmParams& P, int n, int pts2, int pts1) {
     }
     // One launch for the whole batch: the block scheduler back-fills SMs as CTAs finish, so attempts
     // that need many iterations do not hold up a wave.  Lists of up to pts2 colours run two CTAs per SM.
+    if (P.order) {
+        LLFE_KERNEL(ctx, "k_kmeans_order");
+        k_kmeans_order<<<ceil_div(n, 256), 256, 0, ctx->stream>>>(P.count, n, const_cast<int32_t*>(P.order));
+        LLFE_LAUNCHED(ctx);
+    }
     LLFE_KERNEL(ctx, "k_kmeans_fast");
     k_kmeans_fast<KC, true><<<dim3(P.attempts, n), FT, (size_t)pts2 * 4, ctx->stream>>>(P, 0, pts2, 0);
     LLFE_LAUNCHED(ctx);

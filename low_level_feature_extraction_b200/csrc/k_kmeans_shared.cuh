@@ -25,6 +25,7 @@ struct KmParams {
     int32_t* inexact;          // [n][attempts]
     unsigned long long* sums;  // [n][attempts][KMAX][4]  final sums/counts
     unsigned long long* dbg;   // optional [n][attempts][8] phase clocks (LLFE_KMEANS_DEBUG), else null
+    const int32_t* order;      // optional [n]: image handled by blockIdx.y (longest lists first), else null = identity
 };
 
 __device__ __forceinline__ uint32_t idist(uint32_t a, uint32_t b) {
