@@ -23,7 +23,10 @@
  *   - the caller owns every buffer; the context owns only its workspace arena
  *     and pinned staging buffers.
  *   - one context per (process, device); calls on one context are serialised on
- *     its stream (the reference handles one request at a time per worker).
+ *     its stream (the reference handles one request at a time per worker).  Like a
+ *     cuBLAS handle, a context is used with ITS device current: llfe_create makes the
+ *     device current, a process that drives several devices calls cudaSetDevice before
+ *     using each context.
  *   - there is NO CPU fallback: if no CUDA device is usable, llfe_create fails.
  */
 #ifndef LLFE_H

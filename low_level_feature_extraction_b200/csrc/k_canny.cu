@@ -382,11 +382,9 @@ int launch_hysteresis(llfe_ctx* ctx, const uint32_t* weak, uint32_t* edges, int 
         return LLFE_E_UNSUPPORTED;
     }
     const int nstrips = ceil_div(h, hrows);
-    static bool attr_set = false;
-    if (!attr_set) {
+    if (llfe_first_use(ctx, (const void*)k_hyst_strips)) {
         LLFE_CUDA(cudaFuncSetAttribute(k_hyst_strips, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)budget));
         LLFE_CUDA(cudaFuncSetAttribute(k_hyst_finish, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)budget));
-        attr_set = true;
     }
     // round 0 visits every strip; rounds 1..2 only strips whose halo changed; one CTA per image
     // then finishes whatever cross-strip propagation is left (usually nothing).

@@ -522,11 +522,8 @@ __global__ void __launch_bounds__(WARPS * 32, (SHADOW || COLORS) ? CTAS_FULL : C
 
 template <bool E, bool S, bool C>
 int launch_t(llfe_ctx* ctx, const FusedArgs& A, dim3 grid, size_t smem) {
-    static bool attr = false;
-    if (!attr && smem > 48 * 1024) {
+    if (smem > 48 * 1024 && llfe_first_use(ctx, (const void*)k_fused<E, S, C>))   // smem is a constant of the variant
         LLFE_CUDA(cudaFuncSetAttribute(k_fused<E, S, C>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        attr = true;
-    }
     LLFE_KERNEL(ctx, "k_fused");
     k_fused<E, S, C><<<grid, WARPS * 32, smem, ctx->stream>>>(A);
     LLFE_LAUNCHED(ctx);
@@ -557,10 +554,9 @@ int launch_fused(llfe_ctx* ctx, const uint8_t* bgr, int n, int h, int w, int low
     A.img0 = img0;
     A.bitmap = bitmap;
     const bool E = weak != nullptr, S = mask != nullptr, C = bitmap != nullptr;
-    static unsigned long long* s_dummy = nullptr;  // sums go somewhere even if the caller does not want them
-    if (S && !sum_count) {
-        if (!s_dummy) LLFE_CUDA(cudaMalloc(&s_dummy, 65536 * 2 * sizeof(unsigned long long)));
-        A.sum_count = s_dummy;
+    if (S && !sum_count) {   // sums go somewhere even if the caller does not want them
+        if (!ctx->dummy_sums) LLFE_CUDA(cudaMalloc(&ctx->dummy_sums, 65536 * 2 * sizeof(unsigned long long)));
+        A.sum_count = ctx->dummy_sums;
     }
     // Row bands: the grid should fill whole waves of the machine (CTAS_* CTAs per SM) and the bands should be tall
     // enough to amortise their ~10 warm-up rows.  Pick the band count with the best product of the two.

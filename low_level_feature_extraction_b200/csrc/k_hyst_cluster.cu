@@ -411,13 +411,11 @@ size_t hc_smem(int rps, int sp) {
 
 template <int CL, int WPL, bool DILATE>
 int launch_hc(llfe_ctx* ctx, const HcArgs& A, int n, size_t smem) {
-    static bool attr = false;
-    if (!attr) {
+    if (llfe_first_use(ctx, (const void*)k_hyst_mask<CL, WPL, DILATE>)) {
         LLFE_CUDA(cudaFuncSetAttribute(k_hyst_mask<CL, WPL, DILATE>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                        (int)(ctx->smem_optin - 1024)));
         if (CL > 8)
             LLFE_CUDA(cudaFuncSetAttribute(k_hyst_mask<CL, WPL, DILATE>, cudaFuncAttributeNonPortableClusterSizeAllowed, 1));
-        attr = true;
     }
     cudaLaunchConfig_t cfg = {};
     cfg.gridDim = dim3(CL, n, 1);

@@ -29,6 +29,7 @@ namespace {
 constexpr int FT = 512;
 constexpr int FW = FT / 32;
 constexpr int QROWS = 8;    // rows (of 32 points) per bounds-test / drain block
+constexpr size_t STATIC_SMEM_BOUND = 16 * 1024;  // centres, totals, queues, row totals, reduction scratch (upper bound)
 constexpr int RMAX = 112;   // rows per warp the row-total table holds (IN_SMEM lists are shorter)
 constexpr unsigned FULL = 0xffffffffu;
 
@@ -627,11 +628,10 @@ __global__ void __launch_bounds__(256) k_kmeans_order(const int32_t* __restrict_
 
 template <int KC>
 int launch_kc(llfe_ctx* ctx, const KmParams& P, int n, int pts2, int pts1) {
-    static bool attr_set = false;
-    if (!attr_set) {
-        LLFE_CUDA(cudaFuncSetAttribute(k_kmeans_fast<KC, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, pts1 * 4));
-        attr_set = true;
-    }
+    // the limit must not depend on this call's max_unique (pts1 is capped by it): a later call may bring longer lists
+    if (llfe_first_use(ctx, (const void*)k_kmeans_fast<KC, true>))
+        LLFE_CUDA(cudaFuncSetAttribute(k_kmeans_fast<KC, true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                       (int)(ctx->smem_optin - STATIC_SMEM_BOUND)));
     // One launch for the whole batch: the block scheduler back-fills SMs as CTAs finish, so attempts
     // that need many iterations do not hold up a wave.  Lists of up to pts2 colours run two CTAs per SM.
     if (P.order) {
@@ -666,7 +666,7 @@ int launch_kc(llfe_ctx* ctx, const KmParams& P, int n, int pts2, int pts1) {
 int launch_kmeans_fast(llfe_ctx* ctx, const KmParams& P0, int n) {
     KmParams P = P0;
     if (const char* dbg = getenv("LLFE_KMEANS_DEBUG")) P.dbg = (unsigned long long*)(uintptr_t)strtoull(dbg, nullptr, 10);
-    const size_t static_smem = 16 * 1024;  // centres, totals, queues, row totals, reduction scratch (upper bound)
+    const size_t static_smem = STATIC_SMEM_BOUND;
     const size_t per_cta2 = (ctx->smem_optin + 1024) / 2 - 1024;   // two CTAs per SM, 1 KB reserved per CTA
     auto points = [&](size_t per_cta) {
         size_t avail = per_cta > static_smem ? per_cta - static_smem : 0;

@@ -134,6 +134,7 @@ int llfe_destroy(llfe_ctx* ctx) {
     if (ctx->ws) cudaFree(ctx->ws);
     if (ctx->pin) cudaFreeHost(ctx->pin);
     if (ctx->dev_stage) cudaFree(ctx->dev_stage);
+    if (ctx->dummy_sums) cudaFree(ctx->dummy_sums);
     llfe_free_area_tabs(ctx);
     if (ctx->prof) {
         for (int i = 0; i < ctx->prof_events; ++i) {

@@ -23,6 +23,10 @@ struct llfe_ctx {
     size_t dev_stage_bytes = 0;
     // INTER_AREA tables cached per (ssize, dsize)
     struct AreaTab* area_tabs = nullptr;
+    // kernels whose per-device function attributes (dynamic shared memory limit, cluster size) are already set
+    const void* attr_done[64] = {};
+    int n_attr_done = 0;
+    unsigned long long* dummy_sums = nullptr;  // sink for the shadow sums when the caller does not want them
     uint64_t launches = 0;
     // optional per-kernel CUDA-event timing (llfe_profile_begin / llfe_profile_end)
     struct ProfRec* prof = nullptr;
@@ -41,6 +45,14 @@ void llfe_prof_stop(llfe_ctx* ctx);
     do {                                              \
         if ((ctx)->prof_on) llfe_prof_mark(ctx, name); \
     } while (0)
+
+// true the first time `kernel` is seen on this context (function attributes are per device, contexts are per device)
+static inline bool llfe_first_use(llfe_ctx* ctx, const void* kernel) {
+    for (int i = 0; i < ctx->n_attr_done; ++i)
+        if (ctx->attr_done[i] == kernel) return false;
+    if (ctx->n_attr_done < 64) ctx->attr_done[ctx->n_attr_done++] = kernel;
+    return true;
+}
 
 void llfe_set_error(const char* fmt, ...);
 int llfe_cuda_fail(cudaError_t e, const char* what, const char* file, int line);

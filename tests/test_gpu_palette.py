@@ -163,3 +163,37 @@ def test_pipeline_outputs(eng):
         u = cvops.unique_colors(px)
         c = int(out["count"][i])
         assert c == len(u) and np.array_equal(keys_to_rgb(out["keys"][i].cpu().numpy(), c), u)
+
+
+def test_kmeans_short_lists_first_then_long_lists():
+    """A process whose first k-means call sees a small max_unique must still take long lists later (the dynamic
+    shared-memory limit of the kernel may not be sized by the first call).  Function attributes live as long as
+    the process, so this runs in a fresh interpreter."""
+    import os
+    import subprocess
+    import sys
+
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    code = """
+import sys
+sys.path.insert(0, %r)
+import numpy as np, torch, cv2
+import low_level_feature_extraction_b200 as pkg
+from oracle import refpath
+eng = pkg.engine(0)
+dev = lambda a: torch.from_numpy(np.ascontiguousarray(a)).cuda()
+small = np.zeros((1, 64), np.int32)
+small[0, :3] = [0x010203, 0x0a0b0c, 0xf0e0d0]
+c, l, comp, ku = eng.kmeans_unique(dev(small), dev(np.array([3], np.int32)), 2, 1)
+assert int(ku[0]) == 2
+u8 = np.unique(np.random.default_rng(3).integers(0, 256, (30000, 3), dtype=np.uint8), axis=0)
+keys = np.zeros((1, 1 << 15), np.int32)
+keys[0, :len(u8)] = (u8[:, 0].astype(np.int64) << 16 | u8[:, 1].astype(np.int64) << 8 | u8[:, 2]).astype(np.int32)
+c2, l2, comp2, ku2 = eng.kmeans_unique(dev(keys), dev(np.array([len(u8)], np.int32)), 5, 7)
+cv2.setRNGSeed(7)
+_, l_cv, c_cv = cv2.kmeans(np.float32(u8), 5, None, refpath.KMEANS_CRITERIA, 10, cv2.KMEANS_PP_CENTERS)
+assert np.array_equal(l2[0, :len(u8)].cpu().numpy(), l_cv.ravel()) and np.array_equal(c2[0].cpu().numpy(), c_cv)
+print("OK")
+""" % root
+    r = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0 and "OK" in r.stdout, r.stderr[-2000:]
