@@ -255,7 +255,8 @@ int llfe_kmeans_update(llfe_ctx* ctx, int k, uint64_t* d_sums_counts, float* d_c
  * re-reading the image every iteration. */
 
 /* d_hist[key] += number of pixels of colour key = (R << 16) + (G << 8) + B, 2^24 uint32
- * bins (the caller zeroes the table once and all-reduces it across ranks with ncclSum). */
+ * bins (the caller zeroes the table once and all-reduces it across ranks with ncclSum;
+ * the image as a whole must have fewer than 2^31 pixels so that no bin overflows). */
 int llfe_pixels_histogram(llfe_ctx* ctx, const uint8_t* d_bgr, size_t n_pixels, uint32_t* d_hist);
 
 /* Ordered compaction of the non-empty bins into (key, count) entries, key ascending =

@@ -446,6 +446,7 @@ inline unsigned stream_grid(const llfe_ctx* ctx, size_t items_per_thread_groups)
 
 extern "C" int llfe_pixels_histogram(llfe_ctx* ctx, const uint8_t* d_bgr, size_t n_pixels, uint32_t* d_hist) {
     LLFE_CHECK_ARG(ctx != nullptr && d_hist != nullptr && (d_bgr != nullptr || n_pixels == 0));
+    LLFE_CHECK_ARG(n_pixels <= 0x7fffffffull);   // a bin must stay below 2^31 (ranks all-reduce the table as int32)
     if (n_pixels == 0) return LLFE_OK;
     LLFE_KERNEL(ctx, "k_hist_count");
     k_hist_count<<<stream_grid(ctx, n_pixels / 16 + 1), HT, 0, ctx->stream>>>(d_bgr, n_pixels, head_pixels(d_bgr), d_hist);
