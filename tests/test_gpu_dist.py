@@ -159,3 +159,55 @@ def test_histogram_step_equals_pixel_step(eng):
     l2 = torch.empty((100003,), dtype=torch.uint8, device="cuda")
     eng.pixels_lookup(sub.view(1, -1, 3), lut, l2)
     assert torch.equal(l2, lab_a[5: 5 + 100003])
+
+
+def test_config5_full_size_properties(eng):
+    """BASELINE config 5 at its real size (one 16384 x 16384 image = 2^28 pixels, K = 16), where the oracle is far too
+    slow: conservation laws and the equality of the two forms of the assignment step."""
+    n = 16384
+    g = torch.Generator(device="cuda").manual_seed(11)
+    rows = torch.empty((n, n, 3), dtype=torch.uint8, device="cuda")
+    for r0 in range(0, n, 2048):   # smooth ramps + noise: about a million distinct colours
+        y = torch.arange(r0, r0 + 2048, device="cuda").view(-1, 1, 1)
+        x = torch.arange(n, device="cuda").view(1, -1, 1)
+        base = torch.cat([(x * 3 + y) // 197, (x + y * 5) // 311, (x * 7 + y * 2) // 523], dim=2)
+        rows[r0:r0 + 2048] = ((base + torch.randint(0, 12, (2048, n, 3), device="cuda", generator=g)) % 256).to(torch.uint8)
+    npix = n * n
+    init = torch.rand((16, 3), device="cuda", generator=g) * 255
+    hist = torch.zeros((1 << 24,), dtype=torch.int32, device="cuda")
+    eng.pixels_histogram(rows, hist)
+    assert int(hist.to(torch.int64).sum()) == npix
+    keys, counts = eng.histogram_compact(hist)
+    assert int(counts.to(torch.int64).sum()) == npix and bool((keys[1:] > keys[:-1]).all())
+    parts = [eng.histogram_compact(hist, p, 8) for p in range(8)]
+    assert sum(int(k.numel()) for k, _ in parts) == keys.numel()
+    a = torch.zeros((16, 4), dtype=torch.int64, device="cuda")
+    lab_px = torch.empty((npix,), dtype=torch.uint8, device="cuda")
+    eng.kmeans_pixels_step(rows, init, a, lab_px)
+    b = torch.zeros((16, 4), dtype=torch.int64, device="cuda")
+    for k, c in parts:                     # the eight colour shares add up to the per-pixel sums
+        eng.kmeans_hist_step(k, c, init, b)
+    assert torch.equal(a, b) and int(a[:, 3].sum()) == npix
+    tot = torch.zeros((3,), dtype=torch.int64, device="cuda")
+    for r0 in range(0, n, 2048):
+        tot += rows[r0:r0 + 2048].reshape(-1, 3).to(torch.int64).sum(0)
+    assert torch.equal(a[:, :3].sum(0), tot.flip(0))
+    lab_e = torch.empty((keys.numel(),), dtype=torch.uint8, device="cuda")
+    c2 = torch.zeros((16, 4), dtype=torch.int64, device="cuda")
+    eng.kmeans_hist_step(keys, counts, init, c2, lab_e)
+    lut = torch.zeros((1 << 24,), dtype=torch.uint8, device="cuda")
+    eng.hist_labels_to_lut(keys, lab_e, lut)
+    lab2 = torch.empty_like(lab_px)
+    eng.pixels_lookup(rows, lut, lab2)
+    assert torch.equal(lab_px, lab2)
+    assert torch.equal(torch.bincount(lab2.to(torch.int64), minlength=16), a[:, 3])
+    # the farthest-member search with the global index base of the last row shard of 8
+    far = torch.zeros((1,), dtype=torch.int64, device="cuda")
+    r0 = n - n // 8
+    donor = int(a[:, 3].argmax())
+    base3 = [float(v) for v in (a[donor, :3].to(torch.float64) / float(a[donor, 3])).to(torch.float32)]
+    eng.kmeans_pixels_farthest(rows[r0:], init, donor, base3, r0 * n, far)
+    code = int(far.item())
+    assert code > 0
+    gidx = (code - 1) & 0xFFFFFFFF
+    assert r0 * n <= gidx < npix and int(lab_px[gidx]) == donor
