@@ -47,3 +47,25 @@ def test_batched_requests_equal_single_requests():
         for hx in [c.primary, c.background] + list(c.accent):
             assert len(hx) == 7 and hx[0] == "#" and int(hx[1:], 16) >= 0
     assert np.array_equal(again["shape_mask"], res[0]["shape_mask"])
+
+
+def test_pipeline_is_deterministic_run_to_run():
+    """Cluster hysteresis (DSMEM merges), bitmap atomics and the k-means bounds are all order-independent by
+    construction: repeated runs of the same batch must agree bit for bit."""
+    import hashlib
+
+    import torch
+
+    from low_level_feature_extraction_b200.batch import BatchAnalyzer, BatchConfig
+
+    imgs = torch.from_numpy(np.stack([design_image(540, 960, s) for s in range(12)])).cuda()
+    an = BatchAnalyzer(0, 540, 960, BatchConfig())
+    digests = set()
+    for _ in range(6):
+        out = an.run_device(imgs)
+        torch.cuda.synchronize()
+        h = hashlib.sha256()
+        for k in ("shape_mask", "shadow_mask", "shadow_sums", "centers", "count", "k_used", "cluster_sizes"):
+            h.update(out[k].cpu().numpy().tobytes())
+        digests.add(h.hexdigest())
+    assert len(digests) == 1
