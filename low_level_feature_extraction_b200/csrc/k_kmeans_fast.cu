@@ -26,11 +26,12 @@
 
 namespace {
 
-constexpr int FT = 512;
-constexpr int FW = FT / 32;
+constexpr int FT_STD = 512;    // two CTAs per SM (lists of up to pts2 colours) and the global-scratch variant
+constexpr int FT_LONG = 1024;  // one CTA per SM with all of its shared memory: twice the warps keep the SM as busy
 constexpr int QROWS = 8;    // rows (of 32 points) per bounds-test / drain block
-constexpr size_t STATIC_SMEM_BOUND = 16 * 1024;  // centres, totals, queues, row totals, reduction scratch (upper bound)
-constexpr int RMAX = 112;   // rows per warp the row-total table holds (IN_SMEM lists are shorter)
+// static shared memory (centres, totals, queues, row totals, reduction scratch), upper bounds per variant
+constexpr size_t STATIC_SMEM_BOUND = 16 * 1024, STATIC_SMEM_BOUND_LONG = 20 * 1024;
+constexpr int RMAX_POINTS = 112 * 32 * 16;   // most points a shared-memory list may have (row-total table size)
 constexpr unsigned FULL = 0xffffffffu;
 
 __device__ __forceinline__ float fdist4(float r, float g, float b, float4 c) {
@@ -77,9 +78,11 @@ __device__ __forceinline__ uint32_t idist2(uint32_t a, uint32_t b) {
     return __dp4a(d, d, 0u);
 }
 
-template <int KC, bool IN_SMEM>
-__global__ void __launch_bounds__(FT, 2) k_kmeans_fast(KmParams P, int u_lo, int smem_points, int img_base) {
+template <int KC, bool IN_SMEM, int FT>
+__global__ void __launch_bounds__(FT, FT == FT_LONG ? 1 : 2) k_kmeans_fast(KmParams P, int u_lo, int smem_points, int img_base) {
     typedef Fmt<KC> F;
+    constexpr int FW = FT / 32;
+    constexpr int RMAX = RMAX_POINTS / (32 * FW);   // rows per warp the row-total table holds
     extern __shared__ uint32_t dyn[];
     const int att = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int img = (IN_SMEM && P.order) ? P.order[blockIdx.y] : blockIdx.y + img_base;
@@ -628,10 +631,13 @@ __global__ void __launch_bounds__(256) k_kmeans_order(const int32_t* __restrict_
 
 template <int KC>
 int launch_kc(llfe_ctx* ctx, const KmParams& P, int n, int pts2, int pts1) {
-    // the limit must not depend on this call's max_unique (pts1 is capped by it): a later call may bring longer lists
-    if (llfe_first_use(ctx, (const void*)k_kmeans_fast<KC, true>))
-        LLFE_CUDA(cudaFuncSetAttribute(k_kmeans_fast<KC, true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+    // the limits must not depend on this call's max_unique (pts1 is capped by it): a later call may bring longer lists
+    if (llfe_first_use(ctx, (const void*)k_kmeans_fast<KC, true, FT_STD>)) {
+        LLFE_CUDA(cudaFuncSetAttribute(k_kmeans_fast<KC, true, FT_STD>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                        (int)(ctx->smem_optin - STATIC_SMEM_BOUND)));
+        LLFE_CUDA(cudaFuncSetAttribute(k_kmeans_fast<KC, true, FT_LONG>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                       (int)(ctx->smem_optin - STATIC_SMEM_BOUND_LONG)));
+    }
     // One launch for the whole batch: the block scheduler back-fills SMs as CTAs finish, so attempts
     // that need many iterations do not hold up a wave.  Lists of up to pts2 colours run two CTAs per SM.
     if (P.order) {
@@ -640,12 +646,13 @@ int launch_kc(llfe_ctx* ctx, const KmParams& P, int n, int pts2, int pts1) {
         LLFE_LAUNCHED(ctx);
     }
     LLFE_KERNEL(ctx, "k_kmeans_fast");
-    k_kmeans_fast<KC, true><<<dim3(P.attempts, n), FT, (size_t)pts2 * 4, ctx->stream>>>(P, 0, pts2, 0);
+    k_kmeans_fast<KC, true, FT_STD><<<dim3(P.attempts, n), FT_STD, (size_t)pts2 * 4, ctx->stream>>>(P, 0, pts2, 0);
     LLFE_LAUNCHED(ctx);
-    // longer lists: one CTA per SM with all of its shared memory (every CTA of the other images exits at once)
+    // longer lists: one CTA of 1024 threads per SM with all of its shared memory (every CTA of the other images exits
+    // at once)
     if (P.max_unique > pts2 && pts1 > pts2) {
         LLFE_KERNEL(ctx, "k_kmeans_fast_long");
-        k_kmeans_fast<KC, true><<<dim3(P.attempts, n), FT, (size_t)pts1 * 4, ctx->stream>>>(P, pts2, pts1, 0);
+        k_kmeans_fast<KC, true, FT_LONG><<<dim3(P.attempts, n), FT_LONG, (size_t)pts1 * 4, ctx->stream>>>(P, pts2, pts1, 0);
         LLFE_LAUNCHED(ctx);
     }
     // lists that do not fit in shared memory at all: global scratch, P.dist_images images per launch
@@ -653,7 +660,7 @@ int launch_kc(llfe_ctx* ctx, const KmParams& P, int n, int pts2, int pts1) {
         for (int i0 = 0; i0 < n; i0 += P.dist_images) {
             const int m = (n - i0) < P.dist_images ? (n - i0) : P.dist_images;
             LLFE_KERNEL(ctx, "k_kmeans_fast_global");
-            k_kmeans_fast<KC, false><<<dim3(P.attempts, m), FT, 0, ctx->stream>>>(P, 0, pts1, i0);
+            k_kmeans_fast<KC, false, FT_STD><<<dim3(P.attempts, m), FT_STD, 0, ctx->stream>>>(P, 0, pts1, i0);
             LLFE_LAUNCHED(ctx);
         }
     }
@@ -666,16 +673,15 @@ int launch_kc(llfe_ctx* ctx, const KmParams& P, int n, int pts2, int pts1) {
 int launch_kmeans_fast(llfe_ctx* ctx, const KmParams& P0, int n) {
     KmParams P = P0;
     if (const char* dbg = getenv("LLFE_KMEANS_DEBUG")) P.dbg = (unsigned long long*)(uintptr_t)strtoull(dbg, nullptr, 10);
-    const size_t static_smem = STATIC_SMEM_BOUND;
     const size_t per_cta2 = (ctx->smem_optin + 1024) / 2 - 1024;   // two CTAs per SM, 1 KB reserved per CTA
-    auto points = [&](size_t per_cta) {
+    auto points = [&](size_t per_cta, size_t static_smem) {
         size_t avail = per_cta > static_smem ? per_cta - static_smem : 0;
         long long p = (long long)(avail / 4);
         if (p > P.max_unique) p = P.max_unique;
-        if (p > RMAX * 32 * FW) p = RMAX * 32 * FW;
+        if (p > RMAX_POINTS) p = RMAX_POINTS;
         return (int)(p & ~31ll);
     };
-    const int pts2 = points(per_cta2), pts1 = points(ctx->smem_optin);
+    const int pts2 = points(per_cta2, STATIC_SMEM_BOUND), pts1 = points(ctx->smem_optin, STATIC_SMEM_BOUND_LONG);
     if (P.k <= 5) return launch_kc<5>(ctx, P, n, pts2, pts1);
     if (P.k <= 8) return launch_kc<8>(ctx, P, n, pts2, pts1);
     if (P.k <= 16) return launch_kc<16>(ctx, P, n, pts2, pts1);
