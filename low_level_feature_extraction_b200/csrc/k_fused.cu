@@ -79,7 +79,7 @@ struct Raw {
     uint32_t nz[6];
 };
 
-template <bool COLORS>
+template <bool COLORS, bool INJ>
 __device__ __forceinline__ void issue_row(const FusedArgs& A, int img, int y, int x, bool in_x, bool own, Raw& r) {
 #pragma unroll
     for (int k = 0; k < 6; ++k) r.w[k] = 0u;
@@ -88,7 +88,7 @@ __device__ __forceinline__ void issue_row(const FusedArgs& A, int img, int y, in
         const uint2* p = reinterpret_cast<const uint2*>(A.bgr + pix0 * 3);
         const uint2 a = p[0], b = p[1], c = p[2];
         r.w[0] = a.x; r.w[1] = a.y; r.w[2] = b.x; r.w[3] = b.y; r.w[4] = c.x; r.w[5] = c.y;
-        if (COLORS && own && A.noise) {
+        if (COLORS && INJ && own) {
             const uint2* q = reinterpret_cast<const uint2*>(A.noise + pix0 * 3);
             const uint2 na = q[0], nb = q[1], nc = q[2];
             r.nz[0] = na.x; r.nz[1] = na.y; r.nz[2] = nb.x; r.nz[3] = nb.y; r.nz[4] = nc.x; r.nz[5] = nc.y;
@@ -132,10 +132,11 @@ __device__ __forceinline__ uint32_t noisy_key(uint32_t b, uint32_t g, uint32_t r
     return ((uint32_t)R << 16) | ((uint32_t)G << 8) | (uint32_t)B;
 }
 
+template <bool INJ>
 __device__ __forceinline__ void color_issue(const FusedArgs& A, int img, int y, int x, const Raw& r, ColorPending& cp,
                                             uint8_t* my24) {
     // BGR bytes in memory order are already the key layout: B | G<<8 | R<<16
-    if (A.noise) {
+    if (INJ) {
         unpack24(r.w, cp.key);
         uint32_t n24[8];
         unpack24(r.nz, n24);  // noise is stored in RGB order: byte 0 -> R
@@ -214,8 +215,7 @@ __device__ __forceinline__ Q4 hsmooth(const Q4& b) {
 }
 
 struct Grad {
-    Q4 ax, ay;       // |dx|, |dy|
-    Q4 sg;           // bit 15 of each lane: (dx < 0) != (dy < 0)
+    Q4 ax, ay;       // |dx|, |dy| (<= 1020); bit 15 of each ax lane: (dx < 0) != (dy < 0)
 };
 
 // bit 15 of each 16-bit lane set iff a < b (values < 2^15)
@@ -236,9 +236,8 @@ __device__ __forceinline__ void sobel_row(const Q4& bm1, const Q4& b0, const Q4&
     {                                                                 \
         const uint32_t ax = vmax2(R, L) - vmin2(R, L);                \
         const uint32_t ay = vmax2(TP, TM) - vmin2(TP, TM);            \
-        gr.ax.K = ax;                                                 \
+        gr.ax.K = ax | ((lt2(R, L) ^ lt2(TP, TM)) & 0x80008000u);     \
         gr.ay.K = ay;                                                 \
-        gr.sg.K = (lt2(R, L) ^ lt2(TP, TM)) & 0x80008000u;            \
         mag.K = ax + ay;                                              \
     }
     GRAD1(p0, l1, l0, tp1.p0, tm1.p0)
@@ -259,7 +258,8 @@ __device__ __forceinline__ void nms_px(const Q4& m0, uint32_t e0, const Q4& m1, 
                                        const Grad& gr, int low, int high, uint32_t& wbits, uint32_t& sbits) {
     const int m = (int)px<J>(m1, e1);
     if (m <= low) return;
-    const int ax = (int)px<J>(gr.ax, 0u), ay = (int)px<J>(gr.ay, 0u) << 15;
+    const uint32_t axs = px<J>(gr.ax, 0u);   // |dx| with the sign-difference flag in bit 15
+    const int ax = (int)(axs & 0x7fffu), ay = (int)px<J>(gr.ay, 0u) << 15;
     const int tg22x = ax * 13573;
     bool keep;
     if (ay < tg22x) {
@@ -267,7 +267,7 @@ __device__ __forceinline__ void nms_px(const Q4& m0, uint32_t e0, const Q4& m1, 
     } else if (ay > tg22x + (ax << 16)) {
         keep = (m > (int)px<J>(m0, e0)) && (m >= (int)px<J>(m2, e2));
     } else {
-        const bool neg = (px<J>(gr.sg, 0u) & 0x8000u) != 0;
+        const bool neg = (axs & 0x8000u) != 0;
         keep = neg ? ((m > (int)px<J + 1>(m0, e0)) && (m > (int)px<J - 1>(m2, e2)))
                    : ((m > (int)px<J - 1>(m0, e0)) && (m > (int)px<J + 1>(m2, e2)));
     }
@@ -279,7 +279,9 @@ __device__ __forceinline__ void nms_px(const Q4& m0, uint32_t e0, const Q4& m1, 
 
 __device__ __forceinline__ float u2f(uint32_t v) { return __uint_as_float(0x4b000000u | v) - 8388608.0f; }
 
-template <bool EDGES, bool SHADOW, bool COLORS>
+// INJ: the caller injects the reference's noise tensor (parity mode); otherwise the noise words of a row are never
+// loaded and their six registers are free
+template <bool EDGES, bool SHADOW, bool COLORS, bool INJ>
 __global__ void __launch_bounds__(WARPS * 32, (SHADOW || COLORS) ? CTAS_FULL : CTAS_EDGES) k_fused(FusedArgs A) {
     // dynamic shared memory: [128 lanes][24 B] colour scratch, then SHADOW per warp: [RING][2][32] float4 (row-pass
     // results) + [RING][32] uint2 (the blurred pixels as bytes) = 1280 B per row: 4 CTAs per SM
@@ -310,7 +312,7 @@ __global__ void __launch_bounds__(WARPS * 32, (SHADOW || COLORS) ? CTAS_FULL : C
     uint32_t me[3] = {0u, 0u, 0u};
     Grad gprev, gcur;          // gradient of rows vs-1 (the NMS row) and vs
     bw[0] = bw[1] = bw[2] = tw[0] = tw[1] = tw[2] = mw[0] = mw[1] = mw[2] = Q4{0u, 0u, 0u, 0u};
-    gprev.ax = gprev.ay = gprev.sg = gcur.ax = gcur.ay = gcur.sg = Q4{0u, 0u, 0u, 0u};
+    gprev.ax = gprev.ay = gcur.ax = gcur.ay = Q4{0u, 0u, 0u, 0u};
     Q4 blurred = {0u, 0u, 0u, 0u};
     uint32_t lsum = 0, lcnt = 0;
     int ring_slot = RING - 1;
@@ -325,15 +327,15 @@ __global__ void __launch_bounds__(WARPS * 32, (SHADOW || COLORS) ? CTAS_FULL : C
     ColorPending pend;
     bool have_pend = false;
     auto own_row = [&](int vy) { return COLORS && out_lane && vy >= y0 && vy < y1; };
-    issue_row<COLORS>(A, img, reflect101_near(next_vy, H), x, in_x, own_row(next_vy), raw_next);
+    issue_row<COLORS, INJ>(A, img, reflect101_near(next_vy, H), x, in_x, own_row(next_vy), raw_next);
     auto gray_row = [&]() -> Q4 {
         const Raw cur = raw_next;
         const int vy = next_vy++;
-        if (next_vy <= vy_last) issue_row<COLORS>(A, img, reflect101_near(next_vy, H), x, in_x, own_row(next_vy), raw_next);
+        if (next_vy <= vy_last) issue_row<COLORS, INJ>(A, img, reflect101_near(next_vy, H), x, in_x, own_row(next_vy), raw_next);
         if (COLORS) {
             if (have_pend) color_commit(A, img, pend);
             have_pend = own_row(vy);
-            if (have_pend) color_issue(A, img, vy, x, cur, pend, my24);
+            if (have_pend) color_issue<INJ>(A, img, vy, x, cur, pend, my24);
         }
         // virtual gray row vy: BORDER_REFLECT_101 in y (done by the loader); in x the halo lanes are patched here
         Q4 g = gray_of(cur);
@@ -520,14 +522,20 @@ __global__ void __launch_bounds__(WARPS * 32, (SHADOW || COLORS) ? CTAS_FULL : C
     }
 }
 
-template <bool E, bool S, bool C>
-int launch_t(llfe_ctx* ctx, const FusedArgs& A, dim3 grid, size_t smem) {
-    if (smem > 48 * 1024 && llfe_first_use(ctx, (const void*)k_fused<E, S, C>))   // smem is a constant of the variant
-        LLFE_CUDA(cudaFuncSetAttribute(k_fused<E, S, C>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+template <bool E, bool S, bool C, bool INJ>
+int launch_v(llfe_ctx* ctx, const FusedArgs& A, dim3 grid, size_t smem) {
+    if (smem > 48 * 1024 && llfe_first_use(ctx, (const void*)k_fused<E, S, C, INJ>))   // smem is a constant of the variant
+        LLFE_CUDA(cudaFuncSetAttribute(k_fused<E, S, C, INJ>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     LLFE_KERNEL(ctx, "k_fused");
-    k_fused<E, S, C><<<grid, WARPS * 32, smem, ctx->stream>>>(A);
+    k_fused<E, S, C, INJ><<<grid, WARPS * 32, smem, ctx->stream>>>(A);
     LLFE_LAUNCHED(ctx);
     return LLFE_OK;
+}
+
+template <bool E, bool S, bool C>
+int launch_t(llfe_ctx* ctx, const FusedArgs& A, dim3 grid, size_t smem) {
+    if (C && A.noise) return launch_v<E, S, C, true>(ctx, A, grid, smem);
+    return launch_v<E, S, C, false>(ctx, A, grid, smem);
 }
 
 }  // namespace
