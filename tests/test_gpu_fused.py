@@ -131,3 +131,17 @@ def test_unfused_path_still_matches(eng):
         assert np.array_equal(out["shadow_mask"][0].cpu().numpy(), cvops.shadow_parts(img)[1])
     finally:
         del os.environ["LLFE_UNFUSED"]
+
+
+def test_tall_image_single_column_of_bands(eng):
+    """A tall, narrow image (few, very tall row bands per CTA column): the masked sum / count accumulated per lane over
+    thousands of rows must still be exact, also when the adaptive mask fires on very many pixels."""
+    h, w = 3000, 64
+    img = noise_image(h, w, 5)
+    img[::2] = 255                      # rows alternate white / noise: the adaptive mask fires on very many pixels
+    d = torch.from_numpy(img[None]).cuda()
+    out = eng.pipeline(d, colors=False)
+    _, m_ref, s_ref, n_ref, _ = cvops.shadow_parts(img)
+    assert np.array_equal(out["shadow_mask"][0].cpu().numpy(), m_ref)
+    assert [int(v) for v in out["shadow_sums"][0].cpu()] == [s_ref, n_ref]
+    assert np.array_equal(out["shape_mask"][0].cpu().numpy(), cvops.shape_mask(img))
