@@ -23,10 +23,10 @@
  *   - the caller owns every buffer; the context owns only its workspace arena
  *     and pinned staging buffers.
  *   - one context per (process, device); calls on one context are serialised on
- *     its stream (the reference handles one request at a time per worker).  Like a
- *     cuBLAS handle, a context is used with ITS device current: llfe_create makes the
- *     device current, a process that drives several devices calls cudaSetDevice before
- *     using each context.
+ *     its stream (the reference handles one request at a time per worker).  Every
+ *     entry point makes the context's device current for the duration of the call and
+ *     restores the caller's device on return, so a context may be used from any thread
+ *     (a request-handler pool) whatever device that thread has current.
  *   - there is NO CPU fallback: if no CUDA device is usable, llfe_create fails.
  */
 #ifndef LLFE_H
@@ -61,6 +61,14 @@ int llfe_destroy(llfe_ctx* ctx);
 int llfe_set_stream(llfe_ctx* ctx, void* cuda_stream);
 int llfe_use_own_stream(llfe_ctx* ctx);
 int llfe_sync(llfe_ctx* ctx);
+/* Path toggles for parity tests (production leaves both 0): "unfused" = 1 runs the per-stage kernels
+ * instead of the fused front kernel, "hyst_strips" = 1 the multi-launch strip hysteresis instead of the
+ * cluster kernel.  Unknown names fail with LLFE_E_INVALID. */
+int llfe_set_option(llfe_ctx* ctx, const char* name, int64_t value);
+/* Register a device buffer the "kmeans" / "hysteresis" kernels write per-CTA phase clocks to (tools/debug/);
+ * d_buf = NULL switches the records off.  The pointer is validated with cudaPointerGetAttributes (device
+ * memory of this context's device) and the kernels write only when `bytes` covers the launch. */
+int llfe_set_debug_buffer(llfe_ctx* ctx, const char* name, void* d_buf, size_t bytes);
 /* Number of kernels this context has launched so far (for accounting). */
 uint64_t llfe_launch_count(llfe_ctx* ctx);
 int llfe_sm_count(llfe_ctx* ctx);
@@ -172,11 +180,16 @@ int llfe_convert_scale_abs(llfe_ctx* ctx, const uint8_t* d_src, size_t count, fl
  * distribution on the device from `seed` (throughput mode; not bit-equal to
  * NumPy's MT19937 stream).  d_keys receives, per image, the sorted unique colours
  * as R<<16|G<<8|B (== np.unique row order) at d_keys + i*max_unique; d_count[i]
- * receives the number of unique colours (values above max_unique mean truncated).
+ * receives the number of unique colours (values above max_unique mean truncated: only the
+ * first max_unique keys were written; come back with a longer list, see llfe_kmeans_unique).
+ * first_image: index of image 0 of this call in the caller's numbering -- the device noise is a
+ * pure function of (seed, first_image + i, pixel position), so a single image of a larger batch
+ * can be redone later with the same noise.
  * If d_hist is not NULL it receives the pixel count of each unique colour
  * (uint32, same layout as d_keys) -- the weights of the per-pixel k-means mode. */
 int llfe_unique_colors(llfe_ctx* ctx, const uint8_t* d_bgr, int n, int h, int w, const int8_t* d_noise,
-                       uint64_t seed, uint32_t* d_keys, uint32_t* d_hist, int32_t* d_count, int max_unique);
+                       uint64_t seed, int first_image, uint32_t* d_keys, uint32_t* d_hist, int32_t* d_count,
+                       int max_unique);
 
 /* cv2.kmeans(float32(unique), K, None, (EPS+MAX_ITER, max_iter, eps), attempts,
  * KMEANS_PP_CENTERS) on each image's unique-colour list: color_extractor.py:189-197.
@@ -185,11 +198,21 @@ int llfe_unique_colors(llfe_ctx* ctx, const uint8_t* d_bgr, int n, int h, int w,
  * float32, RGB), labels (int32 per unique colour), compactness (double), and
  * k_used = min(k, n_unique), and cluster_sizes (k int32: unique colours per cluster,
  * the np.bincount(labels) of color_extractor.py:232).  Optional outputs may be NULL.
- * Images with fewer than 2 unique colours follow color_extractor.py:185-186
- * (centers = the colours, labels = 0). */
+ * max_iter is clamped to [2, 100] as cv::kmeans does with criteria.maxCount (the reference's 200 is 100).
+ * k = 1 or an image with fewer than 2 unique colours: no clustering, k_used = min(1, n_unique), centre 0 = the
+ * first unique colour, labels = 0 (color_extractor.py:185-186 returns the unique list itself in that case; the
+ * Python layer rebuilds it from d_keys).
+ * A list that was truncated (d_count[i] > max_unique) is NOT clustered: k_used[i] = -1 and status bit
+ * LLFE_KMEANS_TRUNCATED tell the caller to redo that image with a list of d_count[i] entries.
+ * d_status (optional, int32 per image): LLFE_KMEANS_LONG_SUMS = some cluster's channel sum reached 2^24, where
+ * cv2's sequential float32 centre sums round; that regime is reproduced operation by operation (k_kmeans_seq.cuh),
+ * the bit is informational. */
+#define LLFE_KMEANS_LONG_SUMS 1
+#define LLFE_KMEANS_TRUNCATED 2
 int llfe_kmeans_unique(llfe_ctx* ctx, const uint32_t* d_keys, const int32_t* d_count, int n, int max_unique, int k,
                        int attempts, int max_iter, double eps, const uint64_t* d_rng_state, float* d_centers,
-                       int32_t* d_labels, double* d_compactness, int32_t* d_k_used, int32_t* d_cluster_sizes);
+                       int32_t* d_labels, double* d_compactness, int32_t* d_k_used, int32_t* d_cluster_sizes,
+                       int32_t* d_status);
 
 /* Lloyd iterations from given initial centres (the "seeded mode" of SURVEY.md
  * A.8) over weighted colours (d_weights NULL = all ones).  exact_sums = 0:
@@ -306,10 +329,14 @@ int llfe_convert_scale_abs_host(llfe_ctx* ctx, const uint8_t* h_src, size_t coun
 /* ColorExtractor._get_dominant_colors on one host image (color_extractor.py:151,
  * :224-225, :173-201): BGR2RGB + noise + np.unique + cv2.kmeans.  h_noise: the int8
  * noise tensor (h,w,3, RGB order) or NULL for device noise from `seed`.  h_centers:
- * k*3 floats; h_labels: room for min(h*w, 2^24) int32 (n_unique are written). */
+ * k*3 floats; h_labels: room for min(h*w, 2^24) int32 (n_unique are written).  The unique-colour list is
+ * sized from h*w, so it is never truncated.  h_keys (optional, same room as h_labels) receives the sorted
+ * unique colours R<<16|G<<8|B -- what :185-186 returns as "centres" when fewer than two clusters are asked
+ * for or possible; h_status (optional) the LLFE_KMEANS_* bits of llfe_kmeans_unique. */
 int llfe_dominant_colors_host(llfe_ctx* ctx, const uint8_t* h_bgr, int h, int w, const int8_t* h_noise, uint64_t seed,
                               int k, int attempts, int max_iter, double eps, uint64_t rng_state, float* h_centers,
-                              int32_t* h_labels, int32_t* h_n_unique, int32_t* h_k_used, double* h_compactness);
+                              int32_t* h_labels, int32_t* h_n_unique, int32_t* h_k_used, double* h_compactness,
+                              uint32_t* h_keys, int32_t* h_status);
 
 #ifdef __cplusplus
 }

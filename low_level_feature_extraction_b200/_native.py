@@ -34,6 +34,8 @@ PROTOTYPES = {
     "llfe_set_stream": (i32, [vp, vp]),
     "llfe_use_own_stream": (i32, [vp]),
     "llfe_sync": (i32, [vp]),
+    "llfe_set_option": (i32, [vp, C.c_char_p, C.c_int64]),
+    "llfe_set_debug_buffer": (i32, [vp, C.c_char_p, vp, sz]),
     "llfe_launch_count": (u64, [vp]),
     "llfe_sm_count": (i32, [vp]),
     "llfe_profile_begin": (i32, [vp]),
@@ -62,8 +64,8 @@ PROTOTYPES = {
     "llfe_resize_linear": (i32, [vp, vp, i32, i32, i32, i32, vp, i32, i32]),
     "llfe_resize_lanczos4": (i32, [vp, vp, i32, i32, i32, i32, vp, i32, i32]),
     "llfe_convert_scale_abs": (i32, [vp, vp, sz, f32, f32, i32, vp]),
-    "llfe_unique_colors": (i32, [vp, vp, i32, i32, i32, vp, u64, vp, vp, vp, i32]),
-    "llfe_kmeans_unique": (i32, [vp, vp, vp, i32, i32, i32, i32, i32, f64, vp, vp, vp, vp, vp, vp]),
+    "llfe_unique_colors": (i32, [vp, vp, i32, i32, i32, vp, u64, i32, vp, vp, vp, i32]),
+    "llfe_kmeans_unique": (i32, [vp, vp, vp, i32, i32, i32, i32, i32, f64, vp, vp, vp, vp, vp, vp, vp]),
     "llfe_kmeans_lloyd": (i32, [vp, vp, vp, vp, i32, i32, i32, i32, f64, i32, vp, vp, vp, vp, vp]),
     "llfe_kmeans_pixels_step": (i32, [vp, vp, sz, i32, vp, vp, vp, vp]),
     "llfe_kmeans_pixels_zero": (i32, [vp, i32, vp, vp]),
@@ -85,7 +87,7 @@ PROTOTYPES = {
     "llfe_resize_lanczos4_host": (i32, [vp, vp, i32, i32, i32, vp, i32, i32]),
     "llfe_gaussian_blur5_host": (i32, [vp, vp, i32, i32, i32, vp]),
     "llfe_convert_scale_abs_host": (i32, [vp, vp, sz, f32, f32, i32, vp]),
-    "llfe_dominant_colors_host": (i32, [vp, vp, i32, i32, vp, u64, i32, i32, i32, f64, u64, vp, vp, vp, vp, vp]),
+    "llfe_dominant_colors_host": (i32, [vp, vp, i32, i32, vp, u64, i32, i32, i32, f64, u64, vp, vp, vp, vp, vp, vp, vp]),
 }
 
 _lib = None
@@ -148,7 +150,7 @@ class Context:
 
     def call(self, name: str, *args):
         fn = getattr(self.lib, name)
-        rc = fn(self.handle, *[_ptr(a) if not isinstance(a, (int, float)) else a for a in args])
+        rc = fn(self.handle, *[a if isinstance(a, (int, float, bytes)) else _ptr(a) for a in args])
         if rc != LLFE_OK:
             raise LlfeError(rc, self.lib.llfe_last_error().decode())
 
@@ -161,6 +163,17 @@ class Context:
 
     def sync(self):
         self.call("llfe_sync")
+
+    def set_option(self, name: str, value: int):
+        """Parity-test path toggles: "unfused", "hyst_strips" (include/llfe.h)."""
+        self.call("llfe_set_option", name.encode(), int(value))
+
+    def set_debug_buffer(self, name: str, tensor=None):
+        """Phase-clock records of the "kmeans" / "hysteresis" kernels into a CUDA tensor (None = off)."""
+        if tensor is None:
+            self.call("llfe_set_debug_buffer", name.encode(), None, 0)
+        else:
+            self.call("llfe_set_debug_buffer", name.encode(), tensor, tensor.numel() * tensor.element_size())
 
     def profile_begin(self):
         self.call("llfe_profile_begin")

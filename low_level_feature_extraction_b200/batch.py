@@ -27,7 +27,10 @@ class BatchConfig:
     attempts: int = 10         # cv2.kmeans attempts of the reference
     max_iter: int = 200
     eps: float = 0.2
-    max_unique: int = 1 << 16  # capacity of the per-image unique-colour list
+    # capacity of the per-image unique-colour list of the batched launch.  An image with more colours (any
+    # photo-like frame) is never clustered on a truncated list: the batched k-means skips it (k_used = -1)
+    # and `resolve_overflow` redoes it alone with a list sized from its own count.
+    max_unique: int = 1 << 16
     low: int = 50
     high: int = 150
     seed: int = 0              # device noise seed / cv::RNG state base
@@ -62,12 +65,16 @@ class BatchAnalyzer:
             out["labels"] = torch.empty((n, c.max_unique), dtype=torch.int32, device=d)
             out["k_used"] = torch.empty((n,), dtype=torch.int32, device=d)
             out["cluster_sizes"] = torch.empty((n, c.k), dtype=torch.int32, device=d)
+            out["status"] = torch.empty((n,), dtype=torch.int32, device=d)
             out["rng"] = (torch.arange(n, dtype=torch.int64, device=d) + 1000 + c.seed)
         return out
 
     def run_device(self, bgr: torch.Tensor, out: dict | None = None, engine: Engine | None = None,
-                   noise: torch.Tensor | None = None) -> dict:
-        """All results stay on the device.  Asynchronous on torch's current stream."""
+                   noise: torch.Tensor | None = None, resolve: bool = True) -> dict:
+        """All results stay on the device.  With resolve=True (default) the call ends by reading the unique-colour
+        counts (one small device->host copy, i.e. it synchronises torch's current stream) and redoing every image
+        whose list did not fit `max_unique`; resolve=False stays asynchronous and leaves k_used = -1 for those
+        images (call `resolve_overflow` before using the palettes)."""
         c = self.cfg
         eng = engine or self.engines[0]
         n = bgr.shape[0]
@@ -82,8 +89,32 @@ class BatchAnalyzer:
                 eng._bind()
                 eng.ctx.call("llfe_kmeans_unique", view["keys"], view["count"], sl.stop - sl.start, c.max_unique, c.k,
                              c.attempts, c.max_iter, float(c.eps), view["rng"], view["centers"], view["labels"], None,
-                             view["k_used"], view["cluster_sizes"])
+                             view["k_used"], view["cluster_sizes"], view["status"])
+        if c.colors and resolve:
+            self.resolve_overflow(bgr, out, eng, noise)
         return out
+
+    def resolve_overflow(self, bgr: torch.Tensor, out: dict, engine: Engine | None = None,
+                         noise: torch.Tensor | None = None, counts=None) -> list:
+        """Redo the palette of every image whose unique-colour list overflowed `max_unique` (count > max_unique,
+        k_used = -1), each with a list sized from its own count and the SAME noise as the batched pass.
+        centers / k_used / cluster_sizes / status of those images are overwritten; their keys / labels rows keep the
+        truncated list.  Returns the indices that were redone.  counts: the host copy of out["count"] if the
+        caller already has it."""
+        c = self.cfg
+        eng = engine or self.engines[0]
+        cnt = out["count"].cpu() if counts is None else counts
+        redo = [int(i) for i in torch.nonzero(cnt > c.max_unique).flatten()]
+        for i in redo:
+            i0 = (i // c.chunk) * c.chunk          # run_device seeds every chunk with c.seed + i0
+            cen, kused, sizes, status = eng.palette_large(
+                bgr[i], int(cnt[i]), c.k, 1000 + c.seed + i, seed=c.seed + i0, first_image=i - i0,
+                noise=None if noise is None else noise[i], attempts=c.attempts, max_iter=c.max_iter, eps=c.eps)
+            out["centers"][i].copy_(cen)
+            out["k_used"][i:i + 1].copy_(kused)
+            out["cluster_sizes"][i].copy_(sizes)
+            out["status"][i:i + 1].copy_(status)
+        return redo
 
     # ---- end to end: pinned host in, host out -------------------------------------------------
     def alloc_host_outputs(self, n: int) -> dict:
@@ -99,6 +130,7 @@ class BatchAnalyzer:
             out["count"] = torch.empty((n,), dtype=torch.int32).pin_memory()
             out["k_used"] = torch.empty((n,), dtype=torch.int32).pin_memory()
             out["cluster_sizes"] = torch.empty((n, c.k), dtype=torch.int32).pin_memory()
+            out["status"] = torch.empty((n,), dtype=torch.int32).pin_memory()
         return out
 
     def _stages(self, n: int):
@@ -153,13 +185,37 @@ class BatchAnalyzer:
                 din.copy_(images[i0:i0 + m], non_blocking=True)
                 bytes_in += din.numel()
                 dout = {k: v[:m] for k, v in self._dev_out[b].items()}
-                self.run_device(din, dout, engine=self.engines[b])
-                for key in ("shape_mask", "shadow_mask", "shadow_sums", "centers", "count", "k_used", "cluster_sizes"):
+                self.run_device(din, dout, engine=self.engines[b], resolve=False)
+                for key in ("shape_mask", "shadow_mask", "shadow_sums", "centers", "count", "k_used", "cluster_sizes",
+                            "status"):
                     if key in host_out:
                         host_out[key][i0:i0 + m].copy_(dout[key], non_blocking=True)
                         bytes_out += dout[key].numel() * dout[key].element_size()
         for st in self.streams:
             st.synchronize()
+        if c.colors:
+            # images whose colour list overflowed the batched capacity: upload again, redo alone (rare: photo-like
+            # frames), patch the host results.  The stage's chunk-local index fixes the noise.
+            over = [int(i) for i in torch.nonzero(host_out["count"][:n] > c.max_unique).flatten()]
+            stage_of = {}
+            for (i0, m) in self._stages(n):
+                for i in range(i0, i0 + m):
+                    stage_of[i] = i0
+            eng = self.engines[0]
+            for i in over:
+                with torch.cuda.stream(self.streams[0]):
+                    din = self._dev_in[0][:1]
+                    din.copy_(images[i:i + 1], non_blocking=True)
+                    bytes_in += din.numel()
+                    # run_device saw this image at index i - i0 of a call seeded with c.seed (stage-local chunk 0)
+                    cen, kused, sizes, status = eng.palette_large(
+                        din[0], int(host_out["count"][i]), c.k, 1000 + c.seed + (i - stage_of[i]), seed=c.seed,
+                        first_image=i - stage_of[i], attempts=c.attempts, max_iter=c.max_iter, eps=c.eps)
+                    host_out["centers"][i].copy_(cen, non_blocking=True)
+                    host_out["k_used"][i:i + 1].copy_(kused, non_blocking=True)
+                    host_out["cluster_sizes"][i].copy_(sizes, non_blocking=True)
+                    host_out["status"][i:i + 1].copy_(status, non_blocking=True)
+                self.streams[0].synchronize()
         host_out["_h2d_bytes"] = bytes_in
         host_out["_d2h_bytes"] = bytes_out
         return host_out

@@ -445,6 +445,7 @@ inline unsigned stream_grid(const llfe_ctx* ctx, size_t items_per_thread_groups)
 }  // namespace
 
 extern "C" int llfe_pixels_histogram(llfe_ctx* ctx, const uint8_t* d_bgr, size_t n_pixels, uint32_t* d_hist) {
+    LLFE_ENTER(ctx);
     LLFE_CHECK_ARG(ctx != nullptr && d_hist != nullptr && (d_bgr != nullptr || n_pixels == 0));
     LLFE_CHECK_ARG(n_pixels <= 0x7fffffffull);   // a bin must stay below 2^31 (ranks all-reduce the table as int32)
     if (n_pixels == 0) return LLFE_OK;
@@ -456,6 +457,7 @@ extern "C" int llfe_pixels_histogram(llfe_ctx* ctx, const uint8_t* d_bgr, size_t
 
 extern "C" int llfe_histogram_compact(llfe_ctx* ctx, const uint32_t* d_hist, int part, int parts, uint32_t* d_keys_or_null,
                                       uint32_t* d_counts_or_null, size_t cap, int32_t* d_n) {
+    LLFE_ENTER(ctx);
     LLFE_CHECK_ARG(ctx != nullptr && d_hist != nullptr && d_n != nullptr && parts >= 1 && part >= 0 && part < parts);
     LLFE_CHECK_ARG(cap == 0 || (d_keys_or_null != nullptr && d_counts_or_null != nullptr));
     void* ws = nullptr;
@@ -480,6 +482,7 @@ extern "C" int llfe_histogram_compact(llfe_ctx* ctx, const uint32_t* d_hist, int
 extern "C" int llfe_kmeans_hist_step(llfe_ctx* ctx, const uint32_t* d_keys, const uint32_t* d_counts, size_t n, int k,
                                      const float* d_centers, uint64_t* d_sums_counts, uint8_t* d_labels_or_null,
                                      const int32_t* d_state_or_null) {
+    LLFE_ENTER(ctx);
     LLFE_CHECK_ARG(ctx != nullptr && d_centers != nullptr && d_sums_counts != nullptr && k >= 1 && k <= KMAX);
     LLFE_CHECK_ARG(n == 0 || (d_keys != nullptr && d_counts != nullptr));
     if (n == 0) return LLFE_OK;
@@ -494,6 +497,7 @@ extern "C" int llfe_kmeans_hist_step(llfe_ctx* ctx, const uint32_t* d_keys, cons
 
 extern "C" int llfe_hist_labels_to_lut(llfe_ctx* ctx, const uint32_t* d_keys, const uint8_t* d_labels, size_t n,
                                        uint8_t* d_lut) {
+    LLFE_ENTER(ctx);
     LLFE_CHECK_ARG(ctx != nullptr && d_lut != nullptr && (n == 0 || (d_keys != nullptr && d_labels != nullptr)));
     if (n == 0) return LLFE_OK;
     LLFE_KERNEL(ctx, "k_hist_lut");
@@ -504,6 +508,7 @@ extern "C" int llfe_hist_labels_to_lut(llfe_ctx* ctx, const uint32_t* d_keys, co
 
 extern "C" int llfe_pixels_lookup(llfe_ctx* ctx, const uint8_t* d_bgr, size_t n_pixels, const uint8_t* d_lut,
                                   uint8_t* d_labels) {
+    LLFE_ENTER(ctx);
     LLFE_CHECK_ARG(ctx != nullptr && d_lut != nullptr && (n_pixels == 0 || (d_bgr != nullptr && d_labels != nullptr)));
     if (n_pixels == 0) return LLFE_OK;
     LLFE_KERNEL(ctx, "k_pixels_lookup");
@@ -515,6 +520,7 @@ extern "C" int llfe_pixels_lookup(llfe_ctx* ctx, const uint8_t* d_bgr, size_t n_
 
 extern "C" int llfe_kmeans_hist_farthest(llfe_ctx* ctx, const uint32_t* d_keys, size_t n, int k, const float* d_centers,
                                          int donor, const float* h_base3, uint32_t* d_out_bits) {
+    LLFE_ENTER(ctx);
     LLFE_CHECK_ARG(ctx != nullptr && d_centers != nullptr && h_base3 != nullptr && d_out_bits != nullptr);
     LLFE_CHECK_ARG(k >= 1 && k <= KMAX && donor >= 0 && donor < k && (n == 0 || d_keys != nullptr));
     if (n == 0) return LLFE_OK;
@@ -529,6 +535,7 @@ extern "C" int llfe_kmeans_pixels_farthest(llfe_ctx* ctx, const uint8_t* d_bgr, 
                                            const float* d_centers, int donor, const float* h_base3,
                                            uint32_t index_base, const uint32_t* h_skip, int n_skip, uint32_t want_dist_bits,
                                            uint64_t* d_out) {
+    LLFE_ENTER(ctx);
     LLFE_CHECK_ARG(ctx != nullptr && d_centers != nullptr && h_base3 != nullptr && d_out != nullptr);
     LLFE_CHECK_ARG(n_pixels == 0 || d_bgr != nullptr);
     LLFE_CHECK_ARG(n_skip >= 0 && n_skip <= KMAX && (n_skip == 0 || h_skip != nullptr));

@@ -469,10 +469,8 @@ int launch_hysteresis_mask_cluster(llfe_ctx* ctx, const uint32_t* weak, const ui
     A.wpr = wpr;
     A.rps = 0;
     A.aligned = (w % 16 == 0) && ((uintptr_t)mask % 16 == 0);
-    A.dbg = nullptr;
-    if (const char* dbg = getenv("LLFE_HYST_DEBUG")) {  // address of a device buffer [n][16][8] u64, as decimal
-        A.dbg = (unsigned long long*)(uintptr_t)strtoull(dbg, nullptr, 10);
-    }
+    // phase clocks [n][16][8] u64, only into a buffer registered (and validated) by llfe_set_debug_buffer
+    A.dbg = (ctx->dbg_hyst && ctx->dbg_hyst_bytes >= (size_t)n * 16 * 8 * 8) ? ctx->dbg_hyst : nullptr;
     if (wpr <= 32) return launch_hc_w<1>(ctx, A, n, dilate);
     if (wpr <= 64) return launch_hc_w<2>(ctx, A, n, dilate);
     if (wpr <= 128) return launch_hc_w<4>(ctx, A, n, dilate);

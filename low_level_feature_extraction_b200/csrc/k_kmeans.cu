@@ -64,7 +64,7 @@ __global__ void __launch_bounds__(KT) k_kmeans(KmParams P) {
     const int U = min(P.count[img], P.max_unique);
     const int K = min(P.k, U);
     const size_t slot = (size_t)img * P.attempts + att;
-    if (K <= 1) {
+    if (K <= 1 || P.count[img] > P.max_unique) {   // nothing to cluster / list truncated (see k_kmeans_pick)
         if (tid == 0) {
             P.compact[slot] = 0.0;
             P.iters[slot] = 0;
@@ -305,17 +305,32 @@ __global__ void __launch_bounds__(KT) k_kmeans(KmParams P) {
 // keep the attempt with the smallest compactness (strict '<': the first wins ties)
 __global__ void __launch_bounds__(256) k_kmeans_pick(KmParams P, float* out_centers, int32_t* out_labels,
                                                      double* out_compact, int32_t* out_kused, int32_t* out_iters,
-                                                     unsigned long long* out_sums, int32_t* out_sizes) {
+                                                     unsigned long long* out_sums, int32_t* out_sizes,
+                                                     int32_t* out_status) {
     const int img = blockIdx.x, tid = threadIdx.x;
     const int U = min(P.count[img], P.max_unique);
     const int K = min(P.k, U);
     const uint32_t* keys = P.keys + (size_t)img * P.max_unique;
+    if (P.count[img] > P.max_unique) {
+        // the caller's list is too short for this image: clustering a truncated list would silently give a wrong
+        // palette, so nothing is clustered; k_used = -1 tells the caller to come back with a list of `count` entries
+        if (tid == 0) {
+            if (out_kused) out_kused[img] = -1;
+            if (out_compact) out_compact[img] = 0.0;
+            if (out_iters) out_iters[img] = 0;
+            if (out_status) out_status[img] = LLFE_KMEANS_TRUNCATED;
+            if (out_sizes)
+                for (int i = 0; i < P.k; ++i) out_sizes[(size_t)img * P.k + i] = 0;
+        }
+        return;
+    }
     if (K <= 1) {
         // color_extractor.py:185-186: centres = the unique colours themselves, labels = 0
         if (tid == 0) {
             if (out_kused) out_kused[img] = U > 0 ? 1 : 0;
             if (out_compact) out_compact[img] = 0.0;
             if (out_iters) out_iters[img] = 0;
+            if (out_status) out_status[img] = 0;
             if (U > 0) unpack(keys[0], out_centers[(size_t)img * P.k * 3], out_centers[(size_t)img * P.k * 3 + 1],
                               out_centers[(size_t)img * P.k * 3 + 2]);
             if (out_sizes)
@@ -347,11 +362,16 @@ __global__ void __launch_bounds__(256) k_kmeans_pick(KmParams P, float* out_cent
         if (out_kused) out_kused[img] = K;
         if (out_compact) out_compact[img] = bc;
         if (out_iters) out_iters[img] = P.iters[slot];
+        if (out_status) {
+            int st = 0;
+            for (int a = 0; a < P.attempts; ++a) st |= P.inexact[(size_t)img * P.attempts + a];
+            out_status[img] = st;
+        }
     }
 }
 
 int run_kmeans(llfe_ctx* ctx, KmParams P, int n, float* d_centers, int32_t* d_labels, double* d_compact, int32_t* d_kused,
-               int32_t* d_iters, uint64_t* d_sums, int32_t* d_sizes) {
+               int32_t* d_iters, uint64_t* d_sums, int32_t* d_sizes, int32_t* d_status) {
     const size_t slots = (size_t)n * P.attempts;
     const bool fast = P.weights == nullptr && !P.exact_sums;
     // the fast path keeps the lists in shared memory; its global scratch (lists that do not fit) is
@@ -389,7 +409,7 @@ int run_kmeans(llfe_ctx* ctx, KmParams P, int n, float* d_centers, int32_t* d_la
     }
     LLFE_KERNEL(ctx, "k_kmeans_pick");
     k_kmeans_pick<<<n, 256, 0, ctx->stream>>>(P, d_centers, d_labels, d_compact, d_kused, d_iters,
-                                              (unsigned long long*)d_sums, d_sizes);
+                                              (unsigned long long*)d_sums, d_sizes, d_status);
     LLFE_LAUNCHED(ctx);
     return LLFE_OK;
 }
@@ -399,7 +419,8 @@ int run_kmeans(llfe_ctx* ctx, KmParams P, int n, float* d_centers, int32_t* d_la
 extern "C" int llfe_kmeans_unique(llfe_ctx* ctx, const uint32_t* d_keys, const int32_t* d_count, int n, int max_unique,
                                   int k, int attempts, int max_iter, double eps, const uint64_t* d_rng_state,
                                   float* d_centers, int32_t* d_labels, double* d_compactness, int32_t* d_k_used,
-                                  int32_t* d_cluster_sizes) {
+                                  int32_t* d_cluster_sizes, int32_t* d_status) {
+    LLFE_ENTER(ctx);
     LLFE_CHECK_ARG(ctx != nullptr && d_keys != nullptr && d_count != nullptr && d_rng_state != nullptr &&
                    d_centers != nullptr);
     LLFE_CHECK_ARG(n >= 0 && n <= 65535 && max_unique > 0 && k >= 1 && k <= KMAX && attempts >= 1 && attempts <= 64 &&
@@ -412,7 +433,7 @@ extern "C" int llfe_kmeans_unique(llfe_ctx* ctx, const uint32_t* d_keys, const i
     P.max_unique = max_unique;
     P.k = k;
     P.attempts = attempts;
-    P.max_iter = max_iter;
+    P.max_iter = max_iter < 2 ? 2 : (max_iter > 100 ? 100 : max_iter);   // cv::kmeans clamps maxCount to [2, 100]
     P.eps2 = eps * eps;
     P.exact_sums = 0;
     P.rng_state = d_rng_state;
@@ -429,7 +450,8 @@ extern "C" int llfe_kmeans_unique(llfe_ctx* ctx, const uint32_t* d_keys, const i
         Q.rng_state = d_rng_state + i0;
         LLFE_TRY(run_kmeans(ctx, Q, m, d_centers + (size_t)i0 * k * 3, d_labels ? d_labels + (size_t)i0 * max_unique : nullptr,
                             d_compactness ? d_compactness + i0 : nullptr, d_k_used ? d_k_used + i0 : nullptr, nullptr,
-                            nullptr, d_cluster_sizes ? d_cluster_sizes + (size_t)i0 * k : nullptr));
+                            nullptr, d_cluster_sizes ? d_cluster_sizes + (size_t)i0 * k : nullptr,
+                            d_status ? d_status + i0 : nullptr));
     }
     return LLFE_OK;
 }
@@ -438,6 +460,7 @@ extern "C" int llfe_kmeans_lloyd(llfe_ctx* ctx, const uint32_t* d_keys, const ui
                                  int n, int max_unique, int k, int max_iter, double eps, int exact_sums,
                                  const float* d_init_centers, float* d_centers, int32_t* d_labels, int32_t* d_iters,
                                  uint64_t* d_sums_counts) {
+    LLFE_ENTER(ctx);
     LLFE_CHECK_ARG(ctx != nullptr && d_keys != nullptr && d_count != nullptr && d_init_centers != nullptr &&
                    d_centers != nullptr);
     LLFE_CHECK_ARG(n >= 0 && n <= 65535 && max_unique > 0 && k >= 1 && k <= KMAX && max_iter >= 1);
@@ -449,7 +472,9 @@ extern "C" int llfe_kmeans_lloyd(llfe_ctx* ctx, const uint32_t* d_keys, const ui
     P.max_unique = max_unique;
     P.k = k;
     P.attempts = 1;
-    P.max_iter = max_iter;
+    // cv2's rule (exact_sums = 0) inherits cv::kmeans' clamp of maxCount to [2, 100]; the pinned exact-sum rule
+    // of the per-pixel mode keeps the caller's limit
+    P.max_iter = exact_sums ? max_iter : (max_iter < 2 ? 2 : (max_iter > 100 ? 100 : max_iter));
     P.eps2 = eps * eps;
     P.exact_sums = exact_sums ? 1 : 0;
     P.rng_state = nullptr;
@@ -466,7 +491,7 @@ extern "C" int llfe_kmeans_lloyd(llfe_ctx* ctx, const uint32_t* d_keys, const ui
         Q.init = d_init_centers + (size_t)i0 * k * 3;
         LLFE_TRY(run_kmeans(ctx, Q, m, d_centers + (size_t)i0 * k * 3, d_labels ? d_labels + (size_t)i0 * max_unique : nullptr,
                             nullptr, nullptr, d_iters ? d_iters + i0 : nullptr,
-                            d_sums_counts ? d_sums_counts + (size_t)i0 * k * 4 : nullptr, nullptr));
+                            d_sums_counts ? d_sums_counts + (size_t)i0 * k * 4 : nullptr, nullptr, nullptr));
     }
     return LLFE_OK;
 }

@@ -91,7 +91,7 @@ __global__ void __launch_bounds__(FT, FT == FT_LONG ? 1 : 2) k_kmeans_fast(KmPar
     // this launch owns the images with u_lo < U <= smem_points (IN_SMEM) / U > smem_points (global scratch)
     if (IN_SMEM ? (U <= u_lo || U > smem_points) : (U <= smem_points)) return;
     const size_t slot = (size_t)img * P.attempts + att;
-    if (K <= 1) {
+    if (K <= 1 || P.count[img] > P.max_unique) {   // nothing to cluster / list truncated (see k_kmeans_pick)
         if (tid == 0) {
             P.compact[slot] = 0.0;
             P.iters[slot] = 0;
@@ -672,7 +672,8 @@ int launch_kc(llfe_ctx* ctx, const KmParams& P, int n, int pts2, int pts1) {
 // pts2 / pts1: how many colours (4 bytes each) fit in the dynamic shared memory of one CTA with two / one CTA per SM
 int launch_kmeans_fast(llfe_ctx* ctx, const KmParams& P0, int n) {
     KmParams P = P0;
-    if (const char* dbg = getenv("LLFE_KMEANS_DEBUG")) P.dbg = (unsigned long long*)(uintptr_t)strtoull(dbg, nullptr, 10);
+    // phase clocks [n][attempts][8] u64, only into a buffer registered (and validated) by llfe_set_debug_buffer
+    P.dbg = (ctx->dbg_kmeans && ctx->dbg_kmeans_bytes >= (size_t)n * P.attempts * 8 * 8) ? ctx->dbg_kmeans : nullptr;
     const size_t per_cta2 = (ctx->smem_optin + 1024) / 2 - 1024;   // two CTAs per SM, 1 KB reserved per CTA
     auto points = [&](size_t per_cta, size_t static_smem) {
         size_t avail = per_cta > static_smem ? per_cta - static_smem : 0;

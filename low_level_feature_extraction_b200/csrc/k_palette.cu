@@ -145,7 +145,7 @@ static size_t unique_ws_per_image(bool with_rank) {
 }
 
 int launch_unique_colors(llfe_ctx* ctx, const uint8_t* d_bgr, int n, int h, int w, const int8_t* d_noise, uint64_t seed,
-                         uint32_t* d_keys, uint32_t* d_hist, int32_t* d_count, int max_unique) {
+                         int first_image, uint32_t* d_keys, uint32_t* d_hist, int32_t* d_count, int max_unique) {
     const size_t npix = (size_t)h * w;
     const bool with_rank = d_hist != nullptr;
     // chunk the batch so that the bitmaps of a chunk stay L2-sized (<= 64 MiB of bitmaps)
@@ -166,13 +166,14 @@ int launch_unique_colors(llfe_ctx* ctx, const uint8_t* d_bgr, int n, int h, int 
         const int8_t* nz = d_noise ? d_noise + (size_t)i0 * npix * 3 : nullptr;
         LLFE_CUDA(cudaMemsetAsync(bitmap, 0, (size_t)BM_WORDS * 4 * m, ctx->stream));
         LLFE_KERNEL(ctx, "k_color_bitmap");
-        k_color_pass<0><<<dim3(gx, m), 256, 0, ctx->stream>>>(src, npix, nz, seed, i0, bitmap, nullptr, nullptr, max_unique);
+        k_color_pass<0><<<dim3(gx, m), 256, 0, ctx->stream>>>(src, npix, nz, seed, first_image + i0, bitmap, nullptr, nullptr,
+                                                              max_unique);
         LLFE_LAUNCHED(ctx);
         LLFE_TRY(launch_bitmap_compact(ctx, bitmap, bsum, m, d_keys + (size_t)i0 * max_unique, rank, d_count + i0,
                                        max_unique));
         if (d_hist) {
             LLFE_KERNEL(ctx, "k_color_count");
-            k_color_pass<1><<<dim3(gx, m), 256, 0, ctx->stream>>>(src, npix, nz, seed, i0, bitmap, rank,
+            k_color_pass<1><<<dim3(gx, m), 256, 0, ctx->stream>>>(src, npix, nz, seed, first_image + i0, bitmap, rank,
                                                                  d_hist + (size_t)i0 * max_unique, max_unique);
             LLFE_LAUNCHED(ctx);
         }
@@ -199,9 +200,11 @@ int launch_bitmap_compact(llfe_ctx* ctx, const uint32_t* bitmap, uint32_t* bsum,
 }
 
 extern "C" int llfe_unique_colors(llfe_ctx* ctx, const uint8_t* d_bgr, int n, int h, int w, const int8_t* d_noise,
-                                  uint64_t seed, uint32_t* d_keys, uint32_t* d_hist, int32_t* d_count, int max_unique) {
+                                  uint64_t seed, int first_image, uint32_t* d_keys, uint32_t* d_hist, int32_t* d_count,
+                                  int max_unique) {
+    LLFE_ENTER(ctx);
     LLFE_CHECK_ARG(ctx != nullptr && d_bgr != nullptr && d_keys != nullptr && d_count != nullptr);
-    LLFE_CHECK_ARG(n >= 0 && n <= 65535 && h > 0 && w > 0 && max_unique > 0);
+    LLFE_CHECK_ARG(n >= 0 && n <= 65535 && h > 0 && w > 0 && max_unique > 0 && first_image >= 0);
     if (n == 0) return LLFE_OK;
-    return launch_unique_colors(ctx, d_bgr, n, h, w, d_noise, seed, d_keys, d_hist, d_count, max_unique);
+    return launch_unique_colors(ctx, d_bgr, n, h, w, d_noise, seed, first_image, d_keys, d_hist, d_count, max_unique);
 }

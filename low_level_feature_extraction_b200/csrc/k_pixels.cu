@@ -280,6 +280,7 @@ __global__ void k_pixels_zero(int K, unsigned long long* sums, const int32_t* __
 }  // namespace
 
 extern "C" int llfe_kmeans_pixels_zero(llfe_ctx* ctx, int k, uint64_t* d_sums_counts, const int32_t* d_state_or_null) {
+    LLFE_ENTER(ctx);
     LLFE_CHECK_ARG(ctx != nullptr && d_sums_counts != nullptr && k >= 1 && k <= KMAX);
     LLFE_KERNEL(ctx, "k_pixels_zero");
     k_pixels_zero<<<1, 128, 0, ctx->stream>>>(k, (unsigned long long*)d_sums_counts, d_state_or_null);
@@ -290,6 +291,7 @@ extern "C" int llfe_kmeans_pixels_zero(llfe_ctx* ctx, int k, uint64_t* d_sums_co
 extern "C" int llfe_kmeans_pixels_step(llfe_ctx* ctx, const uint8_t* d_bgr, size_t n_pixels, int k,
                                        const float* d_centers, uint64_t* d_sums_counts, uint8_t* d_labels_or_null,
                                        const int32_t* d_state_or_null) {
+    LLFE_ENTER(ctx);
     LLFE_CHECK_ARG(ctx != nullptr && d_bgr != nullptr && d_centers != nullptr && d_sums_counts != nullptr);
     LLFE_CHECK_ARG(k >= 1 && k <= KMAX);
     if (n_pixels == 0) return LLFE_OK;
@@ -309,6 +311,7 @@ extern "C" int llfe_kmeans_pixels_step(llfe_ctx* ctx, const uint8_t* d_bgr, size
 extern "C" int llfe_kmeans_update(llfe_ctx* ctx, int k, uint64_t* d_sums_counts, float* d_centers, int max_iter,
                                   double eps, int32_t* d_state, double* d_shift, uint64_t* d_consumed_or_null,
                                   int zero_sums) {
+    LLFE_ENTER(ctx);
     LLFE_CHECK_ARG(ctx != nullptr && d_sums_counts != nullptr && d_centers != nullptr && d_state != nullptr);
     LLFE_CHECK_ARG(k >= 1 && k <= KMAX && max_iter >= 1 && (!zero_sums || d_consumed_or_null != nullptr));
     LLFE_CHECK_ARG(d_consumed_or_null != d_sums_counts);

@@ -175,6 +175,7 @@ void llfe_free_area_tabs(llfe_ctx* ctx) {
 
 extern "C" int llfe_resize_area(llfe_ctx* ctx, const uint8_t* d_src, int n, int sh, int sw, int c, uint8_t* d_dst,
                                 int dh, int dw) {
+    LLFE_ENTER(ctx);
     LLFE_CHECK_ARG(ctx != nullptr && d_src != nullptr && d_dst != nullptr);
     LLFE_CHECK_ARG(n >= 0 && n <= 65535 && sh > 0 && sw > 0 && dh > 0 && dw > 0 && (c == 1 || c == 3));
     if (dh > sh || dw > sw) {
@@ -279,6 +280,7 @@ __global__ void __launch_bounds__(256) k_resize_linear(const uint8_t* __restrict
 
 extern "C" int llfe_resize_linear(llfe_ctx* ctx, const uint8_t* d_src, int n, int sh, int sw, int c, uint8_t* d_dst,
                                   int dh, int dw) {
+    LLFE_ENTER(ctx);
     LLFE_CHECK_ARG(ctx != nullptr && d_src != nullptr && d_dst != nullptr);
     LLFE_CHECK_ARG(n >= 0 && n <= 65535 && sh > 0 && sw > 0 && dh > 0 && dw > 0 && dh <= 65535 && (c == 1 || c == 3));
     if (n == 0) return LLFE_OK;
@@ -414,6 +416,7 @@ __global__ void __launch_bounds__(256) k_resize_lanczos4(const uint8_t* __restri
 
 extern "C" int llfe_resize_lanczos4(llfe_ctx* ctx, const uint8_t* d_src, int n, int sh, int sw, int c, uint8_t* d_dst,
                                     int dh, int dw) {
+    LLFE_ENTER(ctx);
     LLFE_CHECK_ARG(ctx != nullptr && d_src != nullptr && d_dst != nullptr);
     LLFE_CHECK_ARG(n >= 0 && n <= 65535 && sh > 0 && sw > 0 && dh > 0 && dw > 0 && dh <= 65535 && (c == 1 || c == 3));
     if (n == 0) return LLFE_OK;

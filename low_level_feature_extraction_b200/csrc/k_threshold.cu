@@ -38,19 +38,34 @@ __global__ void __launch_bounds__(256) k_adaptive(const uint8_t* __restrict__ sr
         tin[ry][rx] = s[(size_t)y * w + x];
     }
     __syncthreads();
-    // row pass: s = k0*x[-5]; s = fma(x[i-5], k[i], s) for i = 1..10 (left to right)
+    // row pass: s = k0*x[-5]; s = fma(x[i-5], k[i], s) for i = 1..10 (left to right).
+    // Tail columns (pinned against the installed cv2 binary, oracle/cvops.py:gauss11_f32): OpenCV's row
+    // filter runs 8-wide and then 4-wide FMA vectors; the last w % 4 columns go through its scalar loop, whose
+    // compiled code multiplies and adds separately for taps 1..8 and fuses only the last two taps.
+    const int n8 = w & ~7, n4 = (w - n8 >= 4) ? n8 + 4 : n8;
     for (int i = tid; i < (ATH + 10) * ATW; i += 256) {
         int ry = i / ATW, rx = i - ry * ATW;
         const uint8_t* p = &tin[ry][rx];
         float acc = __fmul_rn(GK0, (float)p[0]);
-        acc = __fmaf_rn((float)p[1], GK1, acc);
-        acc = __fmaf_rn((float)p[2], GK2, acc);
-        acc = __fmaf_rn((float)p[3], GK3, acc);
-        acc = __fmaf_rn((float)p[4], GK4, acc);
-        acc = __fmaf_rn((float)p[5], GK5, acc);
-        acc = __fmaf_rn((float)p[6], GK4, acc);
-        acc = __fmaf_rn((float)p[7], GK3, acc);
-        acc = __fmaf_rn((float)p[8], GK2, acc);
+        if (x0 + rx < n4) {
+            acc = __fmaf_rn((float)p[1], GK1, acc);
+            acc = __fmaf_rn((float)p[2], GK2, acc);
+            acc = __fmaf_rn((float)p[3], GK3, acc);
+            acc = __fmaf_rn((float)p[4], GK4, acc);
+            acc = __fmaf_rn((float)p[5], GK5, acc);
+            acc = __fmaf_rn((float)p[6], GK4, acc);
+            acc = __fmaf_rn((float)p[7], GK3, acc);
+            acc = __fmaf_rn((float)p[8], GK2, acc);
+        } else {
+            acc = __fadd_rn(__fmul_rn((float)p[1], GK1), acc);
+            acc = __fadd_rn(__fmul_rn((float)p[2], GK2), acc);
+            acc = __fadd_rn(__fmul_rn((float)p[3], GK3), acc);
+            acc = __fadd_rn(__fmul_rn((float)p[4], GK4), acc);
+            acc = __fadd_rn(__fmul_rn((float)p[5], GK5), acc);
+            acc = __fadd_rn(__fmul_rn((float)p[6], GK4), acc);
+            acc = __fadd_rn(__fmul_rn((float)p[7], GK3), acc);
+            acc = __fadd_rn(__fmul_rn((float)p[8], GK2), acc);
+        }
         acc = __fmaf_rn((float)p[9], GK1, acc);
         acc = __fmaf_rn((float)p[10], GK0, acc);
         rs[ry][rx] = acc;
@@ -63,11 +78,19 @@ __global__ void __launch_bounds__(256) k_adaptive(const uint8_t* __restrict__ sr
         int y = y0 + ry, x = x0 + rx;
         if (y >= h || x >= w) continue;
         float v = __fmul_rn(GK5, rs[ry + 5][rx]);
-        v = __fmaf_rn(__fadd_rn(rs[ry + 6][rx], rs[ry + 4][rx]), GK4, v);
-        v = __fmaf_rn(__fadd_rn(rs[ry + 7][rx], rs[ry + 3][rx]), GK3, v);
-        v = __fmaf_rn(__fadd_rn(rs[ry + 8][rx], rs[ry + 2][rx]), GK2, v);
-        v = __fmaf_rn(__fadd_rn(rs[ry + 9][rx], rs[ry + 1][rx]), GK1, v);
-        v = __fmaf_rn(__fadd_rn(rs[ry + 10][rx], rs[ry + 0][rx]), GK0, v);
+        if (x < n8) {
+            v = __fmaf_rn(__fadd_rn(rs[ry + 6][rx], rs[ry + 4][rx]), GK4, v);
+            v = __fmaf_rn(__fadd_rn(rs[ry + 7][rx], rs[ry + 3][rx]), GK3, v);
+            v = __fmaf_rn(__fadd_rn(rs[ry + 8][rx], rs[ry + 2][rx]), GK2, v);
+            v = __fmaf_rn(__fadd_rn(rs[ry + 9][rx], rs[ry + 1][rx]), GK1, v);
+            v = __fmaf_rn(__fadd_rn(rs[ry + 10][rx], rs[ry + 0][rx]), GK0, v);
+        } else {   // OpenCV's column filter: 8-wide FMA vectors, then separate multiply + add for the last w % 8 columns
+            v = __fadd_rn(__fmul_rn(__fadd_rn(rs[ry + 6][rx], rs[ry + 4][rx]), GK4), v);
+            v = __fadd_rn(__fmul_rn(__fadd_rn(rs[ry + 7][rx], rs[ry + 3][rx]), GK3), v);
+            v = __fadd_rn(__fmul_rn(__fadd_rn(rs[ry + 8][rx], rs[ry + 2][rx]), GK2), v);
+            v = __fadd_rn(__fmul_rn(__fadd_rn(rs[ry + 9][rx], rs[ry + 1][rx]), GK1), v);
+            v = __fadd_rn(__fmul_rn(__fadd_rn(rs[ry + 10][rx], rs[ry + 0][rx]), GK0), v);
+        }
         int mean = min(max(__float2int_rn(v), 0), 255);
         int px = tin[ry + 5][rx + 5];
         bool on = (px - mean) <= -C;

@@ -149,24 +149,67 @@ int llfe_destroy(llfe_ctx* ctx) {
 }
 
 int llfe_set_stream(llfe_ctx* ctx, void* cuda_stream) {
+    LLFE_ENTER(ctx);
     LLFE_CHECK_ARG(ctx != nullptr);
     ctx->stream = (cudaStream_t)cuda_stream;
     return LLFE_OK;
 }
 
 int llfe_use_own_stream(llfe_ctx* ctx) {
+    LLFE_ENTER(ctx);
     LLFE_CHECK_ARG(ctx != nullptr);
     ctx->stream = ctx->own_stream;
     return LLFE_OK;
 }
 
+int llfe_set_option(llfe_ctx* ctx, const char* name, int64_t value) {
+    LLFE_ENTER(ctx);
+    LLFE_CHECK_ARG(name != nullptr);
+    if (!strcmp(name, "unfused")) ctx->opt_unfused = value != 0;
+    else if (!strcmp(name, "hyst_strips")) ctx->opt_hyst_strips = value != 0;
+    else {
+        llfe_set_error("llfe_set_option: unknown option '%s'", name);
+        return LLFE_E_INVALID;
+    }
+    return LLFE_OK;
+}
+
+int llfe_set_debug_buffer(llfe_ctx* ctx, const char* name, void* d_buf, size_t bytes) {
+    LLFE_ENTER(ctx);
+    LLFE_CHECK_ARG(name != nullptr);
+    if (d_buf) {   // must be device memory of this context's device, at least `bytes` long as far as CUDA can tell
+        cudaPointerAttributes at;
+        cudaError_t e = cudaPointerGetAttributes(&at, d_buf);
+        if (e != cudaSuccess || at.type != cudaMemoryTypeDevice || at.device != ctx->device) {
+            cudaGetLastError();
+            llfe_set_error("llfe_set_debug_buffer: %p is not device memory of device %d", d_buf, ctx->device);
+            return LLFE_E_INVALID;
+        }
+    } else {
+        bytes = 0;
+    }
+    if (!strcmp(name, "kmeans")) {
+        ctx->dbg_kmeans = (unsigned long long*)d_buf;
+        ctx->dbg_kmeans_bytes = bytes;
+    } else if (!strcmp(name, "hysteresis")) {
+        ctx->dbg_hyst = (unsigned long long*)d_buf;
+        ctx->dbg_hyst_bytes = bytes;
+    } else {
+        llfe_set_error("llfe_set_debug_buffer: unknown buffer '%s'", name);
+        return LLFE_E_INVALID;
+    }
+    return LLFE_OK;
+}
+
 int llfe_sync(llfe_ctx* ctx) {
+    LLFE_ENTER(ctx);
     LLFE_CHECK_ARG(ctx != nullptr);
     LLFE_CUDA(cudaStreamSynchronize(ctx->stream));
     return LLFE_OK;
 }
 
 int llfe_profile_begin(llfe_ctx* ctx) {
+    LLFE_ENTER(ctx);
     LLFE_CHECK_ARG(ctx != nullptr);
     if (!ctx->prof) {
         ctx->prof_cap = 1 << 16;
@@ -180,6 +223,7 @@ int llfe_profile_begin(llfe_ctx* ctx) {
 }
 
 int llfe_profile_end(llfe_ctx* ctx, char* json, size_t cap) {
+    LLFE_ENTER(ctx);
     LLFE_CHECK_ARG(ctx != nullptr && json != nullptr && cap >= 64);
     ctx->prof_on = false;
     LLFE_CUDA(cudaStreamSynchronize(ctx->stream));
@@ -219,12 +263,13 @@ uint64_t llfe_launch_count(llfe_ctx* ctx) { return ctx ? ctx->launches : 0; }
 int llfe_sm_count(llfe_ctx* ctx) { return ctx ? ctx->sm_count : 0; }
 
 int llfe_malloc(llfe_ctx* ctx, size_t bytes, void** d_out) {
-    LLFE_CHECK_ARG(ctx != nullptr && d_out != nullptr);
-    LLFE_CUDA(cudaSetDevice(ctx->device));
+    LLFE_ENTER(ctx);
+    LLFE_CHECK_ARG(d_out != nullptr);
     LLFE_CUDA(cudaMalloc(d_out, bytes ? bytes : 1));
     return LLFE_OK;
 }
 int llfe_free(llfe_ctx* ctx, void* d_ptr) {
+    LLFE_ENTER(ctx);
     LLFE_CHECK_ARG(ctx != nullptr);
     if (d_ptr) {
         LLFE_CUDA(cudaStreamSynchronize(ctx->stream));
@@ -233,26 +278,31 @@ int llfe_free(llfe_ctx* ctx, void* d_ptr) {
     return LLFE_OK;
 }
 int llfe_malloc_host(llfe_ctx* ctx, size_t bytes, void** h_out) {
+    LLFE_ENTER(ctx);
     LLFE_CHECK_ARG(ctx != nullptr && h_out != nullptr);
     LLFE_CUDA(cudaMallocHost(h_out, bytes ? bytes : 1));
     return LLFE_OK;
 }
 int llfe_free_host(llfe_ctx* ctx, void* h_ptr) {
+    LLFE_ENTER(ctx);
     LLFE_CHECK_ARG(ctx != nullptr);
     if (h_ptr) LLFE_CUDA(cudaFreeHost(h_ptr));
     return LLFE_OK;
 }
 int llfe_memcpy_h2d(llfe_ctx* ctx, void* d_dst, const void* h_src, size_t bytes) {
+    LLFE_ENTER(ctx);
     LLFE_CHECK_ARG(ctx != nullptr);
     if (bytes) LLFE_CUDA(cudaMemcpyAsync(d_dst, h_src, bytes, cudaMemcpyHostToDevice, ctx->stream));
     return LLFE_OK;
 }
 int llfe_memcpy_d2h(llfe_ctx* ctx, void* h_dst, const void* d_src, size_t bytes) {
+    LLFE_ENTER(ctx);
     LLFE_CHECK_ARG(ctx != nullptr);
     if (bytes) LLFE_CUDA(cudaMemcpyAsync(h_dst, d_src, bytes, cudaMemcpyDeviceToHost, ctx->stream));
     return LLFE_OK;
 }
 int llfe_memset(llfe_ctx* ctx, void* d_dst, int value, size_t bytes) {
+    LLFE_ENTER(ctx);
     LLFE_CHECK_ARG(ctx != nullptr);
     if (bytes) LLFE_CUDA(cudaMemsetAsync(d_dst, value, bytes, ctx->stream));
     return LLFE_OK;
@@ -262,12 +312,14 @@ int llfe_memset(llfe_ctx* ctx, void* d_dst, int value, size_t bytes) {
 
 // ---- pointwise ----------------------------------------------------------------
 int llfe_bgr2gray(llfe_ctx* ctx, const uint8_t* d_bgr, int n, int h, int w, uint8_t* d_gray) {
+    LLFE_ENTER(ctx);
     LLFE_IMG_ARGS(d_bgr);
     LLFE_CHECK_ARG(d_gray != nullptr);
     return launch_bgr2gray(ctx, d_bgr, (size_t)n * h * w, d_gray);
 }
 
 int llfe_bgr2rgb(llfe_ctx* ctx, const uint8_t* d_bgr, int n, int h, int w, uint8_t* d_rgb) {
+    LLFE_ENTER(ctx);
     LLFE_IMG_ARGS(d_bgr);
     LLFE_CHECK_ARG(d_rgb != nullptr);
     return launch_bgr2rgb(ctx, d_bgr, (size_t)n * h * w, d_rgb);
@@ -275,18 +327,21 @@ int llfe_bgr2rgb(llfe_ctx* ctx, const uint8_t* d_bgr, int n, int h, int w, uint8
 
 int llfe_convert_scale_abs(llfe_ctx* ctx, const uint8_t* d_src, size_t count, float a1, float a2, int single,
                            uint8_t* d_dst) {
+    LLFE_ENTER(ctx);
     LLFE_CHECK_ARG(ctx != nullptr && d_src != nullptr && d_dst != nullptr);
     return launch_lut2(ctx, d_src, count, a1, a2, single, d_dst);
 }
 
 // ---- blur -------------------------------------------------------------------
 int llfe_gaussian_blur5(llfe_ctx* ctx, const uint8_t* d_src, int n, int h, int w, int c, uint8_t* d_dst) {
+    LLFE_ENTER(ctx);
     LLFE_IMG_ARGS(d_src);
     LLFE_CHECK_ARG(d_dst != nullptr && (c == 1 || c == 3) && d_src != d_dst);
     return launch_blur5(ctx, d_src, n, h, w, c, d_dst);
 }
 
 int llfe_gray_blur5(llfe_ctx* ctx, const uint8_t* d_bgr, int n, int h, int w, uint8_t* d_blurred) {
+    LLFE_ENTER(ctx);
     LLFE_IMG_ARGS(d_bgr);
     LLFE_CHECK_ARG(d_blurred != nullptr);
     return launch_gray_blur5(ctx, d_bgr, n, h, w, d_blurred);
@@ -297,7 +352,7 @@ int llfe_gray_blur5(llfe_ctx* ctx, const uint8_t* d_bgr, int n, int h, int w, ui
 // fit in shared memory, else the multi-launch strip kernels + the expand kernel.
 static int hysteresis_to_mask(llfe_ctx* ctx, const uint32_t* weak, uint32_t* edges, int n, int h, int w,
                               uint32_t* flags, int dilate, uint8_t* d_out) {
-    if (!getenv("LLFE_HYST_STRIPS")) {
+    if (!ctx->opt_hyst_strips) {
         const int rc = launch_hysteresis_mask_cluster(ctx, weak, edges, n, h, w, dilate, d_out);
         if (rc != LLFE_E_UNSUPPORTED) return rc;
     }
@@ -322,6 +377,7 @@ static size_t canny_ws_bytes(int n, int h, int w) {
 }
 
 int llfe_canny(llfe_ctx* ctx, const uint8_t* d_gray, int n, int h, int w, int low, int high, uint8_t* d_edges) {
+    LLFE_ENTER(ctx);
     LLFE_IMG_ARGS(d_gray);
     LLFE_CHECK_ARG(d_edges != nullptr);
     if ((size_t)n * h * w == 0) return LLFE_OK;
@@ -332,6 +388,7 @@ int llfe_canny(llfe_ctx* ctx, const uint8_t* d_gray, int n, int h, int w, int lo
 
 int llfe_hysteresis(llfe_ctx* ctx, const uint8_t* d_weak, const uint8_t* d_strong, int n, int h, int w, int dilate,
                     uint8_t* d_edges) {
+    LLFE_ENTER(ctx);
     LLFE_IMG_ARGS(d_weak);
     LLFE_CHECK_ARG(d_strong != nullptr && d_edges != nullptr);
     if ((size_t)n * h * w == 0) return LLFE_OK;
@@ -348,16 +405,18 @@ int llfe_hysteresis(llfe_ctx* ctx, const uint8_t* d_weak, const uint8_t* d_stron
 }
 
 int llfe_dilate3(llfe_ctx* ctx, const uint8_t* d_src, int n, int h, int w, uint8_t* d_dst) {
+    LLFE_ENTER(ctx);
     LLFE_IMG_ARGS(d_src);
     LLFE_CHECK_ARG(d_dst != nullptr && d_src != d_dst);
     return launch_dilate3_u8(ctx, d_src, n, h, w, d_dst);
 }
 
 int llfe_shape_mask(llfe_ctx* ctx, const uint8_t* d_bgr, int n, int h, int w, int low, int high, uint8_t* d_mask) {
+    LLFE_ENTER(ctx);
     LLFE_IMG_ARGS(d_bgr);
     LLFE_CHECK_ARG(d_mask != nullptr);
     if ((size_t)n * h * w == 0) return LLFE_OK;
-    if (fused_supported(h, w) && !getenv("LLFE_UNFUSED"))
+    if (fused_supported(h, w) && !ctx->opt_unfused)
         return llfe_pipeline(ctx, d_bgr, n, h, w, low, high, d_mask, nullptr, nullptr, nullptr, 0, nullptr, nullptr, 0);
     const size_t img = WsCarver::need((size_t)n * h * w);
     void* ws;
@@ -370,6 +429,7 @@ int llfe_shape_mask(llfe_ctx* ctx, const uint8_t* d_bgr, int n, int h, int w, in
 // ---- thresholds ---------------------------------------------------------------
 int llfe_adaptive_threshold(llfe_ctx* ctx, const uint8_t* d_gray, int n, int h, int w, int C, uint8_t* d_mask,
                             uint64_t* d_sum_count) {
+    LLFE_ENTER(ctx);
     LLFE_IMG_ARGS(d_gray);
     LLFE_CHECK_ARG(d_mask != nullptr);
     return launch_adaptive(ctx, d_gray, n, h, w, C, d_mask, d_sum_count);
@@ -377,10 +437,11 @@ int llfe_adaptive_threshold(llfe_ctx* ctx, const uint8_t* d_gray, int n, int h, 
 
 int llfe_shadow_mask(llfe_ctx* ctx, const uint8_t* d_bgr, int n, int h, int w, uint8_t* d_mask, uint8_t* d_blurred,
                      uint64_t* d_sum_count) {
+    LLFE_ENTER(ctx);
     LLFE_IMG_ARGS(d_bgr);
     LLFE_CHECK_ARG(d_mask != nullptr);
     if ((size_t)n * h * w == 0) return LLFE_OK;
-    if (!d_blurred && fused_supported(h, w) && !getenv("LLFE_UNFUSED"))
+    if (!d_blurred && fused_supported(h, w) && !ctx->opt_unfused)
         return llfe_pipeline(ctx, d_bgr, n, h, w, 50, 150, nullptr, d_mask, d_sum_count, nullptr, 0, nullptr, nullptr, 0);
     uint8_t* blurred = d_blurred;
     if (!blurred) {
@@ -393,6 +454,7 @@ int llfe_shadow_mask(llfe_ctx* ctx, const uint8_t* d_bgr, int n, int h, int w, u
 }
 
 int llfe_font_mask(llfe_ctx* ctx, const uint8_t* d_bgr, int n, int h, int w, uint8_t* d_mask) {
+    LLFE_ENTER(ctx);
     LLFE_IMG_ARGS(d_bgr);
     LLFE_CHECK_ARG(d_mask != nullptr);
     if ((size_t)n * h * w == 0) return LLFE_OK;
@@ -419,6 +481,7 @@ static size_t otsu_ws_bytes(int n) {
 
 int llfe_otsu(llfe_ctx* ctx, const uint8_t* d_gray, int n, int h, int w, int invert_if_light, uint8_t* d_mask,
               int32_t* d_thresh) {
+    LLFE_ENTER(ctx);
     LLFE_IMG_ARGS(d_gray);
     LLFE_CHECK_ARG(d_mask != nullptr);
     if ((size_t)n * h * w == 0) return LLFE_OK;
@@ -428,6 +491,7 @@ int llfe_otsu(llfe_ctx* ctx, const uint8_t* d_gray, int n, int h, int w, int inv
 }
 
 int llfe_text_mask(llfe_ctx* ctx, const uint8_t* d_bgr, int n, int h, int w, uint8_t* d_mask, int32_t* d_thresh) {
+    LLFE_ENTER(ctx);
     LLFE_IMG_ARGS(d_bgr);
     LLFE_CHECK_ARG(d_mask != nullptr);
     if ((size_t)n * h * w == 0) return LLFE_OK;
@@ -443,11 +507,12 @@ int llfe_text_mask(llfe_ctx* ctx, const uint8_t* d_bgr, int n, int h, int w, uin
 int llfe_pipeline(llfe_ctx* ctx, const uint8_t* d_bgr, int n, int h, int w, int low, int high, uint8_t* d_shape_mask,
                   uint8_t* d_shadow_mask, uint64_t* d_shadow_sum_count, const int8_t* d_noise, uint64_t seed,
                   uint32_t* d_keys, int32_t* d_count, int max_unique) {
+    LLFE_ENTER(ctx);
     LLFE_IMG_ARGS(d_bgr);
     LLFE_CHECK_ARG(h > 0 && w > 0);
     LLFE_CHECK_ARG(d_keys == nullptr || (d_count != nullptr && max_unique > 0));
     if (n == 0) return LLFE_OK;
-    if (fused_supported(h, w) && !getenv("LLFE_UNFUSED")) {
+    if (fused_supported(h, w) && !ctx->opt_unfused) {
         // One read of the image: planes + shadow mask + colour bitmap, then the small post-passes.
         // The front kernel runs in chunks of 32 images so that the 2 MiB bitmaps of a chunk stay in L2;
         // the hysteresis is latency-bound (a few busy warps per image), so it runs once per super-chunk
@@ -496,7 +561,7 @@ int llfe_pipeline(llfe_ctx* ctx, const uint8_t* d_bgr, int n, int h, int w, int 
         if (d_shape_mask) LLFE_TRY(canny_from_gray(ctx, blurred, n, h, w, low, high, 1, d_shape_mask, (char*)ws + img));
         if (d_shadow_mask) LLFE_TRY(launch_adaptive(ctx, blurred, n, h, w, 2, d_shadow_mask, d_shadow_sum_count));
     }
-    if (d_keys) LLFE_TRY(launch_unique_colors(ctx, d_bgr, n, h, w, d_noise, seed, d_keys, nullptr, d_count, max_unique));
+    if (d_keys) LLFE_TRY(launch_unique_colors(ctx, d_bgr, n, h, w, d_noise, seed, 0, d_keys, nullptr, d_count, max_unique));
     return LLFE_OK;
 }
 
@@ -531,6 +596,7 @@ static int stage_end(HostStage* st, void* h_out, size_t out_bytes, size_t d_off)
 }
 
 int llfe_shape_mask_host(llfe_ctx* ctx, const uint8_t* h_bgr, int h, int w, int low, int high, uint8_t* h_mask) {
+    LLFE_ENTER(ctx);
     LLFE_CHECK_ARG(ctx != nullptr && h_bgr != nullptr && h_mask != nullptr && h > 0 && w > 0);
     const size_t p = (size_t)h * w;
     HostStage st;
@@ -541,6 +607,7 @@ int llfe_shape_mask_host(llfe_ctx* ctx, const uint8_t* h_bgr, int h, int w, int 
 
 int llfe_shadow_mask_host(llfe_ctx* ctx, const uint8_t* h_bgr, int h, int w, uint8_t* h_mask, uint8_t* h_blurred,
                           uint64_t* h_sum_count) {
+    LLFE_ENTER(ctx);
     LLFE_CHECK_ARG(ctx != nullptr && h_bgr != nullptr && h > 0 && w > 0 && (h_mask || h_sum_count));
     const size_t p = (size_t)h * w, pa = WsCarver::need(p);
     HostStage st;
@@ -560,6 +627,7 @@ int llfe_shadow_mask_host(llfe_ctx* ctx, const uint8_t* h_bgr, int h, int w, uin
 }
 
 int llfe_text_mask_host(llfe_ctx* ctx, const uint8_t* h_bgr, int h, int w, uint8_t* h_mask, int32_t* h_thresh) {
+    LLFE_ENTER(ctx);
     LLFE_CHECK_ARG(ctx != nullptr && h_bgr != nullptr && h_mask != nullptr && h > 0 && w > 0);
     const size_t p = (size_t)h * w, pa = WsCarver::need(p);
     HostStage st;
@@ -575,6 +643,7 @@ int llfe_text_mask_host(llfe_ctx* ctx, const uint8_t* h_bgr, int h, int w, uint8
 }
 
 int llfe_font_mask_host(llfe_ctx* ctx, const uint8_t* h_bgr, int h, int w, uint8_t* h_mask) {
+    LLFE_ENTER(ctx);
     LLFE_CHECK_ARG(ctx != nullptr && h_bgr != nullptr && h_mask != nullptr && h > 0 && w > 0);
     const size_t p = (size_t)h * w;
     HostStage st;
@@ -585,7 +654,9 @@ int llfe_font_mask_host(llfe_ctx* ctx, const uint8_t* h_bgr, int h, int w, uint8
 
 int llfe_dominant_colors_host(llfe_ctx* ctx, const uint8_t* h_bgr, int h, int w, const int8_t* h_noise, uint64_t seed,
                               int k, int attempts, int max_iter, double eps, uint64_t rng_state, float* h_centers,
-                              int32_t* h_labels, int32_t* h_n_unique, int32_t* h_k_used, double* h_compactness) {
+                              int32_t* h_labels, int32_t* h_n_unique, int32_t* h_k_used, double* h_compactness,
+                              uint32_t* h_keys, int32_t* h_status) {
+    LLFE_ENTER(ctx);
     LLFE_CHECK_ARG(ctx != nullptr && h_bgr != nullptr && h_centers != nullptr && h_labels != nullptr &&
                    h_n_unique != nullptr && h_k_used != nullptr && h > 0 && w > 0 && k >= 1);
     const size_t p = (size_t)h * w;
@@ -609,19 +680,21 @@ int llfe_dominant_colors_host(llfe_ctx* ctx, const uint8_t* h_bgr, int h, int w,
     int32_t* d_kused = (int32_t*)(d_small + 8);
     uint64_t* d_rng = (uint64_t*)(d_small + 16);
     double* d_comp = (double*)(d_small + 24);
+    int32_t* d_status = (int32_t*)(d_small + 32);
     float* d_centers = (float*)(d_small + 64);         // k*3 floats (k <= 32)
     uint8_t* p_small = pin + in_bytes + lab_b;
     memcpy(p_small + 16, &rng_state, 8);
     LLFE_CUDA(cudaMemcpyAsync(d_rng, p_small + 16, 8, cudaMemcpyHostToDevice, ctx->stream));
-    LLFE_TRY(llfe_unique_colors(ctx, d_img, 1, h, w, d_noise, seed, d_keys, nullptr, d_count, max_unique));
+    LLFE_TRY(llfe_unique_colors(ctx, d_img, 1, h, w, d_noise, seed, 0, d_keys, nullptr, d_count, max_unique));
     LLFE_TRY(llfe_kmeans_unique(ctx, d_keys, d_count, 1, max_unique, k, attempts, max_iter, eps, d_rng, d_centers, d_labels,
-                                d_comp, d_kused, nullptr));
+                                d_comp, d_kused, nullptr, d_status));
     LLFE_CUDA(cudaMemcpyAsync(p_small, d_small, 64 + (size_t)k * 12, cudaMemcpyDeviceToHost, ctx->stream));
     LLFE_CUDA(cudaStreamSynchronize(ctx->stream));
     int32_t n_unique = *(int32_t*)p_small;
     *h_n_unique = n_unique;
     *h_k_used = *(int32_t*)(p_small + 8);
     if (h_compactness) *h_compactness = *(double*)(p_small + 24);
+    if (h_status) *h_status = *(int32_t*)(p_small + 32);
     memcpy(h_centers, p_small + 64, (size_t)k * 12);
     const size_t nl = (size_t)(n_unique < max_unique ? n_unique : max_unique);
     if (nl) {
@@ -629,12 +702,18 @@ int llfe_dominant_colors_host(llfe_ctx* ctx, const uint8_t* h_bgr, int h, int w,
         LLFE_CUDA(cudaMemcpyAsync(p_lab, d_labels, nl * 4, cudaMemcpyDeviceToHost, ctx->stream));
         LLFE_CUDA(cudaStreamSynchronize(ctx->stream));
         memcpy(h_labels, p_lab, nl * 4);
+        if (h_keys) {
+            LLFE_CUDA(cudaMemcpyAsync(p_lab, d_keys, nl * 4, cudaMemcpyDeviceToHost, ctx->stream));
+            LLFE_CUDA(cudaStreamSynchronize(ctx->stream));
+            memcpy(h_keys, p_lab, nl * 4);
+        }
     }
     return LLFE_OK;
 }
 
 int llfe_convert_scale_abs_host(llfe_ctx* ctx, const uint8_t* h_src, size_t count, float a1, float a2, int single,
                                 uint8_t* h_dst) {
+    LLFE_ENTER(ctx);
     LLFE_CHECK_ARG(ctx != nullptr && h_src != nullptr && h_dst != nullptr);
     if (count == 0) return LLFE_OK;
     HostStage st;
@@ -644,6 +723,7 @@ int llfe_convert_scale_abs_host(llfe_ctx* ctx, const uint8_t* h_src, size_t coun
 }
 
 int llfe_gaussian_blur5_host(llfe_ctx* ctx, const uint8_t* h_src, int h, int w, int c, uint8_t* h_dst) {
+    LLFE_ENTER(ctx);
     LLFE_CHECK_ARG(ctx != nullptr && h_src != nullptr && h_dst != nullptr && h > 0 && w > 0 && (c == 1 || c == 3));
     const size_t b = (size_t)h * w * c;
     HostStage st;
@@ -653,6 +733,7 @@ int llfe_gaussian_blur5_host(llfe_ctx* ctx, const uint8_t* h_src, int h, int w, 
 }
 
 int llfe_resize_area_host(llfe_ctx* ctx, const uint8_t* h_src, int sh, int sw, int c, uint8_t* h_dst, int dh, int dw) {
+    LLFE_ENTER(ctx);
     LLFE_CHECK_ARG(ctx != nullptr && h_src != nullptr && h_dst != nullptr && sh > 0 && sw > 0 && dh > 0 && dw > 0);
     const size_t in = (size_t)sh * sw * c, out = (size_t)dh * dw * c;
     HostStage st;
@@ -662,6 +743,7 @@ int llfe_resize_area_host(llfe_ctx* ctx, const uint8_t* h_src, int sh, int sw, i
 }
 
 int llfe_resize_linear_host(llfe_ctx* ctx, const uint8_t* h_src, int sh, int sw, int c, uint8_t* h_dst, int dh, int dw) {
+    LLFE_ENTER(ctx);
     LLFE_CHECK_ARG(ctx != nullptr && h_src != nullptr && h_dst != nullptr && sh > 0 && sw > 0 && dh > 0 && dw > 0);
     const size_t in = (size_t)sh * sw * c, out = (size_t)dh * dw * c;
     HostStage st;
@@ -671,6 +753,7 @@ int llfe_resize_linear_host(llfe_ctx* ctx, const uint8_t* h_src, int sh, int sw,
 }
 
 int llfe_resize_lanczos4_host(llfe_ctx* ctx, const uint8_t* h_src, int sh, int sw, int c, uint8_t* h_dst, int dh, int dw) {
+    LLFE_ENTER(ctx);
     LLFE_CHECK_ARG(ctx != nullptr && h_src != nullptr && h_dst != nullptr && sh > 0 && sw > 0 && dh > 0 && dw > 0);
     const size_t in = (size_t)sh * sw * c, out = (size_t)dh * dw * c;
     HostStage st;

@@ -32,6 +32,14 @@ struct llfe_ctx {
     struct ProfRec* prof = nullptr;
     int prof_cap = 0, prof_used = 0, prof_events = 0, prof_pending = -1;
     bool prof_on = false;
+    // llfe_set_option: path toggles used by the parity tests (both off in production)
+    bool opt_unfused = false;      // per-stage kernels instead of the fused front kernel
+    bool opt_hyst_strips = false;  // multi-launch strip hysteresis instead of the cluster kernel
+    // llfe_set_debug_buffer: validated device buffers the k-means / hysteresis kernels write phase clocks to
+    unsigned long long* dbg_kmeans = nullptr;
+    size_t dbg_kmeans_bytes = 0;
+    unsigned long long* dbg_hyst = nullptr;
+    size_t dbg_hyst_bytes = 0;
 };
 
 struct ProfRec {
@@ -70,6 +78,33 @@ int llfe_cuda_fail(cudaError_t e, const char* what, const char* file, int line);
             return LLFE_E_INVALID;                                            \
         }                                                                     \
     } while (0)
+
+// First statement of every extern "C" entry point that takes a context: the calling thread may have another
+// device current (a request-handler thread pool, torch's own device guard), and everything below -- workspace
+// and staging allocations, kernel launches, function attributes -- must land on the context's device.  The
+// caller's current device is restored on return.
+struct LlfeDeviceGuard {
+    int prev = -1;
+    bool switched = false;
+    cudaError_t err = cudaSuccess;
+    explicit LlfeDeviceGuard(int device) {
+        err = cudaGetDevice(&prev);
+        if (err == cudaSuccess && prev != device) {
+            err = cudaSetDevice(device);
+            switched = err == cudaSuccess;
+        }
+    }
+    ~LlfeDeviceGuard() {
+        if (switched) cudaSetDevice(prev);
+    }
+};
+#define LLFE_ENTER(ctx)                                                        \
+    if (!(ctx)) {                                                              \
+        llfe_set_error("%s: invalid argument: ctx is null", __func__);         \
+        return LLFE_E_INVALID;                                                 \
+    }                                                                          \
+    LlfeDeviceGuard _llfe_guard((ctx)->device);                                \
+    if (_llfe_guard.err != cudaSuccess) return llfe_cuda_fail(_llfe_guard.err, "cudaSetDevice", __FILE__, __LINE__)
 
 #define LLFE_TRY(expr)                \
     do {                              \
@@ -135,7 +170,7 @@ size_t hysteresis_flag_words(int n, int h);
 int launch_dilate3_u8(llfe_ctx* ctx, const uint8_t* src, int n, int h, int w, uint8_t* dst);
 void llfe_free_area_tabs(llfe_ctx* ctx);
 int launch_unique_colors(llfe_ctx* ctx, const uint8_t* d_bgr, int n, int h, int w, const int8_t* d_noise, uint64_t seed,
-                         uint32_t* d_keys, uint32_t* d_hist, int32_t* d_count, int max_unique);
+                         int first_image, uint32_t* d_keys, uint32_t* d_hist, int32_t* d_count, int max_unique);
 
 size_t bitmap_words_per_image();
 size_t bitmap_blocks_per_image();

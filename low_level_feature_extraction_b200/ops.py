@@ -250,12 +250,13 @@ class Engine:
 
     # -- palette ------------------------------------------------------------------
     def unique_colors(self, bgr: torch.Tensor, noise: torch.Tensor | None = None, seed: int = 0,
-                      max_unique: int = 1 << 16, with_counts: bool = False):
+                      max_unique: int = 1 << 16, with_counts: bool = False, first_image: int = 0):
         """np.unique(noised RGB pixels, axis=0) per image.
 
         noise: int8 (n,h,w,3) tensor in RGB order (the reference's
         `np.random.normal(0, 0.5, pixels.shape).astype(np.int8)`), or None to
-        generate noise of the same distribution on the device from `seed`.
+        generate noise of the same distribution on the device from `seed` (a pure function of
+        seed, first_image + i and the pixel position).
         -> (keys uint32-as-int32 (n,max_unique) = R<<16|G<<8|B ascending,
             count int32 (n,)[, pixel counts int32 (n,max_unique)])."""
         x, single = _batch(bgr, 3)
@@ -268,8 +269,8 @@ class Engine:
         count = self._empty((n,), torch.int32)
         hist = self._empty((n, max_unique), torch.int32) if with_counts else None
         self._bind()
-        self.ctx.call("llfe_unique_colors", x, n, h, w, noise, int(seed) & 0xFFFFFFFFFFFFFFFF, keys, hist, count,
-                      int(max_unique))
+        self.ctx.call("llfe_unique_colors", x, n, h, w, noise, int(seed) & 0xFFFFFFFFFFFFFFFF, int(first_image), keys,
+                      hist, count, int(max_unique))
         res = (keys, count, hist) if with_counts else (keys, count)
         return tuple(t[0] for t in res) if single else res
 
@@ -278,7 +279,8 @@ class Engine:
         """cv2.kmeans(float32(unique), k, None, (EPS+MAX_ITER, max_iter, eps), attempts, KMEANS_PP_CENTERS)
         per image.  rng_state: int or sequence of ints (cv::RNG state; cv2.setRNGSeed(s) => s).
         -> (centers float32 (n,k,3) RGB, labels int32 (n,max_unique), compactness float64 (n,), k_used int32 (n,)).
-        self.last_cluster_sizes holds np.bincount(labels) per image (int32 (n,k))."""
+        self.last_cluster_sizes holds np.bincount(labels) per image (int32 (n,k)), self.last_status the
+        LLFE_KMEANS_* bits per image (1 = long float32 sums reproduced, 2 = list truncated: k_used = -1)."""
         if keys.dim() == 1:
             keys, count = keys.unsqueeze(0), count.reshape(1)
         n, max_unique = keys.shape
@@ -289,11 +291,25 @@ class Engine:
         comp = self._empty((n,), torch.float64)
         kused = self._empty((n,), torch.int32)
         sizes = self._empty((n, k), torch.int32)
+        status = self._empty((n,), torch.int32)
         self._bind()
         self.ctx.call("llfe_kmeans_unique", keys.contiguous(), count.contiguous(), n, max_unique, int(k), int(attempts),
-                      int(max_iter), float(eps), rs, centers, labels, comp, kused, sizes)
+                      int(max_iter), float(eps), rs, centers, labels, comp, kused, sizes, status)
         self.last_cluster_sizes = sizes
+        self.last_status = status
         return centers, labels, comp, kused
+
+    def palette_large(self, bgr_image: torch.Tensor, n_unique: int, k: int, rng_state: int, seed: int = 0,
+                      first_image: int = 0, noise: torch.Tensor | None = None, attempts: int = 10, max_iter: int = 200,
+                      eps: float = 0.2):
+        """The palette of ONE image whose unique-colour list has n_unique entries (any length up to 2^24): the
+        list is sized from n_unique instead of a batch-wide capacity.  Same noise as the batch call that counted the
+        colours when (seed, first_image) are that call's seed and the image's index in it.
+        -> (centers (k,3) f32, k_used (1,) i32, cluster_sizes (k,) i32, status (1,) i32) device tensors."""
+        cap = max(1, int(n_unique))
+        keys, count = self.unique_colors(bgr_image, noise, seed=seed, max_unique=cap, first_image=first_image)
+        centers, _, _, kused = self.kmeans_unique(keys, count, k, rng_state, attempts, max_iter, eps)
+        return centers[0], kused, self.last_cluster_sizes[0], self.last_status
 
     def kmeans_lloyd(self, keys: torch.Tensor, count: torch.Tensor, init_centers: torch.Tensor,
                      weights: torch.Tensor | None = None, exact_sums: bool = False, max_iter: int = 200,

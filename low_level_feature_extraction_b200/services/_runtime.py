@@ -30,11 +30,21 @@ def lock() -> threading.RLock:
 
 
 def as_bgr_u8(image: np.ndarray) -> np.ndarray:
-    """C-contiguous (H, W, 3) uint8 view/copy of a BGR image; raises like cv2 on bad input."""
+    """C-contiguous (H, W, 3) uint8 BGR array for the kernels, with the input contract of the cv2 calls the
+    service methods replace: `cv2.cvtColor(image, COLOR_BGR2GRAY)` followed by an 8-bit-only op (Canny,
+    adaptiveThreshold, Otsu).  3-channel uint8 passes through; 4-channel uint8 (BGRA) is accepted and its alpha
+    ignored, as cvtColor does; everything else -- not an ndarray, another channel count, another depth, an empty
+    image -- raises `cv2.error`, the exception the reference's callers see."""
+    import cv2
+
     if not isinstance(image, np.ndarray):
-        raise TypeError("Expected a numpy.ndarray image")
-    if image.ndim != 3 or image.shape[2] != 3 or image.dtype != np.uint8:
-        raise ValueError(f"Expected an (H, W, 3) uint8 BGR image, got shape {image.shape} dtype {image.dtype}")
+        raise cv2.error("cvtColor: Overload resolution failed: src is not a numpy array, neither a scalar")
+    if image.ndim != 3 or image.shape[2] not in (3, 4):
+        raise cv2.error(f"cvtColor: Invalid number of channels in input image: 'VScn::contains(scn)', shape {image.shape}")
     if image.shape[0] == 0 or image.shape[1] == 0:
-        raise ValueError("Empty image")
+        raise cv2.error("cvtColor: (-215:Assertion failed) !_src.empty()")
+    if image.dtype != np.uint8:
+        raise cv2.error(f"(-215:Assertion failed) depth == CV_8U: unsupported image depth {image.dtype}")
+    if image.shape[2] == 4:
+        image = image[:, :, :3]
     return np.ascontiguousarray(image)

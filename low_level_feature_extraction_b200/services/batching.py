@@ -152,8 +152,17 @@ class RequestBatcher:
                 fut = futs[i]
                 try:
                     k = int(k_used[i])
-                    c8 = centers[i, :k].astype(np.uint8)                      # color_extractor.py:197 truncation
-                    colors = ColorExtractor._palette_from_clusters(c8, sizes[i, :k].astype(np.int64) if k > 1 else None)
+                    if k < 0:
+                        raise RuntimeError("unique-colour list truncated and not resolved by the analyzer")
+                    if self.n_colors <= 1:
+                        # color_extractor.py:185-186 returns the whole unique list as "centres" in this case: take
+                        # the single-image path, which brings the list to the host (device noise, as the batch)
+                        c8, lab = ColorExtractor._dominant_from_bgr(items[i][0], None, self.n_colors)
+                        colors = ColorExtractor._palette_from_clusters(
+                            c8, np.bincount(lab, minlength=len(c8)) if len(c8) > 1 else None)
+                    else:
+                        c8 = centers[i, :k].astype(np.uint8)                  # color_extractor.py:197 truncation
+                        colors = ColorExtractor._palette_from_clusters(c8, sizes[i, :k].astype(np.int64) if k > 1 else None)
                     shape_mask = shape_masks[i].copy()
                     res = {"colors": colors,
                            "shapes": ShapeAnalyzer.shapes_from_mask(shape_mask, w, h) if self.shapes else None,

@@ -47,6 +47,7 @@ class ColorExtractor:
     noise_mode = "numpy"
     _rng_state = 0xFFFFFFFF      # cv::RNG default state (what cv2.setRNGSeed(0) gives)
     _device_seed = 0
+    last_status = 0              # LLFE_KMEANS_* bits of the last k-means call (1 = long float32 sums reproduced)
 
     # ---- seeding ----------------------------------------------------------------
     @classmethod
@@ -163,16 +164,28 @@ class ColorExtractor:
         n_unique = np.zeros(1, np.int32)
         k_used = np.zeros(1, np.int32)
         comp = np.zeros(1, np.float64)
+        status = np.zeros(1, np.int32)
+        # the unique list itself is what the reference returns when fewer than two clusters are asked for / possible
+        keys = np.empty(labels.shape, np.uint32) if k_req <= 1 else None
         nz = None if noise is None else np.ascontiguousarray(noise.reshape(h, w, 3))
         with _runtime.lock():
             cls._device_seed += 1
             _runtime.context().call("llfe_dominant_colors_host", bgr, h, w, nz, cls._device_seed, max(k_req, 1),
                                     cls.KMEANS_ATTEMPTS, cls.KMEANS_MAX_ITER, cls.KMEANS_EPS, cls._rng_state,
-                                    centers, labels, n_unique, k_used, comp)
+                                    centers, labels, n_unique, k_used, comp, keys, status)
         u, k = int(n_unique[0]), int(k_used[0])
+        cls.last_status = int(status[0])
         actual = min(k_req, u)
         if actual < k_req:
             print(f"Warning: Only {u} unique colors found, reducing number of clusters from {k_req} to {actual}")
+        if actual <= 1:
+            # color_extractor.py:185-186: `return unique_colors, np.array([0] * len(unique_colors))` -- ALL unique
+            # colours as "centres" (also for n_colors <= 1 on a many-coloured image), labels all zero
+            if keys is None:      # n_colors >= 2 but the image has a single colour: the centre is that colour
+                return centers[:u].astype(np.uint8), np.zeros(u, np.int64)
+            kk = keys[:u]
+            uniq = np.stack([(kk >> 16) & 255, (kk >> 8) & 255, kk & 255], axis=1).astype(np.uint8)
+            return uniq, np.zeros(u, np.int64)
         if k > 1:   # cv2 made 1 + 6 (K-1) draws per attempt
             cls._advance_rng(cls.KMEANS_ATTEMPTS * (1 + 6 * (k - 1)))
         # color_extractor.py:197 truncates float centres with astype(uint8)

@@ -179,19 +179,42 @@ def _fma(a: np.ndarray, b, c: np.ndarray) -> np.ndarray:
     return (a.astype(np.float64) * np.float64(b) + c.astype(np.float64)).astype(f32)
 
 
+def _mad(a: np.ndarray, b, c: np.ndarray) -> np.ndarray:
+    # separately rounded float32 multiply and add
+    return ((a.astype(f32) * f32(b)).astype(f32) + c.astype(f32)).astype(f32)
+
+
 def gauss11_f32(src_u8: np.ndarray) -> np.ndarray:
-    """11x11 sigma=2 Gaussian mean in float32 with OpenCV's exact op order:
-    row pass = left-to-right FMA chain, column pass = symmetric-pair FMA chain,
-    BORDER_REPLICATE."""
+    """11x11 sigma=2 Gaussian mean in float32 with the op order of the installed OpenCV binary
+    (cv2 4.13.0.92: what adaptiveThreshold's internal GaussianBlur(CV_32F, BORDER_REPLICATE) returns, compared
+    bit for bit on widths 2..49, 101, 203, 330, 1001, 1366, 1444, 1921, heights >= 2, 1 and 8 threads):
+      row pass    = left-to-right chain  s = k0*x[-5];  s = op(x[i-5], k[i], s), i = 1..10
+      column pass = symmetric-pair chain v = k5*r[0];   v = op(r[+i] + r[-i], k[5+i], v), i = 1..5
+    with op = fused multiply-add in the vectorised columns and separately rounded multiply + add in the tail:
+      row pass:    columns < n4 fused (8-wide, then one 4-wide vector); the last w % 4 columns run the scalar loop,
+                   whose compiled code is mul + add for taps 1..8 and fused for taps 9 and 10;
+      column pass: columns < n8 fused; the last w % 8 columns mul + add,
+    n8 = w - w % 8, n4 = n8 + 4 if w - n8 >= 4 else n8.  Widths that are a multiple of 8 (1920, 3840) have no tail.
+    (Images with a single row or column take another OpenCV code path and are not covered.)"""
     k = gaussian_kernel_f32(11)
     h, w = src_u8.shape
+    n8 = w - w % 8
+    n4 = n8 + 4 if w - n8 >= 4 else n8
     p = np.pad(src_u8.astype(f32), 5, mode="edge")
     s = (k[0] * p[:, 0:w]).astype(f32)
     for i in range(1, 11):
-        s = _fma(p[:, i:i + w], k[i], s)
+        x = p[:, i:i + w]
+        t = _fma(x, k[i], s)
+        if n4 < w and i <= 8:
+            t[:, n4:] = _mad(x[:, n4:], k[i], s[:, n4:])
+        s = t
     v = (k[5] * s[5:5 + h]).astype(f32)
     for i in range(1, 6):
-        v = _fma((s[5 + i:5 + i + h] + s[5 - i:5 - i + h]).astype(f32), k[5 + i], v)
+        pr = (s[5 + i:5 + i + h] + s[5 - i:5 - i + h]).astype(f32)
+        t = _fma(pr, k[5 + i], v)
+        if n8 < w:
+            t[:, n8:] = _mad(pr[:, n8:], k[5 + i], v[:, n8:])
+        v = t
     return v
 
 
@@ -649,10 +672,19 @@ def centers_update_exact(data_int: np.ndarray, labels: np.ndarray, k: int, weigh
     return centers, labels, sums, cnt
 
 
+def cv_max_count(max_iter: int) -> int:
+    """cv::kmeans clamps criteria.maxCount to [2, 100] (`std::min(std::max(criteria.maxCount, 2), 100)`):
+    the reference's 200 (color_extractor.py:190) is therefore 100 iterations.  Verified against the installed
+    cv2: maxCount 100, 101 and 200 give identical results on a slow-converging list, 99 differs
+    (tests/test_oracle_vs_cv2.py)."""
+    return min(max(int(max_iter), 2), 100)
+
+
 def lloyd_cv(data: np.ndarray, init_centers: np.ndarray, max_iter: int = 200, eps: float = 0.2):
     """cv2.kmeans(data,K,labels0,crit,1,KMEANS_USE_INITIAL_LABELS) with
     labels0 = assign(init_centers): plain Lloyd from given centres, f32 sums.
     Returns (centers, labels, iters, compactness)."""
+    max_iter = cv_max_count(max_iter)
     k = len(init_centers)
     eps2 = eps * eps
     labels, _ = assign(data, init_centers)
@@ -696,6 +728,7 @@ def lloyd_exact(data_u8: np.ndarray, init_centers: np.ndarray, max_iter: int = 2
 def cv_kmeans(data: np.ndarray, k: int, rng: CvRNG, attempts: int = 10, max_iter: int = 200, eps: float = 0.2):
     """Full cv2.kmeans(data, K, None, (EPS+MAX_ITER, max_iter, eps), attempts,
     KMEANS_PP_CENTERS).  Returns (compactness, labels, centers)."""
+    max_iter = cv_max_count(max_iter)
     eps2 = eps * eps
     best = (np.inf, None, None)
     for _ in range(attempts):

@@ -122,15 +122,15 @@ def test_4k_palette_k16(eng):
 
 
 def test_unfused_path_still_matches(eng):
-    """LLFE_UNFUSED=1 forces the per-stage kernels (the path odd widths take)."""
+    """The "unfused" option forces the per-stage kernels (the path odd widths take)."""
     img = design_image(96, 160, 1)
-    os.environ["LLFE_UNFUSED"] = "1"
+    eng.ctx.set_option("unfused", 1)
     try:
         out = eng.pipeline(dev(img[None]), colors=False)
         assert np.array_equal(out["shape_mask"][0].cpu().numpy(), cvops.shape_mask(img))
         assert np.array_equal(out["shadow_mask"][0].cpu().numpy(), cvops.shadow_parts(img)[1])
     finally:
-        del os.environ["LLFE_UNFUSED"]
+        eng.ctx.set_option("unfused", 0)
 
 
 def test_tall_image_single_column_of_bands(eng):

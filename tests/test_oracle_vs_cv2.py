@@ -45,9 +45,11 @@ def test_shape_mask_design():
     assert np.array_equal(cvops.shape_mask(img), refpath.shape_mask(img))
 
 
-@pytest.mark.parametrize("shape", [(64, 96), (53, 40), (11, 16), (135, 256), (30, 1920)])
+@pytest.mark.parametrize("shape", [(64, 96), (53, 40), (11, 16), (135, 256), (30, 1920), (45, 77), (33, 9), (20, 203),
+                                   (17, 1001), (12, 1366), (9, 1444), (7, 1921), (40, 67), (40, 69), (2, 13)]
+                         + [(6, w) for w in range(2, 41)])
 def test_adaptive(shape):
-    # widths are multiples of 8: OpenCV's scalar tail columns use a non-FMA path
+    # any width: the restatement follows OpenCV's vector body and its tail columns, float for float
     r = np.random.default_rng(shape[0])
     g = cv2.GaussianBlur(r.integers(0, 256, shape, dtype=np.uint8), (5, 5), 0)
     cvf = cv2.GaussianBlur(g.astype(np.float32), (11, 11), 0, borderType=cv2.BORDER_REPLICATE)
@@ -196,3 +198,21 @@ def test_extract_colors_matches_cv2_port():
         ref = refpath.extract_colors(img, 5)
         noise = cvops.make_noise((img.shape[0] * img.shape[1], 3), seed)
         assert cvops.extract_colors(img, 5, noise, seed) == ref
+
+
+def test_kmeans_max_count_is_clamped_to_100():
+    """cv::kmeans clamps criteria.maxCount to [2, 100]: the reference's 200 (color_extractor.py:190) means 100.
+    A slow-converging list with eps = 0: cv2 returns the same result for 100, 101 and 200, another one for 99,
+    and the restatement follows."""
+    r = np.random.default_rng(5)
+    data = r.integers(0, 256, (20000, 3)).astype(np.float32)
+    res = {}
+    for mc in (99, 100, 200):
+        cv2.setRNGSeed(7)
+        res[mc] = cv2.kmeans(data, 16, None, (cv2.TERM_CRITERIA_EPS + cv2.TERM_CRITERIA_MAX_ITER, mc, 0.0), 1,
+                             cv2.KMEANS_PP_CENTERS)
+    assert res[100][0] == res[200][0] and np.array_equal(res[100][1], res[200][1])
+    assert res[99][0] != res[100][0]
+    comp, labels, centers = cvops.cv_kmeans(data, 16, cvops.CvRNG(7), attempts=1, max_iter=200, eps=0.0)
+    assert np.array_equal(labels, res[200][1].ravel()) and np.array_equal(centers, res[200][2])
+    assert abs(comp - res[200][0]) <= 1e-9 * res[200][0]

@@ -65,3 +65,33 @@ def test_process_image_without_reference():
     assert ColorExtractor._process_image(None).shape == (100, 100, 3)
     g = INPUTS["gray2d"](r)
     assert np.array_equal(ColorExtractor._process_image(g), np.stack([g, g, g], -1))
+
+
+BAD_INPUTS = {
+    "gray2d": lambda r: r.integers(0, 256, (40, 120), dtype=np.uint8),
+    "two_ch": lambda r: r.integers(0, 256, (40, 120, 2), dtype=np.uint8),
+    "five_ch": lambda r: r.integers(0, 256, (40, 120, 5), dtype=np.uint8),
+    "float": lambda r: r.random((40, 120, 3)).astype(np.float32),
+    "u16": lambda r: r.integers(0, 60000, (40, 120, 3), dtype=np.uint16),
+    "empty": lambda r: np.zeros((0, 0, 3), np.uint8),
+    "list": lambda r: [[1, 2, 3]],
+    "none": lambda r: None,
+}
+
+
+@pytest.mark.parametrize("kind", sorted(BAD_INPUTS))
+def test_service_input_contract_raises_like_cv2(kind):
+    """Inputs the reference's cv2 calls reject raise cv2.error in the drop-in too (before any GPU work), checked
+    against the live reference classes where they are available."""
+    import cv2
+    from low_level_feature_extraction_b200.services import FontDetector, ShadowAnalyzer, ShapeAnalyzer
+
+    x = BAD_INPUTS[kind](np.random.default_rng(3))
+    for fn in (ShapeAnalyzer.preprocess_image, ShadowAnalyzer.analyze_shadow_level, FontDetector.preprocess_image):
+        with pytest.raises(cv2.error):
+            fn(x)
+    if load_reference.available():
+        ref = load_reference.load()
+        for fn in (ref["ShapeAnalyzer"].preprocess_image, ref["ShadowAnalyzer"].analyze_shadow_level):
+            with pytest.raises(cv2.error):
+                fn(x)

@@ -10,7 +10,7 @@ d=torch.from_numpy(base).cuda()
 dbg=torch.zeros((n,16,8),dtype=torch.int64,device='cuda')
 for _ in range(2): eng.shape_mask(d)
 torch.cuda.synchronize()
-os.environ["LLFE_HYST_DEBUG"]=str(dbg.data_ptr())
+eng.ctx.set_debug_buffer("hysteresis", dbg)
 e0,e1=torch.cuda.Event(enable_timing=True),torch.cuda.Event(enable_timing=True)
 e0.record(); eng.shape_mask(d); e1.record(); torch.cuda.synchronize()
 print("shape_mask ms", e0.elapsed_time(e1))

@@ -11,7 +11,7 @@ out=eng.pipeline(d, seed=1, max_unique=1<<16, shapes=False, shadows=False)
 dbg=torch.zeros((n,10,8),dtype=torch.int64,device='cuda')
 for _ in range(2): eng.kmeans_unique(out["keys"], out["count"], 5, [1000+i for i in range(n)])
 torch.cuda.synchronize()
-os.environ["LLFE_KMEANS_DEBUG"]=str(dbg.data_ptr())
+eng.ctx.set_debug_buffer("kmeans", dbg)
 e0,e1=torch.cuda.Event(enable_timing=True),torch.cuda.Event(enable_timing=True)
 e0.record(); eng.kmeans_unique(out["keys"], out["count"], 5, [1000+i for i in range(n)]); e1.record(); torch.cuda.synchronize()
 print("kmeans ms", e0.elapsed_time(e1), "for", n, "images")
