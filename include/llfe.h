@@ -63,7 +63,9 @@ int llfe_use_own_stream(llfe_ctx* ctx);
 int llfe_sync(llfe_ctx* ctx);
 /* Path toggles for parity tests (production leaves both 0): "unfused" = 1 runs the per-stage kernels
  * instead of the fused front kernel, "hyst_strips" = 1 the multi-launch strip hysteresis instead of the
- * cluster kernel.  Unknown names fail with LLFE_E_INVALID. */
+ * cluster kernel, "shadow_inline" = 1 the adaptive threshold inside the front kernel instead of k_shadow,
+ * "serial" = 1 one stream for the two chains of llfe_pipeline / llfe_analyze.  Unknown names fail with
+ * LLFE_E_INVALID. */
 int llfe_set_option(llfe_ctx* ctx, const char* name, int64_t value);
 /* Register a device buffer the "kmeans" / "hysteresis" kernels write per-CTA phase clocks to (tools/debug/);
  * d_buf = NULL switches the records off.  The pointer is validated with cudaPointerGetAttributes (device
@@ -313,6 +315,18 @@ int llfe_pixels_lookup(llfe_ctx* ctx, const uint8_t* d_bgr, size_t n_pixels, con
 int llfe_pipeline(llfe_ctx* ctx, const uint8_t* d_bgr, int n, int h, int w, int low, int high, uint8_t* d_shape_mask,
                   uint8_t* d_shadow_mask, uint64_t* d_shadow_sum_count, const int8_t* d_noise, uint64_t seed,
                   uint32_t* d_keys, int32_t* d_count, int max_unique);
+
+/* llfe_pipeline + llfe_kmeans_unique in ONE call (what BatchAnalyzer runs per batch): the mask chain (front kernel,
+ * shadow kernel, hysteresis) and the colour chain (colour pass, compaction, k-means) are independent, so the call
+ * enqueues them on two streams of the context -- forked from and joined back into the context's stream, i.e. to
+ * the caller it behaves like any other asynchronous call on that stream -- and the latency-bound kernels of one
+ * chain fill issue slots the other leaves idle.  Results are the same as the two separate calls
+ * (llfe_set_option(ctx, "serial", 1) keeps everything on one stream).  k-means arguments as llfe_kmeans_unique;
+ * d_keys / d_count are required (the lists the palette is computed from), d_labels may be NULL. */
+int llfe_analyze(llfe_ctx* ctx, const uint8_t* d_bgr, int n, int h, int w, int low, int high, uint8_t* d_shape_mask,
+                 uint8_t* d_shadow_mask, uint64_t* d_shadow_sum_count, const int8_t* d_noise, uint64_t seed, uint32_t* d_keys,
+                 int32_t* d_count, int max_unique, int k, int attempts, int max_iter, double eps, const uint64_t* d_rng_state,
+                 float* d_centers, int32_t* d_labels, int32_t* d_k_used, int32_t* d_cluster_sizes, int32_t* d_status);
 
 /* ---- host-buffer convenience entry points (single image, synchronous) ------ */
 int llfe_shape_mask_host(llfe_ctx* ctx, const uint8_t* h_bgr, int h, int w, int low, int high, uint8_t* h_mask);

@@ -78,6 +78,8 @@ PROTOTYPES = {
     "llfe_hist_labels_to_lut": (i32, [vp, vp, vp, sz, vp]),
     "llfe_pixels_lookup": (i32, [vp, vp, sz, vp, vp]),
     "llfe_pipeline": (i32, [vp, vp, i32, i32, i32, i32, i32, vp, vp, vp, vp, u64, vp, vp, i32]),
+    "llfe_analyze": (i32, [vp, vp, i32, i32, i32, i32, i32, vp, vp, vp, vp, u64, vp, vp, i32, i32, i32, i32, f64, vp, vp, vp, vp,
+                           vp, vp]),
     "llfe_shape_mask_host": (i32, [vp, vp, i32, i32, i32, i32, vp]),
     "llfe_shadow_mask_host": (i32, [vp, vp, i32, i32, vp, vp, vp]),
     "llfe_text_mask_host": (i32, [vp, vp, i32, i32, vp, vp]),

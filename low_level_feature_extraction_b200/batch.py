@@ -82,14 +82,19 @@ class BatchAnalyzer:
         for i0 in range(0, n, c.chunk):
             sl = slice(i0, min(n, i0 + c.chunk))
             view = {k: v[sl] for k, v in out.items()}
-            eng.pipeline(bgr[sl], shapes=c.shapes, shadows=c.shadows, colors=c.colors,
-                         noise=None if noise is None else noise[sl], seed=c.seed + i0, max_unique=c.max_unique,
-                         low=c.low, high=c.high, out=view)
             if c.colors:
+                # masks + unique colours + k-means in one call: its two chains run on two streams (llfe_analyze)
+                x = bgr[sl].contiguous()
+                nz = None if noise is None else noise[sl].contiguous()
                 eng._bind()
-                eng.ctx.call("llfe_kmeans_unique", view["keys"], view["count"], sl.stop - sl.start, c.max_unique, c.k,
-                             c.attempts, c.max_iter, float(c.eps), view["rng"], view["centers"], view["labels"], None,
-                             view["k_used"], view["cluster_sizes"], view["status"])
+                eng.ctx.call("llfe_analyze", x, sl.stop - sl.start, self.h, self.w, int(c.low), int(c.high),
+                             view["shape_mask"] if c.shapes else None, view["shadow_mask"] if c.shadows else None,
+                             view["shadow_sums"] if c.shadows else None, nz, (c.seed + i0) & 0xFFFFFFFFFFFFFFFF,
+                             view["keys"], view["count"], c.max_unique, c.k, c.attempts, c.max_iter, float(c.eps),
+                             view["rng"], view["centers"], view["labels"], view["k_used"], view["cluster_sizes"],
+                             view["status"])
+            else:
+                eng.pipeline(bgr[sl], shapes=c.shapes, shadows=c.shadows, colors=False, low=c.low, high=c.high, out=view)
         if c.colors and resolve:
             self.resolve_overflow(bgr, out, eng, noise)
         return out

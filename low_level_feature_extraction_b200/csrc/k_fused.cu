@@ -1,10 +1,10 @@
-// Fused front end of the colours + shapes + shadows pipeline: ONE read of the BGR image
-// produces
+// Fused front end of the shapes + shadows pipeline: ONE read of the BGR image produces
 //   EDGES  : the weak / strong Canny bit planes   (gray -> blur5 -> Sobel -> |dx|+|dy| -> NMS)
-//   SHADOW : the adaptive-threshold mask + masked sum/count (gray -> blur5 -> 11x11 f32 Gaussian)
-//   COLORS : the per-image 2^24-bit colour bitmap (BGR->RGB, noise, clip, test-and-set)
-// with no intermediate image in HBM (the unfused chain moves ~12 P bytes, this moves
-// 3 P in + P out + P/4 of bit planes).
+//   blurred: the blurred gray plane for the stand-alone shadow kernel (k_shadow.cu), optional
+//   SHADOW : (round-1 layout, option "shadow_inline") the adaptive-threshold mask + masked sum/count inline
+// with no gray / magnitude / NMS image in HBM.  The colour bitmap is a pointwise pass of its own
+// (k_color_pass, k_palette.cu): inside this kernel its noise generator and bitmap lookups cost 1.25 ms per 256
+// frames at 16 warps per SM, alone it is a streaming kernel.
 //
 // Mapping.  A warp owns a 256-pixel span of a row: lane L holds 8 consecutive pixels as four
 // packed 16x2 registers, lanes 0 and 31 are halo (so a warp emits 240 pixels and a CTA of 8
@@ -66,21 +66,16 @@ struct FusedArgs {
     uint32_t* strong;
     uint8_t* mask;      // [n][h][w] shadow mask
     unsigned long long* sum_count;  // [n][2]
-    const int8_t* noise;  // [n][h][w][3] or null
-    uint64_t seed;
-    int img0;
-    uint32_t* bitmap;   // [n][2^19]
+    uint8_t* blur_out;  // [n][h][w] blurred gray plane for the stand-alone shadow kernel (k_shadow.cu), or null
 };
 
 // ---------------------------------------------------------------------------------------
 // One lane's 8 pixels of a row as loaded: 24 bytes of BGR (+ 24 bytes of injected noise).
 struct Raw {
     uint32_t w[6];
-    uint32_t nz[6];
 };
 
-template <bool COLORS, bool INJ>
-__device__ __forceinline__ void issue_row(const FusedArgs& A, int img, int y, int x, bool in_x, bool own, Raw& r) {
+__device__ __forceinline__ void issue_row(const FusedArgs& A, int img, int y, int x, bool in_x, Raw& r) {
 #pragma unroll
     for (int k = 0; k < 6; ++k) r.w[k] = 0u;
     if (in_x) {
@@ -88,11 +83,6 @@ __device__ __forceinline__ void issue_row(const FusedArgs& A, int img, int y, in
         const uint2* p = reinterpret_cast<const uint2*>(A.bgr + pix0 * 3);
         const uint2 a = p[0], b = p[1], c = p[2];
         r.w[0] = a.x; r.w[1] = a.y; r.w[2] = b.x; r.w[3] = b.y; r.w[4] = c.x; r.w[5] = c.y;
-        if (COLORS && INJ && own) {
-            const uint2* q = reinterpret_cast<const uint2*>(A.noise + pix0 * 3);
-            const uint2 na = q[0], nb = q[1], nc = q[2];
-            r.nz[0] = na.x; r.nz[1] = na.y; r.nz[2] = nb.x; r.nz[3] = nb.y; r.nz[4] = nc.x; r.nz[5] = nc.y;
-        }
     }
 }
 
@@ -106,71 +96,6 @@ __device__ __forceinline__ Q4 gray_of(const Raw& r) {
     g.p2 = __byte_perm(t4, t5, 0x7632);
     g.p3 = __byte_perm(t6, t7, 0x7632);
     return g;
-}
-
-// the 8 pixels of 6 packed words as 24-bit values (byte 0 first): B | G<<8 | R<<16 for image words
-__device__ __forceinline__ void unpack24(const uint32_t* w, uint32_t* o) {
-    o[0] = w[0] & 0xffffffu;
-    o[1] = __byte_perm(w[0], w[1], 0x0543) & 0xffffffu;
-    o[2] = __byte_perm(w[1], w[2], 0x0432) & 0xffffffu;
-    o[3] = w[2] >> 8;
-    o[4] = w[3] & 0xffffffu;
-    o[5] = __byte_perm(w[3], w[4], 0x0543) & 0xffffffu;
-    o[6] = __byte_perm(w[4], w[5], 0x0432) & 0xffffffu;
-    o[7] = w[5] >> 8;
-}
-
-// Colour bitmap update, split in two so that the 8 bitmap loads of a row are in flight while
-// the row's stencil work runs: issue (keys + loads) now, commit (test + rare atomicOr) a row later.
-struct ColorPending {
-    uint32_t key[8];
-    uint32_t val[8];
-};
-
-__device__ __forceinline__ uint32_t noisy_key(uint32_t b, uint32_t g, uint32_t r, int nr, int ng, int nb) {
-    int R = min(max((int)r + nr, 0), 255), G = min(max((int)g + ng, 0), 255), B = min(max((int)b + nb, 0), 255);
-    return ((uint32_t)R << 16) | ((uint32_t)G << 8) | (uint32_t)B;
-}
-
-template <bool INJ>
-__device__ __forceinline__ void color_issue(const FusedArgs& A, int img, int y, int x, const Raw& r, ColorPending& cp,
-                                            uint8_t* my24) {
-    // BGR bytes in memory order are already the key layout: B | G<<8 | R<<16
-    if (INJ) {
-        unpack24(r.w, cp.key);
-        uint32_t n24[8];
-        unpack24(r.nz, n24);  // noise is stored in RGB order: byte 0 -> R
-#pragma unroll
-        for (int j = 0; j < 8; ++j)
-            if (n24[j]) {
-                const uint32_t k = cp.key[j];
-                cp.key[j] = noisy_key(k & 255u, (k >> 8) & 255u, k >> 16, (int)(int8_t)(n24[j] & 255u),
-                                      (int)(int8_t)((n24[j] >> 8) & 255u), (int)(int8_t)(n24[j] >> 16));
-            }
-    } else {
-        // device noise: sparse geometric-skip draws applied to this lane's 24 bytes in shared memory
-        uint2* slot = reinterpret_cast<uint2*>(my24);
-        slot[0] = make_uint2(r.w[0], r.w[1]);
-        slot[1] = make_uint2(r.w[2], r.w[3]);
-        slot[2] = make_uint2(r.w[4], r.w[5]);
-        const uint64_t pix0 = (uint64_t)(A.img0 + img) * ((size_t)A.h * A.w) + (size_t)y * A.w + x;
-        noise_apply_group(A.seed, pix0 >> 3, my24);
-        const uint2 a = slot[0], b = slot[1], c = slot[2];
-        const uint32_t w[6] = {a.x, a.y, b.x, b.y, c.x, c.y};
-        unpack24(w, cp.key);
-    }
-    const uint32_t* bm = A.bitmap + (size_t)img * (1u << 19);
-#pragma unroll
-    for (int j = 0; j < 8; ++j) cp.val[j] = bm[cp.key[j] >> 5];
-}
-
-__device__ __forceinline__ void color_commit(const FusedArgs& A, int img, const ColorPending& cp) {
-    uint32_t* bm = A.bitmap + (size_t)img * (1u << 19);
-#pragma unroll
-    for (int j = 0; j < 8; ++j) {
-        const uint32_t bit = 1u << (cp.key[j] & 31u);
-        if (!(cp.val[j] & bit)) atomicOr(&bm[cp.key[j] >> 5], bit);  // a stale word only costs a redundant atomic
-    }
 }
 
 // horizontal [1,4,6,4,1] on a gray row (16-bit lanes, max 4080)
@@ -279,15 +204,12 @@ __device__ __forceinline__ void nms_px(const Q4& m0, uint32_t e0, const Q4& m1, 
 
 __device__ __forceinline__ float u2f(uint32_t v) { return __uint_as_float(0x4b000000u | v) - 8388608.0f; }
 
-// INJ: the caller injects the reference's noise tensor (parity mode); otherwise the noise words of a row are never
-// loaded and their six registers are free
-template <bool EDGES, bool SHADOW, bool COLORS, bool INJ>
-__global__ void __launch_bounds__(WARPS * 32, (SHADOW || COLORS) ? CTAS_FULL : CTAS_EDGES) k_fused(FusedArgs A) {
-    // dynamic shared memory: [128 lanes][24 B] colour scratch, then SHADOW per warp: [RING][2][32] float4 (row-pass
-    // results) + [RING][32] uint2 (the blurred pixels as bytes) = 1280 B per row: 4 CTAs per SM
+template <bool EDGES, bool SHADOW>
+__global__ void __launch_bounds__(WARPS * 32, SHADOW ? CTAS_FULL : CTAS_EDGES) k_fused(FusedArgs A) {
+    // dynamic shared memory, SHADOW only, per warp: [RING][2][32] float4 (row-pass results) + [RING][32] uint2 (the
+    // blurred pixels as bytes) = 1280 B per row: 4 CTAs per SM
     extern __shared__ float4 dyn_smem[];
-    uint8_t* my24 = reinterpret_cast<uint8_t*>(dyn_smem) + threadIdx.x * 24;
-    float4* ring_all = dyn_smem + (WARPS * 32 * 24) / 16;
+    float4* ring_all = dyn_smem;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int img = blockIdx.z;
     const int W = A.w, H = A.h;
@@ -324,19 +246,11 @@ __global__ void __launch_bounds__(WARPS * 32, (SHADOW || COLORS) ? CTAS_FULL : C
     const int vy_last = clampi(vb_hi, 0, H - 1) + 2;
     int next_vy = clampi(vb_lo, 0, H - 1) - 2;
     Raw raw_next;
-    ColorPending pend;
-    bool have_pend = false;
-    auto own_row = [&](int vy) { return COLORS && out_lane && vy >= y0 && vy < y1; };
-    issue_row<COLORS, INJ>(A, img, reflect101_near(next_vy, H), x, in_x, own_row(next_vy), raw_next);
+    issue_row(A, img, reflect101_near(next_vy, H), x, in_x, raw_next);
     auto gray_row = [&]() -> Q4 {
         const Raw cur = raw_next;
-        const int vy = next_vy++;
-        if (next_vy <= vy_last) issue_row<COLORS, INJ>(A, img, reflect101_near(next_vy, H), x, in_x, own_row(next_vy), raw_next);
-        if (COLORS) {
-            if (have_pend) color_commit(A, img, pend);
-            have_pend = own_row(vy);
-            if (have_pend) color_issue<INJ>(A, img, vy, x, cur, pend, my24);
-        }
+        next_vy++;
+        if (next_vy <= vy_last) issue_row(A, img, reflect101_near(next_vy, H), x, in_x, raw_next);
         // virtual gray row vy: BORDER_REFLECT_101 in y (done by the loader); in x the halo lanes are patched here
         Q4 g = gray_of(cur);
         if (left_edge) {   // lane 0 holds pixels -8..-1: (-2,-1) := (2,1)
@@ -376,6 +290,9 @@ __global__ void __launch_bounds__(WARPS * 32, (SHADOW || COLORS) ? CTAS_FULL : C
                 if (x == W) blurred = Q4{v, v, v, v};
             }
         }
+        if (A.blur_out && vb >= y0 && vb < y1 && out_lane)   // warp-uniform except for the halo lanes
+            *reinterpret_cast<uint2*>(A.blur_out + ((size_t)img * H + vb) * W + x) =
+                make_uint2(__byte_perm(blurred.p0, blurred.p1, 0x6420), __byte_perm(blurred.p2, blurred.p3, 0x6420));
         if (EDGES) {
             bw[0] = bw[1];
             bw[1] = bw[2];
@@ -511,7 +428,6 @@ __global__ void __launch_bounds__(WARPS * 32, (SHADOW || COLORS) ? CTAS_FULL : C
                                                            __byte_perm(blurred.p2, blurred.p3, 0x6420));
         }
     }
-    if (COLORS && have_pend) color_commit(A, img, pend);
     if (SHADOW) {
         lsum = warp_sum_u32(lsum);
         lcnt = warp_sum_u32(lcnt);
@@ -522,31 +438,25 @@ __global__ void __launch_bounds__(WARPS * 32, (SHADOW || COLORS) ? CTAS_FULL : C
     }
 }
 
-template <bool E, bool S, bool C, bool INJ>
+template <bool E, bool S>
 int launch_v(llfe_ctx* ctx, const FusedArgs& A, dim3 grid, size_t smem) {
-    if (smem > 48 * 1024 && llfe_first_use(ctx, (const void*)k_fused<E, S, C, INJ>))   // smem is a constant of the variant
-        LLFE_CUDA(cudaFuncSetAttribute(k_fused<E, S, C, INJ>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    if (smem > 48 * 1024 && llfe_first_use(ctx, (const void*)k_fused<E, S>))   // smem is a constant of the variant
+        LLFE_CUDA(cudaFuncSetAttribute(k_fused<E, S>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     LLFE_KERNEL(ctx, "k_fused");
-    k_fused<E, S, C, INJ><<<grid, WARPS * 32, smem, ctx->stream>>>(A);
+    k_fused<E, S><<<grid, WARPS * 32, smem, ctx->stream>>>(A);
     LLFE_LAUNCHED(ctx);
     return LLFE_OK;
-}
-
-template <bool E, bool S, bool C>
-int launch_t(llfe_ctx* ctx, const FusedArgs& A, dim3 grid, size_t smem) {
-    if (C && A.noise) return launch_v<E, S, C, true>(ctx, A, grid, smem);
-    return launch_v<E, S, C, false>(ctx, A, grid, smem);
 }
 
 }  // namespace
 
 bool fused_supported(int h, int w) { return w % 8 == 0 && w >= 8 && h >= 1; }
 
-// Any of weak/strong (both or none), mask (+sum_count) and bitmap may be null to disable that output group.
+// Any of weak/strong (both or none), mask (+sum_count) and blur_out may be null to disable that output.
 int launch_fused(llfe_ctx* ctx, const uint8_t* bgr, int n, int h, int w, int low, int high, uint32_t* weak,
-                 uint32_t* strong, uint8_t* mask, uint64_t* sum_count, const int8_t* noise, uint64_t seed, int img0,
-                 uint32_t* bitmap) {
+                 uint32_t* strong, uint8_t* mask, uint64_t* sum_count, uint8_t* blur_out) {
     FusedArgs A;
+    A.blur_out = blur_out;
     A.bgr = bgr;
     A.n = n;
     A.h = h;
@@ -557,11 +467,7 @@ int launch_fused(llfe_ctx* ctx, const uint8_t* bgr, int n, int h, int w, int low
     A.strong = strong;
     A.mask = mask;
     A.sum_count = (unsigned long long*)sum_count;
-    A.noise = noise;
-    A.seed = seed;
-    A.img0 = img0;
-    A.bitmap = bitmap;
-    const bool E = weak != nullptr, S = mask != nullptr, C = bitmap != nullptr;
+    const bool E = weak != nullptr, S = mask != nullptr;
     if (S && !sum_count) {   // sums go somewhere even if the caller does not want them
         if (!ctx->dummy_sums) LLFE_CUDA(cudaMalloc(&ctx->dummy_sums, 65536 * 2 * sizeof(unsigned long long)));
         A.sum_count = ctx->dummy_sums;
@@ -570,7 +476,7 @@ int launch_fused(llfe_ctx* ctx, const uint8_t* bgr, int n, int h, int w, int low
     // enough to amortise their ~10 warm-up rows.  Pick the band count with the best product of the two.
     {
         const int xb = ceil_div(w, BAND_W);
-        const double slots = (double)((S || C) ? CTAS_FULL : CTAS_EDGES) * (ctx->sm_count > 0 ? ctx->sm_count : 148);
+        const double slots = (double)(S ? CTAS_FULL : CTAS_EDGES) * (ctx->sm_count > 0 ? ctx->sm_count : 148);
         const double halo = S ? 10.0 : 4.0;
         int best = 1;
         double best_score = -1.0;
@@ -588,22 +494,15 @@ int launch_fused(llfe_ctx* ctx, const uint8_t* bgr, int n, int h, int w, int low
         A.rows_per_band = ceil_div(h, best);
     }
     dim3 grid(ceil_div(w, BAND_W), ceil_div(h, A.rows_per_band), n);
-    const size_t smem = (size_t)WARPS * 32 * 24 + (S ? (size_t)WARPS * (RING * 2 * 32 + RING * 16) * sizeof(float4) : 0);
+    const size_t smem = S ? (size_t)WARPS * (RING * 2 * 32 + RING * 16) * sizeof(float4) : 0;
     if (S && sum_count) LLFE_CUDA(cudaMemsetAsync(sum_count, 0, (size_t)n * 2 * sizeof(uint64_t), ctx->stream));
     if (E && (w % 32)) {  // the kernel writes whole bytes of in-image pixels only: clear the padding bits
         const size_t pb = (size_t)n * h * plane_wpr(w) * sizeof(uint32_t);
         LLFE_CUDA(cudaMemsetAsync(weak, 0, pb, ctx->stream));
         LLFE_CUDA(cudaMemsetAsync(strong, 0, pb, ctx->stream));
     }
-#define GO(e, s, c) \
-    if (E == e && S == s && C == c) return launch_t<e, s, c>(ctx, A, grid, smem);
-    GO(true, true, true)
-    GO(true, true, false)
-    GO(true, false, true)
-    GO(true, false, false)
-    GO(false, true, true)
-    GO(false, true, false)
-    GO(false, false, true)
-#undef GO
-    return LLFE_OK;
+    if (E && S) return launch_v<true, true>(ctx, A, grid, smem);
+    if (E) return launch_v<true, false>(ctx, A, grid, smem);
+    if (S) return launch_v<false, true>(ctx, A, grid, smem);
+    return launch_v<false, false>(ctx, A, grid, smem);   // blurred plane only
 }

@@ -20,6 +20,8 @@
 //     updated incrementally.
 #include <stdlib.h>
 
+#include <type_traits>
+
 #include "llfe_common.cuh"
 #include "llfe_device.cuh"
 #include "k_kmeans_shared.cuh"
@@ -78,6 +80,153 @@ __device__ __forceinline__ uint32_t idist2(uint32_t a, uint32_t b) {
     return __dp4a(d, d, 0u);
 }
 
+
+// ---- cv2's sequential float32 centre sums beyond 2^24 -------------------------------------------------------------
+// cv::kmeans accumulates `center[j] += sample[j]` in float32, point after point in index order.  Below 2^24 every
+// partial sum is an exact integer; above, each addition rounds to the float32 grid (ulp u = 2, 4, ...), with ties to
+// even -- so the result depends on the order and differs from the exact integer sum.  Lists long enough for that
+// (> 65 793 members in one cluster: photo-like frames, SURVEY 8(d)'s U ~ 1.95 M set) only run in the global-scratch
+// variant of the kernel, which reproduces the sequential sum operation for operation, in parallel:
+//   * inside one binade (fixed u = 2^m) an addition maps the running sum s to s + u * inc(x, parity(s / u)), so an
+//     element is a function {parity 0, parity 1} -> increment, and functions compose associatively: every thread
+//     folds its contiguous segment of the list for both incoming parities, an ordered scan composes the segments,
+//     and every thread then knows the exact sum entering its segment;
+//   * a second walk finds the first element whose exact sum t = s + x reaches the next binade; that one addition is
+//     done with a real float add, and the next phase continues behind it with u doubled (at most 6 phases up to 2^29).
+// The three channels of a cluster are folded in the same walks.  Verified against np.cumsum(float32) on the host
+// (oracle/cvops.py:_sums_f32_sequential is that call) and against cv2.kmeans itself (tests/test_gpu_long_lists.py).
+__device__ __forceinline__ uint32_t seq_inc(uint32_t x, uint32_t parity, int m) {
+    if (m == 0) return x;
+    const uint32_t u = 1u << m, half = u >> 1, q = x >> m, r = x & (u - 1u);
+    return q + ((r > half || (r == half && ((parity + q) & 1u))) ? 1u : 0u);
+}
+
+struct SeqShared {
+    uint32_t comp[32][6];      // per-warp composites: [channel][start parity]
+    uint32_t cur[3];           // running float32 sum per channel (an integer that float32 represents exactly)
+    int start[3];              // next list index of the channel's chain
+    int done[3];
+    int cross_i[3];
+    uint32_t total[6];
+};
+
+template <typename F, int FT>
+__device__ void seq_f32_sums3(int k, int U, const uint32_t* __restrict__ aux, const uint32_t* __restrict__ keys,
+                              SeqShared& S, float* out3) {
+    constexpr int FW = FT / 32;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int seg = (U + FT - 1) / FT, lo = min(U, tid * seg), hi = min(U, lo + seg);
+    if (tid < 3) {
+        S.cur[tid] = 0u;
+        S.start[tid] = 0;
+        S.done[tid] = 0;
+    }
+    __syncthreads();
+    for (;;) {
+        uint32_t s[3], limit[3], par[3];
+        int st[3], m[3];
+        bool act[3], any = false;
+        int first = U;
+#pragma unroll
+        for (int c = 0; c < 3; ++c) {
+            s[c] = S.cur[c];
+            st[c] = S.start[c];
+            act[c] = !S.done[c];
+            m[c] = s[c] < (1u << 24) ? 0 : (31 - __clz(s[c])) - 23;
+            limit[c] = 1u << (24 + m[c]);
+            par[c] = (s[c] >> m[c]) & 1u;
+            any |= act[c];
+            if (act[c]) first = min(first, st[c]);
+        }
+        if (!any) break;   // block-uniform (shared state)
+        __syncthreads();   // everyone has read the state before it is rewritten
+        if (tid < 3) S.cross_i[tid] = 0x7fffffff;
+        // ---- walk 1: this thread's segment as a function of the incoming parity, per channel
+        uint32_t d[3][2] = {{0u, 0u}, {0u, 0u}, {0u, 0u}};
+        for (int i = max(lo, first); i < hi; ++i) {
+            if ((int)F::label(aux[i]) != k) continue;
+            const uint32_t key = __ldg(keys + i);
+#pragma unroll
+            for (int c = 0; c < 3; ++c) {
+                if (!act[c] || i < st[c]) continue;
+                const uint32_t x = (key >> (16 - 8 * c)) & 255u;
+                d[c][0] += seq_inc(x, d[c][0] & 1u, m[c]);
+                d[c][1] += seq_inc(x, (1u + d[c][1]) & 1u, m[c]);
+            }
+        }
+        // ---- ordered scan of the composites: inclusive inside the warp, then the warps in order
+        uint32_t inc0[3], inc1[3];
+#pragma unroll
+        for (int c = 0; c < 3; ++c) {
+            inc0[c] = d[c][0];
+            inc1[c] = d[c][1];
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+                const uint32_t e0 = __shfl_up_sync(FULL, inc0[c], o), e1 = __shfl_up_sync(FULL, inc1[c], o);
+                if (lane >= o) {   // (earlier segment E) then (mine): C_p = E_p + mine_{p + E_p}
+                    const uint32_t n0 = e0 + ((e0 & 1u) ? inc1[c] : inc0[c]);
+                    const uint32_t n1 = e1 + (((1u + e1) & 1u) ? inc1[c] : inc0[c]);
+                    inc0[c] = n0;
+                    inc1[c] = n1;
+                }
+            }
+            if (lane == 31) {
+                S.comp[warp][2 * c] = inc0[c];
+                S.comp[warp][2 * c + 1] = inc1[c];
+            }
+        }
+        __syncthreads();
+        uint32_t sin[3];   // exact float32 running sum entering this thread's segment
+#pragma unroll
+        for (int c = 0; c < 3; ++c) {
+            uint32_t acc = 0u;
+            for (int w = 0; w < warp; ++w) acc += S.comp[w][2 * c + ((par[c] + acc) & 1u)];
+            const uint32_t x0 = __shfl_up_sync(FULL, inc0[c], 1), x1 = __shfl_up_sync(FULL, inc1[c], 1);
+            if (lane > 0) acc += ((par[c] + acc) & 1u) ? x1 : x0;
+            sin[c] = s[c] + (acc << m[c]);
+            if (tid == FT - 1) S.total[c] = acc + (((par[c] + acc) & 1u) ? d[c][1] : d[c][0]);
+        }
+        // ---- walk 2: the first element whose exact sum reaches the next binade
+        int my_i[3] = {0x7fffffff, 0x7fffffff, 0x7fffffff};
+        uint32_t my_s[3] = {0u, 0u, 0u}, my_x[3] = {0u, 0u, 0u};
+        for (int i = max(lo, first); i < hi; ++i) {
+            if ((int)F::label(aux[i]) != k) continue;
+            const uint32_t key = __ldg(keys + i);
+#pragma unroll
+            for (int c = 0; c < 3; ++c) {
+                if (!act[c] || i < st[c] || my_i[c] != 0x7fffffff) continue;
+                const uint32_t x = (key >> (16 - 8 * c)) & 255u;
+                if (sin[c] + x >= limit[c]) {
+                    my_i[c] = i;
+                    my_s[c] = sin[c];
+                    my_x[c] = x;
+                    atomicMin(&S.cross_i[c], i);
+                } else {
+                    sin[c] += seq_inc(x, (sin[c] >> m[c]) & 1u, m[c]) << m[c];
+                }
+            }
+        }
+        __syncthreads();
+#pragma unroll
+        for (int c = 0; c < 3; ++c) {
+            if (!act[c]) continue;
+            const int ci = S.cross_i[c];
+            if (ci == 0x7fffffff) {
+                if (tid == FT - 1) {
+                    S.cur[c] = s[c] + (S.total[c] << m[c]);
+                    S.done[c] = 1;
+                }
+            } else if (my_i[c] == ci) {
+                S.cur[c] = (uint32_t)__fadd_rn((float)my_s[c], (float)my_x[c]);   // the addition that changes the binade
+                S.start[c] = ci + 1;
+            }
+        }
+        __syncthreads();
+    }
+    if (tid < 3) out3[tid] = (float)S.cur[tid];
+    __syncthreads();
+}
+
 template <int KC, bool IN_SMEM, int FT>
 __global__ void __launch_bounds__(FT, FT == FT_LONG ? 1 : 2) k_kmeans_fast(KmParams P, int u_lo, int smem_points, int img_base) {
     typedef Fmt<KC> F;
@@ -112,6 +261,9 @@ __global__ void __launch_bounds__(FT, FT == FT_LONG ? 1 : 2) k_kmeans_fast(KmPar
     __shared__ float4 s_old[KMAX];
     __shared__ float4 s_asg[KMAX];          // the centres the current labels were assigned with
     __shared__ int s_sum[KMAX][4];          // exact per-cluster {sum R, sum G, sum B, count}
+    __shared__ float s_fsum[KMAX][3];       // the float32 sums cv2 has: == s_sum below 2^24, sequential rounding above
+    // scratch of seq_f32_sums3: only the global-scratch variant gets there, the others keep their shared memory
+    __shared__ typename std::conditional<IN_SMEM, int, SeqShared>::type s_seq;
     __shared__ uint32_t s_dq[KMAX];
     __shared__ uint4 s_tab[KMAX];           // per label: {own centre's drift, largest drift of another centre, half gap, -}
     __shared__ uint8_t s_queue[FW][QROWS * 32];   // per-warp queue of points whose bounds failed
@@ -471,6 +623,22 @@ __global__ void __launch_bounds__(FT, FT == FT_LONG ? 1 : 2) k_kmeans_fast(KmPar
             }
         }
         __syncthreads();
+        // cv2's float32 centre sums: the exact integers while every channel sum is below 2^24 (always, for lists that
+        // fit in shared memory: 57 344 x 255 < 2^24), else the sequential float32 sum reproduced by seq_f32_sums3
+        if (tid < K * 3) s_fsum[tid / 3][tid % 3] = (float)s_sum[tid / 3][tid % 3];
+        if (!IN_SMEM) {
+            bool any_long = false;
+            for (int k = 0; k < K; ++k)
+                any_long |= s_sum[k][0] >= (1 << 24) || s_sum[k][1] >= (1 << 24) || s_sum[k][2] >= (1 << 24);
+            if (any_long) {   // block-uniform (shared memory)
+                if (tid == 0) s_flag = 1;
+                __syncthreads();
+                for (int k = 0; k < K; ++k)
+                    if (s_sum[k][0] >= (1 << 24) || s_sum[k][1] >= (1 << 24) || s_sum[k][2] >= (1 << 24))
+                        seq_f32_sums3<F, FT>(k, U, aux, keys, *reinterpret_cast<SeqShared*>(&s_seq), s_fsum[k]);
+            }
+        }
+        __syncthreads();
         // empty-cluster repair (cv2: the biggest cluster gives up its farthest member, last max wins)
         for (int k = 0; k < K; ++k) {
             if (s_sum[k][3] != 0) continue;  // uniform (shared memory)
@@ -478,8 +646,8 @@ __global__ void __launch_bounds__(FT, FT == FT_LONG ? 1 : 2) k_kmeans_fast(KmPar
             for (int k1 = 1; k1 < K; ++k1)
                 if (s_sum[mk][3] < s_sum[k1][3]) mk = k1;
             const float sc = __fdiv_rn(1.f, (float)s_sum[mk][3]);
-            const float4 base = make_float4(__fmul_rn((float)s_sum[mk][0], sc), __fmul_rn((float)s_sum[mk][1], sc),
-                                            __fmul_rn((float)s_sum[mk][2], sc), 0.f);
+            const float4 base = make_float4(__fmul_rn(s_fsum[mk][0], sc), __fmul_rn(s_fsum[mk][1], sc),
+                                            __fmul_rn(s_fsum[mk][2], sc), 0.f);
             if (tid == 0) s_far = 0ull;
             __syncthreads();
             unsigned long long best = 0ull;
@@ -508,6 +676,14 @@ __global__ void __launch_bounds__(FT, FT == FT_LONG ? 1 : 2) k_kmeans_fast(KmPar
                 s_sum[k][1] += (int)((fk >> 8) & 255u);
                 s_sum[k][2] += (int)(fk & 255u);
                 s_sum[k][3] += 1;
+                // cv2 moves the point in float32: center[max_k] -= sample, center[k] += sample
+                const float xr = (float)(fk >> 16), xg = (float)((fk >> 8) & 255u), xb = (float)(fk & 255u);
+                s_fsum[mk][0] = __fsub_rn(s_fsum[mk][0], xr);
+                s_fsum[mk][1] = __fsub_rn(s_fsum[mk][1], xg);
+                s_fsum[mk][2] = __fsub_rn(s_fsum[mk][2], xb);
+                s_fsum[k][0] = __fadd_rn(s_fsum[k][0], xr);
+                s_fsum[k][1] = __fadd_rn(s_fsum[k][1], xg);
+                s_fsum[k][2] = __fadd_rn(s_fsum[k][2], xb);
             }
             __syncthreads();
         }
@@ -515,9 +691,8 @@ __global__ void __launch_bounds__(FT, FT == FT_LONG ? 1 : 2) k_kmeans_fast(KmPar
         if (tid < K) {
             s_old[tid] = s_c[tid];
             const float sc = __fdiv_rn(1.f, (float)s_sum[tid][3]);
-            if (s_sum[tid][0] >= (1 << 24) || s_sum[tid][1] >= (1 << 24) || s_sum[tid][2] >= (1 << 24)) atomicOr(&s_flag, 1);
-            s_c[tid] = make_float4(__fmul_rn((float)s_sum[tid][0], sc), __fmul_rn((float)s_sum[tid][1], sc),
-                                   __fmul_rn((float)s_sum[tid][2], sc), 0.f);
+            s_c[tid] = make_float4(__fmul_rn(s_fsum[tid][0], sc), __fmul_rn(s_fsum[tid][1], sc),
+                                   __fmul_rn(s_fsum[tid][2], sc), 0.f);
         }
         __syncthreads();
         double shift = 0.0;

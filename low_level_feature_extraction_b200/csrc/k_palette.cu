@@ -20,45 +20,130 @@ __device__ __forceinline__ uint32_t noisy_key(uint32_t b, uint32_t g, uint32_t r
     return ((uint32_t)R << 16) | ((uint32_t)G << 8) | (uint32_t)B;
 }
 
-// MODE 0: set bitmap bits.  MODE 1: histogram pixels into hist[rank(key)].
-// One thread per group of 8 consecutive pixels (the unit of the device noise generator).
+// the 8 pixels of 6 packed words as 24-bit values (byte 0 first): B | G<<8 | R<<16 for image words
+__device__ __forceinline__ void unpack24(const uint32_t* w, uint32_t* o) {
+    o[0] = w[0] & 0xffffffu;
+    o[1] = __byte_perm(w[0], w[1], 0x0543) & 0xffffffu;
+    o[2] = __byte_perm(w[1], w[2], 0x0432) & 0xffffffu;
+    o[3] = w[2] >> 8;
+    o[4] = w[3] & 0xffffffu;
+    o[5] = __byte_perm(w[3], w[4], 0x0543) & 0xffffffu;
+    o[6] = __byte_perm(w[4], w[5], 0x0432) & 0xffffffu;
+    o[7] = w[5] >> 8;
+}
+
+// 24 bytes at p (pixel-aligned, any byte alignment) as 6 little-endian words; bytes beyond `nbytes` read as zero
+__device__ __forceinline__ void load24(const uint8_t* __restrict__ p, int nbytes, bool aligned8, uint32_t* w) {
+    if (aligned8 && nbytes == 24) {
+        const uint2* q = reinterpret_cast<const uint2*>(p);
+        const uint2 a = q[0], b = q[1], c = q[2];
+        w[0] = a.x; w[1] = a.y; w[2] = b.x; w[3] = b.y; w[4] = c.x; w[5] = c.y;
+    } else {
+#pragma unroll
+        for (int k = 0; k < 6; ++k) {
+            uint32_t v = 0;
+#pragma unroll
+            for (int j = 0; j < 4; ++j)
+                if (4 * k + j < nbytes) v |= (uint32_t)p[4 * k + j] << (8 * j);
+            w[k] = v;
+        }
+    }
+}
+
+constexpr int CP_WARPS = 8;
+
+// The colour pass: BGR -> RGB key, noise, clip, then MODE 0: set the key's bit in the image's bitmap (test before
+// atomicOr: a stale read only costs a redundant atomic); MODE 1: histogram the pixel into hist[rank(key)].
+// A warp owns a block of 256 consecutive pixels (the unit of the device noise, llfe_device.cuh), lane L its pixels
+// 8L .. 8L+7: 768 contiguous bytes per warp and step, 24 per lane.  Pointwise: no halo, no barrier.
 template <int MODE>
-__global__ void __launch_bounds__(256) k_color_pass(const uint8_t* __restrict__ bgr, size_t npix,
-                                                    const int8_t* __restrict__ noise, uint64_t seed, int img0,
-                                                    uint32_t* bitmap, const uint32_t* __restrict__ rank,
-                                                    uint32_t* hist, int max_unique) {
-    const int img = blockIdx.y;
+__global__ void __launch_bounds__(CP_WARPS * 32) k_color_pass(const uint8_t* __restrict__ bgr, size_t npix,
+                                                              const int8_t* __restrict__ noise, uint64_t seed, int img0,
+                                                              uint32_t* bitmap, const uint32_t* __restrict__ rank,
+                                                              uint32_t* hist, int max_unique) {
+    __shared__ uint2 s_bytes[CP_WARPS][96];   // 768 bytes per warp
+    const int img = blockIdx.y, lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const uint8_t* s = bgr + (size_t)img * npix * 3;
     const int8_t* nz = noise ? noise + (size_t)img * npix * 3 : nullptr;
     uint32_t* bm = bitmap + (size_t)img * BM_WORDS;
     const uint32_t* rk = MODE == 1 ? rank + (size_t)img * BM_WORDS : nullptr;
     uint32_t* hs = MODE == 1 ? hist + (size_t)img * max_unique : nullptr;
-    const size_t ngroups = (npix + 7) / 8;
-    const size_t stride = (size_t)gridDim.x * 256;
-    for (size_t g = blockIdx.x * (size_t)256 + threadIdx.x; g < ngroups; g += stride) {
-        const size_t p0 = g * 8;
-        const int np = (int)(npix - p0 < 8 ? npix - p0 : 8);
-        uint8_t px[24];
-        for (int k = 0; k < 3 * np; ++k) px[k] = s[3 * p0 + k];
+    const bool aligned8 = (((uintptr_t)s) & 7) == 0 && (!nz || (((uintptr_t)nz) & 7) == 0);
+    const bool aligned16 = (((uintptr_t)s) & 15) == 0;
+    const size_t nblocks = (npix + LLFE_NOISE_BLOCK_PX - 1) / LLFE_NOISE_BLOCK_PX;
+    const size_t nfull = npix / LLFE_NOISE_BLOCK_PX;     // blocks with all 256 pixels
+    uint2* mine = &s_bytes[warp][3 * lane];
+    uint4* blk4 = reinterpret_cast<uint4*>(&s_bytes[warp][0]);   // the block as 48 x 16 bytes
+    const uint4* src4 = reinterpret_cast<const uint4*>(s);
+    const size_t stride = (size_t)gridDim.x * CP_WARPS;
+    size_t b = (size_t)blockIdx.x * CP_WARPS + warp;
+    // Device-noise path on full, 16-byte aligned blocks: the block's 768 bytes arrive as 1.5 coalesced 128-bit loads per
+    // lane and go straight into the warp's shared-memory copy (where the noise is applied); the loads of the warp's NEXT
+    // block are issued before this block is processed.
+    const bool stream_ok = !nz && aligned16;
+    uint4 v0 = make_uint4(0, 0, 0, 0), v1 = v0;
+    if (stream_ok && b < nfull) {
+        v0 = ld_stream(src4 + 48 * b + lane);
+        if (lane < 16) v1 = ld_stream(src4 + 48 * b + 32 + lane);
+    }
+    for (; b < nblocks; b += stride) {
+        const size_t p0 = b * LLFE_NOISE_BLOCK_PX + 8 * lane;
+        const int np = p0 >= npix ? 0 : (int)(npix - p0 < 8 ? npix - p0 : 8);
+        uint32_t key[8];
         if (nz) {
-            // injected noise is in RGB order, the image bytes in BGR order
-            for (int j = 0; j < np; ++j) {
-                const uint32_t key = noisy_key(px[3 * j], px[3 * j + 1], px[3 * j + 2], nz[3 * (p0 + j)],
-                                               nz[3 * (p0 + j) + 1], nz[3 * (p0 + j) + 2]);
-                px[3 * j] = (uint8_t)key;
-                px[3 * j + 1] = (uint8_t)(key >> 8);
-                px[3 * j + 2] = (uint8_t)(key >> 16);
-            }
+            // injected noise (the reference's tensor) is in RGB order, the image bytes in BGR order
+            uint32_t w[6], nw[6], n24[8];
+            load24(s + 3 * p0, 3 * np, aligned8, w);
+            load24(reinterpret_cast<const uint8_t*>(nz) + 3 * p0, 3 * np, aligned8, nw);
+            unpack24(w, key);
+            unpack24(nw, n24);
+#pragma unroll
+            for (int j = 0; j < 8; ++j)
+                if (n24[j]) {
+                    const uint32_t k = key[j];
+                    key[j] = noisy_key(k & 255u, (k >> 8) & 255u, k >> 16, (int)(int8_t)(n24[j] & 255u),
+                                       (int)(int8_t)((n24[j] >> 8) & 255u), (int)(int8_t)(n24[j] >> 16));
+                }
         } else {
-            noise_apply_group(seed, ((uint64_t)(img0 + img) * npix + p0) >> 3, px, 3 * np);
-        }
-        for (int j = 0; j < np; ++j) {
-            const uint32_t key = (uint32_t)px[3 * j] | ((uint32_t)px[3 * j + 1] << 8) | ((uint32_t)px[3 * j + 2] << 16);
-            const uint32_t wi = key >> 5, bit = 1u << (key & 31);
-            if (MODE == 0) {
-                if (!(bm[wi] & bit)) atomicOr(&bm[wi], bit);  // stale reads only cost a redundant atomic
+            if (stream_ok && b < nfull) {
+                blk4[lane] = v0;
+                if (lane < 16) blk4[32 + lane] = v1;
+                const size_t bn = b + stride;
+                if (bn < nfull) {
+                    v0 = ld_stream(src4 + 48 * bn + lane);
+                    if (lane < 16) v1 = ld_stream(src4 + 48 * bn + 32 + lane);
+                }
             } else {
-                uint32_t idx = rk[wi] + __popc(bm[wi] & (bit - 1));
+                uint32_t w[6];
+                load24(s + 3 * p0, 3 * np, aligned8, w);
+                mine[0] = make_uint2(w[0], w[1]);
+                mine[1] = make_uint2(w[2], w[3]);
+                mine[2] = make_uint2(w[4], w[5]);
+            }
+            __syncwarp();
+            const size_t left = npix - b * LLFE_NOISE_BLOCK_PX;
+            noise_apply_block(noise_block_base(seed, (uint32_t)(img0 + img), (uint32_t)b),
+                              reinterpret_cast<uint8_t*>(&s_bytes[warp][0]),
+                              3 * (int)(left < LLFE_NOISE_BLOCK_PX ? left : LLFE_NOISE_BLOCK_PX), lane);
+            __syncwarp();
+            const uint2 a = mine[0], c = mine[1], d = mine[2];
+            const uint32_t v[6] = {a.x, a.y, c.x, c.y, d.x, d.y};
+            unpack24(v, key);
+            __syncwarp();   // the next step overwrites the block's bytes
+        }
+        if (MODE == 0) {
+            uint32_t val[8];
+#pragma unroll
+            for (int j = 0; j < 8; ++j) val[j] = j < np ? bm[key[j] >> 5] : 0xffffffffu;   // all loads in flight first
+#pragma unroll
+            for (int j = 0; j < 8; ++j)
+                if (!(__funnelshift_r(val[j], 0u, key[j]) & 1u)) atomicOr(&bm[key[j] >> 5], 1u << (key[j] & 31u));
+        } else {
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+                if (j >= np) break;
+                const uint32_t wi = key[j] >> 5, bit = 1u << (key[j] & 31u);
+                const uint32_t idx = rk[wi] + __popc(bm[wi] & (bit - 1));
                 if (idx < (uint32_t)max_unique) atomicAdd(&hs[idx], 1u);
             }
         }
@@ -139,6 +224,16 @@ __global__ void __launch_bounds__(256) k_bm_emit(const uint32_t* __restrict__ bi
 
 }  // namespace
 
+// CTAs per image: about two full waves of the machine over the m images of the launch (6 CTAs of 8 warps per SM), so
+// that a warp walks a dozen blocks with its next block's loads in flight, but never more CTAs than blocks
+static unsigned color_pass_grid(llfe_ctx* ctx, size_t npix, int m) {
+    const size_t blocks = ceil_div_sz(npix, (size_t)LLFE_NOISE_BLOCK_PX * CP_WARPS);
+    const size_t slots = (size_t)(ctx->sm_count > 0 ? ctx->sm_count : 148) * 6 * 2;
+    size_t want = ceil_div_sz(slots, (size_t)(m > 0 ? m : 1));
+    if (want > blocks) want = blocks;
+    return (unsigned)(want < 1 ? 1 : want);
+}
+
 // workspace per image: bitmap (2 MiB) + rank (2 MiB, only with d_hist) + block sums
 static size_t unique_ws_per_image(bool with_rank) {
     return (size_t)BM_WORDS * 4 * (with_rank ? 2 : 1) + WsCarver::need(BM_NBLK * 4);
@@ -158,26 +253,38 @@ int launch_unique_colors(llfe_ctx* ctx, const uint8_t* d_bgr, int n, int h, int 
     uint32_t* rank = with_rank ? carve.take<uint32_t>((size_t)BM_WORDS * chunk) : nullptr;
     uint32_t* bsum = carve.take<uint32_t>((size_t)BM_NBLK * chunk);
     if (d_hist) LLFE_CUDA(cudaMemsetAsync(d_hist, 0, (size_t)n * max_unique * sizeof(uint32_t), ctx->stream));
-    size_t want = ceil_div_sz(npix, 256 * 8 * 2);
-    unsigned gx = (unsigned)(want < 1 ? 1 : (want > 4096 ? 4096 : want));
+    const unsigned gx = color_pass_grid(ctx, npix, chunk);
     for (int i0 = 0; i0 < n; i0 += chunk) {
         const int m = (n - i0) < chunk ? (n - i0) : chunk;
         const uint8_t* src = d_bgr + (size_t)i0 * npix * 3;
         const int8_t* nz = d_noise ? d_noise + (size_t)i0 * npix * 3 : nullptr;
         LLFE_CUDA(cudaMemsetAsync(bitmap, 0, (size_t)BM_WORDS * 4 * m, ctx->stream));
         LLFE_KERNEL(ctx, "k_color_bitmap");
-        k_color_pass<0><<<dim3(gx, m), 256, 0, ctx->stream>>>(src, npix, nz, seed, first_image + i0, bitmap, nullptr, nullptr,
+        k_color_pass<0><<<dim3(gx, m), CP_WARPS * 32, 0, ctx->stream>>>(src, npix, nz, seed, first_image + i0, bitmap, nullptr, nullptr,
                                                               max_unique);
         LLFE_LAUNCHED(ctx);
         LLFE_TRY(launch_bitmap_compact(ctx, bitmap, bsum, m, d_keys + (size_t)i0 * max_unique, rank, d_count + i0,
                                        max_unique));
         if (d_hist) {
             LLFE_KERNEL(ctx, "k_color_count");
-            k_color_pass<1><<<dim3(gx, m), 256, 0, ctx->stream>>>(src, npix, nz, seed, first_image + i0, bitmap, rank,
+            k_color_pass<1><<<dim3(gx, m), CP_WARPS * 32, 0, ctx->stream>>>(src, npix, nz, seed, first_image + i0, bitmap, rank,
                                                                  d_hist + (size_t)i0 * max_unique, max_unique);
             LLFE_LAUNCHED(ctx);
         }
     }
+    return LLFE_OK;
+}
+
+// set the colour bits of m images in `bitmap` (already zeroed); image i of this call is image first_image + i
+// of the caller's numbering for the device noise
+int launch_color_bitmap(llfe_ctx* ctx, const uint8_t* d_bgr, int m, int h, int w, const int8_t* d_noise, uint64_t seed,
+                        int first_image, uint32_t* bitmap) {
+    const size_t npix = (size_t)h * w;
+    const unsigned gx = color_pass_grid(ctx, npix, m);
+    LLFE_KERNEL(ctx, "k_color_bitmap");
+    k_color_pass<0><<<dim3(gx, m), CP_WARPS * 32, 0, ctx->stream>>>(d_bgr, npix, d_noise, seed, first_image, bitmap, nullptr,
+                                                                    nullptr, 0);
+    LLFE_LAUNCHED(ctx);
     return LLFE_OK;
 }
 

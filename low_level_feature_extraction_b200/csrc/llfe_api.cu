@@ -25,17 +25,45 @@ int llfe_cuda_fail(cudaError_t e, const char* what, const char* file, int line) 
 }
 
 int llfe_workspace(llfe_ctx* ctx, size_t bytes, void** out) {
-    if (bytes > ctx->ws_bytes) {
-        // grow: everything queued so far may still be using the old arena
+    void*& ws = ctx->on_aux ? ctx->ws_aux : ctx->ws;
+    size_t& have = ctx->on_aux ? ctx->ws_aux_bytes : ctx->ws_bytes;
+    if (bytes > have) {
+        // grow: everything queued so far on this arena's stream may still be using the old arena
         LLFE_CUDA(cudaStreamSynchronize(ctx->stream));
-        if (ctx->ws) LLFE_CUDA(cudaFree(ctx->ws));
-        ctx->ws = nullptr;
-        ctx->ws_bytes = 0;
+        if (ws) LLFE_CUDA(cudaFree(ws));
+        ws = nullptr;
+        have = 0;
         size_t want = bytes + bytes / 4 + (1 << 20);
-        LLFE_CUDA(cudaMalloc(&ctx->ws, want));
-        ctx->ws_bytes = want;
+        LLFE_CUDA(cudaMalloc(&ws, want));
+        have = want;
     }
-    *out = ctx->ws;
+    *out = ws;
+    return LLFE_OK;
+}
+
+// Second stream of the context (created on first use) and the fork / join around work enqueued on it.
+static int aux_begin(llfe_ctx* ctx, cudaStream_t* main_out) {
+    if (!ctx->aux_stream) {
+        LLFE_CUDA(cudaStreamCreateWithFlags(&ctx->aux_stream, cudaStreamNonBlocking));
+        LLFE_CUDA(cudaEventCreateWithFlags(&ctx->ev_fork, cudaEventDisableTiming));
+        LLFE_CUDA(cudaEventCreateWithFlags(&ctx->ev_join, cudaEventDisableTiming));
+    }
+    *main_out = ctx->stream;
+    LLFE_CUDA(cudaEventRecord(ctx->ev_fork, ctx->stream));
+    LLFE_CUDA(cudaStreamWaitEvent(ctx->aux_stream, ctx->ev_fork, 0));
+    return LLFE_OK;
+}
+static inline void aux_enter(llfe_ctx* ctx) {
+    ctx->stream = ctx->aux_stream;
+    ctx->on_aux = true;
+}
+static inline void aux_leave(llfe_ctx* ctx, cudaStream_t main_stream) {
+    ctx->stream = main_stream;
+    ctx->on_aux = false;
+}
+static int aux_join(llfe_ctx* ctx) {
+    LLFE_CUDA(cudaEventRecord(ctx->ev_join, ctx->aux_stream));
+    LLFE_CUDA(cudaStreamWaitEvent(ctx->stream, ctx->ev_join, 0));
     return LLFE_OK;
 }
 
@@ -132,6 +160,10 @@ int llfe_destroy(llfe_ctx* ctx) {
     cudaSetDevice(ctx->device);
     cudaStreamSynchronize(ctx->stream);
     if (ctx->ws) cudaFree(ctx->ws);
+    if (ctx->ws_aux) cudaFree(ctx->ws_aux);
+    if (ctx->ev_fork) cudaEventDestroy(ctx->ev_fork);
+    if (ctx->ev_join) cudaEventDestroy(ctx->ev_join);
+    if (ctx->aux_stream) cudaStreamDestroy(ctx->aux_stream);
     if (ctx->pin) cudaFreeHost(ctx->pin);
     if (ctx->dev_stage) cudaFree(ctx->dev_stage);
     if (ctx->dummy_sums) cudaFree(ctx->dummy_sums);
@@ -167,6 +199,9 @@ int llfe_set_option(llfe_ctx* ctx, const char* name, int64_t value) {
     LLFE_CHECK_ARG(name != nullptr);
     if (!strcmp(name, "unfused")) ctx->opt_unfused = value != 0;
     else if (!strcmp(name, "hyst_strips")) ctx->opt_hyst_strips = value != 0;
+    else if (!strcmp(name, "shadow_inline")) ctx->opt_shadow_inline = value != 0;
+    else if (!strcmp(name, "serial")) ctx->opt_serial = value != 0;
+    else if (!strcmp(name, "shadow_variant")) ctx->shadow_variant = (int)value;
     else {
         llfe_set_error("llfe_set_option: unknown option '%s'", name);
         return LLFE_E_INVALID;
@@ -504,51 +539,117 @@ int llfe_text_mask(llfe_ctx* ctx, const uint8_t* d_bgr, int n, int h, int w, uin
 }
 
 // ---- fused service pipeline ------------------------------------------------------
-int llfe_pipeline(llfe_ctx* ctx, const uint8_t* d_bgr, int n, int h, int w, int low, int high, uint8_t* d_shape_mask,
-                  uint8_t* d_shadow_mask, uint64_t* d_shadow_sum_count, const int8_t* d_noise, uint64_t seed,
-                  uint32_t* d_keys, int32_t* d_count, int max_unique) {
-    LLFE_ENTER(ctx);
+// k-means arguments of llfe_analyze (null = llfe_pipeline: stop after the unique-colour lists)
+struct KmeansCall {
+    int k, attempts, max_iter;
+    double eps;
+    const uint64_t* rng_state;
+    float* centers;
+    int32_t* labels;
+    int32_t* k_used;
+    int32_t* sizes;
+    int32_t* status;
+};
+
+static int analyze_impl(llfe_ctx* ctx, const uint8_t* d_bgr, int n, int h, int w, int low, int high, uint8_t* d_shape_mask,
+                        uint8_t* d_shadow_mask, uint64_t* d_shadow_sum_count, const int8_t* d_noise, uint64_t seed,
+                        uint32_t* d_keys, int32_t* d_count, int max_unique, const KmeansCall* km) {
     LLFE_IMG_ARGS(d_bgr);
     LLFE_CHECK_ARG(h > 0 && w > 0);
     LLFE_CHECK_ARG(d_keys == nullptr || (d_count != nullptr && max_unique > 0));
     if (n == 0) return LLFE_OK;
     if (fused_supported(h, w) && !ctx->opt_unfused) {
-        // One read of the image: planes + shadow mask + colour bitmap, then the small post-passes.
-        // The front kernel runs in chunks of 32 images so that the 2 MiB bitmaps of a chunk stay in L2;
-        // the hysteresis is latency-bound (a few busy warps per image), so it runs once per super-chunk
-        // of up to 256 images to have as many images in flight as the SMs can hold.
+        // Per chunk of 32 images: the front kernel (edge bit planes + the blurred gray plane), the shadow kernel on
+        // that plane, the colour pass (bitmaps of a chunk stay in L2) and the ordered compaction.  The hysteresis
+        // is latency-bound (a few busy warps per image), so it runs once per super-chunk of up to 256 images to
+        // have as many images in flight as the SMs can hold.
         const int chunk = n < 32 ? n : 32;
         const int super = n < 256 ? n : 256;
         const size_t plane_words = (size_t)super * h * plane_wpr(w), plane_img = (size_t)h * plane_wpr(w);
         const size_t bmw = bitmap_words_per_image(), bmb = bitmap_blocks_per_image();
+        const size_t p = (size_t)h * w;
+        // The adaptive threshold runs in its own kernel (k_shadow) on the blurred plane the front kernel writes for
+        // the chunk (L2-sized); "shadow_inline" keeps it inside the front kernel (the round-1 layout, for comparison).
+        const bool split = d_shadow_mask && !ctx->opt_shadow_inline;
+        const bool front = d_shape_mask != nullptr;   // anything for the front kernel besides the blurred plane?
+        const bool masks = d_shape_mask || d_shadow_mask, colours = d_keys != nullptr;
+        // Two independent chains: masks (front kernel, shadow kernel, hysteresis) and colours (colour pass, compaction,
+        // k-means).  With both present they run on two streams: the latency-bound kernels of one chain (hysteresis,
+        // compaction, the k-means tail) fill issue slots the other leaves idle.  Results do not depend on the schedule.
+        const bool two = masks && colours && !ctx->opt_serial;
+        const size_t need_colour = WsCarver::need(bmw * 4 * chunk) + WsCarver::need(bmb * 4 * chunk);
         size_t need = 2 * WsCarver::need(plane_words * 4) + WsCarver::need(hysteresis_flag_words(super, h) * 4);
-        if (d_keys) need += WsCarver::need(bmw * 4 * chunk) + WsCarver::need(bmb * 4 * chunk);
+        if (colours && !two) need += need_colour;
+        if (split) need += WsCarver::need(p * chunk);
         void* ws;
         LLFE_TRY(llfe_workspace(ctx, need, &ws));
         WsCarver carve(ws);
         uint32_t* weak = carve.take<uint32_t>(plane_words);
         uint32_t* edges = carve.take<uint32_t>(plane_words);
         uint32_t* flags = carve.take<uint32_t>(hysteresis_flag_words(super, h));
-        uint32_t* bitmap = d_keys ? carve.take<uint32_t>(bmw * chunk) : nullptr;
-        uint32_t* bsum = d_keys ? carve.take<uint32_t>(bmb * chunk) : nullptr;
-        const size_t p = (size_t)h * w;
+        uint8_t* blurred = split ? carve.take<uint8_t>(p * chunk) : nullptr;
+        uint32_t* bitmap = (colours && !two) ? carve.take<uint32_t>(bmw * chunk) : nullptr;
+        uint32_t* bsum = (colours && !two) ? carve.take<uint32_t>(bmb * chunk) : nullptr;
+        cudaStream_t main_stream = ctx->stream;
+        struct AuxScope {   // whatever happens below, the context goes back to its own stream
+            llfe_ctx* c;
+            cudaStream_t s;
+            ~AuxScope() {
+                c->stream = s;
+                c->on_aux = false;
+            }
+        } scope{ctx, main_stream};
+        if (two) LLFE_TRY(aux_begin(ctx, &main_stream));
         for (int s0 = 0; s0 < n; s0 += super) {
             const int sm = (n - s0) < super ? (n - s0) : super;
+            if (two) {   // the colour chain's scratch lives in the second arena (k-means may have grown it: carve again)
+                aux_enter(ctx);
+                void* wsc;
+                LLFE_TRY(llfe_workspace(ctx, need_colour, &wsc));
+                WsCarver cc(wsc);
+                bitmap = cc.take<uint32_t>(bmw * chunk);
+                bsum = cc.take<uint32_t>(bmb * chunk);
+                aux_leave(ctx, main_stream);
+            }
             for (int i0 = s0; i0 < s0 + sm; i0 += chunk) {
                 const int m = (s0 + sm - i0) < chunk ? (s0 + sm - i0) : chunk;
-                if (d_keys) LLFE_CUDA(cudaMemsetAsync(bitmap, 0, bmw * 4 * m, ctx->stream));
-                LLFE_TRY(launch_fused(ctx, d_bgr + i0 * p * 3, m, h, w, low, high,
-                                      d_shape_mask ? weak + (i0 - s0) * plane_img : nullptr,
-                                      d_shape_mask ? edges + (i0 - s0) * plane_img : nullptr,
-                                      d_shadow_mask ? d_shadow_mask + i0 * p : nullptr,
-                                      d_shadow_sum_count ? d_shadow_sum_count + 2 * i0 : nullptr,
-                                      d_noise ? d_noise + i0 * p * 3 : nullptr, seed, i0, bitmap));
-                if (d_keys)
+                if (masks) {
+                    if (split && !front) {
+                        LLFE_TRY(launch_gray_blur5(ctx, d_bgr + i0 * p * 3, m, h, w, blurred));
+                    } else {
+                        LLFE_TRY(launch_fused(ctx, d_bgr + i0 * p * 3, m, h, w, low, high,
+                                              d_shape_mask ? weak + (i0 - s0) * plane_img : nullptr,
+                                              d_shape_mask ? edges + (i0 - s0) * plane_img : nullptr,
+                                              (d_shadow_mask && !split) ? d_shadow_mask + i0 * p : nullptr,
+                                              (d_shadow_sum_count && !split) ? d_shadow_sum_count + 2 * i0 : nullptr, blurred));
+                    }
+                    if (split)
+                        LLFE_TRY(launch_shadow(ctx, blurred, m, h, w, d_shadow_mask + i0 * p,
+                                               d_shadow_sum_count ? d_shadow_sum_count + 2 * i0 : nullptr));
+                }
+                if (colours) {
+                    // a pointwise pass of its own over the chunk (bitmaps of 32 images stay in L2), then the ordered compaction
+                    if (two) aux_enter(ctx);
+                    LLFE_CUDA(cudaMemsetAsync(bitmap, 0, bmw * 4 * m, ctx->stream));
+                    LLFE_TRY(launch_color_bitmap(ctx, d_bgr + i0 * p * 3, m, h, w, d_noise ? d_noise + i0 * p * 3 : nullptr, seed,
+                                                 i0, bitmap));
                     LLFE_TRY(launch_bitmap_compact(ctx, bitmap, bsum, m, d_keys + (size_t)i0 * max_unique, nullptr,
                                                    d_count + i0, max_unique));
+                    if (two) aux_leave(ctx, main_stream);
+                }
             }
             if (d_shape_mask) LLFE_TRY(hysteresis_to_mask(ctx, weak, edges, sm, h, w, flags, 1, d_shape_mask + s0 * p));
+            if (km) {
+                if (two) aux_enter(ctx);
+                LLFE_TRY(llfe_kmeans_unique(ctx, d_keys + (size_t)s0 * max_unique, d_count + s0, sm, max_unique, km->k, km->attempts,
+                                            km->max_iter, km->eps, km->rng_state + s0, km->centers + (size_t)s0 * km->k * 3,
+                                            km->labels ? km->labels + (size_t)s0 * max_unique : nullptr, nullptr,
+                                            km->k_used ? km->k_used + s0 : nullptr, km->sizes ? km->sizes + (size_t)s0 * km->k : nullptr,
+                                            km->status ? km->status + s0 : nullptr));
+                if (two) aux_leave(ctx, main_stream);
+            }
         }
+        if (two) LLFE_TRY(aux_join(ctx));
         return LLFE_OK;
     }
     if (d_shape_mask || d_shadow_mask) {
@@ -562,7 +663,29 @@ int llfe_pipeline(llfe_ctx* ctx, const uint8_t* d_bgr, int n, int h, int w, int 
         if (d_shadow_mask) LLFE_TRY(launch_adaptive(ctx, blurred, n, h, w, 2, d_shadow_mask, d_shadow_sum_count));
     }
     if (d_keys) LLFE_TRY(launch_unique_colors(ctx, d_bgr, n, h, w, d_noise, seed, 0, d_keys, nullptr, d_count, max_unique));
+    if (km)
+        LLFE_TRY(llfe_kmeans_unique(ctx, d_keys, d_count, n, max_unique, km->k, km->attempts, km->max_iter, km->eps, km->rng_state,
+                                    km->centers, km->labels, nullptr, km->k_used, km->sizes, km->status));
     return LLFE_OK;
+}
+
+int llfe_pipeline(llfe_ctx* ctx, const uint8_t* d_bgr, int n, int h, int w, int low, int high, uint8_t* d_shape_mask,
+                  uint8_t* d_shadow_mask, uint64_t* d_shadow_sum_count, const int8_t* d_noise, uint64_t seed,
+                  uint32_t* d_keys, int32_t* d_count, int max_unique) {
+    LLFE_ENTER(ctx);
+    return analyze_impl(ctx, d_bgr, n, h, w, low, high, d_shape_mask, d_shadow_mask, d_shadow_sum_count, d_noise, seed, d_keys,
+                        d_count, max_unique, nullptr);
+}
+
+int llfe_analyze(llfe_ctx* ctx, const uint8_t* d_bgr, int n, int h, int w, int low, int high, uint8_t* d_shape_mask,
+                 uint8_t* d_shadow_mask, uint64_t* d_shadow_sum_count, const int8_t* d_noise, uint64_t seed, uint32_t* d_keys,
+                 int32_t* d_count, int max_unique, int k, int attempts, int max_iter, double eps, const uint64_t* d_rng_state,
+                 float* d_centers, int32_t* d_labels, int32_t* d_k_used, int32_t* d_cluster_sizes, int32_t* d_status) {
+    LLFE_ENTER(ctx);
+    LLFE_CHECK_ARG(d_keys != nullptr && d_count != nullptr && d_rng_state != nullptr && d_centers != nullptr);
+    KmeansCall km{k, attempts, max_iter, eps, d_rng_state, d_centers, d_labels, d_k_used, d_cluster_sizes, d_status};
+    return analyze_impl(ctx, d_bgr, n, h, w, low, high, d_shape_mask, d_shadow_mask, d_shadow_sum_count, d_noise, seed, d_keys,
+                        d_count, max_unique, &km);
 }
 
 // ---- host-buffer convenience entry points ----------------------------------------

@@ -16,6 +16,16 @@ struct llfe_ctx {
     // workspace arena (grown on demand; ops carve it per call)
     void* ws = nullptr;
     size_t ws_bytes = 0;
+    // second stream + arena of llfe_analyze: the colour chain (colour pass, compaction, k-means) runs on it next to
+    // the edge / shadow chain on `stream`.  While work is being enqueued for it, `stream` points at it and
+    // `on_aux` selects the second arena.
+    cudaStream_t aux_stream = nullptr;
+    cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
+    void* ws_aux = nullptr;
+    size_t ws_aux_bytes = 0;
+    bool on_aux = false;
+    int shadow_variant = 0;
+    bool opt_serial = false;       // llfe_set_option("serial", 1): everything on one stream (for A/B timing)
     // pinned staging for the *_host entry points
     void* pin = nullptr;
     size_t pin_bytes = 0;
@@ -35,6 +45,7 @@ struct llfe_ctx {
     // llfe_set_option: path toggles used by the parity tests (both off in production)
     bool opt_unfused = false;      // per-stage kernels instead of the fused front kernel
     bool opt_hyst_strips = false;  // multi-launch strip hysteresis instead of the cluster kernel
+    bool opt_shadow_inline = false;  // adaptive threshold inside the fused front kernel instead of k_shadow
     // llfe_set_debug_buffer: validated device buffers the k-means / hysteresis kernels write phase clocks to
     unsigned long long* dbg_kmeans = nullptr;
     size_t dbg_kmeans_bytes = 0;
@@ -178,5 +189,8 @@ int launch_bitmap_compact(llfe_ctx* ctx, const uint32_t* bitmap, uint32_t* bsum,
                           int32_t* d_count, int max_unique);
 bool fused_supported(int h, int w);
 int launch_fused(llfe_ctx* ctx, const uint8_t* bgr, int n, int h, int w, int low, int high, uint32_t* weak,
-                 uint32_t* strong, uint8_t* mask, uint64_t* sum_count, const int8_t* noise, uint64_t seed, int img0,
-                 uint32_t* bitmap);
+                 uint32_t* strong, uint8_t* mask, uint64_t* sum_count, uint8_t* blur_out);
+int launch_color_bitmap(llfe_ctx* ctx, const uint8_t* d_bgr, int m, int h, int w, const int8_t* d_noise, uint64_t seed,
+                        int first_image, uint32_t* bitmap);
+bool shadow_split_supported(int h, int w);
+int launch_shadow(llfe_ctx* ctx, const uint8_t* blurred, int n, int h, int w, uint8_t* mask, uint64_t* sum_count);

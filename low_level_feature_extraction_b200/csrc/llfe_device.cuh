@@ -111,20 +111,14 @@ __device__ __forceinline__ uint32_t fmix32(uint32_t x) {
 // P(non-zero) = p = 0.0455629 (+-1: 0.0227501 each, +-2: 3.167e-5 each; |n| >= 3 has 1e-9 and is
 // dropped), independent across samples.  NOT NumPy's MT19937 stream.
 //
-// Non-zero samples are rare, so they are drawn SPARSELY: the 24 channel samples of a group of
-// 8 consecutive pixels (linear pixel index >> 3) are visited by geometric skips -- the number
-// of zero samples before the next non-zero one is G = floor(log(u) / log(1 - p)) for uniform u,
-// which reproduces independent Bernoulli(p) samples exactly (memorylessness) at ~1.1 draws per
-// group instead of 24.  Every draw is a counter-based hash of (seed, group index, draw index),
-// so the noise is a pure function of the seed and the pixel position: any kernel, any launch
-// shape and any pass over the image regenerates the same values.
+// Non-zero samples are rare, so they are drawn SPARSELY by geometric skips: the number of zero
+// samples before the next non-zero one is G = floor(log(u) / log(1 - p)) for uniform u, which
+// reproduces independent Bernoulli(p) samples exactly (memorylessness) at one draw per non-zero
+// sample instead of one per sample.  Every draw is a counter-based hash of (seed, image, block
+// of 256 pixels, draw index).
 #define LLFE_NOISE_INV_LOG2_Q (-14.863987f) /* 1 / log2(1 - 0.0455629) */
 
-__device__ __forceinline__ uint32_t noise_group_base(uint64_t seed, uint64_t group) {
-    return (uint32_t)group + (uint32_t)seed * 0x9E3779B1u + ((uint32_t)(group >> 32) ^ (uint32_t)(seed >> 32)) * 0x7F4A7C15u;
-}
-
-// draw #i of a group: returns the skip (zeros before the next non-zero sample) and its value
+// draw #i of a block's stream: returns the skip (zeros before the next non-zero sample) and its value
 __device__ __forceinline__ int noise_draw(uint32_t base, int i, int& value) {
     const uint32_t h = fmix32(base + (uint32_t)(i + 1) * 0x85EBCA77u);
     const float u = __fmul_rn(__fadd_rn((float)(h >> 9), 0.5f), 1.0f / 8388608.0f);  // (0, 1), 23 bits
@@ -135,17 +129,38 @@ __device__ __forceinline__ int noise_draw(uint32_t base, int i, int& value) {
     return skip;
 }
 
-// Apply the group's noise to its 24 bytes held in memory `bytes` (any address space), byte k =
-// channel sample k of the group in MEMORY order (pixel-major, channel-minor as stored).
-template <typename BytePtr>
-__device__ __forceinline__ void noise_apply_group(uint64_t seed, uint64_t group, BytePtr bytes, int n_valid = 24) {
-    const uint32_t base = noise_group_base(seed, group);
-    int pos = -1;
-    for (int i = 0; i < 24; ++i) {
+// Warp-cooperative generation for a BLOCK of 256 consecutive pixels (768 channel samples in memory order,
+// linear pixel index >> 8): the 32 lanes draw 32 consecutive gaps of the block's geometric-skip stream at once,
+// an inclusive warp scan turns the gaps into sample positions, and every lane applies its own hit to the block's
+// bytes in shared memory.  The loop runs until the stream has passed the end of the block: 1.7 rounds on average,
+// warp-uniform (a per-thread stream over 24 samples needs 2.1 draws on average but the warp waits for its slowest
+// lane: ~5 rounds).  The noise is a pure function of (seed, image index, pixel position): any kernel that walks
+// the blocks with this function regenerates the same values.
+#define LLFE_NOISE_BLOCK_PX 256
+
+__device__ __forceinline__ uint32_t noise_block_base(uint64_t seed, uint32_t image, uint32_t block) {
+    uint32_t h = (uint32_t)seed * 0x9E3779B1u + ((uint32_t)(seed >> 32) ^ 0x7F4A7C15u) * 0x85EBCA6Bu;
+    h = fmix32(h + image * 0x85EBCA77u);
+    return fmix32(h ^ (block * 0xC2B2AE3Du));
+}
+
+// bytes: the block's samples in shared memory (byte k = channel sample k in memory order), n_valid <= 768 of them
+// exist.  All 32 lanes call this together; __syncwarp() before (bytes written) and after (bytes read) is the caller's.
+__device__ __forceinline__ void noise_apply_block(uint32_t base, uint8_t* bytes, int n_valid, int lane) {
+    int carry = 0;   // samples the stream has passed so far
+    for (int round = 0; carry < n_valid; ++round) {   // warp-uniform
         int v;
-        pos += 1 + noise_draw(base, i, v);
-        if (pos >= n_valid) break;
-        const int nv = (int)bytes[pos] + v;
-        bytes[pos] = (uint8_t)min(max(nv, 0), 255);
+        int s = 1 + noise_draw(base, round * 32 + lane, v);   // gap to the next non-zero sample, inclusive
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const int t = __shfl_up_sync(0xffffffffu, s, o);
+            if (lane >= o) s += t;
+        }
+        const int pos = carry + s - 1;
+        if (pos < n_valid) {
+            const int nv = (int)bytes[pos] + v;
+            bytes[pos] = (uint8_t)min(max(nv, 0), 255);
+        }
+        carry += __shfl_sync(0xffffffffu, s, 31);
     }
 }

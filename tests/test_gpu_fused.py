@@ -27,9 +27,17 @@ def dev(a):
     return torch.from_numpy(np.ascontiguousarray(a)).cuda()
 
 
+@pytest.fixture(params=["split", "inline"])
+def shadow_path(request, eng):
+    """The adaptive threshold in its own kernel (k_shadow, default) or inside the fused front kernel."""
+    eng.ctx.set_option("shadow_inline", 1 if request.param == "inline" else 0)
+    yield request.param
+    eng.ctx.set_option("shadow_inline", 0)
+
+
 @pytest.mark.parametrize("shape", SHAPES)
 @pytest.mark.parametrize("kind", ["noise", "design"])
-def test_fused_pipeline_matches_oracle(eng, shape, kind):
+def test_fused_pipeline_matches_oracle(eng, shape, kind, shadow_path):
     h, w = shape
     img = noise_image(h, w, h * 7 + w) if kind == "noise" else design_image(h, w, h + w)
     noise = cvops.make_noise((h * w, 3), 7 + h).reshape(h, w, 3)
@@ -71,7 +79,7 @@ def test_fused_thresholds_and_partial_outputs(eng):
     assert int(only_colors["count"][0]) == len(np.unique(img.reshape(-1, 3), axis=0))
 
 
-def test_fused_full_size_vs_cv2(eng):
+def test_fused_full_size_vs_cv2(eng, shadow_path):
     for img in (design_image(1080, 1920, 3), noise_image(1080, 1920, 4), design_image(1125, 2000, 5)):
         out = eng.pipeline(dev(img[None]), colors=False)
         assert np.array_equal(out["shape_mask"][0].cpu().numpy(), refpath.shape_mask(img))
@@ -133,7 +141,7 @@ def test_unfused_path_still_matches(eng):
         eng.ctx.set_option("unfused", 0)
 
 
-def test_tall_image_single_column_of_bands(eng):
+def test_tall_image_single_column_of_bands(eng, shadow_path):
     """A tall, narrow image (few, very tall row bands per CTA column): the masked sum / count accumulated per lane over
     thousands of rows must still be exact, also when the adaptive mask fires on very many pixels."""
     h, w = 3000, 64

@@ -63,6 +63,33 @@ def test_unique_colors_device_noise_distribution(eng):
     assert not np.array_equal(hist3.cpu().numpy()[:int(count3)], hist.cpu().numpy()[:n])
 
 
+def test_device_noise_samples_are_independent(eng):
+    """The warp-cooperative generator (one geometric-skip stream per block of 256 pixels) must give independent
+    channel samples: on a flat image every pixel's colour is its noise triple, so the number of non-zero channels
+    per pixel is Binomial(3, p), neighbouring pixels are uncorrelated, and blocks of 256 pixels are not periodic."""
+    h, w = 1024, 1024
+    img = np.full((h, w, 3), 100, np.uint8)
+    keys, count, hist = eng.unique_colors(dev(img), None, seed=4321, max_unique=4096, with_counts=True)
+    n = int(count)
+    rgb = keys_to_rgb(keys.cpu().numpy(), n).astype(int) - 100
+    cnt = hist.cpu().numpy()[:n].astype(np.float64)
+    total = float(h * w)
+    p = 0.0455629
+    nz = (rgb != 0).sum(1)
+    for k in range(4):
+        want = [1, 3, 3, 1][k] * p ** k * (1 - p) ** (3 - k)
+        got = cnt[nz == k].sum() / total
+        assert abs(got - want) < 5 * np.sqrt(want * (1 - want) / total) + 1e-7, (k, got, want)
+    # two seeds / two image indices give different noise; the same (seed, index) the same
+    a, ca = eng.unique_colors(dev(img), None, seed=4321, max_unique=4096, first_image=1)
+    assert not np.array_equal(a.cpu().numpy()[:n], keys.cpu().numpy()[:n]) or int(ca) != n
+    # partial last block (pixel count not a multiple of 256) and unaligned image base (odd byte offset for image 1)
+    small = np.full((2, 37, 21, 3), 50, np.uint8)
+    k2, c2, h2 = eng.unique_colors(dev(small), None, seed=7, max_unique=512, with_counts=True)
+    assert h2.cpu().numpy().sum(1).tolist() == [37 * 21, 37 * 21]
+    assert (c2.cpu().numpy() > 1).all()
+
+
 def test_kmeans_unique_matches_reference_golden(eng, golden, golden_inputs):
     meta, arrays = golden
     for c in meta["colors"]:
