@@ -33,7 +33,10 @@ BM = 1 << 21                                   # the 2^24-bit colour bitmap of o
 KERNEL_BYTES = {
     # fused front: read BGR (3P); write shadow mask (P) + weak/strong bit planes (2 * P/8); the
     # bitmap is L2-resident scratch (zeroed + scanned by other kernels) and is not counted here
+    # front kernel: read BGR (3P); write the weak/strong bit planes (2 * P/8) + the blurred gray plane (P)
     "k_fused": lambda P, U, A: 3 * P + P + P // 4,
+    # shadow kernel: read the blurred plane, write the mask
+    "k_shadow": lambda P, U, A: P + P,
     "k_gray_blur5": lambda P, U, A: 3 * P + P,
     "k_canny_front": lambda P, U, A: P + P // 4,
     "k_adaptive": lambda P, U, A: P + P,
@@ -77,13 +80,16 @@ def parse_args():
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", choices=["ours", "reference"], default="ours")
-    ap.add_argument("--workload", choices=sorted(WORKLOAD_BYTES), default="pipeline")
+    ap.add_argument("--workload", choices=sorted(WORKLOAD_BYTES) + ["pixel_kmeans"], default="pipeline")
     ap.add_argument("--batch", type=int, default=256, help="images per GPU per step")
     ap.add_argument("--height", type=int, default=1080)
     ap.add_argument("--width", type=int, default=1920)
     ap.add_argument("--k", type=int, default=5, help="palette size (n_colors); BASELINE config 3 uses 16")
-    ap.add_argument("--distinct", type=int, default=8, help="distinct synthetic images generated on the host")
-    ap.add_argument("--e2e-steps", type=int, default=2)
+    ap.add_argument("--distinct", type=int, default=64, help="distinct synthetic images generated on the host")
+    ap.add_argument("--e2e-steps", type=int, default=6)
+    ap.add_argument("--e2e-tail", choices=["thread", "inline"], default="thread",
+                    help="host palette tail of e2e: on a worker thread under the next step's copies, or inline")
+    ap.add_argument("--no-extras", action="store_true", help="skip the extra records (BASELINE configs 2, 3, 5, adversarial frames)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--cpu-seconds", type=float, default=10.0, help="target CPU time of the cpu_baseline sample")
@@ -216,145 +222,336 @@ def measured_peak():
         return 6650.0, "fallback (B200_PROFILING.md)"
 
 
+# ---- measurement helpers ------------------------------------------------------------------------------
+# kernels whose time is not bounded by HBM: reported with the bound that does limit them
+SM_BOUND = {"k_kmeans_fast": "sm (issue-bound: every Lloyd iteration runs out of shared memory, zero HBM traffic per iteration)",
+            "k_kmeans_fast_long": "sm", "k_kmeans_fast_global": "sm / L2 (lists that do not fit in shared memory)",
+            "k_hyst_mask": "latency (data-dependent propagation inside a thread-block cluster)"}
+
+
+def device_batch(dev, rank, B, H, W, distinct, kind="design"):
+    """(B, H, W, 3) u8 device batch: `distinct` synthetic images generated on the host, tiled (row-rolled) to B."""
+    import numpy as np
+    import torch
+
+    from low_level_feature_extraction_b200.synth import design_image, noise_image
+
+    distinct = max(1, min(distinct, B))
+    gen = design_image if kind == "design" else noise_image
+    batch = torch.empty((B, H, W, 3), dtype=torch.uint8, device=dev)
+    for s in range(distinct):
+        batch[s] = torch.from_numpy(gen(H, W, 100 * rank + s)).to(dev)
+    for i in range(distinct, B):
+        batch[i] = torch.roll(batch[i % distinct], shifts=7 * (i // distinct), dims=0)
+    return batch
+
+
+def timed_steps(an, batch, out, steps, warmup, world, dev, profile=False):
+    """-> (ms per step [max over ranks], per-kernel dict or None, launches summed over ranks)."""
+    import torch
+    import torch.distributed as dist
+
+    eng = an.engines[0]
+    for _ in range(warmup):
+        an.run_device(batch, out)
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize()
+    launches0 = eng.launches
+    if profile:
+        eng.ctx.profile_begin()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(steps):
+        an.run_device(batch, out)
+    e1.record()
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize()
+    kernels = eng.ctx.profile_end() if profile else None
+    ms = e0.elapsed_time(e1) / steps
+    launches = eng.launches - launches0
+    if world > 1:
+        t = torch.tensor([ms, float(launches)], dtype=torch.float64, device=dev)
+        mx = t.clone()
+        dist.all_reduce(mx, op=dist.ReduceOp.MAX)
+        dist.all_reduce(t, op=dist.ReduceOp.SUM)
+        ms, launches = float(mx[0].item()), int(t[1].item())
+    return ms, kernels, launches
+
+
+def measure_e2e(an, batch, steps, world, dev, colors, tail="thread"):
+    """images/sec through BatchAnalyzer.run_host: pinned host images in, host masks + palettes out, the
+    reference's palette tail (argsort / hex / ColorFeatures, color_extractor.py:231-284) computed on the host for
+    every image -- on a worker thread, while the next step's copies and kernels run."""
+    import time
+    from concurrent.futures import ThreadPoolExecutor
+
+    import torch
+    import torch.distributed as dist
+
+    B = batch.shape[0]
+    host_in = torch.empty(tuple(batch.shape), dtype=torch.uint8).pin_memory()
+    host_in.copy_(batch)
+    outs = [an.alloc_host_outputs(B) for _ in range(2)]      # double-buffered: the tail of step i reads buffer i % 2
+    res = an.run_host(host_in, outs[0])                      # warm-up (allocates the staging chunks)
+    if colors:
+        an.palettes(res)                                     # ... and the tail's first call (imports, pydantic model build)
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    pool = ThreadPoolExecutor(1)
+    sys.setswitchinterval(0.0005)   # the tail thread must not hold the interpreter for 5 ms while this thread enqueues copies
+    pending = []
+    n_palettes = 0
+    te = time.perf_counter()
+    for i in range(steps):
+        if len(pending) >= 2:
+            n_palettes += len(pending.pop(0).result())       # buffer i % 2 is free again
+        res = an.run_host(host_in, outs[i % 2])
+        if colors and tail == "thread":
+            pending.append(pool.submit(an.palettes, res))
+        elif colors:
+            n_palettes += len(an.palettes(res))
+    for f in pending:
+        n_palettes += len(f.result())
+    torch.cuda.synchronize()
+    dt = time.perf_counter() - te
+    pool.shutdown()
+    if world > 1:
+        t = torch.tensor([dt], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        dt = float(t.item())
+    return {"value": B * world * steps / dt, "unit": "images/sec",
+            "h2d_bytes_per_step": int(res["_h2d_bytes"]) * world, "d2h_bytes_per_step": int(res["_d2h_bytes"]) * world,
+            "steps": steps, "palette_tail_on_host": (tail if colors else False), "palettes_per_step": n_palettes // max(1, steps),
+            "api": "BatchAnalyzer.run_host: pinned host images in, host masks + ColorFeatures out; chunked copies overlapped "
+                   f"with kernels ({an.cfg.host_streams} streams, {an.cfg.host_chunk} images per stage)"}
+
+
+def pipeline_record(args, workload, B, H, W, k, steps, warmup, rank, world, local, dev, distinct, kind="design", e2e_steps=0,
+                    max_unique=1 << 16, sampler=None):
+    """One workload through BatchAnalyzer: device-resident throughput, per-kernel times (a separate short pass with the
+    two chains serialised, so that a kernel's time is its own), roofline of the dominant HBM-path kernel and of the step."""
+    import torch
+
+    from low_level_feature_extraction_b200.batch import BatchAnalyzer, BatchConfig
+
+    P = H * W
+    batch = device_batch(dev, rank, B, H, W, distinct, kind)
+    cfg = BatchConfig(colors=workload in ("pipeline", "colors", "palette_shadows"),
+                      shapes=workload in ("pipeline", "shapes"),
+                      shadows=workload in ("pipeline", "shadows", "palette_shadows"), k=k, max_unique=max_unique)
+    an = BatchAnalyzer(local, H, W, cfg)
+    eng = an.engines[0]
+    out = an.alloc_outputs(B)
+    t_begin = time.perf_counter()
+    ms, _, launches = timed_steps(an, batch, out, steps, warmup, world, dev)
+    t_end = time.perf_counter()
+    # the nvidia-smi sampler covers the warm-up + timed steps only: its NVML queries (every 50 ms) stall CUDA submissions
+    # enough to cost the copy-bound e2e loop two thirds of its throughput
+    clocks = sampler.stop(t_begin, t_end) if sampler else None
+    # per-kernel times: serial pass (on two streams the kernels of the two chains overlap and each one's event time
+    # contains the other's share of the SMs)
+    eng.ctx.set_option("serial", 1)
+    ms_serial, kernels, _ = timed_steps(an, batch, out, max(2, min(steps, 5)), 1, world, dev, profile=True)
+    eng.ctx.set_option("serial", 0)
+    psteps = max(2, min(steps, 5))
+    peak, peak_src = measured_peak()
+    u_avg = float(out["count"].float().mean().item()) if "count" in out else 0.0
+    overflow = int((out["count"] > cfg.max_unique).sum().item()) if "count" in out else 0
+
+    def kbytes(name):
+        return KERNEL_BYTES.get(name, lambda P, U, A: 0)(P, u_avg, cfg.attempts)
+
+    krec = {}
+    for name, v in sorted(kernels.items(), key=lambda kv: -kv[1]["ms"]):
+        per_step = v["ms"] / psteps
+        gbs = kbytes(name) * B / (per_step / 1e3) / 1e9 if per_step > 0 else 0.0
+        krec[name] = {"ms_per_step": per_step, "launches_per_step": v["launches"] / psteps,
+                      "bound": SM_BOUND.get(name, "hbm"), "achieved_gbs": gbs,
+                      "frac_of_hbm_peak": gbs / peak}
+    hbm = [(n, r) for n, r in krec.items() if r["bound"] == "hbm" and kbytes(n) > 0]
+    roofline = None
+    if hbm:
+        name, r = max(hbm, key=lambda kv: kv[1]["ms_per_step"])
+        per_launch_ms = r["ms_per_step"] / r["launches_per_step"]
+        imgs = B / r["launches_per_step"]
+        algo = kbytes(name) * imgs
+        ach = algo / (per_launch_ms / 1e3) / 1e9
+        rec = NCU_TRAFFIC.get(name)
+        traffic = None
+        if rec:
+            traffic = rec["bytes_per_launch"] * (imgs / rec["images_per_launch"] if rec.get("images_per_launch") else 1.0)
+        total = sum(x["ms_per_step"] for x in krec.values()) or 1.0
+        roofline = {"bound": "hbm", "kernel": name, "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak,
+                    "traffic": traffic, "peak_source": peak_src, "algorithmic_bytes_per_launch": algo,
+                    "avg_launch_ms": per_launch_ms, "share_of_step": r["ms_per_step"] / total, "images_per_launch": imgs,
+                    "note": "dominant kernel of the HBM path (largest CUDA-event time among the kernels that stream the images); "
+                            "per-kernel times from a pass with the two chains on one stream"}
+    step_bytes = WORKLOAD_BYTES[workload](P)
+    step_ach = step_bytes * B / (ms / 1e3) / 1e9
+    rec = {"workload": workload, "images_per_gpu": B, "height": H, "width": W, "k": k, "input": kind,
+           "distinct_images": min(distinct, B), "value": B * world / (ms / 1e3), "unit": "images/sec", "ms_per_step": ms,
+           "ms_per_step_serial": ms_serial, "steps": steps, "gpu_launches": launches, "unique_colours_per_image": u_avg,
+           "lists_redone_per_step": overflow, "clocks": clocks,
+           "roofline": roofline,
+           "roofline_step": {"bound": "hbm", "algorithmic_bytes_per_image": step_bytes, "achieved": step_ach, "peak": peak,
+                             "unit": "GB/s", "frac": step_ach / peak,
+                             "note": "whole step (all kernels, both streams) against the workload's algorithmic bytes, per GPU"},
+           "kernels": krec}
+    if e2e_steps:
+        rec["e2e"] = measure_e2e(an, batch, e2e_steps, world, dev, cfg.colors, getattr(args, "e2e_tail", "thread"))
+    del batch, out, an
+    torch.cuda.empty_cache()
+    return rec
+
+
+def pixel_kmeans_record(rank, world, local, dev, height, width, k, synth="design"):
+    """BASELINE config 5: ONE height x width image, rows sharded over the ranks (strong scaling), per-pixel k-means with
+    exact integer sums; the colour count table crosses NVLink once (reduce-scatter), the K x 4 sums every iteration."""
+    import hashlib
+    import importlib.util
+
+    import torch
+    import torch.distributed as dist
+
+    import low_level_feature_extraction_b200 as pkg
+    from low_level_feature_extraction_b200.dist import PixelKMeans, row_shard
+
+    spec = importlib.util.spec_from_file_location("run_pixel_kmeans", os.path.join(ROOT, "tools", "run_pixel_kmeans.py"))
+    rp = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(rp)
+    eng = pkg.engine(local)
+    r0, r1 = row_shard(height, rank, world)
+    gen = rp.synth_rows_photo if synth == "photo" else rp.synth_rows
+    rows = torch.cat([gen(s, min(r1, s + 1024), width, dev) for s in range(r0, r1, 1024)], dim=0)
+    g = torch.Generator().manual_seed(42)
+    pos = torch.randint(0, height * width, (k,), generator=g)
+    init = torch.zeros((k, 3), dtype=torch.float32, device=dev)
+    for j, p in enumerate(pos.tolist()):
+        y, x = divmod(p, width)
+        if r0 <= y < r1:
+            init[j] = rows[y - r0, x].flip(0).to(torch.float32)
+    if world > 1:
+        dist.all_reduce(init)
+    km = PixelKMeans(eng)
+    km.fit(rows, init, index_base=r0 * width)          # warm-up (allocations, NCCL channels)
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    reps = 5
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(reps):
+        res = km.fit(rows, init, index_base=r0 * width)
+    e1.record()
+    torch.cuda.synchronize()
+    fit_ms = e0.elapsed_time(e1) / reps
+    # the all-reduce of the K x 4 sums alone (what every iteration pays on top of its kernels)
+    sums = torch.zeros((k, 4), dtype=torch.int64, device=dev)
+    a0, a1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    for _ in range(3):
+        km._allreduce(sums, dist.ReduceOp.SUM)
+    a0.record()
+    for _ in range(20):
+        km._allreduce(sums, dist.ReduceOp.SUM)
+    a1.record()
+    torch.cuda.synchronize()
+    ar_ms = a0.elapsed_time(a1) / 20 if world > 1 else 0.0
+    if world > 1:
+        t = torch.tensor([fit_ms, ar_ms], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        fit_ms, ar_ms = t.tolist()
+    peak, _ = measured_peak()
+    npix = height * width
+    rec = {"workload": f"per-pixel k-means of ONE {width}x{height} image ({synth}-like synthetic rows), K={k}, rows sharded over "
+                       f"{world} GPU(s); colour-histogram form (rows read once, Lloyd over the distinct colours)",
+           "scaling": "strong", "n_gpus": world, "iterations": res.iters, "fit_ms": fit_ms, "value": 1e3 / fit_ms,
+           "unit": "fits/sec", "iterations_per_sec": res.iters / (fit_ms / 1e3),
+           "allreduce_ms_per_iteration": ar_ms, "allreduce_share_of_fit": ar_ms * res.iters / fit_ms,
+           "table_exchange": "reduce-scatter of the block-transposed 64 MiB colour table (each rank receives its 1/G)"
+                             if world > 1 else "none (1 GPU)",
+           "roofline_fit": {"bound": "hbm", "algorithmic_bytes": 3 * npix, "achieved": 3 * npix / (fit_ms / 1e3) / 1e9 / 1.0,
+                            "peak": peak * world, "unit": "GB/s", "frac": 3 * npix / (fit_ms / 1e3) / 1e9 / (peak * world),
+                            "note": "the whole fit against ONE read of the image (3 bytes per pixel), all GPUs"},
+           "centres_sha256": hashlib.sha256(res.centers.cpu().numpy().tobytes()).hexdigest(),
+           "comm_nranks_ok": (dist.get_world_size() == world) if world > 1 else True}
+    del rows
+    torch.cuda.empty_cache()
+    return rec
+
+
 def run_ours(args):
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local = int(os.environ.get("LOCAL_RANK", "0"))
     cpu = None
-    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+    if rank == 0 and world == 1 and not args.no_cpu_baseline and args.workload != "pixel_kmeans":
         cpu = cpu_baseline(args, args.cpu_seconds)     # before CUDA is initialised (fork-based pool)
 
-    import numpy as np
     import torch
     import torch.distributed as dist
-
-    from low_level_feature_extraction_b200.batch import BatchAnalyzer, BatchConfig
-    from low_level_feature_extraction_b200.synth import design_image
 
     torch.cuda.set_device(local)
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     dev = torch.device("cuda", local)
-    B, H, W = args.batch, args.height, args.width
-    P = H * W
 
-    # synthetic inputs: a few distinct design images per rank, tiled (rolled) to the batch on the device
-    base = np.stack([design_image(H, W, 100 * rank + s) for s in range(args.distinct)])
-    base_d = torch.from_numpy(base).to(dev)
-    batch = torch.empty((B, H, W, 3), dtype=torch.uint8, device=dev)
-    for i in range(B):
-        batch[i] = torch.roll(base_d[i % args.distinct], shifts=7 * (i // args.distinct), dims=0)
-    del base_d
-
-    cfg = BatchConfig(colors=args.workload in ("pipeline", "colors", "palette_shadows"),
-                      shapes=args.workload in ("pipeline", "shapes"),
-                      shadows=args.workload in ("pipeline", "shadows", "palette_shadows"), k=args.k)
-    an = BatchAnalyzer(local, H, W, cfg)
-    eng = an.engines[0]
-    out = an.alloc_outputs(B)
-
-    def barrier():
-        torch.cuda.synchronize()
+    if args.workload == "pixel_kmeans":
+        rec = pixel_kmeans_record(rank, world, local, dev, args.height if args.height != 1080 else 16384,
+                                  args.width if args.width != 1920 else 16384, args.k if args.k != 5 else 16)
+        if rank == 0:
+            line = {"metric": "fits/sec of one 16384x16384 per-pixel k-means (BASELINE config 5)", "value": rec["value"],
+                    "unit": "fits/sec", "n_gpus": world, "steps": 5, "warmup": 1, "ms_per_step": rec["fit_ms"],
+                    "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "u8", "data": "synthetic",
+                    "config": {"workload": rec["workload"]}, "record": rec}
+            print(json.dumps(line), flush=True)
         if world > 1:
-            dist.barrier()
-        torch.cuda.synchronize()
+            dist.destroy_process_group()
+        return
 
-    sampler = ClockSampler(local) if rank == 0 else None   # started early: samples during the warm-up are the fallback
-    for _ in range(args.warmup):
-        an.run_device(batch, out)
-    barrier()
+    sampler = ClockSampler(local) if rank == 0 else None   # samples during the whole run; the main record's window is cut out
     if sampler:
         sampler.wait_first()
-    barrier()
-    launches0 = eng.launches
-    eng.ctx.profile_begin()
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    t0 = time.perf_counter()
-    e0.record()
-    for _ in range(args.steps):
-        an.run_device(batch, out)
-    e1.record()
-    barrier()
-    t1 = time.perf_counter()
-    kernels = eng.ctx.profile_end()
-    launches = eng.launches - launches0
-    ms = e0.elapsed_time(e1)
-    clocks = sampler.stop(t0, t1) if sampler else None
-    if world > 1:
-        t = torch.tensor([ms], dtype=torch.float64, device=dev)
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        ms = float(t.item())
-        lt = torch.tensor([launches], dtype=torch.int64, device=dev)
-        dist.all_reduce(lt, op=dist.ReduceOp.SUM)
-        launches = int(lt.item())
-    value = B * world * args.steps / (ms / 1e3)
+    main = pipeline_record(args, args.workload, args.batch, args.height, args.width, args.k, args.steps, args.warmup, rank,
+                           world, local, dev, args.distinct, e2e_steps=0 if args.no_e2e else args.e2e_steps, sampler=sampler)
+    clocks = main.pop("clocks")
 
-    # ---- end to end through the host-buffer API ----------------------------------------
-    e2e = None
-    if not args.no_e2e:
-        host_in = torch.empty((B, H, W, 3), dtype=torch.uint8).pin_memory()
-        host_in.copy_(batch)
-        host_out = an.alloc_host_outputs(B)
-        an.run_host(host_in, host_out)     # warm-up (allocates the staging chunks)
-        barrier()
-        te = time.perf_counter()
-        for _ in range(args.e2e_steps):
-            res = an.run_host(host_in, host_out)
-        torch.cuda.synchronize()
-        dt = time.perf_counter() - te
-        if world > 1:
-            t = torch.tensor([dt], dtype=torch.float64, device=dev)
-            dist.all_reduce(t, op=dist.ReduceOp.MAX)
-            dt = float(t.item())
-        e2e = {"value": B * world * args.e2e_steps / dt, "unit": "images/sec",
-               "h2d_bytes_per_step": int(res["_h2d_bytes"]) * world, "d2h_bytes_per_step": int(res["_d2h_bytes"]) * world,
-               "steps": args.e2e_steps,
-               "api": "BatchAnalyzer.run_host: pinned host images in, host masks/palettes out, chunked copies "
-                      f"overlapped with kernels ({an.cfg.host_streams} streams, {an.cfg.host_chunk} images per stage)"}
+    extra = {}
+    if args.workload == "pipeline" and not args.no_extras:
+        def guarded(name, fn):
+            try:
+                extra[name] = fn()
+                extra[name].pop("clocks", None)
+            except Exception as e:   # an extra record never takes the headline line down with it
+                extra[name] = {"error": f"{type(e).__name__}: {e}"[:300]}
+                if world > 1:
+                    raise
+
+        guarded("config2_shapes_256x1080p", lambda: pipeline_record(
+            args, "shapes", 256, 1080, 1920, 5, 5, 2, rank, world, local, dev, 32))
+        guarded("config3_palette_shadows_64x4k_k16", lambda: pipeline_record(
+            args, "palette_shadows", 64, 2160, 3840, 16, 3, 1, rank, world, local, dev, 8))
+        if world == 1:
+            guarded("adversarial_uniform_noise_1080p", lambda: pipeline_record(
+                args, "pipeline", 4, 1080, 1920, 5, 1, 1, rank, world, local, dev, 4, kind="noise"))
+        guarded("config5_pixel_kmeans_16384x16384_k16", lambda: pixel_kmeans_record(
+            rank, world, local, dev, 16384, 16384, 16))
+        guarded("config5_pixel_kmeans_photo_like", lambda: pixel_kmeans_record(
+            rank, world, local, dev, 16384, 16384, 16, synth="photo"))
 
     if rank == 0:
-        peak, peak_src = measured_peak()
-        u_avg = float(out["count"].float().mean().item()) if "count" in out else 0.0
-
-        def ncu_traffic(name, imgs_per_launch):
-            """dram bytes per launch from the committed ncu capture, scaled to this run's images per launch."""
-            rec = NCU_TRAFFIC.get(name)
-            if not rec:
-                return None
-            scale = imgs_per_launch / rec["images_per_launch"] if rec.get("images_per_launch") else 1.0
-            return rec["bytes_per_launch"] * scale
-
-        def kernel_bytes(name):
-            return KERNEL_BYTES.get(name, lambda P, U, A: 0)(P, u_avg, cfg.attempts)
-
-        # dominant kernel: largest total device time inside the timed region
-        dom = max(kernels.items(), key=lambda kv: kv[1]["ms"]) if kernels else (None, None)
-        roofline = None
-        total_kernel_ms = sum(v["ms"] for v in kernels.values()) or 1.0
-        if dom[0]:
-            name, rec = dom
-            per_launch_ms = rec["ms"] / rec["launches"]
-            imgs_per_launch = B * args.steps / rec["launches"]
-            algo = kernel_bytes(name) * imgs_per_launch
-            ach = algo / (per_launch_ms / 1e3) / 1e9
-            roofline = {"bound": "hbm", "kernel": name, "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak,
-                        "traffic": ncu_traffic(name, imgs_per_launch), "peak_source": peak_src, "algorithmic_bytes_per_launch": algo,
-                        "avg_launch_ms": per_launch_ms, "share_of_step": rec["ms"] / total_kernel_ms,
-                        "images_per_launch": imgs_per_launch}
-        step_bytes = WORKLOAD_BYTES[args.workload](P) * B
-        step_ach = step_bytes / (ms / args.steps / 1e3) / 1e9
-        line = {"metric": METRIC, "value": value, "unit": "images/sec", "n_gpus": world, "steps": args.steps,
-                "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak",
+        line = {"metric": METRIC, "value": main["value"], "unit": "images/sec", "n_gpus": world, "steps": args.steps,
+                "warmup": args.warmup, "ms_per_step": main["ms_per_step"], "higher_is_better": True, "scaling": "weak",
                 "vs_baseline": None, "dtype": "u8", "data": "synthetic", "config": config_of(args, world),
-                "roofline": roofline,
-                "roofline_step": {"bound": "hbm", "algorithmic_bytes_per_image": WORKLOAD_BYTES[args.workload](P),
-                                  "achieved": step_ach, "peak": peak, "unit": "GB/s", "frac": step_ach / peak,
-                                  "note": "whole step (all kernels) against the workload's algorithmic bytes, per GPU"},
-                "kernels": {k: {"ms_per_step": v["ms"] / args.steps, "launches_per_step": v["launches"] / args.steps,
-                                "achieved_gbs": kernel_bytes(k) * B * args.steps / (v["ms"] / 1e3) / 1e9 if v["ms"] > 0 else 0.0}
-                            for k, v in sorted(kernels.items(), key=lambda kv: -kv[1]["ms"])},
-                "unique_colours_per_image": u_avg,
-                "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": launches, "clocks": clocks}
+                "roofline": main["roofline"], "roofline_step": main["roofline_step"], "kernels": main["kernels"],
+                "ms_per_step_serial": main["ms_per_step_serial"],
+                "unique_colours_per_image": main["unique_colours_per_image"],
+                "cpu_baseline": cpu, "e2e": main.get("e2e"), "gpu_launches": main["gpu_launches"],
+                "clocks": clocks, "extra": extra}
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()

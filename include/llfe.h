@@ -288,16 +288,20 @@ int llfe_pixels_histogram(llfe_ctx* ctx, const uint8_t* d_bgr, size_t n_pixels, 
  * np.unique's (R, G, B) order.  The table is cut into blocks of 2048 keys; only blocks b with
  * b % parts == part are emitted (rank r of a world of G passes part = r, parts = G).
  * *d_n = number of entries of that part; at most `cap` entries are written (cap = 0 with NULL
- * arrays just counts). */
+ * arrays just counts).  packed != 0: d_hist holds ONLY this part's blocks, back to back (block b of
+ * the table at slot b / parts; 8192 % parts == 0) -- what a reduce-scatter over the block-transposed
+ * table leaves on each rank, so that only 1/G of the table crosses NVLink instead of all of it. */
 int llfe_histogram_compact(llfe_ctx* ctx, const uint32_t* d_hist, int part, int parts, uint32_t* d_keys_or_null,
-                           uint32_t* d_counts_or_null, size_t cap, int32_t* d_n);
+                           uint32_t* d_counts_or_null, size_t cap, int32_t* d_n, int packed);
 
 /* llfe_kmeans_pixels_step over (key, count) entries: nearest centre per distinct colour
  * (cv2's float32 distance, first minimum), d_sums_counts += count * {R, G, B, 1}; optional
- * one label byte per entry; same d_state_or_null convention. */
+ * one label byte per entry; same d_state_or_null convention.  d_n_or_null: the number of entries as
+ * llfe_histogram_compact left it on the device (min(n, *d_n) entries are used), so that the host never
+ * has to read the count back between the compaction and the iterations. */
 int llfe_kmeans_hist_step(llfe_ctx* ctx, const uint32_t* d_keys, const uint32_t* d_counts, size_t n, int k,
                           const float* d_centers, uint64_t* d_sums_counts, uint8_t* d_labels_or_null,
-                          const int32_t* d_state_or_null);
+                          const int32_t* d_state_or_null, const int32_t* d_n_or_null);
 
 /* d_lut[key] = label for every entry (d_lut: 2^24 bytes, zeroed by the caller; ranks
  * all-reduce it with ncclSum since every colour belongs to exactly one part). */

@@ -73,8 +73,8 @@ PROTOTYPES = {
     "llfe_kmeans_hist_farthest": (i32, [vp, vp, sz, i32, vp, i32, vp, vp]),
     "llfe_kmeans_update": (i32, [vp, i32, vp, vp, i32, f64, vp, vp, vp, i32]),
     "llfe_pixels_histogram": (i32, [vp, vp, sz, vp]),
-    "llfe_histogram_compact": (i32, [vp, vp, i32, i32, vp, vp, sz, vp]),
-    "llfe_kmeans_hist_step": (i32, [vp, vp, vp, sz, i32, vp, vp, vp, vp]),
+    "llfe_histogram_compact": (i32, [vp, vp, i32, i32, vp, vp, sz, vp, i32]),
+    "llfe_kmeans_hist_step": (i32, [vp, vp, vp, sz, i32, vp, vp, vp, vp, vp]),
     "llfe_hist_labels_to_lut": (i32, [vp, vp, vp, sz, vp]),
     "llfe_pixels_lookup": (i32, [vp, vp, sz, vp, vp]),
     "llfe_pipeline": (i32, [vp, vp, i32, i32, i32, i32, i32, vp, vp, vp, vp, u64, vp, vp, i32]),

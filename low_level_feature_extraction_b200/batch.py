@@ -138,6 +138,16 @@ class BatchAnalyzer:
             out["status"] = torch.empty((n,), dtype=torch.int32).pin_memory()
         return out
 
+    def palettes(self, host_out: dict) -> list:
+        """The reference's palette tail (color_extractor.py:231-284: bincount order, hex, white / black filter, primary /
+        accents / background) for every image of a `run_host` result -> list of ColorFeatures."""
+        from .services.color_extractor import ColorExtractor
+
+        k_used = host_out["k_used"].numpy()
+        if (k_used < 0).any():
+            raise RuntimeError("unique-colour list truncated and not resolved")
+        return ColorExtractor._palettes_from_batch(host_out["centers"].numpy(), k_used, host_out["cluster_sizes"].numpy())
+
     def _stages(self, n: int):
         """(first image, count) of every pipeline stage: short stages at both ends so that the un-overlapped
         first upload and last download are small, full `host_chunk` stages in between."""

@@ -78,12 +78,13 @@ __global__ void __launch_bounds__(HT) k_hist_count(const uint8_t* __restrict__ b
 }
 
 // ---- ordered compaction of the non-empty bins of the blocks that belong to `part` --------------
-__global__ void __launch_bounds__(HT) k_hist_blockcount(const uint32_t* __restrict__ hist, int part, int parts,
+// packed != 0: `hist` is this part's share only, its blocks back to back (block b of the table at slot b / parts)
+__global__ void __launch_bounds__(HT) k_hist_blockcount(const uint32_t* __restrict__ hist, int part, int parts, int packed,
                                                         uint32_t* __restrict__ bcount) {
     const int b = blockIdx.x;
     int c = 0;
     if (b % parts == part) {
-        const uint4* p = reinterpret_cast<const uint4*>(hist + (size_t)b * HB) + threadIdx.x * (EPT / 4);
+        const uint4* p = reinterpret_cast<const uint4*>(hist + (size_t)(packed ? b / parts : b) * HB) + threadIdx.x * (EPT / 4);
 #pragma unroll
         for (int i = 0; i < EPT / 4; ++i) {
             const uint4 v = p[i];
@@ -140,14 +141,14 @@ __global__ void __launch_bounds__(1024) k_hist_blockscan(const uint32_t* __restr
     }
 }
 
-__global__ void __launch_bounds__(HT) k_hist_emit(const uint32_t* __restrict__ hist, int part, int parts,
+__global__ void __launch_bounds__(HT) k_hist_emit(const uint32_t* __restrict__ hist, int part, int parts, int packed,
                                                   const uint32_t* __restrict__ boffs, uint32_t* __restrict__ keys,
                                                   uint32_t* __restrict__ counts, size_t cap) {
     const int b = blockIdx.x;
     if (b % parts != part) return;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     uint32_t v[EPT];
-    const uint4* p = reinterpret_cast<const uint4*>(hist + (size_t)b * HB) + tid * (EPT / 4);
+    const uint4* p = reinterpret_cast<const uint4*>(hist + (size_t)(packed ? b / parts : b) * HB) + tid * (EPT / 4);
     int c = 0;
 #pragma unroll
     for (int i = 0; i < EPT / 4; ++i) {
@@ -212,8 +213,13 @@ __global__ void __launch_bounds__(HT) k_hist_step(const uint32_t* __restrict__ k
                                                   const uint32_t* __restrict__ counts, size_t n, int K,
                                                   const float* __restrict__ centers, u64* sums,
                                                   uint8_t* __restrict__ labels_out,
-                                                  const int32_t* __restrict__ state) {
+                                                  const int32_t* __restrict__ state, const int32_t* __restrict__ n_dev) {
     if (state && (state[1] | state[3])) return;
+    if (n_dev) {   // the list length lives on the device (no host round trip after the compaction)
+        const size_t nd = (size_t)max(*n_dev, 0);
+        n = nd < n ? nd : n;
+        if ((size_t)blockIdx.x * (HT * EPS_T) >= n) return;
+    }
     __shared__ u64 s_nc[KMAX][3];   // (-c, -c)
     __shared__ u64 s_acc[HT / 32][KMAX][4];
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -456,9 +462,10 @@ extern "C" int llfe_pixels_histogram(llfe_ctx* ctx, const uint8_t* d_bgr, size_t
 }
 
 extern "C" int llfe_histogram_compact(llfe_ctx* ctx, const uint32_t* d_hist, int part, int parts, uint32_t* d_keys_or_null,
-                                      uint32_t* d_counts_or_null, size_t cap, int32_t* d_n) {
+                                      uint32_t* d_counts_or_null, size_t cap, int32_t* d_n, int packed) {
     LLFE_ENTER(ctx);
     LLFE_CHECK_ARG(ctx != nullptr && d_hist != nullptr && d_n != nullptr && parts >= 1 && part >= 0 && part < parts);
+    LLFE_CHECK_ARG(!packed || NBLK % parts == 0);
     LLFE_CHECK_ARG(cap == 0 || (d_keys_or_null != nullptr && d_counts_or_null != nullptr));
     void* ws = nullptr;
     LLFE_TRY(llfe_workspace(ctx, 2 * WsCarver::need(NBLK * sizeof(uint32_t)), &ws));
@@ -466,14 +473,14 @@ extern "C" int llfe_histogram_compact(llfe_ctx* ctx, const uint32_t* d_hist, int
     uint32_t* bcount = carve.take<uint32_t>(NBLK);
     uint32_t* boffs = carve.take<uint32_t>(NBLK);
     LLFE_KERNEL(ctx, "k_hist_blockcount");
-    k_hist_blockcount<<<NBLK, HT, 0, ctx->stream>>>(d_hist, part, parts, bcount);
+    k_hist_blockcount<<<NBLK, HT, 0, ctx->stream>>>(d_hist, part, parts, packed, bcount);
     LLFE_LAUNCHED(ctx);
     LLFE_KERNEL(ctx, "k_hist_blockscan");
     k_hist_blockscan<<<1, 1024, 0, ctx->stream>>>(bcount, boffs, d_n);
     LLFE_LAUNCHED(ctx);
     if (cap > 0) {
         LLFE_KERNEL(ctx, "k_hist_emit");
-        k_hist_emit<<<NBLK, HT, 0, ctx->stream>>>(d_hist, part, parts, boffs, d_keys_or_null, d_counts_or_null, cap);
+        k_hist_emit<<<NBLK, HT, 0, ctx->stream>>>(d_hist, part, parts, packed, boffs, d_keys_or_null, d_counts_or_null, cap);
         LLFE_LAUNCHED(ctx);
     }
     return LLFE_OK;
@@ -481,7 +488,7 @@ extern "C" int llfe_histogram_compact(llfe_ctx* ctx, const uint32_t* d_hist, int
 
 extern "C" int llfe_kmeans_hist_step(llfe_ctx* ctx, const uint32_t* d_keys, const uint32_t* d_counts, size_t n, int k,
                                      const float* d_centers, uint64_t* d_sums_counts, uint8_t* d_labels_or_null,
-                                     const int32_t* d_state_or_null) {
+                                     const int32_t* d_state_or_null, const int32_t* d_n_or_null) {
     LLFE_ENTER(ctx);
     LLFE_CHECK_ARG(ctx != nullptr && d_centers != nullptr && d_sums_counts != nullptr && k >= 1 && k <= KMAX);
     LLFE_CHECK_ARG(n == 0 || (d_keys != nullptr && d_counts != nullptr));
@@ -490,7 +497,7 @@ extern "C" int llfe_kmeans_hist_step(llfe_ctx* ctx, const uint32_t* d_keys, cons
     const size_t cap = (size_t)ctx->sm_count * 8;
     LLFE_KERNEL(ctx, "k_hist_step");
     k_hist_step<<<(unsigned)(want > cap ? cap : want), HT, 0, ctx->stream>>>(
-        d_keys, d_counts, n, k, d_centers, (u64*)d_sums_counts, d_labels_or_null, d_state_or_null);
+        d_keys, d_counts, n, k, d_centers, (u64*)d_sums_counts, d_labels_or_null, d_state_or_null, d_n_or_null);
     LLFE_LAUNCHED(ctx);
     return LLFE_OK;
 }

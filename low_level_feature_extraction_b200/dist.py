@@ -98,6 +98,24 @@ class PixelKMeans:
         if dist.is_available() and dist.is_initialized() and dist.get_world_size(self.group) > 1:
             dist.all_reduce(t, op=op, group=self.group)
 
+    HB = 2048                    # keys per ownership block of the colour table (k_colorhist.cu)
+
+    def _reduce_scatter_blocks(self, hist: torch.Tensor, rank: int, ws: int):
+        """Sum of the colour table over the ranks, but only this rank's blocks (b % ws == rank), packed back to back.
+        None when the world size does not divide the block count or the backend has no reduce-scatter (gloo): the
+        caller falls back to the all-reduce of the whole table."""
+        nblk = hist.numel() // self.HB
+        if ws == 1:
+            return hist                          # packed with parts = 1 is the table itself
+        if nblk % ws != 0 or not (dist.is_available() and dist.is_initialized()):
+            return None
+        if dist.get_backend(self.group) != "nccl":
+            return None
+        send = hist.view(nblk // ws, ws, self.HB).transpose(0, 1).contiguous().view(-1)   # rank-major blocks
+        share = torch.empty((hist.numel() // ws,), dtype=hist.dtype, device=hist.device)
+        dist.reduce_scatter_tensor(share, send, op=dist.ReduceOp.SUM, group=self.group)
+        return share
+
     def fit(self, bgr_rows: torch.Tensor, init_centers: torch.Tensor, index_base: int = 0, max_iter: int = 200,
             eps: float = 0.2, want_labels: bool = False) -> PixelKMeansResult:
         """bgr_rows: this rank's (rows, w, 3) uint8 BGR rows (may be empty); init_centers: (k, 3)
@@ -118,13 +136,20 @@ class PixelKMeans:
             rank, ws = self._rank_world()
             hist = torch.zeros((1 << 24,), dtype=torch.int32, device=dev)
             be.pixels_histogram(bgr_rows, hist)
-            self._allreduce(hist, dist.ReduceOp.SUM)            # once: 64 MiB
-            keys, counts = be.histogram_compact(hist, rank, ws)  # this rank's interleaved share of the colours
-            del hist
+            # Every rank needs only ITS share of the summed table (the interleaved 2048-key blocks b % G == rank):
+            # reduce-scatter over the block-transposed table moves 1/G of what an all-reduce of the 64 MiB would.
+            share = self._reduce_scatter_blocks(hist, rank, ws)
+            if share is not None:
+                keys, counts, n_dev = be.histogram_compact_device(share, rank, ws, packed=True)
+            else:
+                self._allreduce(hist, dist.ReduceOp.SUM)
+                keys, counts, n_dev = be.histogram_compact_device(hist, rank, ws)
+            del hist, share
+            # the entry count stays on the device: no host round trip between the compaction and the iterations
             entry_labels = torch.empty((keys.numel(),), dtype=torch.uint8, device=dev) if want_labels else None
 
             def step():
-                be.kmeans_hist_step(keys, counts, centers, local, entry_labels, state)
+                be.kmeans_hist_step(keys, counts, centers, local, entry_labels, state, n_dev)
         else:
             def step():
                 be.kmeans_pixels_step(bgr_rows, centers, local, labels, state)
@@ -143,6 +168,10 @@ class PixelKMeans:
                                  zero_sums=True)
             st = state.tolist()          # the one host synchronisation per batch
             if st[3]:
+                if self.histogram and keys.numel() != int(n_dev.item()):   # the repair walks the real list (rare path)
+                    nn = int(n_dev.item())
+                    keys, counts = keys[:nn], counts[:nn]
+                    entry_labels = entry_labels[:nn] if entry_labels is not None else None
                 overrides = self._repair(flat, centers, sums, far, index_base, npix, None if self.histogram else labels,
                                          keys if self.histogram else None)
                 state[2:4] = 0
@@ -154,7 +183,8 @@ class PixelKMeans:
             if st[1]:
                 if self.histogram and want_labels:
                     lut = torch.zeros((1 << 24,), dtype=torch.uint8, device=dev)
-                    be.hist_labels_to_lut(keys, entry_labels, lut)
+                    nn = int(n_dev.item())
+                    be.hist_labels_to_lut(keys[:nn], entry_labels[:nn], lut)
                     self._allreduce(lut, dist.ReduceOp.SUM)   # every colour belongs to exactly one rank's share
                     be.pixels_lookup(bgr_rows, lut, labels)
                     if overrides_iter == st[0]:               # the repair came after the last assignment

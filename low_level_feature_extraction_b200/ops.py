@@ -373,20 +373,36 @@ class Engine:
         """(keys, counts): the non-empty bins of this part's interleaved blocks, key ascending (int32 tensors)."""
         self._bind()
         n = torch.zeros((1,), dtype=torch.int32, device=hist.device)
-        self.ctx.call("llfe_histogram_compact", hist, int(part), int(parts), None, None, 0, n)
+        self.ctx.call("llfe_histogram_compact", hist, int(part), int(parts), None, None, 0, n, 0)
         u = int(n.item())
         keys = torch.empty((u,), dtype=torch.int32, device=hist.device)
         counts = torch.empty((u,), dtype=torch.int32, device=hist.device)
         if u:
-            self.ctx.call("llfe_histogram_compact", hist, int(part), int(parts), keys, counts, u, n)
+            self.ctx.call("llfe_histogram_compact", hist, int(part), int(parts), keys, counts, u, n, 0)
         return keys, counts
 
+    def histogram_compact_device(self, hist: torch.Tensor, part: int = 0, parts: int = 1, packed: bool = False,
+                                 cap: int | None = None):
+        """Like histogram_compact but without the host round trip: (keys, counts) have room for every bin of the
+        part (or `cap`), the number of entries stays on the device -> (keys, counts, n (1,) int32).  packed: `hist`
+        is this part's share only (what `reduce_scatter` over the block-transposed table returns)."""
+        bins = hist.numel() if packed else self.HIST_BINS // int(parts) + 2048
+        cap = bins if cap is None else min(int(cap), bins)
+        keys = torch.empty((cap,), dtype=torch.int32, device=hist.device)
+        counts = torch.empty((cap,), dtype=torch.int32, device=hist.device)
+        n = torch.zeros((1,), dtype=torch.int32, device=hist.device)
+        self._bind()
+        self.ctx.call("llfe_histogram_compact", hist, int(part), int(parts), keys, counts, cap, n, 1 if packed else 0)
+        return keys, counts, n
+
     def kmeans_hist_step(self, keys: torch.Tensor, counts: torch.Tensor, centers: torch.Tensor, sums: torch.Tensor,
-                         labels: torch.Tensor | None = None, state: torch.Tensor | None = None):
-        """sums (k,4) int64 += count * {R, G, B, 1} per cluster over the (key, count) entries."""
+                         labels: torch.Tensor | None = None, state: torch.Tensor | None = None,
+                         n_dev: torch.Tensor | None = None):
+        """sums (k,4) int64 += count * {R, G, B, 1} per cluster over the (key, count) entries (the first n_dev[0] of
+        them when the count lives on the device)."""
         self._bind()
         self.ctx.call("llfe_kmeans_hist_step", keys, counts, keys.numel(), centers.shape[0], centers, sums, labels,
-                      state)
+                      state, n_dev)
 
     def hist_labels_to_lut(self, keys: torch.Tensor, labels: torch.Tensor, lut: torch.Tensor):
         assert lut.numel() == self.HIST_BINS and lut.dtype == torch.uint8

@@ -223,6 +223,41 @@ class ColorExtractor:
         bg_color = "#FFFFFF" if not ColorExtractor.is_light_color(ColorExtractor.hex_to_rgb(primary)) else "#000000"
         return ColorFeatures(primary=primary, background=bg_color, accent=accent_colors[:3], metadata=meta)
 
+    @staticmethod
+    def _palettes_from_batch(centers: np.ndarray, k_used: np.ndarray, sizes: np.ndarray) -> list:
+        """`_palette_from_clusters` for a whole batch: centers (n, K, 3) float32 as cv2.kmeans returns them, k_used
+        (n,), sizes (n, K) = np.bincount(labels) per image.  The ordering is the same literal NumPy call
+        (`np.argsort(-counts)`, applied row by row by `axis=1`: NumPy runs its 1-D argsort on every row, so ties fall
+        exactly as in the per-image call); everything else is the reference's arithmetic on integers instead of
+        on strings.  Equality with the per-image function is tested on the host (tests/test_services_host.py)."""
+        n, kk = sizes.shape
+        c8 = centers.astype(np.uint8)                                   # color_extractor.py:197 truncation
+        out: list = [None] * n
+        full = np.flatnonzero(k_used == kk) if kk > 1 else np.empty(0, np.int64)
+        if len(full):
+            order = np.argsort(-sizes[full].astype(np.int64), axis=1)  # color_extractor.py:234, one row per image
+            cs = np.take_along_axis(c8[full], order[:, :, None], axis=1).astype(np.uint32)
+            codes = ((cs[:, :, 0] << 16) | (cs[:, :, 1] << 8) | cs[:, :, 2]).tolist()
+            meta = {"success": True, "timestamp": 0.0, "processing_time": 0.0}
+            for row, i in zip(codes, full.tolist()):
+                cols = [v for v in row if v != 0xFFFFFF and v != 0]       # :242 drops pure white / black
+                if not cols:
+                    bg = "#000000" if ColorExtractor.is_light_color((255, 255, 255)) else "#FFFFFF"
+                    out[i] = ColorFeatures(primary=bg, background=bg, accent=[bg] * 3, metadata=dict(meta))
+                    continue
+                p = cols[0]
+                acc = [v for v in cols if v != p][:3]
+                while len(acc) < 3:
+                    acc.append(acc[-1] if acc else p)
+                light = ColorExtractor.is_light_color((p >> 16, (p >> 8) & 255, p & 255))
+                out[i] = ColorFeatures(primary="#%06x" % p, background="#000000" if light else "#FFFFFF",
+                                       accent=["#%06x" % v for v in acc], metadata=dict(meta))
+        for i in range(n):
+            if out[i] is None:      # fewer colours than clusters (or K = 1): the per-image path
+                k = int(k_used[i])
+                out[i] = ColorExtractor._palette_from_clusters(c8[i, :k], sizes[i, :k].astype(np.int64) if k > 1 else None)
+        return out
+
     # ---- the service call -------------------------------------------------------------------
     @staticmethod
     def extract_colors(image: Union[np.ndarray, Image.Image], n_colors: int = 5) -> ColorFeatures:

@@ -105,9 +105,29 @@ class OracleBackend:
         keys = keys[(keys // self.HB) % parts == part]
         return torch.from_numpy(keys.astype(np.int32)), torch.from_numpy(h[keys].astype(np.int32))
 
-    def kmeans_hist_step(self, keys, counts, centers, sums, labels=None, state=None):
+    def histogram_compact_device(self, hist, part=0, parts=1, packed=False, cap=None):
+        """(keys, counts) padded to the capacity of the part + the entry count as a tensor, as the CUDA engine returns."""
+        h = hist.numpy()
+        if packed:      # slot j of the share is block j * parts + part of the table
+            nz = np.flatnonzero(h)
+            keys = ((nz // self.HB) * parts + part) * self.HB + nz % self.HB
+            vals = h[nz]
+        else:
+            keys = np.flatnonzero(h)
+            keys = keys[(keys // self.HB) % parts == part]
+            vals = h[keys]
+        pad = 5    # some unused capacity behind the entries, like the real buffers
+        k = np.concatenate([keys, np.zeros(pad, np.int64)]).astype(np.int32)
+        v = np.concatenate([vals, np.zeros(pad, np.int64)]).astype(np.int32)
+        return torch.from_numpy(k), torch.from_numpy(v), torch.tensor([len(keys)], dtype=torch.int32)
+
+    def kmeans_hist_step(self, keys, counts, centers, sums, labels=None, state=None, n_dev=None):
         if state is not None and (int(state[1]) or int(state[3])):
             return
+        if n_dev is not None:
+            nn = int(n_dev[0])
+            keys, counts = keys[:nn], counts[:nn]
+            labels = labels[:nn] if labels is not None else None
         if keys.numel() == 0:
             return
         kk = keys.numpy().astype(np.int64)

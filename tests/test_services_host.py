@@ -95,3 +95,27 @@ def test_service_input_contract_raises_like_cv2(kind):
         for fn in (ref["ShapeAnalyzer"].preprocess_image, ref["ShadowAnalyzer"].analyze_shadow_level):
             with pytest.raises(cv2.error):
                 fn(x)
+
+
+def test_batched_palette_tail_equals_per_image_tail():
+    """`_palettes_from_batch` == `_palette_from_clusters` image by image, including tied cluster sizes (argsort's tie
+    order), pure white / black centres, palettes that lose every colour, and images with fewer colours than clusters."""
+    r = np.random.default_rng(7)
+    n, k = 600, 5
+    centers = r.integers(0, 256, (n, k, 3)).astype(np.float32) + r.random((n, k, 3)).astype(np.float32) * 0.99
+    sizes = r.integers(1, 6, (n, k)).astype(np.int32)             # many ties
+    k_used = np.full(n, k, np.int32)
+    centers[::7, 0] = 255.2                                        # white
+    centers[::11, 1] = 0.4                                         # black
+    centers[5] = np.array([[255.0] * 3, [0.0] * 3, [255.9] * 3, [0.9] * 3, [255.0] * 3])   # nothing left
+    centers[::13, 2] = centers[::13, 3]                            # duplicate colours
+    k_used[3], k_used[4] = 2, 1
+    sizes[3, 2:] = 0
+    sizes[4, 1:] = 0
+    got = ColorExtractor._palettes_from_batch(centers, k_used, sizes)
+    for i in range(n):
+        kk = int(k_used[i])
+        want = ColorExtractor._palette_from_clusters(centers[i, :kk].astype(np.uint8),
+                                                     sizes[i, :kk].astype(np.int64) if kk > 1 else None)
+        assert (got[i].primary, got[i].background, list(got[i].accent), got[i].metadata) == \
+               (want.primary, want.background, list(want.accent), want.metadata), i
