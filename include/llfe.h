@@ -332,6 +332,15 @@ int llfe_analyze(llfe_ctx* ctx, const uint8_t* d_bgr, int n, int h, int w, int l
                  int32_t* d_count, int max_unique, int k, int attempts, int max_iter, double eps, const uint64_t* d_rng_state,
                  float* d_centers, int32_t* d_labels, int32_t* d_k_used, int32_t* d_cluster_sizes, int32_t* d_status);
 
+/* ---- bit-packed masks for the host path -----------------------------------------------
+ * The masks the reference returns (u8, {0, 255}) carry one bit per pixel.  For host consumers the library can pack a
+ * device mask into a bit plane (bit x & 31 of word x >> 5, rows padded to llfe_mask_bits_words_per_row(w) 32-bit words,
+ * images back to back), so that P/8 instead of P bytes cross PCIe, and expand a plane that has arrived in host memory
+ * into the u8 array with `threads` host threads (no CUDA involved: plain pointers, any host memory). */
+int llfe_pack_mask_bits(llfe_ctx* ctx, const uint8_t* d_mask, int n, int h, int w, uint32_t* d_bits);
+int llfe_mask_bits_words_per_row(int w);
+int llfe_expand_mask_bits_host(const uint32_t* h_bits, int n, int h, int w, uint8_t* h_mask, int threads);
+
 /* ---- host-buffer convenience entry points (single image, synchronous) ------ */
 int llfe_shape_mask_host(llfe_ctx* ctx, const uint8_t* h_bgr, int h, int w, int low, int high, uint8_t* h_mask);
 int llfe_shadow_mask_host(llfe_ctx* ctx, const uint8_t* h_bgr, int h, int w, uint8_t* h_mask, uint8_t* h_blurred,

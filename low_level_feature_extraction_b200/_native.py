@@ -80,6 +80,9 @@ PROTOTYPES = {
     "llfe_pipeline": (i32, [vp, vp, i32, i32, i32, i32, i32, vp, vp, vp, vp, u64, vp, vp, i32]),
     "llfe_analyze": (i32, [vp, vp, i32, i32, i32, i32, i32, vp, vp, vp, vp, u64, vp, vp, i32, i32, i32, i32, f64, vp, vp, vp, vp,
                            vp, vp]),
+    "llfe_pack_mask_bits": (i32, [vp, vp, i32, i32, i32, vp]),
+    "llfe_mask_bits_words_per_row": (i32, [i32]),
+    "llfe_expand_mask_bits_host": (i32, [vp, i32, i32, i32, vp, i32]),
     "llfe_shape_mask_host": (i32, [vp, vp, i32, i32, i32, i32, vp]),
     "llfe_shadow_mask_host": (i32, [vp, vp, i32, i32, vp, vp, vp]),
     "llfe_text_mask_host": (i32, [vp, vp, i32, i32, vp, vp]),

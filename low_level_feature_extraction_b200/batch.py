@@ -37,6 +37,12 @@ class BatchConfig:
     chunk: int = 256           # images per C-ABI call on the device path (the library sub-chunks for L2)
     host_chunk: int = 16       # images per copy/compute pipeline stage of run_host
     host_streams: int = 3      # pipeline depth of run_host (streams / llfe contexts / staging buffers)
+    # run_host: masks cross PCIe as bit planes (P/8 bytes instead of P) and are expanded to the reference's u8 arrays
+    # by host threads while later stages are copied and computed (the copy back otherwise costs the inbound direction
+    # ~8 % on one GPU and more than half when eight ranks share the host's PCIe fabric)
+    packed_masks: bool = True
+    expand_threads: int = 4    # host threads per expansion call
+    expand_workers: int = 3    # stages being expanded at the same time
 
 
 class BatchAnalyzer:
@@ -48,6 +54,7 @@ class BatchAnalyzer:
         self.engines = [Engine(device) for _ in range(ns)]
         self.streams = [torch.cuda.Stream(self.device) for _ in range(ns)]
         self._dev_in = None
+        self._pool = None
 
     # ---- device-resident ---------------------------------------------------------------
     def alloc_outputs(self, n: int) -> dict:
@@ -187,10 +194,33 @@ class BatchAnalyzer:
         c = self.cfg
         n = images.shape[0]
         host_out = host_out if host_out is not None else self.alloc_host_outputs(n)
+        mask_keys = [k for k in ("shape_mask", "shadow_mask") if k in host_out]
+        packed = c.packed_masks and len(mask_keys) > 0
         if self._dev_in is None:
             ns = len(self.streams)
             self._dev_in = [torch.empty((c.host_chunk, self.h, self.w, 3), dtype=torch.uint8, device=self.device) for _ in range(ns)]
             self._dev_out = [self.alloc_outputs(c.host_chunk) for _ in range(ns)]
+            self._host_bits = None
+        if packed and (self._host_bits is None or self._host_bits.shape[1] < n):
+            from concurrent.futures import ThreadPoolExecutor
+
+            wpr = self.engines[0].ctx.lib.llfe_mask_bits_words_per_row(self.w)
+            self._dev_bits = [torch.empty((len(mask_keys), c.host_chunk, self.h, wpr), dtype=torch.int32, device=self.device)
+                              for _ in range(len(self.streams))]
+            self._host_bits = torch.empty((len(mask_keys), n, self.h, wpr), dtype=torch.int32).pin_memory()
+            if self._pool is None:
+                self._pool = ThreadPoolExecutor(max(1, c.expand_workers), thread_name_prefix="llfe-expand")
+        lib = self.engines[0].ctx.lib
+        pending = []
+
+        def expand(ev, i0, m):
+            ev.synchronize()                     # releases the GIL; the expansion below is a ctypes call (ditto)
+            for j, key in enumerate(mask_keys):
+                rc = lib.llfe_expand_mask_bits_host(self._host_bits[j, i0:i0 + m].data_ptr(), m, self.h, self.w,
+                                                    host_out[key][i0:i0 + m].data_ptr(), c.expand_threads)
+                if rc != 0:
+                    raise RuntimeError(lib.llfe_last_error().decode())
+
         bytes_in = bytes_out = 0
         for j, (i0, m) in enumerate(self._stages(n)):
             b = j % len(self.streams)
@@ -201,13 +231,27 @@ class BatchAnalyzer:
                 bytes_in += din.numel()
                 dout = {k: v[:m] for k, v in self._dev_out[b].items()}
                 self.run_device(din, dout, engine=self.engines[b], resolve=False)
-                for key in ("shape_mask", "shadow_mask", "shadow_sums", "centers", "count", "k_used", "cluster_sizes",
-                            "status"):
+                small = ["shadow_sums", "centers", "count", "k_used", "cluster_sizes", "status"]
+                if packed:
+                    eng = self.engines[b]
+                    for q, key in enumerate(mask_keys):
+                        bits = self._dev_bits[b][q, :m]
+                        eng.ctx.call("llfe_pack_mask_bits", dout[key], m, self.h, self.w, bits)
+                        self._host_bits[q, i0:i0 + m].copy_(bits, non_blocking=True)
+                        bytes_out += bits.numel() * 4
+                    ev = torch.cuda.Event()
+                    ev.record(st)
+                    pending.append(self._pool.submit(expand, ev, i0, m))
+                else:
+                    small = mask_keys + small
+                for key in small:
                     if key in host_out:
                         host_out[key][i0:i0 + m].copy_(dout[key], non_blocking=True)
                         bytes_out += dout[key].numel() * dout[key].element_size()
         for st in self.streams:
             st.synchronize()
+        for f in pending:
+            f.result()
         if c.colors:
             # images whose colour list overflowed the batched capacity: upload again, redo alone (rare: photo-like
             # frames), patch the host results.  The stage's chunk-local index fixes the noise.

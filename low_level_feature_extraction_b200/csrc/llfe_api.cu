@@ -5,6 +5,8 @@
 #include <string.h>
 
 #include <new>
+#include <thread>
+#include <vector>
 
 #include "llfe_common.cuh"
 
@@ -686,6 +688,60 @@ int llfe_analyze(llfe_ctx* ctx, const uint8_t* d_bgr, int n, int h, int w, int l
     KmeansCall km{k, attempts, max_iter, eps, d_rng_state, d_centers, d_labels, d_k_used, d_cluster_sizes, d_status};
     return analyze_impl(ctx, d_bgr, n, h, w, low, high, d_shape_mask, d_shadow_mask, d_shadow_sum_count, d_noise, seed, d_keys,
                         d_count, max_unique, &km);
+}
+
+// ---- bit-packed masks for the host path ---------------------------------------------------
+// A u8 mask in {0, 255} carries one bit per pixel: over PCIe it travels as a bit plane (P/8 bytes instead of P) and is
+// expanded to the reference's u8 array by host threads.  Plane layout as everywhere in the library: bit (x & 31) of word
+// (x >> 5), rows padded to plane_wpr(w) words, images back to back.
+int llfe_pack_mask_bits(llfe_ctx* ctx, const uint8_t* d_mask, int n, int h, int w, uint32_t* d_bits) {
+    LLFE_ENTER(ctx);
+    LLFE_CHECK_ARG(d_mask != nullptr && d_bits != nullptr && n >= 0 && h >= 0 && w >= 0 && n <= 65535);
+    return launch_mask_to_plane(ctx, d_mask, nullptr, n, h, w, d_bits);
+}
+
+int llfe_mask_bits_words_per_row(int w) { return plane_wpr(w); }
+
+int llfe_expand_mask_bits_host(const uint32_t* h_bits, int n, int h, int w, uint8_t* h_mask, int threads) {
+    if (!h_bits || !h_mask || n < 0 || h < 0 || w < 0) {
+        llfe_set_error("llfe_expand_mask_bits_host: invalid argument");
+        return LLFE_E_INVALID;
+    }
+    static uint64_t lut[256];
+    static bool lut_ready = false;
+    if (!lut_ready) {   // byte of 8 mask bits -> 8 mask bytes (benign race: every thread writes the same values)
+        for (int b = 0; b < 256; ++b) {
+            uint64_t v = 0;
+            for (int j = 0; j < 8; ++j)
+                if (b & (1 << j)) v |= 0xffull << (8 * j);
+            lut[b] = v;
+        }
+        lut_ready = true;
+    }
+    const int wpr = plane_wpr(w);
+    const size_t rows = (size_t)n * h;
+    auto work = [=](size_t r0, size_t r1) {
+        for (size_t r = r0; r < r1; ++r) {
+            const uint8_t* src = reinterpret_cast<const uint8_t*>(h_bits + r * wpr);
+            uint8_t* dst = h_mask + r * (size_t)w;
+            const int full = w >> 3;
+            for (int i = 0; i < full; ++i) {
+                const uint64_t v = lut[src[i]];
+                memcpy(dst + 8 * (size_t)i, &v, 8);
+            }
+            for (int x = full << 3; x < w; ++x) dst[x] = (src[x >> 3] >> (x & 7)) & 1 ? 255 : 0;
+        }
+    };
+    int t = threads < 1 ? 1 : threads;
+    if ((size_t)t > rows) t = rows ? (int)rows : 1;
+    if (t == 1) {
+        work(0, rows);
+        return LLFE_OK;
+    }
+    std::vector<std::thread> pool;
+    for (int i = 0; i < t; ++i) pool.emplace_back(work, rows * i / t, rows * (i + 1) / t);
+    for (auto& th : pool) th.join();
+    return LLFE_OK;
 }
 
 // ---- host-buffer convenience entry points ----------------------------------------

@@ -8,8 +8,10 @@ from low_level_feature_extraction_b200.synth import design_image
 B, H, W = 256, 1080, 1920
 base = np.stack([design_image(H, W, s) for s in range(8)])
 host = torch.from_numpy(np.concatenate([base] * (B // 8))).pin_memory()
-for name, cfgkw, opts in [("default", {}, {}), ("serial", {}, {"serial": 1}), ("streams1", {"host_streams": 1}, {}),
-                          ("chunk32", {"host_chunk": 32}, {}), ("nocolors", {"colors": False}, {})]:
+for name, cfgkw, opts in [("default (packed masks)", {}, {}), ("u8 masks over PCIe", {"packed_masks": False}, {}),
+                          ("packed, 2 threads x 2 workers", {"expand_threads": 2, "expand_workers": 2}, {}),
+                          ("packed, 8 threads x 3 workers", {"expand_threads": 8, "expand_workers": 3}, {}),
+                          ("packed, chunk 32", {"host_chunk": 32}, {})]:
     an = BatchAnalyzer(0, H, W, BatchConfig(**cfgkw))
     for e in an.engines:
         for k, v in opts.items():
