@@ -40,7 +40,7 @@ KERNEL_BYTES = {
     "k_gray_blur5": lambda P, U, A: 3 * P + P,
     "k_canny_front": lambda P, U, A: P + P // 4,
     "k_adaptive": lambda P, U, A: P + P,
-    "k_color_bitmap": lambda P, U, A: 3 * P,
+    "k_color_pass": lambda P, U, A: 3 * P,
     # hysteresis: read weak + strong planes, write the edge plane (in place)
     "k_hyst": lambda P, U, A: 3 * (P // 8),
     "k_hyst_mask": lambda P, U, A: 2 * (P // 8) + P,

@@ -332,6 +332,22 @@ int llfe_analyze(llfe_ctx* ctx, const uint8_t* d_bgr, int n, int h, int w, int l
                  int32_t* d_count, int max_unique, int k, int attempts, int max_iter, double eps, const uint64_t* d_rng_state,
                  float* d_centers, int32_t* d_labels, int32_t* d_k_used, int32_t* d_cluster_sizes, int32_t* d_status);
 
+/* ---- external contours of a mask (cv2.findContours(mask, RETR_EXTERNAL, CHAIN_APPROX_SIMPLE)) -----------------------
+ * Replaces the call in ShapeAnalyzer.extract_shapes / analyze_shapes (app/services/__pycache__/shape_analyzer.cpython-312.pyc,
+ * source lines 76 and 140) and FontDetector.detect_text_regions (app/services/analyze/font_detector.py:51-55).
+ * Any non-zero mask byte is foreground, as in OpenCV.  Per image the call writes
+ *   d_counts  (n, 4) int32: {external contours found, points written, 1 if max_points was too small, 0};
+ *   d_headers (n, max_contours) records of 40 bytes = int32 {start (y * w + x of the contour's first point), npts, offset
+ *             (index of its first point in the image's point array, -1 if its points were not written), min x, min y,
+ *             max x, max y, 0} + int64 {2 * signed area (Green's formula: |value| / 2 == cv2.contourArea)};
+ *   d_points  (n, max_points, 2) int32 (x, y): the CHAIN_APPROX_SIMPLE vertices, in OpenCV's order, of the contours with
+ *             |2 * area| >= min_area2 (the reference drops contours with cv2.contourArea < 100: min_area2 = 200).
+ * The records are in no particular order; cv2 returns contours by DESCENDING `start`.  A caller that sees
+ * counts[0] > max_contours or counts[2] != 0 repeats the call with larger buffers.  max_points = 0 (d_points may be NULL)
+ * returns headers only (bounding boxes, areas). */
+int llfe_contours_external(llfe_ctx* ctx, const uint8_t* d_mask, int n, int h, int w, int64_t min_area2, int32_t* d_headers,
+                           int max_contours, int32_t* d_points, int max_points, int32_t* d_counts);
+
 /* ---- bit-packed masks for the host path -----------------------------------------------
  * The masks the reference returns (u8, {0, 255}) carry one bit per pixel.  For host consumers the library can pack a
  * device mask into a bit plane (bit x & 31 of word x >> 5, rows padded to llfe_mask_bits_words_per_row(w) 32-bit words,
@@ -343,6 +359,13 @@ int llfe_expand_mask_bits_host(const uint32_t* h_bits, int n, int h, int w, uint
 
 /* ---- host-buffer convenience entry points (single image, synchronous) ------ */
 int llfe_shape_mask_host(llfe_ctx* ctx, const uint8_t* h_bgr, int h, int w, int low, int high, uint8_t* h_mask);
+/* contours of a host mask / of the shape mask of a host image (ShapeAnalyzer: gray -> blur -> Canny -> dilate -> contours in
+ * one call; h_mask may be NULL when the caller does not need the mask itself) */
+int llfe_contours_external_host(llfe_ctx* ctx, const uint8_t* h_mask, int h, int w, int64_t min_area2, int32_t* h_headers,
+                                int max_contours, int32_t* h_points, int max_points, int32_t* h_counts);
+int llfe_shape_contours_host(llfe_ctx* ctx, const uint8_t* h_bgr, int h, int w, int low, int high, int64_t min_area2,
+                             uint8_t* h_mask, int32_t* h_headers, int max_contours, int32_t* h_points, int max_points,
+                             int32_t* h_counts);
 int llfe_shadow_mask_host(llfe_ctx* ctx, const uint8_t* h_bgr, int h, int w, uint8_t* h_mask, uint8_t* h_blurred,
                           uint64_t* h_sum_count);
 int llfe_text_mask_host(llfe_ctx* ctx, const uint8_t* h_bgr, int h, int w, uint8_t* h_mask, int32_t* h_thresh);

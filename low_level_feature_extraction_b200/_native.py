@@ -77,6 +77,9 @@ PROTOTYPES = {
     "llfe_kmeans_hist_step": (i32, [vp, vp, vp, sz, i32, vp, vp, vp, vp, vp]),
     "llfe_hist_labels_to_lut": (i32, [vp, vp, vp, sz, vp]),
     "llfe_pixels_lookup": (i32, [vp, vp, sz, vp, vp]),
+    "llfe_contours_external": (i32, [vp, vp, i32, i32, i32, C.c_int64, vp, i32, vp, i32, vp]),
+    "llfe_contours_external_host": (i32, [vp, vp, i32, i32, C.c_int64, vp, i32, vp, i32, vp]),
+    "llfe_shape_contours_host": (i32, [vp, vp, i32, i32, i32, i32, C.c_int64, vp, vp, i32, vp, i32, vp]),
     "llfe_pipeline": (i32, [vp, vp, i32, i32, i32, i32, i32, vp, vp, vp, vp, u64, vp, vp, i32]),
     "llfe_analyze": (i32, [vp, vp, i32, i32, i32, i32, i32, vp, vp, vp, vp, u64, vp, vp, i32, i32, i32, i32, f64, vp, vp, vp, vp,
                            vp, vp]),

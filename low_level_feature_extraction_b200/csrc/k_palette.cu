@@ -259,7 +259,7 @@ int launch_unique_colors(llfe_ctx* ctx, const uint8_t* d_bgr, int n, int h, int 
         const uint8_t* src = d_bgr + (size_t)i0 * npix * 3;
         const int8_t* nz = d_noise ? d_noise + (size_t)i0 * npix * 3 : nullptr;
         LLFE_CUDA(cudaMemsetAsync(bitmap, 0, (size_t)BM_WORDS * 4 * m, ctx->stream));
-        LLFE_KERNEL(ctx, "k_color_bitmap");
+        LLFE_KERNEL(ctx, "k_color_pass");
         k_color_pass<0><<<dim3(gx, m), CP_WARPS * 32, 0, ctx->stream>>>(src, npix, nz, seed, first_image + i0, bitmap, nullptr, nullptr,
                                                               max_unique);
         LLFE_LAUNCHED(ctx);
@@ -281,7 +281,7 @@ int launch_color_bitmap(llfe_ctx* ctx, const uint8_t* d_bgr, int m, int h, int w
                         int first_image, uint32_t* bitmap) {
     const size_t npix = (size_t)h * w;
     const unsigned gx = color_pass_grid(ctx, npix, m);
-    LLFE_KERNEL(ctx, "k_color_bitmap");
+    LLFE_KERNEL(ctx, "k_color_pass");
     k_color_pass<0><<<dim3(gx, m), CP_WARPS * 32, 0, ctx->stream>>>(d_bgr, npix, d_noise, seed, first_image, bitmap, nullptr,
                                                                     nullptr, 0);
     LLFE_LAUNCHED(ctx);

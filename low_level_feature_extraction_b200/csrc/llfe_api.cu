@@ -941,4 +941,56 @@ int llfe_resize_lanczos4_host(llfe_ctx* ctx, const uint8_t* h_src, int sh, int s
     return stage_end(&st, h_dst, out, 0);
 }
 
+// ---- contours (k_contours.cu) on host buffers: only headers + polygon vertices come back ----------------------------
+static int contours_fetch(llfe_ctx* ctx, HostStage* st, size_t hdr_off, size_t pts_off, size_t cnt_off, int max_contours,
+                          int max_points, int32_t* h_headers, int32_t* h_points, int32_t* h_counts) {
+    LLFE_CUDA(cudaMemcpyAsync(st->p_out + cnt_off, st->d_out + cnt_off, 16, cudaMemcpyDeviceToHost, ctx->stream));
+    LLFE_CUDA(cudaStreamSynchronize(ctx->stream));
+    int32_t cnt[4];
+    memcpy(cnt, st->p_out + cnt_off, 16);
+    const size_t nh = (size_t)(cnt[0] < max_contours ? cnt[0] : max_contours) * 40;
+    const size_t np = (size_t)(cnt[1] < max_points ? cnt[1] : max_points) * 8;
+    if (nh) LLFE_CUDA(cudaMemcpyAsync(st->p_out + hdr_off, st->d_out + hdr_off, nh, cudaMemcpyDeviceToHost, ctx->stream));
+    if (np) LLFE_CUDA(cudaMemcpyAsync(st->p_out + pts_off, st->d_out + pts_off, np, cudaMemcpyDeviceToHost, ctx->stream));
+    if (nh || np) LLFE_CUDA(cudaStreamSynchronize(ctx->stream));
+    if (nh) memcpy(h_headers, st->p_out + hdr_off, nh);
+    if (np) memcpy(h_points, st->p_out + pts_off, np);
+    memcpy(h_counts, cnt, 16);
+    return LLFE_OK;
+}
+
+int llfe_contours_external_host(llfe_ctx* ctx, const uint8_t* h_mask, int h, int w, int64_t min_area2, int32_t* h_headers,
+                                int max_contours, int32_t* h_points, int max_points, int32_t* h_counts) {
+    LLFE_ENTER(ctx);
+    LLFE_CHECK_ARG(h_mask != nullptr && h_headers != nullptr && h_counts != nullptr && h > 0 && w > 0 && max_contours > 0 &&
+                   max_points >= 0 && (h_points != nullptr || max_points == 0));
+    const size_t p = (size_t)h * w, hb = WsCarver::need((size_t)max_contours * 40), pb = WsCarver::need((size_t)max_points * 8);
+    HostStage st;
+    LLFE_TRY(stage_begin(ctx, h_mask, p, hb + pb + 256, &st));
+    LLFE_TRY(llfe_contours_external(ctx, st.d_in, 1, h, w, min_area2, (int32_t*)st.d_out, max_contours,
+                                    (int32_t*)(st.d_out + hb), max_points, (int32_t*)(st.d_out + hb + pb)));
+    return contours_fetch(ctx, &st, 0, hb, hb + pb, max_contours, max_points, h_headers, h_points, h_counts);
+}
+
+int llfe_shape_contours_host(llfe_ctx* ctx, const uint8_t* h_bgr, int h, int w, int low, int high, int64_t min_area2,
+                             uint8_t* h_mask, int32_t* h_headers, int max_contours, int32_t* h_points, int max_points,
+                             int32_t* h_counts) {
+    LLFE_ENTER(ctx);
+    LLFE_CHECK_ARG(h_bgr != nullptr && h_headers != nullptr && h_counts != nullptr && h > 0 && w > 0 && max_contours > 0 &&
+                   max_points >= 0 && (h_points != nullptr || max_points == 0));
+    const size_t p = (size_t)h * w, ma = WsCarver::need(p), hb = WsCarver::need((size_t)max_contours * 40),
+                 pb = WsCarver::need((size_t)max_points * 8);
+    HostStage st;
+    LLFE_TRY(stage_begin(ctx, h_bgr, 3 * p, ma + hb + pb + 256, &st));
+    uint8_t* d_mask = st.d_out;
+    LLFE_TRY(llfe_shape_mask(ctx, st.d_in, 1, h, w, low, high, d_mask));
+    LLFE_TRY(llfe_contours_external(ctx, d_mask, 1, h, w, min_area2, (int32_t*)(st.d_out + ma), max_contours,
+                                    (int32_t*)(st.d_out + ma + hb), max_points, (int32_t*)(st.d_out + ma + hb + pb)));
+    if (h_mask) LLFE_CUDA(cudaMemcpyAsync(st.p_out, d_mask, p, cudaMemcpyDeviceToHost, ctx->stream));
+    LLFE_TRY(contours_fetch(ctx, &st, ma, ma + hb, ma + hb + pb, max_contours, max_points, h_headers, h_points, h_counts));
+    if (h_mask) memcpy(h_mask, st.p_out, p);
+    return LLFE_OK;
+}
+
 }  // extern "C"
+

@@ -153,6 +153,20 @@ class Engine:
         return out[0] if single and out.dim() == 3 else out
 
     # -- thresholds ---------------------------------------------------------------
+    def contours_external(self, mask: torch.Tensor, min_area2: int = 200, max_contours: int = 4096,
+                          max_points: int = 1 << 16):
+        """cv2.findContours(mask, RETR_EXTERNAL, CHAIN_APPROX_SIMPLE) per image on the device.
+        -> headers (n, max_contours, 10) int32 [contours.HEADER records], points (n, max_points, 2) int32,
+        counts (n, 4) int32; see include/llfe.h for the overflow protocol."""
+        x, single = _batch(mask, None)
+        n, h, w = x.shape
+        hdr = self._empty((n, max_contours, 10), torch.int32)
+        pts = self._empty((n, max(max_points, 1), 2), torch.int32)
+        cnt = self._empty((n, 4), torch.int32)
+        self._bind()
+        self.ctx.call("llfe_contours_external", x, n, h, w, int(min_area2), hdr, max_contours, pts, max_points, cnt)
+        return (hdr[0], pts[0], cnt[0]) if single else (hdr, pts, cnt)
+
     def adaptive_threshold(self, gray: torch.Tensor, c: int = 2, with_sums: bool = False):
         x, single = _batch(gray, None)
         n, h, w = x.shape

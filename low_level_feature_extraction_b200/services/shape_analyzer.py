@@ -2,10 +2,13 @@
 
 Mirrors app/services/__pycache__/shape_analyzer.cpython-312.pyc (source lines
 L5-189): same class, method names, arguments, return shapes and error
-behaviour.  `preprocess_image` (gray -> blur -> Canny -> dilate, src L6-30) runs
-on the GPU through libllfe.so; contour tracing and polygon geometry stay host
-cv2 calls on the returned mask, exactly as in the reference (src L140-181) --
-they are sequential border following on tiny data.
+behaviour.  `preprocess_image` (gray -> blur -> Canny -> dilate, src L6-30) and the
+contour finder (`cv2.findContours(mask, RETR_EXTERNAL, CHAIN_APPROX_SIMPLE)`, src
+L76 / L140; csrc/k_contours.cu) run on the GPU through libllfe.so: for
+`analyze_shapes` / `extract_shapes` the mask never leaves the device, only the
+vertices of the contours that pass the reference's area threshold come back.
+The per-contour polygon geometry (approxPolyDP, convexHull, arcLength; src
+L142-181) stays the reference's own cv2 calls on those few points.
 """
 from __future__ import annotations
 
@@ -15,6 +18,7 @@ import cv2
 import numpy as np
 
 from . import _runtime
+from .. import contours as _contours
 
 
 class ShapeAnalyzer:
@@ -64,14 +68,19 @@ class ShapeAnalyzer:
                 shape_type = "circle" if circularity > 0.8 else "polygon"
         return shape_type
 
+    @staticmethod
+    def _device_contours(image: np.ndarray):
+        """image -> contours with cv2.contourArea >= 100, as cv2.findContours would list them (src L76-78 / L140-142)."""
+        img = _runtime.as_bgr_u8(image)
+        with _runtime.lock():
+            headers, points = _contours.shape_contours_host(_runtime.context(), img, ShapeAnalyzer.CANNY_LOW,
+                                                            ShapeAnalyzer.CANNY_HIGH)
+        return _contours.to_cv2_contours(headers, points)
+
     def extract_shapes(self, image: np.ndarray) -> List[Dict[str, Any]]:
         """src L63-123: [{'type', 'coordinates': [{'x','y'}, ...]}]."""
-        preprocessed = self.preprocess_image(image)
-        contours, _ = cv2.findContours(preprocessed, cv2.RETR_EXTERNAL, cv2.CHAIN_APPROX_SIMPLE)
         shape_results = []
-        for contour in contours:
-            if cv2.contourArea(contour) < 100:
-                continue
+        for contour in self._device_contours(image):
             shape_type = self._classify(contour)
             coordinates = [{"x": int(point[0][0]), "y": int(point[0][1])} for point in contour]
             shape_results.append({"type": shape_type, "coordinates": coordinates})
@@ -80,16 +89,20 @@ class ShapeAnalyzer:
     @staticmethod
     def analyze_shapes(image: np.ndarray) -> Dict[str, Any]:
         """src L125-189: {'shapes': [...], 'total_shapes', 'metadata': {'image_width','image_height'}}."""
-        return ShapeAnalyzer.shapes_from_mask(ShapeAnalyzer.preprocess_image(image), image.shape[1], image.shape[0])
+        return ShapeAnalyzer.shapes_from_contours(ShapeAnalyzer._device_contours(image), image.shape[1], image.shape[0])
 
     @staticmethod
     def shapes_from_mask(preprocessed: np.ndarray, image_width: int, image_height: int) -> Dict[str, Any]:
-        """The host tail of analyze_shapes (src L134-189) on an already computed edge mask."""
-        contours, _ = cv2.findContours(preprocessed, cv2.RETR_EXTERNAL, cv2.CHAIN_APPROX_SIMPLE)
+        """The tail of analyze_shapes (src L134-189) on an already computed edge mask in host memory."""
+        with _runtime.lock():
+            headers, points = _contours.find_external_host(_runtime.context(), preprocessed, _contours.REFERENCE_MIN_AREA2)
+        return ShapeAnalyzer.shapes_from_contours(_contours.to_cv2_contours(headers, points), image_width, image_height)
+
+    @staticmethod
+    def shapes_from_contours(contours, image_width: int, image_height: int) -> Dict[str, Any]:
+        """src L142-189 on the contours that passed `cv2.contourArea(contour) < 100: continue`."""
         shape_results = []
         for contour in contours:
-            if cv2.contourArea(contour) < 100:
-                continue
             x, y, w, h = cv2.boundingRect(contour)
             border_radius = ShapeAnalyzer.detect_border_radius(contour)
             shape_type = ShapeAnalyzer._classify(contour)
