@@ -336,7 +336,7 @@ int llfe_analyze(llfe_ctx* ctx, const uint8_t* d_bgr, int n, int h, int w, int l
  * Replaces the call in ShapeAnalyzer.extract_shapes / analyze_shapes (app/services/__pycache__/shape_analyzer.cpython-312.pyc,
  * source lines 76 and 140) and FontDetector.detect_text_regions (app/services/analyze/font_detector.py:51-55).
  * Any non-zero mask byte is foreground, as in OpenCV.  Per image the call writes
- *   d_counts  (n, 4) int32: {external contours found, points written, 1 if max_points was too small, 0};
+ *   d_counts  (n, 4) int32: {external contours found, points written, 1 if max_points was too small, internal};
  *   d_headers (n, max_contours) records of 40 bytes = int32 {start (y * w + x of the contour's first point), npts, offset
  *             (index of its first point in the image's point array, -1 if its points were not written), min x, min y,
  *             max x, max y, 0} + int64 {2 * signed area (Green's formula: |value| / 2 == cv2.contourArea)};

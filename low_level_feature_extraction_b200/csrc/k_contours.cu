@@ -21,8 +21,9 @@
 //      plane in registers and jumps along axis-aligned straight edges (up to ~60 pixels per iteration: horizontal
 //      edges inside the window, vertical edges through a transposed copy of the plane), which is what UI masks are
 //      made of.  The polygon's doubled area (Green's formula, exact integers == 2 * cv2.contourArea) and bounding box
-//      are accumulated on the way, so contours below the reference's threshold (`if area < 100: continue`) never
-//      get their points written.
+//      are accumulated on the way; the points go through chained scratch blocks (one pass: the point count is only
+//      known at the end) and only contours at or above the reference's threshold (`if area < 100: continue`) are
+//      copied, by the whole warp, into the point array the caller gets.
 #include "llfe_common.cuh"
 #include "llfe_device.cuh"
 
@@ -294,29 +295,54 @@ __device__ __forceinline__ int ct_skip_down(uint64_t side, uint64_t line, int po
     return min(min(zrun - 2, orun), pos - 2);
 }
 
-// WRITE = false: count the points, accumulate area and bounding box; WRITE = true: store the points
-template <bool WRITE>
+// Points leave the follower through chained blocks of a scratch pool (the number of points of a border is only known
+// when the walk is over): 63 points + the index of the next block per 512-byte block.
+constexpr int CT_BLOCK_PTS = 63;
+
+struct CtSink {
+    int2* pool;
+    int* pool_used;
+    int pool_blocks;
+    int first = -1, cur = -1, slot = 0;
+    bool on, failed = false;
+    __device__ __forceinline__ void put(int x, int y) {
+        if (!on || failed) return;
+        if (cur < 0 || slot == CT_BLOCK_PTS) {
+            const int nb = atomicAdd(pool_used, 1);
+            if (nb >= pool_blocks) {
+                failed = true;
+                return;
+            }
+            if (cur >= 0) pool[(size_t)cur * 64 + CT_BLOCK_PTS].x = nb;
+            else first = nb;
+            cur = nb;
+            slot = 0;
+        }
+        pool[(size_t)cur * 64 + slot++] = make_int2(x, y);
+    }
+};
+
+__device__ __forceinline__ void ct_prefetch(const uint32_t* p) { asm volatile("prefetch.global.L1 [%0];" ::"l"(p)); }
+
+// follows the border that starts at (x0, y0): number of CHAIN_APPROX_SIMPLE points; area, bounding box; points -> sink
 __device__ int ct_trace(const uint32_t* __restrict__ P, const uint32_t* __restrict__ T, const CtGeom& g, int x0, int y0,
-                        int2* out, long long& area2, int& minx, int& miny, int& maxx, int& maxy) {
+                        CtSink& sink, long long& area2, int& minx, int& miny, int& maxx, int& maxy) {
     const int pw = g.pw, pwT = g.pwT;
     int n = 0, fx = 0, fy = 0, px = 0, py = 0;
     auto emit = [&](int x, int y) {
-        if (WRITE) {
-            out[n] = make_int2(x, y);
+        sink.put(x, y);
+        if (n == 0) {
+            fx = x;
+            fy = y;
         } else {
-            if (n == 0) {
-                fx = x;
-                fy = y;
-            } else {
-                area2 += (long long)px * y - (long long)py * x;
-            }
-            px = x;
-            py = y;
-            minx = min(minx, x);
-            maxx = max(maxx, x);
-            miny = min(miny, y);
-            maxy = max(maxy, y);
+            area2 += (long long)px * y - (long long)py * x;
         }
+        px = x;
+        py = y;
+        minx = min(minx, x);
+        maxx = max(maxx, x);
+        miny = min(miny, y);
+        maxy = max(maxy, y);
         ++n;
     };
     int X = x0 + 32, Y = y0 + 1;   // padded coordinates
@@ -359,13 +385,17 @@ __device__ int ct_trace(const uint32_t* __restrict__ P, const uint32_t* __restri
         const int X4 = X + ct_dx(sn), Y4 = Y + ct_dy(sn);
         if (X4 == X0 && Y4 == Y0 && X == X1 && Y == Y1) break;
         if (Y4 > Y) {
+            const uint32_t* r2 = P + (size_t)(Y4 + 1) * pw + cq;
             up = mid;
             mid = dn;
-            dn = ct_ld2(P + (size_t)(Y4 + 1) * pw + cq);
+            dn = ct_ld2(r2);
+            ct_prefetch(r2 + 2 * pw);   // borders are locally coherent: the rows ahead will be wanted next
         } else if (Y4 < Y) {
+            const uint32_t* r2 = P + (size_t)(Y4 - 1) * pw + cq;
             dn = mid;
             mid = up;
-            up = ct_ld2(P + (size_t)(Y4 - 1) * pw + cq);
+            up = ct_ld2(r2);
+            if (Y4 >= 3) ct_prefetch(r2 - 2 * pw);
         }
         X = X4;
         Y = Y4;
@@ -402,60 +432,92 @@ __device__ int ct_trace(const uint32_t* __restrict__ P, const uint32_t* __restri
         }
         nb = neighbours();
     }
-    if (!WRITE) area2 += (long long)px * fy - (long long)py * fx;   // last -> first closes Green's sum
+    area2 += (long long)px * fy - (long long)py * fx;   // last -> first closes Green's sum
     return n;
 }
 
-// one warp slot per contour (lane 0 follows the border: the walk is sequential and latency-bound, a converged warp
-// keeps other contours from serialising behind it)
+// One warp per contour.  Lane 0 follows the border (the walk is sequential and latency-bound; a converged warp keeps
+// other contours from serialising behind it) and leaves the points in chained scratch blocks; then the whole warp
+// copies the points of a contour that passed the area threshold to its final place in the image's point array.
 __global__ void __launch_bounds__(128) k_ct_trace(const uint32_t* __restrict__ plane, const uint32_t* __restrict__ planeT,
                                                   CtGeom g, CtHeader* hdr, int max_contours, long long min_area2, int2* points,
-                                                  int max_points, int32_t* counts) {
-    if (threadIdx.x & 31) return;
+                                                  int max_points, int2* pool, int pool_blocks, int32_t* counts) {
+    const int lane = threadIdx.x & 31;
     const int i = blockIdx.x * 4 + (threadIdx.x >> 5);
     int32_t* cnt = counts + blockIdx.z * 4;
     const int n_starts = min(cnt[0], max_contours);
     if (i >= n_starts) return;
-    CtHeader* hd = hdr + (size_t)blockIdx.z * max_contours + i;
-    const uint32_t* P = plane + blockIdx.z * g.plane_words;
-    const uint32_t* T = planeT + blockIdx.z * g.planeT_words;
-    const int p = hd->start, y0 = p / g.w, x0 = p - y0 * g.w;
-    long long area2 = 0;
-    int minx = x0, miny = y0, maxx = x0, maxy = y0;
-    const int n = ct_trace<false>(P, T, g, x0, y0, nullptr, area2, minx, miny, maxx, maxy);
-    CtHeader H;
-    H.start = p;
-    H.npts = n;
-    H.offset = -1;
-    H.minx = minx;
-    H.miny = miny;
-    H.maxx = maxx;
-    H.maxy = maxy;
-    H.pad = 0;
-    H.area2 = area2;
-    const long long a = area2 < 0 ? -area2 : area2;
-    if (a >= min_area2 && max_points > 0) {
-        const int off = atomicAdd(&cnt[1], n);
-        if (off + n <= max_points) {
-            H.offset = off;
-            ct_trace<true>(P, T, g, x0, y0, points + (size_t)blockIdx.z * max_points + off, area2, minx, miny, maxx, maxy);
-        } else {
-            atomicOr(&cnt[2], 1);   // point capacity exceeded: the caller retries with a larger buffer
+    int n = 0, first = -1, off = -1;
+    if (lane == 0) {
+        CtHeader* hd = hdr + (size_t)blockIdx.z * max_contours + i;
+        const uint32_t* P = plane + blockIdx.z * g.plane_words;
+        const uint32_t* T = planeT + blockIdx.z * g.planeT_words;
+        const int p = hd->start, y0 = p / g.w, x0 = p - y0 * g.w;
+        long long area2 = 0;
+        int minx = x0, miny = y0, maxx = x0, maxy = y0;
+        CtSink sink;
+        sink.pool = pool + (size_t)blockIdx.z * pool_blocks * 64;
+        sink.pool_used = &cnt[3];
+        sink.pool_blocks = pool_blocks;
+        sink.on = max_points > 0;
+        n = ct_trace(P, T, g, x0, y0, sink, area2, minx, miny, maxx, maxy);
+        CtHeader H;
+        H.start = p;
+        H.npts = n;
+        H.offset = -1;
+        H.minx = minx;
+        H.miny = miny;
+        H.maxx = maxx;
+        H.maxy = maxy;
+        H.pad = 0;
+        H.area2 = area2;
+        const long long a = area2 < 0 ? -area2 : area2;
+        if (a >= min_area2 && max_points > 0) {
+            if (sink.failed) {
+                atomicOr(&cnt[2], 1);   // scratch pool exhausted: the caller retries with larger buffers
+            } else {
+                off = atomicAdd(&cnt[1], n);
+                if (off + n <= max_points) {
+                    H.offset = off;
+                    first = sink.first;
+                } else {
+                    atomicOr(&cnt[2], 1);   // point capacity exceeded
+                    off = -1;
+                }
+            }
         }
+        *hd = H;
     }
-    *hd = H;
+    __syncwarp();
+    first = __shfl_sync(FULL, first, 0);
+    if (first < 0) return;
+    n = __shfl_sync(FULL, n, 0);
+    off = __shfl_sync(FULL, off, 0);
+    const int2* pl = pool + (size_t)blockIdx.z * pool_blocks * 64;
+    int2* out = points + (size_t)blockIdx.z * max_points + off;
+    int blk = first;
+    for (int done = 0; done < n; done += CT_BLOCK_PTS) {
+        const int2* src = pl + (size_t)blk * 64;
+        const int m = min(CT_BLOCK_PTS, n - done);
+        for (int t = lane; t < m; t += 32) out[done + t] = src[t];
+        blk = src[CT_BLOCK_PTS].x;
+    }
 }
 
 }  // namespace
 
-size_t contours_ws_bytes(int n, int h, int w) {
+static int ct_pool_blocks(int max_contours, int max_points) {
+    return max_points > 0 ? max_contours + 2 * ceil_div(max_points, CT_BLOCK_PTS) : 0;
+}
+
+size_t contours_ws_bytes(int n, int h, int w, int max_contours, int max_points) {
     const CtGeom g = ct_geom(h, w);
     return WsCarver::need(n * (g.plane_words + g.planeT_words) * 4) + 2 * WsCarver::need(n * g.sin_words * 4) +
-           WsCarver::need(n * g.label_words * 4);
+           WsCarver::need(n * g.label_words * 4) + WsCarver::need((size_t)n * ct_pool_blocks(max_contours, max_points) * 512);
 }
 
 // d_mask (n, h, w) u8 -> per image: headers (max_contours x 10 int32, see CtHeader), points (max_points x 2 int32),
-// counts {external components found, points written, point-capacity flag, -}
+// counts {external components found, points written, capacity flag, scratch blocks used}
 extern "C" int llfe_contours_external(llfe_ctx* ctx, const uint8_t* d_mask, int n, int h, int w, int64_t min_area2,
                                       int32_t* d_headers, int max_contours, int32_t* d_points, int max_points,
                                       int32_t* d_counts) {
@@ -465,13 +527,15 @@ extern "C" int llfe_contours_external(llfe_ctx* ctx, const uint8_t* d_mask, int 
     static_assert(sizeof(CtHeader) == 40, "header layout is part of the ABI");
     const CtGeom g = ct_geom(h, w);
     void* ws;
-    LLFE_TRY(llfe_workspace(ctx, contours_ws_bytes(n, h, w), &ws));
+    LLFE_TRY(llfe_workspace(ctx, contours_ws_bytes(n, h, w, max_contours, max_points), &ws));
     WsCarver carve(ws);
     uint32_t* plane = carve.take<uint32_t>(n * (g.plane_words + g.planeT_words));
     uint32_t* planeT = plane + n * g.plane_words;
     int* sinF = carve.take<int>(n * g.sin_words);
     int* sinB = carve.take<int>(n * g.sin_words);
     int* labels = carve.take<int>(n * g.label_words);
+    const int pool_blocks = ct_pool_blocks(max_contours, max_points);
+    int2* pool = carve.take<int2>((size_t)n * pool_blocks * 64);
     LLFE_CUDA(cudaMemsetAsync(plane, 0, n * (g.plane_words + g.planeT_words) * 4, ctx->stream));
     LLFE_CUDA(cudaMemsetAsync(d_counts, 0, (size_t)n * 4 * sizeof(int32_t), ctx->stream));
     LLFE_KERNEL(ctx, "k_ct_plane");
@@ -494,7 +558,8 @@ extern "C" int llfe_contours_external(llfe_ctx* ctx, const uint8_t* d_mask, int 
     LLFE_KERNEL(ctx, "k_ct_trace");
     k_ct_trace<<<dim3(ceil_div(max_contours, 4), 1, n), 128, 0, ctx->stream>>>(plane, planeT, g, (CtHeader*)d_headers,
                                                                               max_contours, (long long)min_area2,
-                                                                              (int2*)d_points, max_points, d_counts);
+                                                                              (int2*)d_points, max_points, pool, pool_blocks,
+                                                                              d_counts);
     LLFE_LAUNCHED(ctx);
     return LLFE_OK;
 }
