@@ -43,6 +43,12 @@ class BatchConfig:
     packed_masks: bool = True
     expand_threads: int = 4    # host threads per expansion call
     expand_workers: int = 3    # stages being expanded at the same time
+    # external contours of the shape mask on the device (cv2.findContours(EXTERNAL, SIMPLE) + the reference's
+    # `contourArea < 100` filter): per image `max_contours` header records and `max_points` vertices; an image that
+    # needs more reports it in contour_counts (column 0 > max_contours or column 2 != 0) and the caller redoes it alone
+    contours: bool = False
+    max_contours: int = 1024
+    max_points: int = 8192
 
 
 class BatchAnalyzer:
@@ -62,6 +68,10 @@ class BatchAnalyzer:
         out = {}
         if c.shapes:
             out["shape_mask"] = torch.empty((n, self.h, self.w), dtype=torch.uint8, device=d)
+        if c.shapes and c.contours:
+            out["contour_headers"] = torch.empty((n, c.max_contours, 10), dtype=torch.int32, device=d)
+            out["contour_points"] = torch.empty((n, c.max_points, 2), dtype=torch.int32, device=d)
+            out["contour_counts"] = torch.empty((n, 4), dtype=torch.int32, device=d)
         if c.shadows:
             out["shadow_mask"] = torch.empty((n, self.h, self.w), dtype=torch.uint8, device=d)
             out["shadow_sums"] = torch.empty((n, 2), dtype=torch.int64, device=d)
@@ -102,6 +112,11 @@ class BatchAnalyzer:
                              view["status"])
             else:
                 eng.pipeline(bgr[sl], shapes=c.shapes, shadows=c.shadows, colors=False, low=c.low, high=c.high, out=view)
+            if c.shapes and c.contours:
+                eng._bind()
+                eng.ctx.call("llfe_contours_external", view["shape_mask"], sl.stop - sl.start, self.h, self.w, 200,
+                             view["contour_headers"], c.max_contours, view["contour_points"], c.max_points,
+                             view["contour_counts"])
         if c.colors and resolve:
             self.resolve_overflow(bgr, out, eng, noise)
         return out
@@ -134,6 +149,10 @@ class BatchAnalyzer:
         out = {}
         if c.shapes:
             out["shape_mask"] = torch.empty((n, self.h, self.w), dtype=torch.uint8).pin_memory()
+        if c.shapes and c.contours:
+            out["contour_headers"] = torch.empty((n, c.max_contours, 10), dtype=torch.int32).pin_memory()
+            out["contour_points"] = torch.empty((n, c.max_points, 2), dtype=torch.int32).pin_memory()
+            out["contour_counts"] = torch.empty((n, 4), dtype=torch.int32).pin_memory()
         if c.shadows:
             out["shadow_mask"] = torch.empty((n, self.h, self.w), dtype=torch.uint8).pin_memory()
             out["shadow_sums"] = torch.empty((n, 2), dtype=torch.int64).pin_memory()
@@ -144,6 +163,17 @@ class BatchAnalyzer:
             out["cluster_sizes"] = torch.empty((n, c.k), dtype=torch.int32).pin_memory()
             out["status"] = torch.empty((n,), dtype=torch.int32).pin_memory()
         return out
+
+    def contours(self, host_out: dict, i: int):
+        """cv2-ordered contours (area >= 100) of image i of a `run_host` result, or None when the image needs more
+        than max_contours / max_points (the caller then takes the single-image path)."""
+        from . import contours as ct
+
+        cnt = host_out["contour_counts"][i].numpy()
+        if cnt[0] > self.cfg.max_contours or cnt[2]:
+            return None
+        headers = host_out["contour_headers"][i, :int(cnt[0])].numpy().view(ct.HEADER).reshape(-1)
+        return ct.to_cv2_contours(headers, host_out["contour_points"][i].numpy())
 
     def palettes(self, host_out: dict) -> list:
         """The reference's palette tail (color_extractor.py:231-284: bincount order, hex, white / black filter, primary /
@@ -231,7 +261,8 @@ class BatchAnalyzer:
                 bytes_in += din.numel()
                 dout = {k: v[:m] for k, v in self._dev_out[b].items()}
                 self.run_device(din, dout, engine=self.engines[b], resolve=False)
-                small = ["shadow_sums", "centers", "count", "k_used", "cluster_sizes", "status"]
+                small = ["shadow_sums", "centers", "count", "k_used", "cluster_sizes", "status",
+                         "contour_headers", "contour_points", "contour_counts"]
                 if packed:
                     eng = self.engines[b]
                     for q, key in enumerate(mask_keys):

@@ -516,18 +516,9 @@ size_t contours_ws_bytes(int n, int h, int w, int max_contours, int max_points) 
            WsCarver::need(n * g.label_words * 4) + WsCarver::need((size_t)n * ct_pool_blocks(max_contours, max_points) * 512);
 }
 
-// d_mask (n, h, w) u8 -> per image: headers (max_contours x 10 int32, see CtHeader), points (max_points x 2 int32),
-// counts {external components found, points written, capacity flag, scratch blocks used}
-extern "C" int llfe_contours_external(llfe_ctx* ctx, const uint8_t* d_mask, int n, int h, int w, int64_t min_area2,
-                                      int32_t* d_headers, int max_contours, int32_t* d_points, int max_points,
-                                      int32_t* d_counts) {
-    LLFE_ENTER(ctx);
-    LLFE_CHECK_ARG(d_mask != nullptr && d_headers != nullptr && d_counts != nullptr && (d_points != nullptr || max_points == 0));
-    LLFE_CHECK_ARG(n > 0 && n <= 65535 && h > 0 && w > 0 && (size_t)h * w < 0x7ffffff0ull && max_contours > 0 && max_points >= 0);
-    static_assert(sizeof(CtHeader) == 40, "header layout is part of the ABI");
+static int contours_chunk(llfe_ctx* ctx, const uint8_t* d_mask, int n, int h, int w, int64_t min_area2, int32_t* d_headers,
+                          int max_contours, int32_t* d_points, int max_points, int32_t* d_counts, void* ws) {
     const CtGeom g = ct_geom(h, w);
-    void* ws;
-    LLFE_TRY(llfe_workspace(ctx, contours_ws_bytes(n, h, w, max_contours, max_points), &ws));
     WsCarver carve(ws);
     uint32_t* plane = carve.take<uint32_t>(n * (g.plane_words + g.planeT_words));
     uint32_t* planeT = plane + n * g.plane_words;
@@ -561,5 +552,26 @@ extern "C" int llfe_contours_external(llfe_ctx* ctx, const uint8_t* d_mask, int 
                                                                               (int2*)d_points, max_points, pool, pool_blocks,
                                                                               d_counts);
     LLFE_LAUNCHED(ctx);
+    return LLFE_OK;
+}
+
+// d_mask (n, h, w) u8 -> per image: headers (max_contours x 10 int32, see CtHeader), points (max_points x 2 int32),
+// counts {external components found, points written, capacity flag, scratch blocks used}
+extern "C" int llfe_contours_external(llfe_ctx* ctx, const uint8_t* d_mask, int n, int h, int w, int64_t min_area2,
+                                      int32_t* d_headers, int max_contours, int32_t* d_points, int max_points,
+                                      int32_t* d_counts) {
+    LLFE_ENTER(ctx);
+    LLFE_CHECK_ARG(d_mask != nullptr && d_headers != nullptr && d_counts != nullptr && (d_points != nullptr || max_points == 0));
+    LLFE_CHECK_ARG(n > 0 && h > 0 && w > 0 && (size_t)h * w < 0x7ffffff0ull && max_contours > 0 && max_points >= 0);
+    static_assert(sizeof(CtHeader) == 40, "header layout is part of the ABI");
+    const int chunk = n < 32 ? n : 32;   // images per pass: the union-find nodes take 4 bytes per pixel
+    void* ws;
+    LLFE_TRY(llfe_workspace(ctx, contours_ws_bytes(chunk, h, w, max_contours, max_points), &ws));
+    for (int i0 = 0; i0 < n; i0 += chunk) {
+        const int m = n - i0 < chunk ? n - i0 : chunk;
+        LLFE_TRY(contours_chunk(ctx, d_mask + (size_t)i0 * h * w, m, h, w, min_area2, d_headers + (size_t)i0 * max_contours * 10,
+                                max_contours, d_points ? d_points + (size_t)i0 * max_points * 2 : nullptr, max_points,
+                                d_counts + (size_t)i0 * 4, ws));
+    }
     return LLFE_OK;
 }

@@ -91,7 +91,8 @@ class RequestBatcher:
     def _default_factory(self, h: int, w: int):
         from ..batch import BatchAnalyzer, BatchConfig
 
-        return BatchAnalyzer(self.device, h, w, BatchConfig(k=self.n_colors, host_chunk=min(16, self.max_batch)))
+        return BatchAnalyzer(self.device, h, w, BatchConfig(k=self.n_colors, host_chunk=min(16, self.max_batch),
+                                                            contours=self.shapes))
 
     def _loop(self) -> None:
         stop = False
@@ -164,8 +165,13 @@ class RequestBatcher:
                         c8 = centers[i, :k].astype(np.uint8)                  # color_extractor.py:197 truncation
                         colors = ColorExtractor._palette_from_clusters(c8, sizes[i, :k].astype(np.int64) if k > 1 else None)
                     shape_mask = shape_masks[i].copy()
+                    shapes = None
+                    if self.shapes:
+                        conts = an.contours(out, i) if "contour_counts" in out else None
+                        shapes = (ShapeAnalyzer.shapes_from_contours(conts, w, h) if conts is not None
+                                  else ShapeAnalyzer.shapes_from_mask(shape_mask, w, h))
                     res = {"colors": colors,
-                           "shapes": ShapeAnalyzer.shapes_from_mask(shape_mask, w, h) if self.shapes else None,
+                           "shapes": shapes,
                            "shadow_level": ShadowAnalyzer.level_from_sums(int(sums[i, 0]), int(sums[i, 1])),
                            "shape_mask": shape_mask,
                            "shadow_mask": shadow_masks[i].copy()}

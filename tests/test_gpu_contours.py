@@ -147,3 +147,25 @@ def test_services_use_device_contours(monkeypatch):
     assert ShapeAnalyzer.shapes_from_mask(refpath.shape_mask(img), img.shape[1], img.shape[0]) == want
     assert FontDetector.detect_text_regions(FontDetector.preprocess_image(img)) == regions_want
     assert len(regions_want) > 0
+
+
+def test_batch_analyzer_contours_and_overflow_fallback():
+    from low_level_feature_extraction_b200.batch import BatchAnalyzer, BatchConfig
+
+    imgs = np.stack([design_image(270, 480, s) for s in range(5)] + [noise_image(270, 480, 9)])
+    pinned = torch.from_numpy(imgs).pin_memory()
+    an = BatchAnalyzer(0, 270, 480, BatchConfig(colors=False, shadows=False, contours=True, max_contours=2, max_points=4096,
+                                                host_chunk=4))
+    out = an.run_host(pinned)
+    seen = set()
+    for i in range(len(imgs)):
+        mask = out["shape_mask"][i].numpy()
+        assert np.array_equal(mask, refpath.shape_mask(imgs[i]))
+        want = [c for c in cv_all(mask) if cv2.contourArea(c) >= 100]
+        got = an.contours(out, i)
+        seen.add(len(cv_all(mask)) > 2)
+        if len(cv_all(mask)) > 2:
+            assert got is None                                   # the caller redoes this image alone
+        else:
+            assert len(got) == len(want) and all(np.array_equal(a, b) for a, b in zip(got, want))
+    assert seen == {True, False}
