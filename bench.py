@@ -450,7 +450,21 @@ def pixel_kmeans_record(rank, world, local, dev, height, width, k, synth="design
     e1.record()
     torch.cuda.synchronize()
     fit_ms = e0.elapsed_time(e1) / reps
-    # the all-reduce of the K x 4 sums alone (what every iteration pays on top of its kernels)
+    # the same fit with ncclAllReduce + update per iteration instead of the fused NVLink exchange (for comparison)
+    fit_nccl_ms = None
+    if world > 1:
+        km2 = PixelKMeans(eng, p2p=False)
+        km2.fit(rows, init, index_base=r0 * width)
+        torch.cuda.synchronize()
+        dist.barrier()
+        e0.record()
+        for _ in range(reps):
+            res2 = km2.fit(rows, init, index_base=r0 * width)
+        e1.record()
+        torch.cuda.synchronize()
+        fit_nccl_ms = e0.elapsed_time(e1) / reps
+        assert torch.equal(res2.centers, res.centers) and res2.iters == res.iters
+    # the all-reduce of the K x 4 sums alone (what every iteration would pay on top of its kernels with NCCL)
     sums = torch.zeros((k, 4), dtype=torch.int64, device=dev)
     a0, a1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     for _ in range(3):
@@ -462,16 +476,21 @@ def pixel_kmeans_record(rank, world, local, dev, height, width, k, synth="design
     torch.cuda.synchronize()
     ar_ms = a0.elapsed_time(a1) / 20 if world > 1 else 0.0
     if world > 1:
-        t = torch.tensor([fit_ms, ar_ms], dtype=torch.float64, device=dev)
+        t = torch.tensor([fit_ms, ar_ms, fit_nccl_ms], dtype=torch.float64, device=dev)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        fit_ms, ar_ms = t.tolist()
+        fit_ms, ar_ms, fit_nccl_ms = t.tolist()
     peak, _ = measured_peak()
     npix = height * width
     rec = {"workload": f"per-pixel k-means of ONE {width}x{height} image ({synth}-like synthetic rows), K={k}, rows sharded over "
                        f"{world} GPU(s); colour-histogram form (rows read once, Lloyd over the distinct colours)",
            "scaling": "strong", "n_gpus": world, "iterations": res.iters, "fit_ms": fit_ms, "value": 1e3 / fit_ms,
            "unit": "fits/sec", "iterations_per_sec": res.iters / (fit_ms / 1e3),
-           "allreduce_ms_per_iteration": ar_ms, "allreduce_share_of_fit": ar_ms * res.iters / fit_ms,
+           "sums_exchange": ("fused: one kernel per rank stores the K x 4 u64 partial sums into every peer's mailbox over NVLink "
+                             "(CUDA IPC), waits for the peers' flags, adds them and updates the centres "
+                             "(llfe_kmeans_update_p2p)") if world > 1 else "none (1 GPU)",
+           "fit_ms_with_nccl_allreduce": fit_nccl_ms,
+           "nccl_allreduce_ms_per_iteration": ar_ms,
+           "exchange_saving_per_iteration_ms": ((fit_nccl_ms - fit_ms) / max(1, res.iters)) if fit_nccl_ms else 0.0,
            "table_exchange": "reduce-scatter of the block-transposed 64 MiB colour table (each rank receives its 1/G)"
                              if world > 1 else "none (1 GPU)",
            "roofline_fit": {"bound": "hbm", "algorithmic_bytes": 3 * npix, "achieved": 3 * npix / (fit_ms / 1e3) / 1e9 / 1.0,

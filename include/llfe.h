@@ -272,6 +272,23 @@ int llfe_kmeans_hist_farthest(llfe_ctx* ctx, const uint32_t* d_keys, size_t n, i
 int llfe_kmeans_update(llfe_ctx* ctx, int k, uint64_t* d_sums_counts, float* d_centers, int max_iter, double eps,
                        int32_t* d_state, double* d_shift, uint64_t* d_consumed_or_null, int zero_sums);
 
+/* ---- fused all-reduce + centre update over peer memory (config 5 on N > 1 GPUs of one node) --------------------------
+ * Replaces the pair {ncclAllReduce of the k x 4 sums, llfe_kmeans_update} of the per-iteration loop ("per
+ * iteration each rank produces K x 3 channel sums + K counts as uint64 => all-reduce, then every rank recomputes identical
+ * centres") by ONE kernel per rank that exchanges the partial sums through NVLink peer stores.  Set-up, once per process
+ * group: every rank allocates a mailbox of llfe_p2p_mailbox_bytes() with llfe_malloc, zeroes it, exports it
+ * (llfe_ipc_export -> 64 opaque bytes, the cudaIpcMemHandle), exchanges the handles out of band, opens the peers'
+ * (llfe_ipc_open) and keeps the `world` device pointers (its own at index `rank`) in a device array; a barrier before the
+ * first use.  Every rank then calls llfe_kmeans_update_p2p the same number of times: d_partial_sums (this rank's k x 4
+ * accumulator) is consumed and cleared, d_totals receives the global sums, centres / state / shift behave exactly as in
+ * llfe_kmeans_update (a converged or frozen state makes the call a no-op on every rank alike). */
+size_t llfe_p2p_mailbox_bytes(void);
+int llfe_ipc_export(llfe_ctx* ctx, void* d_ptr, uint8_t* handle64);
+int llfe_ipc_open(llfe_ctx* ctx, const uint8_t* handle64, void** d_peer_out);
+int llfe_ipc_close(llfe_ctx* ctx, void* d_peer);
+int llfe_kmeans_update_p2p(llfe_ctx* ctx, int k, uint64_t* d_partial_sums, void* const* d_mailboxes, int rank, int world,
+                           float* d_centers, int max_iter, double eps, int32_t* d_state, double* d_shift, uint64_t* d_totals);
+
 /* ---- colour-histogram form of the per-pixel k-means (BASELINE config 5) ------
  * A u8 image has at most 2^24 distinct colours and the centre update needs only exact
  * integer sums, so the rows are streamed ONCE into a count table and the Lloyd iterations
@@ -303,6 +320,15 @@ int llfe_kmeans_hist_step(llfe_ctx* ctx, const uint32_t* d_keys, const uint32_t*
                           const float* d_centers, uint64_t* d_sums_counts, uint8_t* d_labels_or_null,
                           const int32_t* d_state_or_null, const int32_t* d_n_or_null);
 
+/* The whole per-iteration loop {llfe_kmeans_hist_step, exchange of the sums, llfe_kmeans_update} as ONE persistent
+ * cooperative kernel per rank: up to `iterations` Lloyd iterations over this rank's (key, count) entries, with the sums
+ * exchanged through the peers' mailboxes (d_mailboxes as for llfe_kmeans_update_p2p; NULL with world = 1) and the centres,
+ * state, shift and totals updated as by llfe_kmeans_update.  The kernel stops early when the state says converged or
+ * frozen (the host repairs an empty cluster and calls again).  Every rank calls it with the same `iterations`. */
+int llfe_kmeans_hist_lloyd(llfe_ctx* ctx, const uint32_t* d_keys, const uint32_t* d_counts, size_t n, const int32_t* d_n_or_null,
+                           int k, float* d_centers, uint64_t* d_partial_sums, uint8_t* d_labels_or_null,
+                           void* const* d_mailboxes_or_null, int rank, int world, int max_iter, double eps, int32_t* d_state,
+                           double* d_shift, uint64_t* d_totals, int iterations);
 /* d_lut[key] = label for every entry (d_lut: 2^24 bytes, zeroed by the caller; ranks
  * all-reduce it with ncclSum since every colour belongs to exactly one part). */
 int llfe_hist_labels_to_lut(llfe_ctx* ctx, const uint32_t* d_keys, const uint8_t* d_labels, size_t n, uint8_t* d_lut);

@@ -72,9 +72,15 @@ PROTOTYPES = {
     "llfe_kmeans_pixels_farthest": (i32, [vp, vp, sz, i32, vp, i32, vp, C.c_uint32, vp, i32, C.c_uint32, vp]),
     "llfe_kmeans_hist_farthest": (i32, [vp, vp, sz, i32, vp, i32, vp, vp]),
     "llfe_kmeans_update": (i32, [vp, i32, vp, vp, i32, f64, vp, vp, vp, i32]),
+    "llfe_p2p_mailbox_bytes": (sz, []),
+    "llfe_ipc_export": (i32, [vp, vp, vp]),
+    "llfe_ipc_open": (i32, [vp, vp, C.POINTER(vp)]),
+    "llfe_ipc_close": (i32, [vp, vp]),
+    "llfe_kmeans_update_p2p": (i32, [vp, i32, vp, vp, i32, i32, vp, i32, f64, vp, vp, vp]),
     "llfe_pixels_histogram": (i32, [vp, vp, sz, vp]),
     "llfe_histogram_compact": (i32, [vp, vp, i32, i32, vp, vp, sz, vp, i32]),
     "llfe_kmeans_hist_step": (i32, [vp, vp, vp, sz, i32, vp, vp, vp, vp, vp]),
+    "llfe_kmeans_hist_lloyd": (i32, [vp, vp, vp, sz, vp, i32, vp, vp, vp, vp, i32, i32, i32, f64, vp, vp, vp, i32]),
     "llfe_hist_labels_to_lut": (i32, [vp, vp, vp, sz, vp]),
     "llfe_pixels_lookup": (i32, [vp, vp, sz, vp, vp]),
     "llfe_contours_external": (i32, [vp, vp, i32, i32, i32, C.c_int64, vp, i32, vp, i32, vp]),

@@ -15,6 +15,10 @@
 #include "llfe_common.cuh"
 #include "llfe_device.cuh"
 #include "k_kmeans_shared.cuh"
+#include "k_kmeans_p2p.cuh"
+
+#include <cooperative_groups.h>
+namespace cg = cooperative_groups;
 
 namespace {
 
@@ -209,22 +213,14 @@ constexpr int EPS_T = 4;   // entries per thread per trip of k_hist_step (two f3
 // one Lloyd assignment over (key, count) entries: cv2's float32 distance and first-minimum rule per
 // distinct colour (on PAIRS of colours with packed f32x2 arithmetic, x + (-c) == x - c exactly), exact u64
 // sums weighted by the pixel counts
-__global__ void __launch_bounds__(HT) k_hist_step(const uint32_t* __restrict__ keys,
-                                                  const uint32_t* __restrict__ counts, size_t n, int K,
-                                                  const float* __restrict__ centers, u64* sums,
-                                                  uint8_t* __restrict__ labels_out,
-                                                  const int32_t* __restrict__ state, const int32_t* __restrict__ n_dev) {
-    if (state && (state[1] | state[3])) return;
-    if (n_dev) {   // the list length lives on the device (no host round trip after the compaction)
-        const size_t nd = (size_t)max(*n_dev, 0);
-        n = nd < n ? nd : n;
-        if ((size_t)blockIdx.x * (HT * EPS_T) >= n) return;
-    }
-    __shared__ u64 s_nc[KMAX][3];   // (-c, -c)
-    __shared__ u64 s_acc[HT / 32][KMAX][4];
+// The body of one assignment, called by every thread of a block of HT threads; centres are read through L2 (the
+// persistent kernel below rewrites them between its iterations).
+__device__ __forceinline__ void hist_step_body(const uint32_t* __restrict__ keys, const uint32_t* __restrict__ counts, size_t n,
+                                               int K, const float* centers, u64* sums, uint8_t* __restrict__ labels_out,
+                                               u64 (*s_nc)[3], u64 (*s_acc)[KMAX][4]) {
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     for (int i = tid; i < K * 3; i += HT) {
-        const float c = centers[i];
+        const float c = __ldcg(&centers[i]);
         (&s_nc[0][0])[i] = pack2(-c, -c);
     }
     for (int i = tid; i < (HT / 32) * KMAX * 4; i += HT) (&s_acc[0][0][0])[i] = 0ull;
@@ -300,6 +296,55 @@ __global__ void __launch_bounds__(HT) k_hist_step(const uint32_t* __restrict__ k
         u64 t = 0;
         for (int w = 0; w < HT / 32; ++w) t += s_acc[w][i >> 2][i & 3];
         if (t) atomicAdd(&sums[i], t);
+    }
+}
+
+__global__ void __launch_bounds__(HT) k_hist_step(const uint32_t* __restrict__ keys,
+                                                  const uint32_t* __restrict__ counts, size_t n, int K,
+                                                  const float* __restrict__ centers, u64* sums,
+                                                  uint8_t* __restrict__ labels_out,
+                                                  const int32_t* __restrict__ state, const int32_t* __restrict__ n_dev) {
+    if (state && (state[1] | state[3])) return;
+    if (n_dev) {   // the list length lives on the device (no host round trip after the compaction)
+        const size_t nd = (size_t)max(*n_dev, 0);
+        n = nd < n ? nd : n;
+        if ((size_t)blockIdx.x * (HT * EPS_T) >= n) return;
+    }
+    __shared__ u64 s_nc[KMAX][3];   // (-c, -c)
+    __shared__ u64 s_acc[HT / 32][KMAX][4];
+    hist_step_body(keys, counts, n, K, centers, sums, labels_out, s_nc, s_acc);
+}
+
+// The whole Lloyd loop of the colour-histogram form as ONE persistent cooperative kernel per rank: assignment over this
+// rank's (key, count) entries by every CTA, grid barrier, exchange of the K x 4 partial sums with the other ranks through
+// their NVLink mailboxes + centre update by CTA 0 (k_kmeans_p2p.cuh), grid barrier, next iteration -- until the state says
+// converged (every rank sees the same state) or frozen (empty cluster: the host repairs and launches again) or `iters`
+// iterations have run.  No launch, no host look and no NCCL call between iterations; the entries (a few thousand for a
+// design, <= 2^24) and the centres stay in L2.
+__global__ void __launch_bounds__(HT) k_hist_lloyd(const uint32_t* __restrict__ keys, const uint32_t* __restrict__ counts,
+                                                   size_t n, const int32_t* __restrict__ n_dev, int K, float* centers,
+                                                   u64* partial, uint8_t* __restrict__ labels_out, P2PMailbox* const* peers,
+                                                   int rank, int world, int max_iter, double eps2, int32_t* state,
+                                                   double* shift_out, u64* totals, int iters) {
+    cg::grid_group grid = cg::this_grid();
+    __shared__ u64 s_nc[KMAX][3];
+    __shared__ u64 s_acc[HT / 32][KMAX][4];
+    __shared__ u64 s_tot[KMAX * 4];
+    if (n_dev) {
+        const size_t nd = (size_t)max(*n_dev, 0);
+        n = nd < n ? nd : n;
+    }
+    for (int it = 0; it < iters; ++it) {
+        const volatile int32_t* vs = state;
+        if (vs[1] | vs[3]) break;                 // grid-uniform: written before the last grid barrier
+        if ((size_t)blockIdx.x * (HT * EPS_T) < n)
+            hist_step_body(keys, counts, n, K, centers, partial, labels_out, s_nc, s_acc);
+        __threadfence();
+        grid.sync();
+        if (blockIdx.x == 0)
+            p2p_exchange_and_update(K, partial, peers, rank, world, centers, max_iter, eps2, state, shift_out, totals, s_tot);
+        __threadfence();
+        grid.sync();
     }
 }
 
@@ -498,6 +543,34 @@ extern "C" int llfe_kmeans_hist_step(llfe_ctx* ctx, const uint32_t* d_keys, cons
     LLFE_KERNEL(ctx, "k_hist_step");
     k_hist_step<<<(unsigned)(want > cap ? cap : want), HT, 0, ctx->stream>>>(
         d_keys, d_counts, n, k, d_centers, (u64*)d_sums_counts, d_labels_or_null, d_state_or_null, d_n_or_null);
+    LLFE_LAUNCHED(ctx);
+    return LLFE_OK;
+}
+
+extern "C" int llfe_kmeans_hist_lloyd(llfe_ctx* ctx, const uint32_t* d_keys, const uint32_t* d_counts, size_t n,
+                                      const int32_t* d_n_or_null, int k, float* d_centers, uint64_t* d_partial_sums,
+                                      uint8_t* d_labels_or_null, void* const* d_mailboxes_or_null, int rank, int world,
+                                      int max_iter, double eps, int32_t* d_state, double* d_shift, uint64_t* d_totals,
+                                      int iterations) {
+    LLFE_ENTER(ctx);
+    LLFE_CHECK_ARG(d_centers != nullptr && d_partial_sums != nullptr && d_state != nullptr && d_totals != nullptr &&
+                   d_totals != d_partial_sums && k >= 1 && k <= KMAX && max_iter >= 1 && iterations >= 1);
+    LLFE_CHECK_ARG(n == 0 || (d_keys != nullptr && d_counts != nullptr));
+    LLFE_CHECK_ARG(world >= 1 && world <= P2P_MAXW && rank >= 0 && rank < world && (world == 1 || d_mailboxes_or_null != nullptr));
+    int per_sm = 0;
+    LLFE_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_hist_lloyd, HT, 0));
+    LLFE_CHECK_ARG(per_sm >= 1);
+    const size_t want = n ? ceil_div_sz(n, HT * EPS_T) : 1;
+    const size_t cap = (size_t)ctx->sm_count * (per_sm < 4 ? per_sm : 4);
+    const unsigned grid = (unsigned)(want > cap ? cap : want);
+    const double eps2 = eps * eps;
+    P2PMailbox* const* peers = (P2PMailbox* const*)d_mailboxes_or_null;
+    u64* partial = (u64*)d_partial_sums;
+    u64* totals = (u64*)d_totals;
+    void* args[] = {&d_keys, &d_counts, &n, &d_n_or_null, &k, &d_centers, &partial, &d_labels_or_null, &peers, &rank, &world,
+                    &max_iter, (void*)&eps2, &d_state, &d_shift, &totals, &iterations};
+    LLFE_KERNEL(ctx, "k_hist_lloyd");
+    LLFE_CUDA(cudaLaunchCooperativeKernel((const void*)k_hist_lloyd, dim3(grid), dim3(HT), args, 0, ctx->stream));
     LLFE_LAUNCHED(ctx);
     return LLFE_OK;
 }

@@ -8,7 +8,10 @@
 // IEEE-exact float32 operations per instruction; add.rn / mul.rn kept separate exactly like
 // OpenCV's normL2Sqr, never fused).  Per-cluster sums are exact integers reduced with
 // ballot + REDUX per warp, shared-memory tables per warp, one 64-bit atomic per table entry.
+#include <string.h>
+
 #include "llfe_common.cuh"
+#include "k_kmeans_p2p.cuh"
 #include "llfe_device.cuh"
 #include "k_kmeans_shared.cuh"
 
@@ -271,6 +274,14 @@ __global__ void __launch_bounds__(32) k_pixels_update(int K, unsigned long long*
     }
 }
 
+// ---- fused all-reduce + centre update over peer memory (config 5, N > 1): see k_kmeans_p2p.cuh ------------------------
+__global__ void __launch_bounds__(128) k_pixels_update_p2p(int K, unsigned long long* sums, P2PMailbox* const* peers, int rank,
+                                                           int world, float* centers, int max_iter, double eps2,
+                                                           int32_t* state, double* shift_out, unsigned long long* totals) {
+    __shared__ unsigned long long s_tot[KMAX * 4];
+    p2p_exchange_and_update(K, sums, peers, rank, world, centers, max_iter, eps2, state, shift_out, totals, s_tot);
+}
+
 // zero the per-rank accumulator for the next iteration -- unless the loop is converged or frozen
 __global__ void k_pixels_zero(int K, unsigned long long* sums, const int32_t* __restrict__ state) {
     if (state && (state[1] | state[3])) return;
@@ -318,6 +329,49 @@ extern "C" int llfe_kmeans_update(llfe_ctx* ctx, int k, uint64_t* d_sums_counts,
     LLFE_KERNEL(ctx, "k_pixels_update");
     k_pixels_update<<<1, 32, 0, ctx->stream>>>(k, (unsigned long long*)d_sums_counts, d_centers, max_iter, eps * eps,
                                                d_state, d_shift, (unsigned long long*)d_consumed_or_null, zero_sums);
+    LLFE_LAUNCHED(ctx);
+    return LLFE_OK;
+}
+
+extern "C" size_t llfe_p2p_mailbox_bytes(void) { return sizeof(P2PMailbox); }
+
+extern "C" int llfe_ipc_export(llfe_ctx* ctx, void* d_ptr, uint8_t* handle64) {
+    LLFE_ENTER(ctx);
+    LLFE_CHECK_ARG(d_ptr != nullptr && handle64 != nullptr);
+    static_assert(sizeof(cudaIpcMemHandle_t) == 64, "handle size is part of the ABI");
+    cudaIpcMemHandle_t h;
+    LLFE_CUDA(cudaIpcGetMemHandle(&h, d_ptr));
+    memcpy(handle64, &h, 64);
+    return LLFE_OK;
+}
+
+extern "C" int llfe_ipc_open(llfe_ctx* ctx, const uint8_t* handle64, void** d_peer_out) {
+    LLFE_ENTER(ctx);
+    LLFE_CHECK_ARG(handle64 != nullptr && d_peer_out != nullptr);
+    cudaIpcMemHandle_t h;
+    memcpy(&h, handle64, 64);
+    LLFE_CUDA(cudaIpcOpenMemHandle(d_peer_out, h, cudaIpcMemLazyEnablePeerAccess));
+    return LLFE_OK;
+}
+
+extern "C" int llfe_ipc_close(llfe_ctx* ctx, void* d_peer) {
+    LLFE_ENTER(ctx);
+    LLFE_CHECK_ARG(d_peer != nullptr);
+    LLFE_CUDA(cudaIpcCloseMemHandle(d_peer));
+    return LLFE_OK;
+}
+
+extern "C" int llfe_kmeans_update_p2p(llfe_ctx* ctx, int k, uint64_t* d_partial_sums, void* const* d_mailboxes, int rank,
+                                      int world, float* d_centers, int max_iter, double eps, int32_t* d_state,
+                                      double* d_shift, uint64_t* d_totals) {
+    LLFE_ENTER(ctx);
+    LLFE_CHECK_ARG(d_partial_sums != nullptr && d_mailboxes != nullptr && d_centers != nullptr && d_state != nullptr &&
+                   d_totals != nullptr && d_totals != d_partial_sums);
+    LLFE_CHECK_ARG(k >= 1 && k <= KMAX && max_iter >= 1 && world >= 1 && world <= P2P_MAXW && rank >= 0 && rank < world);
+    LLFE_KERNEL(ctx, "k_pixels_update_p2p");
+    k_pixels_update_p2p<<<1, 128, 0, ctx->stream>>>(k, (unsigned long long*)d_partial_sums, (P2PMailbox* const*)d_mailboxes,
+                                                    rank, world, d_centers, max_iter, eps * eps, d_state, d_shift,
+                                                    (unsigned long long*)d_totals);
     LLFE_LAUNCHED(ctx);
     return LLFE_OK;
 }

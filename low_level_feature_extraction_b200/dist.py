@@ -62,6 +62,34 @@ def gather_results(local: torch.Tensor, n_total: int, group=None) -> torch.Tenso
     return torch.cat([o[: b - a] for o, (a, b) in zip(out, sizes)], dim=0)
 
 
+class P2PSums:
+    """Peer mailboxes for the fused all-reduce + centre update of config 5 (`llfe_kmeans_update_p2p`): every rank of a
+    one-node NCCL group allocates a mailbox in its own HBM, exports it as a CUDA IPC handle, and maps the others'.
+    Built once per (engine, group); `table` is the device array of the `world` mailbox pointers."""
+
+    def __init__(self, engine, group=None):
+        self.engine = engine
+        self.rank = dist.get_rank(group)
+        self.world = dist.get_world_size(group)
+        if self.world > 16:
+            raise RuntimeError("at most 16 ranks")
+        nbytes = int(engine.ctx.lib.llfe_p2p_mailbox_bytes())
+        self.own = engine.raw_malloc(nbytes)
+        torch.cuda.synchronize(engine.device)
+        handles = [None] * self.world
+        dist.all_gather_object(handles, engine.ipc_export(self.own), group=group)
+        self.peers = [self.own if r == self.rank else engine.ipc_open(handles[r]) for r in range(self.world)]
+        self.table = torch.tensor(self.peers, dtype=torch.int64, device=engine.device)
+        dist.barrier(group=group)      # nobody writes into a mailbox before its owner has zeroed it
+
+    def close(self):
+        for r, p in enumerate(self.peers):
+            if r != self.rank:
+                self.engine.ipc_close(p)
+        self.engine.raw_free(self.own)
+        self.peers = []
+
+
 @dataclass
 class PixelKMeansResult:
     centers: torch.Tensor      # (k, 3) float32, RGB
@@ -79,9 +107,15 @@ class PixelKMeans:
     shift test max_k |c - old|^2 <= eps^2 from iteration 1 on, cv2's empty-cluster repair.
     """
 
-    def __init__(self, backend, group=None, iterations_per_sync: int = 8, histogram: bool = True):
+    def __init__(self, backend, group=None, iterations_per_sync: int = 8, histogram: bool = True, p2p: bool | None = None):
         self.be = backend
         self.group = group
+        # p2p: the per-iteration all-reduce of the k x 4 sums + the centre update as ONE kernel over NVLink peer stores
+        # (P2PSums) instead of ncclAllReduce + update.  None = whenever the group is NCCL with more than one rank and the
+        # backend is the CUDA engine; the gloo / CPU-backend tests keep the all-reduce.
+        self.p2p = p2p
+        self._p2p_sums = None
+        self.persistent = None    # None / True: the histogram form iterates inside one persistent kernel when it can
         self.iterations_per_sync = iterations_per_sync   # iterations enqueued per host look at the device state
         # histogram=True: stream the rows once into a 2^24-bin colour count table, all-reduce it, and iterate
         # over this rank's share of the DISTINCT colours weighted by their counts (identical labels, sums and
@@ -97,6 +131,18 @@ class PixelKMeans:
     def _allreduce(self, t: torch.Tensor, op) -> None:
         if dist.is_available() and dist.is_initialized() and dist.get_world_size(self.group) > 1:
             dist.all_reduce(t, op=op, group=self.group)
+
+    def _p2p_setup(self):
+        if self.p2p is False or self._p2p_sums is not None:
+            return self._p2p_sums
+        ok = (dist.is_available() and dist.is_initialized() and dist.get_world_size(self.group) > 1
+              and dist.get_backend(self.group) == "nccl" and hasattr(self.be, "kmeans_update_p2p"))
+        if not ok:
+            if self.p2p:
+                raise RuntimeError("p2p=True needs an NCCL group with more than one rank and the CUDA engine")
+            return None
+        self._p2p_sums = P2PSums(self.be, self.group)
+        return self._p2p_sums
 
     HB = 2048                    # keys per ownership block of the colour table (k_colorhist.cu)
 
@@ -154,6 +200,10 @@ class PixelKMeans:
             def step():
                 be.kmeans_pixels_step(bgr_rows, centers, local, labels, state)
 
+        p2p = self._p2p_setup()
+        _, ws_now = self._rank_world()
+        persistent = (self.histogram and self.persistent is not False and hasattr(be, "kmeans_hist_lloyd")
+                      and (ws_now == 1 or p2p is not None))
         overrides: list[tuple[int, int]] = []   # (local pixel, label) set by the repair after the last assignment
         overrides_iter = -1
         batch = max(1, int(self.iterations_per_sync))
@@ -161,11 +211,21 @@ class PixelKMeans:
             # `batch` iterations are enqueued back to back: assignment into the per-rank accumulator, in-place
             # all-reduce, update (which keeps the totals in `sums` and clears the accumulator).  Once the device
             # state says converged (or frozen for a repair) the remaining ones are no-ops on every rank alike.
-            for _ in range(batch):
+            if persistent:
+                # the whole batch is one persistent cooperative kernel (assignment, NVLink exchange, update per iteration)
+                be.kmeans_hist_lloyd(keys, counts, centers, local, entry_labels, state, shift, sums, n_dev=n_dev,
+                                     mailboxes=None if p2p is None else p2p.table, rank=0 if p2p is None else p2p.rank,
+                                     world=1 if p2p is None else p2p.world, max_iter=max_iter, eps=eps,
+                                     iterations=4 * batch)
+            for _ in range(0 if persistent else batch):
                 step()
-                self._allreduce(local, dist.ReduceOp.SUM)
-                be.kmeans_update(local, centers, state, shift, max_iter=max_iter, eps=eps, consumed=sums,
-                                 zero_sums=True)
+                if p2p is not None:
+                    be.kmeans_update_p2p(local, p2p.table, p2p.rank, p2p.world, centers, state, shift, sums,
+                                         max_iter=max_iter, eps=eps)
+                else:
+                    self._allreduce(local, dist.ReduceOp.SUM)
+                    be.kmeans_update(local, centers, state, shift, max_iter=max_iter, eps=eps, consumed=sums,
+                                     zero_sums=True)
             st = state.tolist()          # the one host synchronisation per batch
             if st[3]:
                 if self.histogram and keys.numel() != int(n_dev.item()):   # the repair walks the real list (rare path)

@@ -376,6 +376,50 @@ class Engine:
     # ---- colour-histogram form of the per-pixel k-means (config 5) ----------------------------------
     HIST_BINS = 1 << 24
 
+    def kmeans_update_p2p(self, partial: torch.Tensor, mailboxes: torch.Tensor, rank: int, world: int,
+                          centers: torch.Tensor, state: torch.Tensor, shift: torch.Tensor, totals: torch.Tensor,
+                          max_iter: int = 200, eps: float = 0.2):
+        """All-reduce of the (k,4) partial sums through the peers' mailboxes + centre update in one kernel
+        (llfe_kmeans_update_p2p): `partial` is consumed and cleared, `totals` receives the global sums."""
+        self._bind()
+        self.ctx.call("llfe_kmeans_update_p2p", partial.shape[0], partial, mailboxes, int(rank), int(world), centers,
+                      int(max_iter), float(eps), state, shift, totals)
+
+    # -- peer memory (one node, NVLink): raw device allocations that can be exported to the other ranks ----------
+    def raw_malloc(self, nbytes: int) -> int:
+        import ctypes as C
+
+        ptr = C.c_void_p()
+        rc = self.ctx.lib.llfe_malloc(self.ctx.handle, int(nbytes), C.byref(ptr))
+        if rc != 0:
+            raise RuntimeError(self.ctx.lib.llfe_last_error().decode())
+        self._bind()
+        self.ctx.call("llfe_memset", ptr.value, 0, int(nbytes))
+        return int(ptr.value)
+
+    def raw_free(self, ptr: int):
+        self.ctx.call("llfe_free", int(ptr))
+
+    def ipc_export(self, ptr: int) -> bytes:
+        import ctypes as C
+
+        buf = (C.c_uint8 * 64)()
+        self.ctx.call("llfe_ipc_export", int(ptr), C.addressof(buf))
+        return bytes(buf)
+
+    def ipc_open(self, handle: bytes) -> int:
+        import ctypes as C
+
+        buf = (C.c_uint8 * 64).from_buffer_copy(handle)
+        out = C.c_void_p()
+        rc = self.ctx.lib.llfe_ipc_open(self.ctx.handle, C.addressof(buf), C.byref(out))
+        if rc != 0:
+            raise RuntimeError(self.ctx.lib.llfe_last_error().decode())
+        return int(out.value)
+
+    def ipc_close(self, ptr: int):
+        self.ctx.call("llfe_ipc_close", int(ptr))
+
     def pixels_histogram(self, bgr_rows: torch.Tensor, hist: torch.Tensor):
         """hist (2^24,) int32 += pixel count per colour key (R << 16) + (G << 8) + B."""
         x = bgr_rows.contiguous()
@@ -417,6 +461,16 @@ class Engine:
         self._bind()
         self.ctx.call("llfe_kmeans_hist_step", keys, counts, keys.numel(), centers.shape[0], centers, sums, labels,
                       state, n_dev)
+
+    def kmeans_hist_lloyd(self, keys: torch.Tensor, counts: torch.Tensor, centers: torch.Tensor, partial: torch.Tensor,
+                          labels: torch.Tensor | None, state: torch.Tensor, shift: torch.Tensor, totals: torch.Tensor,
+                          n_dev: torch.Tensor | None = None, mailboxes: torch.Tensor | None = None, rank: int = 0,
+                          world: int = 1, max_iter: int = 200, eps: float = 0.2, iterations: int = 32):
+        """Up to `iterations` Lloyd iterations over (key, count) entries in one persistent cooperative kernel, the sums
+        exchanged through the peers' mailboxes (llfe_kmeans_hist_lloyd); stops early on converged / frozen."""
+        self._bind()
+        self.ctx.call("llfe_kmeans_hist_lloyd", keys, counts, keys.numel(), n_dev, centers.shape[0], centers, partial, labels,
+                      mailboxes, int(rank), int(world), int(max_iter), float(eps), state, shift, totals, int(iterations))
 
     def hist_labels_to_lut(self, keys: torch.Tensor, labels: torch.Tensor, lut: torch.Tensor):
         assert lut.numel() == self.HIST_BINS and lut.dtype == torch.uint8

@@ -30,10 +30,15 @@ def _init_from_pixels(px, k, seed):
     return np.float32(px[np.random.default_rng(seed).choice(len(px), k, replace=False)])
 
 
-@pytest.mark.parametrize("histogram", [True, False])
+@pytest.mark.parametrize("histogram", [True, "launch-per-iteration", False])
 @pytest.mark.parametrize("case", [("design", 96, 128, 16, 42), ("design", 45, 77, 5, 1), ("noise", 64, 96, 8, 3)])
 def test_pixel_kmeans_matches_exact_oracle(eng, case, histogram):
-    from low_level_feature_extraction_b200.dist import PixelKMeans
+    from low_level_feature_extraction_b200.dist import PixelKMeans as _PKM
+
+    def PixelKMeans(e, histogram):       # True: persistent cooperative kernel; "launch-per-iteration": step + update launches
+        km = _PKM(e, histogram=bool(histogram))
+        km.persistent = histogram is True
+        return km
 
     kind, h, w, k, seed = case
     img = design_image(h, w, seed) if kind == "design" else noise_image(h, w, seed)
@@ -53,9 +58,14 @@ def test_pixel_kmeans_matches_exact_oracle(eng, case, histogram):
         assert np.abs(res.centers.cpu().numpy() - c_cv).max() / 255.0 <= 1e-3
 
 
-@pytest.mark.parametrize("histogram", [True, False])
+@pytest.mark.parametrize("histogram", [True, "launch-per-iteration", False])
 def test_pixel_kmeans_empty_cluster_repair(eng, histogram):
-    from low_level_feature_extraction_b200.dist import PixelKMeans
+    from low_level_feature_extraction_b200.dist import PixelKMeans as _PKM
+
+    def PixelKMeans(e, histogram):
+        km = _PKM(e, histogram=bool(histogram))
+        km.persistent = histogram is True
+        return km
 
     img = design_image(40, 56, 9)
     px = img.reshape(-1, 3)[:, ::-1]
@@ -211,3 +221,48 @@ def test_config5_full_size_properties(eng):
     assert code > 0
     gidx = (code - 1) & 0xFFFFFFFF
     assert r0 * n <= gidx < npix and int(lab_px[gidx]) == donor
+
+
+def test_p2p_update_kernel_on_one_rank_equals_plain_update(eng):
+    """llfe_kmeans_update_p2p with a world of one (its own mailbox only): same centres / state / totals as
+    llfe_kmeans_update over several epochs (both mailbox parities), and the converged state makes it a no-op."""
+    k = 16
+    rng = np.random.default_rng(0)
+    mailbox = eng.raw_malloc(int(eng.ctx.lib.llfe_p2p_mailbox_bytes()))
+    table = torch.tensor([mailbox], dtype=torch.int64, device="cuda")
+    c_a = torch.from_numpy(rng.random((k, 3)).astype(np.float32) * 255).cuda()
+    c_b = c_a.clone()
+    st_a = torch.zeros(4, dtype=torch.int32, device="cuda")
+    st_b = st_a.clone()
+    sh_a = torch.zeros(1, dtype=torch.float64, device="cuda")
+    sh_b = sh_a.clone()
+    tot_a = torch.zeros((k, 4), dtype=torch.int64, device="cuda")
+    tot_b = tot_a.clone()
+    for it in range(5):
+        cnt = rng.integers(1, 1 << 28, (k, 1))
+        sums = np.concatenate([cnt * rng.integers(0, 256, (k, 3)), cnt], axis=1).astype(np.int64)
+        if it >= 3:
+            sums = last                                  # repeated sums: zero shift -> converged
+        last = sums
+        pa = torch.from_numpy(sums).cuda()
+        pb = pa.clone()
+        eng.kmeans_update(pa, c_a, st_a, sh_a, max_iter=200, eps=0.2, consumed=tot_a, zero_sums=True)
+        eng.kmeans_update_p2p(pb, table, 0, 1, c_b, st_b, sh_b, tot_b, max_iter=200, eps=0.2)
+        assert torch.equal(c_a, c_b) and torch.equal(st_a, st_b) and torch.equal(tot_a, tot_b) and torch.equal(sh_a, sh_b)
+        assert torch.equal(pa, pb)                       # cleared while running, left alone once converged
+    assert int(st_b[1]) == 1
+    eng.raw_free(mailbox)
+
+
+@pytest.mark.skipif(torch.cuda.device_count() < 2, reason="needs two GPUs on the box (gpurun --gpus 2)")
+def test_p2p_fit_equals_allreduce_fit_on_two_gpus():
+    """The fused NVLink exchange gives bit-identical centres to the NCCL all-reduce loop (tools/p2p_check.py)."""
+    import json
+    import subprocess
+
+    out = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2",
+                          "--master-addr", "127.0.0.1", "--master-port", "29617", os.path.join(ROOT, "tools", "p2p_check.py"),
+                          "--size", "2048"], capture_output=True, text=True, timeout=600)
+    assert out.returncode == 0, out.stderr[-2000:]
+    rec = json.loads(out.stdout.strip().splitlines()[-1])
+    assert rec["identical"] and rec["world"] == 2
