@@ -320,6 +320,14 @@ int llfe_kmeans_hist_step(llfe_ctx* ctx, const uint32_t* d_keys, const uint32_t*
                           const float* d_centers, uint64_t* d_sums_counts, uint8_t* d_labels_or_null,
                           const int32_t* d_state_or_null, const int32_t* d_n_or_null);
 
+/* The colour table across the ranks of one node without NCCL (config 5): every rank's 2^24-bin table lives in memory
+ * exported to the peers (llfe_ipc_export); llfe_p2p_barrier (device-side barrier through the mailboxes: all tables are
+ * complete) and then llfe_histogram_pull_reduce, which reads this rank's interleaved 2048-key blocks out of every table in
+ * d_tables[world] over NVLink, sums them and writes the packed share (2^24 / world bins) that llfe_histogram_compact takes
+ * with packed = 1.  world must divide 8192. */
+int llfe_p2p_barrier(llfe_ctx* ctx, void* const* d_mailboxes, int rank, int world);
+int llfe_histogram_pull_reduce(llfe_ctx* ctx, const uint32_t* const* d_tables, int rank, int world, uint32_t* d_share);
+
 /* The whole per-iteration loop {llfe_kmeans_hist_step, exchange of the sums, llfe_kmeans_update} as ONE persistent
  * cooperative kernel per rank: up to `iterations` Lloyd iterations over this rank's (key, count) entries, with the sums
  * exchanged through the peers' mailboxes (d_mailboxes as for llfe_kmeans_update_p2p; NULL with world = 1) and the centres,

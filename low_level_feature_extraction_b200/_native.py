@@ -80,6 +80,8 @@ PROTOTYPES = {
     "llfe_pixels_histogram": (i32, [vp, vp, sz, vp]),
     "llfe_histogram_compact": (i32, [vp, vp, i32, i32, vp, vp, sz, vp, i32]),
     "llfe_kmeans_hist_step": (i32, [vp, vp, vp, sz, i32, vp, vp, vp, vp, vp]),
+    "llfe_p2p_barrier": (i32, [vp, vp, i32, i32]),
+    "llfe_histogram_pull_reduce": (i32, [vp, vp, i32, i32, vp]),
     "llfe_kmeans_hist_lloyd": (i32, [vp, vp, vp, sz, vp, i32, vp, vp, vp, vp, i32, i32, i32, f64, vp, vp, vp, i32]),
     "llfe_hist_labels_to_lut": (i32, [vp, vp, vp, sz, vp]),
     "llfe_pixels_lookup": (i32, [vp, vp, sz, vp, vp]),

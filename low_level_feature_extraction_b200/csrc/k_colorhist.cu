@@ -315,6 +315,32 @@ __global__ void __launch_bounds__(HT) k_hist_step(const uint32_t* __restrict__ k
     hist_step_body(keys, counts, n, K, centers, sums, labels_out, s_nc, s_acc);
 }
 
+// ---- the colour table across ranks without NCCL: barrier, then every rank PULLS its share from the peers ---------------
+__global__ void __launch_bounds__(128) k_p2p_barrier(P2PMailbox* const* peers, int rank, int world) {
+    p2p_barrier(peers, rank, world);
+}
+
+// share[j * HB + i] = sum over ranks q of table_q[(j * world + rank) * HB + i]: the interleaved 2048-key blocks this rank
+// owns, read straight out of every peer's HBM over NVLink (16-byte loads), summed, packed back to back -- what the
+// reduce-scatter of the block-transposed table delivered, without the transposition copy and the NCCL launch.
+__global__ void __launch_bounds__(256) k_hist_pull_reduce(const uint32_t* const* tables, int rank, int world,
+                                                          uint32_t* __restrict__ share) {
+    const size_t n4 = (size_t)(1u << 24) / world / 4;       // uint4 elements of the share
+    for (size_t v = (size_t)blockIdx.x * 256 + threadIdx.x; v < n4; v += (size_t)gridDim.x * 256) {
+        const size_t j = v / (HB / 4), i4 = v % (HB / 4);
+        const size_t src = (j * world + rank) * (HB / 4) + i4;
+        uint4 acc = make_uint4(0u, 0u, 0u, 0u);
+        for (int q = 0; q < world; ++q) {
+            const uint4 a = __ldcg(reinterpret_cast<const uint4*>(tables[q]) + src);
+            acc.x += a.x;
+            acc.y += a.y;
+            acc.z += a.z;
+            acc.w += a.w;
+        }
+        reinterpret_cast<uint4*>(share)[v] = acc;
+    }
+}
+
 // The whole Lloyd loop of the colour-histogram form as ONE persistent cooperative kernel per rank: assignment over this
 // rank's (key, count) entries by every CTA, grid barrier, exchange of the K x 4 partial sums with the other ranks through
 // their NVLink mailboxes + centre update by CTA 0 (k_kmeans_p2p.cuh), grid barrier, next iteration -- until the state says
@@ -543,6 +569,26 @@ extern "C" int llfe_kmeans_hist_step(llfe_ctx* ctx, const uint32_t* d_keys, cons
     LLFE_KERNEL(ctx, "k_hist_step");
     k_hist_step<<<(unsigned)(want > cap ? cap : want), HT, 0, ctx->stream>>>(
         d_keys, d_counts, n, k, d_centers, (u64*)d_sums_counts, d_labels_or_null, d_state_or_null, d_n_or_null);
+    LLFE_LAUNCHED(ctx);
+    return LLFE_OK;
+}
+
+extern "C" int llfe_p2p_barrier(llfe_ctx* ctx, void* const* d_mailboxes, int rank, int world) {
+    LLFE_ENTER(ctx);
+    LLFE_CHECK_ARG(d_mailboxes != nullptr && world >= 1 && world <= P2P_MAXW && rank >= 0 && rank < world);
+    LLFE_KERNEL(ctx, "k_p2p_barrier");
+    k_p2p_barrier<<<1, 128, 0, ctx->stream>>>((P2PMailbox* const*)d_mailboxes, rank, world);
+    LLFE_LAUNCHED(ctx);
+    return LLFE_OK;
+}
+
+extern "C" int llfe_histogram_pull_reduce(llfe_ctx* ctx, const uint32_t* const* d_tables, int rank, int world,
+                                          uint32_t* d_share) {
+    LLFE_ENTER(ctx);
+    LLFE_CHECK_ARG(d_tables != nullptr && d_share != nullptr && world >= 1 && world <= P2P_MAXW && rank >= 0 && rank < world);
+    LLFE_CHECK_ARG(NBLK % world == 0);
+    LLFE_KERNEL(ctx, "k_hist_pull_reduce");
+    k_hist_pull_reduce<<<stream_grid(ctx, (size_t)(1u << 24) / world / 4), 256, 0, ctx->stream>>>(d_tables, rank, world, d_share);
     LLFE_LAUNCHED(ctx);
     return LLFE_OK;
 }

@@ -17,7 +17,9 @@ struct P2PMailbox {
     unsigned long long slots[2][P2P_MAXW][KMAX * 4];
     unsigned int flags[2][P2P_MAXW];
     unsigned int epoch;
-    unsigned int pad[31];
+    unsigned int bflags[2][P2P_MAXW];   // the stand-alone barrier (p2p_barrier) has its own flags and epoch
+    unsigned int bepoch;
+    unsigned int pad[30];
 };
 
 __device__ __forceinline__ void st_release_sys(unsigned int* p, unsigned int v) {
@@ -108,4 +110,21 @@ __device__ __forceinline__ void p2p_exchange_and_update(int K, unsigned long lon
         state[1] = (it == last_it) || (it0 > 0 && sh <= eps2);
         if (shift_out) *shift_out = sh;
     }
+}
+
+// Cross-rank barrier on the device, called by one CTA of >= `world` threads on every rank: "everything this rank enqueued
+// before is visible to the peers, and the peers have got as far".  Same flag protocol as above with its own epoch.
+__device__ __forceinline__ void p2p_barrier(P2PMailbox* const* peers, int rank, int world) {
+    const int t = threadIdx.x;
+    P2PMailbox* mine = peers[rank];
+    const unsigned int e = mine->bepoch + 1u;
+    __threadfence_system();
+    __syncthreads();
+    if (t < world) {
+        st_release_sys(&peers[t]->bflags[e & 1u][rank], e);
+        while (ld_acquire_sys(&mine->bflags[e & 1u][t]) != e) {
+        }
+    }
+    __syncthreads();
+    if (t == 0) mine->bepoch = e;
 }

@@ -73,13 +73,17 @@ class P2PSums:
         self.world = dist.get_world_size(group)
         if self.world > 16:
             raise RuntimeError("at most 16 ranks")
-        nbytes = int(engine.ctx.lib.llfe_p2p_mailbox_bytes())
+        # one exported allocation per rank: the mailbox, then this rank's 2^24-bin colour table (64 MiB)
+        self.table_offset = (int(engine.ctx.lib.llfe_p2p_mailbox_bytes()) + 255) & ~255
+        nbytes = self.table_offset + (1 << 24) * 4
         self.own = engine.raw_malloc(nbytes)
         torch.cuda.synchronize(engine.device)
         handles = [None] * self.world
         dist.all_gather_object(handles, engine.ipc_export(self.own), group=group)
         self.peers = [self.own if r == self.rank else engine.ipc_open(handles[r]) for r in range(self.world)]
         self.table = torch.tensor(self.peers, dtype=torch.int64, device=engine.device)
+        self.hist_tables = torch.tensor([p + self.table_offset for p in self.peers], dtype=torch.int64, device=engine.device)
+        self.own_hist = self.own + self.table_offset
         dist.barrier(group=group)      # nobody writes into a mailbox before its owner has zeroed it
 
     def close(self):
@@ -180,11 +184,22 @@ class PixelKMeans:
         flat = bgr_rows.reshape(-1, 3)
         if self.histogram:
             rank, ws = self._rank_world()
-            hist = torch.zeros((1 << 24,), dtype=torch.int32, device=dev)
-            be.pixels_histogram(bgr_rows, hist)
-            # Every rank needs only ITS share of the summed table (the interleaved 2048-key blocks b % G == rank):
-            # reduce-scatter over the block-transposed table moves 1/G of what an all-reduce of the 64 MiB would.
-            share = self._reduce_scatter_blocks(hist, rank, ws)
+            p2p_tab = self._p2p_setup() if (1 << 24) // self.HB % max(ws, 1) == 0 else None
+            if p2p_tab is not None:
+                # the table lives in memory the peers can read: device barrier, then every rank pulls and sums ITS share
+                # (the interleaved 2048-key blocks b % G == rank) straight out of the peers' HBM over NVLink
+                be.raw_memset(p2p_tab.own_hist, 0, (1 << 24) * 4)
+                be.pixels_histogram_raw(bgr_rows, p2p_tab.own_hist)
+                be.p2p_barrier(p2p_tab.table, rank, ws)
+                hist = None
+                share = torch.empty(((1 << 24) // ws,), dtype=torch.int32, device=dev)
+                be.histogram_pull_reduce(p2p_tab.hist_tables, rank, ws, share)
+            else:
+                hist = torch.zeros((1 << 24,), dtype=torch.int32, device=dev)
+                be.pixels_histogram(bgr_rows, hist)
+                # Every rank needs only ITS share of the summed table: reduce-scatter over the block-transposed table
+                # moves 1/G of what an all-reduce of the 64 MiB would.
+                share = self._reduce_scatter_blocks(hist, rank, ws)
             if share is not None:
                 keys, counts, n_dev = be.histogram_compact_device(share, rank, ws, packed=True)
             else:

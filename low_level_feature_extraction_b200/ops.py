@@ -397,6 +397,24 @@ class Engine:
         self.ctx.call("llfe_memset", ptr.value, 0, int(nbytes))
         return int(ptr.value)
 
+    def raw_memset(self, ptr: int, value: int, nbytes: int):
+        self._bind()
+        self.ctx.call("llfe_memset", int(ptr), int(value), int(nbytes))
+
+    def pixels_histogram_raw(self, bgr_rows: torch.Tensor, hist_ptr: int):
+        """pixels_histogram into a raw (exported) 2^24-bin table."""
+        x = bgr_rows.contiguous()
+        self._bind()
+        self.ctx.call("llfe_pixels_histogram", x, x.numel() // 3, int(hist_ptr))
+
+    def p2p_barrier(self, mailboxes: torch.Tensor, rank: int, world: int):
+        self._bind()
+        self.ctx.call("llfe_p2p_barrier", mailboxes, int(rank), int(world))
+
+    def histogram_pull_reduce(self, tables: torch.Tensor, rank: int, world: int, share: torch.Tensor):
+        self._bind()
+        self.ctx.call("llfe_histogram_pull_reduce", tables, int(rank), int(world), share)
+
     def raw_free(self, ptr: int):
         self.ctx.call("llfe_free", int(ptr))
 
