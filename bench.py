@@ -89,7 +89,7 @@ def parse_args():
     ap.add_argument("--e2e-steps", type=int, default=6)
     ap.add_argument("--e2e-tail", choices=["thread", "inline"], default="thread",
                     help="host palette tail of e2e: on a worker thread under the next step's copies, or inline")
-    ap.add_argument("--no-extras", action="store_true", help="skip the extra records (BASELINE configs 2, 3, 5, adversarial frames)")
+    ap.add_argument("--no-extras", action="store_true", help="skip the extra records (BASELINE configs 2, 3, literal 4, 5, contours, adversarial frames)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--cpu-seconds", type=float, default=10.0, help="target CPU time of the cpu_baseline sample")
@@ -409,6 +409,44 @@ def pipeline_record(args, workload, B, H, W, k, steps, warmup, rank, world, loca
     return rec
 
 
+def contours_record(local, dev, rank, B, H, W):
+    """external contours (cv2.findContours(EXTERNAL, SIMPLE) + the reference's area filter) of the shape
+    masks of a device-resident batch, all images traced concurrently; next to cv2 on one host core."""
+    import cv2
+    import torch
+
+    import low_level_feature_extraction_b200 as pkg
+
+    eng = pkg.engine(local)
+    batch = device_batch(dev, rank, B, H, W, 32, "design")
+    masks = eng.shape_mask(batch)
+    eng.contours_external(masks[:8], 200, 1024, 8192)
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    reps = 3
+    e0.record()
+    for _ in range(reps):
+        hdr, pts, cnt = eng.contours_external(masks, 200, 1024, 8192)
+    e1.record()
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1) / reps
+    c = cnt.cpu()
+    host = masks[:8].cpu().numpy()
+    t0 = time.perf_counter()
+    for m in host:
+        cv2.findContours(m, cv2.RETR_EXTERNAL, cv2.CHAIN_APPROX_SIMPLE)
+    cv_ms = (time.perf_counter() - t0) * 1e3 / len(host)
+    rec = {"workload": f"external contours of {B} {W}x{H} shape masks (device-resident), area filter 100", "images_per_gpu": B,
+           "ms_per_step": ms, "value": B / (ms / 1e3), "unit": "images/sec",
+           "contours_per_image": float(c[:, 0].float().mean()), "points_per_image": float(c[:, 1].float().mean()),
+           "overflowed_images": int(((c[:, 0] > 1024) | (c[:, 2] != 0)).sum()),
+           "cv2_findContours_ms_per_image_one_core": cv_ms,
+           "d2h_bytes_per_image_if_fetched": 1024 * 40 + 8192 * 8 + 16}
+    del batch, masks, hdr, pts
+    torch.cuda.empty_cache()
+    return rec
+
+
 def pixel_kmeans_record(rank, world, local, dev, height, width, k, synth="design"):
     """BASELINE config 5: ONE height x width image, rows sharded over the ranks (strong scaling), per-pixel k-means with
     exact integer sums; the colour count table crosses NVLink once (reduce-scatter), the K x 4 sums every iteration."""
@@ -552,11 +590,16 @@ def run_ours(args):
 
         guarded("config2_shapes_256x1080p", lambda: pipeline_record(
             args, "shapes", 256, 1080, 1920, 5, 5, 2, rank, world, local, dev, 32))
+        # BASELINE config 4 literally: 8192 images over 8 GPUs = 1024 per GPU (the headline line runs 256 per GPU)
+        guarded("config4_pipeline_1024_per_gpu_1080p", lambda: pipeline_record(
+            args, "pipeline", 1024, 1080, 1920, 5, 3, 1, rank, world, local, dev, 32))
         guarded("config3_palette_shadows_64x4k_k16", lambda: pipeline_record(
             args, "palette_shadows", 64, 2160, 3840, 16, 3, 1, rank, world, local, dev, 8))
         if world == 1:
             guarded("adversarial_uniform_noise_1080p", lambda: pipeline_record(
                 args, "pipeline", 4, 1080, 1920, 5, 1, 1, rank, world, local, dev, 4, kind="noise"))
+        if world == 1:
+            guarded("contours_256x1080p", lambda: contours_record(local, dev, rank, 256, 1080, 1920))
         guarded("config5_pixel_kmeans_16384x16384_k16", lambda: pixel_kmeans_record(
             rank, world, local, dev, 16384, 16384, 16))
         guarded("config5_pixel_kmeans_photo_like", lambda: pixel_kmeans_record(

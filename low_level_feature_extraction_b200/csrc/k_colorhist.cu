@@ -607,7 +607,7 @@ extern "C" int llfe_kmeans_hist_lloyd(llfe_ctx* ctx, const uint32_t* d_keys, con
     LLFE_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_hist_lloyd, HT, 0));
     LLFE_CHECK_ARG(per_sm >= 1);
     const size_t want = n ? ceil_div_sz(n, HT * EPS_T) : 1;
-    const size_t cap = (size_t)ctx->sm_count * (per_sm < 4 ? per_sm : 4);
+    const size_t cap = (size_t)ctx->sm_count * (per_sm < 8 ? per_sm : 8);
     const unsigned grid = (unsigned)(want > cap ? cap : want);
     const double eps2 = eps * eps;
     P2PMailbox* const* peers = (P2PMailbox* const*)d_mailboxes_or_null;
