@@ -112,6 +112,21 @@ __global__ void __launch_bounds__(256) k_ct_plane(const uint8_t* __restrict__ ma
     if (lane == 0) plane[blockIdx.z * g.plane_words + (size_t)(y + 1) * g.pw + word + 1] = f;
 }
 
+// the same for widths that are a multiple of 32 (rows 16-byte aligned): a thread per word, 32 mask bytes as two 128-bit
+// loads; four bytes become four bits with one compare, one mask and one multiply (the partial products land on distinct bits)
+__device__ __forceinline__ uint32_t ct_nibble(uint32_t v) { return (((__vcmpne4(v, 0u) & 0x01010101u) * 0x01020408u) >> 24) & 0xfu; }
+
+__global__ void __launch_bounds__(256) k_ct_plane32(const uint8_t* __restrict__ mask, CtGeom g, uint32_t* __restrict__ plane) {
+    const int idx = blockIdx.x * 256 + threadIdx.x;
+    if (idx >= g.h * g.wpr) return;
+    const int y = idx / g.wpr, word = idx - y * g.wpr;
+    const uint4* p = reinterpret_cast<const uint4*>(mask + (size_t)blockIdx.z * g.h * g.w + (size_t)y * g.w + word * 32);
+    const uint4 a = ld_stream(p), b = ld_stream(p + 1);
+    const uint32_t f = ct_nibble(a.x) | (ct_nibble(a.y) << 4) | (ct_nibble(a.z) << 8) | (ct_nibble(a.w) << 12) |
+                       (ct_nibble(b.x) << 16) | (ct_nibble(b.y) << 20) | (ct_nibble(b.z) << 24) | (ct_nibble(b.w) << 28);
+    plane[blockIdx.z * g.plane_words + (size_t)(y + 1) * g.pw + word + 1] = f;
+}
+
 // 32 x 32 bit blocks of the plane, transposed (one warp per block)
 __global__ void __launch_bounds__(32) k_ct_transpose(const uint32_t* __restrict__ plane, CtGeom g, uint32_t* __restrict__ planeT) {
     const int bx = blockIdx.x, by = blockIdx.y, lane = threadIdx.x;
@@ -510,42 +525,56 @@ static int ct_pool_blocks(int max_contours, int max_points) {
     return max_points > 0 ? max_contours + 2 * ceil_div(max_points, CT_BLOCK_PTS) : 0;
 }
 
-size_t contours_ws_bytes(int n, int h, int w, int max_contours, int max_points) {
+// Workspace of one pass over n images: planes + scratch point pool for all of them (every border of the pass is followed
+// in ONE launch: the pass lasts as long as its longest border, so it should cover many images), union-find state (4 bytes
+// per pixel: the part that must stay L2-sized) for `sub` images at a time.
+constexpr int CT_SUB = 16;          // images per union-find sub-pass (1080p: 16 x 9.3 MB)
+constexpr int CT_PASS = 256;        // images per pass
+
+static size_t contours_ws_bytes(int n, int sub, int h, int w, int max_contours, int max_points) {
     const CtGeom g = ct_geom(h, w);
-    return WsCarver::need(n * (g.plane_words + g.planeT_words) * 4) + 2 * WsCarver::need(n * g.sin_words * 4) +
-           WsCarver::need(n * g.label_words * 4) + WsCarver::need((size_t)n * ct_pool_blocks(max_contours, max_points) * 512);
+    return WsCarver::need(n * (g.plane_words + g.planeT_words) * 4) +
+           WsCarver::need((size_t)n * ct_pool_blocks(max_contours, max_points) * 512) + 2 * WsCarver::need(sub * g.sin_words * 4) +
+           WsCarver::need(sub * g.label_words * 4);
 }
 
-static int contours_chunk(llfe_ctx* ctx, const uint8_t* d_mask, int n, int h, int w, int64_t min_area2, int32_t* d_headers,
-                          int max_contours, int32_t* d_points, int max_points, int32_t* d_counts, void* ws) {
+static int contours_pass(llfe_ctx* ctx, const uint8_t* d_mask, int n, int sub, int h, int w, int64_t min_area2,
+                         int32_t* d_headers, int max_contours, int32_t* d_points, int max_points, int32_t* d_counts, void* ws) {
     const CtGeom g = ct_geom(h, w);
     WsCarver carve(ws);
     uint32_t* plane = carve.take<uint32_t>(n * (g.plane_words + g.planeT_words));
     uint32_t* planeT = plane + n * g.plane_words;
-    int* sinF = carve.take<int>(n * g.sin_words);
-    int* sinB = carve.take<int>(n * g.sin_words);
-    int* labels = carve.take<int>(n * g.label_words);
     const int pool_blocks = ct_pool_blocks(max_contours, max_points);
     int2* pool = carve.take<int2>((size_t)n * pool_blocks * 64);
+    int* sinF = carve.take<int>(sub * g.sin_words);
+    int* sinB = carve.take<int>(sub * g.sin_words);
+    int* labels = carve.take<int>(sub * g.label_words);
     LLFE_CUDA(cudaMemsetAsync(plane, 0, n * (g.plane_words + g.planeT_words) * 4, ctx->stream));
     LLFE_CUDA(cudaMemsetAsync(d_counts, 0, (size_t)n * 4 * sizeof(int32_t), ctx->stream));
     LLFE_KERNEL(ctx, "k_ct_plane");
-    k_ct_plane<<<dim3(ceil_div(g.wpr, 8), h, n), 256, 0, ctx->stream>>>(d_mask, g, plane);
+    if (w % 32 == 0 && ((uintptr_t)d_mask & 15) == 0)
+        k_ct_plane32<<<dim3(ceil_div(h * g.wpr, 256), 1, n), 256, 0, ctx->stream>>>(d_mask, g, plane);
+    else
+        k_ct_plane<<<dim3(ceil_div(g.wpr, 8), h, n), 256, 0, ctx->stream>>>(d_mask, g, plane);
     LLFE_LAUNCHED(ctx);
     LLFE_KERNEL(ctx, "k_ct_transpose");
     k_ct_transpose<<<dim3(g.wpr, g.hpr, n), 32, 0, ctx->stream>>>(plane, g, planeT);
     LLFE_LAUNCHED(ctx);
-    LLFE_KERNEL(ctx, "k_ct_rows");
-    k_ct_rows<<<dim3(ceil_div(h, 8), 1, n), 256, 0, ctx->stream>>>(plane, g, sinF, sinB, labels);
-    LLFE_LAUNCHED(ctx);
     const int words = h * g.wpr;
-    LLFE_KERNEL(ctx, "k_ct_merge");
-    k_ct_merge<<<dim3(ceil_div(words, 256), 1, n), 256, 0, ctx->stream>>>(plane, g, sinF, sinB, labels);
-    LLFE_LAUNCHED(ctx);
-    LLFE_KERNEL(ctx, "k_ct_starts");
-    k_ct_starts<<<dim3(ceil_div(words, 256), 1, n), 256, 0, ctx->stream>>>(plane, g, sinB, labels, (CtHeader*)d_headers,
-                                                                          max_contours, d_counts);
-    LLFE_LAUNCHED(ctx);
+    for (int i0 = 0; i0 < n; i0 += sub) {
+        const int m = n - i0 < sub ? n - i0 : sub;
+        const uint32_t* pl = plane + (size_t)i0 * g.plane_words;
+        LLFE_KERNEL(ctx, "k_ct_rows");
+        k_ct_rows<<<dim3(ceil_div(h, 8), 1, m), 256, 0, ctx->stream>>>(pl, g, sinF, sinB, labels);
+        LLFE_LAUNCHED(ctx);
+        LLFE_KERNEL(ctx, "k_ct_merge");
+        k_ct_merge<<<dim3(ceil_div(words, 256), 1, m), 256, 0, ctx->stream>>>(pl, g, sinF, sinB, labels);
+        LLFE_LAUNCHED(ctx);
+        LLFE_KERNEL(ctx, "k_ct_starts");
+        k_ct_starts<<<dim3(ceil_div(words, 256), 1, m), 256, 0, ctx->stream>>>(
+            pl, g, sinB, labels, (CtHeader*)d_headers + (size_t)i0 * max_contours, max_contours, d_counts + (size_t)i0 * 4);
+        LLFE_LAUNCHED(ctx);
+    }
     LLFE_KERNEL(ctx, "k_ct_trace");
     k_ct_trace<<<dim3(ceil_div(max_contours, 4), 1, n), 128, 0, ctx->stream>>>(plane, planeT, g, (CtHeader*)d_headers,
                                                                               max_contours, (long long)min_area2,
@@ -564,14 +593,19 @@ extern "C" int llfe_contours_external(llfe_ctx* ctx, const uint8_t* d_mask, int 
     LLFE_CHECK_ARG(d_mask != nullptr && d_headers != nullptr && d_counts != nullptr && (d_points != nullptr || max_points == 0));
     LLFE_CHECK_ARG(n > 0 && h > 0 && w > 0 && (size_t)h * w < 0x7ffffff0ull && max_contours > 0 && max_points >= 0);
     static_assert(sizeof(CtHeader) == 40, "header layout is part of the ABI");
-    const int chunk = n < 32 ? n : 32;   // images per pass: the union-find nodes take 4 bytes per pixel
+    // the union-find nodes of a sub-pass should stay in L2 (16 x 1080p), at least one image
+    const size_t px = (size_t)h * w;
+    int sub = (int)(((size_t)CT_SUB * 1080 * 1920) / px);
+    sub = sub < 1 ? 1 : sub > 64 ? 64 : sub;
+    const int pass = n < CT_PASS ? n : CT_PASS;
+    if (sub > pass) sub = pass;
     void* ws;
-    LLFE_TRY(llfe_workspace(ctx, contours_ws_bytes(chunk, h, w, max_contours, max_points), &ws));
-    for (int i0 = 0; i0 < n; i0 += chunk) {
-        const int m = n - i0 < chunk ? n - i0 : chunk;
-        LLFE_TRY(contours_chunk(ctx, d_mask + (size_t)i0 * h * w, m, h, w, min_area2, d_headers + (size_t)i0 * max_contours * 10,
-                                max_contours, d_points ? d_points + (size_t)i0 * max_points * 2 : nullptr, max_points,
-                                d_counts + (size_t)i0 * 4, ws));
+    LLFE_TRY(llfe_workspace(ctx, contours_ws_bytes(pass, sub, h, w, max_contours, max_points), &ws));
+    for (int i0 = 0; i0 < n; i0 += pass) {
+        const int m = n - i0 < pass ? n - i0 : pass;
+        LLFE_TRY(contours_pass(ctx, d_mask + (size_t)i0 * h * w, m, sub, h, w, min_area2, d_headers + (size_t)i0 * max_contours * 10,
+                               max_contours, d_points ? d_points + (size_t)i0 * max_points * 2 : nullptr, max_points,
+                               d_counts + (size_t)i0 * 4, ws));
     }
     return LLFE_OK;
 }
