@@ -168,6 +168,32 @@ int llfe_resize_linear(llfe_ctx* ctx, const uint8_t* d_src, int n, int sh, int s
 int llfe_resize_lanczos4(llfe_ctx* ctx, const uint8_t* d_src, int n, int sh, int sw, int c, uint8_t* d_dst, int dh,
                          int dw);
 
+/* ---- image decode and Pillow thumbnailing ---------------------------------------------------------------
+ * cv2.imdecode(buf, IMREAD_COLOR) of a non-interlaced PNG (app/services/analyze/utils.py:108-109,
+ * image_processor.py:62-66, :208-211) after the host has inflated the IDAT stream: d_stream holds, per image,
+ * h scanlines of [filter type][llfe_png_rowbytes bytes] and is reconstructed IN PLACE (PNG filters None / Sub / Up /
+ * Average / Paeth), then converted to BGR u8 the way OpenCV configures libpng (16-bit samples -> high byte, gray 1/2/4
+ * bits scaled to 0..255, palette looked up in d_palette = n x 256 x 3 RGB bytes zero-padded, alpha / tRNS dropped).
+ * color_type / bit_depth are IHDR's.  d_status[i] != 0: image i has an invalid filter byte (libpng fails the decode). */
+int64_t llfe_png_rowbytes(int w, int color_type, int bit_depth);
+int llfe_png_reconstruct(llfe_ctx* ctx, uint8_t* d_stream, int n, int h, int w, int color_type, int bit_depth,
+                         const uint8_t* d_palette, uint8_t* d_bgr, int32_t* d_status);
+
+/* Host-only: inflate a zlib stream (RFC 1950 / 1951; the concatenated IDAT payloads of a PNG) into out, at most out_cap
+ * bytes.  Failure (LLFE_E_INVALID) wherever zlib's inflate fails -- invalid code sets or symbols, distance too far back,
+ * truncated input, Adler-32 mismatch; input beyond the point where the output is full is ignored, as libpng does once the
+ * image is complete.  No context, no device. */
+int llfe_inflate_zlib(const uint8_t* in, size_t in_len, uint8_t* out, size_t out_cap, size_t* out_len);
+
+/* Pillow's ImagingReduce(im, (fx, fy), box) and ImagingResample(im, (dw, dh), LANCZOS, box) on u8, c = 1 or 3: the two
+ * steps of `pil_image.thumbnail(size, Image.Resampling.LANCZOS)` (image_processor.py:221-224; reducing_gap = 2.0).
+ * box = host int32[4] / float[4] (left, upper, right, lower) in source pixels.  llfe_pil_reduce writes
+ * ceil((box[3]-box[1])/fy) x ceil((box[2]-box[0])/fx) pixels. */
+int llfe_pil_reduce(llfe_ctx* ctx, const uint8_t* d_src, int n, int sh, int sw, int c, const int32_t* box, int fx, int fy,
+                    uint8_t* d_dst);
+int llfe_pil_resample_lanczos(llfe_ctx* ctx, const uint8_t* d_src, int n, int sh, int sw, int c, const float* box,
+                              uint8_t* d_dst, int dh, int dw);
+
 /* cv2.convertScaleAbs(x, alpha=a1, beta=0) followed by (alpha=a2, beta=0), the
  * pair of calls of ImageTransformer.adjust_brightness_contrast (image_transformer
  * pyc L139-142) fused into one pass.  Pass a2 = 1.0f with single = 1 for one call. */
@@ -407,6 +433,20 @@ int llfe_font_mask_host(llfe_ctx* ctx, const uint8_t* h_bgr, int h, int w, uint8
 int llfe_resize_area_host(llfe_ctx* ctx, const uint8_t* h_src, int sh, int sw, int c, uint8_t* h_dst, int dh, int dw);
 int llfe_resize_linear_host(llfe_ctx* ctx, const uint8_t* h_src, int sh, int sw, int c, uint8_t* h_dst, int dh, int dw);
 int llfe_resize_lanczos4_host(llfe_ctx* ctx, const uint8_t* h_src, int sh, int sw, int c, uint8_t* h_dst, int dh, int dw);
+/* llfe_png_reconstruct on a host stream (h_palette: palette_entries x 3 RGB bytes or NULL); returns LLFE_E_INVALID with
+ * the message "bad adaptive filter value" for a stream libpng would reject. */
+int llfe_png_reconstruct_host(llfe_ctx* ctx, const uint8_t* h_stream, int h, int w, int color_type, int bit_depth,
+                              const uint8_t* h_palette, int palette_entries, uint8_t* h_bgr);
+/* The whole decode of one non-interlaced PNG after the chunk walk: h_idat = the concatenated IDAT payloads; inflated on the
+ * calling thread straight into pinned memory (llfe_inflate_zlib), reconstructed and converted on the device.  A damaged
+ * stream (short, invalid, bad filter byte) returns LLFE_E_INVALID. */
+int llfe_png_decode_host(llfe_ctx* ctx, const uint8_t* h_idat, size_t idat_bytes, int h, int w, int color_type, int bit_depth,
+                         const uint8_t* h_palette, int palette_entries, uint8_t* h_bgr);
+/* Image.resize(size, LANCZOS, box, reducing_gap) below PIL/Image.py's Python layer on a host image: an optional
+ * ImagingReduce by (fx, fy) over reduce_box (fx = fy = 1: none) followed by ImagingResample with `box` (in pixels of the
+ * reduced image) to dh x dw; the intermediate stays on the device. */
+int llfe_pil_resize_lanczos_host(llfe_ctx* ctx, const uint8_t* h_src, int sh, int sw, int c, int fx, int fy,
+                                 const int32_t* reduce_box, const float* box, uint8_t* h_dst, int dh, int dw);
 int llfe_gaussian_blur5_host(llfe_ctx* ctx, const uint8_t* h_src, int h, int w, int c, uint8_t* h_dst);
 int llfe_convert_scale_abs_host(llfe_ctx* ctx, const uint8_t* h_src, size_t count, float a1, float a2, int single,
                                 uint8_t* h_dst);

@@ -13,6 +13,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(HERE, "libllfe.so")
 
 LLFE_OK = 0
+LLFE_E_INVALID = -1
 ERRORS = {-1: "LLFE_E_INVALID", -2: "LLFE_E_CUDA", -3: "LLFE_E_NOMEM", -4: "LLFE_E_UNSUPPORTED", -5: "LLFE_E_NODEVICE"}
 
 
@@ -102,6 +103,14 @@ PROTOTYPES = {
     "llfe_resize_linear_host": (i32, [vp, vp, i32, i32, i32, vp, i32, i32]),
     "llfe_resize_lanczos4_host": (i32, [vp, vp, i32, i32, i32, vp, i32, i32]),
     "llfe_gaussian_blur5_host": (i32, [vp, vp, i32, i32, i32, vp]),
+    "llfe_png_rowbytes": (C.c_int64, [i32, i32, i32]),
+    "llfe_png_reconstruct": (i32, [vp, vp, i32, i32, i32, i32, i32, vp, vp, vp]),
+    "llfe_png_reconstruct_host": (i32, [vp, vp, i32, i32, i32, i32, vp, i32, vp]),
+    "llfe_inflate_zlib": (i32, [vp, sz, vp, sz, C.POINTER(sz)]),
+    "llfe_png_decode_host": (i32, [vp, vp, sz, i32, i32, i32, i32, vp, i32, vp]),
+    "llfe_pil_reduce": (i32, [vp, vp, i32, i32, i32, i32, vp, i32, i32, vp]),
+    "llfe_pil_resample_lanczos": (i32, [vp, vp, i32, i32, i32, i32, vp, vp, i32, i32]),
+    "llfe_pil_resize_lanczos_host": (i32, [vp, vp, i32, i32, i32, i32, i32, vp, vp, vp, i32, i32]),
     "llfe_convert_scale_abs_host": (i32, [vp, vp, sz, f32, f32, i32, vp]),
     "llfe_dominant_colors_host": (i32, [vp, vp, i32, i32, vp, u64, i32, i32, i32, f64, u64, vp, vp, vp, vp, vp, vp, vp]),
 }

@@ -1,0 +1,246 @@
+// PNG scanline reconstruction + conversion to the BGR image `cv2.imdecode(buf, cv2.IMREAD_COLOR)` returns
+// (reference call sites: app/services/analyze/utils.py:108-109, image_processor.py:62-66, :208-211).
+//
+// A PNG's IDAT chunks hold ONE zlib stream; inflated it is h scanlines of [filter type byte][rowbytes filtered bytes].
+// Inflate is a serial bit-level decode of a single stream and stays on the host (zlib); everything after it runs here:
+//
+//   k_png_unfilter   Recon(x) = Filt(x) + predictor(a = left, b = up, c = up-left), bytes `bpp` apart (PNG spec 9.2:
+//                    None, Sub, Up, Average = floor((a + b) / 2), Paeth).  Every byte depends on its left, upper and
+//                    upper-left neighbours, so one image is reconstructed as a skewed wavefront: thread j owns rows
+//                    j, j + T, j + 2T, ... and walks each in 32-byte chunks, one chunk behind the thread that owns the row
+//                    above (rows are padded to at least T chunks, so the first row of the next round never overtakes the
+//                    last row of the previous one); a block barrier per step; the row above is handed down through
+//                    shared memory, and global memory is read / written a whole row-chunk per warp instruction.  One
+//                    CTA per image: a batch fills the SMs.
+//   k_png_to_bgr     pointwise: samples of 1 / 2 / 4 / 8 / 16 bits -> 8 bits the way OpenCV configures libpng for
+//                    IMREAD_COLOR (16 -> the high byte, gray 1/2/4 scaled by 255/85/17, palette looked up, alpha and tRNS
+//                    dropped, gray replicated), RGB -> BGR.
+#include "llfe_common.cuh"
+#include "llfe_device.cuh"
+
+namespace {
+
+constexpr int PNG_CH = 32;   // bytes per wavefront step
+
+__device__ __forceinline__ int paeth(int a, int b, int c) {
+    const int pa = abs(b - c), pb = abs(a - c), pc = abs(a + b - 2 * c);
+    return (pa <= pb && pa <= pc) ? a : (pb <= pc ? b : c);
+}
+
+constexpr int PNG_TW = PNG_CH / 4 + 1;   // words per shared-memory row (odd: a lane per row reads without bank conflicts)
+
+// Global memory is touched a row-chunk at a time by the whole warp (32 contiguous bytes per instruction); a thread per
+// row with byte accesses would spread every load over 32 cache lines.
+template <int BPP>
+__global__ void __launch_bounds__(256) k_png_unfilter(uint8_t* __restrict__ stream, int h, int rowbytes, int chunks, int cpad,
+                                                      int32_t* __restrict__ status) {
+    __shared__ uint32_t tin[256 * PNG_TW];          // filtered bytes of this step, a row per thread
+    __shared__ uint32_t tout[2][256 * PNG_TW];      // reconstructed bytes of this / the previous step (the row above)
+    const size_t stride = (size_t)rowbytes + 1;
+    uint8_t* img = stream + (size_t)blockIdx.x * h * stride;
+    const int T = blockDim.x, j = threadIdx.x, lane = j & 31, wbase = j & ~31;
+    const int rounds = (h + T - 1) / T;
+    const int span = rounds * cpad;
+    const int total = T + span;
+    int win[BPP], cw[BPP];   // the last BPP reconstructed bytes of this row (a) and of the row above (c)
+    int ft = 0;
+    for (int t = 0; t < total; ++t) {
+        const int q = t - j;
+        int r = -1, sc = 0;
+        if (q >= 0 && q < span) {
+            const int m = q / cpad;
+            sc = q - m * cpad;
+            r = j + T * m;
+            if (r >= h || sc >= chunks) r = -1;
+        }
+        // 1. the warp fetches the 32 chunks of its rows
+#pragma unroll 4
+        for (int k = 0; k < 32; ++k) {
+            const int rk = __shfl_sync(0xffffffffu, r, k), sk = __shfl_sync(0xffffffffu, sc, k);
+            if (rk < 0) continue;
+            const int o = sk * PNG_CH + lane;
+            if (o < rowbytes) reinterpret_cast<uint8_t*>(tin + (wbase + k) * PNG_TW)[lane] = img[(size_t)rk * stride + 1 + o];
+        }
+        __syncwarp();
+        uint32_t* mine = tout[t & 1] + j * PNG_TW;
+        if (r >= 0) {
+            const int nb = min(PNG_CH, rowbytes - sc * PNG_CH);
+            const bool has_up = r > 0;
+            if (sc == 0) {
+                ft = img[(size_t)r * stride];
+#pragma unroll
+                for (int k = 0; k < BPP; ++k) win[k] = cw[k] = 0;
+            }
+            int x[PNG_CH], b[PNG_CH];
+#pragma unroll
+            for (int w = 0; w < PNG_CH / 4; ++w) {
+                const uint32_t v = tin[j * PNG_TW + w];
+                x[4 * w] = v & 255, x[4 * w + 1] = (v >> 8) & 255, x[4 * w + 2] = (v >> 16) & 255, x[4 * w + 3] = v >> 24;
+            }
+#pragma unroll
+            for (int i = 0; i < PNG_CH; ++i)
+                if (i >= nb) x[i] = 0;
+            if (!has_up) {
+#pragma unroll
+                for (int i = 0; i < PNG_CH; ++i) b[i] = 0;
+            } else if (j > 0) {
+                // the thread above finished this chunk of its row in the previous step
+                const uint32_t* above = tout[(t & 1) ^ 1] + (j - 1) * PNG_TW;
+#pragma unroll
+                for (int w = 0; w < PNG_CH / 4; ++w) {
+                    const uint32_t v = above[w];
+                    b[4 * w] = v & 255, b[4 * w + 1] = (v >> 8) & 255, b[4 * w + 2] = (v >> 16) & 255, b[4 * w + 3] = v >> 24;
+                }
+            } else {
+                // first thread: the row above belongs to the last thread of the previous round (stored long ago)
+                const uint8_t* up = img + (size_t)(r - 1) * stride + 1 + sc * PNG_CH;
+#pragma unroll
+                for (int i = 0; i < PNG_CH; ++i) b[i] = i < nb ? up[i] : 0;
+            }
+            if (ft == 1) {
+#pragma unroll
+                for (int i = 0; i < PNG_CH; ++i) {
+                    const int a = i < BPP ? win[i] : x[i - BPP];
+                    x[i] = (x[i] + a) & 255;
+                }
+            } else if (ft == 2) {
+#pragma unroll
+                for (int i = 0; i < PNG_CH; ++i) x[i] = (x[i] + b[i]) & 255;
+            } else if (ft == 3) {
+#pragma unroll
+                for (int i = 0; i < PNG_CH; ++i) {
+                    const int a = i < BPP ? win[i] : x[i - BPP];
+                    x[i] = (x[i] + ((a + b[i]) >> 1)) & 255;
+                }
+            } else if (ft == 4) {
+#pragma unroll
+                for (int i = 0; i < PNG_CH; ++i) {
+                    const int a = i < BPP ? win[i] : x[i - BPP];
+                    const int c = i < BPP ? cw[i] : b[i - BPP];
+                    x[i] = (x[i] + paeth(a, b[i], c)) & 255;
+                }
+            } else if (ft != 0) {
+                if (sc == 0) atomicOr(&status[blockIdx.x], 1);   // libpng: "bad adaptive filter value"
+            }
+#pragma unroll
+            for (int w = 0; w < PNG_CH / 4; ++w)
+                mine[w] = (uint32_t)x[4 * w] | ((uint32_t)x[4 * w + 1] << 8) | ((uint32_t)x[4 * w + 2] << 16) | ((uint32_t)x[4 * w + 3] << 24);
+            // the next chunk's left / upper-left neighbours (a full chunk always precedes another chunk)
+#pragma unroll
+            for (int k = 0; k < BPP; ++k) win[k] = x[PNG_CH - BPP + k], cw[k] = b[PNG_CH - BPP + k];
+        }
+        __syncwarp();
+        // 2. the warp stores the 32 reconstructed chunks
+#pragma unroll 4
+        for (int k = 0; k < 32; ++k) {
+            const int rk = __shfl_sync(0xffffffffu, r, k), sk = __shfl_sync(0xffffffffu, sc, k);
+            if (rk < 0) continue;
+            const int o = sk * PNG_CH + lane;
+            if (o < rowbytes)
+                img[(size_t)rk * stride + 1 + o] = reinterpret_cast<const uint8_t*>(tout[t & 1] + (wbase + k) * PNG_TW)[lane];
+        }
+        __syncthreads();
+    }
+}
+
+struct PngFmt {
+    int h, w, rowbytes, color_type, depth;
+};
+
+__device__ __forceinline__ int png_sample(const uint8_t* row, int idx, int depth) {
+    if (depth == 8) return row[idx];
+    if (depth == 16) return row[2 * idx];                      // png_set_strip_16: the high byte
+    const int bit = idx * depth;
+    return (row[bit >> 3] >> (8 - depth - (bit & 7))) & ((1 << depth) - 1);
+}
+
+__global__ void __launch_bounds__(256) k_png_to_bgr(const uint8_t* __restrict__ stream, PngFmt f,
+                                                    const uint8_t* __restrict__ palette, uint8_t* __restrict__ bgr) {
+    const int x = blockIdx.x * 256 + threadIdx.x, y = blockIdx.y, img = blockIdx.z;
+    if (x >= f.w) return;
+    const size_t stride = (size_t)f.rowbytes + 1;
+    const uint8_t* row = stream + ((size_t)img * f.h + y) * stride + 1;
+    int r, g, b;
+    switch (f.color_type) {
+        case 0: {
+            int v = png_sample(row, x, f.depth);
+            if (f.depth < 8) v *= f.depth == 1 ? 255 : f.depth == 2 ? 85 : 17;   // png_set_expand_gray_1_2_4_to_8
+            r = g = b = v;
+            break;
+        }
+        case 2:
+            r = png_sample(row, 3 * x, f.depth), g = png_sample(row, 3 * x + 1, f.depth), b = png_sample(row, 3 * x + 2, f.depth);
+            break;
+        case 3: {
+            const uint8_t* p = palette + (size_t)img * 768 + 3 * png_sample(row, x, f.depth);
+            r = p[0], g = p[1], b = p[2];
+            break;
+        }
+        case 4:
+            r = g = b = png_sample(row, 2 * x, f.depth);
+            break;
+        default:
+            r = png_sample(row, 4 * x, f.depth), g = png_sample(row, 4 * x + 1, f.depth), b = png_sample(row, 4 * x + 2, f.depth);
+            break;
+    }
+    uint8_t* o = bgr + (((size_t)img * f.h + y) * f.w + x) * 3;
+    o[0] = (uint8_t)b, o[1] = (uint8_t)g, o[2] = (uint8_t)r;
+}
+
+}  // namespace
+
+static int png_channels(int color_type) {
+    switch (color_type) {
+        case 0: return 1;
+        case 2: return 3;
+        case 3: return 1;
+        case 4: return 2;
+        case 6: return 4;
+    }
+    return 0;
+}
+
+extern "C" int64_t llfe_png_rowbytes(int w, int color_type, int bit_depth) {
+    const int ch = png_channels(color_type);
+    if (ch == 0 || w <= 0) return -1;
+    const bool ok = color_type == 0   ? (bit_depth == 1 || bit_depth == 2 || bit_depth == 4 || bit_depth == 8 || bit_depth == 16)
+                    : color_type == 3 ? (bit_depth == 1 || bit_depth == 2 || bit_depth == 4 || bit_depth == 8)
+                                      : (bit_depth == 8 || bit_depth == 16);
+    if (!ok) return -1;
+    return ((int64_t)w * ch * bit_depth + 7) / 8;
+}
+
+extern "C" int llfe_png_reconstruct(llfe_ctx* ctx, uint8_t* d_stream, int n, int h, int w, int color_type, int bit_depth,
+                                    const uint8_t* d_palette, uint8_t* d_bgr, int32_t* d_status) {
+    LLFE_ENTER(ctx);
+    LLFE_CHECK_ARG(d_stream != nullptr && d_bgr != nullptr && d_status != nullptr);
+    LLFE_CHECK_ARG(n >= 0 && n <= 65535 && h > 0 && h <= 65535 && w > 0);
+    const int64_t rb = llfe_png_rowbytes(w, color_type, bit_depth);
+    LLFE_CHECK_ARG(rb > 0 && rb < 0x7fffffff);
+    LLFE_CHECK_ARG(color_type != 3 || d_palette != nullptr);
+    if (n == 0) return LLFE_OK;
+    const int rowbytes = (int)rb;
+    const int bpp = (png_channels(color_type) * bit_depth + 7) / 8;   // filter distance in bytes
+    const int chunks = ceil_div(rowbytes, PNG_CH);
+    int T = chunks >= 256 ? 256 : (chunks / 32) * 32;
+    if (T < 32) T = 32;
+    if (T > ((h + 31) / 32) * 32) T = ((h + 31) / 32) * 32;
+    const int cpad = chunks > T ? chunks : T;
+    LLFE_CUDA(cudaMemsetAsync(d_status, 0, (size_t)n * sizeof(int32_t), ctx->stream));
+    LLFE_KERNEL(ctx, "k_png_unfilter");
+    switch (bpp) {
+        case 1: k_png_unfilter<1><<<n, T, 0, ctx->stream>>>(d_stream, h, rowbytes, chunks, cpad, d_status); break;
+        case 2: k_png_unfilter<2><<<n, T, 0, ctx->stream>>>(d_stream, h, rowbytes, chunks, cpad, d_status); break;
+        case 3: k_png_unfilter<3><<<n, T, 0, ctx->stream>>>(d_stream, h, rowbytes, chunks, cpad, d_status); break;
+        case 4: k_png_unfilter<4><<<n, T, 0, ctx->stream>>>(d_stream, h, rowbytes, chunks, cpad, d_status); break;
+        case 6: k_png_unfilter<6><<<n, T, 0, ctx->stream>>>(d_stream, h, rowbytes, chunks, cpad, d_status); break;
+        case 8: k_png_unfilter<8><<<n, T, 0, ctx->stream>>>(d_stream, h, rowbytes, chunks, cpad, d_status); break;
+        default: llfe_set_error("llfe_png_reconstruct: unsupported pixel size %d", bpp); return LLFE_E_UNSUPPORTED;
+    }
+    LLFE_LAUNCHED(ctx);
+    const PngFmt f{h, w, rowbytes, color_type, bit_depth};
+    LLFE_KERNEL(ctx, "k_png_to_bgr");
+    k_png_to_bgr<<<dim3(ceil_div(w, 256), h, n), 256, 0, ctx->stream>>>(d_stream, f, d_palette, d_bgr);
+    LLFE_LAUNCHED(ctx);
+    return LLFE_OK;
+}

@@ -911,6 +911,109 @@ int llfe_gaussian_blur5_host(llfe_ctx* ctx, const uint8_t* h_src, int h, int w, 
     return stage_end(&st, h_dst, b, 0);
 }
 
+int llfe_png_reconstruct_host(llfe_ctx* ctx, const uint8_t* h_stream, int h, int w, int color_type, int bit_depth,
+                              const uint8_t* h_palette, int palette_entries, uint8_t* h_bgr) {
+    LLFE_ENTER(ctx);
+    LLFE_CHECK_ARG(h_stream != nullptr && h_bgr != nullptr && h > 0 && w > 0);
+    const int64_t rb = llfe_png_rowbytes(w, color_type, bit_depth);
+    LLFE_CHECK_ARG(rb > 0 && palette_entries >= 0 && palette_entries <= 256 && (color_type != 3 || h_palette != nullptr));
+    const size_t in = (size_t)h * (rb + 1), out = (size_t)h * w * 3;
+    // staging: the stream in; the image and, behind it, the status word out
+    HostStage st;
+    LLFE_TRY(stage_begin(ctx, h_stream, in, WsCarver::need(out) + 256, &st));
+    uint8_t* d_pal = nullptr;
+    void* ws;
+    LLFE_TRY(llfe_workspace(ctx, 1024, &ws));
+    if (color_type == 3) {
+        uint8_t pal[768];
+        memset(pal, 0, sizeof pal);
+        memcpy(pal, h_palette, (size_t)palette_entries * 3);
+        d_pal = (uint8_t*)ws;
+        LLFE_CUDA(cudaMemcpyAsync(d_pal, pal, 768, cudaMemcpyHostToDevice, ctx->stream));   // pageable: staged before return
+    }
+    int32_t* d_status = (int32_t*)(st.d_out + WsCarver::need(out));
+    LLFE_TRY(llfe_png_reconstruct(ctx, st.d_in, 1, h, w, color_type, bit_depth, d_pal, st.d_out, d_status));
+    LLFE_TRY(stage_end(&st, h_bgr, out, 0));
+    int32_t status = 0;
+    LLFE_CUDA(cudaMemcpy(&status, d_status, sizeof status, cudaMemcpyDeviceToHost));
+    if (status != 0) {
+        llfe_set_error("llfe_png_reconstruct_host: bad adaptive filter value");
+        return LLFE_E_INVALID;
+    }
+    return LLFE_OK;
+}
+
+int llfe_png_decode_host(llfe_ctx* ctx, const uint8_t* h_idat, size_t idat_bytes, int h, int w, int color_type, int bit_depth,
+                         const uint8_t* h_palette, int palette_entries, uint8_t* h_bgr) {
+    LLFE_ENTER(ctx);
+    LLFE_CHECK_ARG(h_idat != nullptr && h_bgr != nullptr && h > 0 && w > 0);
+    const int64_t rb = llfe_png_rowbytes(w, color_type, bit_depth);
+    LLFE_CHECK_ARG(rb > 0 && palette_entries >= 0 && palette_entries <= 256 && (color_type != 3 || h_palette != nullptr));
+    const size_t in = (size_t)h * (rb + 1), out = (size_t)h * w * 3;
+    const size_t a = WsCarver::need(in), b = WsCarver::need(out) + 256;
+    LLFE_TRY(ensure_stage(ctx, a + b, a + b));
+    uint8_t* p_in = (uint8_t*)ctx->pin;
+    uint8_t* d_in = (uint8_t*)ctx->dev_stage;
+    uint8_t* d_out = d_in + a;
+    size_t got = 0;
+    LLFE_TRY(llfe_inflate_zlib(h_idat, idat_bytes, p_in, in, &got));
+    if (got != in) {
+        llfe_set_error("llfe_png_decode_host: not enough image data");
+        return LLFE_E_INVALID;
+    }
+    LLFE_CUDA(cudaMemcpyAsync(d_in, p_in, in, cudaMemcpyHostToDevice, ctx->stream));
+    uint8_t* d_pal = nullptr;
+    if (color_type == 3) {
+        void* ws;
+        LLFE_TRY(llfe_workspace(ctx, 1024, &ws));
+        uint8_t pal[768];
+        memset(pal, 0, sizeof pal);
+        memcpy(pal, h_palette, (size_t)palette_entries * 3);
+        d_pal = (uint8_t*)ws;
+        LLFE_CUDA(cudaMemcpyAsync(d_pal, pal, 768, cudaMemcpyHostToDevice, ctx->stream));   // pageable: staged before return
+    }
+    int32_t* d_status = (int32_t*)(d_out + WsCarver::need(out));
+    LLFE_TRY(llfe_png_reconstruct(ctx, d_in, 1, h, w, color_type, bit_depth, d_pal, d_out, d_status));
+    // the image straight into the caller's buffer, the status word behind it through pinned memory
+    uint8_t* p_out = p_in + a;
+    LLFE_CUDA(cudaMemcpyAsync(p_out, d_out, out + 0, cudaMemcpyDeviceToHost, ctx->stream));
+    LLFE_CUDA(cudaMemcpyAsync(p_out + WsCarver::need(out), d_status, 4, cudaMemcpyDeviceToHost, ctx->stream));
+    LLFE_CUDA(cudaStreamSynchronize(ctx->stream));
+    int32_t status;
+    memcpy(&status, p_out + WsCarver::need(out), 4);
+    if (status != 0) {
+        llfe_set_error("llfe_png_decode_host: bad adaptive filter value");
+        return LLFE_E_INVALID;
+    }
+    memcpy(h_bgr, p_out, out);
+    return LLFE_OK;
+}
+
+int llfe_pil_resize_lanczos_host(llfe_ctx* ctx, const uint8_t* h_src, int sh, int sw, int c, int fx, int fy,
+                                 const int32_t* reduce_box, const float* box, uint8_t* h_dst, int dh, int dw) {
+    LLFE_ENTER(ctx);
+    LLFE_CHECK_ARG(h_src != nullptr && h_dst != nullptr && box != nullptr && sh > 0 && sw > 0 && dh > 0 && dw > 0);
+    LLFE_CHECK_ARG((c == 1 || c == 3) && fx >= 1 && fy >= 1 && ((fx == 1 && fy == 1) || reduce_box != nullptr));
+    const bool reduce = fx > 1 || fy > 1;
+    int rh = sh, rw = sw;
+    if (reduce) {
+        LLFE_CHECK_ARG(reduce_box[0] >= 0 && reduce_box[1] >= 0 && reduce_box[2] > reduce_box[0] &&
+                       reduce_box[3] > reduce_box[1] && reduce_box[2] <= sw && reduce_box[3] <= sh);
+        rw = ceil_div(reduce_box[2] - reduce_box[0], fx);
+        rh = ceil_div(reduce_box[3] - reduce_box[1], fy);
+    }
+    const size_t in = (size_t)sh * sw * c, mid = reduce ? WsCarver::need((size_t)rh * rw * c) : 0, out = (size_t)dh * dw * c;
+    HostStage st;
+    LLFE_TRY(stage_begin(ctx, h_src, in, mid + out, &st));
+    const uint8_t* src = st.d_in;
+    if (reduce) {
+        LLFE_TRY(llfe_pil_reduce(ctx, st.d_in, 1, sh, sw, c, reduce_box, fx, fy, st.d_out));
+        src = st.d_out;
+    }
+    LLFE_TRY(llfe_pil_resample_lanczos(ctx, src, 1, rh, rw, c, box, st.d_out + mid, dh, dw));
+    return stage_end(&st, h_dst, out, mid);
+}
+
 int llfe_resize_area_host(llfe_ctx* ctx, const uint8_t* h_src, int sh, int sw, int c, uint8_t* h_dst, int dh, int dw) {
     LLFE_ENTER(ctx);
     LLFE_CHECK_ARG(ctx != nullptr && h_src != nullptr && h_dst != nullptr && sh > 0 && sw > 0 && dh > 0 && dw > 0);

@@ -262,6 +262,63 @@ class Engine:
         self.ctx.call("llfe_resize_lanczos4", x, n, sh, sw, c, out, int(dh), int(dw))
         return out[0] if single else out
 
+    # -- decode / Pillow thumbnail --------------------------------------
+    def png_reconstruct(self, streams: torch.Tensor, h: int, w: int, color_type: int, bit_depth: int,
+                        palettes: torch.Tensor | None = None):
+        """Inflated IDAT streams (n, h * (1 + rowbytes)) uint8, reconstructed IN PLACE -> (BGR images (n,h,w,3),
+        status int32 (n,): non-zero = invalid filter byte).  palettes: (n, 256, 3) RGB for colour type 3."""
+        rb = int(self.ctx.lib.llfe_png_rowbytes(int(w), int(color_type), int(bit_depth)))
+        if rb <= 0:
+            raise ValueError("invalid PNG colour type / bit depth")
+        if streams.dtype != torch.uint8 or not streams.is_cuda or streams.dim() != 2 or streams.shape[1] != h * (rb + 1) \
+                or not streams.is_contiguous():
+            raise ValueError(f"expected a contiguous CUDA uint8 tensor (n, {h * (rb + 1)})")
+        n = streams.shape[0]
+        if color_type == 3:
+            if palettes is None or palettes.dtype != torch.uint8 or tuple(palettes.shape) != (n, 256, 3):
+                raise ValueError("colour type 3 needs palettes (n, 256, 3) uint8")
+            palettes = palettes.contiguous()
+        out = self._empty((n, h, w, 3))
+        status = self._empty((n,), torch.int32)
+        self._bind()
+        self.ctx.call("llfe_png_reconstruct", streams, n, int(h), int(w), int(color_type), int(bit_depth), palettes, out, status)
+        return out, status
+
+    def pil_reduce(self, src: torch.Tensor, fx: int, fy: int, box=None) -> torch.Tensor:
+        """Pillow's Image.reduce((fx, fy), box) on uint8 (1 or 3 channels)."""
+        import numpy as np
+
+        if src.dim() >= 3 and src.shape[-1] == 3:
+            x, single = _batch(src, 3)
+            n, sh, sw, c = x.shape
+        else:
+            x, single = _batch(src, None)
+            n, sh, sw = x.shape
+            c = 1
+        b = np.asarray(box if box is not None else (0, 0, sw, sh), np.int32)
+        dh, dw = -(-int(b[3] - b[1]) // fy), -(-int(b[2] - b[0]) // fx)
+        out = self._empty((n, dh, dw, 3) if c == 3 else (n, dh, dw))
+        self._bind()
+        self.ctx.call("llfe_pil_reduce", x, n, sh, sw, c, b, int(fx), int(fy), out)
+        return out[0] if single else out
+
+    def pil_resample_lanczos(self, src: torch.Tensor, dh: int, dw: int, box=None) -> torch.Tensor:
+        """Pillow's im.resize((dw, dh), LANCZOS, box, reducing_gap=None) on uint8 (1 or 3 channels)."""
+        import numpy as np
+
+        if src.dim() >= 3 and src.shape[-1] == 3:
+            x, single = _batch(src, 3)
+            n, sh, sw, c = x.shape
+        else:
+            x, single = _batch(src, None)
+            n, sh, sw = x.shape
+            c = 1
+        b = np.asarray(box if box is not None else (0, 0, sw, sh), np.float32)
+        out = self._empty((n, dh, dw, 3) if c == 3 else (n, dh, dw))
+        self._bind()
+        self.ctx.call("llfe_pil_resample_lanczos", x, n, sh, sw, c, b, out, int(dh), int(dw))
+        return out[0] if single else out
+
     # -- palette ------------------------------------------------------------------
     def unique_colors(self, bgr: torch.Tensor, noise: torch.Tensor | None = None, seed: int = 0,
                       max_unique: int = 1 << 16, with_counts: bool = False, first_image: int = 0):

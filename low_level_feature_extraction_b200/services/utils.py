@@ -1,6 +1,7 @@
 """Drop-in for the hot-path part of app/services/analyze/utils.py:
-`validate_and_preprocess_image` (:90-152).  Decode stays host libpng/libjpeg via
-cv2.imdecode (sequential entropy decoding); the `auto`
+`validate_and_preprocess_image` (:90-152).  PNG input: the host inflates the IDAT stream, scanline
+reconstruction and the conversion to BGR run on the GPU (services/png.py, csrc/k_png.cu); every other
+format goes through cv2.imdecode like the reference (sequential entropy decoding).  The `auto`
 INTER_AREA down-scale -- the mode the endpoint hard-codes (endpoints/analyze.py:90) --
 and the `performance` (INTER_LINEAR) and `high_quality` (INTER_LANCZOS4) down-scales run on the GPU.  Download and response assembly (:31-87, :155-214) are network /
 HTTP glue outside the path."""
@@ -13,6 +14,7 @@ import cv2
 import numpy as np
 
 from .image_processor import resize_area, resize_lanczos4, resize_linear
+from .png import imdecode_color
 
 logger = logging.getLogger(__name__)
 
@@ -40,7 +42,7 @@ class PreprocessingMode(str, Enum):
 async def validate_and_preprocess_image(image_bytes: bytes, request_id: str, preprocessing: str) -> np.ndarray:
     """bytes -> (H, W, 3) uint8 BGR; any failure -> HTTPException(400)."""
     try:
-        image = cv2.imdecode(np.frombuffer(image_bytes, dtype=np.uint8), cv2.IMREAD_COLOR)
+        image = imdecode_color(image_bytes)                                            # utils.py:108-109
         if image is None:
             raise HTTPException(status_code=_BAD_REQUEST,
                                 detail="Failed to decode image. The file may be corrupted or in an unsupported format.")

@@ -28,10 +28,12 @@ class FakeBatcher:
 
 
 def png(h=40, w=60):
+    """An upload that decodes without a GPU: PNG bytes go through the device decoder (services/png.py, covered by
+    tests/test_gpu_decode.py), every other format through cv2.imdecode -- so the wiring tests here upload BMP."""
     import cv2
 
     img = np.random.default_rng(0).integers(0, 256, (h, w, 3), dtype=np.uint8)
-    ok, buf = cv2.imencode(".png", img)
+    ok, buf = cv2.imencode(".bmp", img)
     assert ok
     return buf.tobytes()
 
