@@ -1,11 +1,13 @@
 // Host side of the PNG decode row: RFC 1950 / 1951 inflate of the IDAT stream.
 //
 // A deflate stream is one serial bit-level decode (every code's position depends on all codes before it), so it runs on a
-// host core; what the host can do is run it fast.  cv2.imdecode spends ~80 % of a 1080p PNG decode inside zlib 1.2.11's
-// inflate (32-bit bit buffer refilled a byte at a time, one table walk per symbol).  This decoder keeps a 64-bit bit buffer
-// refilled with one unaligned load, resolves most codes with a single look-up in an 11-bit (literal / length) or 8-bit
-// (distance) root table, decodes up to three literals per refill and copies matches eight bytes at a time.  It writes
-// straight into the pinned staging buffer of the context, from where the scanlines go to the device (k_png.cu).
+// host core.  cv2.imdecode spends ~80 % of a 1080p PNG decode inside zlib 1.2.11's inflate.  This decoder keeps a 64-bit
+// bit buffer refilled with one unaligned load, resolves most codes with a single look-up in an 11-bit (literal / length)
+// or 8-bit (distance) root table, decodes up to three literals per refill and copies matches eight bytes at a time; on
+// the noisy design images of the benchmark (one literal per byte) it is bound by the look-up -> shift -> look-up
+// dependency chain and runs 1.1-1.4x zlib (measured: 30 vs 42 ms per 1080p stream in the build container, 24.7 vs
+// 27.7 ms on the GPU box); long-match data gains more.  Its other job is to write straight into the pinned staging
+// buffer of the context, from where the scanlines go to the device (k_png.cu) without a host copy.
 //
 // Error behaviour follows zlib's inflate: over-subscribed or incomplete code sets, a missing end-of-block code, invalid
 // symbols, distances beyond the start of the output, a stored block whose LEN / NLEN disagree, a truncated stream and an

@@ -7,11 +7,10 @@
 //   k_png_unfilter   Recon(x) = Filt(x) + predictor(a = left, b = up, c = up-left), bytes `bpp` apart (PNG spec 9.2:
 //                    None, Sub, Up, Average = floor((a + b) / 2), Paeth).  Every byte depends on its left, upper and
 //                    upper-left neighbours, so one image is reconstructed as a skewed wavefront: thread j owns rows
-//                    j, j + T, j + 2T, ... and walks each in 32-byte chunks, one chunk behind the thread that owns the row
+//                    j, j + T, j + 2T, ... and walks each in 16-byte chunks, one chunk behind the thread that owns the row
 //                    above (rows are padded to at least T chunks, so the first row of the next round never overtakes the
-//                    last row of the previous one); a block barrier per step; the row above is handed down through
-//                    shared memory, and global memory is read / written a whole row-chunk per warp instruction.  One
-//                    CTA per image: a batch fills the SMs.
+//                    last row of the previous one); a block barrier per step.  One CTA per image: a batch fills the
+//                    SMs (148 x 1080p in 3.6 ms); ONE image is bound by the 2 056 dependent steps (3.4 ms at 1080p).
 //   k_png_to_bgr     pointwise: samples of 1 / 2 / 4 / 8 / 16 bits -> 8 bits the way OpenCV configures libpng for
 //                    IMREAD_COLOR (16 -> the high byte, gray 1/2/4 scaled by 255/85/17, palette looked up, alpha and tRNS
 //                    dropped, gray replicated), RGB -> BGR.
@@ -20,54 +19,79 @@
 
 namespace {
 
-constexpr int PNG_CH = 32;   // bytes per wavefront step
+constexpr int PNG_CH = 16;               // bytes of a row per wavefront step
+constexpr int PNG_TW = PNG_CH / 4 + 1;   // words per shared-memory row (odd: a lane per row reads without bank conflicts)
+constexpr int PNG_CARRY = 1536;          // slots of the last-thread -> first-thread delay line
 
 __device__ __forceinline__ int paeth(int a, int b, int c) {
     const int pa = abs(b - c), pb = abs(a - c), pc = abs(a + b - 2 * c);
     return (pa <= pb && pa <= pc) ? a : (pb <= pc ? b : c);
 }
 
-constexpr int PNG_TW = PNG_CH / 4 + 1;   // words per shared-memory row (odd: a lane per row reads without bank conflicts)
+// Position of a thread in its schedule: thread j starts row j at step j, walks it a chunk per step, idles until step
+// `cpad` of the row (so that the thread above stays ahead), then continues with row j + T.
+struct PngPos {
+    int r, sc;
+    __device__ __forceinline__ void advance(int T, int cpad) {
+        if (++sc == cpad) sc = 0, r += T;
+    }
+    __device__ __forceinline__ bool active(int h, int chunks) const { return sc >= 0 && sc < chunks && r < h; }
+};
 
-// Global memory is touched a row-chunk at a time by the whole warp (32 contiguous bytes per instruction); a thread per
-// row with byte accesses would spread every load over 32 cache lines.
+// The latencies are kept off the per-step critical path (a block barrier closes every step, so the slowest thread
+// sets the pace): global memory is touched by the whole warp, 2 row-chunks per instruction; the chunks and the filter
+// byte of step t + 1 are fetched into registers while step t is reconstructed; the row above comes through shared
+// memory -- from the neighbouring thread's previous step, or, for the first thread, from a delay line the last thread
+// feeds (its row above was finished cpad - T + 1 steps earlier).
 template <int BPP>
 __global__ void __launch_bounds__(256) k_png_unfilter(uint8_t* __restrict__ stream, int h, int rowbytes, int chunks, int cpad,
-                                                      int32_t* __restrict__ status) {
+                                                      int use_carry, int32_t* __restrict__ status) {
     __shared__ uint32_t tin[256 * PNG_TW];          // filtered bytes of this step, a row per thread
     __shared__ uint32_t tout[2][256 * PNG_TW];      // reconstructed bytes of this / the previous step (the row above)
-    const size_t stride = (size_t)rowbytes + 1;
+    __shared__ uint4 carry[PNG_CARRY];
+    const uint32_t stride = (uint32_t)rowbytes + 1u;
     uint8_t* img = stream + (size_t)blockIdx.x * h * stride;
     const int T = blockDim.x, j = threadIdx.x, lane = j & 31, wbase = j & ~31;
-    const int rounds = (h + T - 1) / T;
-    const int span = rounds * cpad;
-    const int total = T + span;
+    const int total = T + ((h + T - 1) / T) * cpad;
+    const int d1 = cpad - T + 2;                    // delay-line length
+    const int bi = lane & 15, half = lane >> 4;
     int win[BPP], cw[BPP];   // the last BPP reconstructed bytes of this row (a) and of the row above (c)
-    int ft = 0;
+#pragma unroll
+    for (int k = 0; k < BPP; ++k) win[k] = cw[k] = 0;
+    int ft = 0, ftn = 0, wr = 0;
+    uint32_t vn[16];         // byte `bi` of the chunks of rows 2i + half of this warp, for the NEXT step
+    PngPos cur{j, -j};
+    auto fetch = [&](const PngPos& p) {
+        const bool act = p.active(h, chunks);
+        const uint32_t off = act ? (uint32_t)p.r * stride + 1u + (uint32_t)p.sc * PNG_CH : 0u;
+        const int nb = act ? min(PNG_CH, rowbytes - p.sc * PNG_CH) : 0;
+#pragma unroll
+        for (int i = 0; i < 16; ++i) {
+            const uint32_t ok = __shfl_sync(0xffffffffu, off, 2 * i + half);
+            const int nk = __shfl_sync(0xffffffffu, nb, 2 * i + half);
+            vn[i] = bi < nk ? img[ok + bi] : 0u;
+        }
+        if (act && p.sc == 0) ftn = img[(uint32_t)p.r * stride];
+    };
+    auto stage = [&]() {
+#pragma unroll
+        for (int i = 0; i < 16; ++i) reinterpret_cast<uint8_t*>(tin + (wbase + 2 * i + half) * PNG_TW)[bi] = (uint8_t)vn[i];
+    };
+    fetch(cur);
+    stage();
+    __syncwarp();
     for (int t = 0; t < total; ++t) {
-        const int q = t - j;
-        int r = -1, sc = 0;
-        if (q >= 0 && q < span) {
-            const int m = q / cpad;
-            sc = q - m * cpad;
-            r = j + T * m;
-            if (r >= h || sc >= chunks) r = -1;
-        }
-        // 1. the warp fetches the 32 chunks of its rows
-#pragma unroll 4
-        for (int k = 0; k < 32; ++k) {
-            const int rk = __shfl_sync(0xffffffffu, r, k), sk = __shfl_sync(0xffffffffu, sc, k);
-            if (rk < 0) continue;
-            const int o = sk * PNG_CH + lane;
-            if (o < rowbytes) reinterpret_cast<uint8_t*>(tin + (wbase + k) * PNG_TW)[lane] = img[(size_t)rk * stride + 1 + o];
-        }
-        __syncwarp();
+        PngPos nxt = cur;
+        nxt.advance(T, cpad);
+        const bool act = cur.active(h, chunks);
+        if (act && cur.sc == 0) ft = ftn;
+        fetch(nxt);
         uint32_t* mine = tout[t & 1] + j * PNG_TW;
-        if (r >= 0) {
+        const int rd = wr + 1 == d1 ? 0 : wr + 1;
+        if (act) {
+            const int r = cur.r, sc = cur.sc;
             const int nb = min(PNG_CH, rowbytes - sc * PNG_CH);
-            const bool has_up = r > 0;
             if (sc == 0) {
-                ft = img[(size_t)r * stride];
 #pragma unroll
                 for (int k = 0; k < BPP; ++k) win[k] = cw[k] = 0;
             }
@@ -77,23 +101,30 @@ __global__ void __launch_bounds__(256) k_png_unfilter(uint8_t* __restrict__ stre
                 const uint32_t v = tin[j * PNG_TW + w];
                 x[4 * w] = v & 255, x[4 * w + 1] = (v >> 8) & 255, x[4 * w + 2] = (v >> 16) & 255, x[4 * w + 3] = v >> 24;
             }
-#pragma unroll
-            for (int i = 0; i < PNG_CH; ++i)
-                if (i >= nb) x[i] = 0;
-            if (!has_up) {
+            if (r == 0) {
 #pragma unroll
                 for (int i = 0; i < PNG_CH; ++i) b[i] = 0;
-            } else if (j > 0) {
-                // the thread above finished this chunk of its row in the previous step
-                const uint32_t* above = tout[(t & 1) ^ 1] + (j - 1) * PNG_TW;
+            } else if (j > 0 || use_carry) {
+                // the thread above finished this chunk of its row in the previous step; for the first thread that
+                // was the last thread, d1 - 1 steps ago
+                uint32_t v4[4];
+                if (j > 0) {
+                    const uint32_t* above = tout[(t & 1) ^ 1] + (j - 1) * PNG_TW;
 #pragma unroll
-                for (int w = 0; w < PNG_CH / 4; ++w) {
-                    const uint32_t v = above[w];
+                    for (int w = 0; w < 4; ++w) v4[w] = above[w];
+                } else {
+                    const uint4 c4 = carry[rd];
+                    v4[0] = c4.x, v4[1] = c4.y, v4[2] = c4.z, v4[3] = c4.w;
+                }
+#pragma unroll
+                for (int w = 0; w < 4; ++w) {
+                    const uint32_t v = v4[w];
                     b[4 * w] = v & 255, b[4 * w + 1] = (v >> 8) & 255, b[4 * w + 2] = (v >> 16) & 255, b[4 * w + 3] = v >> 24;
                 }
             } else {
-                // first thread: the row above belongs to the last thread of the previous round (stored long ago)
-                const uint8_t* up = img + (size_t)(r - 1) * stride + 1 + sc * PNG_CH;
+                // rows too long for the delay line: the first thread reads the row above back from the stream (it was
+                // stored at least one step ago, because rows are padded to cpad >= T chunks)
+                const uint8_t* up = img + (uint32_t)(r - 1) * stride + 1u + (uint32_t)sc * PNG_CH;
 #pragma unroll
                 for (int i = 0; i < PNG_CH; ++i) b[i] = i < nb ? up[i] : 0;
             }
@@ -122,23 +153,32 @@ __global__ void __launch_bounds__(256) k_png_unfilter(uint8_t* __restrict__ stre
             } else if (ft != 0) {
                 if (sc == 0) atomicOr(&status[blockIdx.x], 1);   // libpng: "bad adaptive filter value"
             }
-#pragma unroll
-            for (int w = 0; w < PNG_CH / 4; ++w)
-                mine[w] = (uint32_t)x[4 * w] | ((uint32_t)x[4 * w + 1] << 8) | ((uint32_t)x[4 * w + 2] << 16) | ((uint32_t)x[4 * w + 3] << 24);
+            uint4 o;
+            o.x = (uint32_t)x[0] | ((uint32_t)x[1] << 8) | ((uint32_t)x[2] << 16) | ((uint32_t)x[3] << 24);
+            o.y = (uint32_t)x[4] | ((uint32_t)x[5] << 8) | ((uint32_t)x[6] << 16) | ((uint32_t)x[7] << 24);
+            o.z = (uint32_t)x[8] | ((uint32_t)x[9] << 8) | ((uint32_t)x[10] << 16) | ((uint32_t)x[11] << 24);
+            o.w = (uint32_t)x[12] | ((uint32_t)x[13] << 8) | ((uint32_t)x[14] << 16) | ((uint32_t)x[15] << 24);
+            mine[0] = o.x, mine[1] = o.y, mine[2] = o.z, mine[3] = o.w;
+            if (j == T - 1 && use_carry) carry[wr] = o;
             // the next chunk's left / upper-left neighbours (a full chunk always precedes another chunk)
 #pragma unroll
             for (int k = 0; k < BPP; ++k) win[k] = x[PNG_CH - BPP + k], cw[k] = b[PNG_CH - BPP + k];
         }
         __syncwarp();
-        // 2. the warp stores the 32 reconstructed chunks
-#pragma unroll 4
-        for (int k = 0; k < 32; ++k) {
-            const int rk = __shfl_sync(0xffffffffu, r, k), sk = __shfl_sync(0xffffffffu, sc, k);
-            if (rk < 0) continue;
-            const int o = sk * PNG_CH + lane;
-            if (o < rowbytes)
-                img[(size_t)rk * stride + 1 + o] = reinterpret_cast<const uint8_t*>(tout[t & 1] + (wbase + k) * PNG_TW)[lane];
+        // the warp stores its reconstructed chunks, two rows per instruction
+        {
+            const uint32_t off = act ? (uint32_t)cur.r * stride + 1u + (uint32_t)cur.sc * PNG_CH : 0u;
+            const int nb = act ? min(PNG_CH, rowbytes - cur.sc * PNG_CH) : 0;
+#pragma unroll
+            for (int i = 0; i < 16; ++i) {
+                const uint32_t ok = __shfl_sync(0xffffffffu, off, 2 * i + half);
+                const int nk = __shfl_sync(0xffffffffu, nb, 2 * i + half);
+                if (bi < nk) img[ok + bi] = reinterpret_cast<const uint8_t*>(tout[t & 1] + (wbase + 2 * i + half) * PNG_TW)[bi];
+            }
         }
+        stage();          // the prefetched chunks become the next step's input (tin rows are private to the warp)
+        wr = rd;
+        cur = nxt;
         __syncthreads();
     }
 }
@@ -226,15 +266,17 @@ extern "C" int llfe_png_reconstruct(llfe_ctx* ctx, uint8_t* d_stream, int n, int
     if (T < 32) T = 32;
     if (T > ((h + 31) / 32) * 32) T = ((h + 31) / 32) * 32;
     const int cpad = chunks > T ? chunks : T;
+    const int use_carry = cpad - T + 2 <= PNG_CARRY;
+    LLFE_CHECK_ARG((uint64_t)h * ((uint64_t)rowbytes + 1) < 0xffffffffull);   // 32-bit offsets inside one image
     LLFE_CUDA(cudaMemsetAsync(d_status, 0, (size_t)n * sizeof(int32_t), ctx->stream));
     LLFE_KERNEL(ctx, "k_png_unfilter");
     switch (bpp) {
-        case 1: k_png_unfilter<1><<<n, T, 0, ctx->stream>>>(d_stream, h, rowbytes, chunks, cpad, d_status); break;
-        case 2: k_png_unfilter<2><<<n, T, 0, ctx->stream>>>(d_stream, h, rowbytes, chunks, cpad, d_status); break;
-        case 3: k_png_unfilter<3><<<n, T, 0, ctx->stream>>>(d_stream, h, rowbytes, chunks, cpad, d_status); break;
-        case 4: k_png_unfilter<4><<<n, T, 0, ctx->stream>>>(d_stream, h, rowbytes, chunks, cpad, d_status); break;
-        case 6: k_png_unfilter<6><<<n, T, 0, ctx->stream>>>(d_stream, h, rowbytes, chunks, cpad, d_status); break;
-        case 8: k_png_unfilter<8><<<n, T, 0, ctx->stream>>>(d_stream, h, rowbytes, chunks, cpad, d_status); break;
+        case 1: k_png_unfilter<1><<<n, T, 0, ctx->stream>>>(d_stream, h, rowbytes, chunks, cpad, use_carry, d_status); break;
+        case 2: k_png_unfilter<2><<<n, T, 0, ctx->stream>>>(d_stream, h, rowbytes, chunks, cpad, use_carry, d_status); break;
+        case 3: k_png_unfilter<3><<<n, T, 0, ctx->stream>>>(d_stream, h, rowbytes, chunks, cpad, use_carry, d_status); break;
+        case 4: k_png_unfilter<4><<<n, T, 0, ctx->stream>>>(d_stream, h, rowbytes, chunks, cpad, use_carry, d_status); break;
+        case 6: k_png_unfilter<6><<<n, T, 0, ctx->stream>>>(d_stream, h, rowbytes, chunks, cpad, use_carry, d_status); break;
+        case 8: k_png_unfilter<8><<<n, T, 0, ctx->stream>>>(d_stream, h, rowbytes, chunks, cpad, use_carry, d_status); break;
         default: llfe_set_error("llfe_png_reconstruct: unsupported pixel size %d", bpp); return LLFE_E_UNSUPPORTED;
     }
     LLFE_LAUNCHED(ctx);

@@ -3,7 +3,7 @@
 
 A PNG is a chunk container around ONE zlib stream.  The host walks the chunks (CRC-checked, like libpng does for the
 critical ones) and inflates the IDAT stream -- a serial bit-level decode of a single stream, so it stays on a host
-core, with the library's own inflate (csrc/h_inflate.cu, ~3x zlib 1.2.11) writing straight into pinned memory;
+core, with the library's own inflate (csrc/h_inflate.cu, 1.1-1.4x zlib 1.2.11) writing straight into pinned memory;
 `inflate_many` spreads a batch over threads (the call releases the GIL).  Scanline reconstruction (the five
 PNG filters) and the conversion OpenCV asks libpng for (palette / gray expansion, 16 -> 8 bits, alpha dropped,
 RGB -> BGR) run in `llfe_png_reconstruct*` (csrc/k_png.cu).
