@@ -32,7 +32,7 @@ constexpr int FT_STD = 512;    // two CTAs per SM (lists of up to pts2 colours) 
 constexpr int FT_LONG = 1024;  // one CTA per SM with all of its shared memory: twice the warps keep the SM as busy
 constexpr int QROWS = 8;    // rows (of 32 points) per bounds-test / drain block
 // static shared memory (centres, totals, queues, row totals, reduction scratch), upper bounds per variant
-constexpr size_t STATIC_SMEM_BOUND = 16 * 1024, STATIC_SMEM_BOUND_LONG = 20 * 1024;
+constexpr size_t STATIC_SMEM_BOUND = 18 * 1024, STATIC_SMEM_BOUND_LONG = 25 * 1024;
 constexpr int RMAX_POINTS = 112 * 32 * 16;   // most points a shared-memory list may have (row-total table size)
 constexpr unsigned FULL = 0xffffffffu;
 
@@ -267,6 +267,10 @@ __global__ void __launch_bounds__(FT, FT == FT_LONG ? 1 : 2) k_kmeans_fast(KmPar
     __shared__ uint32_t s_dq[KMAX];
     __shared__ uint4 s_tab[KMAX];           // per label: {own centre's drift, largest drift of another centre, half gap, -}
     __shared__ uint8_t s_queue[FW][QROWS * 32];   // per-warp queue of points whose bounds failed
+    // per-warp ring of points that need the exact search (row of the warp << 5 | lane: 12 bits for lists in shared
+    // memory, more for the global-scratch variant)
+    typedef typename std::conditional<IN_SMEM, uint16_t, uint32_t>::type Q2;
+    __shared__ Q2 s_queue2[FW][64];
     __shared__ uint32_t s_rowsum[IN_SMEM ? FW : 1][IN_SMEM ? RMAX : 1];
     __shared__ unsigned long long s_wtot[FW];
     __shared__ unsigned long long s_red3[FW][3];
@@ -554,9 +558,70 @@ __global__ void __launch_bounds__(FT, FT == FT_LONG ? 1 : 2) k_kmeans_fast(KmPar
             // Two phases per block of QROWS rows so that the expensive path runs on full warps: (A) every
             // lane tests the bounds of its points and the failing ones are compacted into the warp's
             // queue; (B) the queue is drained 32 points at a time.
+            Q2* q2 = s_queue2[warp];
+            int q2n = 0, q2head = 0;
+            // (B2) cv2's exact search for one point (rl = row of this warp << 5 | lane)
+            auto search_point = [&](int rl) {
+                const int i = ((rl >> 5) * FW + warp) * 32 + (rl & 31);
+                const uint32_t a = F::label(aux[i]);
+                const uint32_t key = key_at(i);
+                float fr, fg, fb;
+                unpackf(key, fr, fg, fb);
+                if (P.dbg) atomicAdd(&s_cnt[1], 1u);
+                float bd = fdist4(fr, fg, fb, s_c[0]), sd = 3e38f;
+                int bl = 0;
+#pragma unroll
+                for (int k = 1; k < KC; ++k) {
+                    if (k < K) {
+                        float d = fdist4(fr, fg, fb, s_c[k]);
+                        if (d < bd) {
+                            sd = bd;
+                            bd = d;
+                            bl = k;
+                        } else {
+                            sd = fminf(sd, d);
+                        }
+                    }
+                }
+                aux[i] = F::pack((uint32_t)bl, F::q_up(__fsqrt_rn(bd)), F::q_dn(__fsqrt_rn(sd)));
+                if (P.dbg && (uint32_t)bl != a) atomicAdd(&s_cnt[2], 1u);
+                if ((uint32_t)bl != a) {
+                    const int cr = (int)(key >> 16), cg = (int)((key >> 8) & 255u), cb = (int)(key & 255u);
+                    atomicAdd(&s_sum[a][0], -cr);
+                    atomicAdd(&s_sum[a][1], -cg);
+                    atomicAdd(&s_sum[a][2], -cb);
+                    atomicAdd(&s_sum[a][3], -1);
+                    atomicAdd(&s_sum[bl][0], cr);
+                    atomicAdd(&s_sum[bl][1], cg);
+                    atomicAdd(&s_sum[bl][2], cb);
+                    atomicAdd(&s_sum[bl][3], 1);
+                }
+            };
             for (int rb0 = 0; rb0 < rows; rb0 += QROWS) {
                 const int rb1 = min(rows, rb0 + QROWS);
                 int qn = 0;
+                if (rb0 + QROWS <= r_full) {
+                    // the whole block lies inside the list (warp-uniform): the eight state words are loaded first, the
+                    // row addresses are compile-time offsets from one pointer, no validity tests
+                    uint32_t* const ap = aux + (rb0 * FW + warp) * 32 + lane;
+                    const uint32_t below = (1u << lane) - 1u;
+                    uint32_t xs[QROWS];
+#pragma unroll
+                    for (int u = 0; u < QROWS; ++u) xs[u] = ap[u * FW * 32];
+#pragma unroll
+                    for (int u = 0; u < QROWS; ++u) {
+                        const uint32_t x = xs[u];
+                        const uint32_t a = F::label(x);
+                        const uint4 t = s_tab[a];
+                        const uint32_t ub = min(F::UMAX, F::ub(x) + t.x);
+                        const uint32_t lb = max(F::lb(x), t.y) - t.y;
+                        ap[u * FW * 32] = F::pack(a, ub, lb);
+                        const bool need = ub >= max(lb, t.z);
+                        const uint32_t bal = __ballot_sync(FULL, need);
+                        if (need) q[qn + __popc(bal & below)] = (uint8_t)(u * 32 + lane);
+                        qn += __popc(bal);
+                    }
+                } else
                 for (int r = rb0; r < rb1; ++r) {
                     const int i = (r * FW + warp) * 32 + lane;
                     bool need = false;
@@ -575,52 +640,40 @@ __global__ void __launch_bounds__(FT, FT == FT_LONG ? 1 : 2) k_kmeans_fast(KmPar
                 }
                 if (P.dbg && lane == 0) atomicAdd(&s_cnt[0], (unsigned)qn);
                 __syncwarp();
-                for (int j = lane; j < qn; j += 32) {
-                    const int qe = (int)q[j];
-                    const int i = ((rb0 + (qe >> 5)) * FW + warp) * 32 + (qe & 31);
-                    const uint32_t x = aux[i];
-                    const uint32_t a = F::label(x), lb = F::lb(x);
-                    const uint32_t bound = max(lb, s_tab[a].z);
-                    const uint32_t key = key_at(i);
-                    float fr, fg, fb;
-                    unpackf(key, fr, fg, fb);
-                    const uint32_t ub = F::q_up(__fsqrt_rn(fdist4(fr, fg, fb, s_c[a])));  // tighten
-                    if (ub < bound) {
-                        aux[i] = F::pack(a, ub, lb);
-                        continue;
+                // (B1) tighten the upper bound of the queued points with one exact distance to their own centre; the
+                // ones that still fail go to a second queue that is shared by all blocks of this warp's rows, so that
+                // the full search (B2) runs on whole warps: per block it would find ~6 of 32 lanes busy
+                for (int j0 = 0; j0 < qn; j0 += 32) {   // warp-uniform trip count
+                    const int j = j0 + lane;
+                    bool full = false;
+                    int rl = 0;
+                    if (j < qn) {
+                        const int qe = (int)q[j];
+                        rl = ((rb0 + (qe >> 5)) << 5) | (qe & 31);          // row of this warp, lane
+                        const int i = ((rb0 + (qe >> 5)) * FW + warp) * 32 + (qe & 31);
+                        const uint32_t x = aux[i];
+                        const uint32_t a = F::label(x), lb = F::lb(x);
+                        const uint32_t bound = max(lb, s_tab[a].z);
+                        float fr, fg, fb;
+                        unpackf(key_at(i), fr, fg, fb);
+                        const uint32_t ub = F::q_up(__fsqrt_rn(fdist4(fr, fg, fb, s_c[a])));
+                        if (ub < bound) aux[i] = F::pack(a, ub, lb);
+                        else full = true;
                     }
-                    if (P.dbg) atomicAdd(&s_cnt[1], 1u);
-                    float bd = fdist4(fr, fg, fb, s_c[0]), sd = 3e38f;
-                    int bl = 0;
-#pragma unroll
-                    for (int k = 1; k < KC; ++k) {
-                        if (k < K) {
-                            float d = fdist4(fr, fg, fb, s_c[k]);
-                            if (d < bd) {
-                                sd = bd;
-                                bd = d;
-                                bl = k;
-                            } else {
-                                sd = fminf(sd, d);
-                            }
-                        }
-                    }
-                    aux[i] = F::pack((uint32_t)bl, F::q_up(__fsqrt_rn(bd)), F::q_dn(__fsqrt_rn(sd)));
-                    if (P.dbg && (uint32_t)bl != a) atomicAdd(&s_cnt[2], 1u);
-                    if ((uint32_t)bl != a) {
-                        const int cr = (int)(key >> 16), cg = (int)((key >> 8) & 255u), cb = (int)(key & 255u);
-                        atomicAdd(&s_sum[a][0], -cr);
-                        atomicAdd(&s_sum[a][1], -cg);
-                        atomicAdd(&s_sum[a][2], -cb);
-                        atomicAdd(&s_sum[a][3], -1);
-                        atomicAdd(&s_sum[bl][0], cr);
-                        atomicAdd(&s_sum[bl][1], cg);
-                        atomicAdd(&s_sum[bl][2], cb);
-                        atomicAdd(&s_sum[bl][3], 1);
+                    const uint32_t bal = __ballot_sync(FULL, full);
+                    if (full) q2[(q2head + q2n + __popc(bal & ((1u << lane) - 1u))) & 63] = (Q2)rl;
+                    q2n += __popc(bal);
+                    __syncwarp();
+                    if (q2n >= 32) {
+                        search_point((int)q2[(q2head + lane) & 63]);
+                        q2head = (q2head + 32) & 63;
+                        q2n -= 32;
+                        __syncwarp();
                     }
                 }
                 __syncwarp();
             }
+            if (lane < q2n) search_point((int)q2[(q2head + lane) & 63]);
         }
         __syncthreads();
         // cv2's float32 centre sums: the exact integers while every channel sum is below 2^24 (always, for lists that
