@@ -500,10 +500,20 @@ __global__ void __launch_bounds__(FT, FT == FT_LONG ? 1 : 2) k_kmeans_fast(KmPar
             for (int k = 0; k < KC; ++k) acc_lo[k] = acc_hi[k] = 0u;
             for (int r0 = 0; r0 < rows; r0 += 256) {
                 const int r1 = min(rows, r0 + 256);
-                for (int r = r0; r < r1; ++r) {
+                for (int r4 = r0; r4 < r1; r4 += 4) {
+                  // the key loads (L2) of four rows are in flight before the first search starts
+                  uint32_t kv[4];
+#pragma unroll
+                  for (int u = 0; u < 4; ++u) {
+                      const int i = ((r4 + u) * FW + warp) * 32 + lane;
+                      kv[u] = (r4 + u < r1 && i < U) ? key_at(i) : 0u;
+                  }
+#pragma unroll
+                  for (int u = 0; u < 4; ++u) {
+                    const int r = r4 + u;
                     int i = (r * FW + warp) * 32 + lane;
-                    if (i >= U) continue;
-                    uint32_t key = key_at(i);
+                    if (r >= r1 || i >= U) continue;
+                    uint32_t key = kv[u];
                     float fr, fg, fb;
                     unpackf(key, fr, fg, fb);
                     float bd = fdist4(fr, fg, fb, s_c[0]), sd = 3e38f;
@@ -530,6 +540,7 @@ __global__ void __launch_bounds__(FT, FT == FT_LONG ? 1 : 2) k_kmeans_fast(KmPar
                         acc_lo[k] += m ? lo : 0u;
                         acc_hi[k] += m ? pr : 0u;
                     }
+                  }
                 }
                 // flush the 16-bit fields before they can overflow (256 rows * 255 < 65536)
 #pragma unroll
@@ -799,14 +810,23 @@ __global__ void __launch_bounds__(FT, FT == FT_LONG ? 1 : 2) k_kmeans_fast(KmPar
     // compactness with the final centres and the labels of the last assignment; labels out
     uint8_t* labels = P.labels + slot * P.max_unique;
     double part = 0.0;
-    for (int r = 0; r < rows; ++r) {
-        int i = (r * FW + warp) * 32 + lane;
-        if (i >= U) continue;
-        const uint32_t a = F::label(aux[i]);
-        float fr, fg, fb;
-        unpackf(key_at(i), fr, fg, fb);
-        part += (double)fdist4(fr, fg, fb, s_c[a]);
-        labels[i] = (uint8_t)a;
+    for (int r4 = 0; r4 < rows; r4 += 4) {
+        uint32_t kv[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            const int i = ((r4 + u) * FW + warp) * 32 + lane;
+            kv[u] = (r4 + u < rows && i < U) ? key_at(i) : 0u;
+        }
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {   // same order of additions as a row-by-row walk
+            const int i = ((r4 + u) * FW + warp) * 32 + lane;
+            if (r4 + u >= rows || i >= U) continue;
+            const uint32_t a = F::label(aux[i]);
+            float fr, fg, fb;
+            unpackf(kv[u], fr, fg, fb);
+            part += (double)fdist4(fr, fg, fb, s_c[a]);
+            labels[i] = (uint8_t)a;
+        }
     }
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) part += __shfl_xor_sync(FULL, part, o);
