@@ -228,7 +228,10 @@ __global__ void __launch_bounds__(WARPS * 32, SHADOW ? CTAS_FULL : CTAS_EDGES) k
     const int vb_lo = y0 - (SHADOW ? 5 : 2);
     const int vb_hi = y1 - 1 + (SHADOW ? 5 : 2);
 
-    Q4 hb[5];                  // h-blur of gray rows rb-2 .. rb+2
+    // Vertical [1,4,6,4,1] in transposed form: s0..s3 are the partial sums of the next four outputs (s0 lacks only the
+    // newest row), so a new h-blurred row costs one multiply-add per accumulator and nothing has to be shifted along
+    // a window of rows.  The rounding constant rides in through s3.
+    Q4 s0 = {0u, 0u, 0u, 0u}, s1 = s0, s2 = s0, s3 = s0;
     Q4 bw[3], tw[3];           // blurred rows vb-2, vb-1, vb and their [1,2,1] smoothing
     Q4 mw[3];                  // magnitude rows vs-2, vs-1, vs
     uint32_t me[3] = {0u, 0u, 0u};
@@ -267,19 +270,30 @@ __global__ void __launch_bounds__(WARPS * 32, SHADOW ? CTAS_FULL : CTAS_EDGES) k
     for (int vb = vb_lo; vb <= vb_hi; ++vb) {
         const int rb = clampi(vb, 0, H - 1);
         if (!primed || rb != rb_prev) {
+#define VB_FEED(P)                                   \
+    {                                                \
+        const uint32_t h_ = hrow.P;                  \
+        const uint32_t v_ = s0.P + h_;               \
+        s0.P = s1.P + 4u * h_;                       \
+        s1.P = s2.P + 6u * h_;                       \
+        s2.P = s3.P + 4u * h_;                       \
+        s3.P = h_ + 0x00800080u;                     \
+        blurred.P = __byte_perm(v_, 0u, 0x4341);     \
+    }
             if (!primed) {
                 primed = true;
 #pragma unroll
-                for (int k = 0; k < 5; ++k) hb[k] = hblur(gray_row());
-            } else {
-                hb[0] = hb[1];
-                hb[1] = hb[2];
-                hb[2] = hb[3];
-                hb[3] = hb[4];
-                hb[4] = hblur(gray_row());
+                for (int k = 0; k < 4; ++k) {   // rows rb-2 .. rb+1 only fill the accumulators
+                    const Q4 hrow = hblur(gray_row());
+                    VB_FEED(p0) VB_FEED(p1) VB_FEED(p2) VB_FEED(p3)
+                }
             }
+            {
+                const Q4 hrow = hblur(gray_row());
+                VB_FEED(p0) VB_FEED(p1) VB_FEED(p2) VB_FEED(p3)
+            }
+#undef VB_FEED
             rb_prev = rb;
-            blurred = vblur(hb);
             // BORDER_REPLICATE in x for the consumers of the blurred image
             if (left_edge) {
                 const uint32_t v = lo16(__shfl_down_sync(FULL, blurred.p0, 1)) * 0x00010001u;
