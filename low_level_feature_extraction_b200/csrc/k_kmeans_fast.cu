@@ -44,6 +44,14 @@ __device__ __forceinline__ float fdist4(float r, float g, float b, float4 c) {
     return d;
 }
 
+// Square root for the BOUNDS only (never for a value cv2 computes): sqrt.approx is within 2^-23 relative, i.e. 0.002 of
+// the 1/32-unit grid at the largest RGB distance, and q_up / q_dn each keep a whole unit of slack on top of their rounding.
+__device__ __forceinline__ float bound_sqrt(float x) {
+    float r;
+    asm("sqrt.approx.f32 %0, %1;" : "=f"(r) : "f"(x));
+    return r;
+}
+
 // State word of a point during Lloyd: label | ub | lb.  K <= 16: 4 + 14 + 14 bits, bounds in 1/32 colour
 // units (the largest RGB distance, 441.7, is 14134 units); K <= 32: 5 + 13 + 14 bits in 1/16 units.
 // q_up rounds up, q_dn down, each with one extra unit of slack.
@@ -531,7 +539,7 @@ __global__ void __launch_bounds__(FT, FT == FT_LONG ? 1 : 2) k_kmeans_fast(KmPar
                             }
                         }
                     }
-                    aux[i] = F::pack((uint32_t)bl, F::q_up(__fsqrt_rn(bd)), F::q_dn(__fsqrt_rn(sd)));
+                    aux[i] = F::pack((uint32_t)bl, F::q_up(bound_sqrt(bd)), F::q_dn(bound_sqrt(sd)));
                     const uint32_t plo = key & 0xffffu, pr = (key >> 16) | 0x10000u;
                     const uint32_t lo = ((plo & 0xff00u) << 8) | (plo & 0xffu);
 #pragma unroll
@@ -594,7 +602,7 @@ __global__ void __launch_bounds__(FT, FT == FT_LONG ? 1 : 2) k_kmeans_fast(KmPar
                         }
                     }
                 }
-                aux[i] = F::pack((uint32_t)bl, F::q_up(__fsqrt_rn(bd)), F::q_dn(__fsqrt_rn(sd)));
+                aux[i] = F::pack((uint32_t)bl, F::q_up(bound_sqrt(bd)), F::q_dn(bound_sqrt(sd)));
                 if (P.dbg && (uint32_t)bl != a) atomicAdd(&s_cnt[2], 1u);
                 if ((uint32_t)bl != a) {
                     const int cr = (int)(key >> 16), cg = (int)((key >> 8) & 255u), cb = (int)(key & 255u);
@@ -667,7 +675,7 @@ __global__ void __launch_bounds__(FT, FT == FT_LONG ? 1 : 2) k_kmeans_fast(KmPar
                         const uint32_t bound = max(lb, s_tab[a].z);
                         float fr, fg, fb;
                         unpackf(key_at(i), fr, fg, fb);
-                        const uint32_t ub = F::q_up(__fsqrt_rn(fdist4(fr, fg, fb, s_c[a])));
+                        const uint32_t ub = F::q_up(bound_sqrt(fdist4(fr, fg, fb, s_c[a])));
                         if (ub < bound) aux[i] = F::pack(a, ub, lb);
                         else full = true;
                     }
