@@ -91,6 +91,11 @@ int launch_blur5(llfe_ctx* ctx, const uint8_t* src, int n, int h, int w, int c, 
 
 int launch_gray_blur5(llfe_ctx* ctx, const uint8_t* bgr, int n, int h, int w, uint8_t* dst) {
     if (n == 0 || h == 0 || w == 0) return LLFE_OK;
+    // widths the streaming front kernel takes: its blurred-plane-only instance (registers instead of shared-memory tiles,
+    // 128-bit loads, packed 16x2 arithmetic) is ~3x faster than the tile kernel below; "unfused" keeps the tile kernel
+    // as the independent cross-check of the parity tests
+    if (fused_supported(h, w) && !ctx->opt_unfused)
+        return launch_fused(ctx, bgr, n, h, w, 0, 0, nullptr, nullptr, nullptr, nullptr, dst);
     dim3 grid(ceil_div(w, TWB), ceil_div(h, TH), n);
     LLFE_KERNEL(ctx, "k_gray_blur5");
     k_blur5<true><<<grid, 256, 0, ctx->stream>>>(bgr, dst, h, w, 1);
