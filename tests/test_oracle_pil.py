@@ -47,3 +47,30 @@ def test_reduce_equals_pillow(fx, fy):
     assert np.array_equal(pilops.reduce_box_mean(a, fx, fy), np.array(Image.fromarray(a).reduce((fx, fy))))
     box = (3, 5, 80, 58)
     assert np.array_equal(pilops.reduce_box_mean(a, fx, fy, box), np.array(Image.fromarray(a).reduce((fx, fy), box=box)))
+
+
+def test_drop_in_thumbnail_host_logic_without_gpu(monkeypatch):
+    """services/image_processor.py mirrors PIL/Image.py's size / reduce-factor / box rules on the host; the two device
+    primitives are stood in for by the oracle here, so the logic around them is checked against Pillow on CPU."""
+    from low_level_feature_extraction_b200.services import image_processor as ip
+
+    def fake_call(src, fx, fy, reduce_box, box, dw, dh):
+        img = src
+        if fx > 1 or fy > 1:
+            img = pilops.reduce_box_mean(img, fx, fy, tuple(int(v) for v in reduce_box))
+        return pilops.resample_lanczos(img, dw, dh, tuple(float(np.float32(v)) for v in box))
+
+    monkeypatch.setattr(ip, "_pil_resize_call", fake_call)
+    rng = np.random.default_rng(11)
+    for h, w, mw, mh in [(108, 192, 96, 54), (300, 500, 64, 64), (501, 733, 40, 40), (90, 160, 192, 108), (77, 1200, 100, 100),
+                         (1300, 9, 30, 30), (640, 480, 31, 57), (900, 1400, 100, 75), (1210, 11, 40, 40)]:
+        a = rng.integers(0, 256, (h, w, 3), dtype=np.uint8)
+        assert np.array_equal(ip.pil_thumbnail_lanczos(a, mw, mh), pil_thumb(a, mw, mh)), (h, w, mw, mh)
+    a = rng.integers(0, 256, (200, 300, 3), dtype=np.uint8)
+    for size, box in [((70, 50), None), ((33, 21), (10.5, 20.25, 250.0, 180.5)), ((300, 200), None), ((20, 20), (0, 0, 300, 200))]:
+        ref = np.array(Image.fromarray(a).resize(size, Image.Resampling.LANCZOS, box=box, reducing_gap=2.0))
+        assert np.array_equal(ip.pil_resize_lanczos(a, size, box, 2.0), ref), (size, box)
+    with pytest.raises(TypeError):
+        ip.pil_resize_lanczos(a.astype(np.float32), (10, 10))
+    with pytest.raises(ValueError):
+        ip.pil_resize_lanczos(a, (10, 10), reducing_gap=0.5)
