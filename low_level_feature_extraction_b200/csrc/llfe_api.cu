@@ -204,6 +204,7 @@ int llfe_set_option(llfe_ctx* ctx, const char* name, int64_t value) {
     else if (!strcmp(name, "shadow_inline")) ctx->opt_shadow_inline = value != 0;
     else if (!strcmp(name, "serial")) ctx->opt_serial = value != 0;
     else if (!strcmp(name, "shadow_variant")) ctx->shadow_variant = (int)value;
+    else if (!strcmp(name, "chunk")) ctx->opt_chunk = (value >= 1 && value <= 256) ? (int)value : 256;
     else {
         llfe_set_error("llfe_set_option: unknown option '%s'", name);
         return LLFE_E_INVALID;
@@ -561,11 +562,11 @@ static int analyze_impl(llfe_ctx* ctx, const uint8_t* d_bgr, int n, int h, int w
     LLFE_CHECK_ARG(d_keys == nullptr || (d_count != nullptr && max_unique > 0));
     if (n == 0) return LLFE_OK;
     if (fused_supported(h, w) && !ctx->opt_unfused) {
-        // Per chunk of 32 images: the front kernel (edge bit planes + the blurred gray plane), the shadow kernel on
-        // that plane, the colour pass (bitmaps of a chunk stay in L2) and the ordered compaction.  The hysteresis
-        // is latency-bound (a few busy warps per image), so it runs once per super-chunk of up to 256 images to
-        // have as many images in flight as the SMs can hold.
-        const int chunk = n < 32 ? n : 32;
+        // Per chunk (by default the whole super-chunk of up to 256 images): the front kernel (edge bit planes + the blurred
+        // gray plane), the shadow kernel on that plane, the colour pass and the ordered compaction.  The hysteresis is
+        // latency-bound (a few busy warps per image), so it runs once per super-chunk to have as many images in flight as
+        // the SMs can hold.
+        const int chunk = n < ctx->opt_chunk ? n : ctx->opt_chunk;
         const int super = n < 256 ? n : 256;
         const size_t plane_words = (size_t)super * h * plane_wpr(w), plane_img = (size_t)h * plane_wpr(w);
         const size_t bmw = bitmap_words_per_image(), bmb = bitmap_blocks_per_image();
