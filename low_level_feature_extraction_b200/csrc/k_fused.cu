@@ -112,20 +112,6 @@ __device__ __forceinline__ Q4 hblur(const Q4& g) {
     return h;
 }
 
-// vertical [1,4,6,4,1] + rounding: (sum + 128) >> 8 per 16-bit lane (sum <= 65280)
-__device__ __forceinline__ uint32_t vb1(uint32_t a, uint32_t b, uint32_t c, uint32_t d, uint32_t e) {
-    const uint32_t v = a + e + 4u * (b + d) + 6u * c + 0x00800080u;
-    return __byte_perm(v, 0u, 0x4341);  // (v.b1, 0, v.b3, 0)
-}
-__device__ __forceinline__ Q4 vblur(const Q4* hb) {
-    Q4 o;
-    o.p0 = vb1(hb[0].p0, hb[1].p0, hb[2].p0, hb[3].p0, hb[4].p0);
-    o.p1 = vb1(hb[0].p1, hb[1].p1, hb[2].p1, hb[3].p1, hb[4].p1);
-    o.p2 = vb1(hb[0].p2, hb[1].p2, hb[2].p2, hb[3].p2, hb[4].p2);
-    o.p3 = vb1(hb[0].p3, hb[1].p3, hb[2].p3, hb[3].p3, hb[4].p3);
-    return o;
-}
-
 // horizontal [1,2,1] smoothing of a blurred row (needs the neighbours' edge pixels)
 __device__ __forceinline__ Q4 hsmooth(const Q4& b) {
     const uint32_t pm = __shfl_up_sync(FULL, b.p3, 1), pn = __shfl_down_sync(FULL, b.p0, 1);

@@ -153,3 +153,26 @@ def test_tall_image_single_column_of_bands(eng, shadow_path):
     assert np.array_equal(out["shadow_mask"][0].cpu().numpy(), m_ref)
     assert [int(v) for v in out["shadow_sums"][0].cpu()] == [s_ref, n_ref]
     assert np.array_equal(out["shape_mask"][0].cpu().numpy(), cvops.shape_mask(img))
+
+
+def test_results_do_not_depend_on_the_chunking(eng):
+    """llfe_analyze launches each front kernel once per super-chunk by default; the device noise, the masks and the
+    palettes must be the same for any images-per-launch setting (the schedule is not part of the result)."""
+    batch = np.stack([design_image(135, 240, s) for s in range(9)])
+    d = dev(batch)
+    ref = None
+    try:
+        for chunk in (256, 4, 1):
+            eng.ctx.set_option("chunk", chunk)
+            out = eng.pipeline(d, seed=5, max_unique=1 << 15)
+            got = {k: out[k].cpu().numpy().copy() for k in ("shape_mask", "shadow_mask", "shadow_sums", "count")}
+            got["keys"] = [out["keys"][i, :int(out["count"][i])].cpu().numpy().copy() for i in range(9)]
+            if ref is None:
+                ref = got
+                continue
+            for k in ("shape_mask", "shadow_mask", "shadow_sums", "count"):
+                assert np.array_equal(got[k], ref[k]), (chunk, k)
+            for i in range(9):
+                assert np.array_equal(got["keys"][i], ref["keys"][i]), (chunk, i)
+    finally:
+        eng.ctx.set_option("chunk", 256)
