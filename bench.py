@@ -297,6 +297,7 @@ def measure_e2e(an, batch, steps, world, dev, colors, tail="thread"):
     host_in.copy_(batch)
     outs = [an.alloc_host_outputs(B) for _ in range(2)]      # double-buffered: the tail of step i reads buffer i % 2
     res = an.run_host(host_in, outs[0])                      # warm-up (allocates the staging chunks)
+    an.run_host_async(host_in, outs[1]).result()             # ... and the pinned bit planes of the second batch in flight
     if colors:
         an.palettes(res)                                     # ... and the tail's first call (imports, pydantic model build)
     torch.cuda.synchronize()
@@ -307,19 +308,34 @@ def measure_e2e(an, batch, steps, world, dev, colors, tail="thread"):
     # The region is wall-clock on the host (copies, host threads and the interpreter are part of what is measured), so
     # one scheduling hiccup of the box moves a 0.2 s block by tens of per cent: three blocks of `steps` steps are
     # timed, the MEDIAN block is the value and all three are in the record.
+    import gc
+
+    gc.collect()
+    gc.disable()     # a generation-2 pass over the interpreter's heap in the middle of a 0.2 s block is not part of the workload
     blocks = []
     for _ in range(3):
         pending = []
         n_palettes = 0
         te = time.perf_counter()
-        for i in range(steps):
-            if len(pending) >= 2:
-                n_palettes += len(pending.pop(0).result())       # buffer i % 2 is free again
-            res = an.run_host(host_in, outs[i % 2])
+        prev = None
+
+        def finish(call):
+            nonlocal n_palettes
+            res_ = call.result()                                 # this step's masks / palettes are on the host
             if colors and tail == "thread":
-                pending.append(pool.submit(an.palettes, res))
+                pending.append(pool.submit(an.palettes, res_))
             elif colors:
-                n_palettes += len(an.palettes(res))
+                n_palettes += len(an.palettes(res_))
+            return res_
+
+        for i in range(steps):
+            while pending:                                       # the tail of step i - 2 still reads buffer i % 2
+                n_palettes += len(pending.pop(0).result())
+            call = an.run_host_async(host_in, outs[i % 2])       # step i is enqueued while step i - 1 drains
+            if prev is not None:
+                res = finish(prev)
+            prev = call
+        res = finish(prev)
         for f in pending:
             n_palettes += len(f.result())
         torch.cuda.synchronize()
@@ -330,13 +346,15 @@ def measure_e2e(an, batch, steps, world, dev, colors, tail="thread"):
             dt = float(t.item())
         blocks.append(dt)
     pool.shutdown()
+    gc.enable()
     dt = sorted(blocks)[1]
     return {"value": B * world * steps / dt, "unit": "images/sec",
             "h2d_bytes_per_step": int(res["_h2d_bytes"]) * world, "d2h_bytes_per_step": int(res["_d2h_bytes"]) * world,
             "steps": steps, "blocks_images_per_sec": [round(B * world * steps / b, 1) for b in blocks],
+            "note": "median of three blocks of `steps` batches; Python's cyclic garbage collector is paused during the blocks",
             "palette_tail_on_host": (tail if colors else False), "palettes_per_step": n_palettes // max(1, steps),
-            "api": "BatchAnalyzer.run_host: pinned host images in, host masks + ColorFeatures out; chunked copies overlapped "
-                   f"with kernels ({an.cfg.host_streams} streams, {an.cfg.host_chunk} images per stage)"}
+            "api": "BatchAnalyzer.run_host_async (two batches in flight): pinned host images in, host masks + ColorFeatures out; "
+                   f"chunked copies overlapped with kernels ({an.cfg.host_streams} streams, {an.cfg.host_chunk} images per stage)"}
 
 
 def pipeline_record(args, workload, B, H, W, k, steps, warmup, rank, world, local, dev, distinct, kind="design", e2e_steps=0,

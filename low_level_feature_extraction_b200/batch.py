@@ -51,6 +51,20 @@ class BatchConfig:
     max_points: int = 8192
 
 
+class HostCall:
+    """One batch of `BatchAnalyzer.run_host_async` in flight."""
+
+    def __init__(self, owner, images, host_out, n, done, pending, bytes_in, bytes_out, slot):
+        self.owner, self.images, self.host_out, self.n = owner, images, host_out, n
+        self.done, self.pending, self.bytes_in, self.bytes_out, self.slot = done, pending, bytes_in, bytes_out, slot
+        self._result = None
+
+    def result(self) -> dict:
+        if self._result is None:
+            self._result = self.owner._finish_host(self)
+        return self._result
+
+
 class BatchAnalyzer:
     def __init__(self, device: int, h: int, w: int, cfg: BatchConfig | None = None):
         self.cfg = cfg or BatchConfig()
@@ -60,6 +74,10 @@ class BatchAnalyzer:
         self.engines = [Engine(device) for _ in range(ns)]
         self.streams = [torch.cuda.Stream(self.device) for _ in range(ns)]
         self._dev_in = None
+        self._dev_bits = None
+        self._host_bits = [None, None]     # pinned bit planes, one set per batch in flight
+        self._inflight = [None, None]
+        self._calls = 0
         self._pool = None
 
     # ---- device-resident ---------------------------------------------------------------
@@ -221,32 +239,46 @@ class BatchAnalyzer:
 
     def run_host(self, images: torch.Tensor, host_out: dict | None = None) -> dict:
         """images: pinned CPU uint8 (B, H, W, 3).  Returns host tensors; synchronous."""
+        return self.run_host_async(images, host_out).result()
+
+    def run_host_async(self, images: torch.Tensor, host_out: dict | None = None) -> "HostCall":
+        """Enqueue one batch (copies in, kernels, copies out, mask expansion on host threads) and return a handle;
+        `handle.result()` waits for this batch only and returns the host tensors.  Up to two batches may be in flight:
+        the first stages of batch i + 1 are copied in while the last stage of batch i is still being computed and copied
+        back, which a synchronous call per batch cannot hide.  `images` and `host_out` must stay untouched until
+        `result()` returns."""
         c = self.cfg
         n = images.shape[0]
         host_out = host_out if host_out is not None else self.alloc_host_outputs(n)
         mask_keys = [k for k in ("shape_mask", "shadow_mask") if k in host_out]
         packed = c.packed_masks and len(mask_keys) > 0
+        # the batch that used this slot's pinned bit planes two calls ago must be done with them
+        slot = self._calls % 2
+        self._calls += 1
+        if self._inflight[slot] is not None:
+            self._inflight[slot].result()
         if self._dev_in is None:
             ns = len(self.streams)
             self._dev_in = [torch.empty((c.host_chunk, self.h, self.w, 3), dtype=torch.uint8, device=self.device) for _ in range(ns)]
             self._dev_out = [self.alloc_outputs(c.host_chunk) for _ in range(ns)]
-            self._host_bits = None
-        if packed and (self._host_bits is None or self._host_bits.shape[1] < n):
+        if packed and (self._host_bits[slot] is None or self._host_bits[slot].shape[1] < n):
             from concurrent.futures import ThreadPoolExecutor
 
             wpr = self.engines[0].ctx.lib.llfe_mask_bits_words_per_row(self.w)
-            self._dev_bits = [torch.empty((len(mask_keys), c.host_chunk, self.h, wpr), dtype=torch.int32, device=self.device)
-                              for _ in range(len(self.streams))]
-            self._host_bits = torch.empty((len(mask_keys), n, self.h, wpr), dtype=torch.int32).pin_memory()
+            if self._dev_bits is None:
+                self._dev_bits = [torch.empty((len(mask_keys), c.host_chunk, self.h, wpr), dtype=torch.int32, device=self.device)
+                                  for _ in range(len(self.streams))]
+            self._host_bits[slot] = torch.empty((len(mask_keys), n, self.h, wpr), dtype=torch.int32).pin_memory()
             if self._pool is None:
                 self._pool = ThreadPoolExecutor(max(1, c.expand_workers), thread_name_prefix="llfe-expand")
         lib = self.engines[0].ctx.lib
+        host_bits = self._host_bits[slot]
         pending = []
 
         def expand(ev, i0, m):
             ev.synchronize()                     # releases the GIL; the expansion below is a ctypes call (ditto)
             for j, key in enumerate(mask_keys):
-                rc = lib.llfe_expand_mask_bits_host(self._host_bits[j, i0:i0 + m].data_ptr(), m, self.h, self.w,
+                rc = lib.llfe_expand_mask_bits_host(host_bits[j, i0:i0 + m].data_ptr(), m, self.h, self.w,
                                                     host_out[key][i0:i0 + m].data_ptr(), c.expand_threads)
                 if rc != 0:
                     raise RuntimeError(lib.llfe_last_error().decode())
@@ -268,7 +300,7 @@ class BatchAnalyzer:
                     for q, key in enumerate(mask_keys):
                         bits = self._dev_bits[b][q, :m]
                         eng.ctx.call("llfe_pack_mask_bits", dout[key], m, self.h, self.w, bits)
-                        self._host_bits[q, i0:i0 + m].copy_(bits, non_blocking=True)
+                        host_bits[q, i0:i0 + m].copy_(bits, non_blocking=True)
                         bytes_out += bits.numel() * 4
                     ev = torch.cuda.Event()
                     ev.record(st)
@@ -279,9 +311,22 @@ class BatchAnalyzer:
                     if key in host_out:
                         host_out[key][i0:i0 + m].copy_(dout[key], non_blocking=True)
                         bytes_out += dout[key].numel() * dout[key].element_size()
-        for st in self.streams:
-            st.synchronize()
-        for f in pending:
+        done = []
+        for st in self.streams:           # this batch's work only: a later batch may already be behind it on the streams
+            ev = torch.cuda.Event()
+            ev.record(st)
+            done.append(ev)
+        call = HostCall(self, images, host_out, n, done, pending, bytes_in, bytes_out, slot)
+        self._inflight[slot] = call
+        return call
+
+    def _finish_host(self, call: "HostCall") -> dict:
+        c = self.cfg
+        images, host_out, n = call.images, call.host_out, call.n
+        bytes_in, bytes_out = call.bytes_in, call.bytes_out
+        for ev in call.done:
+            ev.synchronize()
+        for f in call.pending:
             f.result()
         if c.colors:
             # images whose colour list overflowed the batched capacity: upload again, redo alone (rare: photo-like
@@ -305,7 +350,11 @@ class BatchAnalyzer:
                     host_out["k_used"][i:i + 1].copy_(kused, non_blocking=True)
                     host_out["cluster_sizes"][i].copy_(sizes, non_blocking=True)
                     host_out["status"][i:i + 1].copy_(status, non_blocking=True)
-                self.streams[0].synchronize()
+                    ev = torch.cuda.Event()
+                    ev.record(self.streams[0])
+                ev.synchronize()
         host_out["_h2d_bytes"] = bytes_in
         host_out["_d2h_bytes"] = bytes_out
+        if self._inflight[call.slot] is call:
+            self._inflight[call.slot] = None
         return host_out

@@ -69,3 +69,31 @@ def test_pipeline_is_deterministic_run_to_run():
             h.update(out[k].cpu().numpy().tobytes())
         digests.add(h.hexdigest())
     assert len(digests) == 1
+
+
+def test_run_host_async_two_batches_in_flight_equals_run_host():
+    """run_host_async overlaps the copies of batch i + 1 with the tail of batch i; results must equal the synchronous
+    call batch by batch (shared staging buffers, per-batch events, double-buffered bit planes)."""
+    import torch
+
+    from low_level_feature_extraction_b200.batch import BatchAnalyzer, BatchConfig
+    from low_level_feature_extraction_b200.synth import design_image
+
+    h, w, n = 120, 200, 10
+    batches = [torch.from_numpy(np.stack([design_image(h, w, 10 * b + i) for i in range(n)])).pin_memory() for b in range(4)]
+    cfg = BatchConfig(host_chunk=4, host_streams=3, seed=3, max_unique=1 << 15)
+    ref_an = BatchAnalyzer(0, h, w, cfg)
+    refs = []
+    for x in batches:
+        out = ref_an.run_host(x)
+        refs.append({k: v.clone() for k, v in out.items() if hasattr(v, "clone")})
+    an = BatchAnalyzer(0, h, w, cfg)
+    outs = [an.alloc_host_outputs(n) for _ in range(4)]
+    calls = [an.run_host_async(batches[0], outs[0]), an.run_host_async(batches[1], outs[1])]
+    calls.append(an.run_host_async(batches[2], outs[2]))        # waits for batch 0 (same slot) before it enqueues
+    got = [c.result() for c in calls]
+    got.append(an.run_host_async(batches[3], outs[3]).result())
+    for b in range(4):
+        for k, v in refs[b].items():
+            assert torch.equal(got[b][k], v), (b, k)
+    assert calls[0].result() is got[0]                          # idempotent
