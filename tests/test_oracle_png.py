@@ -92,3 +92,38 @@ def test_product_parser_accepts_plain_pngs_and_defers_the_rest():
     assert png.inflate(short) is None
     pal = make_case(3, 4, 6, 7, 2)
     assert len(png.parse(pal).palette) % 3 == 0 and png.parse(pal).rowbytes == 4
+
+
+def test_parser_and_inflate_never_raise_on_damaged_files():
+    """Every damaged file is either refused by the chunk walk (CRC, structure) or by the inflate -- the caller then
+    leaves it to cv2.imdecode; nothing raises and nothing reads out of bounds."""
+    from low_level_feature_extraction_b200.services import png
+
+    rng = np.random.default_rng(4)
+    base = [make_case(2, 8, 31, 45, 1), make_case(6, 8, 12, 19, 2, idat_split=50), make_case(3, 4, 20, 33, 3), make_case(0, 16, 9, 14, 4)]
+    refused = accepted = 0
+    for trial in range(600):
+        b = bytearray(base[trial % len(base)])
+        mode = trial % 3
+        if mode == 0:      # flip bytes anywhere (almost always caught by a chunk CRC)
+            for _ in range(int(rng.integers(1, 4))):
+                b[int(rng.integers(0, len(b)))] ^= int(rng.integers(1, 256))
+        elif mode == 1:    # truncate
+            b = b[:int(rng.integers(0, len(b)))]
+        else:              # damage the zlib stream and repair the chunk CRC, so that the inflate sees it
+            pos = bytes(b).find(b"IDAT")
+            (n,) = struct.unpack(">I", bytes(b[pos - 4:pos]))
+            if n > 8:
+                b[pos + 4 + int(rng.integers(2, n))] ^= int(rng.integers(1, 256))
+                b[pos + 4 + n:pos + 8 + n] = struct.pack(">I", zlib.crc32(bytes(b[pos:pos + 4 + n])))
+        info = png.parse(bytes(b))
+        if info is None:
+            refused += 1
+            continue
+        stream = png.inflate(info)
+        if stream is None:
+            refused += 1
+        else:
+            accepted += 1
+            assert len(stream) == info.stream_bytes
+    assert refused > 400 and accepted + refused == 600
