@@ -916,7 +916,7 @@ int launch_kc(llfe_ctx* ctx, const KmParams& P, int n, int pts2, int pts1) {
         for (int i0 = 0; i0 < n; i0 += P.dist_images) {
             const int m = (n - i0) < P.dist_images ? (n - i0) : P.dist_images;
             LLFE_KERNEL(ctx, "k_kmeans_fast_global");
-            k_kmeans_fast<KC, false, FT_STD><<<dim3(P.attempts, m), FT_STD, 0, ctx->stream>>>(P, 0, pts1, i0);
+            k_kmeans_fast<KC, false, FT_LONG><<<dim3(P.attempts, m), FT_LONG, 0, ctx->stream>>>(P, 0, pts1, i0);   // one CTA per SM: 32 warps on the list
             LLFE_LAUNCHED(ctx);
         }
     }
