@@ -45,7 +45,8 @@ def test_png_decode_1080p_files_from_pillow_and_opencv():
         assert np.array_equal(png.decode(b.getvalue()), ref), mode
         assert np.array_equal(png.imdecode_color(b.getvalue()), ref)
     # tall and narrow / wide and flat: more rows than threads, fewer chunks than a warp
-    for h, w in [(3000, 5), (3, 9000), (2161, 777)]:
+    # ... and rows too long for the shared-memory delay line (the first thread reads the row above from the stream)
+    for h, w in [(3000, 5), (3, 9000), (2161, 777), (300, 12500)]:
         rng = np.random.default_rng(h)
         a = (np.cumsum(rng.integers(-3, 4, (h, w, 3)), axis=1) + 100).astype(np.uint8)
         b = io.BytesIO()
