@@ -10,7 +10,6 @@ import math
 import time
 from typing import Union
 
-import cv2
 import numpy as np
 from PIL import Image
 

@@ -10,7 +10,6 @@ from __future__ import annotations
 import logging
 from enum import Enum
 
-import cv2
 import numpy as np
 
 from .image_processor import resize_area, resize_lanczos4, resize_linear
