@@ -15,6 +15,8 @@
 // error: libpng stops reading once the image is complete ("too much image data" is a warning).
 #include <string.h>
 
+#include <atomic>
+
 #include "llfe_common.cuh"
 
 namespace {
@@ -236,7 +238,7 @@ int decode_block(Stream& s_ref, const Ent* lt, const Ent* dt, uint8_t* out_begin
     return rc;
 }
 
-int inflate_raw(Stream& s, uint8_t* out, size_t out_cap, size_t* out_len, bool* finished) {
+int inflate_raw(Stream& s, uint8_t* out, size_t out_cap, size_t* out_len, bool* finished, std::atomic<size_t>* progress) {
     static const Fixed fixed;
     static const uint8_t ORDER[19] = {16, 17, 18, 0, 8, 7, 9, 6, 10, 5, 11, 4, 12, 3, 13, 2, 14, 1, 15};
     Tables* dyn = nullptr;
@@ -356,6 +358,7 @@ int inflate_raw(Stream& s, uint8_t* out, size_t out_cap, size_t* out_len, bool* 
         } else {
             break;   // reserved block type
         }
+        if (progress) progress->store((size_t)(o - out), std::memory_order_release);   // a consumer may take the bytes so far
         if (last) {
             rc = INF_OK;
             *finished = true;
@@ -387,8 +390,11 @@ uint32_t adler32(const uint8_t* p, size_t n) {
 }  // namespace
 
 // zlib-wrapped deflate stream -> out (at most out_cap bytes).  *out_len = bytes written.  LLFE_OK when the stream is valid
-// as far as it was needed: it ended (then the Adler-32 trailer must match) or the output filled up first.
-extern "C" int llfe_inflate_zlib(const uint8_t* in, size_t in_len, uint8_t* out, size_t out_cap, size_t* out_len) {
+// as far as it was needed: it ended (then the Adler-32 trailer must match) or the output filled up first.  `progress`
+// (optional) is advanced to the number of finished output bytes after every deflate block, so that another thread can
+// ship the front of the output while the rest is still being decoded (bytes below the mark never change again).
+int llfe_inflate_zlib_progress(const uint8_t* in, size_t in_len, uint8_t* out, size_t out_cap, size_t* out_len,
+                               std::atomic<size_t>* progress) {
     if (!in || !out || !out_len) {
         llfe_set_error("llfe_inflate_zlib: invalid argument: null pointer");
         return LLFE_E_INVALID;
@@ -401,7 +407,7 @@ extern "C" int llfe_inflate_zlib(const uint8_t* in, size_t in_len, uint8_t* out,
     Stream s;
     s.p = in + 2, s.end = in + in_len;
     bool finished = false;
-    const int rc = inflate_raw(s, out, out_cap, out_len, &finished);
+    const int rc = inflate_raw(s, out, out_cap, out_len, &finished, progress);
     if (rc == INF_ERR) {
         llfe_set_error("llfe_inflate_zlib: invalid or truncated deflate stream");
         return LLFE_E_INVALID;
@@ -419,5 +425,10 @@ extern "C" int llfe_inflate_zlib(const uint8_t* in, size_t in_len, uint8_t* out,
             return LLFE_E_INVALID;
         }
     }
+    if (progress) progress->store(*out_len, std::memory_order_release);
     return LLFE_OK;
+}
+
+extern "C" int llfe_inflate_zlib(const uint8_t* in, size_t in_len, uint8_t* out, size_t out_cap, size_t* out_len) {
+    return llfe_inflate_zlib_progress(in, in_len, out, out_cap, out_len, nullptr);
 }

@@ -44,15 +44,15 @@ struct PngPos {
 // memory -- from the neighbouring thread's previous step, or, for the first thread, from a delay line the last thread
 // feeds (its row above was finished cpad - T + 1 steps earlier).
 template <int BPP>
-__global__ void __launch_bounds__(256) k_png_unfilter(uint8_t* __restrict__ stream, int h, int rowbytes, int chunks, int cpad,
-                                                      int use_carry, int32_t* __restrict__ status) {
+__global__ void __launch_bounds__(256) k_png_unfilter(uint8_t* __restrict__ stream, int h, int row0, int row1, int rowbytes,
+                                                      int chunks, int cpad, int use_carry, int32_t* __restrict__ status) {
     __shared__ uint32_t tin[256 * PNG_TW];          // filtered bytes of this step, a row per thread
     __shared__ uint32_t tout[2][256 * PNG_TW];      // reconstructed bytes of this / the previous step (the row above)
     __shared__ uint4 carry[PNG_CARRY];
     const uint32_t stride = (uint32_t)rowbytes + 1u;
     uint8_t* img = stream + (size_t)blockIdx.x * h * stride;
     const int T = blockDim.x, j = threadIdx.x, lane = j & 31, wbase = j & ~31;
-    const int total = T + ((h + T - 1) / T) * cpad;
+    const int total = T + ((row1 - row0 + T - 1) / T) * cpad;   // rows [row0, row1); rows above row0 are reconstructed already
     const int d1 = cpad - T + 2;                    // delay-line length
     const int bi = lane & 15, half = lane >> 4;
     int win[BPP], cw[BPP];   // the last BPP reconstructed bytes of this row (a) and of the row above (c)
@@ -60,9 +60,9 @@ __global__ void __launch_bounds__(256) k_png_unfilter(uint8_t* __restrict__ stre
     for (int k = 0; k < BPP; ++k) win[k] = cw[k] = 0;
     int ft = 0, ftn = 0, wr = 0;
     uint32_t vn[16];         // byte `bi` of the chunks of rows 2i + half of this warp, for the NEXT step
-    PngPos cur{j, -j};
+    PngPos cur{row0 + j, -j};
     auto fetch = [&](const PngPos& p) {
-        const bool act = p.active(h, chunks);
+        const bool act = p.active(row1, chunks);
         const uint32_t off = act ? (uint32_t)p.r * stride + 1u + (uint32_t)p.sc * PNG_CH : 0u;
         const int nb = act ? min(PNG_CH, rowbytes - p.sc * PNG_CH) : 0;
 #pragma unroll
@@ -83,7 +83,7 @@ __global__ void __launch_bounds__(256) k_png_unfilter(uint8_t* __restrict__ stre
     for (int t = 0; t < total; ++t) {
         PngPos nxt = cur;
         nxt.advance(T, cpad);
-        const bool act = cur.active(h, chunks);
+        const bool act = cur.active(row1, chunks);
         if (act && cur.sc == 0) ft = ftn;
         fetch(nxt);
         uint32_t* mine = tout[t & 1] + j * PNG_TW;
@@ -104,9 +104,9 @@ __global__ void __launch_bounds__(256) k_png_unfilter(uint8_t* __restrict__ stre
             if (r == 0) {
 #pragma unroll
                 for (int i = 0; i < PNG_CH; ++i) b[i] = 0;
-            } else if (j > 0 || use_carry) {
+            } else if (j > 0 || (use_carry && r >= row0 + T)) {
                 // the thread above finished this chunk of its row in the previous step; for the first thread that
-                // was the last thread, d1 - 1 steps ago
+                // was the last thread, d1 - 1 steps ago (in its first round: the row above is in the stream already)
                 uint32_t v4[4];
                 if (j > 0) {
                     const uint32_t* above = tout[(t & 1) ^ 1] + (j - 1) * PNG_TW;
@@ -250,6 +250,41 @@ extern "C" int64_t llfe_png_rowbytes(int w, int color_type, int bit_depth) {
     return ((int64_t)w * ch * bit_depth + 7) / 8;
 }
 
+// reconstruct rows [row0, row1) of n images in place (rows above row0 must be reconstructed already)
+int launch_png_unfilter_rows(llfe_ctx* ctx, uint8_t* d_stream, int n, int h, int row0, int row1, int rowbytes, int bpp,
+                             int32_t* d_status) {
+    const int chunks = ceil_div(rowbytes, PNG_CH);
+    const int rows = row1 - row0;
+    int T = chunks >= 256 ? 256 : (chunks / 32) * 32;
+    if (T < 32) T = 32;
+    if (T > ((rows + 31) / 32) * 32) T = ((rows + 31) / 32) * 32;
+    const int cpad = chunks > T ? chunks : T;
+    const int use_carry = cpad - T + 2 <= PNG_CARRY;
+    LLFE_KERNEL(ctx, "k_png_unfilter");
+    switch (bpp) {
+        case 1: k_png_unfilter<1><<<n, T, 0, ctx->stream>>>(d_stream, h, row0, row1, rowbytes, chunks, cpad, use_carry, d_status); break;
+        case 2: k_png_unfilter<2><<<n, T, 0, ctx->stream>>>(d_stream, h, row0, row1, rowbytes, chunks, cpad, use_carry, d_status); break;
+        case 3: k_png_unfilter<3><<<n, T, 0, ctx->stream>>>(d_stream, h, row0, row1, rowbytes, chunks, cpad, use_carry, d_status); break;
+        case 4: k_png_unfilter<4><<<n, T, 0, ctx->stream>>>(d_stream, h, row0, row1, rowbytes, chunks, cpad, use_carry, d_status); break;
+        case 6: k_png_unfilter<6><<<n, T, 0, ctx->stream>>>(d_stream, h, row0, row1, rowbytes, chunks, cpad, use_carry, d_status); break;
+        case 8: k_png_unfilter<8><<<n, T, 0, ctx->stream>>>(d_stream, h, row0, row1, rowbytes, chunks, cpad, use_carry, d_status); break;
+        default: llfe_set_error("llfe_png_reconstruct: unsupported pixel size %d", bpp); return LLFE_E_UNSUPPORTED;
+    }
+    LLFE_LAUNCHED(ctx);
+    return LLFE_OK;
+}
+
+int launch_png_to_bgr(llfe_ctx* ctx, const uint8_t* d_stream, int n, int h, int w, int rowbytes, int color_type, int bit_depth,
+                      const uint8_t* d_palette, uint8_t* d_bgr) {
+    const PngFmt f{h, w, rowbytes, color_type, bit_depth};
+    LLFE_KERNEL(ctx, "k_png_to_bgr");
+    k_png_to_bgr<<<dim3(ceil_div(w, 256), h, n), 256, 0, ctx->stream>>>(d_stream, f, d_palette, d_bgr);
+    LLFE_LAUNCHED(ctx);
+    return LLFE_OK;
+}
+
+int png_filter_distance(int color_type, int bit_depth) { return (png_channels(color_type) * bit_depth + 7) / 8; }
+
 extern "C" int llfe_png_reconstruct(llfe_ctx* ctx, uint8_t* d_stream, int n, int h, int w, int color_type, int bit_depth,
                                     const uint8_t* d_palette, uint8_t* d_bgr, int32_t* d_status) {
     LLFE_ENTER(ctx);
@@ -260,29 +295,8 @@ extern "C" int llfe_png_reconstruct(llfe_ctx* ctx, uint8_t* d_stream, int n, int
     LLFE_CHECK_ARG(color_type != 3 || d_palette != nullptr);
     if (n == 0) return LLFE_OK;
     const int rowbytes = (int)rb;
-    const int bpp = (png_channels(color_type) * bit_depth + 7) / 8;   // filter distance in bytes
-    const int chunks = ceil_div(rowbytes, PNG_CH);
-    int T = chunks >= 256 ? 256 : (chunks / 32) * 32;
-    if (T < 32) T = 32;
-    if (T > ((h + 31) / 32) * 32) T = ((h + 31) / 32) * 32;
-    const int cpad = chunks > T ? chunks : T;
-    const int use_carry = cpad - T + 2 <= PNG_CARRY;
     LLFE_CHECK_ARG((uint64_t)h * ((uint64_t)rowbytes + 1) < 0xffffffffull);   // 32-bit offsets inside one image
     LLFE_CUDA(cudaMemsetAsync(d_status, 0, (size_t)n * sizeof(int32_t), ctx->stream));
-    LLFE_KERNEL(ctx, "k_png_unfilter");
-    switch (bpp) {
-        case 1: k_png_unfilter<1><<<n, T, 0, ctx->stream>>>(d_stream, h, rowbytes, chunks, cpad, use_carry, d_status); break;
-        case 2: k_png_unfilter<2><<<n, T, 0, ctx->stream>>>(d_stream, h, rowbytes, chunks, cpad, use_carry, d_status); break;
-        case 3: k_png_unfilter<3><<<n, T, 0, ctx->stream>>>(d_stream, h, rowbytes, chunks, cpad, use_carry, d_status); break;
-        case 4: k_png_unfilter<4><<<n, T, 0, ctx->stream>>>(d_stream, h, rowbytes, chunks, cpad, use_carry, d_status); break;
-        case 6: k_png_unfilter<6><<<n, T, 0, ctx->stream>>>(d_stream, h, rowbytes, chunks, cpad, use_carry, d_status); break;
-        case 8: k_png_unfilter<8><<<n, T, 0, ctx->stream>>>(d_stream, h, rowbytes, chunks, cpad, use_carry, d_status); break;
-        default: llfe_set_error("llfe_png_reconstruct: unsupported pixel size %d", bpp); return LLFE_E_UNSUPPORTED;
-    }
-    LLFE_LAUNCHED(ctx);
-    const PngFmt f{h, w, rowbytes, color_type, bit_depth};
-    LLFE_KERNEL(ctx, "k_png_to_bgr");
-    k_png_to_bgr<<<dim3(ceil_div(w, 256), h, n), 256, 0, ctx->stream>>>(d_stream, f, d_palette, d_bgr);
-    LLFE_LAUNCHED(ctx);
-    return LLFE_OK;
+    LLFE_TRY(launch_png_unfilter_rows(ctx, d_stream, n, h, 0, h, rowbytes, png_filter_distance(color_type, bit_depth), d_status));
+    return launch_png_to_bgr(ctx, d_stream, n, h, w, rowbytes, color_type, bit_depth, d_palette, d_bgr);
 }

@@ -5,6 +5,7 @@
 #include <string.h>
 
 #include <new>
+#include <atomic>
 #include <thread>
 #include <vector>
 
@@ -947,22 +948,68 @@ int llfe_png_reconstruct_host(llfe_ctx* ctx, const uint8_t* h_stream, int h, int
 int llfe_png_decode_host(llfe_ctx* ctx, const uint8_t* h_idat, size_t idat_bytes, int h, int w, int color_type, int bit_depth,
                          const uint8_t* h_palette, int palette_entries, uint8_t* h_bgr) {
     LLFE_ENTER(ctx);
-    LLFE_CHECK_ARG(h_idat != nullptr && h_bgr != nullptr && h > 0 && w > 0);
+    LLFE_CHECK_ARG(h_idat != nullptr && h_bgr != nullptr && h > 0 && h <= 65535 && w > 0);
     const int64_t rb = llfe_png_rowbytes(w, color_type, bit_depth);
-    LLFE_CHECK_ARG(rb > 0 && palette_entries >= 0 && palette_entries <= 256 && (color_type != 3 || h_palette != nullptr));
-    const size_t in = (size_t)h * (rb + 1), out = (size_t)h * w * 3;
+    LLFE_CHECK_ARG(rb > 0 && rb < 0x7fffffff && palette_entries >= 0 && palette_entries <= 256 &&
+                   (color_type != 3 || h_palette != nullptr));
+    const int rowbytes = (int)rb;
+    const size_t stride = (size_t)rowbytes + 1, in = (size_t)h * stride, out = (size_t)h * w * 3;
+    LLFE_CHECK_ARG(in < 0xffffffffull);
     const size_t a = WsCarver::need(in), b = WsCarver::need(out) + 256;
     LLFE_TRY(ensure_stage(ctx, a + b, a + b));
     uint8_t* p_in = (uint8_t*)ctx->pin;
     uint8_t* d_in = (uint8_t*)ctx->dev_stage;
     uint8_t* d_out = d_in + a;
+    int32_t* d_status = (int32_t*)(d_out + WsCarver::need(out));
+    const int bpp = png_filter_distance(color_type, bit_depth);
+    LLFE_CUDA(cudaMemsetAsync(d_status, 0, sizeof(int32_t), ctx->stream));
     size_t got = 0;
-    LLFE_TRY(llfe_inflate_zlib(h_idat, idat_bytes, p_in, in, &got));
-    if (got != in) {
-        llfe_set_error("llfe_png_decode_host: not enough image data");
+    int inf_rc = LLFE_OK;
+    // The inflate is a serial decode on one host core and by far the longest part.  For streams worth it, it runs on a
+    // helper thread and reports how far it is after every deflate block; this thread ships each band of rows to the
+    // device and reconstructs it (rows above the band are finished: the wavefront kernel continues from them) while the
+    // rest is still being inflated, so that only the last band's copy and kernel are left when the inflate ends.
+    const int bands = in >= (size_t(1) << 20) && h >= 64 ? 8 : 1;
+    if (bands > 1) {
+        std::atomic<size_t> progress{0};
+        std::atomic<int> done{0};
+        std::thread worker([&] {
+            inf_rc = llfe_inflate_zlib_progress(h_idat, idat_bytes, p_in, in, &got, &progress);
+            done.store(1, std::memory_order_release);
+        });
+        int rc = LLFE_OK;
+        const int rows_per_band = ceil_div(h, bands);
+        for (int r0 = 0; r0 < h && rc == LLFE_OK; r0 += rows_per_band) {
+            const int r1 = r0 + rows_per_band < h ? r0 + rows_per_band : h;
+            const size_t need = (size_t)r1 * stride;
+            while (progress.load(std::memory_order_acquire) < need && !done.load(std::memory_order_acquire)) std::this_thread::yield();
+            if (progress.load(std::memory_order_acquire) < need) break;      // the stream ended early or is damaged
+            const size_t off = (size_t)r0 * stride;
+            cudaError_t e = cudaMemcpyAsync(d_in + off, p_in + off, need - off, cudaMemcpyHostToDevice, ctx->stream);
+            if (e != cudaSuccess) {
+                rc = llfe_cuda_fail(e, "cudaMemcpyAsync(band)", __FILE__, __LINE__);
+                break;
+            }
+            rc = launch_png_unfilter_rows(ctx, d_in, 1, h, r0, r1, rowbytes, bpp, d_status);
+        }
+        worker.join();
+        if (rc != LLFE_OK) {
+            cudaStreamSynchronize(ctx->stream);
+            return rc;
+        }
+    } else {
+        inf_rc = llfe_inflate_zlib_progress(h_idat, idat_bytes, p_in, in, &got, nullptr);
+        if (inf_rc == LLFE_OK && got == in) {
+            LLFE_CUDA(cudaMemcpyAsync(d_in, p_in, in, cudaMemcpyHostToDevice, ctx->stream));
+            LLFE_TRY(launch_png_unfilter_rows(ctx, d_in, 1, h, 0, h, rowbytes, bpp, d_status));
+        }
+    }
+    if (inf_rc != LLFE_OK || got != in) {
+        cudaStreamSynchronize(ctx->stream);     // bands of the valid front may be in flight
+        llfe_set_error(inf_rc != LLFE_OK ? "llfe_png_decode_host: invalid or truncated deflate stream"
+                                         : "llfe_png_decode_host: not enough image data");
         return LLFE_E_INVALID;
     }
-    LLFE_CUDA(cudaMemcpyAsync(d_in, p_in, in, cudaMemcpyHostToDevice, ctx->stream));
     uint8_t* d_pal = nullptr;
     if (color_type == 3) {
         void* ws;
@@ -973,11 +1020,9 @@ int llfe_png_decode_host(llfe_ctx* ctx, const uint8_t* h_idat, size_t idat_bytes
         d_pal = (uint8_t*)ws;
         LLFE_CUDA(cudaMemcpyAsync(d_pal, pal, 768, cudaMemcpyHostToDevice, ctx->stream));   // pageable: staged before return
     }
-    int32_t* d_status = (int32_t*)(d_out + WsCarver::need(out));
-    LLFE_TRY(llfe_png_reconstruct(ctx, d_in, 1, h, w, color_type, bit_depth, d_pal, d_out, d_status));
-    // the image straight into the caller's buffer, the status word behind it through pinned memory
+    LLFE_TRY(launch_png_to_bgr(ctx, d_in, 1, h, w, rowbytes, color_type, bit_depth, d_pal, d_out));
     uint8_t* p_out = p_in + a;
-    LLFE_CUDA(cudaMemcpyAsync(p_out, d_out, out + 0, cudaMemcpyDeviceToHost, ctx->stream));
+    LLFE_CUDA(cudaMemcpyAsync(p_out, d_out, out, cudaMemcpyDeviceToHost, ctx->stream));
     LLFE_CUDA(cudaMemcpyAsync(p_out + WsCarver::need(out), d_status, 4, cudaMemcpyDeviceToHost, ctx->stream));
     LLFE_CUDA(cudaStreamSynchronize(ctx->stream));
     int32_t status;

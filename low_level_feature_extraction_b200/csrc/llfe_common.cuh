@@ -5,6 +5,8 @@
 #include <stdint.h>
 #include <stdio.h>
 
+#include <atomic>
+
 #include "llfe.h"
 
 struct llfe_ctx {
@@ -78,6 +80,9 @@ static inline bool llfe_first_use(llfe_ctx* ctx, const void* kernel) {
 }
 
 void llfe_set_error(const char* fmt, ...);
+// h_inflate.cu: llfe_inflate_zlib with a progress mark another thread may read (bytes below it are final)
+int llfe_inflate_zlib_progress(const uint8_t* in, size_t in_len, uint8_t* out, size_t out_cap, size_t* out_len,
+                               std::atomic<size_t>* progress);
 int llfe_cuda_fail(cudaError_t e, const char* what, const char* file, int line);
 
 #define LLFE_CUDA(call)                                                       \
@@ -197,4 +202,10 @@ int launch_fused(llfe_ctx* ctx, const uint8_t* bgr, int n, int h, int w, int low
 int launch_color_bitmap(llfe_ctx* ctx, const uint8_t* d_bgr, int m, int h, int w, const int8_t* d_noise, uint64_t seed,
                         int first_image, uint32_t* bitmap);
 bool shadow_split_supported(int h, int w);
+// PNG reconstruction (k_png.cu): rows [row0, row1) in place, then the conversion to BGR
+int png_filter_distance(int color_type, int bit_depth);
+int launch_png_unfilter_rows(llfe_ctx* ctx, uint8_t* d_stream, int n, int h, int row0, int row1, int rowbytes, int bpp,
+                             int32_t* d_status);
+int launch_png_to_bgr(llfe_ctx* ctx, const uint8_t* d_stream, int n, int h, int w, int rowbytes, int color_type, int bit_depth,
+                      const uint8_t* d_palette, uint8_t* d_bgr);
 int launch_shadow(llfe_ctx* ctx, const uint8_t* blurred, int n, int h, int w, uint8_t* mask, uint64_t* sum_count);
