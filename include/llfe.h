@@ -437,8 +437,9 @@ int llfe_resize_lanczos4_host(llfe_ctx* ctx, const uint8_t* h_src, int sh, int s
  * the message "bad adaptive filter value" for a stream libpng would reject. */
 int llfe_png_reconstruct_host(llfe_ctx* ctx, const uint8_t* h_stream, int h, int w, int color_type, int bit_depth,
                               const uint8_t* h_palette, int palette_entries, uint8_t* h_bgr);
-/* The whole decode of one non-interlaced PNG after the chunk walk: h_idat = the concatenated IDAT payloads; inflated on the
- * calling thread straight into pinned memory (llfe_inflate_zlib), reconstructed and converted on the device.  A damaged
+/* The whole decode of one non-interlaced PNG after the chunk walk: h_idat = the concatenated IDAT payloads; inflated
+ * straight into pinned memory (llfe_inflate_zlib's decoder, on a helper thread for streams of 1 MB and more so that the
+ * rows already inflated are copied and reconstructed meanwhile), reconstructed and converted on the device.  A damaged
  * stream (short, invalid, bad filter byte) returns LLFE_E_INVALID. */
 int llfe_png_decode_host(llfe_ctx* ctx, const uint8_t* h_idat, size_t idat_bytes, int h, int w, int color_type, int bit_depth,
                          const uint8_t* h_palette, int palette_entries, uint8_t* h_bgr);
