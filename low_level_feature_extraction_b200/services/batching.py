@@ -48,6 +48,7 @@ class RequestBatcher:
         self._analyzers: dict[tuple[int, int], Any] = {}
         self._staging: dict[tuple[int, int], Any] = {}
         self._host_out: dict[tuple[int, int], Any] = {}
+        self._slot: dict[tuple[int, int], int] = {}
         self._q: queue.Queue = queue.Queue()
         self.batches = 0          # launches made
         self.images = 0           # images served
@@ -95,9 +96,21 @@ class RequestBatcher:
                                                             contours=self.shapes))
 
     def _loop(self) -> None:
+        # Two batches overlap: while the per-image host work of batch i (mask copies, contour geometry, palettes) runs,
+        # batch i + 1 is already being copied in and computed (BatchAnalyzer.run_host_async).  A batch in flight is
+        # finished as soon as no new request is waiting, so a lone client never waits for a follower.
         stop = False
+        pending = None
         while not stop:
-            item = self._q.get()
+            if pending is not None:
+                try:
+                    item = self._q.get_nowait()
+                except queue.Empty:
+                    self._complete(pending)
+                    pending = None
+                    continue
+            else:
+                item = self._q.get()
             if item is _STOP:
                 break
             batch = [item]
@@ -115,9 +128,15 @@ class RequestBatcher:
             for img, fut in batch:
                 groups.setdefault(img.shape[:2], []).append((img, fut))
             for shape, items in groups.items():
-                self._run(shape, items)
+                started = self._start(shape, items)
+                if pending is not None:
+                    self._complete(pending)
+                pending = started
+        if pending is not None:
+            self._complete(pending)
 
-    def _run(self, shape: tuple[int, int], items: list) -> None:
+    def _start(self, shape: tuple[int, int], items: list):
+        """Stage the frames and enqueue the batch; returns what `_complete` needs (None if the batch already failed)."""
         import torch
 
         h, w = shape
@@ -126,20 +145,44 @@ class RequestBatcher:
             an = self._analyzers.get(shape)
             if an is None:
                 an = self._analyzers[shape] = self._factory(h, w)
-                st = torch.empty((self.max_batch, h, w, 3), dtype=torch.uint8)
-                self._staging[shape] = st.pin_memory() if torch.cuda.is_available() else st
-                if hasattr(an, "alloc_host_outputs"):   # pinned result buffers are allocated once per shape
-                    self._host_out[shape] = an.alloc_host_outputs(self.max_batch)
-            stage = self._staging[shape]
+                self._staging[shape] = []
+                self._host_out[shape] = []
+                for _ in range(2):          # one set of pinned buffers per batch in flight
+                    st = torch.empty((self.max_batch, h, w, 3), dtype=torch.uint8)
+                    self._staging[shape].append(st.pin_memory() if torch.cuda.is_available() else st)
+                    if hasattr(an, "alloc_host_outputs"):
+                        self._host_out[shape].append(an.alloc_host_outputs(self.max_batch))
+                self._slot[shape] = 0
+            slot = self._slot[shape]
+            self._slot[shape] = slot ^ 1
+            stage = self._staging[shape][slot]
             m = len(items)
             view = stage.numpy()
             list(self._pool.map(lambda i: np.copyto(view[i], items[i][0]), range(m)))
+            host_out = self._host_out[shape][slot] if self._host_out[shape] else None
             with _runtime.lock():
-                if shape in self._host_out:
-                    full = an.run_host(stage[:m], self._host_out[shape])
-                    out = {k: (v[:m] if hasattr(v, "shape") else v) for k, v in full.items()}
-                else:
-                    out = an.run_host(stage[:m])
+                if hasattr(an, "run_host_async"):
+                    call = an.run_host_async(stage[:m], host_out) if host_out is not None else an.run_host_async(stage[:m])
+                    return (shape, items, an, m, call, None)
+                full = an.run_host(stage[:m], host_out) if host_out is not None else an.run_host(stage[:m])
+                return (shape, items, an, m, None, full)
+        except Exception as e:
+            for fut in futs:
+                if not fut.done():
+                    fut.set_exception(e)
+            return None
+
+    def _complete(self, started) -> None:
+        if started is None:
+            return
+        shape, items, an, m, call, full = started
+        h, w = shape
+        futs = [f for _, f in items]
+        try:
+            if call is not None:
+                with _runtime.lock():
+                    full = call.result()
+            out = {k: (v[:m] if hasattr(v, "shape") else v) for k, v in full.items()}
             self.batches += 1
             self.images += m
             centers = out["centers"].numpy()
