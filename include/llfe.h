@@ -185,6 +185,14 @@ int llfe_png_reconstruct(llfe_ctx* ctx, uint8_t* d_stream, int n, int h, int w, 
  * image is complete.  No context, no device. */
 int llfe_inflate_zlib(const uint8_t* in, size_t in_len, uint8_t* out, size_t out_cap, size_t* out_len);
 
+/* Host-only: is `buf` a baseline JFIF JPEG of the subset the device path decodes (8-bit, Huffman, one interleaved scan,
+ * gray or YCbCr 4:4:4 / 4:2:2 / 4:2:0, no Exif orientation / Adobe marker)?  out[0] = width, out[1] = height.
+ * LLFE_E_UNSUPPORTED = a JPEG outside the subset (the caller uses cv2.imdecode), LLFE_E_INVALID = damaged header.
+ * llfe_jpeg_coefficients (host-only, for tests): the entropy-decoded quantised coefficients, blocks [by][bx][64] in natural
+ * order, component after component. */
+int llfe_jpeg_info(const uint8_t* buf, size_t len, int32_t* out);
+int llfe_jpeg_coefficients(const uint8_t* buf, size_t len, int16_t* out, size_t cap, size_t* count);
+
 /* Pillow's ImagingReduce(im, (fx, fy), box) and ImagingResample(im, (dw, dh), LANCZOS, box) on u8, c = 1 or 3: the two
  * steps of `pil_image.thumbnail(size, Image.Resampling.LANCZOS)` (image_processor.py:221-224; reducing_gap = 2.0).
  * box = host int32[4] / float[4] (left, upper, right, lower) in source pixels.  llfe_pil_reduce writes
@@ -443,6 +451,11 @@ int llfe_png_reconstruct_host(llfe_ctx* ctx, const uint8_t* h_stream, int h, int
  * stream (short, invalid, bad filter byte) returns LLFE_E_INVALID. */
 int llfe_png_decode_host(llfe_ctx* ctx, const uint8_t* h_idat, size_t idat_bytes, int h, int w, int color_type, int bit_depth,
                          const uint8_t* h_palette, int palette_entries, uint8_t* h_bgr);
+/* cv2.imdecode(buf, IMREAD_COLOR) of a baseline JPEG (utils.py:108-109, image_processor.py:62-66, :208-211): Huffman
+ * decoding on the calling thread into pinned memory, libjpeg-turbo's islow IDCT, fancy chroma up-sampling and YCbCr -> BGR
+ * conversion on the device, bit for bit.  h, w from llfe_jpeg_info.  Files outside the subset / damaged data:
+ * LLFE_E_UNSUPPORTED / LLFE_E_INVALID (the caller uses cv2.imdecode). */
+int llfe_jpeg_decode_host(llfe_ctx* ctx, const uint8_t* h_buf, size_t len, int h, int w, uint8_t* h_bgr);
 /* Image.resize(size, LANCZOS, box, reducing_gap) below PIL/Image.py's Python layer on a host image: an optional
  * ImagingReduce by (fx, fy) over reduce_box (fx = fy = 1: none) followed by ImagingResample with `box` (in pixels of the
  * reduced image) to dh x dw; the intermediate stays on the device. */

@@ -14,6 +14,7 @@ LIB_PATH = os.path.join(HERE, "libllfe.so")
 
 LLFE_OK = 0
 LLFE_E_INVALID = -1
+LLFE_E_UNSUPPORTED = -4
 ERRORS = {-1: "LLFE_E_INVALID", -2: "LLFE_E_CUDA", -3: "LLFE_E_NOMEM", -4: "LLFE_E_UNSUPPORTED", -5: "LLFE_E_NODEVICE"}
 
 
@@ -108,6 +109,9 @@ PROTOTYPES = {
     "llfe_png_reconstruct_host": (i32, [vp, vp, i32, i32, i32, i32, vp, i32, vp]),
     "llfe_inflate_zlib": (i32, [vp, sz, vp, sz, C.POINTER(sz)]),
     "llfe_png_decode_host": (i32, [vp, vp, sz, i32, i32, i32, i32, vp, i32, vp]),
+    "llfe_jpeg_info": (i32, [vp, sz, vp]),
+    "llfe_jpeg_coefficients": (i32, [vp, sz, vp, sz, C.POINTER(sz)]),
+    "llfe_jpeg_decode_host": (i32, [vp, vp, sz, i32, i32, vp]),
     "llfe_pil_reduce": (i32, [vp, vp, i32, i32, i32, i32, vp, i32, i32, vp]),
     "llfe_pil_resample_lanczos": (i32, [vp, vp, i32, i32, i32, i32, vp, vp, i32, i32]),
     "llfe_pil_resize_lanczos_host": (i32, [vp, vp, i32, i32, i32, i32, i32, vp, vp, vp, i32, i32]),

@@ -1035,6 +1035,14 @@ int llfe_png_decode_host(llfe_ctx* ctx, const uint8_t* h_idat, size_t idat_bytes
     return LLFE_OK;
 }
 
+int llfe_jpeg_decode_host(llfe_ctx* ctx, const uint8_t* h_buf, size_t len, int h, int w, uint8_t* h_bgr) {
+    LLFE_ENTER(ctx);
+    LLFE_CHECK_ARG(h_buf != nullptr && h_bgr != nullptr && h > 0 && w > 0 && len >= 4);
+    const size_t cap = llfe_jpeg_stage_bytes(h, w);
+    LLFE_TRY(ensure_stage(ctx, cap, cap));
+    return llfe_jpeg_decode_impl(ctx, h_buf, len, h, w, h_bgr, (uint8_t*)ctx->pin, (uint8_t*)ctx->dev_stage, cap);
+}
+
 int llfe_pil_resize_lanczos_host(llfe_ctx* ctx, const uint8_t* h_src, int sh, int sw, int c, int fx, int fy,
                                  const int32_t* reduce_box, const float* box, uint8_t* h_dst, int dh, int dw) {
     LLFE_ENTER(ctx);

@@ -202,6 +202,10 @@ int launch_fused(llfe_ctx* ctx, const uint8_t* bgr, int n, int h, int w, int low
 int launch_color_bitmap(llfe_ctx* ctx, const uint8_t* d_bgr, int m, int h, int w, const int8_t* d_noise, uint64_t seed,
                         int first_image, uint32_t* bitmap);
 bool shadow_split_supported(int h, int w);
+// JPEG (k_jpeg.cu): entropy decoding on the host into `pin`, the rest on the device
+size_t llfe_jpeg_stage_bytes(int h, int w);
+int llfe_jpeg_decode_impl(llfe_ctx* ctx, const uint8_t* buf, size_t len, int h, int w, uint8_t* h_bgr, uint8_t* pin, uint8_t* dev,
+                          size_t cap);
 // PNG reconstruction (k_png.cu): rows [row0, row1) in place, then the conversion to BGR
 int png_filter_distance(int color_type, int bit_depth);
 int launch_png_unfilter_rows(llfe_ctx* ctx, uint8_t* d_stream, int n, int h, int row0, int row1, int rowbytes, int bpp,

@@ -176,12 +176,22 @@ def decode_many(bufs, workers: int = 8) -> list:
 
 
 def imdecode_color(buf) -> np.ndarray | None:
-    """Drop-in for `cv2.imdecode(np.frombuffer(buf, np.uint8), cv2.IMREAD_COLOR)`."""
+    """Drop-in for `cv2.imdecode(np.frombuffer(buf, np.uint8), cv2.IMREAD_COLOR)`: PNG and baseline JPEG take the device
+    paths (this module, services/jpeg.py), everything else -- and every file those refuse -- goes to OpenCV."""
     import cv2
 
+    from . import jpeg
+
     arr = np.frombuffer(buf, np.uint8) if isinstance(buf, (bytes, bytearray, memoryview)) else np.asarray(buf, np.uint8)
+    raw = None
     if arr.size >= 8 and arr[:8].tobytes() == SIGNATURE:
-        img = decode(arr.tobytes() if not isinstance(buf, (bytes, bytearray)) else buf)
+        raw = buf if isinstance(buf, (bytes, bytearray)) else arr.tobytes()
+        img = decode(raw)
+        if img is not None:
+            return img
+    elif arr.size >= 4 and arr[:2].tobytes() == jpeg.SIGNATURE:
+        raw = buf if isinstance(buf, (bytes, bytearray)) else arr.tobytes()
+        img = jpeg.decode(raw)
         if img is not None:
             return img
     return cv2.imdecode(arr, cv2.IMREAD_COLOR)

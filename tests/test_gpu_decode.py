@@ -198,3 +198,58 @@ def test_auto_process_image_equals_the_reference_call_sequence():
     assert np.array_equal(ImageProcessor.load_cv2_image(buf), img)
     with pytest.raises(ValueError):
         ImageProcessor.auto_process_image(b"nonsense")
+
+
+# ---- baseline JPEG: entropy decoding on the host, IDCT / up-sampling / colour conversion on the device -------------------------
+from test_oracle_jpeg import CASES as JPEG_CASES  # noqa: E402
+from test_oracle_jpeg import encode as jpeg_encode  # noqa: E402
+
+
+@pytest.mark.parametrize("name,buf", JPEG_CASES, ids=[c[0] for c in JPEG_CASES])
+def test_jpeg_decode_equals_cv2(name, buf):
+    from low_level_feature_extraction_b200.services import jpeg
+
+    got = jpeg.decode(buf)
+    assert got is not None
+    assert np.array_equal(got, cv2_decode(buf))
+
+
+def test_jpeg_decode_large_files_and_every_sampling():
+    from low_level_feature_extraction_b200.services import jpeg, png
+    from low_level_feature_extraction_b200.synth import design_image, noise_image
+
+    for h, w, seed in [(1080, 1920, 3), (2160, 3840, 4), (1081, 1919, 5), (7, 2500, 6), (2500, 7, 7)]:
+        img = design_image(h, w, seed) if min(h, w) > 16 else noise_image(h, w, seed)
+        for params in ([], [cv2.IMWRITE_JPEG_QUALITY, 70], [cv2.IMWRITE_JPEG_SAMPLING_FACTOR, cv2.IMWRITE_JPEG_SAMPLING_FACTOR_444],
+                       [cv2.IMWRITE_JPEG_SAMPLING_FACTOR, cv2.IMWRITE_JPEG_SAMPLING_FACTOR_422, cv2.IMWRITE_JPEG_RST_INTERVAL, 7]):
+            buf = jpeg_encode(img, *params)
+            ref = cv2_decode(buf)
+            got = jpeg.decode(buf)
+            assert got is not None and np.array_equal(got, ref), (h, w, params)
+            assert np.array_equal(png.imdecode_color(buf), ref)
+    gray = cv2.cvtColor(design_image(333, 517, 8), cv2.COLOR_BGR2GRAY)
+    buf = jpeg_encode(gray)
+    assert np.array_equal(jpeg.decode(buf), cv2_decode(buf))
+
+
+def test_jpeg_files_outside_the_subset_go_to_opencv():
+    from low_level_feature_extraction_b200.services import jpeg, png
+    from low_level_feature_extraction_b200.synth import design_image
+
+    img = design_image(200, 300, 9)
+    prog = jpeg_encode(img, cv2.IMWRITE_JPEG_PROGRESSIVE, 1)
+    assert jpeg.decode(prog) is None
+    assert np.array_equal(png.imdecode_color(prog), cv2_decode(prog))
+    base = jpeg_encode(img)
+    cut = base[:len(base) * 2 // 3]                       # truncated: libjpeg pads with gray, this decoder defers
+    assert jpeg.decode(cut) is None
+    ref, got = cv2_decode(cut), png.imdecode_color(cut)
+    assert (ref is None and got is None) or np.array_equal(ref, got)
+    rng = np.random.default_rng(5)
+    for _ in range(40):                                   # damaged entropy data: whatever OpenCV makes of it
+        b = bytearray(base)
+        for _ in range(2):
+            b[int(rng.integers(len(b) // 2, len(b) - 2))] = int(rng.integers(0, 256))
+        mine = jpeg.decode(bytes(b))
+        if mine is not None:
+            assert np.array_equal(mine, cv2_decode(bytes(b)))
