@@ -204,7 +204,19 @@ struct JBits {
     int marker = 0;      // marker that stopped the reader (0 = none)
     int fake = 0;        // zero bits appended behind the last real one (a marker or the end of the file was reached)
     inline void fill() {
-        while (cnt <= 56) {
+        if (cnt >= 32) return;       // a code (<= 16 bits) and its extra bits (<= 15) are there
+        // fast path: four bytes at once when none of them is FF (no stuffing, no marker)
+        while (cnt <= 32 && !marker && end - p >= 4) {
+            uint32_t v;
+            memcpy(&v, p, 4);
+            const uint32_t nv = ~v;
+            if (((nv - 0x01010101u) & ~nv & 0x80808080u) != 0u) break;      // some byte is FF
+            v = __builtin_bswap32(v);
+            buf |= (uint64_t)v << (32 - cnt);
+            cnt += 32;
+            p += 4;
+        }
+        while (cnt < 32) {
             int b = 0;
             if (marker || p >= end) fake += 8;
             if (!marker && p < end) {
@@ -253,7 +265,6 @@ inline int jextend(int v, int t) { return v < (1 << (t - 1)) ? v - (1 << t) + 1 
 
 // entropy-coded segment -> quantised coefficients (natural order, int16), blocks [by][bx][64] per component
 int jpeg_entropy_decode(const JInfo& J, int16_t* coef) {
-    memset(coef, 0, J.coef_count * sizeof(int16_t));
     JBits b;
     b.p = J.scan;
     b.end = J.end;
@@ -281,6 +292,7 @@ int jpeg_entropy_decode(const JInfo& J, int16_t* coef) {
             for (int by = 0; by < c.v; ++by)
                 for (int bx = 0; bx < c.h; ++bx) {
                     int16_t* blk = coef + c.coef_off + ((size_t)(my * c.v + by) * c.bw + (mx * c.h + bx)) * 64;
+                    memset(blk, 0, 64 * sizeof(int16_t));     // cleared right before it is written: one pass over the buffer
                     b.fill();
                     const int t = jdecode(b, hd);
                     if (t < 0 || t > 11) return LLFE_E_INVALID;

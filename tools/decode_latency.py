@@ -52,6 +52,15 @@ def main():
             "of_which_device_call_with_copies": med(lambda: ctx.call("llfe_png_reconstruct_host", stream, 1080, 1920,
                                                                      info.color_type, info.bit_depth, None, 0, dst)),
         }
+    from low_level_feature_extraction_b200.services import jpeg
+    for q in (95, 75):
+        jb = cv2.imencode(".jpg", img, [cv2.IMWRITE_JPEG_QUALITY, q])[1].tobytes()
+        assert np.array_equal(jpeg.decode(jb), cv2.imdecode(np.frombuffer(jb, np.uint8), cv2.IMREAD_COLOR))
+        out[f"1080p_jpeg_q{q}"] = {
+            "file_bytes": len(jb),
+            "cv2_imdecode": med(lambda: cv2.imdecode(np.frombuffer(jb, np.uint8), cv2.IMREAD_COLOR)),
+            "services_jpeg_decode": med(lambda: jpeg.decode(jb)),
+        }
     big = design_image(2160, 3840, 1)
     buf = cv2.imencode(".png", big)[1].tobytes()
 
