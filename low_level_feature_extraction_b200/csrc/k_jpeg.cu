@@ -16,6 +16,9 @@
 // caller hands them to cv2.imdecode, as it does with every file this decoder finds damaged.
 #include <string.h>
 
+#include <atomic>
+#include <thread>
+
 #include "llfe_common.cuh"
 #include "llfe_device.cuh"
 
@@ -28,6 +31,7 @@ const uint8_t JZIGZAG[64] = {0,  1,  8,  16, 9,  2,  3,  10, 17, 24, 32, 25, 18,
 struct JHuff {
     bool present = false;
     uint16_t fast[512];      // (length << 8) | symbol for codes of up to 9 bits, 0 = longer code
+    int16_t fast_ac[512];    // AC tables: (value << 8) | (run << 4) | total bits when code + magnitude bits fit in 9 bits, else 0
     int32_t maxcode[18];     // largest code of each length (-1 = none), left-aligned compare value per length
     int32_t valptr[17];
     int32_t mincode[17];
@@ -72,6 +76,17 @@ bool build_huff(const uint8_t* counts, const uint8_t* vals, int nvals, JHuff* h)
         code <<= 1;
     }
     h->maxcode[17] = 0x7fffffff;
+    // most AC coefficients of a photograph are small and have short codes: one look-up then yields run, value and length
+    for (int i = 0; i < 512; ++i) {
+        h->fast_ac[i] = 0;
+        const uint16_t f = h->fast[i];
+        if (!f) continue;
+        const int len = f >> 8, run = (f >> 4) & 15, size = f & 15;
+        if (size == 0 || len + size > 9) continue;
+        int v = ((i << len) & 511) >> (9 - size);
+        if (v < (1 << (size - 1))) v += 1 - (1 << size);
+        if (v >= -128 && v <= 127) h->fast_ac[i] = (int16_t)((v * 256) + (run * 16) + (len + size));
+    }
     return k == nvals;
 }
 
@@ -264,7 +279,7 @@ inline int jdecode(JBits& b, const JHuff& h) {
 inline int jextend(int v, int t) { return v < (1 << (t - 1)) ? v - (1 << t) + 1 : v; }
 
 // entropy-coded segment -> quantised coefficients (natural order, int16), blocks [by][bx][64] per component
-int jpeg_entropy_decode(const JInfo& J, int16_t* coef) {
+int jpeg_entropy_decode(const JInfo& J, int16_t* coef, std::atomic<int>* rows_done = nullptr) {
     JBits b;
     b.p = J.scan;
     b.end = J.end;
@@ -303,6 +318,14 @@ int jpeg_entropy_decode(const JInfo& J, int16_t* coef) {
                     blk[0] = (int16_t)pred[ci];
                     for (int k = 1; k < 64;) {
                         b.fill();
+                        const int fa = ha.fast_ac[b.peek(9)];
+                        if (fa) {
+                            k += (fa >> 4) & 15;
+                            if (k > 63) return LLFE_E_INVALID;
+                            b.drop(fa & 15);
+                            blk[JZIGZAG[k++]] = (int16_t)(fa >> 8);
+                            continue;
+                        }
                         const int rs = jdecode(b, ha);
                         if (rs < 0) return LLFE_E_INVALID;
                         const int r = rs >> 4, s = rs & 15;
@@ -319,6 +342,7 @@ int jpeg_entropy_decode(const JInfo& J, int16_t* coef) {
                     }
                 }
         }
+        if (rows_done && mx == J.mcux - 1) rows_done->store(my + 1, std::memory_order_release);   // this MCU row is final
     }
     if (b.cnt < b.fake) return LLFE_E_INVALID;
     return LLFE_OK;
@@ -370,10 +394,11 @@ __device__ __forceinline__ void jidct8(int* x, int shift) {   // jidctint.c, one
 }
 
 // a thread per 8 x 8 block: dequantise, two IDCT passes, range limit, 8 rows of 8 bytes into the component plane
-__global__ void __launch_bounds__(128) k_jpeg_idct(const int16_t* __restrict__ coef, JDev J, int comp, uint8_t* __restrict__ planes) {
+__global__ void __launch_bounds__(128) k_jpeg_idct(const int16_t* __restrict__ coef, JDev J, int comp, int blk0, int blk1,
+                                                   uint8_t* __restrict__ planes) {
     const JDevComp c = J.c[comp];
-    const int blk = blockIdx.x * 128 + threadIdx.x;
-    if (blk >= c.bw * c.bh) return;
+    const int blk = blk0 + blockIdx.x * 128 + threadIdx.x;     // blocks [blk0, blk1) of the component
+    if (blk >= blk1) return;
     const int by = blk / c.bw, bx = blk - by * c.bw;
     const uint4* src = reinterpret_cast<const uint4*>(coef + c.coef_off + (size_t)blk * 64);
     int x[64];
@@ -429,8 +454,8 @@ __device__ __forceinline__ int jchroma(const uint8_t* __restrict__ p, const JDev
     return (3 * near + far + ((x & 1) ? 7 : 8)) >> 4;
 }
 
-__global__ void __launch_bounds__(256) k_jpeg_to_bgr(const uint8_t* __restrict__ planes, JDev J, uint8_t* __restrict__ bgr) {
-    const int x = blockIdx.x * 256 + threadIdx.x, y = blockIdx.y;
+__global__ void __launch_bounds__(256) k_jpeg_to_bgr(const uint8_t* __restrict__ planes, JDev J, int y0, uint8_t* __restrict__ bgr) {
+    const int x = blockIdx.x * 256 + threadIdx.x, y = y0 + blockIdx.y;
     if (x >= J.width) return;
     const int yv = planes[J.c[0].plane_off + (size_t)y * (J.c[0].bw * 8) + x];
     uint8_t* o = bgr + ((size_t)y * J.width + x) * 3;
@@ -512,15 +537,10 @@ int llfe_jpeg_decode_impl(llfe_ctx* ctx, const uint8_t* buf, size_t len, int h, 
         return LLFE_E_INVALID;
     }
     int16_t* p_coef = reinterpret_cast<int16_t*>(pin);
-    rc = jpeg_entropy_decode(*J, p_coef);
-    if (rc != LLFE_OK) {
-        llfe_set_error("llfe_jpeg_decode_host: damaged entropy-coded data");
-        return rc;
-    }
     int16_t* d_coef = reinterpret_cast<int16_t*>(dev);
     uint8_t* d_planes = dev + coef_bytes;
     uint8_t* d_out = d_planes + WsCarver::need(J->plane_bytes);
-    LLFE_CUDA(cudaMemcpyAsync(d_coef, p_coef, J->coef_count * 2, cudaMemcpyHostToDevice, ctx->stream));
+    uint8_t* p_out = pin + coef_bytes;
     JDev D;
     D.width = w, D.height = h, D.ncomp = J->ncomp, D.hmax = J->hmax, D.vmax = J->vmax;
     for (int i = 0; i < J->ncomp; ++i) {
@@ -528,18 +548,81 @@ int llfe_jpeg_decode_impl(llfe_ctx* ctx, const uint8_t* buf, size_t len, int h, 
         D.c[i] = JDevComp{c.bw, c.bh, c.cw, c.ch, c.h, c.v, (unsigned long long)c.coef_off, (unsigned long long)c.plane_off, c.tq};
         memcpy(D.q[i], J->qt[c.tq], sizeof(D.q[i]));
     }
-    for (int i = 0; i < J->ncomp; ++i) {
-        LLFE_KERNEL(ctx, "k_jpeg_idct");
-        k_jpeg_idct<<<ceil_div(D.c[i].bw * D.c[i].bh, 128), 128, 0, ctx->stream>>>(d_coef, D, i, d_planes);
-        LLFE_LAUNCHED(ctx);
+    // MCU rows [m0, m1) are final: copy their coefficients in, transform them, convert the pixel rows whose chroma
+    // neighbours are final too, and bring those rows back
+    int rows_out = 0;       // pixel rows converted so far
+    auto ship = [&](int m0, int m1, bool last) -> int {
+        for (int i = 0; i < J->ncomp; ++i) {
+            const JComp& c = J->comp[i];
+            const size_t b0 = (size_t)m0 * c.v * c.bw, b1 = (size_t)m1 * c.v * c.bw;
+            LLFE_CUDA(cudaMemcpyAsync(d_coef + c.coef_off + b0 * 64, p_coef + c.coef_off + b0 * 64, (b1 - b0) * 128,
+                                      cudaMemcpyHostToDevice, ctx->stream));
+            LLFE_KERNEL(ctx, "k_jpeg_idct");
+            k_jpeg_idct<<<ceil_div((int)(b1 - b0), 128), 128, 0, ctx->stream>>>(d_coef, D, i, (int)b0, (int)b1, d_planes);
+            LLFE_LAUNCHED(ctx);
+        }
+        int y1 = last ? h : m1 * 8 * J->vmax - 8;      // the up-sampler looks one chroma row ahead
+        if (y1 > h) y1 = h;
+        if (y1 > rows_out) {
+            LLFE_KERNEL(ctx, "k_jpeg_to_bgr");
+            k_jpeg_to_bgr<<<dim3(ceil_div(w, 256), y1 - rows_out), 256, 0, ctx->stream>>>(d_planes, D, rows_out, d_out);
+            LLFE_LAUNCHED(ctx);
+            const size_t o0 = (size_t)rows_out * w * 3, o1 = (size_t)y1 * w * 3;
+            LLFE_CUDA(cudaMemcpyAsync(p_out + o0, d_out + o0, o1 - o0, cudaMemcpyDeviceToHost, ctx->stream));
+            rows_out = y1;
+        }
+        return LLFE_OK;
+    };
+    const int bands = (J->coef_count * 2 >= (size_t(1) << 20) && J->mcuy >= 16) ? 8 : 1;
+    if (bands == 1) {
+        rc = jpeg_entropy_decode(*J, p_coef);
+        if (rc != LLFE_OK) {
+            llfe_set_error("llfe_jpeg_decode_host: damaged entropy-coded data");
+            return rc;
+        }
+        LLFE_TRY(ship(0, J->mcuy, true));
+        LLFE_CUDA(cudaStreamSynchronize(ctx->stream));
+        memcpy(h_bgr, p_out, out);
+        return LLFE_OK;
     }
-    LLFE_KERNEL(ctx, "k_jpeg_to_bgr");
-    k_jpeg_to_bgr<<<dim3(ceil_div(w, 256), h), 256, 0, ctx->stream>>>(d_planes, D, d_out);
-    LLFE_LAUNCHED(ctx);
-    uint8_t* p_out = pin + coef_bytes;
-    LLFE_CUDA(cudaMemcpyAsync(p_out, d_out, out, cudaMemcpyDeviceToHost, ctx->stream));
-    LLFE_CUDA(cudaStreamSynchronize(ctx->stream));
-    memcpy(h_bgr, p_out, out);
+    // The entropy decoding runs on a helper thread that reports every finished MCU row; this thread ships band after band
+    // (copy in, IDCT, conversion, copy back) and moves finished rows into the caller's buffer meanwhile, so that only the
+    // last band's share of the copies follows the decoder.
+    std::atomic<int> rows_done{0};
+    std::atomic<int> done{0};
+    int ent_rc = LLFE_OK;
+    std::thread worker([&] {
+        ent_rc = jpeg_entropy_decode(*J, p_coef, &rows_done);
+        done.store(1, std::memory_order_release);
+    });
+    const int per = ceil_div(J->mcuy, bands);
+    cudaEvent_t ev = nullptr;
+    int copied = 0, pending_rows = 0;
+    rc = cudaEventCreateWithFlags(&ev, cudaEventDisableTiming) == cudaSuccess ? LLFE_OK : LLFE_E_CUDA;
+    for (int m0 = 0; m0 < J->mcuy && rc == LLFE_OK; m0 += per) {
+        const int m1 = m0 + per < J->mcuy ? m0 + per : J->mcuy;
+        while (rows_done.load(std::memory_order_acquire) < m1 && !done.load(std::memory_order_acquire)) std::this_thread::yield();
+        if (rows_done.load(std::memory_order_acquire) < m1) break;      // the decoder gave up
+        if (pending_rows > copied) {       // rows of the previous band are back by now or soon: hand them over
+            cudaEventSynchronize(ev);
+            memcpy(h_bgr + (size_t)copied * w * 3, p_out + (size_t)copied * w * 3, (size_t)(pending_rows - copied) * w * 3);
+            copied = pending_rows;
+        }
+        rc = ship(m0, m1, m1 == J->mcuy);
+        if (rc == LLFE_OK) {
+            cudaEventRecord(ev, ctx->stream);
+            pending_rows = rows_out;
+        }
+    }
+    worker.join();
+    cudaStreamSynchronize(ctx->stream);
+    if (ev) cudaEventDestroy(ev);
+    if (rc != LLFE_OK) return rc;
+    if (ent_rc != LLFE_OK || rows_out != h) {
+        llfe_set_error("llfe_jpeg_decode_host: damaged entropy-coded data");
+        return ent_rc != LLFE_OK ? ent_rc : LLFE_E_INVALID;
+    }
+    memcpy(h_bgr + (size_t)copied * w * 3, p_out + (size_t)copied * w * 3, (size_t)(h - copied) * w * 3);
     return LLFE_OK;
 }
 
