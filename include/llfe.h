@@ -185,8 +185,8 @@ int llfe_png_reconstruct(llfe_ctx* ctx, uint8_t* d_stream, int n, int h, int w, 
  * image is complete.  No context, no device. */
 int llfe_inflate_zlib(const uint8_t* in, size_t in_len, uint8_t* out, size_t out_cap, size_t* out_len);
 
-/* Host-only: is `buf` a baseline JFIF JPEG of the subset the device path decodes (8-bit, Huffman, one interleaved scan,
- * gray or YCbCr 4:4:4 / 4:2:2 / 4:2:0, no Exif orientation / Adobe marker)?  out[0] = width, out[1] = height.
+/* Host-only: is `buf` a JFIF JPEG of the subset the device path decodes (8-bit, Huffman; baseline with one interleaved
+ * scan or progressive; gray or YCbCr 4:4:4 / 4:2:2 / 4:2:0; no Exif orientation / Adobe marker)?  out[0] = width, out[1] = height.
  * LLFE_E_UNSUPPORTED = a JPEG outside the subset (the caller uses cv2.imdecode), LLFE_E_INVALID = damaged header.
  * llfe_jpeg_coefficients (host-only, for tests): the entropy-decoded quantised coefficients, blocks [by][bx][64] in natural
  * order, component after component. */
@@ -451,7 +451,7 @@ int llfe_png_reconstruct_host(llfe_ctx* ctx, const uint8_t* h_stream, int h, int
  * stream (short, invalid, bad filter byte) returns LLFE_E_INVALID. */
 int llfe_png_decode_host(llfe_ctx* ctx, const uint8_t* h_idat, size_t idat_bytes, int h, int w, int color_type, int bit_depth,
                          const uint8_t* h_palette, int palette_entries, uint8_t* h_bgr);
-/* cv2.imdecode(buf, IMREAD_COLOR) of a baseline JPEG (utils.py:108-109, image_processor.py:62-66, :208-211): Huffman
+/* cv2.imdecode(buf, IMREAD_COLOR) of a baseline or progressive JPEG (utils.py:108-109, image_processor.py:62-66, :208-211): Huffman
  * decoding on the calling thread into pinned memory, libjpeg-turbo's islow IDCT, fancy chroma up-sampling and YCbCr -> BGR
  * conversion on the device, bit for bit.  h, w from llfe_jpeg_info.  Files outside the subset / damaged data:
  * LLFE_E_UNSUPPORTED / LLFE_E_INVALID (the caller uses cv2.imdecode). */

@@ -1,8 +1,9 @@
-// Baseline JPEG -> the BGR image `cv2.imdecode(buf, cv2.IMREAD_COLOR)` returns (reference call sites:
+// Baseline and progressive JPEG -> the BGR image `cv2.imdecode(buf, cv2.IMREAD_COLOR)` returns (reference call sites:
 // app/services/analyze/utils.py:108-109, image_processor.py:62-66, :208-211).
 //
 // Like a PNG's inflate, a JPEG's entropy-coded segment is one serial bit-level decode (every code's position depends on
-// all codes before it) and stays on a host core (ITU T.81 Annex F: Huffman codes, DC prediction, restart intervals);
+// all codes before it) and stays on a host core (ITU T.81 Annex F: Huffman codes, DC prediction, restart intervals;
+// Annex G for progressive files: spectral selection and successive approximation over several scans);
 // it writes the quantised coefficients straight into pinned memory.  Everything after it runs on the device and follows
 // libjpeg-turbo's default decompression path bit for bit (restated in oracle/jpegops.py, pinned against cv2):
 //
@@ -11,8 +12,9 @@
 //   k_jpeg_to_bgr   jdsample.c "fancy" chroma up-sampling (h2v1: 3/4 + 1/4 with alternating rounding, h2v2: the same
 //                   both ways; edge rows / columns replicated) + jdcolor.c YCbCr -> RGB in 16-bit fixed point, BGR out
 //
-// Files outside this subset -- progressive or arithmetic-coded, 12-bit, CMYK / Adobe-marked, more than one scan,
-// sampling other than 4:4:4 / 4:2:2 / 4:2:0, an Exif orientation to apply -- are refused (LLFE_E_UNSUPPORTED) and the
+// Files outside this subset -- arithmetic-coded, 12-bit, CMYK / Adobe-marked, sequential files with more than one scan,
+// progressions that stop before every coefficient is complete (libjpeg smooths those), sampling other than 4:4:4 /
+// 4:2:2 / 4:2:0, an Exif orientation to apply -- are refused (LLFE_E_UNSUPPORTED) and the
 // caller hands them to cv2.imdecode, as it does with every file this decoder finds damaged.
 #include <string.h>
 
@@ -55,6 +57,8 @@ struct JInfo {
     const uint8_t* scan = nullptr;
     const uint8_t* end = nullptr;
     size_t coef_count = 0, plane_bytes = 0;
+    bool progressive = false;
+    size_t first_sos = 0;    // offset of the length field of the first SOS segment
 };
 
 bool build_huff(const uint8_t* counts, const uint8_t* vals, int nvals, JHuff* h) {
@@ -139,8 +143,9 @@ int jpeg_parse(const uint8_t* buf, size_t len, JInfo* J) {
                 if (!build_huff(seg + q + 1, seg + q + 17, nv, tc ? &J->ac[th] : &J->dc[th])) return LLFE_E_INVALID;
                 q += 17 + nv;
             }
-        } else if (m == 0xC0 || m == 0xC1) {
+        } else if (m == 0xC0 || m == 0xC1 || m == 0xC2) {
             if (have_frame || sl < 6) return LLFE_E_INVALID;
+            J->progressive = m == 0xC2;
             if (seg[0] != 8) return LLFE_E_UNSUPPORTED;
             J->height = (seg[1] << 8) | seg[2];
             J->width = (seg[3] << 8) | seg[4];
@@ -156,13 +161,18 @@ int jpeg_parse(const uint8_t* buf, size_t len, JInfo* J) {
                 if (c.tq > 3 || c.h < 1 || c.v < 1) return LLFE_E_INVALID;
             }
             have_frame = true;
-        } else if (m >= 0xC2 && m <= 0xCF && m != 0xC4 && m != 0xC8 && m != 0xCC) {
-            return LLFE_E_UNSUPPORTED;   // progressive, lossless, arithmetic
+        } else if (m >= 0xC3 && m <= 0xCF && m != 0xC4 && m != 0xC8 && m != 0xCC) {
+            return LLFE_E_UNSUPPORTED;   // lossless, hierarchical, arithmetic
         } else if (m == 0xDD) {
             if (sl < 2) return LLFE_E_INVALID;
             J->ri = (seg[0] << 8) | seg[1];
         } else if (m == 0xDA) {
             if (!have_frame || sl < 1) return LLFE_E_INVALID;
+            if (J->progressive) {      // the scans are walked by jpeg_progressive_decode
+                J->first_sos = pos - n;
+                J->end = buf + len;
+                break;
+            }
             const int ns = seg[0];
             if (ns != J->ncomp || sl < (size_t)(4 + 2 * ns)) return LLFE_E_UNSUPPORTED;   // one interleaved scan only
             for (int i = 0; i < ns; ++i) {
@@ -207,6 +217,8 @@ int jpeg_parse(const uint8_t* buf, size_t len, JInfo* J) {
     }
     J->coef_count = co;
     J->plane_bytes = po;
+    for (int i = 0; i < J->ncomp; ++i)
+        if (!J->qt_present[J->comp[i].tq]) return LLFE_E_INVALID;
     return LLFE_OK;
 }
 
@@ -346,6 +358,221 @@ int jpeg_entropy_decode(const JInfo& J, int16_t* coef, std::atomic<int>* rows_do
     }
     if (b.cnt < b.fake) return LLFE_E_INVALID;
     return LLFE_OK;
+}
+
+// ---- progressive (SOF2, T.81 Annex G): several scans refine the same coefficient arrays ----------------------------------------
+struct JScanComp {
+    int ci, td, ta;
+};
+
+int jpeg_progressive_decode(JInfo& J, const uint8_t* buf, size_t len, int16_t* coef) {
+    memset(coef, 0, J.coef_count * sizeof(int16_t));
+    int8_t prec[3][64];               // point transform each coefficient has been sent with so far (-1: not yet)
+    memset(prec, -1, sizeof prec);
+    size_t pos = J.first_sos;
+    for (;;) {
+        // ---- scan header
+        if (pos + 2 > len) return LLFE_E_INVALID;
+        const size_t n = ((size_t)buf[pos] << 8) | buf[pos + 1];
+        if (n < 3 || pos + n > len) return LLFE_E_INVALID;
+        const uint8_t* seg = buf + pos + 2;
+        const int ns = seg[0];
+        if (ns < 1 || ns > J.ncomp || n < (size_t)(6 + 2 * ns)) return LLFE_E_INVALID;
+        JScanComp sc[3];
+        for (int i = 0; i < ns; ++i) {
+            int ci = -1;
+            for (int c = 0; c < J.ncomp; ++c)
+                if (J.comp[c].id == seg[1 + 2 * i]) ci = c;
+            if (ci < 0) return LLFE_E_INVALID;
+            sc[i] = JScanComp{ci, seg[2 + 2 * i] >> 4, seg[2 + 2 * i] & 15};
+            if (sc[i].td > 3 || sc[i].ta > 3) return LLFE_E_INVALID;
+        }
+        const int ss = seg[1 + 2 * ns], se = seg[2 + 2 * ns], ah = seg[3 + 2 * ns] >> 4, al = seg[3 + 2 * ns] & 15;
+        if (ss > se || se > 63 || (ss == 0 && se != 0) || (ss > 0 && ns != 1) || al > 13 || (ah != 0 && ah != al + 1)) return LLFE_E_INVALID;
+        for (int i = 0; i < ns; ++i) {
+            if (ss == 0 && ah == 0 && !J.dc[sc[i].td].present) return LLFE_E_INVALID;
+            if (ss > 0 && !J.ac[sc[i].ta].present) return LLFE_E_INVALID;
+            for (int k = ss; k <= se; ++k) {
+                int8_t& p = prec[sc[i].ci][k];
+                if (ah == 0 ? p != -1 : p != ah) return LLFE_E_UNSUPPORTED;      // an unusual progression: libjpeg's call
+                p = (int8_t)al;
+            }
+        }
+        // ---- entropy-coded data of the scan
+        JBits b;
+        b.p = buf + pos + n;
+        b.end = buf + len;
+        int pred[3] = {0, 0, 0};
+        int eobrun = 0;
+        int uw, uh;                   // units of the scan: MCUs, or the blocks of its one component (real size)
+        if (ns > 1) {
+            uw = J.mcux, uh = J.mcuy;
+        } else {
+            uw = (J.comp[sc[0].ci].cw + 7) / 8, uh = (J.comp[sc[0].ci].ch + 7) / 8;
+        }
+        const int total = uw * uh;
+        int until_restart = J.ri ? J.ri : total + 1;
+        const int bit = 1 << al;
+        for (int u = 0; u < total; ++u) {
+            if (until_restart == 0) {
+                b.fill();
+                if (!(b.marker >= 0xD0 && b.marker <= 0xD7)) return LLFE_E_INVALID;
+                b.p += 2;
+                b.buf = 0, b.cnt = 0, b.marker = 0, b.fake = 0;
+                pred[0] = pred[1] = pred[2] = 0;
+                eobrun = 0;
+                until_restart = J.ri;
+            }
+            --until_restart;
+            if (b.cnt < b.fake) return LLFE_E_INVALID;
+            const int uy = u / uw, ux = u - uy * uw;
+            for (int i = 0; i < ns; ++i) {
+                const JComp& c = J.comp[sc[i].ci];
+                const int nv = ns > 1 ? c.v : 1, nh = ns > 1 ? c.h : 1;
+                for (int by = 0; by < nv; ++by)
+                    for (int bx = 0; bx < nh; ++bx) {
+                        int16_t* blk = coef + c.coef_off + ((size_t)(uy * nv + by) * c.bw + (ux * nh + bx)) * 64;
+                        if (ss == 0) {
+                            b.fill();
+                            if (ah == 0) {
+                                const int t = jdecode(b, J.dc[sc[i].td]);
+                                if (t < 0 || t > 15) return LLFE_E_INVALID;
+                                if (t) {
+                                    pred[sc[i].ci] += jextend((int)b.peek(t), t);
+                                    b.drop(t);
+                                }
+                                blk[0] = (int16_t)(pred[sc[i].ci] * bit);
+                            } else {
+                                if (b.peek(1)) blk[0] |= (int16_t)bit;
+                                b.drop(1);
+                            }
+                            continue;
+                        }
+                        const JHuff& ha = J.ac[sc[i].ta];
+                        if (ah == 0) {
+                            if (eobrun) {
+                                --eobrun;
+                                continue;
+                            }
+                            for (int k = ss; k <= se;) {
+                                b.fill();
+                                const int rs = jdecode(b, ha);
+                                if (rs < 0) return LLFE_E_INVALID;
+                                const int r = rs >> 4, s2 = rs & 15;
+                                if (s2 == 0) {
+                                    if (r < 15) {
+                                        eobrun = (1 << r) - 1;
+                                        if (r) {
+                                            eobrun += (int)b.peek(r);
+                                            b.drop(r);
+                                        }
+                                        break;
+                                    }
+                                    k += 16;
+                                } else {
+                                    k += r;
+                                    if (k > se) return LLFE_E_INVALID;
+                                    blk[JZIGZAG[k]] = (int16_t)(jextend((int)b.peek(s2), s2) * bit);
+                                    b.drop(s2);
+                                    ++k;
+                                }
+                            }
+                            continue;
+                        }
+                        // refinement of AC coefficients: a correction bit for every coefficient that is already non-zero,
+                        // new +-1 coefficients (at this bit position) placed by zero runs over the still-zero ones
+                        auto refine = [&](int16_t* p) {
+                            b.fill();
+                            if (b.peek(1) && (*p & bit) == 0) *p = (int16_t)(*p > 0 ? *p + bit : *p - bit);
+                            b.drop(1);
+                        };
+                        if (eobrun) {
+                            --eobrun;
+                            for (int k = ss; k <= se; ++k)
+                                if (blk[JZIGZAG[k]] != 0) refine(blk + JZIGZAG[k]);
+                            continue;
+                        }
+                        for (int k = ss; k <= se;) {
+                            b.fill();
+                            const int rs = jdecode(b, ha);
+                            if (rs < 0) return LLFE_E_INVALID;
+                            int r = rs >> 4;
+                            const int s2 = rs & 15;
+                            int val = 0;
+                            if (s2 == 0) {
+                                if (r < 15) {
+                                    eobrun = (1 << r) - 1;
+                                    if (r) {
+                                        eobrun += (int)b.peek(r);
+                                        b.drop(r);
+                                    }
+                                    r = 64;       // the rest of the band only gets correction bits
+                                }
+                            } else {
+                                if (s2 != 1) return LLFE_E_INVALID;
+                                val = b.peek(1) ? bit : -bit;
+                                b.drop(1);
+                            }
+                            while (k <= se) {
+                                int16_t* p = blk + JZIGZAG[k++];
+                                if (*p != 0) {
+                                    refine(p);
+                                } else {
+                                    if (r == 0) {
+                                        if (s2) *p = (int16_t)val;
+                                        break;
+                                    }
+                                    --r;
+                                }
+                            }
+                        }
+                    }
+            }
+        }
+        if (b.cnt < b.fake) return LLFE_E_INVALID;
+        // ---- to the next marker: the reader stands on its FF if it has seen it, else search
+        const uint8_t* q = b.p;
+        if (!b.marker)
+            while (q + 1 < buf + len && !(q[0] == 0xFF && q[1] != 0 && !(q[1] >= 0xD0 && q[1] <= 0xD7))) ++q;
+        pos = (size_t)(q - buf);
+        for (;;) {                    // tables may change between scans
+            if (pos + 2 > len || buf[pos] != 0xFF) return LLFE_E_INVALID;
+            while (pos < len && buf[pos] == 0xFF) ++pos;
+            if (pos >= len) return LLFE_E_INVALID;
+            const int m = buf[pos++];
+            if (m == 0xD9) {
+                for (int c = 0; c < J.ncomp; ++c)
+                    for (int k = 0; k < 64; ++k)
+                        if (prec[c][k] != 0) return LLFE_E_UNSUPPORTED;   // incomplete progression: libjpeg smooths such files
+                return LLFE_OK;
+            }
+            if (pos + 2 > len) return LLFE_E_INVALID;
+            const size_t sn = ((size_t)buf[pos] << 8) | buf[pos + 1];
+            if (sn < 2 || pos + sn > len) return LLFE_E_INVALID;
+            if (m == 0xDA) break;     // pos is at the length field of the next scan header
+            const uint8_t* sg = buf + pos + 2;
+            const size_t sl = sn - 2;
+            if (m == 0xC4) {
+                size_t o = 0;
+                while (o < sl) {
+                    if (o + 17 > sl) return LLFE_E_INVALID;
+                    const int tc = sg[o] >> 4, th = sg[o] & 15;
+                    if (tc > 1 || th > 3) return LLFE_E_INVALID;
+                    int nvv = 0;
+                    for (int i = 0; i < 16; ++i) nvv += sg[o + 1 + i];
+                    if (nvv > 256 || o + 17 + nvv > sl) return LLFE_E_INVALID;
+                    if (!build_huff(sg + o + 1, sg + o + 17, nvv, tc ? &J.ac[th] : &J.dc[th])) return LLFE_E_INVALID;
+                    o += 17 + nvv;
+                }
+            } else if (m == 0xDD) {
+                if (sl < 2) return LLFE_E_INVALID;
+                J.ri = (sg[0] << 8) | sg[1];
+            } else if (m == 0xDB || (m >= 0xC0 && m <= 0xCF)) {
+                return LLFE_E_UNSUPPORTED;     // new quantisation tables / frames between scans
+            }
+            pos += sn;
+        }
+    }
 }
 
 // ---- device side ------------------------------------------------------------------------------------------------------
@@ -506,7 +733,7 @@ extern "C" int llfe_jpeg_coefficients(const uint8_t* buf, size_t len, int16_t* o
     int rc = jpeg_parse(buf, len, J);
     if (rc == LLFE_OK) {
         *count = J->coef_count;
-        if (cap >= J->coef_count) rc = jpeg_entropy_decode(*J, out);
+        if (cap >= J->coef_count) rc = J->progressive ? jpeg_progressive_decode(*J, buf, len, out) : jpeg_entropy_decode(*J, out);
     }
     if (rc != LLFE_OK) llfe_set_error("llfe_jpeg_coefficients: unsupported or damaged file");
     delete J;
@@ -573,9 +800,9 @@ int llfe_jpeg_decode_impl(llfe_ctx* ctx, const uint8_t* buf, size_t len, int h, 
         }
         return LLFE_OK;
     };
-    const int bands = (J->coef_count * 2 >= (size_t(1) << 20) && J->mcuy >= 16) ? 8 : 1;
+    const int bands = (!J->progressive && J->coef_count * 2 >= (size_t(1) << 20) && J->mcuy >= 16) ? 8 : 1;
     if (bands == 1) {
-        rc = jpeg_entropy_decode(*J, p_coef);
+        rc = J->progressive ? jpeg_progressive_decode(*J, buf, len, p_coef) : jpeg_entropy_decode(*J, p_coef);
         if (rc != LLFE_OK) {
             llfe_set_error("llfe_jpeg_decode_host: damaged entropy-coded data");
             return rc;

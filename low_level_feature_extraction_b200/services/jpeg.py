@@ -1,11 +1,11 @@
-"""`cv2.imdecode(buf, cv2.IMREAD_COLOR)` for baseline JPEG input with everything after the entropy decoding on the GPU
+"""`cv2.imdecode(buf, cv2.IMREAD_COLOR)` for baseline and progressive JPEG input with everything after the entropy decoding on the GPU
 (reference call sites: app/services/analyze/utils.py:108-109, image_processor.py:62-66, :208-211).
 
 The Huffman-coded segment is one serial bit-level decode and runs on the calling host thread inside the library
 (csrc/k_jpeg.cu), writing the quantised coefficients into pinned memory; dequantisation, libjpeg-turbo's islow IDCT, the
 "fancy" chroma up-sampling and the YCbCr -> BGR conversion run on the device, bit for bit what OpenCV's libjpeg-turbo
-produces.  Files outside the subset (progressive, arithmetic-coded, 12-bit, CMYK / Adobe-marked, several scans, unusual
-sampling, an Exif segment whose orientation OpenCV would apply) and files the decoder finds damaged return None and the
+produces.  Files outside the subset (arithmetic-coded, 12-bit, CMYK / Adobe-marked, sequential files with several scans, incomplete
+progressions, unusual sampling, an Exif segment whose orientation OpenCV would apply) and files the decoder finds damaged return None and the
 caller hands the buffer to `cv2.imdecode`, so OpenCV keeps deciding what those decode to."""
 from __future__ import annotations
 

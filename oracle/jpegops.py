@@ -316,3 +316,209 @@ def imdecode_color(buf: bytes) -> np.ndarray:
         g = planes[0].astype(np.uint8)
         return np.stack([g, g, g], -1)
     return ycc_to_bgr(planes[0], planes[1], planes[2])
+
+
+# ---- progressive JPEG (SOF2): T.81 Annex G -- several scans fill the same coefficient arrays -----------------------------
+
+def _segments(buf: bytes):
+    """yield (marker, segment payload, position after the segment) for the marker segments of the file"""
+    pos = 2
+    while pos + 4 <= len(buf):
+        assert buf[pos] == 0xFF
+        while buf[pos] == 0xFF:
+            pos += 1
+        m = buf[pos]
+        pos += 1
+        if m == 0xD9:
+            return
+        if m in (0x01,) or 0xD0 <= m <= 0xD7:
+            continue
+        (n,) = struct.unpack(">H", buf[pos:pos + 2])
+        yield m, buf[pos + 2:pos + n], pos + n
+        pos += n
+        if m == 0xDA:       # skip the entropy-coded data up to the next marker that is not RSTn / stuffing
+            while pos + 1 < len(buf) and not (buf[pos] == 0xFF and buf[pos + 1] != 0 and not 0xD0 <= buf[pos + 1] <= 0xD7):
+                pos += 1
+
+
+def decode_progressive(buf: bytes):
+    """-> (coef per component as in entropy_decode, (hmax, vmax, mcux, mcuy), comps, qt, width, height)"""
+    qt, dc, ac = {}, {}, {}
+    frame = None
+    ri = 0
+    coef = None
+    for m, seg, after in _segments(buf):
+        if m == 0xDB:
+            q = 0
+            while q < len(seg):
+                pq, tq = seg[q] >> 4, seg[q] & 15
+                q += 1
+                vals = struct.unpack(">64H", seg[q:q + 128]) if pq else list(seg[q:q + 64])
+                q += 128 if pq else 64
+                t = np.zeros(64, np.int64)
+                t[ZIGZAG] = np.array(vals, np.int64)
+                qt[tq] = t
+        elif m == 0xC4:
+            q = 0
+            while q < len(seg):
+                tc, th = seg[q] >> 4, seg[q] & 15
+                counts = list(seg[q + 1:q + 17])
+                nsym = sum(counts)
+                (ac if tc else dc)[th] = Huff(counts, list(seg[q + 17:q + 17 + nsym]))
+                q += 17 + nsym
+        elif m == 0xC2:
+            p, h, w, nc = struct.unpack(">BHHB", seg[:6])
+            comps = [(seg[6 + 3 * i], seg[7 + 3 * i] >> 4, seg[7 + 3 * i] & 15, seg[8 + 3 * i]) for i in range(nc)]
+            if nc == 1:
+                comps = [(comps[0][0], 1, 1, comps[0][3])]
+            hmax = max(c[1] for c in comps)
+            vmax = max(c[2] for c in comps)
+            mcux = -(-w // (8 * hmax))
+            mcuy = -(-h // (8 * vmax))
+            frame = (w, h, comps, hmax, vmax, mcux, mcuy)
+            coef = [np.zeros((mcuy * c[2], mcux * c[1], 64), np.int64) for c in comps]
+        elif m == 0xDD:
+            (ri,) = struct.unpack(">H", seg[:2])
+        elif m == 0xDA:
+            w, h, comps, hmax, vmax, mcux, mcuy = frame
+            ns = seg[0]
+            scan = []
+            for i in range(ns):
+                cid = seg[1 + 2 * i]
+                ci = [c[0] for c in comps].index(cid)
+                scan.append((ci, seg[2 + 2 * i] >> 4, seg[2 + 2 * i] & 15))
+            ss, se, ahal = seg[1 + 2 * ns], seg[2 + 2 * ns], seg[3 + 2 * ns]
+            ah, al = ahal >> 4, ahal & 15
+            # entropy data of this scan: up to the next non-RST marker
+            end = after
+            while end + 1 < len(buf) and not (buf[end] == 0xFF and buf[end + 1] != 0 and not 0xD0 <= buf[end + 1] <= 0xD7):
+                end += 1
+            data = buf[after:end]
+            segs = []
+            cur = bytearray()
+            i = 0
+            while i < len(data):
+                if data[i] == 0xFF and i + 1 < len(data) and 0xD0 <= data[i + 1] <= 0xD7:
+                    segs.append(bytes(cur))
+                    cur = bytearray()
+                    i += 2
+                    continue
+                cur.append(data[i])
+                i += 1
+            segs.append(bytes(cur))
+            # the units of the scan: MCUs (interleaved) or the blocks of the one component (its real size, not MCU-padded)
+            if ns > 1:
+                units = [(my, mx) for my in range(mcuy) for mx in range(mcux)]
+            else:
+                c = comps[scan[0][0]]
+                bw = -(-(-(-w * c[1] // hmax)) // 8)
+                bh = -(-(-(-h * c[2] // vmax)) // 8)
+                units = [(by, bx) for by in range(bh) for bx in range(bw)]
+            per = ri if ri else len(units)
+            ui = 0
+            for sdata in segs:
+                br = Bits(sdata)
+                pred = [0] * len(comps)
+                eobrun = 0
+                for _ in range(per):
+                    if ui >= len(units):
+                        break
+                    uy, ux = units[ui]
+                    ui += 1
+                    blocks = []
+                    if ns > 1:
+                        for (ci, td, ta) in scan:
+                            c = comps[ci]
+                            for by in range(c[2]):
+                                for bx in range(c[1]):
+                                    blocks.append((ci, td, ta, coef[ci][uy * c[2] + by, ux * c[1] + bx]))
+                    else:
+                        ci, td, ta = scan[0]
+                        blocks.append((ci, td, ta, coef[ci][uy, ux]))
+                    for ci, td, ta, blk in blocks:
+                        if ss == 0:
+                            if ah == 0:
+                                t = br.symbol(dc[td])
+                                pred[ci] += extend(br.bits(t), t) if t else 0
+                                blk[0] = pred[ci] * (1 << al)
+                            elif br.bit():
+                                blk[0] |= 1 << al
+                            continue
+                        if ah == 0:
+                            if eobrun:
+                                eobrun -= 1
+                                continue
+                            k = ss
+                            while k <= se:
+                                rs = br.symbol(ac[ta])
+                                r, s = rs >> 4, rs & 15
+                                if s == 0:
+                                    if r < 15:
+                                        eobrun = (1 << r) - 1 + (br.bits(r) if r else 0)
+                                        break
+                                    k += 16
+                                else:
+                                    k += r
+                                    blk[ZIGZAG[k]] = extend(br.bits(s), s) * (1 << al)
+                                    k += 1
+                        else:
+                            bit = 1 << al
+
+                            def refine(idx):
+                                v = blk[idx]
+                                if br.bit() and (v & bit) == 0:
+                                    blk[idx] = v + bit if v > 0 else v - bit
+
+                            if eobrun:
+                                eobrun -= 1
+                                for k in range(ss, se + 1):
+                                    if blk[ZIGZAG[k]] != 0:
+                                        refine(ZIGZAG[k])
+                                continue
+                            k = ss
+                            while k <= se:
+                                rs = br.symbol(ac[ta])
+                                r, s = rs >> 4, rs & 15
+                                val = 0
+                                if s == 0:
+                                    if r < 15:
+                                        eobrun = (1 << r) - 1 + (br.bits(r) if r else 0)
+                                        r = 64
+                                else:
+                                    val = bit if br.bit() else -bit
+                                while k <= se:
+                                    idx = ZIGZAG[k]
+                                    k += 1
+                                    if blk[idx] != 0:
+                                        refine(idx)
+                                    else:
+                                        if r == 0:
+                                            if s:
+                                                blk[idx] = val
+                                            break
+                                        r -= 1
+    w, h, comps, hmax, vmax, mcux, mcuy = frame
+    return coef, (hmax, vmax, mcux, mcuy), comps, qt, w, h
+
+
+def imdecode_color_progressive(buf: bytes) -> np.ndarray:
+    coef, (hmax, vmax, mcux, mcuy), comps, qt, w, h = decode_progressive(buf)
+    planes = []
+    for ci, c in enumerate(comps):
+        p = plane(coef[ci], qt[c[3]])
+        cw = -(-w * c[1] // hmax)
+        ch = -(-h * c[2] // vmax)
+        p = p[:ch, :cw]
+        if c[1] == hmax and c[2] == vmax:
+            up = p
+        elif c[1] * 2 == hmax and c[2] == vmax:
+            up = h2v1_fancy(p)
+        elif c[1] * 2 == hmax and c[2] * 2 == vmax:
+            up = h2v2_fancy(p)
+        else:
+            raise ValueError("sampling not restated")
+        planes.append(up[:h, :w].astype(np.int64))
+    if len(planes) == 1:
+        g = planes[0].astype(np.uint8)
+        return np.stack([g, g, g], -1)
+    return ycc_to_bgr(planes[0], planes[1], planes[2])

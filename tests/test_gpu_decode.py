@@ -220,7 +220,8 @@ def test_jpeg_decode_large_files_and_every_sampling():
 
     for h, w, seed in [(1080, 1920, 3), (2160, 3840, 4), (1081, 1919, 5), (7, 2500, 6), (2500, 7, 7)]:
         img = design_image(h, w, seed) if min(h, w) > 16 else noise_image(h, w, seed)
-        for params in ([], [cv2.IMWRITE_JPEG_QUALITY, 70], [cv2.IMWRITE_JPEG_SAMPLING_FACTOR, cv2.IMWRITE_JPEG_SAMPLING_FACTOR_444],
+        for params in ([], [cv2.IMWRITE_JPEG_QUALITY, 70], [cv2.IMWRITE_JPEG_PROGRESSIVE, 1, cv2.IMWRITE_JPEG_QUALITY, 85],
+                       [cv2.IMWRITE_JPEG_SAMPLING_FACTOR, cv2.IMWRITE_JPEG_SAMPLING_FACTOR_444],
                        [cv2.IMWRITE_JPEG_SAMPLING_FACTOR, cv2.IMWRITE_JPEG_SAMPLING_FACTOR_422, cv2.IMWRITE_JPEG_RST_INTERVAL, 7]):
             buf = jpeg_encode(img, *params)
             ref = cv2_decode(buf)
@@ -238,8 +239,12 @@ def test_jpeg_files_outside_the_subset_go_to_opencv():
 
     img = design_image(200, 300, 9)
     prog = jpeg_encode(img, cv2.IMWRITE_JPEG_PROGRESSIVE, 1)
-    assert jpeg.decode(prog) is None
-    assert np.array_equal(png.imdecode_color(prog), cv2_decode(prog))
+    assert np.array_equal(jpeg.decode(prog), cv2_decode(prog))          # progressive files are decoded here too
+    sos = [i for i in range(len(prog) - 1) if prog[i] == 0xFF and prog[i + 1] == 0xDA]
+    early = prog[:sos[3]] + b"\xff\xd9"                                   # an incomplete progression is OpenCV's call
+    assert jpeg.decode(early) is None
+    ref, got = cv2_decode(early), png.imdecode_color(early)
+    assert (ref is None and got is None) or np.array_equal(ref, got)
     base = jpeg_encode(img)
     cut = base[:len(base) * 2 // 3]                       # truncated: libjpeg pads with gray, this decoder defers
     assert jpeg.decode(cut) is None

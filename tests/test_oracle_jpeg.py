@@ -38,6 +38,15 @@ def cases():
     yield "optimised tables", encode(b, cv2.IMWRITE_JPEG_OPTIMIZE, 1)
     yield "1 x 1", encode(noise[:1, :1])
     yield "17 x 9", encode(noise[:9, :17], cv2.IMWRITE_JPEG_QUALITY, 30)
+    P = cv2.IMWRITE_JPEG_PROGRESSIVE
+    yield "progressive 420", encode(a, P, 1)
+    yield "progressive odd q50", encode(b, P, 1, cv2.IMWRITE_JPEG_QUALITY, 50)
+    yield "progressive gray", encode(cv2.cvtColor(b, cv2.COLOR_BGR2GRAY), P, 1)
+    yield "progressive 444", encode(b, P, 1, cv2.IMWRITE_JPEG_SAMPLING_FACTOR, cv2.IMWRITE_JPEG_SAMPLING_FACTOR_444)
+    yield "progressive 422 restart", encode(b, P, 1, cv2.IMWRITE_JPEG_SAMPLING_FACTOR, cv2.IMWRITE_JPEG_SAMPLING_FACTOR_422,
+                                            cv2.IMWRITE_JPEG_RST_INTERVAL, 3)
+    yield "progressive noise q100", encode(noise, P, 1, cv2.IMWRITE_JPEG_QUALITY, 100)
+    yield "progressive optimised", encode(b, P, 1, cv2.IMWRITE_JPEG_OPTIMIZE, 1)
 
 
 CASES = list(cases())
@@ -45,7 +54,8 @@ CASES = list(cases())
 
 @pytest.mark.parametrize("name,buf", CASES, ids=[c[0] for c in CASES])
 def test_oracle_equals_cv2(name, buf):
-    assert np.array_equal(jpegops.imdecode_color(buf), cv2_decode(buf))
+    dec = jpegops.imdecode_color_progressive if name.startswith("progressive") else jpegops.imdecode_color
+    assert np.array_equal(dec(buf), cv2_decode(buf))
 
 
 @pytest.fixture(scope="module")
@@ -64,7 +74,10 @@ def test_native_entropy_decoder_equals_the_oracle(lib, name, buf):
     assert lib.llfe_jpeg_coefficients(buf, len(buf), None, 0, C.byref(n)) == 0
     out = np.zeros(n.value, np.int16)
     assert lib.llfe_jpeg_coefficients(buf, len(buf), out.ctypes.data, n.value, C.byref(n)) == 0
-    coef, _, _ = jpegops.entropy_decode(jpegops.parse(buf))
+    if name.startswith("progressive"):
+        coef = jpegops.decode_progressive(buf)[0]
+    else:
+        coef, _, _ = jpegops.entropy_decode(jpegops.parse(buf))
     want = np.concatenate([c.reshape(-1) for c in coef]).astype(np.int16)
     assert np.array_equal(out, want)
 
@@ -74,9 +87,16 @@ def test_files_outside_the_subset_are_refused(lib):
 
     img = design_image(40, 56, 3)
     info = (C.c_int32 * 2)()
-    prog = encode(img, cv2.IMWRITE_JPEG_PROGRESSIVE, 1)
-    assert lib.llfe_jpeg_info(prog, len(prog), info) == -4                       # LLFE_E_UNSUPPORTED
     base = encode(img)
+    prog = encode(img, cv2.IMWRITE_JPEG_PROGRESSIVE, 1)
+    # a progression that stops early (libjpeg would smooth the blocks): cut the file after its third scan and close it
+    sos = [i for i in range(len(prog) - 1) if prog[i] == 0xFF and prog[i + 1] == 0xDA]
+    assert len(sos) > 4 and lib.llfe_jpeg_info(prog, len(prog), info) == 0
+    early = prog[:sos[3]] + b"\xff\xd9"
+    n0 = C.c_size_t(0)
+    lib.llfe_jpeg_coefficients(prog, len(prog), None, 0, C.byref(n0))
+    scratch = np.zeros(n0.value, np.int16)
+    assert lib.llfe_jpeg_coefficients(early, len(early), scratch.ctypes.data, n0.value, C.byref(n0)) == -4   # LLFE_E_UNSUPPORTED
     exif = base[:2] + b"\xff\xe1\x00\x10Exif\x00\x00" + b"\0" * 8 + base[2:]      # an Exif segment: OpenCV may rotate
     assert lib.llfe_jpeg_info(exif, len(exif), info) == -4
     assert lib.llfe_jpeg_info(b"\x89PNG\r\n\x1a\n" + b"0" * 32, 40, info) == -1  # not a JPEG

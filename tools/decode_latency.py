@@ -53,10 +53,10 @@ def main():
                                                                      info.color_type, info.bit_depth, None, 0, dst)),
         }
     from low_level_feature_extraction_b200.services import jpeg
-    for q in (95, 75):
-        jb = cv2.imencode(".jpg", img, [cv2.IMWRITE_JPEG_QUALITY, q])[1].tobytes()
+    for q, prog in ((95, 0), (75, 0), (90, 1)):
+        jb = cv2.imencode(".jpg", img, [cv2.IMWRITE_JPEG_QUALITY, q, cv2.IMWRITE_JPEG_PROGRESSIVE, prog])[1].tobytes()
         assert np.array_equal(jpeg.decode(jb), cv2.imdecode(np.frombuffer(jb, np.uint8), cv2.IMREAD_COLOR))
-        out[f"1080p_jpeg_q{q}"] = {
+        out[f"1080p_jpeg_q{q}" + ("_progressive" if prog else "")] = {
             "file_bytes": len(jb),
             "cv2_imdecode": med(lambda: cv2.imdecode(np.frombuffer(jb, np.uint8), cv2.IMREAD_COLOR)),
             "services_jpeg_decode": med(lambda: jpeg.decode(jb)),
