@@ -179,6 +179,12 @@ int64_t llfe_png_rowbytes(int w, int color_type, int bit_depth);
 int llfe_png_reconstruct(llfe_ctx* ctx, uint8_t* d_stream, int n, int h, int w, int color_type, int bit_depth,
                          const uint8_t* d_palette, uint8_t* d_bgr, int32_t* d_status);
 
+/* Adam7-interlaced PNGs (IHDR interlace method 1), one image per call: the stream holds seven reduced images, each
+ * filtered on its own; llfe_png_stream_bytes = size of the scanline stream for either interlace method (host-only). */
+int64_t llfe_png_stream_bytes(int w, int h, int color_type, int bit_depth, int interlace);
+int llfe_png_reconstruct_adam7(llfe_ctx* ctx, uint8_t* d_stream, int h, int w, int color_type, int bit_depth,
+                               const uint8_t* d_palette, uint8_t* d_bgr, int32_t* d_status);
+
 /* Host-only: inflate a zlib stream (RFC 1950 / 1951; the concatenated IDAT payloads of a PNG) into out, at most out_cap
  * bytes.  Failure (LLFE_E_INVALID) wherever zlib's inflate fails -- invalid code sets or symbols, distance too far back,
  * truncated input, Adler-32 mismatch; input beyond the point where the output is full is ignored, as libpng does once the
@@ -451,6 +457,9 @@ int llfe_png_reconstruct_host(llfe_ctx* ctx, const uint8_t* h_stream, int h, int
  * stream (short, invalid, bad filter byte) returns LLFE_E_INVALID. */
 int llfe_png_decode_host(llfe_ctx* ctx, const uint8_t* h_idat, size_t idat_bytes, int h, int w, int color_type, int bit_depth,
                          const uint8_t* h_palette, int palette_entries, uint8_t* h_bgr);
+/* llfe_png_decode_host for an Adam7-interlaced file (no overlap of inflate and reconstruction: the passes interleave rows) */
+int llfe_png_decode_adam7_host(llfe_ctx* ctx, const uint8_t* h_idat, size_t idat_bytes, int h, int w, int color_type,
+                               int bit_depth, const uint8_t* h_palette, int palette_entries, uint8_t* h_bgr);
 /* cv2.imdecode(buf, IMREAD_COLOR) of a baseline or progressive JPEG (utils.py:108-109, image_processor.py:62-66, :208-211): Huffman
  * decoding on the calling thread into pinned memory, libjpeg-turbo's islow IDCT, fancy chroma up-sampling and YCbCr -> BGR
  * conversion on the device, bit for bit.  h, w from llfe_jpeg_info.  Files outside the subset / damaged data:

@@ -227,6 +227,50 @@ __global__ void __launch_bounds__(256) k_png_to_bgr(const uint8_t* __restrict__ 
     o[0] = (uint8_t)b, o[1] = (uint8_t)g, o[2] = (uint8_t)r;
 }
 
+// Adam7 (PNG specification 8.2): the stream holds seven reduced images, pass p covering the pixels (x0 + i * dx, y0 + j * dy)
+struct PngAdam7 {
+    int h, w, color_type, depth;
+    unsigned int off[7];          // offset of each pass in the stream (empty passes: unused)
+    int rowbytes[7];
+};
+__constant__ uint8_t c_adam7_pass[64] = {0, 5, 3, 5, 1, 5, 3, 5, 6, 6, 6, 6, 6, 6, 6, 6, 4, 5, 4, 5, 4, 5, 4, 5, 6, 6, 6, 6, 6, 6, 6, 6,
+                                         2, 5, 3, 5, 2, 5, 3, 5, 6, 6, 6, 6, 6, 6, 6, 6, 4, 5, 4, 5, 4, 5, 4, 5, 6, 6, 6, 6, 6, 6, 6, 6};
+__constant__ uint8_t c_adam7_geom[7][4] = {{0, 0, 3, 3}, {4, 0, 3, 3}, {0, 4, 2, 3}, {2, 0, 2, 2}, {0, 2, 1, 2}, {1, 0, 1, 1}, {0, 1, 0, 1}};   // x0, y0, log2 dx, log2 dy
+
+__global__ void __launch_bounds__(256) k_png_adam7_to_bgr(const uint8_t* __restrict__ stream, PngAdam7 f,
+                                                          const uint8_t* __restrict__ palette, uint8_t* __restrict__ bgr) {
+    const int x = blockIdx.x * 256 + threadIdx.x, y = blockIdx.y;
+    if (x >= f.w) return;
+    const int p = c_adam7_pass[(y & 7) * 8 + (x & 7)];
+    const int px = (x - c_adam7_geom[p][0]) >> c_adam7_geom[p][2], py = (y - c_adam7_geom[p][1]) >> c_adam7_geom[p][3];
+    const uint8_t* row = stream + f.off[p] + (size_t)py * (f.rowbytes[p] + 1) + 1;
+    int r, g, b;
+    switch (f.color_type) {
+        case 0: {
+            int v = png_sample(row, px, f.depth);
+            if (f.depth < 8) v *= f.depth == 1 ? 255 : f.depth == 2 ? 85 : 17;
+            r = g = b = v;
+            break;
+        }
+        case 2:
+            r = png_sample(row, 3 * px, f.depth), g = png_sample(row, 3 * px + 1, f.depth), b = png_sample(row, 3 * px + 2, f.depth);
+            break;
+        case 3: {
+            const uint8_t* q = palette + 3 * png_sample(row, px, f.depth);
+            r = q[0], g = q[1], b = q[2];
+            break;
+        }
+        case 4:
+            r = g = b = png_sample(row, 2 * px, f.depth);
+            break;
+        default:
+            r = png_sample(row, 4 * px, f.depth), g = png_sample(row, 4 * px + 1, f.depth), b = png_sample(row, 4 * px + 2, f.depth);
+            break;
+    }
+    uint8_t* o = bgr + ((size_t)y * f.w + x) * 3;
+    o[0] = (uint8_t)b, o[1] = (uint8_t)g, o[2] = (uint8_t)r;
+}
+
 }  // namespace
 
 static int png_channels(int color_type) {
@@ -299,4 +343,48 @@ extern "C" int llfe_png_reconstruct(llfe_ctx* ctx, uint8_t* d_stream, int n, int
     LLFE_CUDA(cudaMemsetAsync(d_status, 0, (size_t)n * sizeof(int32_t), ctx->stream));
     LLFE_TRY(launch_png_unfilter_rows(ctx, d_stream, n, h, 0, h, rowbytes, png_filter_distance(color_type, bit_depth), d_status));
     return launch_png_to_bgr(ctx, d_stream, n, h, w, rowbytes, color_type, bit_depth, d_palette, d_bgr);
+}
+
+// ---- Adam7-interlaced files (one image per call) ---------------------------------------------------------------------------
+static const int ADAM7[7][4] = {{0, 0, 8, 8}, {4, 0, 8, 8}, {0, 4, 4, 8}, {2, 0, 4, 4}, {0, 2, 2, 4}, {1, 0, 2, 2}, {0, 1, 1, 2}};
+
+// size of the scanline stream of a w x h PNG; interlace = IHDR's interlace method (0 or 1)
+extern "C" int64_t llfe_png_stream_bytes(int w, int h, int color_type, int bit_depth, int interlace) {
+    if (llfe_png_rowbytes(w, color_type, bit_depth) < 0 || h <= 0 || interlace < 0 || interlace > 1) return -1;
+    if (!interlace) return (int64_t)h * (llfe_png_rowbytes(w, color_type, bit_depth) + 1);
+    int64_t total = 0;
+    for (int p = 0; p < 7; ++p) {
+        const int pw = w > ADAM7[p][0] ? (w - ADAM7[p][0] + ADAM7[p][2] - 1) / ADAM7[p][2] : 0;
+        const int ph = h > ADAM7[p][1] ? (h - ADAM7[p][1] + ADAM7[p][3] - 1) / ADAM7[p][3] : 0;
+        if (pw && ph) total += (int64_t)ph * (llfe_png_rowbytes(pw, color_type, bit_depth) + 1);
+    }
+    return total;
+}
+
+extern "C" int llfe_png_reconstruct_adam7(llfe_ctx* ctx, uint8_t* d_stream, int h, int w, int color_type, int bit_depth,
+                                          const uint8_t* d_palette, uint8_t* d_bgr, int32_t* d_status) {
+    LLFE_ENTER(ctx);
+    LLFE_CHECK_ARG(d_stream != nullptr && d_bgr != nullptr && d_status != nullptr && h > 0 && h <= 65535 && w > 0);
+    const int64_t total = llfe_png_stream_bytes(w, h, color_type, bit_depth, 1);
+    LLFE_CHECK_ARG(total > 0 && total < 0xffffffffll && (color_type != 3 || d_palette != nullptr));
+    const int bpp = png_filter_distance(color_type, bit_depth);
+    LLFE_CUDA(cudaMemsetAsync(d_status, 0, sizeof(int32_t), ctx->stream));
+    PngAdam7 f;
+    f.h = h, f.w = w, f.color_type = color_type, f.depth = bit_depth;
+    unsigned int off = 0;
+    for (int p = 0; p < 7; ++p) {
+        const int pw = w > ADAM7[p][0] ? (w - ADAM7[p][0] + ADAM7[p][2] - 1) / ADAM7[p][2] : 0;
+        const int ph = h > ADAM7[p][1] ? (h - ADAM7[p][1] + ADAM7[p][3] - 1) / ADAM7[p][3] : 0;
+        f.off[p] = off;
+        f.rowbytes[p] = 0;
+        if (!pw || !ph) continue;
+        const int rb = (int)llfe_png_rowbytes(pw, color_type, bit_depth);
+        f.rowbytes[p] = rb;
+        LLFE_TRY(launch_png_unfilter_rows(ctx, d_stream + off, 1, ph, 0, ph, rb, bpp, d_status));   // every pass is filtered on its own
+        off += (unsigned int)ph * (unsigned int)(rb + 1);
+    }
+    LLFE_KERNEL(ctx, "k_png_adam7_to_bgr");
+    k_png_adam7_to_bgr<<<dim3(ceil_div(w, 256), h), 256, 0, ctx->stream>>>(d_stream, f, d_palette, d_bgr);
+    LLFE_LAUNCHED(ctx);
+    return LLFE_OK;
 }

@@ -1035,6 +1035,51 @@ int llfe_png_decode_host(llfe_ctx* ctx, const uint8_t* h_idat, size_t idat_bytes
     return LLFE_OK;
 }
 
+int llfe_png_decode_adam7_host(llfe_ctx* ctx, const uint8_t* h_idat, size_t idat_bytes, int h, int w, int color_type,
+                               int bit_depth, const uint8_t* h_palette, int palette_entries, uint8_t* h_bgr) {
+    LLFE_ENTER(ctx);
+    LLFE_CHECK_ARG(h_idat != nullptr && h_bgr != nullptr && h > 0 && h <= 65535 && w > 0);
+    const int64_t total = llfe_png_stream_bytes(w, h, color_type, bit_depth, 1);
+    LLFE_CHECK_ARG(total > 0 && total < 0xffffffffll && palette_entries >= 0 && palette_entries <= 256 &&
+                   (color_type != 3 || h_palette != nullptr));
+    const size_t in = (size_t)total, out = (size_t)h * w * 3;
+    const size_t a = WsCarver::need(in), b = WsCarver::need(out) + 256;
+    LLFE_TRY(ensure_stage(ctx, a + b, a + b));
+    uint8_t* p_in = (uint8_t*)ctx->pin;
+    uint8_t* d_in = (uint8_t*)ctx->dev_stage;
+    uint8_t* d_out = d_in + a;
+    int32_t* d_status = (int32_t*)(d_out + WsCarver::need(out));
+    size_t got = 0;
+    if (llfe_inflate_zlib(h_idat, idat_bytes, p_in, in, &got) != LLFE_OK || got != in) {
+        llfe_set_error("llfe_png_decode_adam7_host: invalid, truncated or short deflate stream");
+        return LLFE_E_INVALID;
+    }
+    LLFE_CUDA(cudaMemcpyAsync(d_in, p_in, in, cudaMemcpyHostToDevice, ctx->stream));
+    uint8_t* d_pal = nullptr;
+    if (color_type == 3) {
+        void* ws;
+        LLFE_TRY(llfe_workspace(ctx, 1024, &ws));
+        uint8_t pal[768];
+        memset(pal, 0, sizeof pal);
+        memcpy(pal, h_palette, (size_t)palette_entries * 3);
+        d_pal = (uint8_t*)ws;
+        LLFE_CUDA(cudaMemcpyAsync(d_pal, pal, 768, cudaMemcpyHostToDevice, ctx->stream));   // pageable: staged before return
+    }
+    LLFE_TRY(llfe_png_reconstruct_adam7(ctx, d_in, h, w, color_type, bit_depth, d_pal, d_out, d_status));
+    uint8_t* p_out = p_in + a;
+    LLFE_CUDA(cudaMemcpyAsync(p_out, d_out, out, cudaMemcpyDeviceToHost, ctx->stream));
+    LLFE_CUDA(cudaMemcpyAsync(p_out + WsCarver::need(out), d_status, 4, cudaMemcpyDeviceToHost, ctx->stream));
+    LLFE_CUDA(cudaStreamSynchronize(ctx->stream));
+    int32_t status;
+    memcpy(&status, p_out + WsCarver::need(out), 4);
+    if (status != 0) {
+        llfe_set_error("llfe_png_decode_adam7_host: bad adaptive filter value");
+        return LLFE_E_INVALID;
+    }
+    memcpy(h_bgr, p_out, out);
+    return LLFE_OK;
+}
+
 int llfe_jpeg_decode_host(llfe_ctx* ctx, const uint8_t* h_buf, size_t len, int h, int w, uint8_t* h_bgr) {
     LLFE_ENTER(ctx);
     LLFE_CHECK_ARG(h_buf != nullptr && h_bgr != nullptr && h > 0 && w > 0 && len >= 4);

@@ -8,8 +8,8 @@ core, with the library's own inflate (csrc/h_inflate.cu, 1.1-1.4x zlib 1.2.11) w
 PNG filters) and the conversion OpenCV asks libpng for (palette / gray expansion, 16 -> 8 bits, alpha dropped,
 RGB -> BGR) run in `llfe_png_reconstruct*` (csrc/k_png.cu).
 
-`parse` returns None for anything the device path does not take -- not a PNG, Adam7 interlacing, APNG, an unknown
-chunk, a damaged file -- and the callers hand those buffers to `cv2.imdecode` exactly as the reference does, so the
+`parse` returns None for anything the device path does not take -- not a PNG, APNG, an unknown chunk, a damaged
+file -- and the callers hand those buffers to `cv2.imdecode` exactly as the reference does, so the
 decision "is this decodable, and to what" stays OpenCV's for every input outside the plain-PNG case.
 """
 from __future__ import annotations
@@ -41,6 +41,7 @@ class PngInfo:
     color_type: int
     palette: bytes          # RGB triples (colour type 3), else b""
     idat: bytes             # the concatenated IDAT payloads = one zlib stream
+    interlace: int = 0      # IHDR interlace method: 0, or 1 = Adam7
 
     @property
     def rowbytes(self) -> int:
@@ -48,7 +49,11 @@ class PngInfo:
 
     @property
     def stream_bytes(self) -> int:
-        return self.height * (self.rowbytes + 1)
+        if not self.interlace:
+            return self.height * (self.rowbytes + 1)
+        from .._native import load_library
+
+        return int(load_library().llfe_png_stream_bytes(self.width, self.height, self.color_type, self.bit_depth, 1))
 
 
 def parse(buf) -> PngInfo | None:
@@ -99,13 +104,13 @@ def parse(buf) -> PngInfo | None:
     if ihdr is None or not seen_iend or not idat:
         return None
     w, h, depth, color, comp, filt, interlace = ihdr
-    if color not in _CHANNELS or depth not in _DEPTHS[color] or comp != 0 or filt != 0 or interlace != 0:
+    if color not in _CHANNELS or depth not in _DEPTHS[color] or comp != 0 or filt != 0 or interlace not in (0, 1):
         return None
     if w == 0 or h == 0 or w * h > _MAX_PIXELS or h > 65535:
         return None
     if color == 3 and not palette:
         return None
-    return PngInfo(w, h, depth, color, palette, b"".join(idat))
+    return PngInfo(w, h, depth, color, palette, b"".join(idat), interlace)
 
 
 def inflate(info: PngInfo) -> bytes | None:
@@ -140,8 +145,9 @@ def decode(buf) -> np.ndarray | None:
 
     with _runtime.lock():
         try:
-            _runtime.context().call("llfe_png_decode_host", info.idat, len(info.idat), info.height, info.width,
-                                    info.color_type, info.bit_depth, info.palette or None, len(info.palette) // 3, out)
+            _runtime.context().call("llfe_png_decode_adam7_host" if info.interlace else "llfe_png_decode_host", info.idat,
+                                    len(info.idat), info.height, info.width, info.color_type, info.bit_depth,
+                                    info.palette or None, len(info.palette) // 3, out)
         except LlfeError as e:
             if e.code == LLFE_E_INVALID:
                 return None
@@ -156,6 +162,10 @@ def decode_many(bufs, workers: int = 8) -> list:
 
     infos = [parse(b) for b in bufs]
     out = [None] * len(bufs)
+    for k, info in enumerate(infos):
+        if info is not None and info.interlace:      # Adam7: the one-call path
+            out[k] = decode(bufs[k])
+            infos[k] = None
     with ThreadPoolExecutor(max_workers=workers) as ex:
         futures = [ex.submit(inflate, i) if i is not None else None for i in infos]
         for k, (info, fut) in enumerate(zip(infos, futures)):

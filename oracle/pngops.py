@@ -27,6 +27,20 @@ def chunks(buf: bytes):
         pos += 12 + n
 
 
+ADAM7 = [(0, 0, 8, 8), (4, 0, 8, 8), (0, 4, 4, 8), (2, 0, 4, 4), (0, 2, 2, 4), (1, 0, 2, 2), (0, 1, 1, 2)]   # x0, y0, dx, dy
+
+
+def adam7_passes(w: int, h: int):
+    """-> [(x0, y0, dx, dy, pass width, pass height)] of the non-empty passes (PNG specification 8.2)"""
+    out = []
+    for x0, y0, dx, dy in ADAM7:
+        pw = (w - x0 + dx - 1) // dx if w > x0 else 0
+        ph = (h - y0 + dy - 1) // dy if h > y0 else 0
+        if pw and ph:
+            out.append((x0, y0, dx, dy, pw, ph))
+    return out
+
+
 def parse(buf: bytes):
     """-> (w, h, depth, color_type, palette bytes, scanline stream)"""
     assert buf[:8] == b"\x89PNG\r\n\x1a\n"
@@ -39,7 +53,7 @@ def parse(buf: bytes):
         elif t == b"IDAT":
             idat.append(d)
     w, h, depth, color, _, _, interlace = ihdr
-    assert interlace == 0
+    parse.interlace = interlace
     return w, h, depth, color, pal, zlib.decompress(b"".join(idat))
 
 
@@ -118,9 +132,19 @@ def to_bgr(rows: np.ndarray, w: int, color: int, depth: int, palette: bytes) -> 
 
 def imdecode_color(buf: bytes) -> np.ndarray:
     w, h, depth, color, pal, stream = parse(buf)
-    rowbytes = (w * CHANNELS[color] * depth + 7) // 8
     bpp = max(1, CHANNELS[color] * depth // 8)
-    return to_bgr(unfilter(stream, h, rowbytes, bpp), w, color, depth, pal)
+    if not parse.interlace:
+        rowbytes = (w * CHANNELS[color] * depth + 7) // 8
+        return to_bgr(unfilter(stream, h, rowbytes, bpp), w, color, depth, pal)
+    # Adam7: seven reduced images, each filtered on its own, one after the other in the stream
+    out = np.zeros((h, w, 3), np.uint8)
+    off = 0
+    for x0, y0, dx, dy, pw, ph in adam7_passes(w, h):
+        rb = (pw * CHANNELS[color] * depth + 7) // 8
+        rows = unfilter(stream[off:off + ph * (rb + 1)], ph, rb, bpp)
+        off += ph * (rb + 1)
+        out[y0::dy, x0::dx] = to_bgr(rows, pw, color, depth, pal)
+    return out
 
 
 # ---- a PNG writer with a chosen filter per row (test input: Pillow / OpenCV pick their own) ---------------------------------
@@ -155,6 +179,39 @@ def filter_rows(rows: np.ndarray, bpp: int, filters) -> bytes:
         out += ((cur - pred) & 255).astype(np.uint8).tobytes()
         prev = cur
     return bytes(out)
+
+
+def pack_samples(samples: np.ndarray, depth: int) -> np.ndarray:
+    """(rows, n) integer samples of `depth` bits -> (rows, ceil(n * depth / 8)) packed bytes (MSB first)"""
+    r, n = samples.shape
+    if depth == 8:
+        return samples.astype(np.uint8)
+    if depth == 16:
+        o = np.zeros((r, 2 * n), np.uint8)
+        o[:, 0::2] = samples >> 8
+        o[:, 1::2] = samples & 255
+        return o
+    bits = np.zeros((r, n * depth), np.uint8)
+    for k in range(depth):
+        bits[:, k::depth] = (samples >> (depth - 1 - k)) & 1
+    pad = (-bits.shape[1]) % 8
+    if pad:
+        bits = np.concatenate([bits, np.zeros((r, pad), np.uint8)], 1)
+    return np.packbits(bits, axis=1)
+
+
+def write_png_interlaced(samples: np.ndarray, color: int, depth: int, rng, palette: bytes = b"", level: int = 6) -> bytes:
+    """samples: (h, w, channels) integers of `depth` bits -> an Adam7 PNG with random filter types per pass row"""
+    h, w, ch = samples.shape
+    bpp = max(1, ch * depth // 8)
+    stream = b""
+    for x0, y0, dx, dy, pw, ph in adam7_passes(w, h):
+        sub = samples[y0::dy, x0::dx].reshape(ph, pw * ch)
+        stream += filter_rows(pack_samples(sub, depth), bpp, rng.integers(0, 5, ph))
+    out = b"\x89PNG\r\n\x1a\n" + _chunk(b"IHDR", struct.pack(">IIBBBBB", w, h, depth, color, 0, 0, 1))
+    if palette:
+        out += _chunk(b"PLTE", palette)
+    return out + _chunk(b"IDAT", zlib.compress(stream, level)) + _chunk(b"IEND", b"")
 
 
 def write_png(rows: np.ndarray, w: int, color: int, depth: int, filters, palette: bytes = b"", extra=(), level: int = 6,

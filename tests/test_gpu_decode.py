@@ -10,7 +10,7 @@ import torch
 from PIL import Image
 
 from oracle import pilops, pngops
-from test_oracle_png import CASES, cv2_decode, make_case
+from test_oracle_png import ADAM7_SIZES, CASES, cv2_decode, make_adam7_case, make_case
 
 pytestmark = pytest.mark.gpu
 
@@ -29,6 +29,36 @@ def test_png_decode_equals_cv2(color, depth):
         got = png.decode(buf)
         assert got is not None
         assert np.array_equal(got, cv2_decode(buf)), (color, depth, h, w)
+
+
+@pytest.mark.parametrize("color,depth", CASES)
+def test_adam7_png_decode_equals_cv2(color, depth):
+    from low_level_feature_extraction_b200.services import png
+
+    for seed, (h, w) in enumerate(ADAM7_SIZES + [(300, 1037)]):
+        buf = make_adam7_case(color, depth, h, w, 1000 * color + 10 * depth + seed)
+        got = png.decode(buf)
+        assert got is not None
+        assert np.array_equal(got, cv2_decode(buf)), (color, depth, h, w)
+
+
+def test_adam7_png_1080p_in_a_batch_and_damaged():
+    from low_level_feature_extraction_b200.services import png
+    from low_level_feature_extraction_b200.synth import design_image
+
+    img = design_image(1080, 1920, 5)
+    buf = pngops.write_png_interlaced(img[:, :, ::-1].astype(np.int64), 2, 8, np.random.default_rng(0))
+    plain = cv2.imencode(".png", img)[1].tobytes()
+    out = png.decode_many([plain, buf, buf[:len(buf) // 2]])
+    assert np.array_equal(out[0], img) and np.array_equal(out[1], img) and out[2] is None
+    # a filter byte of 5 in pass 3: refused (the caller leaves the file to OpenCV)
+    w, h, depth, color, pal, stream = pngops.parse(buf)
+    s = bytearray(stream)
+    off = sum(ph * (3 * pw + 1) for _, _, _, _, pw, ph in pngops.adam7_passes(w, h)[:2])
+    s[off] = 5
+    import zlib as _z
+    bad = buf[:33] + pngops._chunk(b"IDAT", _z.compress(bytes(s), 1)) + pngops._chunk(b"IEND", b"")
+    assert png.parse(bad) is not None and png.decode(bad) is None
 
 
 def test_png_decode_1080p_files_from_pillow_and_opencv():

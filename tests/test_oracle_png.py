@@ -76,10 +76,10 @@ def test_product_parser_accepts_plain_pngs_and_defers_the_rest():
     assert (info.width, info.height, info.bit_depth, info.color_type) == (11, 9, 8, 2)
     w, h, depth, color, pal, stream = pngops.parse(buf)
     assert png.inflate(info) == stream and info.rowbytes == 33
-    # deferred to cv2.imdecode: not a PNG, interlaced, APNG / unknown chunk, damaged CRC, truncated file, short stream
+    # deferred to cv2.imdecode: not a PNG, unknown interlace method, APNG / unknown chunk, damaged CRC, truncated file, short stream
     assert png.parse(b"\xff\xd8\xff\xe0" + b"0" * 64) is None
     inter = bytearray(buf)
-    inter[28] = 1
+    inter[28] = 2
     inter[29:33] = struct.pack(">I", zlib.crc32(bytes(inter[12:29])))
     assert png.parse(bytes(inter)) is None
     assert png.parse(make_case(2, 8, 9, 11, 1, extra=[(b"acTL", b"\0" * 8)])) is None
@@ -92,6 +92,35 @@ def test_product_parser_accepts_plain_pngs_and_defers_the_rest():
     assert png.inflate(short) is None
     pal = make_case(3, 4, 6, 7, 2)
     assert len(png.parse(pal).palette) % 3 == 0 and png.parse(pal).rowbytes == 4
+
+
+ADAM7_SIZES = [(1, 1), (3, 5), (8, 8), (9, 17), (40, 67), (2, 1), (1, 7), (5, 2)]
+
+
+def make_adam7_case(color, depth, h, w, seed):
+    """an Adam7-interlaced file with random samples and a random filter type per pass row"""
+    rng = np.random.default_rng(seed)
+    hi, pal = 1 << depth, b""
+    if color == 3:
+        hi = min(hi, int(rng.integers(2, 257)))
+        pal = rng.integers(0, 256, hi * 3, dtype=np.uint8).tobytes()
+    s = rng.integers(0, hi, (h, w, pngops.CHANNELS[color]))
+    s[h // 2:] = (np.cumsum(rng.integers(-2, 3, s[h // 2:].shape), axis=1) + hi // 2) % hi   # smooth rows: every predictor branch
+    return pngops.write_png_interlaced(s, color, depth, rng, pal)
+
+
+@pytest.mark.parametrize("color,depth", CASES)
+def test_oracle_equals_cv2_on_adam7_files(color, depth):
+    """PNG specification 8.2: seven reduced images, each filtered on its own (passes narrower than the image are skipped)"""
+    from low_level_feature_extraction_b200.services import png
+
+    for seed, (h, w) in enumerate(ADAM7_SIZES):
+        buf = make_adam7_case(color, depth, h, w, 1000 * color + 10 * depth + seed)
+        ref = cv2_decode(buf)
+        assert ref is not None
+        assert np.array_equal(pngops.imdecode_color(buf), ref), (color, depth, h, w)
+        info = png.parse(buf)      # the product's parser takes the file and sizes the stream like the inflate does
+        assert info is not None and info.interlace == 1 and info.stream_bytes == len(pngops.parse(buf)[5])
 
 
 def test_parser_and_inflate_never_raise_on_damaged_files():
