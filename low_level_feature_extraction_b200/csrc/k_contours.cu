@@ -37,6 +37,7 @@ struct CtGeom {
     int hpr, pwT;           // transposed plane: (w + 2) rows of pwT = hpr + 2 words; pixel (x, y) = bit (y & 31) of
                             // word (y >> 5) + 1 of row x + 1
     size_t plane_words, planeT_words, sin_words, label_words;   // per image
+    int cut_shift;          // segments: cut rows are the rows y with y % (1 << cut_shift) == 0
 };
 
 __host__ __device__ inline CtGeom ct_geom(int h, int w) {
@@ -51,6 +52,7 @@ __host__ __device__ inline CtGeom ct_geom(int h, int w) {
     g.planeT_words = (size_t)(w + 2) * g.pwT;
     g.sin_words = (size_t)h * g.wpr;
     g.label_words = (size_t)h * w + 1;
+    g.cut_shift = 6;
     return g;
 }
 
@@ -319,9 +321,12 @@ struct CtSink {
     int* pool_used;
     int pool_blocks;
     int first = -1, cur = -1, slot = 0;
+    int entries = 0;          // points + segment references (a reference is one entry: x = -1 - first point, y = points)
+    int refs = 0;
     bool on, failed = false;
     __device__ __forceinline__ void put(int x, int y) {
         if (!on || failed) return;
+        ++entries;
         if (cur < 0 || slot == CT_BLOCK_PTS) {
             const int nb = atomicAdd(pool_used, 1);
             if (nb >= pool_blocks) {
@@ -339,9 +344,154 @@ struct CtSink {
 
 __device__ __forceinline__ void ct_prefetch(const uint32_t* p) { asm volatile("prefetch.global.L1 [%0];" ::"l"(p)); }
 
+// ---- segments: long borders followed in parallel ----------------------------------------------------------------------
+// The follower's state is (pixel, direction of the move into it) and its successor function is local, so ANY state is a
+// valid place to start following.  A HEAD is a state on a cut row (y % 64 == 0) entered by a move with a vertical
+// component, or on a cut column (x % 64 == 0) entered by a move with a horizontal one.  k_ct_segments follows every
+// candidate head (foreground pixel on a cut row / column x six directions with a foreground predecessor) to the next head and records where it ends, its points, their Green sum and bounding box; the
+// leader (ct_trace) then hops from head to head instead of walking.  Candidates that lie on hole borders or on no border
+// at all are followed as well (nobody hops through them); a segment that is too long or finds no room for its points is
+// marked invalid (end = -1) and the leader walks that stretch itself, so pruning and capacities never change the result.
+// tools/debug/contour_segments_proto.py is the same algorithm in Python, checked against cv2.
+// rows / columns between cuts: 1 << CtGeom::cut_shift (64; llfe_set_option("contour_cut_shift") for tests)
+constexpr int CT_SEG_STEPS = 384;    // longest segment that is recorded
+constexpr int CT_SEG_BUF = 8;         // points kept in registers / local memory during the first walk
+constexpr int CT_SEG_MAX_STARTS = 2048;   // masks with more external components than this have short borders: no segments
+
+struct CtSeg {
+    int end;            // state id of the head this segment ends at, -1 = not recorded
+    int n;              // points (direction changes) from the head (inclusive) to the end (exclusive)
+    int voff;           // first point in the segment point pool
+    int first, last;    // first / last point: x | y << 16
+    int bb_min, bb_max; // x | y << 16
+    int pad;
+    long long area2;    // Green sum over consecutive points inside the segment
+};
+static_assert(sizeof(CtSeg) == 40, "CtSeg is read as five 8-byte words");
+
+// State ids.  Row heads (cut row, move with a vertical component: directions 1,2,3,5,6,7) come first,
+//   id = ((y / C) * 6 + code) * w + x,                      R = ceil(h / C) * 6 * w of them,
+// then column heads (cut column, move with a horizontal component: directions 0,1,7,3,4,5) that are not row heads too,
+//   id = R + ((x / C) * 6 + code) * h + y.
+__device__ __forceinline__ int ct_ycode(int d) { return d < 4 ? d - 1 : d - 2; }       // 1,2,3,5,6,7 -> 0..5
+__device__ __forceinline__ int ct_ycode_inv(int c) { return c < 3 ? c + 1 : c + 2; }
+__device__ __forceinline__ int ct_xcode(int d) { return d == 7 ? 2 : d; }              // 0,1,7,3,4,5 -> 0,1,2,3,4,5
+__device__ __forceinline__ int ct_xcode_inv(int c) { return c == 2 ? 7 : c; }
+__device__ __forceinline__ int ct_row_states(const CtGeom& g) { return ((g.h + (1 << g.cut_shift) - 1) >> g.cut_shift) * 6 * g.w; }
+__device__ __forceinline__ int ct_col_states(const CtGeom& g) { return ((g.w + (1 << g.cut_shift) - 1) >> g.cut_shift) * 6 * g.h; }
+
+// id of the state "image pixel (x, y) entered by a move in direction d", -1 if it is not a head
+__device__ __forceinline__ int ct_head_id(const CtGeom& g, int x, int y, int d) {
+    const int m = (1 << g.cut_shift) - 1;
+    if ((d & 3) != 0 && (y & m) == 0) return ((y >> g.cut_shift) * 6 + ct_ycode(d)) * g.w + x;
+    if ((d & 3) != 2 && (x & m) == 0) return ct_row_states(g) + ((x >> g.cut_shift) * 6 + ct_xcode(d)) * g.h + y;
+    return -1;
+}
+__device__ __forceinline__ void ct_head_decode(const CtGeom& g, int id, int& x, int& y, int& d) {
+    const int R = ct_row_states(g);
+    if (id < R) {
+        x = id % g.w;
+        const int t = id / g.w;
+        d = ct_ycode_inv(t % 6);
+        y = (t / 6) << g.cut_shift;
+    } else {
+        id -= R;
+        y = id % g.h;
+        const int t = id / g.h;
+        d = ct_xcode_inv(t % 6);
+        x = (t / 6) << g.cut_shift;
+    }
+}
+
+// 8-neighbour byte of padded pixel (X, Y): bit k = neighbour in chain-code direction k
+__device__ __forceinline__ uint32_t ct_nb8(const uint32_t* __restrict__ P, int pw, int X, int Y) {
+    const int q = (X - 1) >> 5, sh = (X - 1) & 31;
+    const uint32_t* r = P + (size_t)Y * pw + q;
+    const uint32_t u3 = (uint32_t)(ct_ld2(r - pw) >> sh) & 7u, m3 = (uint32_t)(ct_ld2(r) >> sh) & 7u,
+                   d3 = (uint32_t)(ct_ld2(r + pw) >> sh) & 7u;
+    return ((m3 >> 2) & 1u) | (((u3 >> 2) & 1u) << 1) | (((u3 >> 1) & 1u) << 2) | ((u3 & 1u) << 3) | ((m3 & 1u) << 4) |
+           ((d3 & 1u) << 5) | (((d3 >> 1) & 1u) << 6) | (((d3 >> 2) & 1u) << 7);
+}
+
+// one thread per state id
+__global__ void __launch_bounds__(128) k_ct_segments(const uint32_t* __restrict__ plane, CtGeom g, CtSeg* __restrict__ tab,
+                                                     int2* __restrict__ segpool_all, size_t segpool_stride, int segpool_cap,
+                                                     int32_t* counts) {
+    const int total = ct_row_states(g) + ct_col_states(g);
+    const int idx = blockIdx.x * 128 + threadIdx.x;
+    if (idx >= total) return;
+    int32_t* cnt = counts + blockIdx.z * 4;
+    CtSeg* rec = tab + (size_t)blockIdx.z * total + idx;
+    if (cnt[0] > CT_SEG_MAX_STARTS) return;   // the leader does not look at the table either
+    int2* segpool = segpool_all + (size_t)blockIdx.z * segpool_stride;
+    const uint32_t* P = plane + blockIdx.z * g.plane_words;
+    const int pw = g.pw;
+    // consecutive threads: consecutive pixels of one cut row / column and direction (neighbouring border pixels walk alike)
+    int x0, y0, d0;
+    ct_head_decode(g, idx, x0, y0, d0);
+    const int Xh = x0 + 32, Yh = y0 + 1;
+    auto bit = [&](int X, int Y) -> uint32_t { return (__ldg(P + (size_t)Y * pw + (X >> 5)) >> (X & 31)) & 1u; };
+    // (a column head that is a row head as well lives under its row id)
+    if (ct_head_id(g, x0, y0, d0) != idx || !bit(Xh, Yh) || !bit(Xh - ct_dx(d0), Yh - ct_dy(d0)) ||
+        ct_nb8(P, pw, Xh, Yh) == 0xffu) {
+        rec->end = -1;
+        return;
+    }
+    int n = 0, end = -1, first = 0, last = 0, minx = 0x7fff, miny = 0x7fff, maxx = 0, maxy = 0;
+    long long area2 = 0;
+    int2 buf[CT_SEG_BUF];
+    {
+        int X = Xh, Y = Yh, din = d0, px = 0, py = 0;
+        for (int step = 0; step < CT_SEG_STEPS; ++step) {
+            const uint32_t nb = ct_nb8(P, pw, X, Y);
+            const int s = (din + 4) & 7;
+            const uint32_t r = ((nb | (nb << 8)) >> (s + 1)) & 0xffu;
+            const int sn = (s + __ffs(r)) & 7;
+            if (sn != din) {
+                const int x = X - 32, y = Y - 1;
+                if (n == 0) first = x | (y << 16);
+                else area2 += (long long)px * y - (long long)py * x;
+                if (n < CT_SEG_BUF) buf[n] = make_int2(x, y);
+                px = x, py = y;
+                minx = min(minx, x), maxx = max(maxx, x), miny = min(miny, y), maxy = max(maxy, y);
+                ++n;
+            }
+            X += ct_dx(sn), Y += ct_dy(sn), din = sn;
+            end = ct_head_id(g, X - 32, Y - 1, sn);
+            if (end >= 0) break;
+        }
+        last = px | (py << 16);
+    }
+    int voff = 0;
+    if (end >= 0 && n > 0) {
+        voff = atomicAdd(reinterpret_cast<int*>(segpool), n);   // the first entry of the pool is its fill counter
+        if (voff + n > segpool_cap) {
+            end = -1;
+        } else if (n <= CT_SEG_BUF) {
+            for (int i = 0; i < n; ++i) segpool[1 + voff + i] = buf[i];
+        } else {   // second walk: the points go straight to the pool
+            int X = Xh, Y = Yh, din = d0, k = 0;
+            while (k < n) {
+                const uint32_t nb = ct_nb8(P, pw, X, Y);
+                const int s = (din + 4) & 7;
+                const uint32_t r = ((nb | (nb << 8)) >> (s + 1)) & 0xffu;
+                const int sn = (s + __ffs(r)) & 7;
+                if (sn != din) segpool[1 + voff + k++] = make_int2(X - 32, Y - 1);
+                X += ct_dx(sn), Y += ct_dy(sn), din = sn;
+            }
+        }
+    }
+    CtSeg out;
+    out.end = end, out.n = n, out.voff = voff, out.first = first, out.last = last;
+    out.bb_min = minx | (miny << 16), out.bb_max = maxx | (maxy << 16), out.pad = 0, out.area2 = area2;
+    *rec = out;
+}
+
 // follows the border that starts at (x0, y0): number of CHAIN_APPROX_SIMPLE points; area, bounding box; points -> sink
+// SEG: tab is this image's segment table (k_ct_segments); the walk hops along it and takes single steps in between
+template <bool SEG>
 __device__ int ct_trace(const uint32_t* __restrict__ P, const uint32_t* __restrict__ T, const CtGeom& g, int x0, int y0,
-                        CtSink& sink, long long& area2, int& minx, int& miny, int& maxx, int& maxy) {
+                        CtSink& sink, long long& area2, int& minx, int& miny, int& maxx, int& maxy, const CtSeg* __restrict__ tab) {
     const int pw = g.pw, pwT = g.pwT;
     int n = 0, fx = 0, fy = 0, px = 0, py = 0;
     auto emit = [&](int x, int y) {
@@ -386,8 +536,60 @@ __device__ int ct_trace(const uint32_t* __restrict__ P, const uint32_t* __restri
     while (!((nb >> s) & 1u)) s = (s - 1) & 7;
     const int X0 = X, Y0 = Y, X1 = X + ct_dx(s), Y1 = Y + ct_dy(s);
     int prev_s = s ^ 4, straight = 0;
+    int first_head = -1;
+    bool hop = SEG;
     const long long guard_max = 4ll * (g.h + 2) * (g.w + 2) + 16;
     for (long long guard = 0; guard < guard_max; ++guard) {
+        int hid = -1;
+        if (SEG && hop) hid = ct_head_id(g, X - 32, Y - 1, prev_s);
+        if (SEG && hid >= 0) {
+            // a head: hop along the recorded segments up to the one that closes the border (its end is the first head
+            // this walk met), which -- like a segment that was not recorded -- is walked step by step
+            if (first_head < 0) first_head = hid;
+            bool moved = false;
+            for (;;) {
+                const int2* q = reinterpret_cast<const int2*>(tab + hid);
+                const int2 q0 = __ldg(q), q1 = __ldg(q + 1), q2 = __ldg(q + 2), q3 = __ldg(q + 3), q4 = __ldg(q + 4);
+                const int e = q0.x;
+                if (e < 0) break;
+                if (e == first_head) {
+                    hop = false;
+                    break;
+                }
+                const int sn_pts = q0.y;
+                if (sn_pts > 0) {
+                    const int sfx = q1.y & 0xffff, sfy = q1.y >> 16, slx = q2.x & 0xffff, sly = q2.x >> 16;
+                    if (n == 0) {
+                        fx = sfx;
+                        fy = sfy;
+                    } else {
+                        area2 += (long long)px * sfy - (long long)py * sfx;
+                    }
+                    area2 += ((long long)(unsigned int)q4.x) | ((long long)q4.y << 32);
+                    px = slx;
+                    py = sly;
+                    minx = min(minx, q2.y & 0xffff);
+                    miny = min(miny, q2.y >> 16);
+                    maxx = max(maxx, q3.x & 0xffff);
+                    maxy = max(maxy, q3.x >> 16);
+                    n += sn_pts;
+                    sink.put(-1 - q1.x, sn_pts);
+                    ++sink.refs;
+                }
+                hid = e;
+                moved = true;
+            }
+            if (moved) {
+                int hx, hy;
+                ct_head_decode(g, hid, hx, hy, prev_s);
+                X = hx + 32;
+                Y = hy + 1;
+                s = (prev_s + 4) & 7;
+                straight = 0;
+                reload(16);
+                nb = neighbours();
+            }
+        }
         const uint32_t r = ((nb | (nb << 8)) >> (s + 1)) & 0xffu;
         const int sn = (s + __ffs(r)) & 7;   // s + 1 + (ffs - 1)
         if (sn != prev_s) {
@@ -420,7 +622,7 @@ __device__ int ct_trace(const uint32_t* __restrict__ P, const uint32_t* __restri
             reload(sn == 0 ? 2 : sn == 4 ? 30 : 16);
             pos = X - (cq << 5);
         }
-        if (straight >= 1) {
+        if (!SEG && straight >= 1) {   // (no jumps in a walk that hops: a jump could pass a head unseen)
             if (sn == 0) {
                 const int k = ct_skip_up(dn, mid, pos);
                 if (k > 0) X += k;
@@ -454,15 +656,18 @@ __device__ int ct_trace(const uint32_t* __restrict__ P, const uint32_t* __restri
 // One warp per contour.  Lane 0 follows the border (the walk is sequential and latency-bound; a converged warp keeps
 // other contours from serialising behind it) and leaves the points in chained scratch blocks; then the whole warp
 // copies the points of a contour that passed the area threshold to its final place in the image's point array.
+template <bool SEG>
 __global__ void __launch_bounds__(128) k_ct_trace(const uint32_t* __restrict__ plane, const uint32_t* __restrict__ planeT,
                                                   CtGeom g, CtHeader* hdr, int max_contours, long long min_area2, int2* points,
-                                                  int max_points, int2* pool, int pool_blocks, int32_t* counts) {
+                                                  int max_points, int2* pool, int pool_blocks, int32_t* counts,
+                                                  const CtSeg* __restrict__ segtab, int seg_states, const int2* __restrict__ segpool,
+                                                  size_t segpool_stride) {
     const int lane = threadIdx.x & 31;
     const int i = blockIdx.x * 4 + (threadIdx.x >> 5);
     int32_t* cnt = counts + blockIdx.z * 4;
     const int n_starts = min(cnt[0], max_contours);
     if (i >= n_starts) return;
-    int n = 0, first = -1, off = -1;
+    int n = 0, ne = 0, nrefs = 0, first = -1, off = -1;
     if (lane == 0) {
         CtHeader* hd = hdr + (size_t)blockIdx.z * max_contours + i;
         const uint32_t* P = plane + blockIdx.z * g.plane_words;
@@ -475,7 +680,12 @@ __global__ void __launch_bounds__(128) k_ct_trace(const uint32_t* __restrict__ p
         sink.pool_used = &cnt[3];
         sink.pool_blocks = pool_blocks;
         sink.on = max_points > 0;
-        n = ct_trace(P, T, g, x0, y0, sink, area2, minx, miny, maxx, maxy);
+        if (SEG && cnt[0] <= CT_SEG_MAX_STARTS)
+            n = ct_trace<true>(P, T, g, x0, y0, sink, area2, minx, miny, maxx, maxy, segtab + (size_t)blockIdx.z * seg_states);
+        else
+            n = ct_trace<false>(P, T, g, x0, y0, sink, area2, minx, miny, maxx, maxy, nullptr);
+        ne = sink.entries;
+        nrefs = sink.refs;
         CtHeader H;
         H.start = p;
         H.npts = n;
@@ -506,15 +716,48 @@ __global__ void __launch_bounds__(128) k_ct_trace(const uint32_t* __restrict__ p
     __syncwarp();
     first = __shfl_sync(FULL, first, 0);
     if (first < 0) return;
-    n = __shfl_sync(FULL, n, 0);
+    ne = __shfl_sync(FULL, ne, 0);
     off = __shfl_sync(FULL, off, 0);
     const int2* pl = pool + (size_t)blockIdx.z * pool_blocks * 64;
+    const int2* sp = segpool ? segpool + (size_t)blockIdx.z * segpool_stride + 1 : nullptr;   // entry 0 is the fill counter
     int2* out = points + (size_t)blockIdx.z * max_points + off;
-    int blk = first;
-    for (int done = 0; done < n; done += CT_BLOCK_PTS) {
+    int blk = first, opos = 0;
+    n = __shfl_sync(FULL, n, 0);
+    nrefs = __shfl_sync(FULL, nrefs, 0);
+    if (!SEG || nrefs == 0) {   // points only
+        for (int done = 0; done < n; done += CT_BLOCK_PTS) {
+            const int2* src = pl + (size_t)blk * 64;
+            const int m = min(CT_BLOCK_PTS, n - done);
+            for (int t = lane; t < m; t += 32) out[done + t] = src[t];
+            blk = src[CT_BLOCK_PTS].x;
+        }
+        return;
+    }
+    // entries are points or references to a segment's points (x < 0): positions by a warp scan of the entry sizes
+    for (int done = 0; done < ne; done += CT_BLOCK_PTS) {
         const int2* src = pl + (size_t)blk * 64;
-        const int m = min(CT_BLOCK_PTS, n - done);
-        for (int t = lane; t < m; t += 32) out[done + t] = src[t];
+        const int m = min(CT_BLOCK_PTS, ne - done);
+        for (int t0 = 0; t0 < m; t0 += 32) {
+            const int t = t0 + lane;
+            const int2 e = t < m ? src[t] : make_int2(0, 0);
+            const int size = t < m ? (e.x < 0 ? e.y : 1) : 0;
+            int inc = size;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+                const int v = __shfl_up_sync(FULL, inc, o);
+                if (lane >= o) inc += v;
+            }
+            const int at = opos + inc - size;
+            if (t < m && e.x >= 0) out[at] = e;
+            unsigned refs = __ballot_sync(FULL, t < m && e.x < 0);
+            while (refs) {
+                const int l = __ffs(refs) - 1;
+                refs &= refs - 1;
+                const int v0 = -1 - __shfl_sync(FULL, e.x, l), cnt_l = __shfl_sync(FULL, e.y, l), at_l = __shfl_sync(FULL, at, l);
+                for (int k = lane; k < cnt_l; k += 32) out[at_l + k] = sp[v0 + k];
+            }
+            opos += __shfl_sync(FULL, inc, 31);
+        }
         blk = src[CT_BLOCK_PTS].x;
     }
 }
@@ -531,17 +774,36 @@ static int ct_pool_blocks(int max_contours, int max_points) {
 constexpr int CT_SUB = 16;          // images per union-find sub-pass (1080p: 16 x 9.3 MB)
 constexpr int CT_PASS = 256;        // images per pass
 
-static size_t contours_ws_bytes(int n, int sub, int h, int w, int max_contours, int max_points) {
+// segment table + segment point pool (per image), only for calls on a few images: a batch hides the latency of a long
+// border behind the other images' borders
+constexpr int CT_SEG_IMAGES = 2;
+static bool ct_use_segments(const llfe_ctx* ctx, int n, int h, int w) {
+    return ctx->opt_contour_segments && n <= CT_SEG_IMAGES && h < 32768 && w < 32768;
+}
+static int ct_seg_states(int h, int w, int cut_shift) { return ceil_div(h, 1 << cut_shift) * w * 6 + ceil_div(w, 1 << cut_shift) * h * 6; }
+static size_t ct_segpool_points(int h, int w) {
+    const size_t p = (size_t)h * w / 2;
+    return (p < 65536 ? 65536 : p) + 1;   // + the fill counter
+}
+
+static size_t contours_ws_bytes(int n, int sub, int h, int w, int max_contours, int max_points, bool segments, int cut_shift) {
     const CtGeom g = ct_geom(h, w);
-    return WsCarver::need(n * (g.plane_words + g.planeT_words) * 4) +
+    return (segments ? WsCarver::need((size_t)n * ct_seg_states(h, w, cut_shift) * sizeof(CtSeg)) + WsCarver::need(n * ct_segpool_points(h, w) * 8) : 0) +
+           WsCarver::need(n * (g.plane_words + g.planeT_words) * 4) +
            WsCarver::need((size_t)n * ct_pool_blocks(max_contours, max_points) * 512) + 2 * WsCarver::need(sub * g.sin_words * 4) +
            WsCarver::need(sub * g.label_words * 4);
 }
 
 static int contours_pass(llfe_ctx* ctx, const uint8_t* d_mask, int n, int sub, int h, int w, int64_t min_area2,
-                         int32_t* d_headers, int max_contours, int32_t* d_points, int max_points, int32_t* d_counts, void* ws) {
-    const CtGeom g = ct_geom(h, w);
+                         int32_t* d_headers, int max_contours, int32_t* d_points, int max_points, int32_t* d_counts, void* ws,
+                         bool segments) {
+    CtGeom g = ct_geom(h, w);
+    g.cut_shift = ctx->opt_contour_cut_shift;
     WsCarver carve(ws);
+    const int seg_states = ct_seg_states(h, w, g.cut_shift);
+    const size_t segpool_stride = ct_segpool_points(h, w);
+    CtSeg* segtab = segments ? carve.take<CtSeg>((size_t)n * seg_states) : nullptr;
+    int2* segpool = segments ? carve.take<int2>(n * segpool_stride) : nullptr;
     uint32_t* plane = carve.take<uint32_t>(n * (g.plane_words + g.planeT_words));
     uint32_t* planeT = plane + n * g.plane_words;
     const int pool_blocks = ct_pool_blocks(max_contours, max_points);
@@ -575,11 +837,22 @@ static int contours_pass(llfe_ctx* ctx, const uint8_t* d_mask, int n, int sub, i
             pl, g, sinB, labels, (CtHeader*)d_headers + (size_t)i0 * max_contours, max_contours, d_counts + (size_t)i0 * 4);
         LLFE_LAUNCHED(ctx);
     }
+    if (segments) {
+        for (int i = 0; i < n; ++i) LLFE_CUDA(cudaMemsetAsync(segpool + i * segpool_stride, 0, sizeof(int2), ctx->stream));
+        LLFE_KERNEL(ctx, "k_ct_segments");
+        k_ct_segments<<<dim3(ceil_div(seg_states, 128), 1, n), 128, 0, ctx->stream>>>(plane, g, segtab, segpool,
+                                                                                      segpool_stride, (int)segpool_stride - 1, d_counts);
+        LLFE_LAUNCHED(ctx);
+    }
     LLFE_KERNEL(ctx, "k_ct_trace");
-    k_ct_trace<<<dim3(ceil_div(max_contours, 4), 1, n), 128, 0, ctx->stream>>>(plane, planeT, g, (CtHeader*)d_headers,
-                                                                              max_contours, (long long)min_area2,
-                                                                              (int2*)d_points, max_points, pool, pool_blocks,
-                                                                              d_counts);
+    if (segments)
+        k_ct_trace<true><<<dim3(ceil_div(max_contours, 4), 1, n), 128, 0, ctx->stream>>>(
+            plane, planeT, g, (CtHeader*)d_headers, max_contours, (long long)min_area2, (int2*)d_points, max_points, pool, pool_blocks,
+            d_counts, segtab, seg_states, segpool, segpool_stride);
+    else
+        k_ct_trace<false><<<dim3(ceil_div(max_contours, 4), 1, n), 128, 0, ctx->stream>>>(
+            plane, planeT, g, (CtHeader*)d_headers, max_contours, (long long)min_area2, (int2*)d_points, max_points, pool, pool_blocks,
+            d_counts, nullptr, 0, nullptr, 0);
     LLFE_LAUNCHED(ctx);
     return LLFE_OK;
 }
@@ -600,12 +873,13 @@ extern "C" int llfe_contours_external(llfe_ctx* ctx, const uint8_t* d_mask, int 
     const int pass = n < CT_PASS ? n : CT_PASS;
     if (sub > pass) sub = pass;
     void* ws;
-    LLFE_TRY(llfe_workspace(ctx, contours_ws_bytes(pass, sub, h, w, max_contours, max_points), &ws));
+    const bool segments = ct_use_segments(ctx, n, h, w);
+    LLFE_TRY(llfe_workspace(ctx, contours_ws_bytes(pass, sub, h, w, max_contours, max_points, segments, ctx->opt_contour_cut_shift), &ws));
     for (int i0 = 0; i0 < n; i0 += pass) {
         const int m = n - i0 < pass ? n - i0 : pass;
         LLFE_TRY(contours_pass(ctx, d_mask + (size_t)i0 * h * w, m, sub, h, w, min_area2, d_headers + (size_t)i0 * max_contours * 10,
                                max_contours, d_points ? d_points + (size_t)i0 * max_points * 2 : nullptr, max_points,
-                               d_counts + (size_t)i0 * 4, ws));
+                               d_counts + (size_t)i0 * 4, ws, segments));
     }
     return LLFE_OK;
 }

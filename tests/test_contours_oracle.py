@@ -50,3 +50,25 @@ def test_area_formula_equals_cv2():
         for c in ref:
             pts = [(int(p[0][0]), int(p[0][1])) for p in c]
             assert abs(oc.contour_area2(pts)) == int(round(2 * cv2.contourArea(c)))
+
+
+def test_segmented_follower_prototype_equals_cv2():
+    """the algorithm behind k_ct_segments + the hopping leader (tools/debug/contour_segments_proto.py): heads on cut rows /
+    columns, every candidate followed to the next head, the leader hops; segments capped at a few steps are left to the
+    leader.  Point for point against cv2."""
+    import os
+    import sys
+
+    sys.path.insert(0, os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "tools", "debug"))
+    import contour_segments_proto as proto
+
+    rng = np.random.default_rng(5)
+    hops = 0
+    for trial in range(60):
+        h, w = int(rng.integers(1, 36)), int(rng.integers(1, 36))
+        m = random_mask(rng, h, w)
+        stats = [0, 0]
+        got = proto.find_external_segmented(m, int(rng.choice([1, 2, 4, 8])), int(rng.choice([3, 10, 1 << 30])), stats)
+        hops += stats[0]
+        assert sorted(map(tuple, got)) == sorted(map(tuple, cv_contours(m))), (trial, h, w)
+    assert hops > 500     # the hop path is what ran

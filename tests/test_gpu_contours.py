@@ -169,3 +169,62 @@ def test_batch_analyzer_contours_and_overflow_fallback():
         else:
             assert len(got) == len(want) and all(np.array_equal(a, b) for a, b in zip(got, want))
     assert seen == {True, False}
+
+
+# ---- segments: long borders followed in parallel (k_ct_segments + the hopping leader) ---------------------------------
+@pytest.fixture
+def cut_shift():
+    ctx = _runtime.context()
+
+    def set_(shift, on=1):
+        ctx.set_option("contour_cut_shift", shift)
+        ctx.set_option("contour_segments", on)
+
+    yield set_
+    ctx.set_option("contour_cut_shift", 6)
+    ctx.set_option("contour_segments", 1)
+
+
+@pytest.mark.parametrize("shift", [0, 1, 2, 3])
+def test_segments_every_cut_spacing_on_small_masks(cut_shift, shift):
+    """cut rows every 1 / 2 / 4 / 8 rows: nearly every step of a border is a hop, heads on the start row included"""
+    cut_shift(shift)
+    rng = np.random.default_rng(20 + shift)
+    for k in range(150):
+        h, w = rng.integers(1, 90, 2)
+        m = random_mask(rng, int(h), int(w))
+        if k % 4 == 0:
+            m = cv2.dilate(m, np.ones((3, 3), np.uint8))
+        check(m)
+    for shape in [(1, 1), (1, 40), (40, 1), (33, 65)]:
+        check(np.full(shape, 255, np.uint8))
+        m = np.zeros(shape, np.uint8)
+        m[::2, ::2] = 255
+        check(m)
+
+
+def test_segments_long_borders_and_capacity(cut_shift):
+    """spirals / combs with borders of tens of thousands of pixels; segments longer than the recorded maximum (a long
+    horizontal edge between two cut rows) are walked by the leader; same result with the segments switched off"""
+    yy, xx = np.mgrid[0:700, 0:900]
+    spiral = (((np.hypot(yy - 350, xx - 450) + 12 * np.arctan2(yy - 350, xx - 450) / np.pi) % 24) < 9).astype(np.uint8) * 255
+    comb = np.zeros((600, 1500), np.uint8)
+    comb[5:8, 3:-3] = 255
+    comb[5:590, 3:-3:6] = 255
+    zig = np.zeros((300, 1400), np.uint8)
+    for x in range(2, 1390):
+        zig[40 + (x * 7) % 200, x] = zig[41 + (x * 7) % 200, x] = 255
+    zig = cv2.dilate(zig, np.ones((3, 3), np.uint8))
+    masks = [spiral, comb, zig, refpath.shape_mask(design_image(1080, 1920, 1)), refpath.shape_mask(noise_image(270, 480, 3))]
+    ctx = _runtime.context()
+    for m in masks:
+        for shift in (6, 4, 3):
+            cut_shift(shift)
+            check(m)
+            check(m, 200)
+        cut_shift(6)
+        h1, p1 = ct.find_external_host(ctx, m, 200)
+        cut_shift(6, on=0)
+        h0, p0 = ct.find_external_host(ctx, m, 200)
+        a, b = ct.to_cv2_contours(h1, p1), ct.to_cv2_contours(h0, p0)
+        assert len(a) == len(b) and all(np.array_equal(x, y) for x, y in zip(a, b))
