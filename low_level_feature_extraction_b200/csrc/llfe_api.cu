@@ -766,8 +766,13 @@ static int stage_begin(llfe_ctx* ctx, const void* h_in, size_t in_bytes, size_t 
     st->p_out = st->p_in + a;
     st->d_in = (uint8_t*)ctx->dev_stage;
     st->d_out = st->d_in + a;
-    memcpy(st->p_in, h_in, in_bytes);
-    LLFE_CUDA(cudaMemcpyAsync(st->d_in, st->p_in, in_bytes, cudaMemcpyHostToDevice, ctx->stream));
+    // in pieces: the DMA of a piece runs while the next one is copied into the pinned buffer
+    constexpr size_t PIECE = 1 << 20;
+    for (size_t off = 0; off < in_bytes; off += PIECE) {
+        const size_t m = in_bytes - off < PIECE ? in_bytes - off : PIECE;
+        memcpy(st->p_in + off, (const uint8_t*)h_in + off, m);
+        LLFE_CUDA(cudaMemcpyAsync(st->d_in + off, st->p_in + off, m, cudaMemcpyHostToDevice, ctx->stream));
+    }
     return LLFE_OK;
 }
 
