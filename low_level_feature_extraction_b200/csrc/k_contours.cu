@@ -413,26 +413,30 @@ __device__ __forceinline__ uint32_t ct_nb8(const uint32_t* __restrict__ P, int p
            ((d3 & 1u) << 5) | (((d3 >> 1) & 1u) << 6) | (((d3 >> 2) & 1u) << 7);
 }
 
-// one thread per state id
+// one thread per state id: blockIdx.y = (cut row, direction code) for the row heads, then (cut column, direction code)
+// for the column heads; blockIdx.x * 128 + threadIdx.x = the position along the cut (no division in the decode)
 __global__ void __launch_bounds__(128) k_ct_segments(const uint32_t* __restrict__ plane, CtGeom g, CtSeg* __restrict__ tab,
                                                      int2* __restrict__ segpool_all, size_t segpool_stride, int segpool_cap,
                                                      int32_t* counts) {
-    const int total = ct_row_states(g) + ct_col_states(g);
-    const int idx = blockIdx.x * 128 + threadIdx.x;
-    if (idx >= total) return;
+    const int n_cr6 = ((g.h + (1 << g.cut_shift) - 1) >> g.cut_shift) * 6;
+    const bool rows = (int)blockIdx.y < n_cr6;
+    const int line = rows ? blockIdx.y : blockIdx.y - n_cr6;      // cut index * 6 + direction code
+    const int along = blockIdx.x * 128 + threadIdx.x;
+    if (along >= (rows ? g.w : g.h)) return;
     int32_t* cnt = counts + blockIdx.z * 4;
-    CtSeg* rec = tab + (size_t)blockIdx.z * total + idx;
     if (cnt[0] > CT_SEG_MAX_STARTS) return;   // the leader does not look at the table either
+    const int idx = rows ? line * g.w + along : ct_row_states(g) + line * g.h + along;
+    CtSeg* rec = tab + (size_t)blockIdx.z * (ct_row_states(g) + ct_col_states(g)) + idx;
     int2* segpool = segpool_all + (size_t)blockIdx.z * segpool_stride;
     const uint32_t* P = plane + blockIdx.z * g.plane_words;
     const int pw = g.pw;
-    // consecutive threads: consecutive pixels of one cut row / column and direction (neighbouring border pixels walk alike)
-    int x0, y0, d0;
-    ct_head_decode(g, idx, x0, y0, d0);
+    const int cut = (line / 6) << g.cut_shift, code = line % 6;
+    const int x0 = rows ? along : cut, y0 = rows ? cut : along;
+    const int d0 = rows ? ct_ycode_inv(code) : ct_xcode_inv(code);
     const int Xh = x0 + 32, Yh = y0 + 1;
     auto bit = [&](int X, int Y) -> uint32_t { return (__ldg(P + (size_t)Y * pw + (X >> 5)) >> (X & 31)) & 1u; };
     // (a column head that is a row head as well lives under its row id)
-    if (ct_head_id(g, x0, y0, d0) != idx || !bit(Xh, Yh) || !bit(Xh - ct_dx(d0), Yh - ct_dy(d0)) ||
+    if (!bit(Xh, Yh) || !bit(Xh - ct_dx(d0), Yh - ct_dy(d0)) || ct_head_id(g, x0, y0, d0) != idx ||
         ct_nb8(P, pw, Xh, Yh) == 0xffu) {
         rec->end = -1;
         return;
@@ -771,14 +775,14 @@ static int ct_pool_blocks(int max_contours, int max_points) {
 // Workspace of one pass over n images: planes + scratch point pool for all of them (every border of the pass is followed
 // in ONE launch: the pass lasts as long as its longest border, so it should cover many images), union-find state (4 bytes
 // per pixel: the part that must stay L2-sized) for `sub` images at a time.
-constexpr int CT_SUB = 16;          // images per union-find sub-pass (1080p: 16 x 9.3 MB)
+constexpr int CT_SUB = 128;         // images per union-find sub-pass
 constexpr int CT_PASS = 256;        // images per pass
 
 // segment table + segment point pool (per image), only for calls on a few images: a batch hides the latency of a long
 // border behind the other images' borders
 constexpr int CT_SEG_IMAGES = 2;
 static bool ct_use_segments(const llfe_ctx* ctx, int n, int h, int w) {
-    return ctx->opt_contour_segments && n <= CT_SEG_IMAGES && h < 32768 && w < 32768;
+    return (ctx->opt_contour_segments == 2 || (ctx->opt_contour_segments == 1 && n <= CT_SEG_IMAGES)) && h < 32768 && w < 32768;
 }
 static int ct_seg_states(int h, int w, int cut_shift) { return ceil_div(h, 1 << cut_shift) * w * 6 + ceil_div(w, 1 << cut_shift) * h * 6; }
 static size_t ct_segpool_points(int h, int w) {
@@ -838,9 +842,10 @@ static int contours_pass(llfe_ctx* ctx, const uint8_t* d_mask, int n, int sub, i
         LLFE_LAUNCHED(ctx);
     }
     if (segments) {
-        for (int i = 0; i < n; ++i) LLFE_CUDA(cudaMemsetAsync(segpool + i * segpool_stride, 0, sizeof(int2), ctx->stream));
+        LLFE_CUDA(cudaMemset2DAsync(segpool, segpool_stride * sizeof(int2), 0, sizeof(int2), n, ctx->stream));   // the fill counters
         LLFE_KERNEL(ctx, "k_ct_segments");
-        k_ct_segments<<<dim3(ceil_div(seg_states, 128), 1, n), 128, 0, ctx->stream>>>(plane, g, segtab, segpool,
+        const int cut = 1 << g.cut_shift;
+        k_ct_segments<<<dim3(ceil_div(w > h ? w : h, 128), (ceil_div(h, cut) + ceil_div(w, cut)) * 6, n), 128, 0, ctx->stream>>>(plane, g, segtab, segpool,
                                                                                       segpool_stride, (int)segpool_stride - 1, d_counts);
         LLFE_LAUNCHED(ctx);
     }
@@ -869,11 +874,16 @@ extern "C" int llfe_contours_external(llfe_ctx* ctx, const uint8_t* d_mask, int 
     // the union-find nodes of a sub-pass should stay in L2 (16 x 1080p), at least one image
     const size_t px = (size_t)h * w;
     int sub = (int)(((size_t)CT_SUB * 1080 * 1920) / px);
-    sub = sub < 1 ? 1 : sub > 64 ? 64 : sub;
-    const int pass = n < CT_PASS ? n : CT_PASS;
+    sub = sub < 1 ? 1 : sub > 256 ? 256 : sub;
+    int pass = n < CT_PASS ? n : CT_PASS;
+    const bool segments = ct_use_segments(ctx, n, h, w);
+    if (segments) {   // segment tables + point pools of a pass: at most 2 GB
+        const size_t per = (size_t)ct_seg_states(h, w, ctx->opt_contour_cut_shift) * sizeof(CtSeg) + ct_segpool_points(h, w) * 8;
+        const size_t fit = ((size_t)2 << 30) / per;
+        if ((size_t)pass > fit) pass = fit < 1 ? 1 : (int)fit;
+    }
     if (sub > pass) sub = pass;
     void* ws;
-    const bool segments = ct_use_segments(ctx, n, h, w);
     LLFE_TRY(llfe_workspace(ctx, contours_ws_bytes(pass, sub, h, w, max_contours, max_points, segments, ctx->opt_contour_cut_shift), &ws));
     for (int i0 = 0; i0 < n; i0 += pass) {
         const int m = n - i0 < pass ? n - i0 : pass;

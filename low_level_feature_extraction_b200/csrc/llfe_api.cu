@@ -204,7 +204,7 @@ int llfe_set_option(llfe_ctx* ctx, const char* name, int64_t value) {
     else if (!strcmp(name, "hyst_strips")) ctx->opt_hyst_strips = value != 0;
     else if (!strcmp(name, "shadow_inline")) ctx->opt_shadow_inline = value != 0;
     else if (!strcmp(name, "serial")) ctx->opt_serial = value != 0;
-    else if (!strcmp(name, "contour_segments")) ctx->opt_contour_segments = value != 0;
+    else if (!strcmp(name, "contour_segments")) ctx->opt_contour_segments = (value >= 0 && value <= 2) ? (int)value : 1;
     else if (!strcmp(name, "contour_cut_shift")) ctx->opt_contour_cut_shift = (value >= 0 && value <= 8) ? (int)value : 6;
     else if (!strcmp(name, "shadow_variant")) ctx->shadow_variant = (int)value;
     else if (!strcmp(name, "chunk")) ctx->opt_chunk = (value >= 1 && value <= 256) ? (int)value : 256;

@@ -51,7 +51,9 @@ struct llfe_ctx {
     // llfe_set_option: path toggles used by the parity tests (both off in production)
     bool opt_unfused = false;      // per-stage kernels instead of the fused front kernel
     int opt_contour_cut_shift = 6;      // llfe_set_option("contour_cut_shift", 0..8): log2 of the rows between cut rows (tests)
-    bool opt_contour_segments = true;   // llfe_set_option("contour_segments", 0): long borders followed by one thread only
+    // llfe_set_option("contour_segments", v): 0 = every border followed by one thread, 1 = long borders cut into segments
+    // in calls on one or two images (default), 2 = in batches as well (passes sized to 2 GB of segment tables)
+    int opt_contour_segments = 1;
     bool opt_hyst_strips = false;  // multi-launch strip hysteresis instead of the cluster kernel
     bool opt_shadow_inline = false;  // adaptive threshold inside the fused front kernel instead of k_shadow
     // llfe_set_debug_buffer: validated device buffers the k-means / hysteresis kernels write phase clocks to
