@@ -781,13 +781,18 @@ constexpr int CT_PASS = 256;        // images per pass
 // segment table + segment point pool (per image), only for calls on a few images: a batch hides the latency of a long
 // border behind the other images' borders
 constexpr int CT_SEG_IMAGES = 2;
-static bool ct_use_segments(const llfe_ctx* ctx, int n, int h, int w) {
-    return (ctx->opt_contour_segments == 2 || (ctx->opt_contour_segments == 1 && n <= CT_SEG_IMAGES)) && h < 32768 && w < 32768;
-}
 static int ct_seg_states(int h, int w, int cut_shift) { return ceil_div(h, 1 << cut_shift) * w * 6 + ceil_div(w, 1 << cut_shift) * h * 6; }
 static size_t ct_segpool_points(int h, int w) {
     const size_t p = (size_t)h * w / 2;
     return (p < 65536 ? 65536 : p) + 1;   // + the fill counter
+}
+static bool ct_use_segments(const llfe_ctx* ctx, int n, int h, int w) {
+    if (!(ctx->opt_contour_segments == 2 || (ctx->opt_contour_segments == 1 && n <= CT_SEG_IMAGES))) return false;
+    if (h >= 32768 || w >= 32768) return false;   // points are packed as x | y << 16
+    // table + pool of one image: 24 MB at 1080p, 95 MB at 4K; beyond 512 MB (16 k x 16 k) the single walker does it
+    const double per = ((double)ceil_div(h, 1 << ctx->opt_contour_cut_shift) * w + (double)ceil_div(w, 1 << ctx->opt_contour_cut_shift) * h) * 6 *
+                           sizeof(CtSeg) + (double)ct_segpool_points(h, w) * 8;
+    return per <= 512.0 * 1024 * 1024;
 }
 
 static size_t contours_ws_bytes(int n, int sub, int h, int w, int max_contours, int max_points, bool segments, int cut_shift) {
