@@ -192,6 +192,13 @@ int llfe_png_reconstruct_adam7(llfe_ctx* ctx, uint8_t* d_stream, int h, int w, i
  * truncated input, Adler-32 mismatch; input beyond the point where the output is full is ignored, as libpng does once the
  * image is complete.  No context, no device. */
 int llfe_inflate_zlib(const uint8_t* in, size_t in_len, uint8_t* out, size_t out_cap, size_t* out_len);
+/* The same result from `threads` (1..8) decoders working on the one stream: all but the first start at a dynamic-block
+ * header they find in the middle of the compressed data and decode into symbols that may refer to the 32 KB window they
+ * do not know; when the decoder in front arrives at exactly that bit, at a block boundary, the symbols become bytes.  A
+ * start nobody arrives at, or a failing worker, only costs time (the decoder in front goes on alone); streams with fewer
+ * than 128 KB of compressed data per decoder use fewer.  llfe_png_decode_host uses this with
+ * llfe_set_option("inflate_threads") decoders (default 4). */
+int llfe_inflate_zlib_mt(const uint8_t* in, size_t in_len, uint8_t* out, size_t out_cap, size_t* out_len, int threads);
 
 /* Host-only: is `buf` a JFIF JPEG of the subset the device path decodes (8-bit, Huffman; baseline with one interleaved
  * scan or progressive; gray or YCbCr 4:4:4 / 4:2:2 / 4:2:0; no Exif orientation / Adobe marker)?  out[0] = width, out[1] = height.

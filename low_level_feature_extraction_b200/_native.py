@@ -108,6 +108,7 @@ PROTOTYPES = {
     "llfe_png_reconstruct": (i32, [vp, vp, i32, i32, i32, i32, i32, vp, vp, vp]),
     "llfe_png_reconstruct_host": (i32, [vp, vp, i32, i32, i32, i32, vp, i32, vp]),
     "llfe_inflate_zlib": (i32, [vp, sz, vp, sz, C.POINTER(sz)]),
+    "llfe_inflate_zlib_mt": (i32, [vp, sz, vp, sz, C.POINTER(sz), i32]),
     "llfe_png_decode_host": (i32, [vp, vp, sz, i32, i32, i32, i32, vp, i32, vp]),
     "llfe_png_stream_bytes": (C.c_int64, [i32, i32, i32, i32, i32]),
     "llfe_png_reconstruct_adam7": (i32, [vp, vp, i32, i32, i32, i32, vp, vp, vp]),

@@ -16,6 +16,9 @@
 #include <string.h>
 
 #include <atomic>
+#include <mutex>
+#include <thread>
+#include <vector>
 
 #include "llfe_common.cuh"
 
@@ -238,16 +241,242 @@ int decode_block(Stream& s_ref, const Ent* lt, const Ent* dt, uint8_t* out_begin
     return rc;
 }
 
-int inflate_raw(Stream& s, uint8_t* out, size_t out_cap, size_t* out_len, bool* finished, std::atomic<size_t>* progress) {
-    static const Fixed fixed;
+// ---- speculative workers (one stream decoded by several threads) ---------------------------------------------------
+// A worker starts somewhere in the middle of the compressed data: it looks, bit by bit, for the header of a dynamic
+// block that parses (complete code sets, an end-of-block code) and decodes from there without knowing the 32 KB of
+// output in front of it -- into 16-bit symbols: a literal, or 0x8000 | i for "byte i of the unknown window", which match
+// copies carry along like literals.  The decoder in front of it stops when it arrives, at a block boundary, at exactly
+// the bit the worker started from; that proves the start was a real block start, fixes the worker's place in the output,
+// and the symbols are turned into bytes (the window is the finished output in front of them).  A start that is never
+// arrived at, a worker that finds none, or one that fails, only costs time: the decoder in front simply goes on.
+struct SpecWorker {
+    long long scan_from = 0;                   // first bit (relative to the deflate data) this worker may start at
+    std::atomic<long long> start_bit{-1};      // published once the first block from there has decoded
+    std::atomic<int> cancel{0};
+    std::atomic<int> decoded{0};               // 1 = stopped decoding (handed over, end of stream, full, or failed)
+    std::atomic<int> have_off{0};              // the decoder in front has arrived: `off` is this worker's place in the output
+    std::atomic<int> resolved{0};              // 1 = bytes final (or failed: see ok)
+    size_t off = 0;
+    std::vector<uint16_t> sym;
+    size_t len = 0;                            // symbols decoded
+    long long end_bit = 0;                     // where it stopped (a block boundary, or behind the final block)
+    int next = -1;                             // the worker it handed over to
+    int pred = 0;                              // the decoder that arrived at this worker's start (0 = the plain one)
+    bool finished = false;                     // saw the final block
+    bool full = false;                         // stopped because the output cannot be longer than this
+    bool ok = false;
+    uint32_t adler = 1;                        // of its bytes
+    size_t bytes = 0;                          // bytes it put into the output
+};
+
+struct SpecCtl {
+    const uint8_t* base;       // first byte of the deflate data
+    const uint8_t* end;
+    uint8_t* out;
+    size_t out_cap;
+    int n = 0;                 // workers (index 0 is the plain decoder at the front and has no SpecWorker duties)
+    SpecWorker* w = nullptr;
+    std::atomic<int> all_done{0};
+};
+
+// The symbol buffers are kept between calls: a fresh multi-megabyte allocation per worker and call is served by mmap,
+// and the page faults of several threads filling new mappings at once cost more than the decode itself.
+struct SymPool {
+    std::mutex m;
+    std::vector<std::vector<uint16_t>> idle;
+    void take(std::vector<uint16_t>& v) {
+        std::lock_guard<std::mutex> g(m);
+        if (!idle.empty()) {
+            v.swap(idle.back());
+            idle.pop_back();
+        }
+    }
+    void give(std::vector<uint16_t>& v) {
+        std::lock_guard<std::mutex> g(m);
+        if (idle.size() < 8 && v.capacity() <= (size_t(32) << 20)) {   // (64 MB of symbols at most are kept per buffer)
+            idle.emplace_back();
+            idle.back().swap(v);
+        }
+    }
+};
+SymPool& sym_pool() {
+    static SymPool p;
+    return p;
+}
+
+inline long long bit_pos(const Stream& s, const uint8_t* base) { return (long long)(s.p - base) * 8 - s.cnt; }
+
+inline void seek_bit(Stream& s, const uint8_t* base, const uint8_t* end, long long bit) {
+    s.p = base + (bit >> 3), s.end = end, s.buf = 0, s.cnt = 0;
+    s.refill();
+    s.drop((int)(bit & 7));
+}
+
+// at a block boundary of decoder `self`: the worker that starts exactly here, or -1.  Workers whose start (or whose
+// whole search range) lies behind are cancelled: nobody can arrive at them any more.
+int spec_handover(SpecCtl* c, int self, long long bit) {
+    for (int j = self + 1; j < c->n; ++j) {
+        SpecWorker& w = c->w[j];
+        if (w.cancel.load(std::memory_order_relaxed)) continue;
+        const long long st = w.start_bit.load(std::memory_order_acquire);
+        if (st == bit) return j;
+        if (st >= 0 ? st < bit : w.scan_from < bit) w.cancel.store(1, std::memory_order_release);
+    }
+    return -1;
+}
+
+enum { SYM_ROOM = 264 };   // free symbols a step of decode_block_sym may need (three literals or one match)
+
+// decode_block with 16-bit symbols and an unknown window: INF_OK at end of block, INF_FULL when fewer than SYM_ROOM
+// symbols are free (nothing consumed: call again with more room), INF_ERR on invalid data / truncated input
+int decode_block_sym(Stream& s_ref, const Ent* lt, const Ent* dt, uint16_t* out_begin, uint16_t*& out_ref, uint16_t* out_end) {
+    Stream s = s_ref;
+    uint16_t* out = out_ref;
+    int rc = INF_ERR;
+    for (;;) {
+        if (out_end - out < SYM_ROOM) {
+            rc = INF_FULL;
+            break;
+        }
+        s.refill();
+        int lits = 0;
+    again:
+        Ent e = lt[s.buf & ((1u << LBITS) - 1)];
+        if (e.op & OP_SUB) {
+            if (s.cnt < e.bits) break;
+            s.drop(e.bits);
+            e = lt[e.val + s.peek(e.op & 15)];
+        }
+        if (e.bits > s.cnt) break;
+        s.drop(e.bits);
+        if (e.op == OP_LIT) {
+            *out++ = e.val;
+            if (++lits < 3 && s.cnt >= 15) goto again;
+            continue;
+        }
+        if (e.op & OP_BASE) {
+            const int lext = e.op & 15;
+            if (s.cnt < 33) s.refill();
+            if (s.cnt < lext) break;
+            const uint32_t len = e.val + s.peek(lext);
+            s.drop(lext);
+            Ent d = dt[s.buf & ((1u << DBITS) - 1)];
+            if (d.op & OP_SUB) {
+                if (s.cnt < d.bits) break;
+                s.drop(d.bits);
+                d = dt[d.val + s.peek(d.op & 15)];
+            }
+            if (!(d.op & OP_BASE) || d.op == OP_BAD) break;
+            const int dext = d.op & 15;
+            if (d.bits + dext > s.cnt) break;
+            s.drop(d.bits);
+            const uint32_t dist = d.val + s.peek(dext);
+            s.drop(dext);
+            const long long pos = out - out_begin;
+            if (dist <= pos) {
+                const uint16_t* src = out - dist;
+                if (dist >= len) memcpy(out, src, 2 * (size_t)len);
+                else
+                    for (uint32_t i = 0; i < len; ++i) out[i] = src[i];
+            } else {
+                for (uint32_t i = 0; i < len; ++i) {   // (the first 32 KB only) reaches into the unknown window
+                    const long long si = pos + i - dist;
+                    out[i] = si >= 0 ? out_begin[si] : (uint16_t)(0x8000 | (32768 + si));
+                }
+            }
+            out += len;
+            continue;
+        }
+        if (e.op == OP_END) rc = INF_OK;
+        break;
+    }
+    out_ref = out;
+    s_ref = s;
+    return rc;
+}
+
+// the code-length section of a dynamic block (RFC 1951 3.2.7), the stream positioned behind the three header bits
+bool read_dynamic_tables(Stream& s, Tables* dyn) {
     static const uint8_t ORDER[19] = {16, 17, 18, 0, 8, 7, 9, 6, 10, 5, 11, 4, 12, 3, 13, 2, 14, 1, 15};
+    if (s.cnt < 14) return false;
+    const int nlen = s.peek(5) + 257;
+    s.drop(5);
+    const int ndist = s.peek(5) + 1;
+    s.drop(5);
+    const int ncode = s.peek(4) + 4;
+    s.drop(4);
+    if (nlen > 286 || ndist > 30) return false;
+    uint8_t lens[320];
+    memset(lens, 0, 19);
+    for (int i = 0; i < ncode; ++i) {
+        if (s.cnt < 3) s.refill();
+        if (s.cnt < 3) return false;
+        lens[ORDER[i]] = (uint8_t)s.peek(3);
+        s.drop(3);
+    }
+    Ent pre[PCAP];
+    if (!build_table(lens, 19, PRECODE, PBITS, pre, PCAP)) return false;
+    int have = 0;
+    const int total = nlen + ndist;
+    while (have < total) {
+        s.refill();
+        const Ent e = pre[s.buf & ((1u << PBITS) - 1)];
+        if (e.op != OP_LIT || e.bits > s.cnt) return false;
+        const int sym = e.val;
+        int rep, val;
+        if (sym < 16) {
+            s.drop(e.bits);
+            lens[have++] = (uint8_t)sym;
+            continue;
+        }
+        const int xb = sym == 16 ? 2 : sym == 17 ? 3 : 7;
+        if (e.bits + xb > s.cnt) return false;
+        s.drop(e.bits);
+        if (sym == 16) {
+            if (have == 0) return false;
+            val = lens[have - 1];
+            rep = 3 + s.peek(2);
+        } else {
+            val = 0;
+            rep = sym == 17 ? 3 + s.peek(3) : 11 + s.peek(7);
+        }
+        s.drop(xb);
+        if (have + rep > total) return false;
+        while (rep--) lens[have++] = (uint8_t)val;
+    }
+    if (lens[256] == 0) return false;            // missing end-of-block code
+    uint8_t dl[32];
+    memcpy(dl, lens + nlen, ndist);
+    return build_table(lens, nlen, LITLEN, LBITS, dyn->lit, LCAP) && build_table(dl, ndist, DIST, DBITS, dyn->dist, DCAP);
+}
+
+const Fixed& fixed_tables() {
+    static const Fixed fixed;
+    return fixed;
+}
+
+enum { INF_HANDED = 2 };   // inflate_raw: stopped at the block boundary where worker *handed_to starts
+
+// the blocks from the position of `s` on, output from out + start_off (matches may reach back to out).  With `ctl`, the
+// decoder looks at every block boundary for a speculative worker that started exactly there and stops if there is one.
+int inflate_raw(Stream& s, uint8_t* out, size_t start_off, size_t out_cap, size_t* out_len, bool* finished,
+                std::atomic<size_t>* progress, SpecCtl* ctl = nullptr, int* handed_to = nullptr) {
+    const Fixed& fixed = fixed_tables();
     Tables* dyn = nullptr;
-    uint8_t* o = out;
+    uint8_t* o = out + start_off;
     uint8_t* const out_end = out + out_cap;
     int rc = INF_ERR;
     *finished = false;
     for (;;) {
         s.refill();
+        if (ctl) {
+            const int j = spec_handover(ctl, 0, bit_pos(s, ctl->base));
+            if (j >= 0) {
+                *handed_to = j;
+                rc = INF_HANDED;
+                break;
+            }
+        }
         if (s.cnt < 3) break;
         const int last = s.peek(1);
         s.drop(1);
@@ -280,74 +509,8 @@ int inflate_raw(Stream& s, uint8_t* out, size_t out_cap, size_t* out_len, bool* 
             if (type == 1) {
                 lt = fixed.t.lit, dt = fixed.t.dist;
             } else {
-                if (s.cnt < 14) break;
-                const int nlen = s.peek(5) + 257;
-                s.drop(5);
-                const int ndist = s.peek(5) + 1;
-                s.drop(5);
-                const int ncode = s.peek(4) + 4;
-                s.drop(4);
-                if (nlen > 286 || ndist > 30) break;
-                uint8_t lens[320];
-                memset(lens, 0, 19);
-                bool ok = true;
-                for (int i = 0; i < ncode; ++i) {
-                    if (s.cnt < 3) s.refill();
-                    if (s.cnt < 3) {
-                        ok = false;
-                        break;
-                    }
-                    lens[ORDER[i]] = (uint8_t)s.peek(3);
-                    s.drop(3);
-                }
-                Ent pre[PCAP];
-                if (!ok || !build_table(lens, 19, PRECODE, PBITS, pre, PCAP)) break;
-                int have = 0;
-                const int total = nlen + ndist;
-                while (have < total) {
-                    s.refill();
-                    const Ent e = pre[s.buf & ((1u << PBITS) - 1)];
-                    if (e.op != OP_LIT || e.bits > s.cnt) {
-                        ok = false;
-                        break;
-                    }
-                    const int sym = e.val;
-                    int rep, val;
-                    if (sym < 16) {
-                        s.drop(e.bits);
-                        lens[have++] = (uint8_t)sym;
-                        continue;
-                    }
-                    const int xb = sym == 16 ? 2 : sym == 17 ? 3 : 7;
-                    if (e.bits + xb > s.cnt) {
-                        ok = false;
-                        break;
-                    }
-                    s.drop(e.bits);
-                    if (sym == 16) {
-                        if (have == 0) {
-                            ok = false;
-                            break;
-                        }
-                        val = lens[have - 1];
-                        rep = 3 + s.peek(2);
-                    } else {
-                        val = 0;
-                        rep = sym == 17 ? 3 + s.peek(3) : 11 + s.peek(7);
-                    }
-                    s.drop(xb);
-                    if (have + rep > total) {
-                        ok = false;
-                        break;
-                    }
-                    while (rep--) lens[have++] = (uint8_t)val;
-                }
-                if (!ok || lens[256] == 0) break;            // missing end-of-block code
                 if (!dyn) dyn = new Tables;
-                uint8_t dl[32];
-                memcpy(dl, lens + nlen, ndist);
-                if (!build_table(lens, nlen, LITLEN, LBITS, dyn->lit, LCAP) || !build_table(dl, ndist, DIST, DBITS, dyn->dist, DCAP))
-                    break;
+                if (!read_dynamic_tables(s, dyn)) break;
                 lt = dyn->lit, dt = dyn->dist;
             }
             const int r = decode_block(s, lt, dt, out, o, out_end);
@@ -367,6 +530,271 @@ int inflate_raw(Stream& s, uint8_t* out, size_t out_cap, size_t* out_len, bool* 
     }
     delete dyn;
     *out_len = (size_t)(o - out);
+    return rc;
+}
+
+
+// zlib's adler32_combine: the check value of A followed by B from those of A and B and the length of B
+uint32_t adler32_combine(uint32_t a1, uint32_t a2, size_t len2) {
+    const uint32_t BASE = 65521u;
+    const uint32_t rem = (uint32_t)(len2 % BASE);
+    uint32_t sum1 = a1 & 0xffff;
+    uint32_t sum2 = (uint32_t)(((uint64_t)rem * sum1) % BASE);
+    sum1 += (a2 & 0xffff) + BASE - 1;
+    sum2 += ((a1 >> 16) & 0xffff) + ((a2 >> 16) & 0xffff) + BASE - rem;
+    if (sum1 >= BASE) sum1 -= BASE;
+    if (sum1 >= BASE) sum1 -= BASE;
+    if (sum2 >= (BASE << 1)) sum2 -= (BASE << 1);
+    if (sum2 >= BASE) sum2 -= BASE;
+    return sum1 | (sum2 << 16);
+}
+
+uint32_t adler32(const uint8_t* p, size_t n);
+
+// worker k: find a start, decode until handed over / end of stream / full / failure, then -- once the decoder in front
+// has arrived -- turn the symbols into bytes
+void spec_run(SpecCtl* c, int k) {
+    SpecWorker& w = c->w[k];
+    struct Back {
+        std::vector<uint16_t>& v;
+        ~Back() { sym_pool().give(v); }
+    } back{w.sym};
+    const Fixed& fixed = fixed_tables();
+    Tables* dyn = new Tables;
+    const long long total_bits = (long long)(c->end - c->base) * 8;
+    const long long scan_limit = w.scan_from + (1ll << 21);   // 256 KB of compressed data without a block start: give up
+    // a worker cannot contribute more than the whole output: beyond that the output is full wherever its place is
+    const size_t max_syms = c->out_cap + SYM_ROOM + 1;
+    sym_pool().take(w.sym);
+    {
+        size_t cap = c->out_cap / (size_t)c->n + c->out_cap / 8 + 65536;
+        if (cap > max_syms) cap = max_syms;
+        if (w.sym.size() < cap) w.sym.resize(cap);
+    }
+    auto stop_asked = [&]() { return w.cancel.load(std::memory_order_relaxed) || c->all_done.load(std::memory_order_relaxed); };
+    // room for `need` more symbols behind `have`; false = the output is full before that
+    auto room = [&](size_t have, size_t need) -> bool {
+        if (have + need <= w.sym.size()) return true;
+        if (have + need > max_syms) return false;
+        size_t ncap = have + need + w.sym.size() / 2;
+        w.sym.resize(ncap > max_syms ? max_syms : ncap);
+        return true;
+    };
+    bool decoded_ok = false;
+    for (long long cand = w.scan_from; cand < scan_limit && cand + 64 < total_bits; ++cand) {
+        if ((cand & 1023) == 0 && stop_asked()) break;
+        Stream s;
+        seek_bit(s, c->base, c->end, cand);
+        if (s.cnt < 17 || s.peek(3) != 4) continue;       // BFINAL = 0, BTYPE = 2 (dynamic codes)
+        s.drop(3);
+        if (!read_dynamic_tables(s, dyn)) continue;
+        // a header that parses: decode from here
+        size_t have = 0;
+        bool first = true, fail = false;
+        const Ent *lt = dyn->lit, *dt = dyn->dist;
+        int last = 0, kind = 2;      // the block at hand: 0 = stored (already copied), 1 / 2 = coded with lt / dt
+        w.next = -1, w.finished = false, w.full = false;
+        for (;;) {
+            while (kind != 0) {
+                uint16_t* o = w.sym.data() + have;
+                const int r = decode_block_sym(s, lt, dt, w.sym.data(), o, w.sym.data() + w.sym.size());
+                have = (size_t)(o - w.sym.data());
+                if (r == INF_OK) break;
+                if (r == INF_FULL) {
+                    if (room(have, SYM_ROOM)) continue;
+                    w.full = true;
+                    break;
+                }
+                fail = true;
+                break;
+            }
+            if (fail || w.full) break;
+            if (first) {
+                first = false;
+                w.start_bit.store(cand, std::memory_order_release);
+            }
+            if (last) {
+                w.finished = true;
+                break;
+            }
+            // block boundary
+            if (stop_asked()) {
+                fail = true;
+                break;
+            }
+            s.refill();
+            const int j = spec_handover(c, k, bit_pos(s, c->base));
+            if (j >= 0) {
+                w.next = j;
+                break;
+            }
+            if (s.cnt < 3) {
+                fail = true;
+                break;
+            }
+            last = s.peek(1);
+            s.drop(1);
+            kind = s.peek(2);
+            s.drop(2);
+            if (kind == 0) {
+                s.drop(s.cnt & 7);
+                if (s.cnt < 32) s.refill();
+                if (s.cnt < 32) {
+                    fail = true;
+                    break;
+                }
+                const uint32_t len = s.peek(16);
+                s.drop(16);
+                const uint32_t nlen = s.peek(16);
+                s.drop(16);
+                s.p -= s.cnt >> 3;
+                s.buf = 0, s.cnt = 0;
+                if ((len ^ 0xffffu) != nlen || (size_t)(s.end - s.p) < len) {
+                    fail = true;
+                    break;
+                }
+                size_t take = len;
+                if (!room(have, len)) {
+                    room(have, max_syms - have);
+                    take = w.sym.size() - have;
+                    w.full = true;
+                }
+                uint16_t* o = w.sym.data() + have;
+                for (size_t i = 0; i < take; ++i) o[i] = s.p[i];
+                have += take;
+                s.p += len;
+                if (w.full) break;
+            } else if (kind == 1) {
+                lt = fixed.t.lit, dt = fixed.t.dist;
+            } else if (kind == 2) {
+                if (!read_dynamic_tables(s, dyn)) {
+                    fail = true;
+                    break;
+                }
+                lt = dyn->lit, dt = dyn->dist;
+            } else {
+                fail = true;
+                break;
+            }
+        }
+        if (fail && first) continue;      // not a block start after all (or asked to stop): keep looking / leave
+        w.len = have;
+        w.end_bit = bit_pos(s, c->base);
+        decoded_ok = !fail;               // failed behind a published start: whoever arrives here goes on alone
+        break;
+    }
+    delete dyn;
+    w.ok = decoded_ok;
+    w.decoded.store(1, std::memory_order_release);
+    if (!decoded_ok) {
+        w.resolved.store(1, std::memory_order_release);
+        return;
+    }
+    // wait for the decoder in front to arrive (or for the end of the whole job)
+    while (!w.have_off.load(std::memory_order_acquire)) {
+        if (c->all_done.load(std::memory_order_acquire)) return;
+        std::this_thread::yield();
+    }
+    const size_t off = w.off;
+    size_t n = w.len;
+    w.full = off + n > c->out_cap;         // the stream wants more room than there is: what fits is taken, as the plain decoder does
+    if (w.full) n = c->out_cap - off;
+    if (w.next >= 0 && !w.full) {          // pass the place on at once: the next worker converts its literals meanwhile
+        SpecWorker& nx = c->w[w.next];
+        nx.pred = k;
+        nx.off = off + n;
+        nx.have_off.store(1, std::memory_order_release);
+    }
+    uint8_t* dst = c->out + off;
+    const uint16_t* sy = w.sym.data();
+    std::vector<uint32_t> marks;
+    for (size_t i = 0; i < n; ++i) {
+        const uint16_t v = sy[i];
+        if (v < 256) dst[i] = (uint8_t)v;
+        else marks.push_back((uint32_t)i);
+    }
+    if (!marks.empty()) {
+        // window bytes = the finished output in front: the decoder that arrived here must have made its own bytes final
+        while (w.pred > 0 && !c->w[w.pred].resolved.load(std::memory_order_acquire)) {
+            if (c->all_done.load(std::memory_order_acquire)) return;
+            std::this_thread::yield();
+        }
+        for (uint32_t i : marks) {
+            const long long src = (long long)off - 32768 + (sy[i] & 0x7fff);
+            if (src < 0) {                 // distance too far back
+                w.ok = false;
+                break;
+            }
+            dst[i] = c->out[src];
+        }
+    }
+    if (w.ok) {
+        w.bytes = n;
+        w.adler = adler32(dst, n);
+    }
+    w.resolved.store(1, std::memory_order_release);
+}
+
+// The whole stream with `threads` decoders.  Returns what inflate_raw returns; *adler = check value of the output when
+// *adler_known.  `s` is left behind the last block that was decoded.
+int inflate_mt(Stream& s, uint8_t* out, size_t out_cap, size_t* out_len, bool* finished, std::atomic<size_t>* progress,
+               int threads, uint32_t* adler, bool* adler_known) {
+    *adler_known = false;
+    SpecCtl c;
+    c.base = s.p, c.end = s.end, c.out = out, c.out_cap = out_cap, c.n = threads;
+    std::vector<SpecWorker> workers(threads);
+    c.w = workers.data();
+    const size_t in_len = (size_t)(s.end - s.p);
+    std::vector<std::thread> pool;
+    for (int k = 1; k < threads; ++k) {
+        workers[k].scan_from = (long long)(in_len / threads * k) * 8;
+        pool.emplace_back(spec_run, &c, k);
+    }
+    int handed = -1;
+    size_t len0 = 0;
+    int rc = inflate_raw(s, out, 0, out_cap, &len0, finished, progress, &c, &handed);
+    size_t off = len0;
+    if (rc == INF_HANDED) {
+        uint32_t ad = adler32(out, len0);
+        bool ad_ok = true;
+        int cur = handed;
+        workers[cur].pred = 0;
+        workers[cur].off = off;
+        workers[cur].have_off.store(1, std::memory_order_release);
+        for (;;) {
+            SpecWorker& w = workers[cur];
+            while (!w.resolved.load(std::memory_order_acquire)) std::this_thread::yield();
+            if (!w.ok) {
+                // the worker failed behind its start: the plain decoder goes on from there, with the real window
+                c.all_done.store(1, std::memory_order_release);
+                seek_bit(s, c.base, c.end, w.start_bit.load(std::memory_order_acquire));
+                size_t len1 = 0;
+                rc = inflate_raw(s, out, off, out_cap, &len1, finished, progress);
+                off = len1;
+                ad_ok = false;
+                break;
+            }
+            off += w.bytes;
+            ad = adler32_combine(ad, w.adler, w.bytes);
+            if (progress) progress->store(off, std::memory_order_release);
+            if (w.full) {
+                rc = INF_FULL;
+                ad_ok = false;
+                break;
+            }
+            if (w.finished) {
+                rc = INF_OK;
+                *finished = true;
+                seek_bit(s, c.base, c.end, w.end_bit);
+                break;
+            }
+            cur = w.next;     // (a worker that is ok, not full and not finished has handed over)
+        }
+        if (ad_ok && rc == INF_OK) *adler = ad, *adler_known = true;
+    }
+    c.all_done.store(1, std::memory_order_release);
+    for (auto& t : pool) t.join();
+    *out_len = off;
     return rc;
 }
 
@@ -394,7 +822,7 @@ uint32_t adler32(const uint8_t* p, size_t n) {
 // (optional) is advanced to the number of finished output bytes after every deflate block, so that another thread can
 // ship the front of the output while the rest is still being decoded (bytes below the mark never change again).
 int llfe_inflate_zlib_progress(const uint8_t* in, size_t in_len, uint8_t* out, size_t out_cap, size_t* out_len,
-                               std::atomic<size_t>* progress) {
+                               std::atomic<size_t>* progress, int threads) {
     if (!in || !out || !out_len) {
         llfe_set_error("llfe_inflate_zlib: invalid argument: null pointer");
         return LLFE_E_INVALID;
@@ -407,7 +835,13 @@ int llfe_inflate_zlib_progress(const uint8_t* in, size_t in_len, uint8_t* out, s
     Stream s;
     s.p = in + 2, s.end = in + in_len;
     bool finished = false;
-    const int rc = inflate_raw(s, out, out_cap, out_len, &finished, progress);
+    // several decoders only where the stream is long enough to pay for their start (128 KB of compressed data each)
+    if (threads > 8) threads = 8;
+    while (threads > 1 && in_len / threads < (size_t(128) << 10)) --threads;
+    uint32_t adler_mt = 1;
+    bool adler_known = false;
+    const int rc = threads > 1 ? inflate_mt(s, out, out_cap, out_len, &finished, progress, threads, &adler_mt, &adler_known)
+                               : inflate_raw(s, out, 0, out_cap, out_len, &finished, progress);
     if (rc == INF_ERR) {
         llfe_set_error("llfe_inflate_zlib: invalid or truncated deflate stream");
         return LLFE_E_INVALID;
@@ -420,7 +854,7 @@ int llfe_inflate_zlib_progress(const uint8_t* in, size_t in_len, uint8_t* out, s
             return LLFE_E_INVALID;
         }
         const uint32_t want = ((uint32_t)s.p[0] << 24) | ((uint32_t)s.p[1] << 16) | ((uint32_t)s.p[2] << 8) | s.p[3];
-        if (adler32(out, *out_len) != want) {
+        if ((adler_known ? adler_mt : adler32(out, *out_len)) != want) {
             llfe_set_error("llfe_inflate_zlib: incorrect data check");
             return LLFE_E_INVALID;
         }
@@ -430,5 +864,9 @@ int llfe_inflate_zlib_progress(const uint8_t* in, size_t in_len, uint8_t* out, s
 }
 
 extern "C" int llfe_inflate_zlib(const uint8_t* in, size_t in_len, uint8_t* out, size_t out_cap, size_t* out_len) {
-    return llfe_inflate_zlib_progress(in, in_len, out, out_cap, out_len, nullptr);
+    return llfe_inflate_zlib_progress(in, in_len, out, out_cap, out_len, nullptr, 1);
+}
+
+extern "C" int llfe_inflate_zlib_mt(const uint8_t* in, size_t in_len, uint8_t* out, size_t out_cap, size_t* out_len, int threads) {
+    return llfe_inflate_zlib_progress(in, in_len, out, out_cap, out_len, nullptr, threads < 1 ? 1 : threads);
 }

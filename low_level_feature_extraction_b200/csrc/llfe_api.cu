@@ -204,6 +204,7 @@ int llfe_set_option(llfe_ctx* ctx, const char* name, int64_t value) {
     else if (!strcmp(name, "hyst_strips")) ctx->opt_hyst_strips = value != 0;
     else if (!strcmp(name, "shadow_inline")) ctx->opt_shadow_inline = value != 0;
     else if (!strcmp(name, "serial")) ctx->opt_serial = value != 0;
+    else if (!strcmp(name, "inflate_threads")) ctx->opt_inflate_threads = (value >= 1 && value <= 8) ? (int)value : 4;
     else if (!strcmp(name, "contour_segments")) ctx->opt_contour_segments = (value >= 0 && value <= 2) ? (int)value : 1;
     else if (!strcmp(name, "contour_cut_shift")) ctx->opt_contour_cut_shift = (value >= 0 && value <= 8) ? (int)value : 6;
     else if (!strcmp(name, "shadow_variant")) ctx->shadow_variant = (int)value;
@@ -981,7 +982,7 @@ int llfe_png_decode_host(llfe_ctx* ctx, const uint8_t* h_idat, size_t idat_bytes
         std::atomic<size_t> progress{0};
         std::atomic<int> done{0};
         std::thread worker([&] {
-            inf_rc = llfe_inflate_zlib_progress(h_idat, idat_bytes, p_in, in, &got, &progress);
+            inf_rc = llfe_inflate_zlib_progress(h_idat, idat_bytes, p_in, in, &got, &progress, ctx->opt_inflate_threads);
             done.store(1, std::memory_order_release);
         });
         int rc = LLFE_OK;
@@ -1005,7 +1006,7 @@ int llfe_png_decode_host(llfe_ctx* ctx, const uint8_t* h_idat, size_t idat_bytes
             return rc;
         }
     } else {
-        inf_rc = llfe_inflate_zlib_progress(h_idat, idat_bytes, p_in, in, &got, nullptr);
+        inf_rc = llfe_inflate_zlib_progress(h_idat, idat_bytes, p_in, in, &got, nullptr, ctx->opt_inflate_threads);
         if (inf_rc == LLFE_OK && got == in) {
             LLFE_CUDA(cudaMemcpyAsync(d_in, p_in, in, cudaMemcpyHostToDevice, ctx->stream));
             LLFE_TRY(launch_png_unfilter_rows(ctx, d_in, 1, h, 0, h, rowbytes, bpp, d_status));
@@ -1057,7 +1058,7 @@ int llfe_png_decode_adam7_host(llfe_ctx* ctx, const uint8_t* h_idat, size_t idat
     uint8_t* d_out = d_in + a;
     int32_t* d_status = (int32_t*)(d_out + WsCarver::need(out));
     size_t got = 0;
-    if (llfe_inflate_zlib(h_idat, idat_bytes, p_in, in, &got) != LLFE_OK || got != in) {
+    if (llfe_inflate_zlib_progress(h_idat, idat_bytes, p_in, in, &got, nullptr, ctx->opt_inflate_threads) != LLFE_OK || got != in) {
         llfe_set_error("llfe_png_decode_adam7_host: invalid, truncated or short deflate stream");
         return LLFE_E_INVALID;
     }

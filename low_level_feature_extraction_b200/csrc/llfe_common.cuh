@@ -50,6 +50,7 @@ struct llfe_ctx {
     bool prof_on = false;
     // llfe_set_option: path toggles used by the parity tests (both off in production)
     bool opt_unfused = false;      // per-stage kernels instead of the fused front kernel
+    int opt_inflate_threads = 4;        // llfe_set_option("inflate_threads", 1..8): decoders per deflate stream in llfe_png_decode*_host
     int opt_contour_cut_shift = 6;      // llfe_set_option("contour_cut_shift", 0..8): log2 of the rows between cut rows (tests)
     // llfe_set_option("contour_segments", v): 0 = every border followed by one thread, 1 = long borders cut into segments
     // in calls on one or two images (default), 2 = in batches as well (passes sized to 2 GB of segment tables)
@@ -84,9 +85,10 @@ static inline bool llfe_first_use(llfe_ctx* ctx, const void* kernel) {
 }
 
 void llfe_set_error(const char* fmt, ...);
-// h_inflate.cu: llfe_inflate_zlib with a progress mark another thread may read (bytes below it are final)
+// h_inflate.cu: llfe_inflate_zlib with a progress mark another thread may read (bytes below it are final) and `threads`
+// decoders on the one stream (speculative block starts, see there)
 int llfe_inflate_zlib_progress(const uint8_t* in, size_t in_len, uint8_t* out, size_t out_cap, size_t* out_len,
-                               std::atomic<size_t>* progress);
+                               std::atomic<size_t>* progress, int threads);
 int llfe_cuda_fail(cudaError_t e, const char* what, const char* file, int line);
 
 #define LLFE_CUDA(call)                                                       \

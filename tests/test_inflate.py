@@ -109,3 +109,90 @@ def test_damaged_streams_are_rejected_like_zlib(lib):
             assert not ref_ok or rc != 0, trial
         agree += ok == ref_ok
     assert agree >= 2990    # (a corrupted trailer is seen by this inflate, not by a capped zlib call)
+
+
+# ---- several decoders on one stream (llfe_inflate_zlib_mt: speculative block starts) ---------------------------------------
+def inflate_mt(lib, data: bytes, cap: int, threads: int):
+    out = C.create_string_buffer(max(cap, 1))
+    got = C.c_size_t(0)
+    rc = lib.llfe_inflate_zlib_mt(data, len(data), out, cap, C.byref(got), threads)
+    return rc, out.raw[:got.value]
+
+
+def big_payloads():
+    """megabytes of output, so that every decoder gets more than 128 KB of compressed data"""
+    rng = np.random.default_rng(7)
+    from low_level_feature_extraction_b200.synth import design_image
+
+    img = design_image(540, 960, 2)
+    yield "design rows", img.tobytes()
+    yield "sub-filtered rows", np.diff(img.astype(np.int16), axis=1, prepend=0).astype(np.uint8).tobytes()
+    yield "noise", rng.integers(0, 256, 1_500_000, dtype=np.uint8).tobytes()           # incompressible: stored blocks
+    yield "four symbols", rng.integers(0, 4, 6_000_000, dtype=np.uint8).tobytes()
+    walk = (np.cumsum(rng.integers(-1, 2, 3_000_000)) & 255).astype(np.uint8)
+    yield "random walk", walk.tobytes()
+    # long matches whose sources lie far back, across the places where the workers start (window symbols are copied on)
+    block = rng.integers(0, 256, 30000, dtype=np.uint8).tobytes()
+    yield "repeats at distance 30000", b"".join(block[:int(k)] + bytes([i & 255]) for i, k in enumerate(rng.integers(20000, 30000, 120)))
+    yield "mixed", img.tobytes()[:700000] + rng.integers(0, 256, 400000, dtype=np.uint8).tobytes() + walk.tobytes()[:900000] + b"\0" * 500000
+
+
+@pytest.mark.parametrize("threads", [2, 3, 4, 8])
+def test_mt_equals_zlib(lib, threads):
+    for name, data in big_payloads():
+        for level, strategy in ((1, zlib.Z_DEFAULT_STRATEGY), (6, zlib.Z_DEFAULT_STRATEGY), (6, zlib.Z_FILTERED), (3, zlib.Z_RLE),
+                                (6, zlib.Z_HUFFMAN_ONLY), (6, zlib.Z_FIXED), (0, zlib.Z_DEFAULT_STRATEGY)):
+            c = zlib.compressobj(level, zlib.DEFLATED, 15, 8, strategy)
+            z = c.compress(data) + c.flush()
+            rc, out = inflate_mt(lib, z, len(data), threads)
+            assert rc == 0 and out == data, (name, level, strategy, threads)
+
+
+def test_mt_full_flushes_small_blocks_and_caps(lib):
+    rng = np.random.default_rng(8)
+    data = (np.cumsum(rng.integers(-2, 3, 2_500_000)) & 255).astype(np.uint8).tobytes()
+    # many tiny blocks, sync / full flushes (empty stored blocks) in the stream
+    c = zlib.compressobj(6, zlib.DEFLATED, 15, 1)
+    z = b""
+    for i in range(0, len(data), 50000):
+        z += c.compress(data[i:i + 50000]) + c.flush(zlib.Z_SYNC_FLUSH if (i // 50000) % 3 else zlib.Z_FULL_FLUSH)
+    z += c.flush()
+    assert len(z) > 600000
+    for threads in (2, 4, 7):
+        rc, out = inflate_mt(lib, z, len(data), threads)
+        assert rc == 0 and out == data
+        # output capped anywhere: what fits, no error (libpng: too much image data), exactly as the one-decoder call
+        for cap in (0, 1, 1000, len(data) // 4, len(data) // 2 + 17, len(data) - 1, len(data) + 99):
+            rc, out = inflate_mt(lib, z, cap, threads)
+            rc1, out1 = inflate(lib, z, cap)
+            assert (rc, out) == (rc1, out1) and out == data[:cap], (threads, cap)
+
+
+def test_mt_damaged_streams_agree_with_the_single_decoder(lib):
+    """whatever several decoders return -- result code and bytes -- is what one decoder returns: truncations, flipped
+    bits anywhere (before, at and behind the places the workers start from), a damaged check value"""
+    rng = np.random.default_rng(9)
+    from low_level_feature_extraction_b200.synth import design_image
+
+    data = design_image(400, 700, 4).tobytes() + rng.integers(0, 8, 900000, dtype=np.uint8).tobytes()
+    z = zlib.compress(data, 6)
+    assert len(z) > 500000
+    cases = [z[:k] for k in (len(z) - 1, len(z) - 4, len(z) - 5, len(z) // 2, len(z) // 4 * 3 + 1, 300000)]
+    bad = bytearray(z)
+    bad[-1] ^= 1
+    cases.append(bytes(bad))
+    for _ in range(120):
+        b = bytearray(z)
+        for _ in range(int(rng.integers(1, 3))):
+            b[int(rng.integers(2, len(b)))] ^= 1 << int(rng.integers(0, 8))
+        cases.append(bytes(b))
+    accepted = 0
+    for k, zz in enumerate(cases):
+        rc1, out1 = inflate(lib, zz, len(data))
+        for threads in (2, 4):
+            rc, out = inflate_mt(lib, zz, len(data), threads)
+            assert rc == rc1, (k, threads)
+            if rc == 0:
+                assert out == out1, (k, threads)
+        accepted += rc1 == 0
+    assert accepted < len(cases)
