@@ -67,7 +67,9 @@ int llfe_sync(llfe_ctx* ctx);
  * "serial" = 1 one stream for the two chains of llfe_pipeline / llfe_analyze, "contour_segments" = 0 follows every
  * border of llfe_contours_external with one thread (default 1: calls on one or two images cut long borders into
  * segments that are followed in parallel), "contour_cut_shift" = log2 of the rows / columns between the cuts
- * (default 6; tests use 0..3), "chunk" = images per front-kernel launch.  Unknown names fail with LLFE_E_INVALID. */
+ * (default 6; tests use 0..3), "chunk" = images per front-kernel launch, "inflate_threads" = decoders per deflate stream
+ * in llfe_png_decode_host / llfe_png_decode_adam7_host (1..8, default 4; see llfe_inflate_zlib_mt).  Unknown names fail
+ * with LLFE_E_INVALID. */
 int llfe_set_option(llfe_ctx* ctx, const char* name, int64_t value);
 /* Register a device buffer the "kmeans" / "hysteresis" kernels write per-CTA phase clocks to (tools/debug/);
  * d_buf = NULL switches the records off.  The pointer is validated with cudaPointerGetAttributes (device
