@@ -253,7 +253,6 @@ struct SpecWorker {
     long long scan_from = 0;                   // first bit (relative to the deflate data) this worker may start at
     std::atomic<long long> start_bit{-1};      // published once the first block from there has decoded
     std::atomic<int> cancel{0};
-    std::atomic<int> decoded{0};               // 1 = stopped decoding (handed over, end of stream, full, or failed)
     std::atomic<int> have_off{0};              // the decoder in front has arrived: `off` is this worker's place in the output
     std::atomic<int> resolved{0};              // 1 = bytes final (or failed: see ok)
     size_t off = 0;
@@ -685,7 +684,6 @@ void spec_run(SpecCtl* c, int k) {
     }
     delete dyn;
     w.ok = decoded_ok;
-    w.decoded.store(1, std::memory_order_release);
     if (!decoded_ok) {
         w.resolved.store(1, std::memory_order_release);
         return;
