@@ -196,3 +196,20 @@ def test_mt_damaged_streams_agree_with_the_single_decoder(lib):
                 assert out == out1, (k, threads)
         accepted += rc1 == 0
     assert accepted < len(cases)
+
+
+def test_mt_concurrent_calls(lib):
+    """several callers at once (ctypes releases the GIL): the workers of one call never touch another call's state"""
+    from concurrent.futures import ThreadPoolExecutor
+
+    rng = np.random.default_rng(10)
+    datas = [(np.cumsum(rng.integers(-2, 3, 1_200_000 + 100_000 * k)) & 255).astype(np.uint8).tobytes() for k in range(4)]
+    zs = [zlib.compress(d, 6) for d in datas]
+
+    def job(i):
+        k = i % 4
+        rc, out = inflate_mt(lib, zs[k], len(datas[k]), 2 + i % 3)
+        return rc == 0 and out == datas[k]
+
+    with ThreadPoolExecutor(max_workers=4) as ex:
+        assert all(ex.map(job, range(24)))
