@@ -313,13 +313,15 @@ inline void seek_bit(Stream& s, const uint8_t* base, const uint8_t* end, long lo
 
 // at a block boundary of decoder `self`: the worker that starts exactly here, or -1.  Workers whose start (or whose
 // whole search range) lies behind are cancelled: nobody can arrive at them any more.
-int spec_handover(SpecCtl* c, int self, long long bit) {
+// Only a decoder whose own position is proven (the plain decoder at the front, a worker that has been arrived at) may
+// cancel: a worker on a false start decodes garbage and must not take real workers down with it.
+int spec_handover(SpecCtl* c, int self, long long bit, bool may_cancel) {
     for (int j = self + 1; j < c->n; ++j) {
         SpecWorker& w = c->w[j];
         if (w.cancel.load(std::memory_order_relaxed)) continue;
         const long long st = w.start_bit.load(std::memory_order_acquire);
         if (st == bit) return j;
-        if (st >= 0 ? st < bit : w.scan_from < bit) w.cancel.store(1, std::memory_order_release);
+        if (may_cancel && (st >= 0 ? st < bit : w.scan_from < bit)) w.cancel.store(1, std::memory_order_release);
     }
     return -1;
 }
@@ -469,7 +471,7 @@ int inflate_raw(Stream& s, uint8_t* out, size_t start_off, size_t out_cap, size_
     for (;;) {
         s.refill();
         if (ctl) {
-            const int j = spec_handover(ctl, 0, bit_pos(s, ctl->base));
+            const int j = spec_handover(ctl, 0, bit_pos(s, ctl->base), true);
             if (j >= 0) {
                 *handed_to = j;
                 rc = INF_HANDED;
@@ -607,12 +609,22 @@ void spec_run(SpecCtl* c, int k) {
                 fail = true;
                 break;
             }
-            if (fail || w.full) break;
-            if (first) {
-                first = false;
-                w.start_bit.store(cand, std::memory_order_release);
+            if (fail) break;
+            if (w.full) {
+                if (first) fail = true;      // (full inside an unproven first block: not worth publishing)
+                break;
             }
+            // The start is published -- once, for good -- when the block behind the first one has a header that parses
+            // too (or the stream ends / another worker's start is reached there): a false start may survive one block
+            // of garbage, hardly two.
+            auto publish = [&]() {
+                if (first) {
+                    first = false;
+                    w.start_bit.store(cand, std::memory_order_release);
+                }
+            };
             if (last) {
+                publish();
                 w.finished = true;
                 break;
             }
@@ -622,8 +634,9 @@ void spec_run(SpecCtl* c, int k) {
                 break;
             }
             s.refill();
-            const int j = spec_handover(c, k, bit_pos(s, c->base));
+            const int j = spec_handover(c, k, bit_pos(s, c->base), w.have_off.load(std::memory_order_acquire) != 0);
             if (j >= 0) {
+                publish();
                 w.next = j;
                 break;
             }
@@ -662,7 +675,10 @@ void spec_run(SpecCtl* c, int k) {
                 for (size_t i = 0; i < take; ++i) o[i] = s.p[i];
                 have += take;
                 s.p += len;
-                if (w.full) break;
+                if (w.full) {
+                    publish();
+                    break;
+                }
             } else if (kind == 1) {
                 lt = fixed.t.lit, dt = fixed.t.dist;
             } else if (kind == 2) {
@@ -675,6 +691,7 @@ void spec_run(SpecCtl* c, int k) {
                 fail = true;
                 break;
             }
+            publish();
         }
         if (fail && first) continue;      // not a block start after all (or asked to stop): keep looking / leave
         w.len = have;
