@@ -213,3 +213,32 @@ def test_mt_concurrent_calls(lib):
 
     with ThreadPoolExecutor(max_workers=4) as ex:
         assert all(ex.map(job, range(24)))
+
+
+def test_mt_false_block_starts(lib):
+    """deflate streams stored inside a deflate stream: the workers find block headers that parse -- and blocks that
+    decode, up to a final block -- in what is only payload; nobody ever arrives at such a start, so the result is that
+    of the one-decoder call"""
+    rng = np.random.default_rng(11)
+    inner = b"".join(zlib.compress((np.cumsum(rng.integers(-2, 3, 400_000)) & 255).astype(np.uint8).tobytes(), 6) for _ in range(6))
+    assert len(inner) > 1_000_000
+    for outer_level in (0, 1, 6):
+        z = zlib.compress(inner, outer_level)
+        for threads in (2, 4, 8):
+            rc, out = inflate_mt(lib, z, len(inner), threads)
+            assert rc == 0 and out == inner, (outer_level, threads)
+    # the same with real blocks in front and behind (the plain decoder hands over before and after the stored part)
+    walk = (np.cumsum(rng.integers(-2, 3, 2_000_000)) & 255).astype(np.uint8).tobytes()
+    c = zlib.compressobj(6)
+    z = c.compress(walk) + c.flush(zlib.Z_FULL_FLUSH)
+    c0 = zlib.compressobj(0)
+    mid = c0.compress(inner) + c0.flush(zlib.Z_FULL_FLUSH)
+    # (splice the raw deflate data: a zlib header, compressed blocks, stored blocks, compressed blocks, the final block)
+    tail = zlib.compressobj(6, zlib.DEFLATED, -15)
+    raw = z[2:] + mid[2:] + tail.compress(walk[::-1]) + tail.flush()
+    data = walk + inner + walk[::-1]
+    full = z[:2] + raw + zlib.adler32(data).to_bytes(4, "big")
+    assert zlib.decompress(full) == data
+    for threads in (2, 3, 4, 8):
+        rc, out = inflate_mt(lib, full, len(data), threads)
+        assert rc == 0 and out == data, threads
