@@ -89,7 +89,7 @@ def parse_args():
     ap.add_argument("--e2e-steps", type=int, default=6)
     ap.add_argument("--e2e-tail", choices=["thread", "inline"], default="thread",
                     help="host palette tail of e2e: on a worker thread under the next step's copies, or inline")
-    ap.add_argument("--no-extras", action="store_true", help="skip the extra records (BASELINE configs 2, 3, literal 4, 5, contours, adversarial frames)")
+    ap.add_argument("--no-extras", action="store_true", help="skip the extra records (BASELINE configs 1, 2, 3, literal 4, 5, contours, adversarial frames)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--cpu-seconds", type=float, default=10.0, help="target CPU time of the cpu_baseline sample")
@@ -473,6 +473,21 @@ def contours_record(local, dev, rank, B, H, W):
     return rec
 
 
+def config1_record():
+    """BASELINE config 1, the reference's own CPU-runnable case: ONE 1080p PNG through the drop-in service calls
+    (validate_and_preprocess_image = PNG decode + resize policy, extract_colors, analyze_shapes, analyze_shadow_level),
+    single-image latency next to the reference's call sequence on the host cores (the port, like `cpu_baseline`).
+    Runs `tools/service_latency.py` in a child process: the services keep a library context of their own."""
+    r = subprocess.run([sys.executable, os.path.join(ROOT, "tools", "service_latency.py"), "--reps", "5"],
+                       capture_output=True, text=True, timeout=150, cwd=ROOT)
+    if r.returncode != 0:
+        raise RuntimeError(r.stderr.strip()[-300:])
+    d = json.loads(r.stdout.strip().splitlines()[-1])
+    return {"workload": "config 1: " + d["image"] + ", one image at a time through the drop-in services", "unit": d["unit"],
+            "ours_gpu": d["ours_gpu"], "reference_cpu_port": d["reference_cpu_port"], "host_threads_cv2": d["host_threads_cv2"],
+            "images_per_sec_decode_plus_palette": d["config1_images_per_sec"]}
+
+
 def pixel_kmeans_record(rank, world, local, dev, height, width, k, synth="design"):
     """BASELINE config 5: ONE height x width image, rows sharded over the ranks (strong scaling), per-pixel k-means with
     exact integer sums; the colour count table crosses NVLink once (reduce-scatter), the K x 4 sums every iteration."""
@@ -626,6 +641,7 @@ def run_ours(args):
                 args, "pipeline", 4, 1080, 1920, 5, 1, 1, rank, world, local, dev, 4, kind="noise"))
         if world == 1:
             guarded("contours_256x1080p", lambda: contours_record(local, dev, rank, 256, 1080, 1920))
+            guarded("config1_single_image_services_1080p", config1_record)
         guarded("config5_pixel_kmeans_16384x16384_k16", lambda: pixel_kmeans_record(
             rank, world, local, dev, 16384, 16384, 16))
         guarded("config5_pixel_kmeans_photo_like", lambda: pixel_kmeans_record(
