@@ -761,9 +761,14 @@ int inflate_mt(Stream& s, uint8_t* out, size_t out_cap, size_t* out_len, bool* f
     c.w = workers.data();
     const size_t in_len = (size_t)(s.end - s.p);
     std::vector<std::thread> pool;
+    for (int k = 1; k < threads; ++k) workers[k].scan_from = (long long)(in_len / threads * k) * 8;
     for (int k = 1; k < threads; ++k) {
-        workers[k].scan_from = (long long)(in_len / threads * k) * 8;
-        pool.emplace_back(spec_run, &c, k);
+        try {
+            pool.emplace_back(spec_run, &c, k);
+        } catch (...) {      // no more threads to be had: the workers that did start (and the plain decoder) do the job
+            for (int j = k; j < threads; ++j) workers[j].cancel.store(1, std::memory_order_release);
+            break;
+        }
     }
     int handed = -1;
     size_t len0 = 0;
